@@ -1,0 +1,97 @@
+# bnet build: host engine (g++) + sm_100a kernels (nvcc) -> libnccl-net.so
+#
+#   make            build the plugin / runtime library into bagua_net_b200/lib/
+#   make test       C++ unit + loopback tests (no GPU needed)
+#   make bench      native benchmarks (all_reduce_perf clone, p2p_bw)
+#   make sass       SASS / PTX / resource listings of every kernel -> docs/sass/
+#   make tar        release tarball like the reference's `make tar`
+#
+# Counterpart of the reference build (reference: cc/Makefile:1-26): same product
+# name — NCCL dlopen()s libnccl-net.so from LD_LIBRARY_PATH — but no cargo step.
+
+CUDA_HOME ?= /usr/local/cuda
+NVCC      := $(CUDA_HOME)/bin/nvcc
+CXX       ?= g++
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+OUT       := bagua_net_b200/lib
+BUILD     := build
+
+CXXFLAGS  := -O2 -g -fPIC -std=c++17 -Wall -Wno-invalid-offsetof -fvisibility=hidden -pthread \
+             -Iinclude -Icsrc -I$(CUDA_HOME)/include
+NVCCFLAGS := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC,-fvisibility=hidden,-Wno-invalid-offsetof \
+             -Iinclude -Icsrc --expt-relaxed-constexpr
+LDFLAGS   := -shared -cudart static -Xcompiler -pthread -ldl -lrt
+
+HOST_SRCS := csrc/core/common.cc csrc/core/netif.cc csrc/core/telemetry.cc csrc/core/engine.cc \
+             csrc/transport/tcp_threads.cc csrc/transport/tcp_async.cc csrc/transport/nvl.cc \
+             csrc/cuda/cuda_iface.cc csrc/capi.cc
+CU_SRCS   := $(wildcard csrc/cuda/*.cu)
+
+HOST_OBJS := $(patsubst csrc/%.cc,$(BUILD)/%.o,$(HOST_SRCS))
+CU_OBJS   := $(patsubst csrc/%.cu,$(BUILD)/%.cu.o,$(CU_SRCS))
+PLUGIN_OBJ  := $(BUILD)/plugin/plugin.o
+PLUGINX_OBJ := $(BUILD)/plugin/plugin_x.o
+
+PLUGIN_SO  := $(OUT)/libnccl-net.so
+PLUGINX_SO := $(OUT)/libnccl-net-bnetx.so
+ALIAS_SO   := $(OUT)/libnccl-net-bnet.so
+
+default: $(PLUGIN_SO) $(PLUGINX_SO) $(ALIAS_SO)
+
+$(BUILD)/%.o: csrc/%.cc
+	@mkdir -p $(dir $@)
+	$(CXX) $(CXXFLAGS) -MMD -MP -c $< -o $@
+
+$(BUILD)/%.cu.o: csrc/%.cu
+	@mkdir -p $(dir $@)
+	$(NVCC) $(NVCCFLAGS) -MMD -MP -c $< -o $@
+
+$(PLUGINX_OBJ): csrc/plugin/plugin.cc
+	@mkdir -p $(dir $@)
+	$(CXX) $(CXXFLAGS) -DBNET_EXPORT_V9_V10 -c $< -o $@
+
+$(PLUGIN_SO): $(HOST_OBJS) $(CU_OBJS) $(PLUGIN_OBJ)
+	@mkdir -p $(OUT)
+	$(NVCC) $(ARCH) $(LDFLAGS) -o $@ $^
+
+# same engine, additionally exports the v9/v10 tables (select with NCCL_NET_PLUGIN=bnetx)
+$(PLUGINX_SO): $(HOST_OBJS) $(CU_OBJS) $(PLUGINX_OBJ)
+	@mkdir -p $(OUT)
+	$(NVCC) $(ARCH) $(LDFLAGS) -o $@ $^
+
+# NCCL_NET_PLUGIN=bnet  ->  libnccl-net-bnet.so
+$(ALIAS_SO): $(PLUGIN_SO)
+	cp -f $< $@
+
+TEST_BINS := $(BUILD)/tests/unit_tests $(BUILD)/tests/loopback_test
+$(BUILD)/tests/%: csrc/tests/%.cc $(PLUGIN_SO)
+	@mkdir -p $(dir $@)
+	$(CXX) $(CXXFLAGS) -fvisibility=default $< -o $@ -ldl -pthread
+
+test: $(TEST_BINS)
+	$(BUILD)/tests/unit_tests $(PLUGIN_SO)
+	$(BUILD)/tests/loopback_test $(PLUGIN_SO)
+
+BENCH_BINS := $(BUILD)/bench/all_reduce_perf $(BUILD)/bench/p2p_bw
+NCCL_HOME ?= $(shell python -c "import nvidia.nccl, os; print(os.path.dirname(nvidia.nccl.__file__))" 2>/dev/null)
+$(BUILD)/bench/%: bench/%.cu $(PLUGIN_SO)
+	@mkdir -p $(dir $@)
+	$(NVCC) -O3 -std=c++17 $(ARCH) -lineinfo -Iinclude -Icsrc -I$(NCCL_HOME)/include $< -o $@ \
+	    -L$(NCCL_HOME)/lib -l:libnccl.so.2 -Xlinker -rpath=$(NCCL_HOME)/lib -ldl -lpthread -lrt
+
+bench: $(BENCH_BINS)
+
+sass: $(PLUGIN_SO)
+	@mkdir -p docs/sass
+	for f in $(CU_SRCS); do b=$$(basename $$f .cu); \
+	  $(NVCC) $(NVCCFLAGS) -Xptxas -v -cubin $$f -o $(BUILD)/$$b.cubin 2> docs/sass/$$b.ptxas.txt; \
+	  $(CUDA_HOME)/bin/cuobjdump -sass $(BUILD)/$$b.cubin > docs/sass/$$b.sass; done
+
+tar: default
+	tar czf bagua-net-b200_x86_64.tar.gz -C $(OUT) libnccl-net.so libnccl-net-bnet.so libnccl-net-bnetx.so
+
+clean:
+	rm -rf $(BUILD) $(OUT)/*.so
+
+-include $(HOST_OBJS:.o=.d) $(CU_OBJS:.o=.d)
+.PHONY: default test bench sass tar clean

@@ -1,0 +1,616 @@
+// sm_100a copy/reduce executor behind the NVLink transport's isend (K1, K4, K5, K7,
+// K8 of SURVEY.md §2.6).
+//
+// One "device stream" = one thread-block cluster running a semi-persistent kernel
+// that pulls work descriptors from a ring in pinned host memory — the device-side
+// analogue of the reference's per-TCP-stream worker thread + channel
+// (reference: nthread_…:336-361).  The host dispatcher splits a message into
+// max(ceil(n/nclusters), MIN_CHUNKSIZE)-byte chunks and deals them round-robin to
+// the clusters, cursor persisting across messages (reference: nthread_…:393-413).
+//
+// Inside a cluster: the leader CTA polls the ring (ld.acquire.sys on host memory),
+// broadcasts the descriptor through distributed shared memory, all CTAs move their
+// share with 16-byte vector loads/stores (or a TMA bulk-copy pipeline, UBLKCP,
+// when BNET_COPY_ENGINE=tma) straight into the peer GPU's buffer over NVLink,
+// optionally fused with an accumulate (red.global.add) or a bf16<->fp32 cast, then
+// a cluster barrier, a system-scope fence and a release store of the chunk's
+// completion word (pinned host memory, polled by test()).
+//
+// The kernel parks with nanosleep back-off while idle and leaves after
+// BNET_KERNEL_IDLE_US without work so that cudaDeviceSynchronize()/cudaFree() in
+// the application never wait on us for long; the host relaunches on demand with a
+// Dekker-style handshake on the queue's state word.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+
+#include "core/common.h"
+#include "cuda/cuda_iface.h"
+#include "cuda/nvl_exec.h"
+#include "cuda/ptx.cuh"
+
+namespace bnet {
+namespace cuda {
+
+enum ExecOp : uint32_t {
+  OP_COPY = 0,
+  OP_RED_ADD_F32 = 1,      // dst(f32) += src(f32)           (K4: accumulate while moving)
+  OP_RED_ADD_BF16 = 2,     // dst(bf16) += src(bf16)
+  OP_CAST_BF16_TO_F32 = 3, // dst(f32) = src(bf16)           (K5)
+  OP_CAST_F32_TO_BF16 = 4, // dst(bf16) = src(f32)
+  OP_FLUSH = 5,            // K7: fence only
+  OP_ACC_BF16_TO_F32 = 6,  // dst(f32) += src(bf16)          (K4+K5 fused)
+};
+
+constexpr int kQueueDepth = 64;
+constexpr int kThreads = 512;
+constexpr uint32_t ST_EXITED = 0, ST_RUNNING = 1, ST_EXITING = 2;
+
+struct alignas(64) Desc {
+  uint64_t seq;        // == index+1 when valid (written last, release)
+  const void* src;
+  void* dst;
+  uint64_t nbytes;     // bytes of SOURCE to process
+  uint64_t* flag;      // device-visible completion word (pinned host memory)
+  uint64_t flag_val;
+  uint32_t op;
+  uint32_t pad;
+};
+
+struct ClusterQ {
+  alignas(64) volatile uint64_t tail;    // host: descriptors published
+  alignas(64) volatile uint64_t head;    // device: descriptors completed
+  alignas(64) volatile uint32_t state;   // ST_*
+  alignas(64) volatile uint32_t stop;    // host asks the kernel to leave
+  alignas(64) volatile uint64_t err;     // device reports a watchdog trip
+  alignas(64) Desc d[kQueueDepth];
+};
+
+// ------------------------------------------------------------------ device code
+struct SmemDesc {
+  const char* src;
+  char* dst;
+  uint64_t nbytes;
+  uint32_t op;
+  uint32_t quit;
+};
+
+template <int UNROLL>
+__device__ __forceinline__ void copy_vec16(const char* __restrict__ src, char* __restrict__ dst, size_t nvec,
+                                           int tid, int nthreads) {
+  const int4* s = reinterpret_cast<const int4*>(src);
+  int4* d = reinterpret_cast<int4*>(dst);
+  size_t i = tid;
+  const size_t stride = (size_t)nthreads;
+  for (; i + (UNROLL - 1) * stride < nvec; i += UNROLL * stride) {
+    int4 v[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++) v[u] = ptx::ld_na_v4(s + i + u * stride);   // all loads first (MLP)
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++) ptx::st_na_v4(d + i + u * stride, v[u]);
+  }
+  for (; i < nvec; i += stride) ptx::st_na_v4(d + i, ptx::ld_na_v4(s + i));
+}
+
+// Moves/reduces [0,n) source bytes for one CTA's share.  tid/nthreads are CTA-local.
+__device__ void process_range(uint32_t op, const char* src, char* dst, size_t n, int tid, int nthreads) {
+  if (n == 0) return;
+  if (op == OP_COPY) {
+    // align the destination, then go wide if the source agrees
+    size_t head = (16 - ((uintptr_t)dst & 15)) & 15;
+    if (head > n) head = n;
+    for (size_t i = tid; i < head; i += nthreads) dst[i] = src[i];
+    src += head; dst += head; n -= head;
+    if (((uintptr_t)src & 15) == 0) {
+      size_t nvec = n >> 4;
+      copy_vec16<8>(src, dst, nvec, tid, nthreads);
+      size_t done = nvec << 4;
+      for (size_t i = done + tid; i < n; i += nthreads) dst[i] = src[i];
+    } else if ((((uintptr_t)src ^ (uintptr_t)dst) & 3) == 0) {
+      size_t n4 = n >> 2;
+      const uint32_t* s4 = (const uint32_t*)src;
+      uint32_t* d4 = (uint32_t*)dst;
+      for (size_t i = tid; i < n4; i += nthreads) d4[i] = s4[i];
+      for (size_t i = (n4 << 2) + tid; i < n; i += nthreads) dst[i] = src[i];
+    } else {
+      for (size_t i = tid; i < n; i += nthreads) dst[i] = src[i];
+    }
+    return;
+  }
+  if (op == OP_RED_ADD_F32) {
+    size_t ne = n >> 2;
+    const float* s = (const float*)src;
+    float* d = (float*)dst;
+    if ((((uintptr_t)s | (uintptr_t)d) & 15) == 0) {
+      size_t nv = ne >> 2;
+      for (size_t i = tid; i < nv; i += nthreads) {
+        float4 v = ptx::ld_na_f4(reinterpret_cast<const float4*>(s) + i);
+        ptx::red_add_v4_f32(d + 4 * i, v);      // one 16-byte reduction packet over NVLink
+      }
+      for (size_t i = (nv << 2) + tid; i < ne; i += nthreads) ptx::red_add_f32(d + i, s[i]);
+    } else {
+      for (size_t i = tid; i < ne; i += nthreads) ptx::red_add_f32(d + i, s[i]);
+    }
+    return;
+  }
+  if (op == OP_RED_ADD_BF16) {
+    size_t ne = n >> 1;
+    const __nv_bfloat16* s = (const __nv_bfloat16*)src;
+    __nv_bfloat16* d = (__nv_bfloat16*)dst;
+    if ((((uintptr_t)s | (uintptr_t)d) & 15) == 0) {
+      size_t nv = ne >> 3;
+      for (size_t i = tid; i < nv; i += nthreads) {
+        int4 v = ptx::ld_na_v4(reinterpret_cast<const int4*>(s) + i);
+        ptx::red_add_v4_bf16x2(reinterpret_cast<uint32_t*>(d) + 4 * i, v);
+      }
+      for (size_t i = (nv << 3) + tid; i < ne; i += nthreads) atomicAdd(d + i, s[i]);
+    } else {
+      for (size_t i = tid; i < ne; i += nthreads) atomicAdd(d + i, s[i]);
+    }
+    return;
+  }
+  if (op == OP_CAST_BF16_TO_F32 || op == OP_ACC_BF16_TO_F32) {
+    size_t ne = n >> 1;
+    const __nv_bfloat16* s = (const __nv_bfloat16*)src;
+    float* d = (float*)dst;
+    const bool acc = op == OP_ACC_BF16_TO_F32;
+    if ((((uintptr_t)s | (uintptr_t)d) & 15) == 0) {
+      size_t nv = ne >> 3;   // 8 bf16 in, 2 x float4 out
+      for (size_t i = tid; i < nv; i += nthreads) {
+        int4 v = ptx::ld_na_v4(reinterpret_cast<const int4*>(s) + i);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+        float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+        float2 c = __bfloat1622float2(h[2]), e = __bfloat1622float2(h[3]);
+        float4 lo = make_float4(a.x, a.y, b.x, b.y), hi = make_float4(c.x, c.y, e.x, e.y);
+        if (acc) {
+          ptx::red_add_v4_f32(d + 8 * i, lo);
+          ptx::red_add_v4_f32(d + 8 * i + 4, hi);
+        } else {
+          ptx::st_na_f4(reinterpret_cast<float4*>(d) + 2 * i, lo);
+          ptx::st_na_f4(reinterpret_cast<float4*>(d) + 2 * i + 1, hi);
+        }
+      }
+      for (size_t i = (nv << 3) + tid; i < ne; i += nthreads) {
+        float f = __bfloat162float(s[i]);
+        if (acc) ptx::red_add_f32(d + i, f); else d[i] = f;
+      }
+    } else {
+      for (size_t i = tid; i < ne; i += nthreads) {
+        float f = __bfloat162float(s[i]);
+        if (acc) ptx::red_add_f32(d + i, f); else d[i] = f;
+      }
+    }
+    return;
+  }
+  if (op == OP_CAST_F32_TO_BF16) {
+    size_t ne = n >> 2;
+    const float* s = (const float*)src;
+    __nv_bfloat16* d = (__nv_bfloat16*)dst;
+    if ((((uintptr_t)s | (uintptr_t)d) & 15) == 0) {
+      size_t nv = ne >> 3;   // 2 x float4 in, 8 bf16 out
+      for (size_t i = tid; i < nv; i += nthreads) {
+        float4 lo = ptx::ld_na_f4(reinterpret_cast<const float4*>(s) + 2 * i);
+        float4 hi = ptx::ld_na_f4(reinterpret_cast<const float4*>(s) + 2 * i + 1);
+        int4 o;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+        h[0] = __floats2bfloat162_rn(lo.x, lo.y);
+        h[1] = __floats2bfloat162_rn(lo.z, lo.w);
+        h[2] = __floats2bfloat162_rn(hi.x, hi.y);
+        h[3] = __floats2bfloat162_rn(hi.z, hi.w);
+        ptx::st_na_v4(reinterpret_cast<int4*>(d) + i, o);
+      }
+      for (size_t i = (nv << 3) + tid; i < ne; i += nthreads) d[i] = __float2bfloat16_rn(s[i]);
+    } else {
+      for (size_t i = tid; i < ne; i += nthreads) d[i] = __float2bfloat16_rn(s[i]);
+    }
+    return;
+  }
+}
+
+// destination bytes produced per source byte, as a shift pair (num/den)
+__device__ __host__ inline size_t dst_offset_for(uint32_t op, size_t src_off) {
+  if (op == OP_CAST_BF16_TO_F32 || op == OP_ACC_BF16_TO_F32) return src_off * 2;
+  if (op == OP_CAST_F32_TO_BF16) return src_off / 2;
+  return src_off;
+}
+
+// TMA bulk-copy pipeline: one elected thread per CTA moves its share through a ring of
+// shared-memory stages with cp.async.bulk (global->shared, shared->peer global).
+constexpr int kTmaStages = 4;
+constexpr uint32_t kTmaStageBytes = 32768;
+
+__device__ void tma_copy_range(const char* src, char* dst, size_t n, char* smem, uint64_t* bars, uint32_t* phases) {
+  // n, src, dst are multiples of 16 here (checked by the caller)
+  const size_t nchunks = (n + kTmaStageBytes - 1) / kTmaStageBytes;
+  constexpr int D = kTmaStages - 1;   // loads in flight ahead of the store front
+  auto bytes_of = [&](size_t i) -> uint32_t {
+    size_t off = i * (size_t)kTmaStageBytes;
+    return (uint32_t)(n - off < kTmaStageBytes ? n - off : kTmaStageBytes);
+  };
+  auto issue_load = [&](size_t i) {
+    int s = (int)(i % kTmaStages);
+    uint32_t b = bytes_of(i);
+    ptx::mbar_arrive_expect_tx(&bars[s], b);
+    ptx::bulk_g2s(smem + (size_t)s * kTmaStageBytes, src + i * (size_t)kTmaStageBytes, b, &bars[s]);
+  };
+  for (size_t i = 0; i < nchunks && i < (size_t)D; i++) issue_load(i);
+  for (size_t i = 0; i < nchunks; i++) {
+    int s = (int)(i % kTmaStages);
+    ptx::mbar_wait(&bars[s], phases[s]);
+    phases[s] ^= 1;
+    ptx::bulk_s2g(dst + i * (size_t)kTmaStageBytes, smem + (size_t)s * kTmaStageBytes, bytes_of(i));
+    ptx::bulk_commit();
+    size_t j = i + D;
+    if (j < nchunks) {
+      ptx::bulk_wait_read<1>();   // the store issued one iteration ago has drained its stage
+      issue_load(j);
+    }
+  }
+  ptx::bulk_wait_all();           // stores performed before we signal completion
+}
+
+template <bool kUseTma>
+__global__ void __launch_bounds__(kThreads, 1)
+bnet_nvl_stream_kernel(ClusterQ* q, uint64_t idle_ns, uint64_t watchdog_ns) {
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  __shared__ SmemDesc sd;
+  __shared__ __align__(8) uint64_t bars[kTmaStages];
+  __shared__ uint32_t phases[kTmaStages];
+
+  const uint32_t crank = ptx::cluster_ctarank();
+  const uint32_t csize = ptx::cluster_nctarank();
+  const int tid = threadIdx.x;
+  if (kUseTma && tid == 0) {
+    for (int s = 0; s < kTmaStages; s++) {
+      ptx::mbar_init(&bars[s], 1);
+      phases[s] = 0;
+    }
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+
+  uint64_t head = q->head;            // same value in every CTA of the cluster
+  uint64_t last_work = ptx::globaltimer();
+  for (;;) {
+    // ---- leader: wait for the next descriptor, publish it to every CTA of the cluster
+    if (crank == 0 && tid == 0) {
+      SmemDesc loc;
+      loc.quit = 0;
+      uint32_t backoff = 32;
+      Desc* d = &q->d[head % kQueueDepth];
+      for (;;) {
+        if (ptx::ld_acquire_sys_u64(&d->seq) == head + 1) break;
+        uint64_t now = ptx::globaltimer();
+        if (ptx::ld_relaxed_sys_u32((const uint32_t*)&q->stop)) { loc.quit = 1; break; }
+        if (now - last_work > idle_ns) {
+          // leave unless the host published work while we were deciding (store, fence, re-check)
+          ptx::st_release_sys_u32((uint32_t*)&q->state, ST_EXITING);
+          ptx::fence_sc_sys();
+          if (ptx::ld_acquire_sys_u64(&d->seq) == head + 1) {
+            ptx::st_release_sys_u32((uint32_t*)&q->state, ST_RUNNING);
+            break;
+          }
+          loc.quit = 1;
+          break;
+        }
+        __nanosleep(backoff);
+        if (backoff < 1024) backoff <<= 1;
+      }
+      if (!loc.quit) {
+        loc.src = (const char*)d->src;
+        loc.dst = (char*)d->dst;
+        loc.nbytes = d->nbytes;
+        loc.op = d->op;
+      } else {
+        loc.src = nullptr; loc.dst = nullptr; loc.nbytes = 0; loc.op = 0;
+      }
+      for (uint32_t r = 0; r < csize; r++) ptx::st_dsmem(&sd, r, loc);   // distributed shared memory broadcast
+    }
+    ptx::cluster_sync();     // release/acquire at cluster scope; also drops stale L1 lines
+    const SmemDesc cur = sd;
+    if (cur.quit) break;
+
+    if (cur.op != OP_FLUSH) {
+      // ---- every CTA takes a contiguous 16-byte aligned share of the source range
+      size_t units = (cur.nbytes + 15) >> 4;
+      size_t per = (units + csize - 1) / csize;
+      size_t b0 = (size_t)crank * per * 16;
+      size_t b1 = b0 + per * 16;
+      if (b0 > cur.nbytes) b0 = cur.nbytes;
+      if (b1 > cur.nbytes) b1 = cur.nbytes;
+      const char* s = cur.src + b0;
+      char* dd = cur.dst + dst_offset_for(cur.op, b0);
+      size_t n = b1 - b0;
+      bool tma_ok = kUseTma && cur.op == OP_COPY && n >= 16 &&
+                    ((((uintptr_t)s | (uintptr_t)dd) & 15) == 0);
+      if (tma_ok) {
+        size_t nb = n & ~(size_t)15;
+        if (tid == 0) tma_copy_range(s, dd, nb, (char*)dyn_smem, bars, phases);
+        if (n > nb) process_range(OP_COPY, s + nb, dd + nb, n - nb, tid, kThreads);
+      } else {
+        process_range(cur.op, s, dd, n, tid, kThreads);
+      }
+    }
+    __syncthreads();
+    ptx::cluster_sync();     // every CTA's stores are ordered before the leader's fence
+    if (crank == 0 && tid == 0) {
+      Desc* d = &q->d[head % kQueueDepth];
+      uint64_t* flag = d->flag;
+      uint64_t fv = d->flag_val;
+      ptx::fence_acq_rel_sys();                    // peer stores visible system-wide ...
+      ptx::st_release_sys_u64(flag, fv);           // ... before the chunk's completion word
+      ptx::st_release_sys_u64((uint64_t*)&q->head, head + 1);
+      last_work = ptx::globaltimer();
+    }
+    head++;
+    (void)watchdog_ns;
+  }
+  if (crank == 0 && tid == 0) ptx::st_release_sys_u32((uint32_t*)&q->state, ST_EXITED);
+}
+
+// One-shot kernel used when BNET_PERSISTENT=0: a grid of clusters per chunk list.
+struct OneShotArgs {
+  const char* src;
+  char* dst;
+  uint64_t nbytes;
+  uint64_t* flag;
+  uint64_t flag_val;
+  uint32_t op;
+};
+__global__ void __launch_bounds__(kThreads, 1) bnet_nvl_oneshot_kernel(OneShotArgs a) {
+  const uint32_t crank = ptx::cluster_ctarank();
+  const uint32_t csize = ptx::cluster_nctarank();
+  if (a.op != OP_FLUSH) {
+    size_t units = (a.nbytes + 15) >> 4;
+    size_t per = (units + csize - 1) / csize;
+    size_t b0 = (size_t)crank * per * 16, b1 = b0 + per * 16;
+    if (b0 > a.nbytes) b0 = a.nbytes;
+    if (b1 > a.nbytes) b1 = a.nbytes;
+    process_range(a.op, a.src + b0, a.dst + dst_offset_for(a.op, b0), b1 - b0, threadIdx.x, kThreads);
+  }
+  __syncthreads();
+  ptx::cluster_sync();
+  if (crank == 0 && threadIdx.x == 0) {
+    ptx::fence_acq_rel_sys();
+    ptx::st_release_sys_u64(a.flag, a.flag_val);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+namespace {
+
+struct Stream {
+  ClusterQ* q = nullptr;       // pinned host
+  ClusterQ* q_dev = nullptr;   // device alias
+  cudaStream_t stream = nullptr;
+};
+
+struct Exec {
+  int dev = -1;
+  bool ok = false;
+  bool persistent = true;
+  bool tma = false;
+  int nclusters = 4;
+  int cluster_size = 2;
+  size_t min_chunk = 1 << 20;
+  uint64_t idle_ns = 200000;
+  size_t rr = 0;               // persists across messages
+  std::vector<Stream> streams;
+  std::mutex mu;
+  ExecStats stats{};
+};
+
+std::mutex g_mu;
+Exec* g_exec[64] = {nullptr};
+
+template <typename K>
+cudaError_t launch_cluster(K kernel, int nblocks, int cluster, size_t smem, cudaStream_t st, void** args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(nblocks);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelExC(&cfg, (const void*)kernel, args);
+}
+
+Exec* get_exec(int dev) {
+  if (dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_exec[dev]) return g_exec[dev]->ok ? g_exec[dev] : nullptr;
+  Exec* e = new Exec();
+  g_exec[dev] = e;
+  e->dev = dev;
+  const Config& cfg = Config::get();
+  long long nc = env_int("NCLUSTERS", 4);
+  e->nclusters = (int)(nc < 1 ? 1 : nc > kMaxChunksPerJob ? kMaxChunksPerJob : nc);
+  long long cs = env_int("CLUSTER_SIZE", 2);
+  e->cluster_size = (int)(cs < 1 ? 1 : cs > 8 ? 8 : cs);
+  e->min_chunk = (size_t)env_int("DEV_MIN_CHUNKSIZE", (long long)(cfg.min_chunksize < 262144 ? cfg.min_chunksize : 262144));
+  if (e->min_chunk < 16) e->min_chunk = 16;
+  e->persistent = env_int("PERSISTENT", 1) != 0;
+  e->tma = env_str("COPY_ENGINE", "ldst") == "tma";
+  e->idle_ns = (uint64_t)env_int("KERNEL_IDLE_US", 200) * 1000ull;
+  int cur = -1;
+  cudaGetDevice(&cur);
+  if (cur != dev) cudaSetDevice(dev);
+  bool good = true;
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  for (int i = 0; i < e->nclusters && good; i++) {
+    Stream s;
+    void* dp = nullptr;
+    s.q = (ClusterQ*)host_alloc_mapped(sizeof(ClusterQ), &dp);
+    s.q_dev = (ClusterQ*)dp;
+    if (!s.q || cudaStreamCreateWithPriority(&s.stream, cudaStreamNonBlocking, hi) != cudaSuccess) good = false;
+    e->streams.push_back(s);
+  }
+  if (good && e->tma) {
+    cudaError_t err = cudaFuncSetAttribute(bnet_nvl_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           kTmaStages * kTmaStageBytes);
+    if (err != cudaSuccess) { cudaGetLastError(); e->tma = false; }
+  }
+  if (cur != dev && cur >= 0) cudaSetDevice(cur);
+  if (!good) cudaGetLastError();
+  e->ok = good;
+  BNET_INFO("nvl executor on dev %d: %d cluster(s) x %d CTA x %d thr, %s, engine=%s, min chunk %zu, idle %llu us",
+            dev, e->nclusters, e->cluster_size, kThreads, e->persistent ? "persistent" : "one-shot",
+            e->tma ? "tma" : "ld/st", e->min_chunk, (unsigned long long)(e->idle_ns / 1000));
+  return good ? e : nullptr;
+}
+
+int ensure_running(Exec* e, Stream& s) {
+  for (int spin = 0;; spin++) {
+    uint32_t st = __atomic_load_n(&s.q->state, __ATOMIC_ACQUIRE);
+    if (st == ST_RUNNING) return 0;
+    if (st == ST_EXITING) {   // the kernel is deciding; it will settle on RUNNING or EXITED
+      if (spin > 20000000) return -1;
+      continue;
+    }
+    // EXITED: (re)launch
+    __atomic_store_n(&s.q->state, ST_RUNNING, __ATOMIC_RELEASE);
+    ClusterQ* qd = s.q_dev;
+    uint64_t idle = e->idle_ns, wd = 0;
+    void* args[] = {&qd, &idle, &wd};
+    cudaError_t err = e->tma ? launch_cluster(bnet_nvl_stream_kernel<true>, e->cluster_size, e->cluster_size,
+                                              kTmaStages * kTmaStageBytes, s.stream, args)
+                             : launch_cluster(bnet_nvl_stream_kernel<false>, e->cluster_size, e->cluster_size, 0,
+                                              s.stream, args);
+    if (err != cudaSuccess) {
+      cudaGetLastError();
+      __atomic_store_n(&s.q->state, ST_EXITED, __ATOMIC_RELEASE);
+      BNET_WARN("nvl executor: kernel launch failed: %s", cudaGetErrorString(err));
+      return -1;
+    }
+    e->stats.launches++;
+    return 0;
+  }
+}
+
+int submit(Exec* e, uint32_t op, const void* src, void* dst, size_t nbytes, uint64_t* flags_dev, uint64_t flag_value,
+           int* nchunks_out) {
+  std::lock_guard<std::mutex> lk(e->mu);
+  int cur = -1;
+  cudaGetDevice(&cur);
+  if (cur != e->dev) cudaSetDevice(e->dev);
+  size_t unit = (op == OP_RED_ADD_F32 || op == OP_CAST_F32_TO_BF16) ? 32 : 16;   // keep chunk cuts element/vector aligned
+  size_t cs = chunk_size(nbytes, e->min_chunk, (size_t)e->nclusters);
+  cs = (cs + unit - 1) / unit * unit;
+  int nchunks = nbytes ? (int)((nbytes + cs - 1) / cs) : 1;
+  if (nchunks > kMaxChunksPerJob) nchunks = kMaxChunksPerJob;   // cannot happen: nclusters <= kMaxChunksPerJob
+  int rc = 0;
+  for (int c = 0; c < nchunks && rc == 0; c++) {
+    size_t off = (size_t)c * cs;
+    size_t n = nbytes ? (nbytes - off < cs ? nbytes - off : cs) : 0;
+    Stream& s = e->streams[e->rr];
+    e->rr = (e->rr + 1) % e->streams.size();
+    if (e->persistent) {
+      uint64_t t = s.q->tail;
+      uint64_t spins = 0;
+      while (t - __atomic_load_n(&s.q->head, __ATOMIC_ACQUIRE) >= (uint64_t)kQueueDepth) {
+        if (ensure_running(e, s) != 0 || ++spins > 200000000ull) { rc = -1; break; }
+      }
+      if (rc) break;
+      Desc& d = s.q->d[t % kQueueDepth];
+      d.src = (const char*)src + off;
+      d.dst = (char*)dst + dst_offset_for(op, off);
+      d.nbytes = n;
+      d.flag = flags_dev + c;
+      d.flag_val = flag_value;
+      d.op = op;
+      __atomic_store_n(&d.seq, t + 1, __ATOMIC_RELEASE);
+      s.q->tail = t + 1;
+      __atomic_thread_fence(__ATOMIC_SEQ_CST);   // publish, then look at the kernel's state (Dekker)
+      rc = ensure_running(e, s);
+      e->stats.persistent++;
+    } else {
+      OneShotArgs a{(const char*)src + off, (char*)dst + dst_offset_for(op, off), n, flags_dev + c, flag_value, op};
+      void* args[] = {&a};
+      cudaError_t err = launch_cluster(bnet_nvl_oneshot_kernel, e->cluster_size, e->cluster_size, 0, s.stream, args);
+      if (err != cudaSuccess) {
+        cudaGetLastError();
+        rc = -1;
+      }
+      e->stats.launches++;
+    }
+    e->stats.chunks++;
+  }
+  e->stats.jobs++;
+  e->stats.bytes += nbytes;
+  if (cur != e->dev && cur >= 0) cudaSetDevice(cur);
+  *nchunks_out = nchunks;
+  return rc;
+}
+
+}  // namespace
+
+int exec_copy(int dev, const void* src, void* dst, size_t nbytes, volatile uint64_t* flags_host, uint64_t* flags_dev,
+              uint64_t flag_value, int* nchunks) {
+  if (fake()) {   // CPU emulation: synchronous copy, same completion protocol
+    memcpy(dst, src, nbytes);
+    size_t cs = chunk_size(nbytes, (size_t)env_int("DEV_MIN_CHUNKSIZE", 262144), 4);
+    int n = nbytes ? (int)((nbytes + cs - 1) / cs) : 1;
+    for (int i = 0; i < n; i++) flags_host[i] = flag_value;
+    *nchunks = n;
+    return 0;
+  }
+  Exec* e = get_exec(dev);
+  if (!e) return -1;
+  return submit(e, OP_COPY, src, dst, nbytes, flags_dev, flag_value, nchunks);
+}
+
+int exec_flush(int dev, volatile uint64_t* flag_host, uint64_t* flag_dev, uint64_t flag_value) {
+  if (fake()) {
+    *flag_host = flag_value;
+    return 0;
+  }
+  Exec* e = get_exec(dev);
+  if (!e) return -1;
+  int n = 0;
+  return submit(e, OP_FLUSH, nullptr, nullptr, 0, flag_dev, flag_value, &n);
+}
+
+// Extension entry point: fused move+reduce / move+cast between registered buffers
+// (used by tests, bench/p2p_bw and the Python ops layer).
+extern "C" __attribute__((visibility("default"))) int bnet_exec_op(int dev, uint32_t op, const void* src, void* dst, size_t src_bytes,
+                            volatile uint64_t* flags_host, uint64_t* flags_dev, uint64_t flag_value, int* nchunks) {
+  if (op == OP_COPY) return exec_copy(dev, src, dst, src_bytes, flags_host, flags_dev, flag_value, nchunks);
+  Exec* e = get_exec(dev);
+  if (!e) return -1;
+  return submit(e, op, src, dst, src_bytes, flags_dev, flag_value, nchunks);
+}
+
+void exec_stats(ExecStats* out) {
+  memset(out, 0, sizeof(*out));
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (Exec* e : g_exec) {
+    if (!e) continue;
+    out->jobs += e->stats.jobs;
+    out->chunks += e->stats.chunks;
+    out->bytes += e->stats.bytes;
+    out->launches += e->stats.launches;
+    out->persistent += e->stats.persistent;
+  }
+}
+
+void exec_shutdown() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (Exec* e : g_exec) {
+    if (!e || !e->ok) continue;
+    for (Stream& s : e->streams)
+      if (s.q) __atomic_store_n(&s.q->stop, 1u, __ATOMIC_RELEASE);
+  }
+}
+
+}  // namespace cuda
+}  // namespace bnet

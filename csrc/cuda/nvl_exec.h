@@ -1,0 +1,35 @@
+// Device copy executor used by the NVLink transport: moves a registered buffer
+// into the peer GPU's buffer with sm_100a kernels (K1/K8 in SURVEY.md §2.6).
+//
+// A transfer is split into chunks of max(ceil(n/nclusters), MIN_CHUNKSIZE) bytes —
+// the same rule the reference uses to stripe a message over its TCP streams
+// (reference: src/utils.rs:200-205, nthread_…:405-413) — and the chunks are dealt
+// round-robin to thread-block clusters ("device streams"), the cursor persisting
+// across messages.  Every chunk has its own completion word in pinned host memory
+// that the kernel writes with release.sys semantics after its stores; test()
+// polls those words: no syscall, no mutex on the completion path.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+namespace bnet {
+namespace cuda {
+
+constexpr int kMaxChunksPerJob = 16;
+
+struct ExecStats {
+  uint64_t jobs, chunks, bytes, launches, persistent;
+};
+
+// flags_host/flags_dev: the same kMaxChunksPerJob words seen from host and device.
+// On return *nchunks words will eventually hold `flag_value`.
+// Returns 0 on success, <0 on failure (caller falls back to the bounce ring).
+int exec_copy(int dev, const void* src, void* dst, size_t nbytes, volatile uint64_t* flags_host,
+              uint64_t* flags_dev, uint64_t flag_value, int* nchunks);
+// Device-side fence used by iflush (K7): completes `flag` once prior peer stores are visible.
+int exec_flush(int dev, volatile uint64_t* flag_host, uint64_t* flag_dev, uint64_t flag_value);
+void exec_stats(ExecStats* out);
+void exec_shutdown();
+
+}  // namespace cuda
+}  // namespace bnet

@@ -1,0 +1,346 @@
+// NCCL ext-net ABI shims: one exported table per ABI version, all delegating to
+// the engine.  Counterpart of the reference's L1 (reference:
+// cc/v4/nccl_net_v4.cc:1-226, cc/v3/nccl_net_v3.cc:1-226) — but the installed
+// NCCL 2.27/2.28 only probe v6..v11, so v6+ tables are what NCCL actually loads;
+// v3/v4 keep the reference's symbols alive (and drive our own loopback harness).
+//
+// Semantics that differ from the reference on purpose:
+//   * regMr accepts NCCL_PTR_CUDA when the CUDA side is usable and always writes
+//     *mhandle (the reference rejects CUDA and leaves *mhandle unset, :105-109)
+//   * iflush works (device-side fence / no-op for host memory) instead of
+//     returning ncclInternalError (:145-149)
+//   * v5+ connect/accept never block on the peer: they return *comm == NULL
+//     until the connection is ready
+#include <string.h>
+
+#include "bnet/nccl_net_abi.h"
+#include "core/engine.h"
+#include "core/telemetry.h"
+
+using namespace bnet;
+
+#define BNET_EXPORT __attribute__((visibility("default")))
+#pragma GCC diagnostic ignored "-Wunused-function"
+
+namespace {
+
+const char kName[] = "BNet";
+
+// strings handed to NCCL must stay alive: cache per device
+struct PropStrings {
+  std::string name, pci;
+};
+std::vector<PropStrings>& prop_cache() {
+  static std::vector<PropStrings>* v = new std::vector<PropStrings>();
+  return *v;
+}
+std::mutex g_prop_mu;
+
+ncclResult_t fill_common(int dev, DeviceProps* p, char** name, char** pci) {
+  int st = Engine::get().props(dev, p);
+  if (st) return to_nccl(st);
+  std::lock_guard<std::mutex> lk(g_prop_mu);
+  auto& c = prop_cache();
+  if ((int)c.size() <= dev) c.resize(dev + 1);
+  c[dev].name = p->name;
+  c[dev].pci = p->pci_path;
+  *name = const_cast<char*>(c[dev].name.c_str());
+  *pci = c[dev].pci.empty() ? nullptr : const_cast<char*>(c[dev].pci.c_str());
+  return ncclSuccess;
+}
+
+ncclResult_t do_init(ncclDebugLogger_t logfn) {
+  if (logfn) log_set_nccl_logger(logfn);
+  int st = Engine::get().init();
+  if (st) BNET_WARN("init failed: %s", status_str(st));
+  return to_nccl(st);
+}
+
+ncclResult_t do_devices(int* ndev) {
+  if (!ndev) return ncclInvalidArgument;
+  *ndev = Engine::get().ndev();
+  return ncclSuccess;
+}
+
+ncclResult_t do_listen(int dev, void* handle, size_t cap, void** lcomm) {
+  ListenComm* l = nullptr;
+  int st = Engine::get().listen(dev, handle, cap, &l);
+  if (st) {
+    BNET_WARN("listen(dev=%d) failed: %s", dev, status_str(st));
+    return to_nccl(st);
+  }
+  *lcomm = l;
+  return ncclSuccess;
+}
+
+ncclResult_t do_connect(int dev, void* handle, void** scomm) {
+  Comm* c = nullptr;
+  int st = Engine::get().connect(dev, handle, &c);
+  if (st) {
+    BNET_WARN("connect(dev=%d) failed: %s", dev, status_str(st));
+    return to_nccl(st);
+  }
+  *scomm = c;
+  BNET_TRACE("connect dev=%d -> comm %p (%s)", dev, (void*)c, c ? c->transport() : "pending");
+  return ncclSuccess;
+}
+
+ncclResult_t do_accept(void* lcomm, void** rcomm, bool blocking) {
+  if (!lcomm) return ncclInvalidArgument;
+  Comm* c = nullptr;
+  int st = Engine::get().accept(static_cast<ListenComm*>(lcomm), &c, blocking);
+  if (st) {
+    BNET_WARN("accept failed: %s", status_str(st));
+    return to_nccl(st);
+  }
+  *rcomm = c;
+  if (c) BNET_TRACE("accept -> comm %p (%s)", (void*)c, c->transport());
+  return ncclSuccess;
+}
+
+ncclResult_t do_regmr(void* comm, void* data, size_t size, int type, void** mhandle) {
+  if (!comm || !mhandle) return ncclInvalidArgument;
+  MemHandle* mh = nullptr;
+  int st = static_cast<Comm*>(comm)->reg_mr(data, size, type, &mh);
+  if (st) {
+    BNET_WARN("regMr(%p, %zu, type=%d) failed: %s", data, size, type, status_str(st));
+    return to_nccl(st);
+  }
+  *mhandle = mh;
+  return ncclSuccess;
+}
+
+ncclResult_t do_deregmr(void* comm, void* mhandle) {
+  if (!comm) return ncclInvalidArgument;
+  if (!mhandle) return ncclSuccess;
+  return to_nccl(static_cast<Comm*>(comm)->dereg_mr(static_cast<MemHandle*>(mhandle)));
+}
+
+ncclResult_t do_isend(void* scomm, void* data, size_t size, int tag, void* mh, void** request) {
+  if (!scomm || !request) return ncclInvalidArgument;
+  Request* r = nullptr;
+  int st = static_cast<Comm*>(scomm)->isend(data, size, tag, static_cast<MemHandle*>(mh), &r);
+  if (st) {
+    BNET_WARN("isend(%zu bytes) failed: %s", size, status_str(st));
+    return to_nccl(st);
+  }
+  *request = r;
+  BNET_TRACE("isend comm=%p data=%p size=%zu req=%p", scomm, data, size, (void*)r);
+  return ncclSuccess;
+}
+
+ncclResult_t do_irecv(void* rcomm, void* data, size_t size, int tag, void* mh, void** request) {
+  if (!rcomm || !request) return ncclInvalidArgument;
+  Request* r = nullptr;
+  int st = static_cast<Comm*>(rcomm)->irecv(data, size, tag, static_cast<MemHandle*>(mh), &r);
+  if (st) {
+    BNET_WARN("irecv(%zu bytes) failed: %s", size, status_str(st));
+    return to_nccl(st);
+  }
+  *request = r;
+  BNET_TRACE("irecv comm=%p data=%p size=%zu req=%p", rcomm, data, size, (void*)r);
+  return ncclSuccess;
+}
+
+ncclResult_t do_iflush(void* rcomm, void* data, size_t size, void* mh, void** request) {
+  if (!rcomm || !request) return ncclInvalidArgument;
+  Request* r = nullptr;
+  int st = static_cast<Comm*>(rcomm)->iflush(data, size, static_cast<MemHandle*>(mh), &r);
+  if (st) return to_nccl(st);
+  *request = r;
+  return ncclSuccess;
+}
+
+ncclResult_t do_test(void* request, int* done, int* size) {
+  if (!request || !done) return ncclInvalidArgument;
+  Request* r = static_cast<Request*>(request);
+  size_t sz = 0;
+  int st = r->comm->test(r, done, &sz);
+  if (st) {
+    BNET_WARN("test: request %llu on %s comm failed: %s", (unsigned long long)r->id, r->comm->transport(),
+              status_str(st));
+    return to_nccl(st);
+  }
+  if (*done && size) *size = (int)sz;
+  return ncclSuccess;
+}
+
+ncclResult_t do_close(void* comm) {
+  delete static_cast<Comm*>(comm);
+  return ncclSuccess;
+}
+
+// ---- v3 / v4 (blocking accept like the reference; int sizes; 64-byte handle) --------
+ncclResult_t v4_init(ncclDebugLogger_t f) { return do_init(f); }
+ncclResult_t v4_props(int dev, ncclNetProperties_v4_t* o) {
+  DeviceProps p;
+  ncclResult_t r = fill_common(dev, &p, &o->name, &o->pciPath);
+  if (r) return r;
+  o->guid = p.guid;
+  o->ptrSupport = p.ptr_support;
+  o->speed = p.speed_mbps;
+  o->port = p.port;
+  o->maxComms = p.max_comms;
+  return ncclSuccess;
+}
+ncclResult_t v4_listen(int dev, void* h, void** l) { return do_listen(dev, h, NCCL_NET_HANDLE_MAXSIZE_V4, l); }
+ncclResult_t v4_connect(int dev, void* h, void** s) { return do_connect(dev, h, s); }
+ncclResult_t v4_accept(void* l, void** r) { return do_accept(l, r, /*blocking=*/true); }
+ncclResult_t v4_regmr(void* c, void* d, int size, int type, void** mh) { return do_regmr(c, d, (size_t)size, type, mh); }
+ncclResult_t v4_isend(void* c, void* d, int size, void* mh, void** req) {
+  // v4 has no "try again" contract in the reference (queues are unbounded there):
+  // wait for a request slot instead of returning NULL.
+  for (;;) {
+    ncclResult_t r = do_isend(c, d, (size_t)size, 0, mh, req);
+    if (r || *req) return r;
+    static_cast<Comm*>(c)->progress();
+    sched_yield();
+  }
+}
+ncclResult_t v4_irecv(void* c, void* d, int size, void* mh, void** req) {
+  for (;;) {
+    ncclResult_t r = do_irecv(c, d, (size_t)size, 0, mh, req);
+    if (r || *req) return r;
+    static_cast<Comm*>(c)->progress();
+    sched_yield();
+  }
+}
+ncclResult_t v4_iflush(void* c, void* d, int size, void* mh, void** req) { return do_iflush(c, d, (size_t)size, mh, req); }
+ncclResult_t v3_flush(void* c, void* d, int size, void* mh) {
+  void* req = nullptr;
+  ncclResult_t r = do_iflush(c, d, (size_t)size, mh, &req);
+  if (r) return r;
+  int done = 0;
+  while (req && !done) {
+    r = do_test(req, &done, nullptr);
+    if (r) return r;
+  }
+  return ncclSuccess;
+}
+
+// ---- v5..v8 -----------------------------------------------------------------------
+template <typename P>
+ncclResult_t props_v6like(int dev, P* o) {
+  DeviceProps p;
+  ncclResult_t r = fill_common(dev, &p, &o->name, &o->pciPath);
+  if (r) return r;
+  o->guid = p.guid;
+  o->ptrSupport = p.ptr_support;
+  o->speed = p.speed_mbps;
+  o->port = p.port;
+  o->latency = p.latency_us;
+  o->maxComms = p.max_comms;
+  o->maxRecvs = p.max_recvs;
+  return ncclSuccess;
+}
+ncclResult_t v6_props(int dev, ncclNetProperties_v6_t* o) { return props_v6like(dev, o); }
+ncclResult_t v7_props(int dev, ncclNetProperties_v7_t* o) {
+  ncclResult_t r = props_v6like(dev, o);
+  o->netDeviceType = NCCL_NET_DEVICE_HOST;
+  o->netDeviceVersion = NCCL_NET_DEVICE_INVALID_VERSION;
+  return r;
+}
+ncclResult_t v8_props(int dev, ncclNetProperties_v8_t* o) {
+  ncclResult_t r = props_v6like(dev, o);
+  o->regIsGlobal = 0;
+  o->netDeviceType = NCCL_NET_DEVICE_HOST;
+  o->netDeviceVersion = NCCL_NET_DEVICE_INVALID_VERSION;
+  return r;
+}
+ncclResult_t v9_props(int dev, ncclNetProperties_v9_t* o) {
+  ncclResult_t r = props_v6like(dev, o);
+  o->regIsGlobal = 0;
+  o->forceFlush = 0;
+  o->netDeviceType = NCCL_NET_DEVICE_HOST;
+  o->netDeviceVersion = NCCL_NET_DEVICE_INVALID_VERSION;
+  o->vProps.ndevs = 1;
+  o->vProps.devs[0] = dev;
+  o->maxP2pBytes = (size_t)1 << 40;
+  o->maxCollBytes = (size_t)1 << 40;
+  return r;
+}
+
+ncclResult_t v6_listen(int dev, void* h, void** l) { return do_listen(dev, h, NCCL_NET_HANDLE_MAXSIZE, l); }
+ncclResult_t v6_connect(int dev, void* h, void** s) { return do_connect(dev, h, s); }
+ncclResult_t v6_accept(void* l, void** r) { return do_accept(l, r, /*blocking=*/false); }
+ncclResult_t v7_connect(int dev, void* h, void** s, ncclNetDeviceHandle_v7_t** dh) {
+  if (dh) *dh = nullptr;
+  return do_connect(dev, h, s);
+}
+ncclResult_t v7_accept(void* l, void** r, ncclNetDeviceHandle_v7_t** dh) {
+  if (dh) *dh = nullptr;
+  return do_accept(l, r, false);
+}
+ncclResult_t v10_connect(int dev, ncclNetCommConfig_v10_t*, void* h, void** s, ncclNetDeviceHandle_v10_t** dh) {
+  if (dh) *dh = nullptr;
+  return do_connect(dev, h, s);
+}
+ncclResult_t v6_regmr(void* c, void* d, int size, int type, void** mh) { return do_regmr(c, d, (size_t)size, type, mh); }
+ncclResult_t v8_regmr(void* c, void* d, size_t size, int type, void** mh) { return do_regmr(c, d, size, type, mh); }
+ncclResult_t v6_regmr_dmabuf(void* c, void* d, size_t size, int type, uint64_t, int, void** mh) {
+  return do_regmr(c, d, size, type, mh);   // we never advertise NCCL_PTR_DMABUF; treat as plain regMr
+}
+ncclResult_t v6_isend(void* c, void* d, int size, int tag, void* mh, void** req) { return do_isend(c, d, (size_t)size, tag, mh, req); }
+ncclResult_t v9_isend(void* c, void* d, size_t size, int tag, void* mh, void** req) { return do_isend(c, d, size, tag, mh, req); }
+ncclResult_t v10_isend(void* c, void* d, size_t size, int tag, void* mh, void*, void** req) { return do_isend(c, d, size, tag, mh, req); }
+ncclResult_t v6_irecv(void* c, int n, void** data, int* sizes, int* tags, void** mhs, void** req) {
+  if (n != 1) return ncclInvalidUsage;   // maxRecvs = 1
+  return do_irecv(c, data[0], (size_t)sizes[0], tags ? tags[0] : 0, mhs ? mhs[0] : nullptr, req);
+}
+ncclResult_t v9_irecv(void* c, int n, void** data, size_t* sizes, int* tags, void** mhs, void** req) {
+  if (n != 1) return ncclInvalidUsage;
+  return do_irecv(c, data[0], sizes[0], tags ? tags[0] : 0, mhs ? mhs[0] : nullptr, req);
+}
+ncclResult_t v10_irecv(void* c, int n, void** data, size_t* sizes, int* tags, void** mhs, void**, void** req) {
+  return v9_irecv(c, n, data, sizes, tags, mhs, req);
+}
+ncclResult_t v6_iflush(void* c, int n, void** data, int* sizes, void** mhs, void** req) {
+  if (n != 1) return ncclInvalidUsage;
+  return do_iflush(c, data[0], (size_t)sizes[0], mhs ? mhs[0] : nullptr, req);
+}
+ncclResult_t v7_get_device_mr(void*, void*, void**) { return ncclInternalError; }
+ncclResult_t v7_irecv_consumed(void*, int, void*) { return ncclSuccess; }
+ncclResult_t v10_init(ncclDebugLogger_t f, ncclProfilerCallback_t) { return do_init(f); }
+
+}  // namespace
+
+// ---- exported tables -----------------------------------------------------------------
+extern "C" {
+BNET_EXPORT ncclNet_v3_t ncclNetPlugin_v3 = {
+    kName, v4_init, do_devices, v4_props, v4_listen, v4_connect, v4_accept, v4_regmr, do_deregmr,
+    v4_isend, v4_irecv, v3_flush, do_test, do_close, do_close, do_close};
+
+BNET_EXPORT ncclNet_v4_t ncclNetPlugin_v4 = {
+    kName, v4_init, do_devices, v4_props, v4_listen, v4_connect, v4_accept, v4_regmr, do_deregmr,
+    v4_isend, v4_irecv, v4_iflush, do_test, do_close, do_close, do_close};
+
+BNET_EXPORT ncclNet_v5_t ncclNetPlugin_v5 = {
+    kName, v4_init, do_devices, v6_props, v6_listen, v6_connect, v6_accept, v6_regmr, do_deregmr,
+    v6_isend, v6_irecv, v6_iflush, do_test, do_close, do_close, do_close};
+
+BNET_EXPORT ncclNet_v6_t ncclNetPlugin_v6 = {
+    kName, v4_init, do_devices, v6_props, v6_listen, v6_connect, v6_accept, v6_regmr, v6_regmr_dmabuf,
+    do_deregmr, v6_isend, v6_irecv, v6_iflush, do_test, do_close, do_close, do_close};
+
+BNET_EXPORT ncclNet_v7_t ncclNetPlugin_v7 = {
+    kName, v4_init, do_devices, v7_props, v6_listen, v7_connect, v7_accept, v6_regmr, v6_regmr_dmabuf,
+    do_deregmr, v6_isend, v6_irecv, v6_iflush, do_test, do_close, do_close, do_close,
+    v7_get_device_mr, v7_irecv_consumed};
+
+BNET_EXPORT ncclNet_v8_t ncclNetPlugin_v8 = {
+    kName, v4_init, do_devices, v8_props, v6_listen, v7_connect, v7_accept, v8_regmr, v6_regmr_dmabuf,
+    do_deregmr, v6_isend, v6_irecv, v6_iflush, do_test, do_close, do_close, do_close,
+    v7_get_device_mr, v7_irecv_consumed};
+
+#ifdef BNET_EXPORT_V9_V10
+BNET_EXPORT ncclNet_v9_t ncclNetPlugin_v9 = {
+    kName, v4_init, do_devices, v9_props, v6_listen, v7_connect, v7_accept, v8_regmr, v6_regmr_dmabuf,
+    do_deregmr, v9_isend, v9_irecv, v6_iflush, do_test, do_close, do_close, do_close,
+    v7_get_device_mr, v7_irecv_consumed, nullptr};
+
+BNET_EXPORT ncclNet_v10_t ncclNetPlugin_v10 = {
+    kName, v10_init, do_devices, v9_props, v6_listen, v10_connect, v7_accept, v8_regmr, v6_regmr_dmabuf,
+    do_deregmr, v10_isend, v10_irecv, v6_iflush, do_test, do_close, do_close, do_close,
+    v7_get_device_mr, v7_irecv_consumed, nullptr};
+#endif
+}  // extern "C"

@@ -1,0 +1,125 @@
+"""ABI + transport tests over loopback, two processes — BASELINE.json config #1
+("ncclNet_v4 loopback isend/irecv correctness, 2 ranks on CPU sockets") widened to every
+exported ABI version, both TCP backends, the shared-memory (NVL) transport, 8 requests
+in flight, sizes around the chunking boundaries, receive buffers larger than the message.
+The reference has no such test (BASIC backend tests: none)."""
+import pytest
+
+from conftest import run_pair
+
+SIZES = "0,1,8,4096,524288,1048575,1048577,3145729"
+
+
+def _check(outs, transport=None):
+    for rc, res, err in outs:
+        assert res is not None, err
+        assert rc == 0 and res["ok"], (res, err[-2000:])
+        assert res["name"] == "BNet"
+        if transport:
+            assert res["transport"] == transport, res
+    return outs
+
+
+@pytest.mark.parametrize("abi", [3, 4, 6, 8])
+def test_abi_versions_tcp_basic(abi):
+    _check(run_pair(["--abi", str(abi), "--sizes", SIZES, "--inflight", "8", "--rounds", "1"],
+                    env={"BNET_NVL": "0"}), "tcp-threads")
+
+
+def test_abi_v10_table():
+    # exported only by the -bnetx variant; layout checked through the same driver
+    import ctypes
+    import os
+
+    import bagua_net_b200
+    from bagua_net_b200.utils.abi import NetPlugin
+
+    p = NetPlugin(10, "libnccl-net-bnetx.so")
+    p.init()
+    props = p.get_properties(0)
+    assert props["maxRecvs"] == 1 and props["vProps"]["ndevs"] == 1 and props["maxP2pBytes"] > 1 << 30
+    assert os.path.exists(bagua_net_b200.lib_path("libnccl-net-bnet.so"))
+    lib = ctypes.CDLL(bagua_net_b200.lib_path())
+    for v in (3, 4, 5, 6, 7, 8):
+        assert hasattr(lib, f"ncclNetPlugin_v{v}")
+    assert not hasattr(lib, "ncclNetPlugin_v10")      # default build stays on well-known layouts
+
+
+@pytest.mark.parametrize("nstreams", [1, 2, 8])
+@pytest.mark.parametrize("impl", ["BASIC", "TOKIO"])
+def test_tcp_backends_and_nstreams(impl, nstreams):
+    env = {"BNET_NVL": "0", "BAGUA_NET_IMPLEMENT": impl, "BAGUA_NET_NSTREAMS": str(nstreams),
+           "BAGUA_NET_MIN_CHUNKSIZE": "65536"}
+    _check(run_pair(["--sizes", SIZES, "--inflight", "8", "--rounds", "2"], env=env),
+           "tcp-threads" if impl == "BASIC" else "tcp-async")
+
+
+def test_sender_params_win_over_receiver_params():
+    # The reference silently corrupts data when both ends disagree on NSTREAMS/MIN_CHUNKSIZE
+    # (SURVEY.md §2.2 protocol invariant).  Here the preamble carries the sender's values.
+    import json
+    import os
+    import subprocess
+    import sys
+    import tempfile
+
+    from conftest import ROOT
+
+    worker = os.path.join(ROOT, "tests", "loopback_worker.py")
+    base = dict(os.environ, PYTHONPATH=ROOT, BNET_NVL="0")
+    with tempfile.TemporaryDirectory() as d:
+        r = subprocess.Popen([sys.executable, worker, "0", d, "--sizes", "1048577,3145729"],
+                             env=dict(base, BAGUA_NET_NSTREAMS="2", BAGUA_NET_MIN_CHUNKSIZE="1048576"),
+                             stdout=subprocess.PIPE, text=True)
+        s = subprocess.Popen([sys.executable, worker, "1", d, "--sizes", "1048577,3145729"],
+                             env=dict(base, BAGUA_NET_NSTREAMS="5", BAGUA_NET_MIN_CHUNKSIZE="4096",
+                                      BAGUA_NET_IMPLEMENT="TOKIO"),
+                             stdout=subprocess.PIPE, text=True)
+        ro, so = r.communicate(timeout=120)[0], s.communicate(timeout=120)[0]
+    rres, sres = json.loads(ro.splitlines()[-1]), json.loads(so.splitlines()[-1])
+    assert rres["ok"] and sres["ok"], (rres, sres)
+    assert rres["transport"] == "tcp-async"        # receiver followed the sender's backend too
+
+
+def test_wire_compat_mode():
+    # bare reference framing: 8-byte BE stream id preamble, sockaddr-only handle
+    _check(run_pair(["--abi", "4", "--sizes", "0,8,1048577", "--inflight", "4", "--rounds", "1"],
+                    env={"BNET_WIRE_COMPAT": "1", "BNET_NVL": "0"}), "tcp-threads")
+
+
+def test_nvl_shared_memory_host_buffers():
+    _check(run_pair(["--sizes", SIZES + ",9437184", "--inflight", "8", "--rounds", "2"],
+                    env={"BNET_NVL": "1", "BNET_SHM_RING_BYTES": "1048576"}), "nvl")
+
+
+def test_nvl_direct_path_with_emulated_device_memory():
+    # regMr(NCCL_PTR_CUDA) export/import, FIFO matching and per-chunk completion words,
+    # with "device memory" emulated by shm segments (BNET_FAKE_CUDA=1)
+    outs = _check(run_pair(["--mem", "fakecuda", "--sizes", "0,1,8,4096,1048577,3145729", "--inflight", "8",
+                            "--rounds", "2"], env={"BNET_NVL": "1", "BNET_FAKE_CUDA": "1"}), "nvl")
+    assert outs[0][1]["messages"] == 96
+
+
+def test_cuda_pointers_over_tcp_are_staged():
+    _check(run_pair(["--mem", "fakecuda", "--sizes", "1,4096,1048577,3145729", "--inflight", "4", "--rounds", "1"],
+                    env={"BNET_NVL": "0", "BNET_FAKE_CUDA": "1"}), "tcp-threads")
+    _check(run_pair(["--mem", "fakecuda", "--sizes", "1,4096,1048577", "--inflight", "4", "--rounds", "1"],
+                    env={"BNET_NVL": "0", "BNET_FAKE_CUDA": "1", "BAGUA_NET_IMPLEMENT": "TOKIO"}), "tcp-async")
+
+
+@pytest.mark.parametrize("env", [{"BNET_NVL": "0"}, {"BNET_NVL": "0", "BAGUA_NET_IMPLEMENT": "TOKIO"},
+                                 {"BNET_NVL": "1"}])
+def test_peer_death_is_an_error_not_a_hang(env):
+    # fault injection the reference lacks (data-stream errors hang there)
+    outs = run_pair(["--sizes", "4194304", "--inflight", "8", "--rounds", "4", "--die-after", "9"],
+                    env=dict(env, BNET_SHM_RING_BYTES="262144"), timeout=60)
+    rc, res, err = outs[0]          # receiver
+    assert res is not None and not res["ok"], (res, err[-1000:])
+    assert res["code"] in (2, 6), res      # ncclSystemError / ncclRemoteError
+
+
+def test_injected_stream_failure_surfaces_in_test():
+    outs = run_pair(["--sizes", "2097152", "--inflight", "4", "--rounds", "3"],
+                    env={"BNET_NVL": "0", "BNET_FAULT_INJECT": "send_drop_after=3", "BAGUA_NET_MIN_CHUNKSIZE": "65536"},
+                    timeout=60)
+    assert any(res is not None and not res["ok"] for _, res, _ in outs)

@@ -1,0 +1,92 @@
+"""Unit tests of the OS utilities — same cases as the reference's only unit tests
+(reference: src/utils.rs:263-314 test_parse / test_socket_handle / test_chunks) plus the
+NIC-filter syntax and chunking invariants SURVEY.md §4 asks for."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from bagua_net_b200 import utils
+
+
+def test_parse_user_pass_addr():
+    assert utils.parse_user_pass_and_addr("nagle:1984@127.0.0.1:9090") == ("nagle", "1984", "127.0.0.1:9090")
+    assert utils.parse_user_pass_and_addr("127.0.0.1:9090") == ("", "", "127.0.0.1:9090")
+    assert utils.parse_user_pass_and_addr("") is None
+    assert utils.parse_user_pass_and_addr("has space:1") is None
+
+
+def test_socket_handle_roundtrip():
+    # sockaddr -> 64-byte NCCL handle -> sockaddr (reference test_socket_handle: 127.0.0.1:8123)
+    assert utils.sockaddr_roundtrip("127.0.0.1:8123") == "127.0.0.1:8123"
+    # the reference truncates IPv6 at the FFI (src/lib.rs:157-158); ours fits
+    assert utils.sockaddr_roundtrip("[fe80::1]:4242") == "[fe80::1]:4242"
+
+
+def test_chunks_reference_cases():
+    assert utils.chunk_count(1024, 1, 20) == 20
+    assert utils.chunk_count(1024, 1000, 20) == 2
+
+
+@pytest.mark.parametrize("total", [1, 15, 16, 4097, 1 << 20, (1 << 20) + 1, 123456789])
+@pytest.mark.parametrize("minc", [1, 4096, 65535, 1 << 20])
+@pytest.mark.parametrize("n", [1, 2, 3, 8])
+def test_chunk_invariants(total, minc, n):
+    cs = utils.chunk_size(total, minc, n)
+    assert cs >= minc and cs * n >= total
+    cnt = utils.chunk_count(total, minc, n)
+    assert 1 <= cnt <= n                          # never more chunks than streams
+    assert (cnt - 1) * cs < total <= cnt * cs     # both ends compute the same split
+
+
+def test_if_filter_syntax():
+    f = utils.if_filter_accepts
+    assert not f("^docker,lo", "lo") and not f("^docker,lo", "docker0") and f("^docker,lo", "eth0")
+    assert f("eth", "eth0") and f("eth", "eth1") and not f("eth", "ib0")      # prefix include
+    assert f("=eth0", "eth0") and not f("=eth0", "eth01")                      # exact
+    assert f("eth0,ib", "ib3") and not f("eth0,ib", "enp1s0")
+    assert f("^=lo", "lo0") and not f("^=lo", "lo")
+
+
+def test_find_interfaces_falls_back_to_loopback():
+    env = dict(os.environ, NCCL_SOCKET_IFNAME="^docker,eth,en,ib,wl,ifb,veth,br")
+    code = ("import json; from bagua_net_b200 import utils; print(json.dumps(utils.find_interfaces()))")
+    env["PYTHONPATH"] = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout
+    # explicit user filter that excludes everything -> empty list, no silent fallback
+    assert isinstance(json.loads(out), list)
+    devs = utils.find_interfaces("lo")
+    assert [d["name"] for d in devs] == ["lo"] and devs[0]["loopback"]
+    assert devs[0]["speed"] == 10000          # default when sysfs has no speed (reference utils.rs:8)
+    assert utils.find_interfaces("=doesnotexist0") == []
+    v4 = utils.find_interfaces("lo", 2)
+    assert v4 and v4[0]["addr"].startswith("127.0.0.1")
+
+
+def test_base64_for_basic_auth():
+    assert utils.base64("user:pass") == "dXNlcjpwYXNz"
+    assert utils.base64("a") == "YQ==" and utils.base64("ab") == "YWI=" and utils.base64("") == ""
+
+
+def test_config_env_aliases():
+    env_code = "from bagua_net_b200 import utils; import json; print(json.dumps(utils.config()))"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def cfg(**env):
+        e = {k: v for k, v in os.environ.items() if not k.startswith(("BNET_", "BAGUA_NET_"))}
+        e.update(env, PYTHONPATH=root)
+        return json.loads(subprocess.run([sys.executable, "-c", env_code], env=e, capture_output=True, text=True,
+                                         check=True).stdout)
+
+    d = cfg()
+    assert d["implement"] == "BASIC" and d["nstreams"] == 2 and d["min_chunksize"] == 1048576   # reference defaults
+    d = cfg(BAGUA_NET_IMPLEMENT="tokio")
+    assert d["implement"] == "TOKIO" and d["min_chunksize"] == 65535
+    d = cfg(BAGUA_NET_NSTREAMS="8", BAGUA_NET_MIN_CHUNKSIZE="4096", RANK="3")
+    assert d["nstreams"] == 8 and d["min_chunksize"] == 4096 and d["rank"] == 3
+    d = cfg(BNET_NSTREAMS="4", BAGUA_NET_NSTREAMS="8")          # BNET_* wins over the legacy name
+    assert d["nstreams"] == 4
+    d = cfg(BAGUA_NET_NSTREAMS="banana")                          # malformed: default, no abort
+    assert d["nstreams"] == 2
