@@ -1,0 +1,57 @@
+"""VGG family (the reference's headline benchmark model is VGG16: reference README.md:52-84)."""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+CFGS = {
+    "vgg11": [64, "M", 128, "M", 256, 256, "M", 512, 512, "M", 512, 512, "M"],
+    "vgg13": [64, 64, "M", 128, 128, "M", 256, 256, "M", 512, 512, "M", 512, 512, "M"],
+    "vgg16": [64, 64, "M", 128, 128, "M", 256, 256, 256, "M", 512, 512, 512, "M", 512, 512, 512, "M"],
+    "vgg19": [64, 64, "M", 128, 128, "M", 256, 256, 256, 256, "M", 512, 512, 512, 512, "M", 512, 512, 512, 512, "M"],
+}
+
+
+class VGG(nn.Module):
+    def __init__(self, cfg="vgg16", num_classes: int = 1000, batch_norm: bool = False, dropout: float = 0.5,
+                 width_div: int = 1, fc_dim: int = 4096, image_size: int = 224):
+        super().__init__()
+        layers, cin = [], 3
+        for v in CFGS[cfg] if isinstance(cfg, str) else cfg:
+            if v == "M":
+                layers.append(nn.MaxPool2d(2, 2))
+            else:
+                cout = max(8, v // width_div)
+                layers.append(nn.Conv2d(cin, cout, 3, padding=1))
+                if batch_norm:
+                    layers.append(nn.BatchNorm2d(cout))
+                layers.append(nn.ReLU(inplace=True))
+                cin = cout
+        self.features = nn.Sequential(*layers)
+        side = image_size // 32
+        self.avgpool = nn.AdaptiveAvgPool2d((side, side)) if image_size % 32 else nn.Identity()
+        self.classifier = nn.Sequential(
+            nn.Linear(cin * side * side, fc_dim), nn.ReLU(True), nn.Dropout(dropout),
+            nn.Linear(fc_dim, fc_dim), nn.ReLU(True), nn.Dropout(dropout),
+            nn.Linear(fc_dim, num_classes),
+        )
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+                nn.init.zeros_(m.bias)
+            elif isinstance(m, nn.Linear):
+                nn.init.normal_(m.weight, 0, 0.01)
+                nn.init.zeros_(m.bias)
+
+    def forward(self, x):
+        x = self.features(x)
+        x = self.avgpool(x)
+        return self.classifier(torch.flatten(x, 1))
+
+
+def vgg16(**kw) -> VGG:
+    return VGG("vgg16", **kw)
+
+
+def vgg19(**kw) -> VGG:
+    return VGG("vgg19", **kw)

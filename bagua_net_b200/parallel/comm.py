@@ -1,0 +1,209 @@
+"""SymmComm — symmetric-memory communicator over the native bnet collectives.
+
+One process per GPU.  Every rank allocates the same-sized heap with the CUDA VMM API,
+the allocations are exchanged as POSIX fds and mapped into every peer (NVLink P2P), and —
+when the fabric exposes it — bound to one multicast object so that the sm_100a kernels
+can reduce inside the NVSwitch (multimem.ld_reduce) and broadcast through it
+(multimem.st).  ``torch.distributed`` is only the control plane that carries the
+128-byte handshake blobs (csrc/cuda/coll.cu, include/bnet/bnet_coll.h).
+
+This is the intra-box data path the reference does not have: it is a TCP-only,
+host-memory transport (reference: nthread_per_socket_backend.rs:252) that leaves the
+reduction to NCCL's kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+import torch.distributed as dist
+
+from ..utils.native import load
+
+DT = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+OPS = {"sum": 0, "avg": 1, "max": 2, "min": 3}
+ALGOS = {"auto": 0, "nvls": 1, "p2p": 2, "oneshot": 3}
+BLOB = 128
+
+
+class _CudaView:
+    """Minimal __cuda_array_interface__ carrier so torch can wrap native memory zero-copy."""
+
+    def __init__(self, ptr: int, nbytes: int, owner):
+        self.__cuda_array_interface__ = {
+            "shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3, "strides": None,
+        }
+        self._owner = owner
+
+
+def _declare(lib):
+    vp, sz, i = C.c_void_p, C.c_size_t, C.c_int
+    lib.bnet_coll_create.argtypes = [i, i, i, sz, C.POINTER(vp)]
+    lib.bnet_coll_export.argtypes = [vp, C.c_char_p]
+    lib.bnet_coll_import.argtypes = [vp, C.c_char_p]
+    lib.bnet_coll_mc_add_device.argtypes = [vp]
+    lib.bnet_coll_mc_bind.argtypes = [vp]
+    lib.bnet_coll_destroy.argtypes = [vp]
+    lib.bnet_coll_heap.restype = vp
+    lib.bnet_coll_heap.argtypes = [vp]
+    lib.bnet_coll_heap_bytes.restype = sz
+    lib.bnet_coll_heap_bytes.argtypes = [vp]
+    lib.bnet_coll_peer_heap.restype = vp
+    lib.bnet_coll_peer_heap.argtypes = [vp, i]
+    lib.bnet_coll_mc_heap.restype = vp
+    lib.bnet_coll_mc_heap.argtypes = [vp]
+    lib.bnet_coll_has_multicast.argtypes = [vp]
+    lib.bnet_coll_status.restype = C.c_uint
+    lib.bnet_coll_status.argtypes = [vp]
+    lib.bnet_coll_last_error.restype = C.c_char_p
+    lib.bnet_allreduce.argtypes = [vp, sz, sz, i, i, i, i, i, vp]
+    lib.bnet_allreduce_oneshot.argtypes = [vp, sz, vp, sz, i, i, i, i, vp]
+    lib.bnet_barrier.argtypes = [vp, i, vp]
+    lib.bnet_fused_allreduce_sgd.argtypes = [vp, sz, sz, sz, i, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp,
+                                             i, i, i, vp]
+    lib.bnet_pack_cast.argtypes = [vp, i, vp, i, i, C.c_float, C.c_uint64, vp]
+
+
+class SymmComm:
+    """Symmetric heap + kernels.  ``group`` defaults to the world group; without an initialised
+    process group the communicator is single-rank (the fused kernels still run — no peers)."""
+
+    def __init__(self, heap_bytes: int, device: int | None = None, group=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("bagua_net_b200 collectives need a CUDA device (sm_100a); none is visible")
+        self.lib = load()
+        _declare(self.lib)
+        self.group = group
+        if dist.is_available() and dist.is_initialized():
+            self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        else:
+            self.rank, self.world = 0, 1
+        self.device = torch.cuda.current_device() if device is None else device
+        torch.cuda.set_device(self.device)
+        self.launches = 0          # number of OUR kernels launched through this communicator
+        h = C.c_void_p()
+        self._chk(self.lib.bnet_coll_create(self.rank, self.world, self.device, heap_bytes, C.byref(h)), "create")
+        self.h = h
+        if self.world > 1:
+            blob = C.create_string_buffer(BLOB)
+            self._chk(self.lib.bnet_coll_export(self.h, blob), "export")
+            blobs = [None] * self.world
+            dist.all_gather_object(blobs, bytes(blob.raw), group=group)
+            self._chk(self.lib.bnet_coll_import(self.h, b"".join(blobs)), "import")
+            # multicast: every rank must reach the same verdict before binding
+            ok = self.lib.bnet_coll_mc_add_device(self.h) == 0
+            ok = self._agree(ok)
+            if ok:
+                ok = self.lib.bnet_coll_mc_bind(self.h) == 0
+                ok = self._agree(ok)
+            if not ok and self.lib.bnet_coll_has_multicast(self.h):
+                raise RuntimeError("ranks disagree on multicast availability")
+            dist.barrier(group=group)
+        self.heap_bytes = int(self.lib.bnet_coll_heap_bytes(self.h))
+        self.heap_ptr = int(self.lib.bnet_coll_heap(self.h))
+        self.has_multicast = bool(self.lib.bnet_coll_has_multicast(self.h))
+        self._heap = torch.as_tensor(_CudaView(self.heap_ptr, self.heap_bytes, self), device=f"cuda:{self.device}")
+        self._bump = 0
+
+    # ------------------------------------------------------------------ plumbing
+    def _chk(self, rc, what):
+        if rc is not None and rc < 0:
+            raise RuntimeError(f"bnet coll {what} failed: {self.lib.bnet_coll_last_error().decode()}")
+        return rc
+
+    def _agree(self, ok: bool) -> bool:
+        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=f"cuda:{self.device}")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+        return bool(t.item())
+
+    def close(self):
+        if getattr(self, "h", None):
+            torch.cuda.synchronize(self.device)
+            self._heap = None
+            self.lib.bnet_coll_destroy(self.h)
+            self.h = None
+
+    def status(self) -> int:
+        """0 = healthy; non-zero after a device-side watchdog trip (a peer never arrived)."""
+        return int(self.lib.bnet_coll_status(self.h))
+
+    # ------------------------------------------------------------------ heap tensors
+    def alloc(self, numel: int, dtype: torch.dtype, align: int = 256) -> torch.Tensor:
+        """Bump-allocate a tensor inside the symmetric heap (same offset on every rank when every
+        rank performs the same sequence of calls)."""
+        es = torch.empty((), dtype=dtype).element_size()
+        # keep every allocation a whole number of 16-byte vectors per rank
+        quantum = max(align, 16 * self.world)
+        off = (self._bump + quantum - 1) // quantum * quantum
+        nbytes = (numel * es + quantum - 1) // quantum * quantum
+        if off + nbytes > self.heap_bytes:
+            raise MemoryError(f"symmetric heap exhausted: need {off + nbytes} of {self.heap_bytes} bytes")
+        self._bump = off + nbytes
+        return self._heap[off:off + numel * es].view(dtype)
+
+    def offset_of(self, t: torch.Tensor) -> int:
+        off = t.data_ptr() - self.heap_ptr
+        if off < 0 or off + t.numel() * t.element_size() > self.heap_bytes:
+            raise ValueError("tensor does not live in the symmetric heap; use comm.alloc()")
+        return off
+
+    def peer_tensor(self, t: torch.Tensor, peer: int) -> torch.Tensor:
+        """The same heap range as ``t`` on another rank (NVLink peer mapping)."""
+        base = int(self.lib.bnet_coll_peer_heap(self.h, peer))
+        nbytes = t.numel() * t.element_size()
+        v = torch.as_tensor(_CudaView(base + self.offset_of(t), nbytes, self), device=f"cuda:{self.device}")
+        return v.view(t.dtype).view(t.shape)
+
+    # ------------------------------------------------------------------ collectives
+    def _stream(self, stream):
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        return C.c_void_p(s.cuda_stream)
+
+    def all_reduce(self, t: torch.Tensor, op: str = "sum", algo: str = "auto", channel: int = 1, nblocks: int = 0,
+                   stream=None) -> torch.Tensor:
+        """In-place all-reduce of a heap tensor.  numel*elsize must be a multiple of 16*world."""
+        n = self._chk(self.lib.bnet_allreduce(self.h, self.offset_of(t), t.numel(), DT[t.dtype], OPS[op], ALGOS[algo],
+                                              channel, nblocks, self._stream(stream)), "all_reduce")
+        self.launches += n
+        return t
+
+    def all_reduce_oneshot(self, t: torch.Tensor, out: torch.Tensor, op: str = "sum", channel: int = 1,
+                           nblocks: int = 0, stream=None) -> torch.Tensor:
+        assert out.is_contiguous() and out.numel() == t.numel() and out.dtype == t.dtype
+        n = self._chk(self.lib.bnet_allreduce_oneshot(self.h, self.offset_of(t), C.c_void_p(out.data_ptr()), t.numel(),
+                                                      DT[t.dtype], OPS[op], channel, nblocks, self._stream(stream)),
+                      "all_reduce_oneshot")
+        self.launches += n
+        return out
+
+    def barrier(self, channel: int = 2, stream=None):
+        self.launches += self._chk(self.lib.bnet_barrier(self.h, channel, self._stream(stream)), "barrier")
+
+    def fused_allreduce_sgd(self, grad: torch.Tensor, param: torch.Tensor, master: torch.Tensor, mom: torch.Tensor,
+                            lr: float, momentum: float, weight_decay: float, grad_scale: float | None = None,
+                            zero_grads: bool = True, channel: int = 0, nblocks: int = 0, stream=None):
+        """One kernel: mean-reduce ``grad`` across ranks, SGD-update this rank's fp32 shard
+        (``master``/``mom``: numel/world each) and write the new ``param`` on every rank."""
+        assert grad.numel() == param.numel() and grad.dtype == param.dtype
+        assert master.dtype == torch.float32 and mom.dtype == torch.float32
+        assert master.numel() * self.world == grad.numel() == mom.numel() * self.world
+        gs = (1.0 / self.world) if grad_scale is None else grad_scale
+        n = self._chk(self.lib.bnet_fused_allreduce_sgd(
+            self.h, self.offset_of(grad), self.offset_of(param), grad.numel(), DT[grad.dtype], lr, momentum,
+            weight_decay, gs, C.c_void_p(master.data_ptr()), C.c_void_p(mom.data_ptr()), 1 if zero_grads else 0,
+            channel, nblocks, self._stream(stream)), "fused_allreduce_sgd")
+        self.launches += n
+
+
+def init_process_group_from_env(backend: str | None = None):
+    """torch.distributed bootstrap for one-process-per-GPU launches (torchrun env)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1 or dist.is_initialized():
+        return
+    local = int(os.environ.get("LOCAL_RANK", os.environ.get("RANK", "0")))
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29511")
+    dist.init_process_group(backend or ("nccl" if torch.cuda.is_available() else "gloo"))

@@ -1,0 +1,181 @@
+"""Data-parallel training engine on top of the fused bnet kernels.
+
+The reference accelerates PyTorch/Bagua DDP by moving NCCL's all-reduce traffic faster
+(reference README.md:52-84).  Here the data-parallel step itself is re-designed for an
+NVSwitch box:
+
+* parameters and gradients live in flat buffers inside the symmetric heap; ``p.data`` and
+  ``p.grad`` are views, so autograd accumulates straight into communication memory (no
+  bucket copy-in/copy-out);
+* when the last gradient of a bucket has been produced, ONE kernel on a side stream
+  reduces the bucket in the switch (NVLS), applies SGD+momentum+weight-decay on the owning
+  rank's fp32 master shard, writes the new bf16 parameters to every rank and re-zeroes the
+  gradients — overlapping the rest of the backward pass;
+* optimizer state is sharded 1/world (ZeRO-1 style) for free.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from .comm import SymmComm
+
+
+class _Bucket:
+    __slots__ = ("params", "start", "numel", "ready", "grad", "param", "master", "mom")
+
+    def __init__(self):
+        self.params = []
+        self.start = 0
+        self.numel = 0
+        self.ready = 0
+
+
+class BnetDDP(torch.nn.Module):
+    """Wraps ``module``; owns the optimizer (SGD with momentum, fused into the collective).
+
+    bucket_mb sizes buckets for launch latency and overlap (NVSwitch: no per-link bound).
+    """
+
+    def __init__(self, module: torch.nn.Module, lr: float = 0.01, momentum: float = 0.9, weight_decay: float = 0.0,
+                 bucket_mb: float = 64.0, comm: SymmComm | None = None, extra_heap_bytes: int = 64 << 20,
+                 nblocks: int = 0, group=None):
+        super().__init__()
+        self.module = module
+        self.lr, self.momentum, self.weight_decay = lr, momentum, weight_decay
+        self.nblocks = nblocks
+        params = [p for p in module.parameters() if p.requires_grad]
+        if not params:
+            raise ValueError("module has no trainable parameters")
+        dtype = params[0].dtype
+        if any(p.dtype != dtype for p in params):
+            raise ValueError("BnetDDP expects a single parameter dtype (bf16 or fp32)")
+        if dtype not in (torch.bfloat16, torch.float32):
+            raise ValueError(f"unsupported parameter dtype {dtype}")
+        self.dtype = dtype
+        es = params[0].element_size()
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        quantum = 16 * world // es * 8           # elements: whole 16-byte vectors per rank, generously aligned
+        # gradients become ready roughly in reverse registration order: bucket in that order
+        cap = int(bucket_mb * (1 << 20)) // es
+        self.buckets: list[_Bucket] = []
+        cur = _Bucket()
+        offset = 0
+        layout = []
+        for p in reversed(params):
+            n = p.numel()
+            if cur.params and cur.numel + n > cap:
+                cur.numel = (cur.numel + quantum - 1) // quantum * quantum
+                offset += cur.numel
+                self.buckets.append(cur)
+                cur = _Bucket()
+                cur.start = offset
+            layout.append((p, cur, cur.start + cur.numel))
+            cur.params.append(p)
+            cur.numel += (n + 7) // 8 * 8        # keep every tensor 16-byte aligned inside the flat buffer
+        cur.numel = (cur.numel + quantum - 1) // quantum * quantum
+        offset += cur.numel
+        self.buckets.append(cur)
+        total = offset
+
+        dev = params[0].device
+        if comm is None:
+            comm = SymmComm(2 * total * es + extra_heap_bytes + (1 << 20), device=dev.index, group=group)
+        self.comm = comm
+        self.flat_param = comm.alloc(total, dtype)
+        self.flat_grad = comm.alloc(total, dtype)
+        self.flat_param.zero_()
+        self.flat_grad.zero_()
+        def shaped(flat, off, p):
+            # keep a channels_last parameter channels_last inside the flat buffer (cuDNN's
+            # preferred filter layout on tensor cores): same bytes, permuted view
+            seg = flat[off:off + p.numel()]
+            if p.dim() == 4 and not p.is_contiguous() and p.is_contiguous(memory_format=torch.channels_last):
+                n, c, h, w = p.shape
+                return seg.view(n, h, w, c).permute(0, 3, 1, 2)
+            return seg.view(p.shape)
+
+        with torch.no_grad():
+            for p, b, off in layout:
+                view = shaped(self.flat_param, off, p)
+                view.copy_(p.data)
+                p.data = view
+                p.grad = shaped(self.flat_grad, off, p)
+        self._param_bucket = {id(p): b for p, b, _ in layout}
+        # identical start on every rank (like DDP's initial broadcast): rank 0 wins, through our own all-reduce
+        if comm.world > 1:
+            if comm.rank != 0:
+                self.flat_param.zero_()
+            torch.cuda.synchronize()
+            dist.barrier(group=group)
+            comm.all_reduce(self.flat_param, "sum")
+            torch.cuda.synchronize()
+        # fp32 master weights + momentum for this rank's shard of every bucket
+        for b in self.buckets:
+            b.grad = self.flat_grad[b.start:b.start + b.numel]
+            b.param = self.flat_param[b.start:b.start + b.numel]
+            shard = b.numel // comm.world
+            b.master = b.param[comm.rank * shard:(comm.rank + 1) * shard].float().contiguous()
+            b.mom = torch.zeros_like(b.master)
+        self.comm_stream = torch.cuda.Stream(device=dev, priority=-1)
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in params]
+        self._inflight = False
+        torch.cuda.synchronize()
+        if comm.world > 1:
+            dist.barrier(group=group)
+
+    # ------------------------------------------------------------------ autograd integration
+    def _on_grad(self, p: torch.Tensor):
+        b = self._param_bucket[id(p)]
+        b.ready += 1
+        if b.ready == len(b.params):
+            self._launch(b)
+
+    def _launch(self, b: _Bucket):
+        cur = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self.comm_stream.wait_event(ev)          # the bucket's gradients are complete on the compute stream
+        self.comm.fused_allreduce_sgd(b.grad, b.param, b.master, b.mom, self.lr, self.momentum, self.weight_decay,
+                                      zero_grads=True, channel=0, nblocks=self.nblocks, stream=self.comm_stream)
+        b.ready = 0
+        self._inflight = True
+
+    def finish_step(self):
+        """Make the updated parameters visible to the compute stream (call after backward)."""
+        for b in self.buckets:
+            if b.ready:                           # parameters that got no gradient this step
+                self._launch(b)
+        if self._inflight:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+            self._inflight = False
+
+    # ------------------------------------------------------------------ user API
+    def forward(self, *args, **kwargs):
+        return self.module(*args, **kwargs)
+
+    def train_step(self, inputs: torch.Tensor, targets: torch.Tensor, loss_fn=None) -> torch.Tensor:
+        """forward + backward + fused all-reduce/optimizer.  Returns the (device) loss tensor."""
+        loss_fn = loss_fn or torch.nn.functional.cross_entropy
+        out = self.module(inputs)
+        loss = loss_fn(out.float(), targets)
+        loss.backward()
+        self.finish_step()
+        return loss.detach()
+
+    def train_step_from_host(self, inputs_pinned: torch.Tensor, targets_pinned: torch.Tensor, loss_fn=None) -> float:
+        """End-to-end step as a user runs it: H2D copy of this step's batch from pinned host
+        memory, train_step, D2H read of the loss."""
+        dev = self.flat_param.device
+        x = inputs_pinned.to(dev, non_blocking=True)
+        y = targets_pinned.to(dev, non_blocking=True)
+        if x.dim() == 4:
+            x = x.contiguous(memory_format=torch.channels_last)
+        return float(self.train_step(x, y, loss_fn).item())
+
+    def set_lr(self, lr: float):
+        self.lr = lr
+
+    @property
+    def kernel_launches(self) -> int:
+        return self.comm.launches

@@ -1,0 +1,44 @@
+"""Environment helpers: how to make NCCL load the bnet plugin.
+
+The reference documents one step — put the directory holding libnccl-net.so on
+LD_LIBRARY_PATH and look for "NCCL INFO Using network BaguaNet" (reference
+README.md:32-45).  Inside one NVSwitch box NCCL would never use a network plugin on
+its own (it picks P2P/NVLS/SHM), so ``force_net`` also disables those transports —
+that is how a net plugin is exercised on a single node.
+"""
+from __future__ import annotations
+
+import os
+
+from .. import LIB_DIR
+
+
+def nccl_plugin_env(plugin: str = "bnet", force_net: bool = False, gdr: bool = True, debug: bool = False,
+                    extra: dict | None = None) -> dict:
+    """Environment variables (as a dict) that make NCCL >= 2.2x dlopen our plugin.
+
+    plugin: "bnet" -> libnccl-net-bnet.so (tables v3..v8); "bnetx" adds the v9/v10 tables.
+    """
+    ld = os.environ.get("LD_LIBRARY_PATH", "")
+    env = {
+        "LD_LIBRARY_PATH": LIB_DIR + (os.pathsep + ld if ld else ""),
+        "NCCL_NET_PLUGIN": plugin,
+        "NCCL_NET": "BNet",
+    }
+    if force_net:
+        env.update({"NCCL_P2P_DISABLE": "1", "NCCL_SHM_DISABLE": "1", "NCCL_NVLS_ENABLE": "0",
+                    "NCCL_NET_DISABLE_INTRA": "0"})
+    if gdr:
+        # our "NIC" is the NVLink fabric: let NCCL hand us device pointers wherever the GPU sits
+        env.update({"NCCL_NET_GDR_LEVEL": "SYS", "NCCL_NET_GDR_READ": "1", "NCCL_DMABUF_ENABLE": "0"})
+    else:
+        env["BNET_GDR"] = "0"
+    if debug:
+        env.update({"NCCL_DEBUG": "INFO", "NCCL_DEBUG_SUBSYS": "INIT,NET,ENV"})
+    if extra:
+        env.update(extra)
+    return env
+
+
+def apply(env: dict) -> None:
+    os.environ.update(env)

@@ -243,11 +243,23 @@ void release_export(MemExport* e) {
   }
 }
 
+struct ImportKey {
+  uint64_t pid, base;
+  int dev;
+  bool operator<(const ImportKey& o) const {
+    return pid != o.pid ? pid < o.pid : (base != o.base ? base < o.base : dev < o.dev);
+  }
+};
 struct ImportCookie {
   CUmemGenericAllocationHandle h;
   size_t size;
   bool vmm;
+  void* base;
+  int refs;
+  ImportKey key;
 };
+static std::mutex g_import_mu;
+static std::map<ImportKey, ImportCookie*> g_imports;
 
 int import_memory(const MemExport& e, int local_fd, int dev, void** base_out, void** cookie_out) {
   *base_out = nullptr;
@@ -287,6 +299,19 @@ int import_memory(const MemExport& e, int local_fd, int dev, void** base_out, vo
     *base_out = (void*)e.alloc_base;
     return 0;
   }
+  // One mapping per (exporter, allocation, importing device) and process: many registered
+  // buffers usually live in the same allocation, and a CUDA IPC handle must not be opened twice.
+  ImportKey key{e.pid, e.alloc_base, dev};
+  {
+    std::lock_guard<std::mutex> lk(g_import_mu);
+    auto it = g_imports.find(key);
+    if (it != g_imports.end()) {
+      it->second->refs++;
+      *base_out = it->second->base;
+      *cookie_out = it->second;
+      return 0;
+    }
+  }
   if (e.kind == EXPORT_CUDA_IPC) {
     cudaIpcMemHandle_t ipc;
     memcpy(&ipc, e.ipc, sizeof(ipc));
@@ -297,7 +322,9 @@ int import_memory(const MemExport& e, int local_fd, int dev, void** base_out, vo
       BNET_INFO("cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(err));
       return -1;
     }
-    ImportCookie* c = new ImportCookie{0, (size_t)e.alloc_size, false};
+    ImportCookie* c = new ImportCookie{0, (size_t)e.alloc_size, false, p, 1, key};
+    std::lock_guard<std::mutex> lk(g_import_mu);
+    g_imports[key] = c;
     *base_out = p;
     *cookie_out = c;
     return 0;
@@ -336,8 +363,11 @@ int import_memory(const MemExport& e, int local_fd, int dev, void** base_out, vo
       d.MemRelease(h);
       return -1;
     }
+    ImportCookie* c = new ImportCookie{h, sz, true, (void*)va, 1, key};
+    std::lock_guard<std::mutex> lk(g_import_mu);
+    g_imports[key] = c;
     *base_out = (void*)va;
-    *cookie_out = new ImportCookie{h, sz, true};
+    *cookie_out = c;
     return 0;
   }
   return -1;
@@ -350,6 +380,11 @@ void release_import(const MemExport& e, void* base, void* cookie) {
   }
   ImportCookie* c = (ImportCookie*)cookie;
   if (!c) return;
+  {
+    std::lock_guard<std::mutex> lk(g_import_mu);
+    if (--c->refs > 0) return;
+    g_imports.erase(c->key);
+  }
   if (c->vmm) {
     const DriverApi& d = driver();
     d.MemUnmap((CUdeviceptr)base, c->size);

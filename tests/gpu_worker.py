@@ -1,0 +1,345 @@
+"""Per-rank bodies of the GPU tests (launched by tests/test_gpu.py, one process per GPU)."""
+from __future__ import annotations
+
+import os
+import sys
+import time
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+RANK = int(os.environ.get("RANK", "0"))
+WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+LOCAL = int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def setup(backend="nccl"):
+    torch.cuda.set_device(LOCAL)
+    if WORLD > 1:
+        dist.init_process_group(backend)
+
+
+def teardown():
+    if WORLD > 1 and dist.is_initialized():
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------ executor (transport kernels)
+def job_executor():
+    from bagua_net_b200.ops import P2PExecutor
+    from bagua_net_b200.utils import native
+
+    torch.cuda.set_device(0)
+    ex = P2PExecutor(0)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    # copy: sizes around vector/chunk boundaries, unaligned offsets on both sides
+    for n in [1, 15, 16, 17, 4095, 65536, 262144 + 3, 1 << 20, (4 << 20) + 13, 32 << 20]:
+        for so, do in [(0, 0), (1, 1), (3, 7), (16, 4)]:
+            src = torch.randint(0, 256, (n + 64,), device="cuda", dtype=torch.uint8, generator=g)
+            dst = torch.zeros(n + 64, device="cuda", dtype=torch.uint8)
+            ex.run("copy", src[so:so + n], dst[do:do + n])
+            torch.cuda.synchronize()
+            assert torch.equal(dst[do:do + n], src[so:so + n]), f"copy mismatch n={n} so={so} do={do}"
+            assert int(dst[:do].sum()) == 0 and int(dst[do + n:].sum()) == 0, f"copy wrote outside n={n}"
+    # many jobs in flight (queue depth, round-robin over clusters)
+    srcs = [torch.randn(100003 + 17 * i, device="cuda") for i in range(40)]
+    dsts = [torch.empty_like(s) for s in srcs]
+    tickets = [ex.submit("copy", s, d) for s, d in zip(srcs, dsts)]
+    for t in tickets:
+        ex.wait(t)
+    torch.cuda.synchronize()
+    for s, d in zip(srcs, dsts):
+        assert torch.equal(s, d)
+    # fused accumulate / cast vs fp32 reference
+    for n in [8, 1000, 4096, (1 << 20) + 8]:
+        a = torch.randn(n, device="cuda")
+        b = torch.randn(n, device="cuda")
+        ref = a + b
+        ex.run("red_add_f32", a, b)              # b += a
+        torch.cuda.synchronize()
+        assert torch.allclose(b, ref, rtol=0, atol=1e-6), "red_add_f32"
+        h = torch.randn(n, device="cuda").to(torch.bfloat16)
+        f = torch.empty(n, device="cuda")
+        ex.run("cast_bf16_to_f32", h, f)
+        torch.cuda.synchronize()
+        assert torch.equal(f, h.float()), "cast_bf16_to_f32"
+        h2 = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+        ex.run("cast_f32_to_bf16", a, h2)
+        torch.cuda.synchronize()
+        assert torch.equal(h2, a.to(torch.bfloat16)), "cast_f32_to_bf16"
+        acc = torch.randn(n, device="cuda")
+        ref = acc + h.float()
+        ex.run("acc_bf16_to_f32", h, acc)        # acc += float(h): move + cast + accumulate in one pass
+        torch.cuda.synchronize()
+        assert torch.allclose(acc, ref, rtol=0, atol=1e-6), "acc_bf16_to_f32"
+        x = torch.randn(n, device="cuda").to(torch.bfloat16)
+        y = torch.randn(n, device="cuda").to(torch.bfloat16)
+        ref = (x.float() + y.float())
+        ex.run("red_add_bf16", x, y)
+        torch.cuda.synchronize()
+        assert torch.allclose(y.float(), ref, rtol=1e-2, atol=1e-2), "red_add_bf16"
+    # bandwidth line (device-local copy through the transport kernel)
+    big = torch.empty(256 << 20, device="cuda", dtype=torch.uint8).random_(0, 255)
+    out = torch.empty_like(big)
+    ex.run("copy", big, out)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        ex.run("copy", big, out)
+    dt = (time.perf_counter() - t0) / 5
+    print(f"executor env={ {k: v for k, v in os.environ.items() if k.startswith('BNET_')} } "
+          f"local copy {big.numel() / dt / 1e9:.1f} GB/s (x2 traffic) stats={native.exec_stats()}", flush=True)
+
+
+def job_executor_idle():
+    from bagua_net_b200.ops import P2PExecutor
+    from bagua_net_b200.utils import native
+
+    torch.cuda.set_device(0)
+    ex = P2PExecutor(0)
+    a = torch.randn(1 << 16, device="cuda")
+    b = torch.empty_like(a)
+    for i in range(6):
+        b.zero_()
+        ex.run("copy", a, b)
+        torch.cuda.synchronize()                 # returns only after the parked kernel has left
+        assert torch.equal(a, b)
+        time.sleep(0.01)                         # > idle timeout: next job needs a relaunch
+    st = native.exec_stats()
+    assert st["launches"] >= 3, st
+    print("idle/relaunch ok", st, flush=True)
+
+
+# ------------------------------------------------------------------ fused SGD
+def _sgd_reference(p32, g_list, lr, mu, wd, steps):
+    buf = torch.zeros_like(p32)
+    p = p32.clone()
+    for s in range(steps):
+        g = torch.stack([x.float() for x in g_list[s]]).sum(0) / len(g_list[s])
+        dp = g + wd * p
+        buf = mu * buf + dp
+        p = p - lr * buf
+    return p
+
+
+def job_fused_sgd():
+    from bagua_net_b200.parallel import SymmComm
+
+    setup()
+    comm = SymmComm(256 << 20)
+    for dtype in (torch.bfloat16, torch.float32):
+        n = 8 * WORLD * 4099
+        torch.manual_seed(7)
+        p0 = (torch.randn(n, device="cuda") * 0.1)
+        param = comm.alloc(n, dtype)
+        grad = comm.alloc(n, dtype)
+        param.copy_(p0.to(dtype))
+        shard = n // WORLD
+        master = param[RANK * shard:(RANK + 1) * shard].float().contiguous()
+        mom = torch.zeros_like(master)
+        lr, mu, wd, steps = 0.1, 0.9, 0.01, 4
+        all_g = []
+        for s in range(steps):
+            gs = []
+            for r in range(WORLD):
+                torch.manual_seed(100 * s + r)
+                gs.append((torch.randn(n, device="cuda")).to(dtype))
+            all_g.append(gs)
+        for s in range(steps):
+            grad.copy_(all_g[s][RANK])
+            torch.cuda.synchronize()
+            if WORLD > 1:
+                dist.barrier()
+            comm.fused_allreduce_sgd(grad, param, master, mom, lr, mu, wd, zero_grads=True)
+            torch.cuda.synchronize()
+            assert int((grad != 0).sum()) == 0, "gradients were not re-zeroed"
+        ref = _sgd_reference(p0.to(dtype).float(), all_g, lr, mu, wd, steps)
+        # fp32 master stays close to the fp32 reference (bf16 only rounds the reduced gradient)
+        err_m = (master - ref[RANK * shard:(RANK + 1) * shard]).abs().max().item()
+        tol = 3e-2 if dtype == torch.bfloat16 else 1e-5
+        assert err_m < tol, f"{dtype} master err {err_m}"
+        err_p = (param.float() - ref).abs().max().item()
+        assert err_p < (6e-2 if dtype == torch.bfloat16 else 1e-5), f"{dtype} param err {err_p}"
+        if WORLD > 1:   # every rank holds identical parameters
+            chk = param.float().sum().double().reshape(1)
+            lst = [torch.zeros_like(chk) for _ in range(WORLD)]
+            dist.all_gather(lst, chk)
+            assert all(torch.equal(lst[0], x) for x in lst), "ranks diverged"
+        print(f"rank {RANK}: fused sgd {dtype} ok (master err {err_m:.2e}, param err {err_p:.2e}, "
+              f"multicast={comm.has_multicast})", flush=True)
+    assert comm.status() == 0
+    teardown()
+
+
+# ------------------------------------------------------------------ DDP engine vs torch DDP semantics
+def job_ddp_engine():
+    from bagua_net_b200.models import build_model
+    from bagua_net_b200.parallel import BnetDDP
+
+    setup()
+    torch.backends.cudnn.allow_tf32 = False          # compare against torch SGD at full fp32 precision
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    kw = dict(width_div=8, fc_dim=128, image_size=32, num_classes=10, dropout=0.0)
+    model = build_model("vgg16", **kw).cuda()
+    ref = build_model("vgg16", **kw).cuda()
+    ref.load_state_dict(model.state_dict())
+    model = model.to(memory_format=torch.channels_last)
+    lr, mu, wd = 0.05, 0.9, 1e-4
+    eng = BnetDDP(model, lr=lr, momentum=mu, weight_decay=wd, bucket_mb=0.25)
+    assert len(eng.buckets) > 1
+    opt = torch.optim.SGD(ref.parameters(), lr=lr, momentum=mu, weight_decay=wd)
+    losses, ref_losses = [], []
+    for step in range(6):
+        xs, ys = [], []
+        for r in range(WORLD):
+            torch.manual_seed(1000 + 10 * step + r)
+            xs.append(torch.randn(4, 3, 32, 32, device="cuda"))
+            ys.append(torch.randint(0, 10, (4,), device="cuda"))
+        losses.append(float(eng.train_step(xs[RANK].contiguous(memory_format=torch.channels_last), ys[RANK])))
+        # reference: full global batch on one model == averaged per-rank gradients
+        opt.zero_grad()
+        loss = torch.nn.functional.cross_entropy(ref(torch.cat(xs)), torch.cat(ys))
+        loss.backward()
+        opt.step()
+        ref_losses.append(float(torch.nn.functional.cross_entropy(ref(xs[RANK]), ys[RANK]).item()))
+    torch.cuda.synchronize()
+    worst = 0.0
+    for (n1, p1), (n2, p2) in zip(model.named_parameters(), ref.named_parameters()):
+        worst = max(worst, (p1.float() - p2.float()).abs().max().item())
+    assert worst < 1e-3, f"fp32 engine diverged from torch SGD: {worst}"
+    assert eng.kernel_launches >= 6 * len(eng.buckets)
+    print(f"rank {RANK}: ddp engine fp32 matches torch SGD (max param diff {worst:.2e}); losses {losses[:3]}...", flush=True)
+    # bf16 variant trains (loss goes down on a fixed batch)
+    torch.manual_seed(1)
+    m2 = build_model("vgg16", **kw).cuda().to(torch.bfloat16).to(memory_format=torch.channels_last)
+    e2 = BnetDDP(m2, lr=0.02, momentum=0.9, weight_decay=0.0, bucket_mb=0.25)
+    torch.manual_seed(5 + RANK)
+    x = torch.randn(8, 3, 32, 32, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    y = torch.randint(0, 10, (8,), device="cuda")
+    ls = [float(e2.train_step(x, y)) for _ in range(25)]
+    assert ls[-1] < ls[0] * 0.7, ls
+    xh, yh = x.cpu().pin_memory(), y.cpu().pin_memory()
+    assert isinstance(e2.train_step_from_host(xh, yh), float)
+    print(f"rank {RANK}: bf16 engine loss {ls[0]:.3f} -> {ls[-1]:.3f}", flush=True)
+    assert eng.comm.status() == 0 and e2.comm.status() == 0
+    teardown()
+
+
+def job_pack_cast():
+    from bagua_net_b200.ops import pack_cast
+    from bagua_net_b200.parallel import SymmComm
+
+    setup()
+    comm = SymmComm(64 << 20)
+    ts = [torch.randn(n, device="cuda") for n in (1, 7, 1024, 100003, 1 << 20)]
+    total = sum(t.numel() for t in ts)
+    dst = comm.alloc(total, torch.bfloat16)
+    pack_cast(comm, ts, dst, scale=0.5)
+    torch.cuda.synchronize()
+    ref = torch.cat([(t * 0.5).to(torch.bfloat16) for t in ts])
+    assert torch.equal(dst, ref)
+    print("pack_cast ok", flush=True)
+    teardown()
+
+
+# ------------------------------------------------------------------ multi-GPU all-reduce
+def job_allreduce():
+    from bagua_net_b200.parallel import SymmComm
+
+    setup()
+    comm = SymmComm(1 << 30)
+    algos = ["p2p"] + (["nvls"] if comm.has_multicast else [])
+    print(f"rank {RANK}: multicast={comm.has_multicast}", flush=True)
+    for dtype in (torch.float32, torch.bfloat16, torch.float16):
+        for n in [16 * WORLD, 4096 * WORLD, (1 << 20) + 16 * WORLD * 3, 16 << 20]:
+            n = n // (16 * WORLD) * (16 * WORLD)
+            t = comm.alloc(n, dtype)
+            torch.manual_seed(RANK + 17)
+            mine = torch.randn(n, device="cuda").to(dtype)
+            alls = []
+            for r in range(WORLD):
+                torch.manual_seed(r + 17)
+                alls.append(torch.randn(n, device="cuda").to(dtype).float())
+            for op in ("sum", "avg", "max", "min"):
+                ref = {"sum": sum(alls), "avg": sum(alls) / WORLD, "max": torch.stack(alls).max(0).values,
+                       "min": torch.stack(alls).min(0).values}[op]
+                for algo in algos:
+                    t.copy_(mine)
+                    torch.cuda.synchronize()
+                    dist.barrier()
+                    comm.all_reduce(t, op, algo=algo)
+                    torch.cuda.synchronize()
+                    tol = 1e-5 if dtype == torch.float32 else (2e-2 if dtype == torch.bfloat16 else 4e-3)
+                    err = (t.float() - ref).abs().max().item()
+                    assert err <= tol * max(1.0, ref.abs().max().item()), f"{algo} {op} {dtype} n={n} err={err}"
+                # one-shot, out of place
+                t.copy_(mine)
+                torch.cuda.synchronize()
+                dist.barrier()
+                out = torch.empty_like(t)
+                comm.all_reduce_oneshot(t, out, op)
+                torch.cuda.synchronize()
+                err = (out.float() - ref).abs().max().item()
+                assert err <= (1e-5 if dtype == torch.float32 else 2e-2) * max(1.0, ref.abs().max().item()), f"oneshot {op} {dtype}"
+    # quick bandwidth lines
+    for algo in algos:
+        for nbytes in (1 << 20, 64 << 20, 512 << 20):
+            t = comm.alloc(nbytes // 2, torch.bfloat16)
+            t.fill_(1)
+            for _ in range(3):
+                comm.all_reduce(t, "sum", algo=algo)
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                comm.all_reduce(t, "sum", algo=algo)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            if RANK == 0:
+                alg = nbytes / ms / 1e6
+                print(f"allreduce {algo} {nbytes >> 20} MiB: {ms * 1e3:.1f} us algbw {alg:.1f} GB/s busbw "
+                      f"{alg * 2 * (WORLD - 1) / WORLD:.1f} GB/s", flush=True)
+            comm._bump -= 0   # keep allocations: heap is 1 GiB
+    assert comm.status() == 0
+    teardown()
+
+
+def job_nccl_allreduce():
+    """Stock torch.distributed all_reduce with NCCL forced through our plugin (env set by the test)."""
+    setup("nccl")
+    for n in (1, 1024, 1 << 20, (8 << 20) + 5):
+        t = torch.full((n,), float(RANK + 1), device="cuda")
+        dist.all_reduce(t)
+        torch.cuda.synchronize()
+        exp = float(sum(range(1, WORLD + 1)))
+        assert torch.all(t == exp), f"nccl allreduce over plugin wrong for n={n}: {t[:4]}"
+    b = torch.full((1 << 22,), float(RANK), device="cuda", dtype=torch.bfloat16)
+    dist.all_reduce(b)
+    torch.cuda.synchronize()
+    assert torch.all(b.float() == float(sum(range(WORLD))))
+    x = torch.randn(64 << 20, device="cuda")
+    for _ in range(3):
+        dist.all_reduce(x)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        dist.all_reduce(x)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / 5
+    if RANK == 0:
+        from bagua_net_b200.utils import native
+
+        print(f"nccl-over-plugin allreduce 256 MiB: algbw {x.numel() * 4 / dt / 1e9:.2f} GB/s exec={native.exec_stats()}",
+              flush=True)
+    teardown()
+
+
+JOBS = {k[4:]: v for k, v in globals().items() if k.startswith("job_")}
+
+if __name__ == "__main__":
+    JOBS[sys.argv[1]]()

@@ -51,6 +51,39 @@ class FakeCudaBuf:
         return self.arr
 
 
+class CudaBuf:
+    """Real device memory (torch caching allocator -> cudaMalloc -> CUDA IPC export)."""
+
+    def __init__(self, n):
+        import torch
+
+        self.t = torch.zeros(max(n, 16), dtype=torch.uint8, device="cuda")
+        self.addr = self.t.data_ptr()
+        self.type = NCCL_PTR_CUDA
+
+    def view(self):
+        return _CudaProxy(self.t)
+
+
+class _CudaProxy:
+    """numpy-ish slice assignment/reads on a CUDA tensor, enough for this driver."""
+
+    def __init__(self, t):
+        self.t = t
+
+    def __setitem__(self, sl, val):
+        import torch
+
+        self.t[sl] = torch.from_numpy(np.ascontiguousarray(val)).to(self.t.device)
+        torch.cuda.synchronize()
+
+    def __getitem__(self, sl):
+        import torch
+
+        torch.cuda.synchronize()
+        return self.t[sl].cpu().numpy()
+
+
 def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("role", type=int)
@@ -59,7 +92,7 @@ def main() -> int:
     ap.add_argument("--sizes", default="0,1,8,4096,524288,1048575,1048577,4194304")
     ap.add_argument("--inflight", type=int, default=8)
     ap.add_argument("--rounds", type=int, default=2)
-    ap.add_argument("--mem", default="host", choices=["host", "fakecuda"])
+    ap.add_argument("--mem", default="host", choices=["host", "fakecuda", "cuda"])
     ap.add_argument("--die-after", type=int, default=-1, help="sender exits abruptly after N messages")
     ap.add_argument("--expect-error", action="store_true")
     ap.add_argument("--bw", action="store_true", help="print a bandwidth line for the largest size")
@@ -71,7 +104,12 @@ def main() -> int:
     assert p.devices() >= 1, "no device"
     hfile = os.path.join(a.dir, "handle.bin")
     result = {"role": a.role, "abi": a.abi, "name": p.name}
-    alloc = (lambda n: FakeCudaBuf(p.lib, n)) if a.mem == "fakecuda" else HostBuf
+    if a.mem == "cuda":
+        import torch
+
+        torch.cuda.set_device(int(os.environ.get("BNET_TEST_CUDA_DEV", a.role)) % torch.cuda.device_count())
+        torch.zeros(1, device="cuda")
+    alloc = (lambda n: FakeCudaBuf(p.lib, n)) if a.mem == "fakecuda" else (CudaBuf if a.mem == "cuda" else HostBuf)
 
     if a.role == 0:
         handle, lcomm = p.listen(0)
@@ -141,6 +179,12 @@ def main() -> int:
         result["error"] = f"timeout: {e}"
         result["code"] = -1
     result["messages"] = nmsg
+    try:
+        from bagua_net_b200.utils import native
+
+        result["exec"] = native.exec_stats()
+    except Exception:
+        pass
     (p.close_recv if a.role == 0 else p.close_send)(comm)
     print(json.dumps(result), flush=True)
     if a.expect_error:

@@ -1,0 +1,133 @@
+"""GPU tests (run on a B200 with `pytest -m gpu`).  Every kernel is compared against a plain
+PyTorch fp32 reference of the same op.  Multi-GPU cases launch one process per GPU and are
+skipped on a single-GPU box."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _torch():
+    import torch
+
+    assert torch.cuda.is_available(), "GPU test on a box without CUDA"
+    return torch
+
+
+def _run_worker(name, nproc, extra_env=None, args=(), timeout=300):
+    """One process per GPU, torchrun-style environment, rendezvous on 127.0.0.1."""
+    import socket
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    procs = []
+    for r in range(nproc):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(nproc), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port), PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+        env.update(extra_env or {})
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "gpu_worker.py"), name, *args],
+                                      env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = []
+    for p in procs:
+        try:
+            o, e = p.communicate(timeout=timeout)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+        outs.append((p.returncode, o, e))
+    for rc, o, e in outs:
+        assert rc == 0, f"worker failed rc={rc}\nstdout:\n{o[-3000:]}\nstderr:\n{e[-3000:]}"
+    return outs
+
+
+# ------------------------------------------------------------------ transport executor (K1/K4/K5/K7/K8)
+@pytest.mark.parametrize("env", [{}, {"BNET_PERSISTENT": "0"}, {"BNET_COPY_ENGINE": "tma"},
+                                 {"BNET_NCLUSTERS": "8", "BNET_CLUSTER_SIZE": "4", "BNET_DEV_MIN_CHUNKSIZE": "4096"}],
+                         ids=["persistent", "oneshot", "tma", "8x4clusters"])
+def test_executor_copy_reduce_cast(env):
+    _run_worker("executor", 1, extra_env=env)
+
+
+def test_executor_relaunch_after_idle():
+    _run_worker("executor_idle", 1, extra_env={"BNET_KERNEL_IDLE_US": "100"})
+
+
+# ------------------------------------------------------------------ fused optimizer / DDP engine, single GPU
+def test_fused_sgd_matches_torch_single_gpu():
+    _run_worker("fused_sgd", 1)
+
+
+def test_ddp_engine_trains_like_torch_sgd():
+    _run_worker("ddp_engine", 1)
+
+
+def test_pack_cast():
+    _run_worker("pack_cast", 1)
+
+
+def test_smoke_entry():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as g
+
+    g.smoke()
+
+
+def test_bench_contract_single_gpu():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "3", "--warmup", "3", "--batch", "8"],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-3000:]
+    line = [ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1]
+    d = json.loads(line)
+    assert d["metric"] == "vgg16_train_img_per_sec" and d["n_gpus"] == 1 and d["value"] > 0
+    assert d["gpu_launches"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["dtype"] == "bf16"
+    ref = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference"], capture_output=True,
+                         text=True, timeout=60)
+    assert ref.returncode == 0 and json.loads(ref.stdout.splitlines()[-1])["impl"] == "reference"
+
+
+# ------------------------------------------------------------------ multi-GPU: collectives, plugin, NCCL in the loop
+@pytest.mark.multigpu
+def test_allreduce_kernels_2gpu():
+    _run_worker("allreduce", 2)
+
+
+@pytest.mark.multigpu
+def test_fused_sgd_2gpu_matches_reference():
+    _run_worker("fused_sgd", 2)
+
+
+@pytest.mark.multigpu
+def test_ddp_engine_2gpu():
+    _run_worker("ddp_engine", 2)
+
+
+@pytest.mark.multigpu
+def test_plugin_nvl_transport_with_cuda_buffers():
+    from conftest import run_pair
+
+    outs = run_pair(["--mem", "cuda", "--sizes", "0,1,8,4096,524288,1048577,4194304", "--inflight", "8", "--rounds", "2"],
+                    env={"BNET_NVL": "1"}, timeout=240)
+    for rc, res, err in outs:
+        assert res is not None and rc == 0 and res["ok"], (res, err[-3000:])
+        assert res["transport"] == "nvl"
+    sender = outs[1][1]
+    assert sender["exec"]["chunks"] > 0, f"device kernels were not used: {sender}"
+
+
+@pytest.mark.multigpu
+def test_nccl_loads_plugin_and_allreduces():
+    from bagua_net_b200.utils.env import nccl_plugin_env
+
+    env = nccl_plugin_env(force_net=True, debug=True)
+    outs = _run_worker("nccl_allreduce", 2, extra_env=env, timeout=300)
+    log = "".join(o + e for _, o, e in outs)
+    assert "Using network BNet" in log or "NET/Plugin: Loaded net plugin BNet" in log, log[-4000:]
