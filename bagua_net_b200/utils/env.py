@@ -42,3 +42,10 @@ def nccl_plugin_env(plugin: str = "bnet", force_net: bool = False, gdr: bool = T
 
 def apply(env: dict) -> None:
     os.environ.update(env)
+
+
+if __name__ == "__main__":   # `env $(python -m bagua_net_b200.utils.env) <cmd>` loads the plugin into NCCL
+    import sys
+
+    kw = {"force_net": "--no-force" not in sys.argv, "debug": "--debug" in sys.argv, "gdr": "--no-gdr" not in sys.argv}
+    print(" ".join(f"{k}={v}" for k, v in nccl_plugin_env(**kw).items()))

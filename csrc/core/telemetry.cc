@@ -53,7 +53,14 @@ struct Telemetry::Impl {
 };
 
 Telemetry& Telemetry::get() {
-  static Telemetry* t = new Telemetry();  // intentionally leaked: used from detached workers at exit
+  // intentionally leaked (workers may still record while the process exits); the final
+  // flush — root span end + last push, the reference does it in Drop (nthread_…:652-658) —
+  // runs from atexit instead of a destructor.
+  static Telemetry* t = [] {
+    Telemetry* x = new Telemetry();
+    atexit([] { Telemetry::get().shutdown(); });
+    return x;
+  }();
   return *t;
 }
 
