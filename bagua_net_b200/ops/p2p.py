@@ -32,7 +32,11 @@ class P2PExecutor:
         self.seq = 0
         self.slot = 0
 
-    def submit(self, op: str, src: torch.Tensor, dst: torch.Tensor, src_bytes: int | None = None):
+    def submit(self, op: str, src: torch.Tensor, dst: torch.Tensor, src_bytes: int | None = None, sync: bool = True):
+        # The executor's kernels run on their own streams: whatever produced `src` / initialised
+        # `dst` on torch's stream must be finished first (NCCL gives the plugin the same guarantee).
+        if sync:
+            torch.cuda.current_stream(self.device).synchronize()
         nbytes = src.numel() * src.element_size() if src_bytes is None else src_bytes
         self.seq += 1
         slot = self.slot

@@ -35,7 +35,7 @@ namespace bnet {
 namespace coll {
 
 constexpr int kThreads = 512;
-constexpr size_t kPadBytes = 1 << 16;   // signal pad at the start of every rank's allocation
+constexpr size_t kPadBytes = 1 << 18;   // signal pad at the start of every rank's allocation
 static_assert(BNET_COLL_SIGNAL_BYTES <= kPadBytes, "signal pad too small");
 
 struct CollDev {
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(kThreads) bnet_allreduce_nvls_kernel(CollDev d
   char* base = d.mc + off + (size_t)d.rank * per * 16;
   const size_t stride = (size_t)gridDim.x * kThreads;
   const float s = 1.0f / (float)d.world;
-  constexpr int U = 4;
+  constexpr int U = 8;   // 8 in-switch reductions in flight per thread
   size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
   for (; i + (U - 1) * stride < per; i += U * stride) {
     int4 v[U];
@@ -288,36 +288,51 @@ __global__ void __launch_bounds__(kThreads) bnet_barrier_kernel(CollDev d, int c
 
 // ------------------------------------------------------------------ fused all-reduce + SGD + broadcast
 // MODE 0: single GPU, 1: NVLS multicast, 2: peer loads/stores
-template <int DT, int MODE>
-__global__ void __launch_bounds__(kThreads) bnet_fused_sgd_kernel(CollDev d, size_t goff, size_t poff, size_t nvec,
-                                                                 float lr, float mu, float wd, float gscale,
-                                                                 float* __restrict__ master, float* __restrict__ mom,
-                                                                 int zero_grads, int chan) {
+//
+// One batch = U 16-byte gradient vectors per thread.  All loads of the batch (in-switch
+// reductions / peer loads, fp32 master + momentum) are issued before any dependent math so that
+// U*(1 + 2*E/4) requests per thread are in flight: the kernel is latency*bandwidth bound
+// (NVLink round trip ~3 us, HBM), not ALU bound.
+template <int DT, int MODE, int U>
+__device__ __forceinline__ void fused_sgd_batch(const CollDev& d, size_t goff, size_t poff, size_t start, size_t i,
+                                                size_t stride, float lr, float mu, float wd, float gscale,
+                                                float* __restrict__ master, float* __restrict__ mom) {
   constexpr int E = VecTraits<DT>::kElems;
-  if constexpr (MODE != 0) rank_barrier(d, chan);
-  const size_t per = nvec / d.world;
-  const size_t start = (size_t)d.rank * per;
-  const size_t stride = (size_t)gridDim.x * kThreads;
-  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < per; i += stride) {
-    const size_t vo = (start + i) * 16;
-    float g[8];
-    if constexpr (MODE == 1) {
-      int4 v = mc_ld_reduce<DT, BNET_SUM>(d.mc + goff + vo);
-      unpack<DT>(v, g);
-    } else if constexpr (MODE == 2) {
-      p2p_reduce<DT, BNET_SUM>(d, goff + vo, d.rank, g);
-    } else {
-      int4 v = ptx::ld_na_v4(reinterpret_cast<const int4*>(d.heap[0] + goff + vo));
-      unpack<DT>(v, g);
-    }
-    // optimizer state of this rank's shard, fp32
-    float4* mp = reinterpret_cast<float4*>(master + i * E);
-    float4* bp = reinterpret_cast<float4*>(mom + i * E);
-    float p[8], b[8];
+  constexpr int Q = E / 4;
+  int4 gv[U];
+  float4 pm[U][Q], bm[U][Q];
+  float gp2p[(MODE == 2) ? U : 1][8];
 #pragma unroll
-    for (int q = 0; q < E / 4; q++) {
-      float4 t = mp[q]; p[4 * q] = t.x; p[4 * q + 1] = t.y; p[4 * q + 2] = t.z; p[4 * q + 3] = t.w;
-      float4 u = bp[q]; b[4 * q] = u.x; b[4 * q + 1] = u.y; b[4 * q + 2] = u.z; b[4 * q + 3] = u.w;
+  for (int u = 0; u < U; u++) {
+    const size_t vo = (start + i + u * stride) * 16;
+    if constexpr (MODE == 1) gv[u] = mc_ld_reduce<DT, BNET_SUM>(d.mc + goff + vo);
+    else if constexpr (MODE == 2) p2p_reduce<DT, BNET_SUM>(d, goff + vo, d.rank, gp2p[u]);
+    else gv[u] = ptx::ld_na_v4(reinterpret_cast<const int4*>(d.heap[0] + goff + vo));
+  }
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    const float4* mp = reinterpret_cast<const float4*>(master + (i + u * stride) * E);
+    const float4* bp = reinterpret_cast<const float4*>(mom + (i + u * stride) * E);
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+      pm[u][q] = ptx::ld_na_f4(mp + q);
+      bm[u][q] = ptx::ld_na_f4(bp + q);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    const size_t vo = (start + i + u * stride) * 16;
+    float g[8], p[8], b[8];
+    if constexpr (MODE == 2) {
+#pragma unroll
+      for (int k = 0; k < E; k++) g[k] = gp2p[u][k];
+    } else {
+      unpack<DT>(gv[u], g);
+    }
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+      p[4 * q] = pm[u][q].x; p[4 * q + 1] = pm[u][q].y; p[4 * q + 2] = pm[u][q].z; p[4 * q + 3] = pm[u][q].w;
+      b[4 * q] = bm[u][q].x; b[4 * q + 1] = bm[u][q].y; b[4 * q + 2] = bm[u][q].z; b[4 * q + 3] = bm[u][q].w;
     }
 #pragma unroll
     for (int k = 0; k < E; k++) {
@@ -325,10 +340,12 @@ __global__ void __launch_bounds__(kThreads) bnet_fused_sgd_kernel(CollDev d, siz
       b[k] = fmaf(mu, b[k], dp);                  // buf = mu*buf + d_p
       p[k] = fmaf(-lr, b[k], p[k]);               // p  -= lr*buf
     }
+    float4* mp = reinterpret_cast<float4*>(master + (i + u * stride) * E);
+    float4* bp = reinterpret_cast<float4*>(mom + (i + u * stride) * E);
 #pragma unroll
-    for (int q = 0; q < E / 4; q++) {
-      mp[q] = make_float4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
-      bp[q] = make_float4(b[4 * q], b[4 * q + 1], b[4 * q + 2], b[4 * q + 3]);
+    for (int q = 0; q < Q; q++) {
+      ptx::st_na_f4(mp + q, make_float4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]));
+      ptx::st_na_f4(bp + q, make_float4(b[4 * q], b[4 * q + 1], b[4 * q + 2], b[4 * q + 3]));
     }
     const int4 out = pack<DT>(p);
     if constexpr (MODE == 1) {
@@ -340,14 +357,31 @@ __global__ void __launch_bounds__(kThreads) bnet_fused_sgd_kernel(CollDev d, siz
         ptx::st_na_v4(reinterpret_cast<int4*>(d.heap[pr] + poff + vo), out);
       }
     } else {
-      *reinterpret_cast<int4*>(d.heap[0] + poff + vo) = out;
+      ptx::st_na_v4(reinterpret_cast<int4*>(d.heap[0] + poff + vo), out);
     }
   }
+}
+
+template <int DT, int MODE>
+__global__ void __launch_bounds__(kThreads, 2) bnet_fused_sgd_kernel(CollDev d, size_t goff, size_t poff, size_t nvec,
+                                                                 float lr, float mu, float wd, float gscale,
+                                                                 float* __restrict__ master, float* __restrict__ mom,
+                                                                 int zero_grads, int chan) {
+  if constexpr (MODE != 0) rank_barrier(d, chan);
+  const size_t per = nvec / d.world;
+  const size_t start = (size_t)d.rank * per;
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  constexpr int U = 2;   // 16-byte gradient vectors per thread per batch (register budget: 2 CTAs/SM)
+  size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
+  for (; i + (U - 1) * stride < per; i += U * stride)
+    fused_sgd_batch<DT, MODE, U>(d, goff, poff, start, i, stride, lr, mu, wd, gscale, master, mom);
+  for (; i < per; i += stride)
+    fused_sgd_batch<DT, MODE, 1>(d, goff, poff, start, i, stride, lr, mu, wd, gscale, master, mom);
   if constexpr (MODE != 0) rank_barrier(d, chan);
   if (zero_grads) {   // every peer has finished reading our gradients: reset them for the next backward
     int4* gz = reinterpret_cast<int4*>(d.heap[d.rank] + goff);
     const int4 z = make_int4(0, 0, 0, 0);
-    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < nvec; i += stride) gz[i] = z;
+    for (size_t j = (size_t)blockIdx.x * kThreads + threadIdx.x; j < nvec; j += stride) ptx::st_na_v4(gz + j, z);
   }
 }
 
@@ -477,13 +511,18 @@ int launch(K kernel, int nblocks, int threads, cudaStream_t st, Args... args) {
   return 1;
 }
 
+// NVLink-bound kernels need enough requests in flight to cover ~3 us of fabric latency
+// (770 GB/s * 3 us = 2.3 MB): default 96 CTAs x 512 threads x 8 x 16 B = 6 MB.  A single GPU has no
+// fabric to wait for but all of HBM to feed: 2 CTAs per SM.
 int pick_blocks(const BnetColl* c, size_t vec_per_rank, int requested) {
   if (requested > 0) return requested > BNET_COLL_MAX_BLOCKS ? BNET_COLL_MAX_BLOCKS : requested;
-  static const int dflt = (int)env_int("COLL_BLOCKS", 32);
-  size_t want = (vec_per_rank + kThreads * 4 - 1) / (kThreads * 4);   // >= 4 vectors per thread before adding CTAs
+  static const int dflt_multi = (int)env_int("COLL_BLOCKS", 96);
+  static const int dflt_single = (int)env_int("COLL_BLOCKS_SINGLE", 296);
+  int cap = c->world == 1 ? dflt_single : dflt_multi;
+  if (cap > BNET_COLL_MAX_BLOCKS) cap = BNET_COLL_MAX_BLOCKS;
+  size_t want = (vec_per_rank + kThreads * 2 - 1) / (kThreads * 2);   // >= 2 vectors per thread before adding CTAs
   if (want < 1) want = 1;
-  if (want > (size_t)dflt) want = dflt;
-  (void)c;
+  if (want > (size_t)cap) want = cap;
   return (int)want;
 }
 

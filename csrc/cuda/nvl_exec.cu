@@ -590,6 +590,11 @@ extern "C" __attribute__((visibility("default"))) int bnet_exec_op(int dev, uint
   return submit(e, op, src, dst, src_bytes, flags_dev, flag_value, nchunks);
 }
 
+int exec_prepare(int dev) {
+  if (fake()) return 0;
+  return get_exec(dev) ? 0 : -1;
+}
+
 void exec_stats(ExecStats* out) {
   memset(out, 0, sizeof(*out));
   std::lock_guard<std::mutex> lk(g_mu);

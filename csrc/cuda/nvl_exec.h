@@ -28,6 +28,8 @@ int exec_copy(int dev, const void* src, void* dst, size_t nbytes, volatile uint6
               uint64_t* flags_dev, uint64_t flag_value, int* nchunks);
 // Device-side fence used by iflush (K7): completes `flag` once prior peer stores are visible.
 int exec_flush(int dev, volatile uint64_t* flag_host, uint64_t* flag_dev, uint64_t flag_value);
+// Create streams / queues / pinned memory for `dev` now (setup phase) instead of at the first job.
+int exec_prepare(int dev);
 void exec_stats(ExecStats* out);
 void exec_shutdown();
 

@@ -33,6 +33,8 @@
 #include <deque>
 #include <map>
 #include <mutex>
+#include <thread>
+#include <vector>
 
 #include "core/engine.h"
 #include "core/telemetry.h"
@@ -149,6 +151,10 @@ int recv_fd(int sock, NvlMsg* m, int* fd) {
   return 1;
 }
 
+class NvlComm;
+void watchdog_register(NvlComm* c);
+void watchdog_unregister(NvlComm* c);
+
 class NvlComm : public Comm {
  public:
   NvlComm(Kind k, int dev_, int uds, NvlShm* shm, size_t shm_bytes, std::string shm_name, uint32_t peer_pid,
@@ -168,9 +174,13 @@ class NvlComm : public Comm {
       }
     }
     set_nonblocking(uds_, true);
+    // all CUDA resource creation happens here, in NCCL's setup phase, never on the data path
+    if (k == SEND && cuda::available() && !cuda::fake()) cuda::exec_prepare(local_dev_);
+    watchdog_register(this);
   }
 
   ~NvlComm() override {
+    watchdog_unregister(this);
     (kind == SEND ? shm_->sender_closed : shm_->receiver_closed).store(1, std::memory_order_release);
     for (auto& kv : imports_)
       if (kv.second.base) cuda::release_import(kv.second.exp, kv.second.base, kv.second.cookie);
@@ -324,6 +334,33 @@ class NvlComm : public Comm {
   }
 
   void progress() override {}   // test() drives progress under the comm lock
+
+  // BNET_WATCHDOG_MS: describe a comm whose oldest request is older than the threshold
+  void dump_if_stuck(uint64_t older_than_ns) {
+    std::unique_lock<std::mutex> lk(mu_, std::try_to_lock);
+    if (!lk.owns_lock() || pending_.empty()) return;
+    Request* r = pending_.front();
+    uint64_t age = now_ns() - r->t_post;
+    if (age < older_than_ns) return;
+    uint64_t k = r->u[0];
+    const RecvDesc& d = shm_->rdesc[k % kSlots];
+    fprintf(stderr,
+            "[bnet watchdog] %s comm %llu pid %d dev %d peer pid %u: %zu pending, head msg %llu stage %llu size %zu "
+            "moved %llu age %.1f ms | rdesc.seq %llu cap %llu mr %u type %u | ann.seq %llu nbytes %llu ring %u err %d | "
+            "done.seq %llu | ring w %llu r %llu | next seq %llu\n",
+            kind == SEND ? "send" : "recv", (unsigned long long)id, (int)getpid(), local_dev_, peer_pid_, pending_.size(),
+            (unsigned long long)k, (unsigned long long)r->u[1], r->size, (unsigned long long)r->u[2], age / 1e6,
+            (unsigned long long)d.seq.load(), (unsigned long long)d.capacity, d.mr_idx, d.dst_type,
+            (unsigned long long)shm_->ann[k % kSlots].seq.load(), (unsigned long long)shm_->ann[k % kSlots].nbytes,
+            shm_->ann[k % kSlots].via_ring, shm_->ann[k % kSlots].err, (unsigned long long)shm_->done[k % kSlots].seq.load(),
+            (unsigned long long)shm_->ring_w.load(), (unsigned long long)shm_->ring_r.load(), (unsigned long long)seq_);
+    if (kind == SEND && r->u[1] == 2 && flags_) {
+      volatile uint64_t* fh = flags_ + (k % kSlots) * cuda::kMaxChunksPerJob;
+      fprintf(stderr, "[bnet watchdog]   chunk flags (%llu expected %llu):", (unsigned long long)r->u[2], (unsigned long long)(k + 1));
+      for (uint64_t c = 0; c < r->u[2]; c++) fprintf(stderr, " %llu", (unsigned long long)fh[c]);
+      fprintf(stderr, "\n");
+    }
+  }
 
  private:
   bool flush_flags_ready() {
@@ -664,6 +701,35 @@ class NvlComm : public Comm {
   std::map<uint32_t, uint32_t> fd_gen_;
   std::map<int, cuda::MemExport> exports_;
 };
+
+std::mutex g_wd_mu;
+std::vector<NvlComm*> g_wd_comms;
+bool g_wd_started = false;
+
+void watchdog_register(NvlComm* c) {
+  static const long long ms = env_int("WATCHDOG_MS", 0);
+  if (ms <= 0) return;
+  std::lock_guard<std::mutex> lk(g_wd_mu);
+  g_wd_comms.push_back(c);
+  if (!g_wd_started) {
+    g_wd_started = true;
+    std::thread([] {
+      const uint64_t thr = (uint64_t)env_int("WATCHDOG_MS", 0) * 1000000ull;
+      for (int dumps = 0; dumps < 20;) {
+        usleep((useconds_t)(thr / 1000));
+        std::lock_guard<std::mutex> lk(g_wd_mu);
+        for (NvlComm* c : g_wd_comms) c->dump_if_stuck(thr);
+        dumps++;
+      }
+    }).detach();
+  }
+}
+
+void watchdog_unregister(NvlComm* c) {
+  std::lock_guard<std::mutex> lk(g_wd_mu);
+  for (size_t i = 0; i < g_wd_comms.size(); i++)
+    if (g_wd_comms[i] == c) { g_wd_comms.erase(g_wd_comms.begin() + i); break; }
+}
 
 size_t shm_total(size_t ring) { return offsetof(NvlShm, ring) + ring; }
 

@@ -23,7 +23,7 @@ extern "C" {
 
 #define BNET_COLL_BLOB_BYTES 128
 #define BNET_COLL_MAX_WORLD 16
-#define BNET_COLL_MAX_BLOCKS 128
+#define BNET_COLL_MAX_BLOCKS 304
 #define BNET_COLL_CHANNELS 8
 #define BNET_COLL_SIGNAL_BYTES (BNET_COLL_CHANNELS * BNET_COLL_MAX_BLOCKS * BNET_COLL_MAX_WORLD * 4)
 
