@@ -72,7 +72,7 @@ test: $(TEST_BINS)
 	$(BUILD)/tests/unit_tests $(PLUGIN_SO)
 	$(BUILD)/tests/loopback_test $(PLUGIN_SO)
 
-BENCH_BINS := $(BUILD)/bench/all_reduce_perf $(BUILD)/bench/p2p_bw
+BENCH_BINS := $(BUILD)/bench/all_reduce_perf
 NCCL_HOME ?= $(shell python -c "import nvidia.nccl, os; print(os.path.dirname(nvidia.nccl.__file__))" 2>/dev/null)
 $(BUILD)/bench/%: bench/%.cu $(PLUGIN_SO)
 	@mkdir -p $(dir $@)

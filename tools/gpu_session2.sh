@@ -13,12 +13,11 @@ TAILN=25 step gpu_tests_1 600 python -m pytest tests/test_gpu.py -q -m "gpu and 
 TAILN=40 step gpu_tests_multi 600 python -m pytest tests/test_gpu.py -q -m "multigpu" -p no:cacheprovider -k "not nccl_loads" -s
 # ---- NCCL in the loop, one layer at a time
 PENV=$(python -m bagua_net_b200.utils.env --debug)
-nccl_case() { local name=$1; shift; TAILN=30 step $name 100 env $PENV BNET_LOG_LEVEL=INFO BNET_WATCHDOG_MS=8000 "$@" $TR --master-port 29551 tests/gpu_worker.py nccl_allreduce; grep -E "Using network|Loaded net plugin|GDR|via NET|BNet|bnet" $OUT/$name.log | head -20 | cut -c1-300; }
+nccl_case() { local name=$1; shift; TAILN=30 step $name 75 env $PENV BNET_LOG_LEVEL=INFO BNET_WATCHDOG_MS=8000 "$@" $TR --master-port 29551 tests/gpu_worker.py nccl_allreduce; grep -E "Using network|Loaded net plugin|GDR|via NET|BNet|bnet" $OUT/$name.log | head -20 | cut -c1-300; }
 nccl_case nccl_tcp_host BNET_NVL=0 BNET_GDR=0
 nccl_case nccl_shm_host BNET_NVL=1 BNET_GDR=0
 nccl_case nccl_nvl_gdr_oneshot BNET_NVL=1 BNET_PERSISTENT=0
 nccl_case nccl_nvl_gdr_persistent BNET_NVL=1
-nccl_case nccl_tcp_gdr BNET_NVL=0
 # ---- flagship bench
 step bench1 300 python bench.py --gpus 1 --steps 20 --warmup 5
 step bench2 400 $TR --master-port 29541 bench.py --gpus $NG --steps 20 --warmup 5
