@@ -11,7 +11,7 @@ import torch
 from ..utils.native import load
 
 OPS = {"copy": 0, "red_add_f32": 1, "red_add_bf16": 2, "cast_bf16_to_f32": 3, "cast_f32_to_bf16": 4, "flush": 5,
-       "acc_bf16_to_f32": 6}
+       "acc_bf16_to_f32": 6, "cast_bf16_to_e4m3": 7, "acc_e4m3_to_f32": 8, "cast_f32_to_e4m3": 9}
 
 
 class P2PExecutor:
@@ -26,13 +26,16 @@ class P2PExecutor:
         self.lib = load()
         self.lib.bnet_exec_op.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
                                           C.c_void_p, C.c_uint64, C.POINTER(C.c_int)]
+        self.lib.bnet_exec_op_scaled.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+                                                 C.c_uint64, C.c_float, C.POINTER(C.c_int)]
         self.device = torch.cuda.current_device() if device is None else device
         # pinned + UVA: the same address is valid on host and device
         self.flags = torch.zeros(self.MAX_CHUNKS * 64, dtype=torch.int64).pin_memory()
         self.seq = 0
         self.slot = 0
 
-    def submit(self, op: str, src: torch.Tensor, dst: torch.Tensor, src_bytes: int | None = None, sync: bool = True):
+    def submit(self, op: str, src: torch.Tensor, dst: torch.Tensor, src_bytes: int | None = None, sync: bool = True,
+               scale: float | None = None):
         # The executor's kernels run on their own streams: whatever produced `src` / initialised
         # `dst` on torch's stream must be finished first (NCCL gives the plugin the same guarantee).
         if sync:
@@ -43,8 +46,12 @@ class P2PExecutor:
         self.slot = (self.slot + 1) % 64
         base = self.flags.data_ptr() + slot * self.MAX_CHUNKS * 8
         n = C.c_int(0)
-        rc = self.lib.bnet_exec_op(self.device, OPS[op], C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), nbytes,
-                                   C.c_void_p(base), C.c_void_p(base), self.seq, C.byref(n))
+        if scale is not None:
+            rc = self.lib.bnet_exec_op_scaled(self.device, OPS[op], C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()),
+                                              nbytes, C.c_void_p(base), self.seq, float(scale), C.byref(n))
+        else:
+            rc = self.lib.bnet_exec_op(self.device, OPS[op], C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), nbytes,
+                                       C.c_void_p(base), C.c_void_p(base), self.seq, C.byref(n))
         if rc != 0:
             raise RuntimeError(f"bnet_exec_op({op}) failed")
         return slot, n.value, self.seq
@@ -60,6 +67,6 @@ class P2PExecutor:
             if time.time() - t0 > timeout:
                 raise TimeoutError("device executor did not complete the job")
 
-    def run(self, op: str, src: torch.Tensor, dst: torch.Tensor):
-        self.wait(self.submit(op, src, dst))
+    def run(self, op: str, src: torch.Tensor, dst: torch.Tensor, scale: float | None = None):
+        self.wait(self.submit(op, src, dst, scale=scale))
         return dst

@@ -21,6 +21,7 @@
 // the application never wait on us for long; the host relaunches on demand with a
 // Dekker-style handshake on the queue's state word.
 #include <cuda_bf16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
@@ -44,6 +45,9 @@ enum ExecOp : uint32_t {
   OP_CAST_F32_TO_BF16 = 4, // dst(bf16) = src(f32)
   OP_FLUSH = 5,            // K7: fence only
   OP_ACC_BF16_TO_F32 = 6,  // dst(f32) += src(bf16)          (K4+K5 fused)
+  OP_CAST_BF16_TO_E4M3 = 7,  // dst(fp8 e4m3) = sat(src(bf16) * scale)   (gradient compression, K5)
+  OP_ACC_E4M3_TO_F32 = 8,    // dst(f32) += src(fp8 e4m3) * scale        (decompress + accumulate)
+  OP_CAST_F32_TO_E4M3 = 9,   // dst(fp8 e4m3) = sat(src(f32) * scale)
 };
 
 constexpr int kQueueDepth = 64;
@@ -58,7 +62,7 @@ struct alignas(64) Desc {
   uint64_t* flag;      // device-visible completion word (pinned host memory)
   uint64_t flag_val;
   uint32_t op;
-  uint32_t pad;
+  float scale;         // fp8 (de)quantisation scale
 };
 
 struct ClusterQ {
@@ -77,6 +81,8 @@ struct SmemDesc {
   uint64_t nbytes;
   uint32_t op;
   uint32_t quit;
+  float scale;
+  uint32_t pad;
 };
 
 template <int UNROLL>
@@ -97,7 +103,8 @@ __device__ __forceinline__ void copy_vec16(const char* __restrict__ src, char* _
 }
 
 // Moves/reduces [0,n) source bytes for one CTA's share.  tid/nthreads are CTA-local.
-__device__ void process_range(uint32_t op, const char* src, char* dst, size_t n, int tid, int nthreads) {
+__device__ void process_range(uint32_t op, const char* src, char* dst, size_t n, int tid, int nthreads,
+                              float scale = 1.0f) {
   if (n == 0) return;
   if (op == OP_COPY) {
     // align the destination, then go wide if the source agrees
@@ -209,12 +216,84 @@ __device__ void process_range(uint32_t op, const char* src, char* dst, size_t n,
     }
     return;
   }
+  if (op == OP_CAST_BF16_TO_E4M3 || op == OP_CAST_F32_TO_E4M3) {
+    // 8 source elements -> 8 fp8 bytes per step (one 8-byte store), saturating e4m3
+    const bool from_bf16 = op == OP_CAST_BF16_TO_E4M3;
+    size_t ne = from_bf16 ? n >> 1 : n >> 2;
+    unsigned char* d = (unsigned char*)dst;
+    auto q1 = [&](float f) -> unsigned char {
+      return (unsigned char)__nv_cvt_float_to_fp8(f * scale, __NV_SATFINITE, __NV_E4M3);
+    };
+    if ((((uintptr_t)src) & 15) == 0 && (((uintptr_t)d) & 7) == 0) {
+      size_t nv = ne >> 3;
+      for (size_t i = tid; i < nv; i += nthreads) {
+        float f[8];
+        if (from_bf16) {
+          int4 v = ptx::ld_na_v4(reinterpret_cast<const int4*>(src) + i);
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+          for (int k = 0; k < 4; k++) { float2 t = __bfloat1622float2(h[k]); f[2 * k] = t.x; f[2 * k + 1] = t.y; }
+        } else {
+          float4 lo = ptx::ld_na_f4(reinterpret_cast<const float4*>(src) + 2 * i);
+          float4 hi = ptx::ld_na_f4(reinterpret_cast<const float4*>(src) + 2 * i + 1);
+          f[0] = lo.x; f[1] = lo.y; f[2] = lo.z; f[3] = lo.w; f[4] = hi.x; f[5] = hi.y; f[6] = hi.z; f[7] = hi.w;
+        }
+        uint32_t w[2];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+          uint32_t a = __nv_cvt_float2_to_fp8x2(make_float2(f[4 * k] * scale, f[4 * k + 1] * scale), __NV_SATFINITE, __NV_E4M3);
+          uint32_t b = __nv_cvt_float2_to_fp8x2(make_float2(f[4 * k + 2] * scale, f[4 * k + 3] * scale), __NV_SATFINITE, __NV_E4M3);
+          w[k] = (a & 0xffffu) | (b << 16);
+        }
+        *reinterpret_cast<uint2*>(d + 8 * i) = make_uint2(w[0], w[1]);
+      }
+      for (size_t i = (nv << 3) + tid; i < ne; i += nthreads)
+        d[i] = q1(from_bf16 ? __bfloat162float(((const __nv_bfloat16*)src)[i]) : ((const float*)src)[i]);
+    } else {
+      for (size_t i = tid; i < ne; i += nthreads)
+        d[i] = q1(from_bf16 ? __bfloat162float(((const __nv_bfloat16*)src)[i]) : ((const float*)src)[i]);
+    }
+    return;
+  }
+  if (op == OP_ACC_E4M3_TO_F32) {
+    size_t ne = n;
+    const unsigned char* s = (const unsigned char*)src;
+    float* d = (float*)dst;
+    auto dq = [&](unsigned char b) -> float {
+      __half_raw h = __nv_cvt_fp8_to_halfraw(b, __NV_E4M3);
+      return __half2float(*reinterpret_cast<__half*>(&h)) * scale;
+    };
+    if ((((uintptr_t)s) & 7) == 0 && (((uintptr_t)d) & 15) == 0) {
+      size_t nv = ne >> 3;
+      for (size_t i = tid; i < nv; i += nthreads) {
+        uint2 v = *reinterpret_cast<const uint2*>(s + 8 * i);
+        const unsigned char* b = reinterpret_cast<const unsigned char*>(&v);
+        float4 lo = make_float4(dq(b[0]), dq(b[1]), dq(b[2]), dq(b[3]));
+        float4 hi = make_float4(dq(b[4]), dq(b[5]), dq(b[6]), dq(b[7]));
+        ptx::red_add_v4_f32(d + 8 * i, lo);
+        ptx::red_add_v4_f32(d + 8 * i + 4, hi);
+      }
+      for (size_t i = (nv << 3) + tid; i < ne; i += nthreads) ptx::red_add_f32(d + i, dq(s[i]));
+    } else {
+      for (size_t i = tid; i < ne; i += nthreads) ptx::red_add_f32(d + i, dq(s[i]));
+    }
+    return;
+  }
 }
 
-// destination bytes produced per source byte, as a shift pair (num/den)
+// source bytes per indivisible work unit (keeps CTA / chunk cuts vector-aligned on BOTH sides)
+__device__ __host__ inline size_t src_unit_for(uint32_t op) {
+  if (op == OP_CAST_F32_TO_BF16 || op == OP_CAST_BF16_TO_E4M3 || op == OP_RED_ADD_F32) return 32;
+  if (op == OP_CAST_F32_TO_E4M3) return 64;
+  return 16;
+}
+
+// destination offset that corresponds to a source offset
 __device__ __host__ inline size_t dst_offset_for(uint32_t op, size_t src_off) {
   if (op == OP_CAST_BF16_TO_F32 || op == OP_ACC_BF16_TO_F32) return src_off * 2;
-  if (op == OP_CAST_F32_TO_BF16) return src_off / 2;
+  if (op == OP_CAST_F32_TO_BF16 || op == OP_CAST_BF16_TO_E4M3) return src_off / 2;
+  if (op == OP_ACC_E4M3_TO_F32) return src_off * 4;
+  if (op == OP_CAST_F32_TO_E4M3) return src_off / 4;
   return src_off;
 }
 
@@ -280,6 +359,7 @@ bnet_nvl_stream_kernel(ClusterQ* q, uint64_t idle_ns, uint64_t watchdog_ns) {
     if (crank == 0 && tid == 0) {
       SmemDesc loc;
       loc.quit = 0;
+      loc.pad = 0;
       uint32_t backoff = 32;
       Desc* d = &q->d[head % kQueueDepth];
       for (;;) {
@@ -305,8 +385,9 @@ bnet_nvl_stream_kernel(ClusterQ* q, uint64_t idle_ns, uint64_t watchdog_ns) {
         loc.dst = (char*)d->dst;
         loc.nbytes = d->nbytes;
         loc.op = d->op;
+        loc.scale = d->scale;
       } else {
-        loc.src = nullptr; loc.dst = nullptr; loc.nbytes = 0; loc.op = 0;
+        loc.src = nullptr; loc.dst = nullptr; loc.nbytes = 0; loc.op = 0; loc.scale = 1.0f;
       }
       for (uint32_t r = 0; r < csize; r++) ptx::st_dsmem(&sd, r, loc);   // distributed shared memory broadcast
     }
@@ -316,10 +397,11 @@ bnet_nvl_stream_kernel(ClusterQ* q, uint64_t idle_ns, uint64_t watchdog_ns) {
 
     if (cur.op != OP_FLUSH) {
       // ---- every CTA takes a contiguous 16-byte aligned share of the source range
-      size_t units = (cur.nbytes + 15) >> 4;
+      const size_t unit = src_unit_for(cur.op);
+      size_t units = (cur.nbytes + unit - 1) / unit;
       size_t per = (units + csize - 1) / csize;
-      size_t b0 = (size_t)crank * per * 16;
-      size_t b1 = b0 + per * 16;
+      size_t b0 = (size_t)crank * per * unit;
+      size_t b1 = b0 + per * unit;
       if (b0 > cur.nbytes) b0 = cur.nbytes;
       if (b1 > cur.nbytes) b1 = cur.nbytes;
       const char* s = cur.src + b0;
@@ -332,7 +414,7 @@ bnet_nvl_stream_kernel(ClusterQ* q, uint64_t idle_ns, uint64_t watchdog_ns) {
         if (tid == 0) tma_copy_range(s, dd, nb, (char*)dyn_smem, bars, phases);
         if (n > nb) process_range(OP_COPY, s + nb, dd + nb, n - nb, tid, kThreads);
       } else {
-        process_range(cur.op, s, dd, n, tid, kThreads);
+        process_range(cur.op, s, dd, n, tid, kThreads, cur.scale);
       }
     }
     __syncthreads();
@@ -360,17 +442,19 @@ struct OneShotArgs {
   uint64_t* flag;
   uint64_t flag_val;
   uint32_t op;
+  float scale;
 };
 __global__ void __launch_bounds__(kThreads, 1) bnet_nvl_oneshot_kernel(OneShotArgs a) {
   const uint32_t crank = ptx::cluster_ctarank();
   const uint32_t csize = ptx::cluster_nctarank();
   if (a.op != OP_FLUSH) {
-    size_t units = (a.nbytes + 15) >> 4;
+    const size_t unit = src_unit_for(a.op);
+    size_t units = (a.nbytes + unit - 1) / unit;
     size_t per = (units + csize - 1) / csize;
-    size_t b0 = (size_t)crank * per * 16, b1 = b0 + per * 16;
+    size_t b0 = (size_t)crank * per * unit, b1 = b0 + per * unit;
     if (b0 > a.nbytes) b0 = a.nbytes;
     if (b1 > a.nbytes) b1 = a.nbytes;
-    process_range(a.op, a.src + b0, a.dst + dst_offset_for(a.op, b0), b1 - b0, threadIdx.x, kThreads);
+    process_range(a.op, a.src + b0, a.dst + dst_offset_for(a.op, b0), b1 - b0, threadIdx.x, kThreads, a.scale);
   }
   __syncthreads();
   ptx::cluster_sync();
@@ -498,12 +582,12 @@ int ensure_running(Exec* e, Stream& s) {
 }
 
 int submit(Exec* e, uint32_t op, const void* src, void* dst, size_t nbytes, uint64_t* flags_dev, uint64_t flag_value,
-           int* nchunks_out) {
+           int* nchunks_out, float scale = 1.0f) {
   std::lock_guard<std::mutex> lk(e->mu);
   int cur = -1;
   cudaGetDevice(&cur);
   if (cur != e->dev) cudaSetDevice(e->dev);
-  size_t unit = (op == OP_RED_ADD_F32 || op == OP_CAST_F32_TO_BF16) ? 32 : 16;   // keep chunk cuts element/vector aligned
+  size_t unit = src_unit_for(op) < 64 ? 64 : src_unit_for(op);   // keep chunk cuts vector aligned on both sides
   size_t cs = chunk_size(nbytes, e->min_chunk, (size_t)e->nclusters);
   cs = (cs + unit - 1) / unit * unit;
   int nchunks = nbytes ? (int)((nbytes + cs - 1) / cs) : 1;
@@ -528,13 +612,14 @@ int submit(Exec* e, uint32_t op, const void* src, void* dst, size_t nbytes, uint
       d.flag = flags_dev + c;
       d.flag_val = flag_value;
       d.op = op;
+      d.scale = scale;
       __atomic_store_n(&d.seq, t + 1, __ATOMIC_RELEASE);
       s.q->tail = t + 1;
       __atomic_thread_fence(__ATOMIC_SEQ_CST);   // publish, then look at the kernel's state (Dekker)
       rc = ensure_running(e, s);
       e->stats.persistent++;
     } else {
-      OneShotArgs a{(const char*)src + off, (char*)dst + dst_offset_for(op, off), n, flags_dev + c, flag_value, op};
+      OneShotArgs a{(const char*)src + off, (char*)dst + dst_offset_for(op, off), n, flags_dev + c, flag_value, op, scale};
       void* args[] = {&a};
       cudaError_t err = launch_cluster(bnet_nvl_oneshot_kernel, e->cluster_size, e->cluster_size, 0, s.stream, args);
       if (err != cudaSuccess) {
@@ -588,6 +673,13 @@ extern "C" __attribute__((visibility("default"))) int bnet_exec_op(int dev, uint
   Exec* e = get_exec(dev);
   if (!e) return -1;
   return submit(e, op, src, dst, src_bytes, flags_dev, flag_value, nchunks);
+}
+
+extern "C" __attribute__((visibility("default"))) int bnet_exec_op_scaled(int dev, uint32_t op, const void* src, void* dst, size_t src_bytes,
+                                   uint64_t* flags_dev, uint64_t flag_value, float scale, int* nchunks) {
+  Exec* e = get_exec(dev);
+  if (!e) return -1;
+  return submit(e, op, src, dst, src_bytes, flags_dev, flag_value, nchunks, scale);
 }
 
 int exec_prepare(int dev) {

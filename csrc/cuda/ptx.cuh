@@ -31,14 +31,14 @@ __device__ __forceinline__ void st_na_f4(float4* p, const float4& v) {
 
 // ---- fire-and-forget reductions (no return value: one packet over NVLink) --------------
 __device__ __forceinline__ void red_add_f32(float* p, float v) {
-  asm volatile("red.global.add.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
+  asm volatile("red.relaxed.sys.global.add.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
 }
 __device__ __forceinline__ void red_add_v4_f32(float* p, const float4& v) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};"
+  asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1,%2,%3,%4};"
                :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 __device__ __forceinline__ void red_add_v4_bf16x2(uint32_t* p, const int4& v) {
-  asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1,%2,%3,%4};"
+  asm volatile("red.relaxed.sys.global.add.noftz.v4.bf16x2 [%0], {%1,%2,%3,%4};"
                :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 

@@ -82,6 +82,26 @@ def job_executor():
         ex.run("red_add_bf16", x, y)
         torch.cuda.synchronize()
         assert torch.allclose(y.float(), ref, rtol=1e-2, atol=1e-2), "red_add_bf16"
+    # fp8 (e4m3) gradient compression: quantise while moving, de-quantise + accumulate on arrival
+    if hasattr(torch, "float8_e4m3fn"):
+        for n in [64, 4096, (1 << 20) + 64]:
+            h = (torch.randn(n, device="cuda") * 3).to(torch.bfloat16)
+            scale = 16.0
+            q = torch.empty(n, device="cuda", dtype=torch.uint8)
+            ex.run("cast_bf16_to_e4m3", h, q, scale=scale)
+            torch.cuda.synchronize()
+            ref_q = (h.float() * scale).clamp(-448, 448).to(torch.float8_e4m3fn)
+            assert torch.equal(q.view(torch.float8_e4m3fn).float(), ref_q.float()), "cast_bf16_to_e4m3"
+            f32 = torch.randn(n, device="cuda")
+            q2 = torch.empty(n, device="cuda", dtype=torch.uint8)
+            ex.run("cast_f32_to_e4m3", f32, q2, scale=scale)
+            torch.cuda.synchronize()
+            assert torch.equal(q2.view(torch.float8_e4m3fn).float(), (f32 * scale).clamp(-448, 448).to(torch.float8_e4m3fn).float())
+            acc = torch.randn(n, device="cuda")
+            ref = acc + ref_q.float() / scale
+            ex.run("acc_e4m3_to_f32", q, acc, scale=1.0 / scale)
+            torch.cuda.synchronize()
+            assert torch.allclose(acc, ref, rtol=1e-6, atol=1e-6), "acc_e4m3_to_f32"
     # bandwidth line (device-local copy through the transport kernel)
     big = torch.empty(256 << 20, device="cuda", dtype=torch.uint8).random_(0, 255)
     out = torch.empty_like(big)
