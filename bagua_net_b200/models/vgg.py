@@ -14,19 +14,38 @@ CFGS = {
 
 class VGG(nn.Module):
     def __init__(self, cfg="vgg16", num_classes: int = 1000, batch_norm: bool = False, dropout: float = 0.5,
-                 width_div: int = 1, fc_dim: int = 4096, image_size: int = 224):
+                 width_div: int = 1, fc_dim: int = 4096, image_size: int = 224, fused: bool = False):
+        """fused=True builds the feature extractor from bagua_net_b200.ops.ConvBiasReLU blocks: bias, ReLU,
+        2x2 max-pool, their backward and the bias-gradient reduction run as one sm_100a pass each."""
         super().__init__()
         layers, cin = [], 3
-        for v in CFGS[cfg] if isinstance(cfg, str) else cfg:
-            if v == "M":
-                layers.append(nn.MaxPool2d(2, 2))
-            else:
+        spec = list(CFGS[cfg] if isinstance(cfg, str) else cfg)
+        if fused and not batch_norm:
+            from ..ops.fused_nn import ConvBiasReLU
+
+            i = 0
+            while i < len(spec):
+                v = spec[i]
+                if v == "M":            # a pool that does not directly follow a convolution
+                    layers.append(nn.MaxPool2d(2, 2))
+                    i += 1
+                    continue
                 cout = max(8, v // width_div)
-                layers.append(nn.Conv2d(cin, cout, 3, padding=1))
-                if batch_norm:
-                    layers.append(nn.BatchNorm2d(cout))
-                layers.append(nn.ReLU(inplace=True))
+                pool = i + 1 < len(spec) and spec[i + 1] == "M"
+                layers.append(ConvBiasReLU(cin, cout, 3, 1, 1, pool=pool))
                 cin = cout
+                i += 2 if pool else 1
+        else:
+            for v in spec:
+                if v == "M":
+                    layers.append(nn.MaxPool2d(2, 2))
+                else:
+                    cout = max(8, v // width_div)
+                    layers.append(nn.Conv2d(cin, cout, 3, padding=1))
+                    if batch_norm:
+                        layers.append(nn.BatchNorm2d(cout))
+                    layers.append(nn.ReLU(inplace=True))
+                    cin = cout
         self.features = nn.Sequential(*layers)
         side = image_size // 32
         self.avgpool = nn.AdaptiveAvgPool2d((side, side)) if image_size % 32 else nn.Identity()

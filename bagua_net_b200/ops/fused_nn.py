@@ -1,0 +1,153 @@
+"""Fused conv-block layers (csrc/cuda/nn_kernels.cu): everything memory-bound that follows a
+convolution is folded into one sm_100a pass in forward and one in backward.
+
+    ConvBiasReLU      y = relu(conv(x, w) + b)
+    ConvBiasReLUPool  p = maxpool2x2(relu(conv(x, w) + b))      (y is never written to HBM)
+
+The convolution itself stays a library call (cuDNN implicit GEMM on the tensor cores); the bias
+add, ReLU, 2x2 max-pool, their backward passes and the bias-gradient reduction are ours.
+Inputs must be channels_last with C_out a multiple of 8 (bf16) / 4 (fp32); otherwise the layer
+falls back to the eager PyTorch ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+from torch import nn
+
+from ..utils.native import load
+
+_DT = {torch.float32: 0, torch.bfloat16: 1}
+LAUNCHES = 0          # kernels of ours launched by this module (bench.py reports it)
+_lib = None
+
+
+def _L():
+    global _lib
+    if _lib is None:
+        _lib = load()
+        vp, ll, i = C.c_void_p, C.c_longlong, C.c_int
+        _lib.bnet_nn_bias_relu.argtypes = [vp, vp, ll, i, i, vp]
+        _lib.bnet_nn_relu_bwd_bias_grad.argtypes = [vp, vp, vp, vp, ll, i, i, vp]
+        _lib.bnet_nn_bias_relu_pool_fwd.argtypes = [vp, vp, vp, vp, i, i, i, i, i, vp]
+        _lib.bnet_nn_pool_relu_bwd_bias_grad.argtypes = [vp, vp, vp, vp, i, i, i, i, i, vp]
+    return _lib
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk(rc, what):
+    global LAUNCHES
+    if rc < 0:
+        raise RuntimeError(f"bnet kernel {what} failed (rc={rc})")
+    LAUNCHES += rc
+
+
+def _nhwc(t: torch.Tensor) -> bool:
+    return t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last)
+
+
+def _supported(x: torch.Tensor, cout: int) -> bool:
+    return x.is_cuda and x.dtype in _DT and cout % (8 if x.dtype == torch.bfloat16 else 4) == 0
+
+
+def _conv(x, w, stride, padding):
+    return torch.ops.aten.convolution(x, w, None, stride, padding, [1, 1], False, [0, 0], 1)
+
+
+def _conv_backward(gz, x, w, stride, padding, need_x):
+    gx, gw, _ = torch.ops.aten.convolution_backward(gz, x, w, None, stride, padding, [1, 1], False, [0, 0], 1,
+                                                    [need_x, True, False])
+    return gx, gw
+
+
+class _ConvBiasReLU(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, stride, padding):
+        z = _conv(x, w, stride, padding)
+        if not _nhwc(z):
+            z = z.contiguous(memory_format=torch.channels_last)
+        n, c, h, wd = z.shape
+        _chk(_L().bnet_nn_bias_relu(z.data_ptr(), b.data_ptr(), n * h * wd, c, _DT[z.dtype], _stream()), "bias_relu")
+        ctx.save_for_backward(x, w, z)
+        ctx.conv = (stride, padding)
+        return z
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, y = ctx.saved_tensors
+        stride, padding = ctx.conv
+        if not _nhwc(gy):
+            gy = gy.contiguous(memory_format=torch.channels_last)
+        n, c, h, wd = y.shape
+        gb = torch.zeros(c, device=y.device, dtype=torch.float32)
+        gz = torch.empty_like(gy)
+        _chk(_L().bnet_nn_relu_bwd_bias_grad(gy.data_ptr(), y.data_ptr(), gz.data_ptr(), gb.data_ptr(), n * h * wd, c,
+                                             _DT[y.dtype], _stream()), "relu_bwd_bias_grad")
+        gx, gw = _conv_backward(gz, x, w, stride, padding, ctx.needs_input_grad[0])
+        return gx, gw, gb.to(w.dtype), None, None
+
+
+class _ConvBiasReLUPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, stride, padding):
+        z = _conv(x, w, stride, padding)
+        if not _nhwc(z):
+            z = z.contiguous(memory_format=torch.channels_last)
+        n, c, h, wd = z.shape
+        p = torch.empty((n, c, h // 2, wd // 2), device=z.device, dtype=z.dtype, memory_format=torch.channels_last)
+        idx = torch.empty(n * (h // 2) * (wd // 2) * c, device=z.device, dtype=torch.uint8)
+        _chk(_L().bnet_nn_bias_relu_pool_fwd(z.data_ptr(), b.data_ptr(), p.data_ptr(), idx.data_ptr(), n, h, wd, c,
+                                             _DT[z.dtype], _stream()), "bias_relu_pool_fwd")
+        ctx.save_for_backward(x, w, idx)
+        ctx.conv = (stride, padding)
+        ctx.zshape = (n, c, h, wd)
+        return p
+
+    @staticmethod
+    def backward(ctx, gp):
+        x, w, idx = ctx.saved_tensors
+        stride, padding = ctx.conv
+        n, c, h, wd = ctx.zshape
+        if not _nhwc(gp):
+            gp = gp.contiguous(memory_format=torch.channels_last)
+        gb = torch.zeros(c, device=gp.device, dtype=torch.float32)
+        gz = torch.empty((n, c, h, wd), device=gp.device, dtype=gp.dtype, memory_format=torch.channels_last)
+        _chk(_L().bnet_nn_pool_relu_bwd_bias_grad(gp.data_ptr(), idx.data_ptr(), gz.data_ptr(), gb.data_ptr(), n, h, wd, c,
+                                                  _DT[gp.dtype], _stream()), "pool_relu_bwd_bias_grad")
+        gx, gw = _conv_backward(gz, x, w, stride, padding, ctx.needs_input_grad[0])
+        return gx, gw, gb.to(w.dtype), None, None
+
+
+class ConvBiasReLU(nn.Module):
+    """3x3 (or any) convolution + bias + ReLU, optionally followed by a 2x2/stride-2 max-pool."""
+
+    def __init__(self, cin: int, cout: int, kernel_size: int = 3, stride: int = 1, padding: int = 1, pool: bool = False):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, kernel_size, stride, padding)
+        self.pool = pool
+
+    @property
+    def weight(self):
+        return self.conv.weight
+
+    @property
+    def bias(self):
+        return self.conv.bias
+
+    def forward(self, x):
+        c = self.conv
+        k, s_, p_ = c.kernel_size, c.stride, c.padding
+        ho = (x.shape[2] + 2 * p_[0] - k[0]) // s_[0] + 1
+        wo = (x.shape[3] + 2 * p_[1] - k[1]) // s_[1] + 1
+        if _supported(x, c.out_channels) and c.groups == 1 and c.dilation == (1, 1) and (
+                not self.pool or (ho % 2 == 0 and wo % 2 == 0)):
+            if not _nhwc(x):
+                x = x.contiguous(memory_format=torch.channels_last)
+            fn = _ConvBiasReLUPool if self.pool else _ConvBiasReLU
+            return fn.apply(x, c.weight, c.bias, list(c.stride), list(c.padding))
+        y = torch.relu(c(x))
+        return nn.functional.max_pool2d(y, 2, 2) if self.pool else y

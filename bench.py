@@ -125,6 +125,7 @@ def main() -> int:
     ap.add_argument("--bucket-mb", type=float, default=64.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the all-reduce busbw side measurement")
+    ap.add_argument("--no-fused", action="store_true", help="eager bias/ReLU/pool instead of the fused sm_100a conv blocks")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -154,7 +155,10 @@ def main() -> int:
     torch.backends.cudnn.allow_tf32 = True
     torch.manual_seed(1234)
 
-    model = build_model(args.model).to(dev).to(torch.bfloat16).to(memory_format=torch.channels_last)
+    # our arm trains the model built from our fused conv blocks; the stock-NCCL arms train the plain eager model
+    fused = args.comm == "bnet" and not args.no_fused and args.model.startswith("vgg")
+    model = build_model(args.model, **({"fused": True} if fused else {}))
+    model = model.to(dev).to(torch.bfloat16).to(memory_format=torch.channels_last)
     model.train()
     lr, mom, wd = 0.01, 0.9, 1e-4
     n_params = sum(p.numel() for p in model.parameters())
@@ -171,7 +175,9 @@ def main() -> int:
             return engine.train_step_from_host(xh, yh)
 
         def launches():
-            return comm.launches
+            from bagua_net_b200.ops import fused_nn
+
+            return comm.launches + fused_nn.LAUNCHES
         path = ("nvls" if comm.has_multicast else "p2p") if world > 1 else "single"
     else:
         ddp = (torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
@@ -272,7 +278,7 @@ def main() -> int:
             "higher_is_better": True, "scaling": "weak", "vs_baseline": round(img_s / BASELINE_IMG_S, 4),
             "dtype": "bf16", "data": "synthetic (random images/labels, random-init weights)",
             "config": {"model": args.model, "global_batch": world * B, "per_gpu_batch": B, "seq_len": None,
-                       "image": [3, S, S], "parallelism": f"dp{world}", "comm": args.comm, "path": path,
+                       "image": [3, S, S], "parallelism": f"dp{world}", "comm": args.comm, "path": path, "fused_conv_blocks": fused,
                        "optimizer": f"sgd(lr={lr},momentum={mom},wd={wd}) fused into the collective" if args.comm == "bnet"
                        else f"torch.optim.SGD(lr={lr},momentum={mom},wd={wd})",
                        "params": n_params, "bucket_mb": args.bucket_mb,

@@ -4,7 +4,7 @@
 events, max over ranks, reported against the NVLink roofline.
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
-      bench/allreduce_sweep.py [--min 1K --max 1G --dtype bf16 --blocks 0 --json out.json]
+      bench/allreduce_sweep.py [--lo 1K --hi 1G --dtype bf16 --blocks 0 --json out.json]
 
 Roofline: an in-switch (NVLS) all-reduce of S bytes moves S(1+1/n) bytes in and out of every GPU;
 a P2P two-shot moves 2S(n-1)/n.  Link bandwidth = the measured 770 GB/s per direction per GPU
@@ -34,8 +34,8 @@ def parse_size(s: str) -> int:
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--min", default="1K")
-    ap.add_argument("--max", default="1G")
+    ap.add_argument("--lo", default="1K")
+    ap.add_argument("--hi", default="1G")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32", "f16"])
     ap.add_argument("--blocks", default="0", help="comma list of CTA counts to try for the bnet kernels (0 = default)")
     ap.add_argument("--algos", default="nvls,p2p,oneshot,nccl")
@@ -49,7 +49,7 @@ def main():
     dev = torch.device("cuda", torch.cuda.current_device())
     dtype = {"bf16": torch.bfloat16, "f32": torch.float32, "f16": torch.float16}[a.dtype]
     es = torch.empty((), dtype=dtype).element_size()
-    lo, hi = parse_size(a.min), parse_size(a.max)
+    lo, hi = parse_size(a.lo), parse_size(a.hi)
     comm = SymmComm(hi + (64 << 20))
     algos = [x for x in a.algos.split(",") if x]
     if not comm.has_multicast and "nvls" in algos:
@@ -100,9 +100,10 @@ def main():
                 algbw = nbytes / us / 1e3
                 busbw = algbw * 2 * (world - 1) / world
                 # time lower bound per algorithm at link bandwidth
-                moved = nbytes * (1 + 1 / world) if algo in ("nvls",) else nbytes * 2 * (world - 1) / world
-                if algo == "oneshot":
-                    moved = nbytes * (world - 1)
+                # bytes per direction per GPU: NVLS S(1+1/n); direct two-shot S(n-1)/n (peer loads in,
+                # peer stores out, full duplex); one-shot S(n-1) in; NCCL ring 2S(n-1)/n
+                moved = {"nvls": nbytes * (1 + 1 / world), "p2p": nbytes * (world - 1) / world,
+                         "oneshot": nbytes * (world - 1)}.get(algo, nbytes * 2 * (world - 1) / world)
                 frac = (moved / (LINK_GBS * 1e3)) / us
                 rows.append({"bytes": nbytes, "algo": algo, "ctas": nb, "us": us, "algbw": algbw, "busbw": busbw, "roofline_frac": frac})
                 if rank == 0:

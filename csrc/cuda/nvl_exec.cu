@@ -516,9 +516,9 @@ Exec* get_exec(int dev) {
   g_exec[dev] = e;
   e->dev = dev;
   const Config& cfg = Config::get();
-  long long nc = env_int("NCLUSTERS", 4);
+  long long nc = env_int("NCLUSTERS", 8);
   e->nclusters = (int)(nc < 1 ? 1 : nc > kMaxChunksPerJob ? kMaxChunksPerJob : nc);
-  long long cs = env_int("CLUSTER_SIZE", 2);
+  long long cs = env_int("CLUSTER_SIZE", 4);
   e->cluster_size = (int)(cs < 1 ? 1 : cs > 8 ? 8 : cs);
   e->min_chunk = (size_t)env_int("DEV_MIN_CHUNKSIZE", (long long)(cfg.min_chunksize < 262144 ? cfg.min_chunksize : 262144));
   if (e->min_chunk < 16) e->min_chunk = 16;
@@ -543,6 +543,45 @@ Exec* get_exec(int dev) {
     cudaError_t err = cudaFuncSetAttribute(bnet_nvl_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            kTmaStages * kTmaStageBytes);
     if (err != cudaSuccess) { cudaGetLastError(); e->tma = false; }
+  }
+  if (good) {
+    // CUDA loads kernels lazily, and loading one may need to synchronise the context
+    // (measured: profiles/blocking_calls.txt — a first launch waits for every running kernel).
+    // On the data path that is a dead-lock: the NCCL kernel that is running is waiting for this
+    // very transfer.  So load AND run every kernel once now, in the setup phase.
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, bnet_nvl_stream_kernel<false>);
+    cudaFuncGetAttributes(&fa, bnet_nvl_stream_kernel<true>);
+    cudaFuncGetAttributes(&fa, bnet_nvl_oneshot_kernel);
+    void* wdp = nullptr;
+    uint64_t* wflag = (uint64_t*)host_alloc_mapped(64, &wdp);
+    if (wflag) {
+      OneShotArgs a{nullptr, nullptr, 0, (uint64_t*)wdp, 1, OP_FLUSH, 1.0f};
+      void* args[] = {&a};
+      cudaError_t err = launch_cluster(bnet_nvl_oneshot_kernel, e->cluster_size, e->cluster_size, 0, e->streams[0].stream, args);
+      for (Stream& s : e->streams) {
+        // persistent kernel: start it with stop already requested so it loads, runs and leaves
+        __atomic_store_n(&s.q->stop, 1u, __ATOMIC_RELEASE);
+        __atomic_store_n(&s.q->state, ST_RUNNING, __ATOMIC_RELEASE);
+        ClusterQ* qd = s.q_dev;
+        uint64_t idle = e->idle_ns, wd = 0;
+        void* pargs[] = {&qd, &idle, &wd};
+        cudaError_t e2 = e->tma ? launch_cluster(bnet_nvl_stream_kernel<true>, e->cluster_size, e->cluster_size,
+                                                 kTmaStages * kTmaStageBytes, s.stream, pargs)
+                                : launch_cluster(bnet_nvl_stream_kernel<false>, e->cluster_size, e->cluster_size, 0,
+                                                 s.stream, pargs);
+        if (e2 != cudaSuccess) err = e2;
+        if (cudaStreamSynchronize(s.stream) != cudaSuccess) err = cudaErrorUnknown;
+        __atomic_store_n(&s.q->stop, 0u, __ATOMIC_RELEASE);
+        __atomic_store_n(&s.q->state, ST_EXITED, __ATOMIC_RELEASE);
+      }
+      if (err != cudaSuccess || *(volatile uint64_t*)wflag != 1) {
+        cudaGetLastError();
+        BNET_WARN("nvl executor: warm-up launch failed (%s)", cudaGetErrorString(err));
+        good = false;
+      }
+      // (the 64-byte flag is deliberately not freed: cudaFreeHost waits for running kernels)
+    }
   }
   if (cur != dev && cur >= 0) cudaSetDevice(cur);
   if (!good) cudaGetLastError();

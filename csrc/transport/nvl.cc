@@ -184,6 +184,7 @@ class NvlComm : public Comm {
     (kind == SEND ? shm_->sender_closed : shm_->receiver_closed).store(1, std::memory_order_release);
     for (auto& kv : imports_)
       if (kv.second.base) cuda::release_import(kv.second.exp, kv.second.base, kv.second.cookie);
+    for (auto& im : stale_) cuda::release_import(im.exp, im.base, im.cookie);
     for (auto& kv : fds_) close(kv.second);
     for (auto& kv : exports_) cuda::release_export(&kv.second);
     if (flags_) cuda::host_free_mapped(flags_);
@@ -430,7 +431,8 @@ class NvlComm : public Comm {
     if (!(gen & 1)) return nullptr;
     Import& im = imports_[mr_idx];
     if (im.gen != gen) {
-      if (im.base) cuda::release_import(im.exp, im.base, im.cookie);
+      // unmapping waits for running kernels (profiles/blocking_calls.txt): never on the data path
+      if (im.base) stale_.push_back(im);
       im = Import();
       im.gen = gen;
       im.exp = d.exp;
@@ -697,6 +699,7 @@ class NvlComm : public Comm {
   uint64_t* flush_flag_dev_ = nullptr;
   uint64_t flush_seq_ = 0;
   std::map<uint32_t, Import> imports_;
+  std::vector<Import> stale_;
   std::map<uint32_t, int> fds_;
   std::map<uint32_t, uint32_t> fd_gen_;
   std::map<int, cuda::MemExport> exports_;

@@ -249,6 +249,65 @@ def job_ddp_engine():
     teardown()
 
 
+def job_fused_nn():
+    """ConvBiasReLU / ConvBiasReLUPool vs the eager PyTorch chain, forward and backward."""
+    from bagua_net_b200.ops import fused_nn
+    from bagua_net_b200.ops.fused_nn import ConvBiasReLU
+
+    torch.cuda.set_device(0)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    for dtype, tol in ((torch.float32, 2e-4), (torch.bfloat16, 6e-2)):
+        for (cin, cout, hw, pool) in [(3, 64, 32, False), (64, 64, 32, True), (16, 128, 20, True), (32, 512, 14, False),
+                                      (8, 24 if dtype == torch.float32 else 40, 10, True)]:
+            torch.manual_seed(cin * 7 + cout)
+            blk = ConvBiasReLU(cin, cout, 3, 1, 1, pool=pool).cuda().to(dtype).to(memory_format=torch.channels_last)
+            ref = torch.nn.Conv2d(cin, cout, 3, 1, 1).cuda().float()
+            ref.weight.data.copy_(blk.conv.weight.data.float())
+            ref.bias.data.copy_(blk.conv.bias.data.float())
+            x = torch.randn(4, cin, hw, hw, device="cuda")
+            xa = x.to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_(cin != 3)
+            xb = xa.detach().float().requires_grad_(cin != 3)
+            before = fused_nn.LAUNCHES
+            ya = blk(xa)
+            yb = torch.relu(ref(xb))
+            if pool:
+                yb = torch.nn.functional.max_pool2d(yb, 2, 2)
+            assert fused_nn.LAUNCHES > before, "fused kernel did not run"
+            assert ya.shape == yb.shape
+            err = (ya.float() - yb).abs().max().item()
+            assert err < tol * max(1.0, yb.abs().max().item()), f"fwd {dtype} {cin}->{cout} pool={pool}: {err}"
+            g = torch.randn_like(yb)
+            ya.backward(g.to(dtype))
+            yb.backward(g.to(dtype).float())
+            torch.cuda.synchronize()
+            for name, a_, b_ in (("w", blk.conv.weight.grad, ref.weight.grad), ("b", blk.conv.bias.grad, ref.bias.grad)) + (
+                    (("x", xa.grad, xb.grad),) if cin != 3 else ()):
+                e = (a_.float() - b_).abs().max().item()
+                scale = max(1.0, b_.abs().max().item())
+                # bf16: the masks are computed from bf16-rounded activations; allow a few flipped ties
+                assert e < (tol if dtype == torch.float32 else 0.15) * scale, f"bwd {name} {dtype} {cin}->{cout} pool={pool}: {e} / {scale}"
+    # whole model: fused VGG == eager VGG in fp32
+    from bagua_net_b200.models import build_model
+
+    kw = dict(width_div=8, fc_dim=64, image_size=32, num_classes=10, dropout=0.0)
+    torch.manual_seed(3)
+    a = build_model("vgg16", fused=True, **kw).cuda().to(memory_format=torch.channels_last)
+    b = build_model("vgg16", fused=False, **kw).cuda()
+    for pa, pb in zip(a.parameters(), b.parameters()):
+        pb.data.copy_(pa.data)
+    x = torch.randn(4, 3, 32, 32, device="cuda")
+    y = torch.randint(0, 10, (4,), device="cuda")
+    la = torch.nn.functional.cross_entropy(a(x.contiguous(memory_format=torch.channels_last)), y)
+    lb = torch.nn.functional.cross_entropy(b(x), y)
+    la.backward()
+    lb.backward()
+    assert abs(la.item() - lb.item()) < 1e-4, (la.item(), lb.item())
+    for pa, pb in zip(a.parameters(), b.parameters()):
+        assert (pa.grad - pb.grad).abs().max().item() < 1e-3 * max(1.0, pb.grad.abs().max().item())
+    print("fused_nn ok", flush=True)
+
+
 def job_pack_cast():
     from bagua_net_b200.ops import pack_cast
     from bagua_net_b200.parallel import SymmComm

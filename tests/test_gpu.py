@@ -70,6 +70,10 @@ def test_ddp_engine_trains_like_torch_sgd():
     _run_worker("ddp_engine", 1)
 
 
+def test_fused_conv_blocks_match_eager():
+    _run_worker("fused_nn", 1)
+
+
 def test_pack_cast():
     _run_worker("pack_cast", 1)
 
