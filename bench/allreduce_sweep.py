@@ -4,7 +4,7 @@
 events, max over ranks, reported against the NVLink roofline.
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
-      bench/allreduce_sweep.py [--lo 1K --hi 1G --dtype bf16 --blocks 0 --json out.json]
+      bench/allreduce_sweep.py [--min-bytes 1K --max-bytes 1G --dtype bf16 --blocks 0 --json out.json]
 
 Roofline: an in-switch (NVLS) all-reduce of S bytes moves S(1+1/n) bytes in and out of every GPU;
 a P2P two-shot moves 2S(n-1)/n.  Link bandwidth = the measured 770 GB/s per direction per GPU
@@ -34,8 +34,8 @@ def parse_size(s: str) -> int:
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--lo", default="1K")
-    ap.add_argument("--hi", default="1G")
+    ap.add_argument("--min-bytes", default="1K")
+    ap.add_argument("--max-bytes", default="1G")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32", "f16"])
     ap.add_argument("--blocks", default="0", help="comma list of CTA counts to try for the bnet kernels (0 = default)")
     ap.add_argument("--algos", default="nvls,p2p,oneshot,nccl")
@@ -49,7 +49,7 @@ def main():
     dev = torch.device("cuda", torch.cuda.current_device())
     dtype = {"bf16": torch.bfloat16, "f32": torch.float32, "f16": torch.float16}[a.dtype]
     es = torch.empty((), dtype=dtype).element_size()
-    lo, hi = parse_size(a.lo), parse_size(a.hi)
+    lo, hi = parse_size(a.min_bytes), parse_size(a.max_bytes)
     comm = SymmComm(hi + (64 << 20))
     algos = [x for x in a.algos.split(",") if x]
     if not comm.has_multicast and "nvls" in algos:

@@ -6,6 +6,8 @@
 #include <sys/un.h>
 #include <unistd.h>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "core/telemetry.h"
 #include "cuda/cuda_iface.h"
 
@@ -13,6 +15,13 @@ namespace bnet {
 
 // ------------------------------------------------------------------ Comm base
 static std::atomic<uint64_t> g_comm_ids{1};
+
+// BNET_NVTX=1: one NVTX range per request (isend/irecv -> completion), visible in Nsight Systems
+// next to NCCL's own ranges — the on-box replacement for the reference's Jaeger spans.
+static bool nvtx_on() {
+  static const bool on = env_int("NVTX", 0) != 0;
+  return on;
+}
 
 Comm::Comm(Kind k) : kind(k) { id = g_comm_ids.fetch_add(1); }
 Comm::~Comm() {}
@@ -65,6 +74,12 @@ Request* Comm::alloc_req(ReqKind k, void* buf, size_t size, int tag, MemHandle* 
       r.id = rid;
       r.t_post = now_ns();
       memset(r.u, 0, sizeof(r.u));
+      if (nvtx_on() && k != REQ_FLUSH) {
+        char nm[64];
+        snprintf(nm, sizeof(nm), "bnet %s-%llu %zuB", k == REQ_SEND ? "isend" : "irecv", (unsigned long long)id, size);
+        r.nvtx = nvtxRangeStartA(nm);
+        r.nvtx_open = true;
+      }
       Telemetry& T = Telemetry::get();
       r.span = T.tracing() && k != REQ_FLUSH ? T.span_begin(k == REQ_SEND ? SPAN_ISEND : SPAN_IRECV, id, rid, size) : 0;
       if (k != REQ_FLUSH) T.m().hold_on_request.fetch_add(1, std::memory_order_relaxed);
@@ -78,6 +93,10 @@ Request* Comm::alloc_req(ReqKind k, void* buf, size_t size, int tag, MemHandle* 
 
 void Comm::free_req(Request* r) {
   Telemetry& T = Telemetry::get();
+  if (r->nvtx_open) {
+    nvtxRangeEnd(r->nvtx);
+    r->nvtx_open = false;
+  }
   if (r->span) T.span_end(r->span, r->nbytes.load(std::memory_order_relaxed));
   if (r->kind != REQ_FLUSH) T.m().hold_on_request.fetch_sub(1, std::memory_order_relaxed);
   r->in_use.store(0, std::memory_order_release);

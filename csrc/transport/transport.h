@@ -87,6 +87,8 @@ struct Request {
   uint64_t id = 0;
   uint64_t span = 0;
   uint64_t t_post = 0;
+  uint64_t nvtx = 0;
+  bool nvtx_open = false;
   uint64_t u[6] = {0, 0, 0, 0, 0, 0};   // transport scratch
 
   bool complete() const { return ndone.load(std::memory_order_acquire) == nsub.load(std::memory_order_acquire); }

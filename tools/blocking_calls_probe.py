@@ -186,6 +186,86 @@ def main():
     exec_copy()
     probe("bnet executor: cluster kernel launch + completion", exec_copy)
 
+    # ---- second question: while ANOTHER thread sits in a device-synchronising call (cudaFree as issued
+    # by torch's emptyCache after a cuDNN benchmark, ...), can this thread still launch / map / copy?
+    import threading
+
+    warm = torch.ones(1 << 20, device="cuda")
+    with torch.cuda.stream(side):
+        warm.add_(1)
+    torch.cuda.synchronize()
+
+    def concurrent(xname, xfn, yname, yfn):
+        torch.cuda.synchronize()
+        with torch.cuda.stream(spin_stream):
+            torch.cuda._sleep(cycles)
+        t0 = time.perf_counter()
+        xdone = {}
+
+        def run_x():
+            xfn()
+            xdone["t"] = time.perf_counter() - t0
+
+        th = threading.Thread(target=run_x)
+        th.start()
+        time.sleep(0.05)
+        ty0 = time.perf_counter()
+        try:
+            extra = yfn()
+        except Exception as e:   # noqa: BLE001
+            extra = f"EXC {e}"
+        ty = time.perf_counter() - ty0
+        th.join()
+        torch.cuda.synchronize()
+        total = time.perf_counter() - t0
+        verdict = "BLOCKED" if ty > 0.5 * total else "ok"
+        line = (f"[{xname} in thread A: returned after {xdone.get('t', -1) * 1e3:7.1f} ms]  {yname}: {ty * 1e3:8.2f} ms  {verdict}  {extra or ''}")
+        results.append((f"A={xname} | B={yname}", ty * 1e3, total * 1e3, verdict, extra))
+        print(line, flush=True)
+
+    def y_launch():
+        with torch.cuda.stream(side):
+            warm.add_(1)
+            ev = torch.cuda.Event()
+            ev.record()
+        t0 = time.perf_counter()
+        while not ev.query() and time.perf_counter() - t0 < 3:
+            pass
+        return f"kernel completed {(time.perf_counter() - t0) * 1e3:.1f} ms after launch returned"
+
+    def y_exec():
+        return exec_copy()
+
+    def y_import():
+        return " ".join([imp(2), reserve(2), do_map(2), set_access(2)])
+
+    def y_memcpy():
+        h = state.setdefault("pinned", torch.empty(1 << 20, dtype=torch.uint8).pin_memory())
+        with torch.cuda.stream(side):
+            h.to("cuda", non_blocking=True)
+            side.synchronize()
+        return ""
+
+    def x_cudafree():
+        err, p = cudart.cudaMalloc(256 << 20)
+        state["tofree"] = p
+
+    xs = {
+        "cudaFree": lambda: cudart.cudaFree(state.pop("tofree")),
+        "cudaDeviceSynchronize": lambda: cudart.cudaDeviceSynchronize(),
+        "torch.cuda.empty_cache": lambda: torch.cuda.empty_cache(),
+    }
+    for xname, xfn in xs.items():
+        for yname, yfn in (("kernel launch (loaded)", y_launch), ("bnet cluster kernel", y_exec), ("cudaMemcpyAsync+sync", y_memcpy)):
+            if xname == "cudaFree":
+                x_cudafree()
+            if xname == "torch.cuda.empty_cache":
+                _ = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+                del _
+            concurrent(xname, xfn, yname, yfn)
+    x_cudafree()
+    concurrent("cudaFree", xs["cudaFree"], "cuMem import+map+setaccess", y_import)
+
     conn.send(b"x")
     proc.wait(timeout=20)
     os.unlink(path)
