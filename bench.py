@@ -180,6 +180,17 @@ def main() -> int:
             return comm.launches + fused_nn.LAUNCHES
         path = ("nvls" if comm.has_multicast else "p2p") if world > 1 else "single"
     else:
+        if args.comm == "nccl-plugin":
+            # Let cuDNN pick its algorithms (and torch's allocator settle) BEFORE any collective is in
+            # flight: the benchmark search ends in emptyCache() -> cudaFree, and a cudaFree holds up every
+            # kernel launch in the process (profiles/blocking_calls.txt) — including the transport's.
+            xw = torch.randn(args.batch, 3, args.image, args.image, device=dev, dtype=torch.bfloat16)
+            xw = xw.contiguous(memory_format=torch.channels_last)
+            for _ in range(2):
+                torch.nn.functional.cross_entropy(model(xw).float(), torch.zeros(args.batch, dtype=torch.long, device=dev)).backward()
+            model.zero_grad(set_to_none=True)
+            del xw
+            torch.cuda.synchronize()
         ddp = (torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
                if world > 1 else model)
         opt = torch.optim.SGD(model.parameters(), lr=lr, momentum=mom, weight_decay=wd)

@@ -334,7 +334,7 @@ __device__ void tma_copy_range(const char* src, char* dst, size_t n, char* smem,
 
 template <bool kUseTma>
 __global__ void __launch_bounds__(kThreads, 1)
-bnet_nvl_stream_kernel(ClusterQ* q, uint64_t idle_ns, uint64_t watchdog_ns) {
+bnet_nvl_stream_kernel(ClusterQ* q, uint64_t idle_ns, uint64_t first_idle_ns) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ SmemDesc sd;
   __shared__ __align__(8) uint64_t bars[kTmaStages];
@@ -354,6 +354,9 @@ bnet_nvl_stream_kernel(ClusterQ* q, uint64_t idle_ns, uint64_t watchdog_ns) {
 
   uint64_t head = q->head;            // same value in every CTA of the cluster
   uint64_t last_work = ptx::globaltimer();
+  // armed at connection setup: wait longer for the FIRST job so that it needs no launch on the
+  // data path (a launch can be held up by a cudaFree elsewhere in the process: profiles/blocking_calls.txt)
+  uint64_t idle_limit = first_idle_ns > idle_ns ? first_idle_ns : idle_ns;
   for (;;) {
     // ---- leader: wait for the next descriptor, publish it to every CTA of the cluster
     if (crank == 0 && tid == 0) {
@@ -366,7 +369,7 @@ bnet_nvl_stream_kernel(ClusterQ* q, uint64_t idle_ns, uint64_t watchdog_ns) {
         if (ptx::ld_acquire_sys_u64(&d->seq) == head + 1) break;
         uint64_t now = ptx::globaltimer();
         if (ptx::ld_relaxed_sys_u32((const uint32_t*)&q->stop)) { loc.quit = 1; break; }
-        if (now - last_work > idle_ns) {
+        if (now - last_work > idle_limit) {
           // leave unless the host published work while we were deciding (store, fence, re-check)
           ptx::st_release_sys_u32((uint32_t*)&q->state, ST_EXITING);
           ptx::fence_sc_sys();
@@ -427,9 +430,9 @@ bnet_nvl_stream_kernel(ClusterQ* q, uint64_t idle_ns, uint64_t watchdog_ns) {
       ptx::st_release_sys_u64(flag, fv);           // ... before the chunk's completion word
       ptx::st_release_sys_u64((uint64_t*)&q->head, head + 1);
       last_work = ptx::globaltimer();
+      idle_limit = idle_ns;
     }
     head++;
-    (void)watchdog_ns;
   }
   if (crank == 0 && tid == 0) ptx::st_release_sys_u32((uint32_t*)&q->state, ST_EXITED);
 }
@@ -481,7 +484,8 @@ struct Exec {
   int nclusters = 4;
   int cluster_size = 2;
   size_t min_chunk = 1 << 20;
-  uint64_t idle_ns = 200000;
+  uint64_t idle_ns = 1000000;
+  uint64_t arm_ns = 50000000;
   size_t rr = 0;               // persists across messages
   std::vector<Stream> streams;
   std::mutex mu;
@@ -524,7 +528,8 @@ Exec* get_exec(int dev) {
   if (e->min_chunk < 16) e->min_chunk = 16;
   e->persistent = env_int("PERSISTENT", 1) != 0;
   e->tma = env_str("COPY_ENGINE", "ldst") == "tma";
-  e->idle_ns = (uint64_t)env_int("KERNEL_IDLE_US", 200) * 1000ull;
+  e->idle_ns = (uint64_t)env_int("KERNEL_IDLE_US", 1000) * 1000ull;
+  e->arm_ns = (uint64_t)env_int("KERNEL_ARM_MS", 50) * 1000000ull;
   int cur = -1;
   cudaGetDevice(&cur);
   if (cur != dev) cudaSetDevice(dev);
@@ -592,7 +597,7 @@ Exec* get_exec(int dev) {
   return good ? e : nullptr;
 }
 
-int ensure_running(Exec* e, Stream& s) {
+int ensure_running(Exec* e, Stream& s, bool arm = false) {
   for (int spin = 0;; spin++) {
     uint32_t st = __atomic_load_n(&s.q->state, __ATOMIC_ACQUIRE);
     if (st == ST_RUNNING) return 0;
@@ -603,7 +608,7 @@ int ensure_running(Exec* e, Stream& s) {
     // EXITED: (re)launch
     __atomic_store_n(&s.q->state, ST_RUNNING, __ATOMIC_RELEASE);
     ClusterQ* qd = s.q_dev;
-    uint64_t idle = e->idle_ns, wd = 0;
+    uint64_t idle = e->idle_ns, wd = arm ? e->arm_ns : 0;
     void* args[] = {&qd, &idle, &wd};
     cudaError_t err = e->tma ? launch_cluster(bnet_nvl_stream_kernel<true>, e->cluster_size, e->cluster_size,
                                               kTmaStages * kTmaStageBytes, s.stream, args)
@@ -723,7 +728,21 @@ extern "C" __attribute__((visibility("default"))) int bnet_exec_op_scaled(int de
 
 int exec_prepare(int dev) {
   if (fake()) return 0;
-  return get_exec(dev) ? 0 : -1;
+  Exec* e = get_exec(dev);
+  if (!e) return -1;
+  if (!e->persistent || e->arm_ns == 0) return 0;
+  // Arm: have the stream kernels resident BEFORE the first message so that the data path
+  // needs no kernel launch (one that could be held up by a device-synchronising call
+  // elsewhere in the process while the NCCL kernel it serves is already waiting).
+  std::lock_guard<std::mutex> lk(e->mu);
+  int cur = -1;
+  cudaGetDevice(&cur);
+  if (cur != e->dev) cudaSetDevice(e->dev);
+  int rc = 0;
+  for (Stream& s : e->streams)
+    if (ensure_running(e, s, /*arm=*/true) != 0) rc = -1;
+  if (cur != e->dev && cur >= 0) cudaSetDevice(cur);
+  return rc;
 }
 
 void exec_stats(ExecStats* out) {

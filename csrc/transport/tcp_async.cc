@@ -120,6 +120,7 @@ class AsyncComm : public Comm {
     mh->type = type;
     mh->id = next_mr.fetch_add(1);
     mh->owner = this;
+    if (type == NCCL_PTR_CUDA) cuda::pointer_is_device(data, &mh->dev);
     *out = mh;
     return kOk;
   }
@@ -150,7 +151,7 @@ class AsyncComm : public Comm {
           io_base_ = (char*)cur_->buf;
           if (cuda_cur_ && cur_->size) {
             stage_.resize(cur_->size);
-            if (cuda::memcpy_sync(stage_.data(), cur_->buf, cur_->size, -1) != 0) { finish(kErrCuda); continue; }
+            if (cuda::memcpy_sync(stage_.data(), cur_->buf, cur_->size, cur_->mh->dev) != 0) { finish(kErrCuda); continue; }
             io_base_ = stage_.data();
           }
         }
@@ -225,7 +226,7 @@ class AsyncComm : public Comm {
         if (st_ != DATA) continue;
         if (left_ == 0) {
           int st = kOk;
-          if (kind == RECV && cuda_cur_ && len_ && cuda::memcpy_sync(cur_->buf, stage_.data(), len_, -1) != 0) st = kErrCuda;
+          if (kind == RECV && cuda_cur_ && len_ && cuda::memcpy_sync(cur_->buf, stage_.data(), len_, cur_->mh->dev) != 0) st = kErrCuda;
           cur_->nbytes.store(len_, std::memory_order_relaxed);
           finish(st);
           continue;

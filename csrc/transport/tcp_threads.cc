@@ -38,6 +38,7 @@ struct Chunk {
   size_t n;
   Request* r;
   bool cuda;
+  int dev;
 };
 
 struct Fault {   // BNET_FAULT_INJECT="send_drop_after=<chunks>" | "recv_drop_after=<chunks>"
@@ -101,6 +102,7 @@ class TcpThreadsComm : public Comm {
     mh->type = type;
     mh->id = next_mr.fetch_add(1);
     mh->owner = this;
+    if (type == NCCL_PTR_CUDA) cuda::pointer_is_device(data, &mh->dev);
     *out = mh;
     return kOk;
   }
@@ -158,7 +160,7 @@ class TcpThreadsComm : public Comm {
         for (size_t off = 0; off < r->size; off += cs) {
           size_t n = r->size - off < cs ? r->size - off : cs;
           r->nsub.fetch_add(1, std::memory_order_release);
-          streams_[rr]->push(Chunk{base + off, n, r, cu});
+          streams_[rr]->push(Chunk{base + off, n, r, cu, cu ? r->mh->dev : -1});
           rr = (rr + 1) % ns;
         }
       }
@@ -186,7 +188,7 @@ class TcpThreadsComm : public Comm {
           if (!bounce) st = kErrCuda;
           for (size_t off = 0; off < c.n && !st; off += kBounceBytes) {
             size_t n = c.n - off < kBounceBytes ? c.n - off : kBounceBytes;
-            if (cuda::memcpy_sync(bounce, c.p + off, n, -1) != 0) st = kErrCuda;
+            if (cuda::memcpy_sync(bounce, c.p + off, n, c.dev) != 0) st = kErrCuda;
             else st = write_all(fds_[i], bounce, n, &abort_, timeout_ms_);
           }
         }
@@ -227,7 +229,7 @@ class TcpThreadsComm : public Comm {
         for (size_t off = 0; off < len; off += cs) {
           size_t n = len - off < cs ? len - off : cs;
           r->nsub.fetch_add(1, std::memory_order_release);
-          streams_[rr]->push(Chunk{base + off, n, r, cu});
+          streams_[rr]->push(Chunk{base + off, n, r, cu, cu ? r->mh->dev : -1});
           rr = (rr + 1) % ns;
         }
       }
@@ -253,7 +255,7 @@ class TcpThreadsComm : public Comm {
           for (size_t off = 0; off < c.n && !st; off += kBounceBytes) {
             size_t n = c.n - off < kBounceBytes ? c.n - off : kBounceBytes;
             st = read_exact(fds_[i], bounce, n, &abort_, timeout_ms_);
-            if (!st && cuda::memcpy_sync(c.p + off, bounce, n, -1) != 0) st = kErrCuda;
+            if (!st && cuda::memcpy_sync(c.p + off, bounce, n, c.dev) != 0) st = kErrCuda;
           }
         }
       }

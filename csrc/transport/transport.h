@@ -63,6 +63,7 @@ struct MemHandle {
   size_t size = 0;
   int type = NCCL_PTR_HOST;
   uint32_t id = 0;
+  int dev = -1;             // CUDA device of the buffer (staged copies run on worker threads)
   Comm* owner = nullptr;
   void* priv = nullptr;     // transport specific (NVL: export record)
 };

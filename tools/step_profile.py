@@ -22,10 +22,11 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--out", default="")
+    ap.add_argument("--fused", action="store_true", help="fused conv blocks (bnet arm default in bench.py)")
     a = ap.parse_args()
     torch.cuda.set_device(0)
     torch.backends.cudnn.benchmark = True
-    model = build_model(a.model).cuda().to(torch.bfloat16).to(memory_format=torch.channels_last)
+    model = build_model(a.model, **({"fused": True} if a.fused else {})).cuda().to(torch.bfloat16).to(memory_format=torch.channels_last)
     x = torch.randn(a.batch, 3, 224, 224, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
     y = torch.randint(0, 1000, (a.batch,), device="cuda")
     if a.comm == "bnet":
@@ -60,7 +61,7 @@ def main():
             agg[name][1] += ev.device_time_total
             busy += ev.device_time_total
     busy_ms = busy / 1e3 / a.steps
-    lines = [f"# {a.model} batch {a.batch} comm={a.comm}: step {wall_ms:.3f} ms (CUDA events), sum of kernel time {busy_ms:.3f} ms "
+    lines = [f"# {a.model} batch {a.batch} comm={a.comm} fused={a.fused}: step {wall_ms:.3f} ms (CUDA events), sum of kernel time {busy_ms:.3f} ms "
              f"per step ({100 * busy_ms / wall_ms:.1f}% of the step; >100% means kernels overlap on several streams)"]
     for name, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:28]:
         lines.append(f"{100 * t / busy:5.1f}%  {t / 1e3 / a.steps:8.3f} ms/step  n/step={n / a.steps:6.1f}  {name}")
