@@ -108,6 +108,10 @@ def maybe_reexec_for_plugin(args):
 
     env = dict(os.environ)
     env.update(nccl_plugin_env(force_net=True))
+    # keep the transport's stream kernels resident across iterations: a (re)launch in the middle of a
+    # collective can be held up by a cudaFree elsewhere in the process (profiles/blocking_calls.txt)
+    env.setdefault("BNET_KERNEL_IDLE_US", "100000")
+    env.setdefault("BNET_KERNEL_ARM_MS", "2000")
     env["BNET_BENCH_REEXEC"] = "1"
     os.execve(sys.executable, [sys.executable] + sys.argv, env)
 
@@ -178,7 +182,7 @@ def main() -> int:
             from bagua_net_b200.ops import fused_nn
 
             return comm.launches + fused_nn.LAUNCHES
-        path = ("nvls" if comm.has_multicast else "p2p") if world > 1 else "single"
+        path = ("nvls" if (comm.has_multicast and world > 2) else "p2p") if world > 1 else "single"
     else:
         if args.comm == "nccl-plugin":
             # Let cuDNN pick its algorithms (and torch's allocator settle) BEFORE any collective is in

@@ -241,26 +241,83 @@ __global__ void __launch_bounds__(kThreads) bnet_allreduce_nvls_kernel(CollDev d
   rank_barrier(d, chan);
 }
 
+// Direct two-shot all-reduce: rank r reduces slice r with peer LOADS (reduce-scatter) and writes the
+// result to every rank with peer STORES (all-gather).  Per GPU S(n-1)/n bytes in and out, full duplex.
+// U vectors x W peers of loads are issued before the first dependent add (NVLink latency ~2-3 us).
+template <int DT, int OP, int W, int U>
+__device__ __forceinline__ void p2p_allreduce_body(const CollDev& d, size_t off, size_t per, size_t start) {
+  constexpr int E = VecTraits<DT>::kElems;
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  const float s = 1.0f / (float)W;
+  size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
+  for (; i < per; i += U * stride) {
+    int4 v[U][W];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const size_t ii = i + u * stride;
+      if (ii < per) {
+        const size_t bo = off + (start + ii) * 16;
+#pragma unroll
+        for (int j = 0; j < W; j++) {
+          int p = d.rank + j;
+          if (p >= W) p -= W;
+          v[u][j] = ptx::ld_na_v4(reinterpret_cast<const int4*>(d.heap[p] + bo));
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const size_t ii = i + u * stride;
+      if (ii >= per) continue;
+      const size_t bo = off + (start + ii) * 16;
+      float acc[8], f[8];
+      unpack<DT>(v[u][0], acc);
+#pragma unroll
+      for (int j = 1; j < W; j++) {
+        unpack<DT>(v[u][j], f);
+#pragma unroll
+        for (int k = 0; k < E; k++) acc[k] = combine<OP>(acc[k], f[k]);
+      }
+      if constexpr (OP == BNET_AVG) {
+#pragma unroll
+        for (int k = 0; k < E; k++) acc[k] *= s;
+      }
+      const int4 out = pack<DT>(acc);
+#pragma unroll
+      for (int j = 0; j < W; j++) {
+        int p = d.rank + j;
+        if (p >= W) p -= W;
+        ptx::st_na_v4(reinterpret_cast<int4*>(d.heap[p] + bo), out);
+      }
+    }
+  }
+}
+
 template <int DT, int OP>
 __global__ void __launch_bounds__(kThreads) bnet_allreduce_p2p_kernel(CollDev d, size_t off, size_t nvec, int chan) {
   rank_barrier(d, chan);
   const size_t per = nvec / d.world;
   const size_t start = (size_t)d.rank * per;
-  const size_t stride = (size_t)gridDim.x * kThreads;
-  const float s = 1.0f / (float)d.world;
-  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < per; i += stride) {
-    const size_t bo = off + (start + i) * 16;
-    float acc[8];
-    p2p_reduce<DT, OP>(d, bo, d.rank, acc);
-    if constexpr (OP == BNET_AVG) {
+  if (d.world == 2) p2p_allreduce_body<DT, OP, 2, 4>(d, off, per, start);
+  else if (d.world == 4) p2p_allreduce_body<DT, OP, 4, 4>(d, off, per, start);
+  else if (d.world == 8) p2p_allreduce_body<DT, OP, 8, 2>(d, off, per, start);
+  else {
+    const size_t stride = (size_t)gridDim.x * kThreads;
+    const float s = 1.0f / (float)d.world;
+    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < per; i += stride) {
+      const size_t bo = off + (start + i) * 16;
+      float acc[8];
+      p2p_reduce<DT, OP>(d, bo, d.rank, acc);
+      if constexpr (OP == BNET_AVG) {
 #pragma unroll
-      for (int k = 0; k < VecTraits<DT>::kElems; k++) acc[k] *= s;
-    }
-    const int4 out = pack<DT>(acc);
-    for (int j = 0; j < d.world; j++) {
-      int p = d.rank + j;
-      if (p >= d.world) p -= d.world;
-      ptx::st_na_v4(reinterpret_cast<int4*>(d.heap[p] + bo), out);   // all-gather by peer stores
+        for (int k = 0; k < VecTraits<DT>::kElems; k++) acc[k] *= s;
+      }
+      const int4 out = pack<DT>(acc);
+      for (int j = 0; j < d.world; j++) {
+        int p = d.rank + j;
+        if (p >= d.world) p -= d.world;
+        ptx::st_na_v4(reinterpret_cast<int4*>(d.heap[p] + bo), out);
+      }
     }
   }
   rank_barrier(d, chan);
@@ -511,20 +568,25 @@ int launch(K kernel, int nblocks, int threads, cudaStream_t st, Args... args) {
   return 1;
 }
 
-// NVLink-bound kernels need enough requests in flight to cover ~3 us of fabric latency
-// (770 GB/s * 3 us = 2.3 MB): default 96 CTAs x 512 threads x 8 x 16 B = 6 MB.  A single GPU has no
-// fabric to wait for but all of HBM to feed: 2 CTAs per SM.
-int pick_blocks(const BnetColl* c, size_t vec_per_rank, int requested) {
+// CTA counts measured on 2 x B200 (profiles/allreduce_sweep_2gpu.txt): the in-switch (multimem) kernels
+// peak at ~32 CTAs and lose bandwidth with more; the peer load/store kernels keep gaining up to one CTA
+// per SM; a single GPU has no fabric to wait for but all of HBM to feed: 2 CTAs per SM.
+enum BlockClass { BLK_NVLS = 0, BLK_P2P = 1, BLK_FUSED_NVLS = 2, BLK_SINGLE = 3 };
+int pick_blocks(const BnetColl* c, size_t vec_per_rank, int requested, BlockClass cls) {
   if (requested > 0) return requested > BNET_COLL_MAX_BLOCKS ? BNET_COLL_MAX_BLOCKS : requested;
-  static const int dflt_multi = (int)env_int("COLL_BLOCKS", 96);
-  static const int dflt_single = (int)env_int("COLL_BLOCKS_SINGLE", 296);
-  int cap = c->world == 1 ? dflt_single : dflt_multi;
+  static const int caps[4] = {(int)env_int("COLL_BLOCKS_NVLS", 32), (int)env_int("COLL_BLOCKS_P2P", 148),
+                              (int)env_int("COLL_BLOCKS_FUSED_NVLS", 64), (int)env_int("COLL_BLOCKS_SINGLE", 296)};
+  int cap = c->world == 1 ? caps[BLK_SINGLE] : caps[cls];
   if (cap > BNET_COLL_MAX_BLOCKS) cap = BNET_COLL_MAX_BLOCKS;
+  if (cap < 1) cap = 1;
   size_t want = (vec_per_rank + kThreads * 2 - 1) / (kThreads * 2);   // >= 2 vectors per thread before adding CTAs
   if (want < 1) want = 1;
   if (want > (size_t)cap) want = cap;
   return (int)want;
 }
+
+// With two ranks the direct exchange moves S/2 per direction while the switch path moves 1.5 S.
+bool prefer_nvls(const BnetColl* c) { return c->mc_ready && c->world > 2; }
 
 }  // namespace
 
@@ -806,10 +868,10 @@ BNET_API int bnet_allreduce(BnetColl* c, size_t offset, size_t count, int dtype,
   if (offset + bytes > c->alloc_bytes - kPadBytes) return fail("all-reduce range outside the heap");
   refresh_devp(c);
   if (c->world == 1) return 0;   // nothing to reduce
-  if (algo == BNET_ALGO_AUTO) algo = c->mc_ready ? BNET_ALGO_NVLS : BNET_ALGO_P2P_TWOSHOT;
+  if (algo == BNET_ALGO_AUTO) algo = prefer_nvls(c) ? BNET_ALGO_NVLS : BNET_ALGO_P2P_TWOSHOT;
   if (algo == BNET_ALGO_NVLS && !c->mc_ready) return fail("NVLS requested but multicast is not available");
   size_t nvec = bytes / 16;
-  int nb = pick_blocks(c, nvec / c->world, nblocks);
+  int nb = pick_blocks(c, nvec / c->world, nblocks, algo == BNET_ALGO_NVLS ? BLK_NVLS : BLK_P2P);
   size_t off = kPadBytes + offset;
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
@@ -838,7 +900,7 @@ BNET_API int bnet_allreduce_oneshot(BnetColl* c, size_t offset, void* out, size_
   if (bytes % 16 || offset % 16 || ((uintptr_t)out & 15)) return fail("one-shot all-reduce needs 16-byte alignment");
   refresh_devp(c);
   size_t nvec = bytes / 16;
-  int nb = pick_blocks(c, nvec, nblocks);
+  int nb = pick_blocks(c, nvec, nblocks, BLK_P2P);
   size_t off = kPadBytes + offset;
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
@@ -860,7 +922,7 @@ static int run_fused(BnetColl* c, size_t goff, size_t poff, size_t nvec, float l
                      float* master, float* mom, int zero, int chan, int nb, cudaStream_t st) {
   if (c->world == 1)
     return launch(bnet_fused_sgd_kernel<DT, 0>, nb, kThreads, st, c->devp, goff, poff, nvec, lr, mu, wd, gs, master, mom, zero, chan);
-  if (c->mc_ready && env_int("FUSED_NVLS", 1))
+  if (prefer_nvls(c) && env_int("FUSED_NVLS", 1))
     return launch(bnet_fused_sgd_kernel<DT, 1>, nb, kThreads, st, c->devp, goff, poff, nvec, lr, mu, wd, gs, master, mom, zero, chan);
   return launch(bnet_fused_sgd_kernel<DT, 2>, nb, kThreads, st, c->devp, goff, poff, nvec, lr, mu, wd, gs, master, mom, zero, chan);
 }
@@ -876,7 +938,7 @@ BNET_API int bnet_fused_allreduce_sgd(BnetColl* c, size_t grad_off, size_t param
   if (((uintptr_t)master | (uintptr_t)mom_buf) & 15) return fail("optimizer state must be 16-byte aligned");
   refresh_devp(c);
   size_t nvec = bytes / 16;
-  int nb = pick_blocks(c, nvec / c->world, nblocks);
+  int nb = pick_blocks(c, nvec / c->world, nblocks, prefer_nvls(c) && env_int("FUSED_NVLS", 1) ? BLK_FUSED_NVLS : BLK_P2P);
   cudaStream_t st = (cudaStream_t)stream;
   size_t goff = kPadBytes + grad_off, poff = kPadBytes + param_off;
   if (dtype == BNET_F32) return run_fused<BNET_F32>(c, goff, poff, nvec, lr, momentum, weight_decay, grad_scale, master, mom_buf, zero_grads, channel, nb, st);

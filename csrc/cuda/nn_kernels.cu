@@ -37,6 +37,20 @@ template <> struct Vec<__nv_bfloat16> {
     for (int i = 0; i < 4; i++) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
     *reinterpret_cast<int4*>(p) = v;
   }
+  // read-once / write-once traffic: do not allocate in L1
+  static __device__ __forceinline__ void load_stream(const __nv_bfloat16* p, float* f) {
+    int4 v = bnet::ptx::ld_na_v4(reinterpret_cast<const int4*>(p));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; i++) { float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+  }
+  static __device__ __forceinline__ void store_stream(__nv_bfloat16* p, const float* f) {
+    int4 v;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; i++) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    bnet::ptx::st_na_v4(reinterpret_cast<int4*>(p), v);
+  }
 };
 template <> struct Vec<float> {
   static constexpr int N = 4;
@@ -46,6 +60,13 @@ template <> struct Vec<float> {
   }
   static __device__ __forceinline__ void store(float* p, const float* f) {
     *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  }
+  static __device__ __forceinline__ void load_stream(const float* p, float* f) {
+    float4 v = bnet::ptx::ld_na_f4(reinterpret_cast<const float4*>(p));
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+  }
+  static __device__ __forceinline__ void store_stream(float* p, const float* f) {
+    bnet::ptx::st_na_f4(reinterpret_cast<float4*>(p), make_float4(f[0], f[1], f[2], f[3]));
   }
 };
 
@@ -85,30 +106,43 @@ __device__ __forceinline__ void reduce_bias_grad(float* acc, float* __restrict__
 }
 
 // ---- gz = gy * (y > 0) ; gb += column sums of gz ---------------------------------------------------
-// rows = N*H*W, cvec = C / V.  blockDim.x is a multiple of cvec.
+// rows = N*H*W, cvec = C / V.  blockDim.x is a multiple of cvec.  U rows per thread are loaded before any
+// dependent work so that 2*U 16-byte requests per thread are in flight (HBM-bound streaming kernel).
 template <typename T>
 __global__ void __launch_bounds__(256) relu_bwd_bias_grad_kernel(const T* __restrict__ gy, const T* __restrict__ y,
                                                                  T* __restrict__ gz, float* __restrict__ gb, size_t rows,
                                                                  int cvec) {
   constexpr int V = Vec<T>::N;
+  constexpr int U = 4;
   extern __shared__ float smem[];
   const int rpb = blockDim.x / cvec;
   const int grp = threadIdx.x % cvec, trow = threadIdx.x / cvec;
+  const size_t step = (size_t)gridDim.x * rpb;
   float acc[V];
 #pragma unroll
   for (int k = 0; k < V; k++) acc[k] = 0.f;
-  if (trow < rpb) {
-    for (size_t r = (size_t)blockIdx.x * rpb + trow; r < rows; r += (size_t)gridDim.x * rpb) {
-      const size_t off = (r * cvec + grp) * V;
-      float g[V], a[V];
-      Vec<T>::load(gy + off, g);
-      Vec<T>::load(y + off, a);
+  for (size_t r0 = (size_t)blockIdx.x * rpb + trow; r0 < rows; r0 += U * step) {
+    float g[U][V], a[U][V];
 #pragma unroll
-      for (int k = 0; k < V; k++) {
-        g[k] = a[k] > 0.f ? g[k] : 0.f;
-        acc[k] += g[k];
+    for (int u = 0; u < U; u++) {
+      const size_t r = r0 + u * step;
+      if (r < rows) {
+        const size_t off = (r * cvec + grp) * V;
+        Vec<T>::load_stream(gy + off, g[u]);
+        Vec<T>::load_stream(y + off, a[u]);
       }
-      Vec<T>::store(gz + off, g);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const size_t r = r0 + u * step;
+      if (r < rows) {
+#pragma unroll
+        for (int k = 0; k < V; k++) {
+          g[u][k] = a[u][k] > 0.f ? g[u][k] : 0.f;
+          acc[k] += g[u][k];
+        }
+        Vec<T>::store_stream(gz + (r * cvec + grp) * V, g[u]);
+      }
     }
   }
   reduce_bias_grad<V>(acc, gb, cvec, smem);
@@ -166,40 +200,51 @@ __global__ void __launch_bounds__(256) pool_relu_bwd_bias_grad_kernel(const T* _
                                                                       T* __restrict__ gz, float* __restrict__ gb, int N, int H,
                                                                       int W, int cvec) {
   constexpr int V = Vec<T>::N;
+  constexpr int U = 2;
   extern __shared__ float smem[];
   const int Ho = H / 2, Wo = W / 2;
   const size_t rows = (size_t)N * Ho * Wo;
   const int rpb = blockDim.x / cvec;
   const int g = threadIdx.x % cvec, trow = threadIdx.x / cvec;
+  const size_t step = (size_t)gridDim.x * rpb;
   float acc[V];
 #pragma unroll
   for (int k = 0; k < V; k++) acc[k] = 0.f;
-  if (trow < rpb) {
-    for (size_t r = (size_t)blockIdx.x * rpb + trow; r < rows; r += (size_t)gridDim.x * rpb) {
-      const size_t i = r * cvec + g;
+  for (size_t r0 = (size_t)blockIdx.x * rpb + trow; r0 < rows; r0 += U * step) {
+    float gv[U][V];
+    uint8_t code[U][V];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const size_t r = r0 + u * step;
+      if (r < rows) {
+        const size_t i = r * cvec + g;
+        Vec<T>::load_stream(gp + i * V, gv[u]);
+        if constexpr (V == 8) *reinterpret_cast<uint2*>(code[u]) = *reinterpret_cast<const uint2*>(idx + i * V);
+        else *reinterpret_cast<uint32_t*>(code[u]) = *reinterpret_cast<const uint32_t*>(idx + i * V);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const size_t r = r0 + u * step;
+      if (r >= rows) continue;
       size_t t = r;
       const int wo = (int)(t % Wo);
       t /= Wo;
       const int ho = (int)(t % Ho);
       const int n = (int)(t / Ho);
-      float gv[V];
-      uint8_t code[V];
-      Vec<T>::load(gp + i * V, gv);
-      if constexpr (V == 8) *reinterpret_cast<uint2*>(code) = *reinterpret_cast<const uint2*>(idx + i * V);
-      else *reinterpret_cast<uint32_t*>(code) = *reinterpret_cast<const uint32_t*>(idx + i * V);
       float o[4][V];
 #pragma unroll
       for (int k = 0; k < V; k++) {
-        const float gk = (code[k] & 4) ? gv[k] : 0.f;
+        const float gk = (code[u][k] & 4) ? gv[u][k] : 0.f;
         acc[k] += gk;
 #pragma unroll
-        for (int q = 0; q < 4; q++) o[q][k] = ((code[k] & 3) == q) ? gk : 0.f;
+        for (int q = 0; q < 4; q++) o[q][k] = ((code[u][k] & 3) == q) ? gk : 0.f;
       }
       const size_t base = (((size_t)n * H + 2 * ho) * W + 2 * wo) * cvec + g;
-      Vec<T>::store(gz + base * V, o[0]);
-      Vec<T>::store(gz + (base + cvec) * V, o[1]);
-      Vec<T>::store(gz + (base + (size_t)W * cvec) * V, o[2]);
-      Vec<T>::store(gz + (base + (size_t)W * cvec + cvec) * V, o[3]);
+      Vec<T>::store_stream(gz + base * V, o[0]);
+      Vec<T>::store_stream(gz + (base + cvec) * V, o[1]);
+      Vec<T>::store_stream(gz + (base + (size_t)W * cvec) * V, o[2]);
+      Vec<T>::store_stream(gz + (base + (size_t)W * cvec + cvec) * V, o[3]);
     }
   }
   reduce_bias_grad<V>(acc, gb, cvec, smem);

@@ -334,7 +334,7 @@ __device__ void tma_copy_range(const char* src, char* dst, size_t n, char* smem,
 
 template <bool kUseTma>
 __global__ void __launch_bounds__(kThreads, 1)
-bnet_nvl_stream_kernel(ClusterQ* q, uint64_t idle_ns, uint64_t first_idle_ns) {
+bnet_nvl_stream_kernel(ClusterQ* q, uint64_t idle_ns, uint64_t first_idle_ns, const uint32_t* outstanding) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ SmemDesc sd;
   __shared__ __align__(8) uint64_t bars[kTmaStages];
@@ -369,7 +369,10 @@ bnet_nvl_stream_kernel(ClusterQ* q, uint64_t idle_ns, uint64_t first_idle_ns) {
         if (ptx::ld_acquire_sys_u64(&d->seq) == head + 1) break;
         uint64_t now = ptx::globaltimer();
         if (ptx::ld_relaxed_sys_u32((const uint32_t*)&q->stop)) { loc.quit = 1; break; }
-        if (now - last_work > idle_limit) {
+        // stay resident while the host still has requests in flight on ANY NVL comm of this process (a
+        // collective is running: leaving now would force a launch on the data path later); hard cap 10 s
+        if (now - last_work > idle_limit &&
+            (ptx::ld_relaxed_sys_u32(outstanding) == 0 || now - last_work > 10000000000ull)) {
           // leave unless the host published work while we were deciding (store, fence, re-check)
           ptx::st_release_sys_u32((uint32_t*)&q->state, ST_EXITING);
           ptx::fence_sc_sys();
@@ -476,6 +479,19 @@ struct Stream {
   cudaStream_t stream = nullptr;
 };
 
+// Requests in flight on the NVL comms of this process (host-maintained, pinned, read by the kernels).
+std::atomic<uint32_t>* g_outstanding_host = nullptr;
+uint32_t* g_outstanding_dev = nullptr;
+const uint32_t* outstanding_dev() {
+  if (!g_outstanding_host) {
+    void* dp = nullptr;
+    void* hp = host_alloc_mapped(64, &dp);
+    g_outstanding_host = new (hp) std::atomic<uint32_t>(0);
+    g_outstanding_dev = (uint32_t*)dp;
+  }
+  return g_outstanding_dev;
+}
+
 struct Exec {
   int dev = -1;
   bool ok = false;
@@ -570,7 +586,8 @@ Exec* get_exec(int dev) {
         __atomic_store_n(&s.q->state, ST_RUNNING, __ATOMIC_RELEASE);
         ClusterQ* qd = s.q_dev;
         uint64_t idle = e->idle_ns, wd = 0;
-        void* pargs[] = {&qd, &idle, &wd};
+        const uint32_t* outp = outstanding_dev();
+        void* pargs[] = {&qd, &idle, &wd, &outp};
         cudaError_t e2 = e->tma ? launch_cluster(bnet_nvl_stream_kernel<true>, e->cluster_size, e->cluster_size,
                                                  kTmaStages * kTmaStageBytes, s.stream, pargs)
                                 : launch_cluster(bnet_nvl_stream_kernel<false>, e->cluster_size, e->cluster_size, 0,
@@ -609,7 +626,8 @@ int ensure_running(Exec* e, Stream& s, bool arm = false) {
     __atomic_store_n(&s.q->state, ST_RUNNING, __ATOMIC_RELEASE);
     ClusterQ* qd = s.q_dev;
     uint64_t idle = e->idle_ns, wd = arm ? e->arm_ns : 0;
-    void* args[] = {&qd, &idle, &wd};
+    const uint32_t* outp = outstanding_dev();
+    void* args[] = {&qd, &idle, &wd, &outp};
     cudaError_t err = e->tma ? launch_cluster(bnet_nvl_stream_kernel<true>, e->cluster_size, e->cluster_size,
                                               kTmaStages * kTmaStageBytes, s.stream, args)
                              : launch_cluster(bnet_nvl_stream_kernel<false>, e->cluster_size, e->cluster_size, 0,
@@ -724,6 +742,10 @@ extern "C" __attribute__((visibility("default"))) int bnet_exec_op_scaled(int de
   Exec* e = get_exec(dev);
   if (!e) return -1;
   return submit(e, op, src, dst, src_bytes, flags_dev, flag_value, nchunks, scale);
+}
+
+void exec_outstanding_add(int delta) {
+  if (g_outstanding_host) g_outstanding_host->fetch_add((uint32_t)delta, std::memory_order_relaxed);
 }
 
 int exec_prepare(int dev) {

@@ -30,6 +30,9 @@ int exec_copy(int dev, const void* src, void* dst, size_t nbytes, volatile uint6
 int exec_flush(int dev, volatile uint64_t* flag_host, uint64_t* flag_dev, uint64_t flag_value);
 // Create streams / queues / pinned memory for `dev` now (setup phase) instead of at the first job.
 int exec_prepare(int dev);
+// +1 when a request is posted on an NVL comm, -1 when it completes: the stream kernels stay resident
+// while the count is non-zero so that no kernel launch is needed in the middle of a collective.
+void exec_outstanding_add(int delta);
 void exec_stats(ExecStats* out);
 void exec_shutdown();
 

@@ -175,7 +175,8 @@ class NvlComm : public Comm {
     }
     set_nonblocking(uds_, true);
     // all CUDA resource creation happens here, in NCCL's setup phase, never on the data path
-    if (k == SEND && cuda::available() && !cuda::fake()) cuda::exec_prepare(local_dev_);
+    cuda_live_ = cuda::available() && !cuda::fake();
+    if (cuda_live_) cuda::exec_prepare(local_dev_);
     watchdog_register(this);
   }
 
@@ -265,6 +266,7 @@ class NvlComm : public Comm {
     if (b) return b;
     Request* r = alloc_req(REQ_SEND, const_cast<void*>(data), size, tag, mh);
     if (!r) return kOk;
+    track(+1);
     r->u[0] = seq_++;   // message index
     r->u[1] = 0;        // stage
     pending_.push_back(r);
@@ -281,6 +283,9 @@ class NvlComm : public Comm {
     if (b) return b;
     Request* r = alloc_req(REQ_RECV, data, size, tag, mh);
     if (!r) return kOk;
+    // the first receive of a burst is the earliest sign of a collective on this GPU: make sure this
+    // process' stream kernels are resident before its own isends need them
+    if (track(+1) == 0 && cuda_live_) cuda::exec_prepare(local_dev_);
     uint64_t k = seq_++;
     r->u[0] = k;
     r->u[1] = 0;
@@ -378,6 +383,7 @@ class NvlComm : public Comm {
     for (Request* r : pending_) {
       r->fail(st);
       r->ndone.store(r->nsub.load(), std::memory_order_release);
+      track(-1);
     }
     pending_.clear();
   }
@@ -501,7 +507,16 @@ class NvlComm : public Comm {
     return n;
   }
 
+  // requests in flight across all NVL comms of the process (see cuda::exec_outstanding_add)
+  static int track(int delta) {
+    static std::atomic<int> n{0};
+    int before = n.fetch_add(delta);
+    cuda::exec_outstanding_add(delta);
+    return before;
+  }
+
   void complete(Request* r, size_t nbytes) {
+    track(-1);
     r->nbytes.store(nbytes, std::memory_order_relaxed);
     r->ndone.store(r->nsub.load(std::memory_order_relaxed), std::memory_order_release);
   }
@@ -546,6 +561,7 @@ class NvlComm : public Comm {
           a.err = kErrInvalid;
           a.seq.store(k + 1, std::memory_order_release);
           r->fail(kErrInvalid);
+          track(-1);
           r->u[1] = 3;
           continue;
         }
@@ -588,6 +604,7 @@ class NvlComm : public Comm {
         size_t n = want ? ring_write((const char*)r->buf + r->u[2], want, src_cuda) : 0;
         if (n == (size_t)-1) {
           r->fail(kErrCuda);
+          track(-1);
           r->u[1] = 3;
           broken.store(kErrCuda);
           continue;
@@ -635,6 +652,7 @@ class NvlComm : public Comm {
         if (a.seq.load(std::memory_order_acquire) != k + 1) break;  // sender announces in order
         if (a.err) {
           r->fail(a.err);
+          track(-1);
           r->u[1] = 3;
           continue;
         }
@@ -655,6 +673,7 @@ class NvlComm : public Comm {
         size_t n = want ? ring_read((char*)r->buf + r->u[2], want, dst_cuda) : 0;
         if (n == (size_t)-1) {
           r->fail(kErrCuda);
+          track(-1);
           r->u[1] = 3;
           broken.store(kErrCuda);
           continue;
@@ -687,7 +706,7 @@ class NvlComm : public Comm {
   std::string shm_name_;
   uint32_t peer_pid_;
   int peer_dev_, local_dev_ = -1;
-  bool shm_registered_ = false, uds_eof_ = false;
+  bool shm_registered_ = false, uds_eof_ = false, cuda_live_ = false;
   std::mutex mu_;
   std::deque<Request*> pending_;
   uint64_t seq_ = 0;
