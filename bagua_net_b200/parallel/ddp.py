@@ -154,14 +154,63 @@ class BnetDDP(torch.nn.Module):
     def forward(self, *args, **kwargs):
         return self.module(*args, **kwargs)
 
-    def train_step(self, inputs: torch.Tensor, targets: torch.Tensor, loss_fn=None) -> torch.Tensor:
-        """forward + backward + fused all-reduce/optimizer.  Returns the (device) loss tensor."""
-        loss_fn = loss_fn or torch.nn.functional.cross_entropy
+    def _eager_step(self, inputs, targets, loss_fn):
         out = self.module(inputs)
         loss = loss_fn(out.float(), targets)
         loss.backward()
         self.finish_step()
         return loss.detach()
+
+    def enable_cuda_graph(self, enabled: bool = True):
+        """Capture forward + backward + the fused collective/optimizer kernels (both streams) into ONE
+        CUDA graph and replay it every step: the ~150 launches of a step cost one cudaGraphLaunch.
+        Needs static shapes; re-captured when shapes or the learning rate change.  Every rank must
+        make the same choice."""
+        self._use_graph = enabled
+        self._graph = None
+
+    def _capture(self, inputs, targets, loss_fn, key):
+        from ..ops import fused_nn
+
+        cur = torch.cuda.current_stream()
+        self._gx = inputs.clone(memory_format=torch.preserve_format)
+        self._gy = targets.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):               # warm-up on a side stream (cuDNN autotune, allocator)
+            for _ in range(2):
+                self._eager_step(self._gx, self._gy, loss_fn)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        if self.comm.world > 1:
+            dist.barrier()
+        l0, f0 = self.comm.launches, fused_nn.LAUNCHES
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._gloss = self._eager_step(self._gx, self._gy, loss_fn)
+        self._graph_launches = (self.comm.launches - l0, fused_nn.LAUNCHES - f0)
+        self._graph, self._graph_key = g, key
+        torch.cuda.synchronize()
+        if self.comm.world > 1:
+            dist.barrier()
+
+    def train_step(self, inputs: torch.Tensor, targets: torch.Tensor, loss_fn=None) -> torch.Tensor:
+        """forward + backward + fused all-reduce/optimizer.  Returns the (device) loss tensor."""
+        loss_fn = loss_fn or torch.nn.functional.cross_entropy
+        if not getattr(self, "_use_graph", False):
+            return self._eager_step(inputs, targets, loss_fn)
+        from ..ops import fused_nn
+
+        key = (tuple(inputs.shape), inputs.dtype, tuple(targets.shape), targets.dtype, loss_fn, self.lr, self.momentum,
+               self.weight_decay)
+        if self._graph is None or self._graph_key != key:
+            self._capture(inputs, targets, loss_fn, key)
+        self._gx.copy_(inputs, non_blocking=True)
+        self._gy.copy_(targets, non_blocking=True)
+        self._graph.replay()
+        self.comm.launches += self._graph_launches[0]      # the replay re-issues every captured kernel of ours
+        fused_nn.LAUNCHES += self._graph_launches[1]
+        return self._gloss
 
     def train_step_from_host(self, inputs_pinned: torch.Tensor, targets_pinned: torch.Tensor, loss_fn=None) -> float:
         """End-to-end step as a user runs it: H2D copy of this step's batch from pinned host

@@ -110,7 +110,7 @@ def maybe_reexec_for_plugin(args):
     env.update(nccl_plugin_env(force_net=True))
     # keep the transport's stream kernels resident across iterations: a (re)launch in the middle of a
     # collective can be held up by a cudaFree elsewhere in the process (profiles/blocking_calls.txt)
-    env.setdefault("BNET_KERNEL_IDLE_US", "100000")
+    env.setdefault("BNET_KERNEL_IDLE_US", "2000000")
     env.setdefault("BNET_KERNEL_ARM_MS", "2000")
     env["BNET_BENCH_REEXEC"] = "1"
     os.execve(sys.executable, [sys.executable] + sys.argv, env)
@@ -129,6 +129,7 @@ def main() -> int:
     ap.add_argument("--bucket-mb", type=float, default=64.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the all-reduce busbw side measurement")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel of the step individually (no CUDA graph)")
     ap.add_argument("--no-fused", action="store_true", help="eager bias/ReLU/pool instead of the fused sm_100a conv blocks")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -154,7 +155,9 @@ def main() -> int:
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     init_process_group_from_env("nccl")
-    torch.backends.cudnn.benchmark = True
+    # (the NCCL-over-plugin arm keeps cuDNN's autotuner off: its emptyCache() -> cudaFree in the middle of
+    #  a collective holds up the transport's kernel launches)
+    torch.backends.cudnn.benchmark = args.comm != "nccl-plugin"
     torch.backends.cuda.matmul.allow_tf32 = True
     torch.backends.cudnn.allow_tf32 = True
     torch.manual_seed(1234)
@@ -171,6 +174,8 @@ def main() -> int:
         engine = BnetDDP(model, lr=lr, momentum=mom, weight_decay=wd, bucket_mb=args.bucket_mb,
                          extra_heap_bytes=384 << 20)
         comm = engine.comm
+        if not args.no_graph:
+            engine.enable_cuda_graph(True)
 
         def step_dev(x, y):
             return engine.train_step(x, y)
@@ -293,7 +298,7 @@ def main() -> int:
             "higher_is_better": True, "scaling": "weak", "vs_baseline": round(img_s / BASELINE_IMG_S, 4),
             "dtype": "bf16", "data": "synthetic (random images/labels, random-init weights)",
             "config": {"model": args.model, "global_batch": world * B, "per_gpu_batch": B, "seq_len": None,
-                       "image": [3, S, S], "parallelism": f"dp{world}", "comm": args.comm, "path": path, "fused_conv_blocks": fused,
+                       "image": [3, S, S], "parallelism": f"dp{world}", "comm": args.comm, "path": path, "fused_conv_blocks": fused, "cuda_graph": args.comm == "bnet" and not args.no_graph,
                        "optimizer": f"sgd(lr={lr},momentum={mom},wd={wd}) fused into the collective" if args.comm == "bnet"
                        else f"torch.optim.SGD(lr={lr},momentum={mom},wd={wd})",
                        "params": n_params, "bucket_mb": args.bucket_mb,

@@ -245,7 +245,18 @@ def job_ddp_engine():
     xh, yh = x.cpu().pin_memory(), y.cpu().pin_memory()
     assert isinstance(e2.train_step_from_host(xh, yh), float)
     print(f"rank {RANK}: bf16 engine loss {ls[0]:.3f} -> {ls[-1]:.3f}", flush=True)
-    assert eng.comm.status() == 0 and e2.comm.status() == 0
+    # CUDA-graph mode: the whole step (both streams, the cross-rank kernels included) replays as one graph
+    torch.manual_seed(1)
+    m3 = build_model("vgg16", fused=True, **kw).cuda().to(torch.bfloat16).to(memory_format=torch.channels_last)
+    e3 = BnetDDP(m3, lr=0.02, momentum=0.9, weight_decay=0.0, bucket_mb=0.25)
+    e3.enable_cuda_graph(True)
+    before = e3.kernel_launches
+    lg = [float(e3.train_step(x, y)) for _ in range(25)]
+    assert lg[-1] < lg[0] - 0.1 and all(v == v for v in lg), lg
+    assert e3._graph is not None and e3.kernel_launches - before >= 25 * len(e3.buckets)
+    assert isinstance(e3.train_step_from_host(xh, yh), float)
+    print(f"rank {RANK}: graph engine loss {lg[0]:.3f} -> {lg[-1]:.3f}", flush=True)
+    assert eng.comm.status() == 0 and e2.comm.status() == 0 and e3.comm.status() == 0
     teardown()
 
 
