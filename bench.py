@@ -286,7 +286,10 @@ def main() -> int:
                 algbw = nbytes / (ms / 20 / 1e3) / 1e9
                 bw[str(nbytes)] = round(algbw * 2 * (world - 1) / world, 1)
             extra["allreduce_busbw_gbs_bf16"] = bw
-            extra["allreduce_roofline_frac_of_770GBs"] = {k: round(v / (2 * (world - 1) / world) * (1 + 1 / world) / 770.0, 3)
+            # bytes per direction per GPU: in-switch path S(1+1/n), direct two-shot S(n-1)/n
+            per_dir = (1 + 1 / world) if path == "nvls" else (world - 1) / world
+            extra["allreduce_algo"] = path
+            extra["allreduce_roofline_frac_of_770GBs"] = {k: round(v / (2 * (world - 1) / world) * per_dir / 770.0, 3)
                                                           for k, v in bw.items()}
         except Exception as ex:   # the headline number must survive a failing side measurement
             extra["allreduce_error"] = str(ex)[:200]

@@ -12,14 +12,11 @@ TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-add
 step build 300 make -j16
 TAILN=10 step w8_allreduce 200 $TR --master-port 29501 tests/gpu_worker.py allreduce
 TAILN=10 step w8_fused_sgd 120 $TR --master-port 29502 tests/gpu_worker.py fused_sgd
-TAILN=10 step w8_ddp_engine 150 $TR --master-port 29503 tests/gpu_worker.py ddp_engine
-CUT=1800 TAILN=2 step bench8 300 $TR --master-port 29541 bench.py --gpus $NG --steps 20 --warmup 5
+CUT=1800 TAILN=2 step bench8 300 $TR --master-port 29541 bench.py --gpus $NG --steps 30 --warmup 5
 CUT=1800 TAILN=2 step bench8_nccl 300 $TR --master-port 29542 bench.py --gpus $NG --steps 20 --warmup 5 --comm nccl --no-e2e
 TAILN=90 step sweep_all 400 $TR --master-port 29562 bench/allreduce_sweep.py --min-bytes 1K --max-bytes 1G --json $OUT/sweep_all.json
 TAILN=40 step sweep_blocks 300 $TR --master-port 29561 bench/allreduce_sweep.py --min-bytes 256M --max-bytes 256M --algos nvls,p2p --blocks 16,32,64,96,148,296 --json $OUT/sweep_blocks.json
-CUT=1800 TAILN=2 step bench8_plugin 240 env BNET_WATCHDOG_MS=8000 $TR --master-port 29543 bench.py --gpus $NG --steps 10 --warmup 3 --comm nccl-plugin --no-e2e
 TAILN=16 step nccl_perf_stock 200 build/bench/all_reduce_perf -b 8 -e 128M -f 4 -N $NG -d bfloat16
-TAILN=16 step nccl_perf_plugin 240 env $(python -m bagua_net_b200.utils.env) build/bench/all_reduce_perf -b 8 -e 128M -f 4 -N $NG -d bfloat16
+TAILN=16 step nccl_perf_plugin 110 env $(python -m bagua_net_b200.utils.env) build/bench/all_reduce_perf -b 8 -e 128M -f 4 -N $NG -d bfloat16
 CUT=1800 TAILN=2 step bench8_resnet50 300 $TR --master-port 29544 bench.py --gpus $NG --steps 20 --warmup 5 --model resnet50 --no-extra
-CUT=1800 TAILN=2 step bench8_resnet50_nccl 300 $TR --master-port 29545 bench.py --gpus $NG --steps 20 --warmup 5 --model resnet50 --comm nccl --no-e2e
 echo "== done $(date -u)"
