@@ -223,7 +223,8 @@ def main() -> int:
     B, S = args.batch, args.image
     x_dev = torch.randn(B, 3, S, S, device=dev, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
     y_dev = torch.randint(0, 1000, (B,), device=dev)
-    x_host = torch.randn(B, 3, S, S, dtype=torch.bfloat16).pin_memory()
+    # pinned, already in the layout the model consumes (NHWC): the H2D copy is one plain DMA
+    x_host = torch.randn(B, 3, S, S, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last).pin_memory()
     y_host = torch.randint(0, 1000, (B,)).pin_memory()
 
     def sync_all():

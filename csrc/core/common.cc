@@ -172,7 +172,7 @@ static Config parse_config() {
   c.wire_compat = (int)env_int("WIRE_COMPAT", 0);
   c.timeout_ms = (int)env_int("TIMEOUT_MS", 0);
   c.spin_us = (int)env_int("SPIN_US", 20);
-  c.shm_ring_bytes = (size_t)env_int("SHM_RING_BYTES", 8ll << 20);
+  c.shm_ring_bytes = (size_t)env_int("SHM_RING_BYTES", 1ll << 20);   // per connection; NCCL opens dozens of them
   c.fault = env_str("FAULT_INJECT", "");
   return c;
 }

@@ -786,8 +786,10 @@ Comm* nvl_connect(int dev, const Handle& h) {
   char shm_name[64];
   snprintf(shm_name, sizeof(shm_name), "/bnet-%d-%016llx", (int)getpid(), (unsigned long long)random_u64());
   int sfd = shm_open(shm_name, O_CREAT | O_EXCL | O_RDWR, 0600);
-  if (sfd < 0 || ftruncate(sfd, (off_t)total) != 0) {
-    BNET_INFO("nvl connect: shm_open/ftruncate(%zu) failed: %s", total, strerror(errno));
+  // posix_fallocate reserves the pages now: on a small /dev/shm we fall back to TCP here instead of
+  // dying with SIGBUS at the first touch of an unbacked page (8 ranks x dozens of connections add up)
+  if (sfd < 0 || ftruncate(sfd, (off_t)total) != 0 || posix_fallocate(sfd, 0, (off_t)total) != 0) {
+    BNET_INFO("nvl connect: shm_open/ftruncate/fallocate(%zu) failed: %s", total, strerror(errno));
     if (sfd >= 0) { close(sfd); shm_unlink(shm_name); }
     close(fd);
     return nullptr;
