@@ -95,3 +95,26 @@ clean:
 
 -include $(HOST_OBJS:.o=.d) $(CU_OBJS:.o=.d)
 .PHONY: default test bench sass tar clean
+
+# ---- sanitizer builds of the host engine: `make tsan` / `make asan` rebuild every host
+# object with the sanitizer into build/<san>/, link it with the (uninstrumented) kernel objects and run the
+# C++ unit + loopback tests against that library.
+SAN_CXX ?= /usr/bin/g++
+SAN_FLAGS_tsan := -fsanitize=thread -Wno-tsan
+SAN_FLAGS_asan := -fsanitize=address -fsanitize=undefined -fno-omit-frame-pointer
+define SAN_RULES
+$(BUILD)/$(1)/%.o: csrc/%.cc
+	@mkdir -p $$(dir $$@)
+	$(SAN_CXX) $(CXXFLAGS) -O1 $$(SAN_FLAGS_$(1)) -c $$< -o $$@
+$(BUILD)/$(1)/libnccl-net.so: $(patsubst csrc/%.cc,$(BUILD)/$(1)/%.o,$(HOST_SRCS) csrc/plugin/plugin.cc) $(CU_OBJS)
+	$(NVCC) -ccbin $(SAN_CXX) $(ARCH) $(LDFLAGS) $$(addprefix -Xcompiler ,$$(SAN_FLAGS_$(1))) -o $$@ $$^
+$(BUILD)/$(1)/tests/%: csrc/tests/%.cc $(BUILD)/$(1)/libnccl-net.so
+	@mkdir -p $$(dir $$@)
+	$(SAN_CXX) $(CXXFLAGS) -O1 $$(SAN_FLAGS_$(1)) -fvisibility=default $$< -o $$@ -ldl -pthread
+$(1): $(BUILD)/$(1)/tests/unit_tests $(BUILD)/$(1)/tests/loopback_test
+	$(BUILD)/$(1)/tests/unit_tests $(BUILD)/$(1)/libnccl-net.so
+	$(BUILD)/$(1)/tests/loopback_test $(BUILD)/$(1)/libnccl-net.so
+.PHONY: $(1)
+endef
+$(eval $(call SAN_RULES,tsan))
+$(eval $(call SAN_RULES,asan))

@@ -21,7 +21,8 @@ __version__ = "0.1.0"
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(_PKG_DIR)
-LIB_DIR = os.path.join(_PKG_DIR, "lib")
+# BNET_LIB_DIR points the loader at another build of the same library (sanitizer builds: `make tsan`).
+LIB_DIR = os.environ.get("BNET_LIB_DIR") or os.path.join(_PKG_DIR, "lib")
 LIB_NAME = "libnccl-net.so"
 
 
