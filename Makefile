@@ -79,7 +79,12 @@ $(BUILD)/bench/%: bench/%.cu $(PLUGIN_SO)
 	$(NVCC) -O3 -std=c++17 $(ARCH) -lineinfo -Iinclude -Icsrc -I$(NCCL_HOME)/include $< -o $@ \
 	    -L$(NCCL_HOME)/lib -l:libnccl.so.2 -Xlinker -rpath=$(NCCL_HOME)/lib -ldl -lpthread -lrt
 
-bench: $(BENCH_BINS)
+# host-only transport benchmark (no GPU, no NCCL): loopback TCP / shared-memory ring through the v8 table
+$(BUILD)/bench/net_perf: bench/net_perf.cc $(PLUGIN_SO)
+	@mkdir -p $(dir $@)
+	$(CXX) $(CXXFLAGS) -fvisibility=default $< -o $@ -ldl -pthread
+
+bench: $(BENCH_BINS) $(BUILD)/bench/net_perf
 
 sass: $(PLUGIN_SO)
 	@mkdir -p docs/sass

@@ -222,6 +222,46 @@ class BnetDDP(torch.nn.Module):
             x = x.contiguous(memory_format=torch.channels_last)
         return float(self.train_step(x, y, loss_fn).item())
 
+    def train_from_host(self, batches, loss_fn=None):
+        """Training loop over an iterable of (inputs_pinned, targets_pinned) batches — the loader-facing API.
+        Yields the loss of every step as a float (device→host read per step).  The host→device copy of
+        batch i+1 is issued on a dedicated copy stream right after step i has been enqueued, so the PCIe
+        transfer rides under step i's kernels instead of in front of step i+1 (what a DataLoader prefetcher
+        with pin_memory does for eager PyTorch)."""
+        dev = self.flat_param.device
+        if getattr(self, "_h2d_stream", None) is None:
+            self._h2d_stream = torch.cuda.Stream(device=dev)
+        copy = self._h2d_stream
+
+        def stage(batch):
+            xh, yh = batch
+            with torch.cuda.stream(copy):
+                x = xh.to(dev, non_blocking=True)
+                y = yh.to(dev, non_blocking=True)
+                if x.dim() == 4:
+                    x = x.contiguous(memory_format=torch.channels_last)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+            return x, y, ev
+
+        it = iter(batches)
+        try:
+            nxt = stage(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            x, y, ev = nxt
+            cur = torch.cuda.current_stream()
+            cur.wait_event(ev)
+            x.record_stream(cur)        # allocated on the copy stream, consumed on the compute stream
+            y.record_stream(cur)
+            loss = self.train_step(x, y, loss_fn)
+            try:
+                nxt = stage(next(it))   # overlaps the step that was just enqueued
+            except StopIteration:
+                nxt = None
+            yield float(loss.item())
+
     def set_lr(self, lr: float):
         self.lr = lr
 

@@ -256,6 +256,10 @@ def job_ddp_engine():
     assert e3._graph is not None and e3.kernel_launches - before >= 25 * len(e3.buckets)
     assert isinstance(e3.train_step_from_host(xh, yh), float)
     print(f"rank {RANK}: graph engine loss {lg[0]:.3f} -> {lg[-1]:.3f}", flush=True)
+    # loader-facing loop with the next batch's H2D copy prefetched: one loss per batch, training continues
+    lp = list(e3.train_from_host((xh, yh) for _ in range(6)))
+    assert len(lp) == 6 and all(isinstance(v, float) and v == v for v in lp) and max(lp) < lg[0] + 1.0, lp
+    assert list(e3.train_from_host(iter(()))) == []
     assert eng.comm.status() == 0 and e2.comm.status() == 0 and e3.comm.status() == 0
     teardown()
 
