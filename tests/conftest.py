@@ -70,3 +70,28 @@ def run_pair(args, env=None, timeout=120):
             line = [ln for ln in o.splitlines() if ln.startswith("{")]
             outs.append((p.returncode, json.loads(line[-1]) if line else None, err))
     return outs
+
+
+def run_ring(world, args=(), env=None, timeout=180):
+    """Launch `world` ranks of tests/ring_worker.py (ring all-reduce over the ncclNet table); return their JSON lines."""
+    import json
+    import tempfile
+
+    worker = os.path.join(ROOT, "tests", "ring_worker.py")
+    e = dict(os.environ)
+    e["PYTHONPATH"] = ROOT + os.pathsep + e.get("PYTHONPATH", "")
+    e.update(env or {})
+    with tempfile.TemporaryDirectory() as d:
+        procs = [subprocess.Popen([sys.executable, worker, str(r), str(world), d] + list(args), env=e,
+                                  stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(world)]
+        outs = []
+        for p in procs:
+            try:
+                o, err = p.communicate(timeout=timeout)
+            except subprocess.TimeoutExpired:
+                for q in procs:
+                    q.kill()
+                raise
+            line = [ln for ln in o.splitlines() if ln.startswith("{")]
+            outs.append((p.returncode, json.loads(line[-1]) if line else None, err))
+    return outs

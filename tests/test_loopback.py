@@ -123,3 +123,21 @@ def test_injected_stream_failure_surfaces_in_test():
                     env={"BNET_NVL": "0", "BNET_FAULT_INJECT": "send_drop_after=3", "BAGUA_NET_MIN_CHUNKSIZE": "65536"},
                     timeout=60)
     assert any(res is not None and not res["ok"] for _, res, _ in outs)
+
+
+# ---- N ranks, two different peers per rank, several connections per peer (what NCCL's rings look like)
+@pytest.mark.parametrize("world,env,args,transport", [
+    (4, {"BNET_NVL": "0"}, ["--channels", "2"], "tcp-threads"),
+    (3, {"BNET_NVL": "0", "BAGUA_NET_IMPLEMENT": "TOKIO", "BAGUA_NET_NSTREAMS": "3"}, ["--channels", "2"], "tcp-async"),
+    (4, {}, ["--channels", "2", "--mem", "host"], "nvl"),
+    (8, {"BNET_FAKE_CUDA": "1"}, ["--channels", "4", "--mem", "fakecuda", "--iters", "2"], "nvl"),
+    (3, {"BNET_FAKE_CUDA": "1"}, ["--channels", "1", "--slices", "1", "--mem", "fakecuda"], "nvl"),
+])
+def test_ring_allreduce_over_the_plugin(world, env, args, transport):
+    from conftest import run_ring
+
+    outs = run_ring(world, args, env=env)
+    for rc, res, err in outs:
+        assert rc == 0 and res and res["ok"], err[-2000:]
+        assert res["transports"] == [transport]
+        assert res["allreduces"] > 0
