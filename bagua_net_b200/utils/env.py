@@ -25,6 +25,11 @@ def nccl_plugin_env(plugin: str = "bnet", force_net: bool = False, gdr: bool = T
         "NCCL_NET_PLUGIN": plugin,
         "NCCL_NET": "BNet",
     }
+    if "CUDA_DEVICE_MAX_CONNECTIONS" not in os.environ:
+        # the transport keeps up to 8 resident stream kernels, each on its own CUDA stream; with the default
+        # of 8 hardware work queues per context other streams (NCCL's, the staging copies) can end up queued
+        # BEHIND a resident kernel.  32 queues keep them independent.
+        env["CUDA_DEVICE_MAX_CONNECTIONS"] = "32"
     if force_net:
         env.update({"NCCL_P2P_DISABLE": "1", "NCCL_SHM_DISABLE": "1", "NCCL_NVLS_ENABLE": "0",
                     "NCCL_NET_DISABLE_INTRA": "0"})
