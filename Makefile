@@ -68,9 +68,15 @@ $(BUILD)/tests/%: csrc/tests/%.cc $(PLUGIN_SO)
 	@mkdir -p $(dir $@)
 	$(CXX) $(CXXFLAGS) -fvisibility=default $< -o $@ -ldl -pthread
 
-test: $(TEST_BINS)
+# the per-thread bodies of the fused layer kernels, compiled by g++ and walked over an emulated grid
+$(BUILD)/tests/nn_emu_test: csrc/tests/nn_emu_test.cc csrc/cuda/nn_body.cuh
+	@mkdir -p $(dir $@)
+	$(CXX) -O2 -g -std=c++17 -Wall -fno-strict-aliasing -Icsrc -I$(CUDA_HOME)/include $< -o $@
+
+test: $(TEST_BINS) $(BUILD)/tests/nn_emu_test
 	$(BUILD)/tests/unit_tests $(PLUGIN_SO)
 	$(BUILD)/tests/loopback_test $(PLUGIN_SO)
+	$(BUILD)/tests/nn_emu_test
 
 BENCH_BINS := $(BUILD)/bench/all_reduce_perf
 NCCL_HOME ?= $(shell python -c "import nvidia.nccl, os; print(os.path.dirname(nvidia.nccl.__file__))" 2>/dev/null)

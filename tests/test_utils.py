@@ -90,3 +90,16 @@ def test_config_env_aliases():
     assert d["nstreams"] == 4
     d = cfg(BAGUA_NET_NSTREAMS="banana")                          # malformed: default, no abort
     assert d["nstreams"] == 2
+
+
+def test_fused_layer_kernel_bodies_on_an_emulated_grid():
+    """csrc/cuda/nn_body.cuh compiled by g++ and walked block by block, thread by thread (csrc/tests/nn_emu_test.cc):
+    the row walk, batch tails, pool index coding and bias-gradient sums of the sm_100a kernels, without a GPU."""
+    import subprocess
+
+    import bagua_net_b200
+
+    root = bagua_net_b200.REPO_ROOT
+    subprocess.run(["make", "-s", "build/tests/nn_emu_test"], cwd=root, check=True, capture_output=True)
+    r = subprocess.run([os.path.join(root, "build", "tests", "nn_emu_test")], capture_output=True, text=True)
+    assert r.returncode == 0 and "passed" in r.stdout, r.stdout[-2000:]
