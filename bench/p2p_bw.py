@@ -3,7 +3,7 @@
 rank 0 pushes from its own heap into rank 1's heap through the same sm_100a cluster kernels
 that serve the plugin's isend.  Launch with torchrun on >= 2 GPUs.
 
-  python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/p2p_bw.py
+  python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 bench/p2p_bw.py
 Env: BNET_COPY_ENGINE=ldst|tma  BNET_NCLUSTERS  BNET_CLUSTER_SIZE  BNET_PERSISTENT
 """
 import os

@@ -24,8 +24,8 @@ step bench2 400 $TR --master-port 29541 bench.py --gpus $NG --steps 20 --warmup 
 # ---- tuning: CTA count for the NVLS all-reduce, engine choice for the transport kernels
 TAILN=60 step sweep_blocks 400 $TR --master-port 29561 bench/allreduce_sweep.py --min 16M --max 1G --algos nvls,p2p --blocks 32,64,96,148,200,296 --json $OUT/sweep_blocks.json
 TAILN=60 step sweep_all 400 $TR --master-port 29562 bench/allreduce_sweep.py --min 1K --max 1G --json $OUT/sweep_all.json
-TAILN=20 step p2p_ldst 200 $TR --master-port 29563 tools/p2p_bw.py
-TAILN=20 step p2p_tma 200 env BNET_COPY_ENGINE=tma $TR --master-port 29564 tools/p2p_bw.py
-TAILN=20 step p2p_8x4 200 env BNET_NCLUSTERS=8 BNET_CLUSTER_SIZE=4 $TR --master-port 29565 tools/p2p_bw.py
+TAILN=20 step p2p_ldst 200 $TR --master-port 29563 bench/p2p_bw.py
+TAILN=20 step p2p_tma 200 env BNET_COPY_ENGINE=tma $TR --master-port 29564 bench/p2p_bw.py
+TAILN=20 step p2p_8x4 200 env BNET_NCLUSTERS=8 BNET_CLUSTER_SIZE=4 $TR --master-port 29565 bench/p2p_bw.py
 TAILN=40 step nccl_perf_stock 300 build/bench/all_reduce_perf -b 8 -e 128M -f 4 -N $NG -d bfloat16
 echo "== done $(date -u)"

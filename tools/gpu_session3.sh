@@ -23,7 +23,7 @@ TAILN=32 step step_profile_fused 200 python tools/step_profile.py --out $OUT/ste
 CUT=1500 TAILN=3 step bench2_plugin 240 env BNET_WATCHDOG_MS=8000 $TR --master-port 29543 bench.py --gpus $NG --steps 10 --warmup 3 --comm nccl-plugin --no-e2e
 TAILN=60 step sweep_blocks 400 $TR --master-port 29561 bench/allreduce_sweep.py --min-bytes 16M --max-bytes 1G --algos nvls,p2p --blocks 32,64,96,148,200,296 --json $OUT/sweep_blocks.json
 TAILN=80 step sweep_all 400 $TR --master-port 29562 bench/allreduce_sweep.py --min-bytes 1K --max-bytes 1G --json $OUT/sweep_all.json
-TAILN=20 step p2p_default 200 $TR --master-port 29563 tools/p2p_bw.py
-TAILN=20 step p2p_tma 200 env BNET_COPY_ENGINE=tma $TR --master-port 29564 tools/p2p_bw.py
+TAILN=20 step p2p_default 200 $TR --master-port 29563 bench/p2p_bw.py
+TAILN=20 step p2p_tma 200 env BNET_COPY_ENGINE=tma $TR --master-port 29564 bench/p2p_bw.py
 TAILN=40 step nccl_perf_plugin 300 env $(python -m bagua_net_b200.utils.env) build/bench/all_reduce_perf -b 8 -e 128M -f 4 -N $NG -d bfloat16
 echo "== done $(date -u)"
