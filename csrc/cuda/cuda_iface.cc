@@ -69,6 +69,9 @@ const DriverApi& driver() {
     BIND(MulticastBindMem, "cuMulticastBindMem");
     BIND(MulticastUnbind, "cuMulticastUnbind");
     BIND(MulticastGetGranularity, "cuMulticastGetGranularity");
+    // stream memory operations (copy-engine transport mode): optional as well
+    *(void**)(&a.StreamWriteValue64) = dlsym(h, "cuStreamWriteValue64_v2");
+    if (!a.StreamWriteValue64) *(void**)(&a.StreamWriteValue64) = dlsym(h, "cuStreamWriteValue64");
 #undef BIND
     a.ok = core;
     return a;

@@ -32,6 +32,7 @@ struct DriverApi {
   CUresult (*MulticastBindMem)(CUmemGenericAllocationHandle, size_t, CUmemGenericAllocationHandle, size_t, size_t, unsigned long long);
   CUresult (*MulticastUnbind)(CUmemGenericAllocationHandle, CUdevice, size_t, size_t);
   CUresult (*MulticastGetGranularity)(size_t*, const CUmulticastObjectProp*, CUmulticastGranularity_flags);
+  CUresult (*StreamWriteValue64)(CUstream, CUdeviceptr, cuuint64_t, unsigned int);   // optional
 };
 
 const DriverApi& driver();            // .ok == false when libcuda is missing

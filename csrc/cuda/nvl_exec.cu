@@ -31,6 +31,7 @@
 
 #include "core/common.h"
 #include "cuda/cuda_iface.h"
+#include "cuda/driver_api.h"
 #include "cuda/nvl_exec.h"
 #include "cuda/ptx.cuh"
 
@@ -497,6 +498,7 @@ struct Exec {
   bool ok = false;
   bool persistent = true;
   bool tma = false;
+  bool ce = false;             // BNET_COPY_ENGINE=ce: DMA copy engines + stream memory ops, no kernels at all
   int nclusters = 4;
   int cluster_size = 2;
   size_t min_chunk = 1 << 20;
@@ -544,6 +546,7 @@ Exec* get_exec(int dev) {
   if (e->min_chunk < 16) e->min_chunk = 16;
   e->persistent = env_int("PERSISTENT", 1) != 0;
   e->tma = env_str("COPY_ENGINE", "ldst") == "tma";
+  e->ce = env_str("COPY_ENGINE", "ldst") == "ce" && driver().ok && driver().StreamWriteValue64 != nullptr;
   e->idle_ns = (uint64_t)env_int("KERNEL_IDLE_US", 1000) * 1000ull;
   e->arm_ns = (uint64_t)env_int("KERNEL_ARM_MS", 50) * 1000000ull;
   int cur = -1;
@@ -610,7 +613,7 @@ Exec* get_exec(int dev) {
   e->ok = good;
   BNET_INFO("nvl executor on dev %d: %d cluster(s) x %d CTA x %d thr, %s, engine=%s, min chunk %zu, idle %llu us",
             dev, e->nclusters, e->cluster_size, kThreads, e->persistent ? "persistent" : "one-shot",
-            e->tma ? "tma" : "ld/st", e->min_chunk, (unsigned long long)(e->idle_ns / 1000));
+            e->ce ? "copy-engine" : e->tma ? "tma" : "ld/st", e->min_chunk, (unsigned long long)(e->idle_ns / 1000));
   return good ? e : nullptr;
 }
 
@@ -660,6 +663,19 @@ int submit(Exec* e, uint32_t op, const void* src, void* dst, size_t nbytes, uint
     size_t n = nbytes ? (nbytes - off < cs ? nbytes - off : cs) : 0;
     Stream& s = e->streams[e->rr];
     e->rr = (e->rr + 1) % e->streams.size();
+    if (e->ce && op == OP_COPY) {
+      // copy-engine mode: a DMA copy, then a stream-ordered 64-bit write of the completion word.  No SM is
+      // used and nothing stays resident between messages; the price is two driver calls per chunk.
+      cudaError_t err = n ? cudaMemcpyAsync((char*)dst + off, (const char*)src + off, n, cudaMemcpyDefault, s.stream) : cudaSuccess;
+      if (err != cudaSuccess ||
+          driver().StreamWriteValue64((CUstream)s.stream, (CUdeviceptr)(flags_dev + c), flag_value, 0) != CUDA_SUCCESS) {
+        cudaGetLastError();
+        rc = -1;
+      }
+      e->stats.launches++;
+      e->stats.chunks++;
+      continue;
+    }
     if (e->persistent) {
       uint64_t t = s.q->tail;
       uint64_t spins = 0;
@@ -752,7 +768,7 @@ int exec_prepare(int dev) {
   if (fake()) return 0;
   Exec* e = get_exec(dev);
   if (!e) return -1;
-  if (!e->persistent || e->arm_ns == 0) return 0;
+  if (!e->persistent || e->arm_ns == 0 || e->ce) return 0;   // (copy-engine mode keeps nothing resident)
   // Arm: have the stream kernels resident BEFORE the first message so that the data path
   // needs no kernel launch (one that could be held up by a device-synchronising call
   // elsewhere in the process while the NCCL kernel it serves is already waiting).
