@@ -135,3 +135,21 @@ def test_nccl_loads_plugin_and_allreduces():
     outs = _run_worker("nccl_allreduce", 2, extra_env=env, timeout=300)
     log = "".join(o + e for _, o, e in outs)
     assert "Using network BNet" in log or "NET/Plugin: Loaded net plugin BNet" in log, log[-4000:]
+
+
+# ------------------------------------------------------------------ newest paths last (a failure here must not hide the rest under -x)
+def test_executor_copy_engine_mode():
+    """BNET_COPY_ENGINE=ce: plain copies ride the DMA engines + a stream-ordered completion word; the fused
+    reduce/cast ops still use the cluster kernels."""
+    _run_worker("executor", 1, extra_env={"BNET_COPY_ENGINE": "ce"})
+
+
+@pytest.mark.multigpu
+def test_plugin_nvl_transport_copy_engine_mode():
+    from conftest import run_pair
+
+    outs = run_pair(["--mem", "cuda", "--sizes", "0,1,8,4096,524288,1048577,4194304", "--inflight", "8", "--rounds", "2"],
+                    env={"BNET_NVL": "1", "BNET_COPY_ENGINE": "ce"}, timeout=240)
+    for rc, res, err in outs:
+        assert res is not None and rc == 0 and res["ok"], (res, err[-3000:])
+        assert res["transport"] == "nvl"
