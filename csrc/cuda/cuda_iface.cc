@@ -177,6 +177,18 @@ bool pointer_is_device(const void* p, int* dev_out) {
   return a.type == cudaMemoryTypeDevice;
 }
 
+void* host_device_alias(const void* host_ptr) {
+  if (fake_mode()) return const_cast<void*>(host_ptr);   // the emulated "kernel" is a memcpy in this process
+  if (!available()) return nullptr;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, host_ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (a.type != cudaMemoryTypeHost) return nullptr;       // pageable memory: the GPU cannot read it
+  return a.devicePointer;
+}
+
 // ------------------------------------------------------------------ export / import
 int export_memory(const void* ptr, size_t size, MemExport* out) {
   memset(out, 0, sizeof(*out));

@@ -14,6 +14,8 @@ bool fake();                      // BNET_FAKE_CUDA=1: host-memory emulation for
 int device_count();
 int current_device();             // -1 when unavailable
 bool pointer_is_device(const void* p, int* dev_out);
+// device-side alias of pinned/registered host memory (nullptr when the GPU cannot read it directly)
+void* host_device_alias(const void* host_ptr);
 
 // ---- cross-process memory export / import (regMr for NCCL_PTR_CUDA) ----------
 enum ExportKind : uint32_t { EXPORT_NONE = 0, EXPORT_CUDA_IPC = 1, EXPORT_POSIX_FD = 2, EXPORT_SAME_PROCESS = 3 };

@@ -238,6 +238,12 @@ class NvlComm : public Comm {
         BNET_INFO("nvl regMr: %p +%zu not exportable; this buffer will use the bounce ring", data, size);
       }
     }
+    if (kind == SEND && type == NCCL_PTR_HOST && cuda::available()) {
+      // BNET_HOST_SRC_DIRECT=1: pinned host sources (NCCL keeps its LL send buffers in host memory) are read by
+      // the copy kernel itself and stored straight into the peer GPU, instead of ring + staged H2D copy
+      static const bool host_direct = env_int("HOST_SRC_DIRECT", 0) != 0;
+      if (host_direct) mh->priv = cuda::host_device_alias(data);
+    }
     *out = mh;
     return kOk;
   }
@@ -566,8 +572,12 @@ class NvlComm : public Comm {
           continue;
         }
         bool src_cuda = r->mh && r->mh->type == NCCL_PTR_CUDA;
+        // what the copy kernel reads: the device buffer, or the device alias of a pinned host buffer
+        const char* ksrc = src_cuda ? (const char*)r->buf : nullptr;
+        if (!src_cuda && r->mh && r->mh->priv)
+          ksrc = (const char*)r->mh->priv + ((const char*)r->buf - (const char*)r->mh->addr);
         char* dst = nullptr;
-        if (r->size && src_cuda && d.dst_type == NCCL_PTR_CUDA && d.mr_idx != kNoMr && flags_) {
+        if (r->size && ksrc && d.dst_type == NCCL_PTR_CUDA && d.mr_idx != kNoMr && flags_) {
           bool retry = false;
           dst = resolve(d.mr_idx, d.offset, &retry);
           if (retry) break;
@@ -577,7 +587,7 @@ class NvlComm : public Comm {
         if (dst) {
           uint64_t* fh = flags_ + (k % kSlots) * cuda::kMaxChunksPerJob;
           uint64_t* fd = flags_dev_ + (k % kSlots) * cuda::kMaxChunksPerJob;
-          direct = cuda::exec_copy(local_dev_, r->buf, dst, r->size, fh, fd, k + 1, &nchunks) == 0;
+          direct = cuda::exec_copy(local_dev_, ksrc, dst, r->size, fh, fd, k + 1, &nchunks) == 0;
         }
         a.nbytes = r->size;
         a.via_ring = direct ? 0 : 1;

@@ -93,6 +93,7 @@ def main() -> int:
     ap.add_argument("--inflight", type=int, default=8)
     ap.add_argument("--rounds", type=int, default=2)
     ap.add_argument("--mem", default="host", choices=["host", "fakecuda", "cuda"])
+    ap.add_argument("--send-mem", default=None, choices=["host", "fakecuda", "cuda"], help="sender's memory kind (default: --mem)")
     ap.add_argument("--die-after", type=int, default=-1, help="sender exits abruptly after N messages")
     ap.add_argument("--expect-error", action="store_true")
     ap.add_argument("--bw", action="store_true", help="print a bandwidth line for the largest size")
@@ -109,7 +110,8 @@ def main() -> int:
 
         torch.cuda.set_device(int(os.environ.get("BNET_TEST_CUDA_DEV", a.role)) % torch.cuda.device_count())
         torch.zeros(1, device="cuda")
-    alloc = (lambda n: FakeCudaBuf(p.lib, n)) if a.mem == "fakecuda" else (CudaBuf if a.mem == "cuda" else HostBuf)
+    mem = a.send_mem if (a.role == 1 and a.send_mem) else a.mem
+    alloc = (lambda n: FakeCudaBuf(p.lib, n)) if mem == "fakecuda" else (CudaBuf if mem == "cuda" else HostBuf)
 
     if a.role == 0:
         handle, lcomm = p.listen(0)
@@ -183,6 +185,8 @@ def main() -> int:
         from bagua_net_b200.utils import native
 
         result["exec"] = native.exec_stats()
+        result["kernel_chunks"] = sum(int(float(ln.split()[-1])) for ln in native.metrics_text().splitlines()
+                                      if ln.startswith("bnet_nvl_kernel_chunks_total"))
     except Exception:
         pass
     (p.close_recv if a.role == 0 else p.close_send)(comm)

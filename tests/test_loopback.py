@@ -100,6 +100,16 @@ def test_nvl_direct_path_with_emulated_device_memory():
     assert outs[0][1]["messages"] == 96
 
 
+def test_nvl_pinned_host_source_goes_direct_when_enabled():
+    # NCCL keeps its LL send buffers in pinned host memory; with BNET_HOST_SRC_DIRECT=1 the copy kernel reads them
+    # through their device alias and stores into the peer's device buffer (emulated here), no ring, no staging
+    args = ["--mem", "fakecuda", "--send-mem", "host", "--sizes", "0,1,8,4096,1048577", "--inflight", "8", "--rounds", "2"]
+    on = _check(run_pair(args, env={"BNET_NVL": "1", "BNET_FAKE_CUDA": "1", "BNET_HOST_SRC_DIRECT": "1"}), "nvl")
+    assert on[1][1]["kernel_chunks"] > 0, on[1][1]
+    off = _check(run_pair(args, env={"BNET_NVL": "1", "BNET_FAKE_CUDA": "1"}), "nvl")
+    assert off[1][1]["kernel_chunks"] == 0, off[1][1]
+
+
 def test_cuda_pointers_over_tcp_are_staged():
     _check(run_pair(["--mem", "fakecuda", "--sizes", "1,4096,1048577,3145729", "--inflight", "4", "--rounds", "1"],
                     env={"BNET_NVL": "0", "BNET_FAKE_CUDA": "1"}), "tcp-threads")
