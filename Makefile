@@ -68,15 +68,21 @@ $(BUILD)/tests/%: csrc/tests/%.cc $(PLUGIN_SO)
 	@mkdir -p $(dir $@)
 	$(CXX) $(CXXFLAGS) -fvisibility=default $< -o $@ -ldl -pthread
 
-# the per-thread bodies of the fused layer kernels, compiled by g++ and walked over an emulated grid
+# the per-thread bodies of the device kernels (fused layers, transport executor), compiled by g++ and walked
+# over an emulated grid / cluster
+EMU_FLAGS := -O2 -g -std=c++17 -Wall -Wno-unknown-pragmas -fno-strict-aliasing -Icsrc -I$(CUDA_HOME)/include
 $(BUILD)/tests/nn_emu_test: csrc/tests/nn_emu_test.cc csrc/cuda/nn_body.cuh
 	@mkdir -p $(dir $@)
-	$(CXX) -O2 -g -std=c++17 -Wall -fno-strict-aliasing -Icsrc -I$(CUDA_HOME)/include $< -o $@
+	$(CXX) $(EMU_FLAGS) $< -o $@
+$(BUILD)/tests/exec_emu_test: csrc/tests/exec_emu_test.cc csrc/cuda/exec_body.cuh
+	@mkdir -p $(dir $@)
+	$(CXX) $(EMU_FLAGS) $< -o $@
 
-test: $(TEST_BINS) $(BUILD)/tests/nn_emu_test
+test: $(TEST_BINS) $(BUILD)/tests/nn_emu_test $(BUILD)/tests/exec_emu_test
 	$(BUILD)/tests/unit_tests $(PLUGIN_SO)
 	$(BUILD)/tests/loopback_test $(PLUGIN_SO)
 	$(BUILD)/tests/nn_emu_test
+	$(BUILD)/tests/exec_emu_test
 
 BENCH_BINS := $(BUILD)/bench/all_reduce_perf
 NCCL_HOME ?= $(shell python -c "import nvidia.nccl, os; print(os.path.dirname(nvidia.nccl.__file__))" 2>/dev/null)

@@ -1,0 +1,375 @@
+// The data-movement bodies of the transport executor (csrc/cuda/nvl_exec.cu): what ONE CTA does with its share
+// of a job — copy (K1), move + accumulate (K4), move + cast (K5), fp8 gradient compression.
+//
+// Written as functions of (tid, nthreads) with the PTX accesses behind __CUDA_ARCH__ switches, so that the
+// SAME code is inlined into the sm_100a kernels by nvcc and compiled by g++ for csrc/tests/exec_emu_test.cc,
+// which walks an emulated CTA over every op, size and alignment on the CPU (`make test`, no GPU needed).
+//
+// Memory-level parallelism: every vector loop is `batched<U>` — U 16-byte loads are issued before the first
+// dependent instruction (the reductions/stores that follow are fire-and-forget), see profiles/README.md.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp8.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define BNET_XD __host__ __device__ __forceinline__
+#define BNET_XD_FN __host__ __device__ inline
+#else
+#define BNET_XD inline
+#define BNET_XD_FN inline
+#endif
+
+namespace bnet {
+namespace cuda {
+
+enum ExecOp : uint32_t {
+  OP_COPY = 0,
+  OP_RED_ADD_F32 = 1,      // dst(f32) += src(f32)           (K4: accumulate while moving)
+  OP_RED_ADD_BF16 = 2,     // dst(bf16) += src(bf16)
+  OP_CAST_BF16_TO_F32 = 3, // dst(f32) = src(bf16)           (K5)
+  OP_CAST_F32_TO_BF16 = 4, // dst(bf16) = src(f32)
+  OP_FLUSH = 5,            // K7: fence only
+  OP_ACC_BF16_TO_F32 = 6,  // dst(f32) += src(bf16)          (K4+K5 fused)
+  OP_CAST_BF16_TO_E4M3 = 7,  // dst(fp8 e4m3) = sat(src(bf16) * scale)   (gradient compression, K5)
+  OP_ACC_E4M3_TO_F32 = 8,    // dst(f32) += src(fp8 e4m3) * scale        (decompress + accumulate)
+  OP_CAST_F32_TO_E4M3 = 9,   // dst(fp8 e4m3) = sat(src(f32) * scale)
+};
+
+namespace xb {   // access primitives: PTX on the device, plain C++ in the emulation
+
+BNET_XD int4 ld16(const int4* p) {
+#if defined(__CUDA_ARCH__)
+  int4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+#else
+  int4 r;
+  memcpy(&r, p, 16);
+  return r;
+#endif
+}
+BNET_XD void st16(int4* p, const int4& v) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+#else
+  memcpy(p, &v, 16);
+#endif
+}
+BNET_XD float4 ld16f(const float4* p) {
+#if defined(__CUDA_ARCH__)
+  float4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+  return r;
+#else
+  float4 r;
+  memcpy(&r, p, 16);
+  return r;
+#endif
+}
+BNET_XD void st16f(float4* p, const float4& v) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+#else
+  memcpy(p, &v, 16);
+#endif
+}
+BNET_XD uint2 ld8(const void* p) {          // p is 8-byte aligned
+#if defined(__CUDA_ARCH__)
+  return *reinterpret_cast<const uint2*>(p);
+#else
+  uint2 r;
+  memcpy(&r, p, 8);
+  return r;
+#endif
+}
+BNET_XD void st8(void* p, const uint2& v) {  // p is 8-byte aligned
+#if defined(__CUDA_ARCH__)
+  *reinterpret_cast<uint2*>(p) = v;
+#else
+  memcpy(p, &v, 8);
+#endif
+}
+// fire-and-forget reductions at system scope (one packet over NVLink, no return value)
+BNET_XD void red_f32(float* p, float v) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+#else
+  *p += v;
+#endif
+}
+BNET_XD void red_v4_f32(float* p, const float4& v) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+#else
+  p[0] += v.x; p[1] += v.y; p[2] += v.z; p[3] += v.w;
+#endif
+}
+BNET_XD void red_bf16(__nv_bfloat16* p, __nv_bfloat16 v) {
+#if defined(__CUDA_ARCH__)
+  atomicAdd(p, v);
+#else
+  *p = __float2bfloat16(__bfloat162float(*p) + __bfloat162float(v));
+#endif
+}
+BNET_XD void red_v4_bf16x2(uint32_t* p, const int4& v) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("red.relaxed.sys.global.add.noftz.v4.bf16x2 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+#else
+  __nv_bfloat16 s[8];
+  memcpy((void*)s, &v, 16);
+  __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p);
+  for (int k = 0; k < 8; k++) red_bf16(d + k, s[k]);
+#endif
+}
+
+// U independent 16/32-byte loads in flight per thread, then the dependent work
+template <int U, typename Raw, typename Load, typename Use>
+BNET_XD void batched(size_t nvec, int tid, int nthreads, Load load, Use use) {
+  size_t i = (size_t)tid;
+  const size_t stride = (size_t)nthreads;
+  for (; i + (U - 1) * stride < nvec; i += U * stride) {
+    Raw v[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) v[u] = load(i + u * stride);
+#pragma unroll
+    for (int u = 0; u < U; u++) use(i + u * stride, v[u]);
+  }
+  for (; i < nvec; i += stride) use(i, load(i));
+}
+
+struct F8 { float4 lo, hi; };   // 8 floats = two 16-byte loads
+
+BNET_XD void unpack_bf16x8(const int4& v, float4* lo, float4* hi) {
+  __nv_bfloat162 h[4];
+  memcpy((void*)h, &v, 16);
+  float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+  float2 c = __bfloat1622float2(h[2]), e = __bfloat1622float2(h[3]);
+  *lo = make_float4(a.x, a.y, b.x, b.y);
+  *hi = make_float4(c.x, c.y, e.x, e.y);
+}
+
+}  // namespace xb
+
+// source bytes per indivisible work unit (keeps CTA / chunk cuts vector-aligned on BOTH sides)
+BNET_XD size_t src_unit_for(uint32_t op) {
+  if (op == OP_CAST_F32_TO_BF16 || op == OP_CAST_BF16_TO_E4M3 || op == OP_RED_ADD_F32) return 32;
+  if (op == OP_CAST_F32_TO_E4M3) return 64;
+  return 16;
+}
+
+// destination offset that corresponds to a source offset
+BNET_XD size_t dst_offset_for(uint32_t op, size_t src_off) {
+  if (op == OP_CAST_BF16_TO_F32 || op == OP_ACC_BF16_TO_F32) return src_off * 2;
+  if (op == OP_CAST_F32_TO_BF16 || op == OP_CAST_BF16_TO_E4M3) return src_off / 2;
+  if (op == OP_ACC_E4M3_TO_F32) return src_off * 4;
+  if (op == OP_CAST_F32_TO_E4M3) return src_off / 4;
+  return src_off;
+}
+
+// Every CTA of a cluster takes a contiguous share [b0, b1) of the job's source bytes, cut at multiples of the
+// op's work unit so that both the source and the destination side of every share stay vector aligned.
+BNET_XD void cta_share(uint32_t op, size_t nbytes, uint32_t crank, uint32_t csize, size_t* b0, size_t* b1) {
+  const size_t unit = src_unit_for(op);
+  const size_t units = (nbytes + unit - 1) / unit;
+  const size_t per = (units + csize - 1) / csize;
+  size_t lo = (size_t)crank * per * unit, hi = lo + per * unit;
+  if (lo > nbytes) lo = nbytes;
+  if (hi > nbytes) hi = nbytes;
+  *b0 = lo;
+  *b1 = hi;
+}
+
+// Moves/reduces [0,n) source bytes for one CTA's share.  tid/nthreads are CTA-local.
+BNET_XD_FN void process_range(uint32_t op, const char* src, char* dst, size_t n, int tid, int nthreads, float scale = 1.0f) {
+  if (n == 0) return;
+  if (op == OP_COPY) {
+    // align the destination, then go wide if the source agrees
+    size_t head = (16 - ((uintptr_t)dst & 15)) & 15;
+    if (head > n) head = n;
+    for (size_t i = tid; i < head; i += nthreads) dst[i] = src[i];
+    src += head; dst += head; n -= head;
+    if (((uintptr_t)src & 15) == 0) {
+      const size_t nvec = n >> 4;
+      const int4* s = reinterpret_cast<const int4*>(src);
+      int4* d = reinterpret_cast<int4*>(dst);
+      xb::batched<8, int4>(nvec, tid, nthreads, [&](size_t i) { return xb::ld16(s + i); },
+                           [&](size_t i, const int4& v) { xb::st16(d + i, v); });
+      for (size_t i = (nvec << 4) + tid; i < n; i += nthreads) dst[i] = src[i];
+    } else if ((((uintptr_t)src ^ (uintptr_t)dst) & 3) == 0) {
+      size_t n4 = n >> 2;
+      const uint32_t* s4 = (const uint32_t*)src;
+      uint32_t* d4 = (uint32_t*)dst;
+      for (size_t i = tid; i < n4; i += nthreads) d4[i] = s4[i];
+      for (size_t i = (n4 << 2) + tid; i < n; i += nthreads) dst[i] = src[i];
+    } else {
+      for (size_t i = tid; i < n; i += nthreads) dst[i] = src[i];
+    }
+    return;
+  }
+  if (op == OP_RED_ADD_F32) {
+    size_t ne = n >> 2;
+    const float* s = (const float*)src;
+    float* d = (float*)dst;
+    if ((((uintptr_t)s | (uintptr_t)d) & 15) == 0) {
+      size_t nv = ne >> 2;
+      xb::batched<8, float4>(nv, tid, nthreads, [&](size_t i) { return xb::ld16f(reinterpret_cast<const float4*>(s) + i); },
+                             [&](size_t i, const float4& v) { xb::red_v4_f32(d + 4 * i, v); });   // 16-byte reduction packets
+      for (size_t i = (nv << 2) + tid; i < ne; i += nthreads) xb::red_f32(d + i, s[i]);
+    } else {
+      for (size_t i = tid; i < ne; i += nthreads) xb::red_f32(d + i, s[i]);
+    }
+    return;
+  }
+  if (op == OP_RED_ADD_BF16) {
+    size_t ne = n >> 1;
+    const __nv_bfloat16* s = (const __nv_bfloat16*)src;
+    __nv_bfloat16* d = (__nv_bfloat16*)dst;
+    if ((((uintptr_t)s | (uintptr_t)d) & 15) == 0) {
+      size_t nv = ne >> 3;
+      xb::batched<8, int4>(nv, tid, nthreads, [&](size_t i) { return xb::ld16(reinterpret_cast<const int4*>(s) + i); },
+                           [&](size_t i, const int4& v) { xb::red_v4_bf16x2(reinterpret_cast<uint32_t*>(d) + 4 * i, v); });
+      for (size_t i = (nv << 3) + tid; i < ne; i += nthreads) xb::red_bf16(d + i, s[i]);
+    } else {
+      for (size_t i = tid; i < ne; i += nthreads) xb::red_bf16(d + i, s[i]);
+    }
+    return;
+  }
+  if (op == OP_CAST_BF16_TO_F32 || op == OP_ACC_BF16_TO_F32) {
+    size_t ne = n >> 1;
+    const __nv_bfloat16* s = (const __nv_bfloat16*)src;
+    float* d = (float*)dst;
+    const bool acc = op == OP_ACC_BF16_TO_F32;
+    if ((((uintptr_t)s | (uintptr_t)d) & 15) == 0) {
+      size_t nv = ne >> 3;   // 8 bf16 in, 2 x float4 out
+      xb::batched<8, int4>(nv, tid, nthreads, [&](size_t i) { return xb::ld16(reinterpret_cast<const int4*>(s) + i); },
+                           [&](size_t i, const int4& v) {
+                             float4 lo, hi;
+                             xb::unpack_bf16x8(v, &lo, &hi);
+                             if (acc) {
+                               xb::red_v4_f32(d + 8 * i, lo);
+                               xb::red_v4_f32(d + 8 * i + 4, hi);
+                             } else {
+                               xb::st16f(reinterpret_cast<float4*>(d) + 2 * i, lo);
+                               xb::st16f(reinterpret_cast<float4*>(d) + 2 * i + 1, hi);
+                             }
+                           });
+      for (size_t i = (nv << 3) + tid; i < ne; i += nthreads) {
+        float f = __bfloat162float(s[i]);
+        if (acc) xb::red_f32(d + i, f); else d[i] = f;
+      }
+    } else {
+      for (size_t i = tid; i < ne; i += nthreads) {
+        float f = __bfloat162float(s[i]);
+        if (acc) xb::red_f32(d + i, f); else d[i] = f;
+      }
+    }
+    return;
+  }
+  if (op == OP_CAST_F32_TO_BF16) {
+    size_t ne = n >> 2;
+    const float* s = (const float*)src;
+    __nv_bfloat16* d = (__nv_bfloat16*)dst;
+    if ((((uintptr_t)s | (uintptr_t)d) & 15) == 0) {
+      size_t nv = ne >> 3;   // 2 x float4 in, 8 bf16 out
+      xb::batched<4, xb::F8>(nv, tid, nthreads,
+                             [&](size_t i) {
+                               xb::F8 r;
+                               r.lo = xb::ld16f(reinterpret_cast<const float4*>(s) + 2 * i);
+                               r.hi = xb::ld16f(reinterpret_cast<const float4*>(s) + 2 * i + 1);
+                               return r;
+                             },
+                             [&](size_t i, const xb::F8& r) {
+                               __nv_bfloat162 h[4];
+                               h[0] = __floats2bfloat162_rn(r.lo.x, r.lo.y);
+                               h[1] = __floats2bfloat162_rn(r.lo.z, r.lo.w);
+                               h[2] = __floats2bfloat162_rn(r.hi.x, r.hi.y);
+                               h[3] = __floats2bfloat162_rn(r.hi.z, r.hi.w);
+                               int4 o;
+                               memcpy(&o, h, 16);
+                               xb::st16(reinterpret_cast<int4*>(d) + i, o);
+                             });
+      for (size_t i = (nv << 3) + tid; i < ne; i += nthreads) d[i] = __float2bfloat16_rn(s[i]);
+    } else {
+      for (size_t i = tid; i < ne; i += nthreads) d[i] = __float2bfloat16_rn(s[i]);
+    }
+    return;
+  }
+  if (op == OP_CAST_BF16_TO_E4M3 || op == OP_CAST_F32_TO_E4M3) {
+    // 8 source elements -> 8 fp8 bytes per step (one 8-byte store), saturating e4m3
+    const bool from_bf16 = op == OP_CAST_BF16_TO_E4M3;
+    size_t ne = from_bf16 ? n >> 1 : n >> 2;
+    unsigned char* d = (unsigned char*)dst;
+    auto q1 = [&](float f) -> unsigned char {
+      return (unsigned char)__nv_cvt_float_to_fp8(f * scale, __NV_SATFINITE, __NV_E4M3);
+    };
+    auto pack8 = [&](size_t i, const xb::F8& r) {
+      const float f[8] = {r.lo.x, r.lo.y, r.lo.z, r.lo.w, r.hi.x, r.hi.y, r.hi.z, r.hi.w};
+      uint32_t w[2];
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        uint32_t a = __nv_cvt_float2_to_fp8x2(make_float2(f[4 * k] * scale, f[4 * k + 1] * scale), __NV_SATFINITE, __NV_E4M3);
+        uint32_t b = __nv_cvt_float2_to_fp8x2(make_float2(f[4 * k + 2] * scale, f[4 * k + 3] * scale), __NV_SATFINITE, __NV_E4M3);
+        w[k] = (a & 0xffffu) | (b << 16);
+      }
+      xb::st8(d + 8 * i, make_uint2(w[0], w[1]));
+    };
+    if ((((uintptr_t)src) & 15) == 0 && (((uintptr_t)d) & 7) == 0) {
+      size_t nv = ne >> 3;
+      if (from_bf16) {
+        xb::batched<8, int4>(nv, tid, nthreads, [&](size_t i) { return xb::ld16(reinterpret_cast<const int4*>(src) + i); },
+                             [&](size_t i, const int4& v) {
+                               xb::F8 r;
+                               xb::unpack_bf16x8(v, &r.lo, &r.hi);
+                               pack8(i, r);
+                             });
+      } else {
+        xb::batched<4, xb::F8>(nv, tid, nthreads,
+                               [&](size_t i) {
+                                 xb::F8 r;
+                                 r.lo = xb::ld16f(reinterpret_cast<const float4*>(src) + 2 * i);
+                                 r.hi = xb::ld16f(reinterpret_cast<const float4*>(src) + 2 * i + 1);
+                                 return r;
+                               },
+                               pack8);
+      }
+      for (size_t i = (nv << 3) + tid; i < ne; i += nthreads)
+        d[i] = q1(from_bf16 ? __bfloat162float(((const __nv_bfloat16*)src)[i]) : ((const float*)src)[i]);
+    } else {
+      for (size_t i = tid; i < ne; i += nthreads)
+        d[i] = q1(from_bf16 ? __bfloat162float(((const __nv_bfloat16*)src)[i]) : ((const float*)src)[i]);
+    }
+    return;
+  }
+  if (op == OP_ACC_E4M3_TO_F32) {
+    size_t ne = n;
+    const unsigned char* s = (const unsigned char*)src;
+    float* d = (float*)dst;
+    auto dq = [&](unsigned char b) -> float {
+      __half_raw h = __nv_cvt_fp8_to_halfraw(b, __NV_E4M3);
+      __half hh;
+      memcpy(&hh, &h, sizeof(hh));
+      return __half2float(hh) * scale;
+    };
+    if ((((uintptr_t)s) & 7) == 0 && (((uintptr_t)d) & 15) == 0) {
+      size_t nv = ne >> 3;
+      xb::batched<8, uint2>(nv, tid, nthreads,
+                            [&](size_t i) { return xb::ld8(s + 8 * i); },
+                            [&](size_t i, const uint2& v) {
+                              unsigned char b[8];
+                              memcpy(b, &v, 8);
+                              xb::red_v4_f32(d + 8 * i, make_float4(dq(b[0]), dq(b[1]), dq(b[2]), dq(b[3])));
+                              xb::red_v4_f32(d + 8 * i + 4, make_float4(dq(b[4]), dq(b[5]), dq(b[6]), dq(b[7])));
+                            });
+      for (size_t i = (nv << 3) + tid; i < ne; i += nthreads) xb::red_f32(d + i, dq(s[i]));
+    } else {
+      for (size_t i = tid; i < ne; i += nthreads) xb::red_f32(d + i, dq(s[i]));
+    }
+    return;
+  }
+}
+
+}  // namespace cuda
+}  // namespace bnet

@@ -32,24 +32,12 @@
 #include "core/common.h"
 #include "cuda/cuda_iface.h"
 #include "cuda/driver_api.h"
+#include "cuda/exec_body.cuh"
 #include "cuda/nvl_exec.h"
 #include "cuda/ptx.cuh"
 
 namespace bnet {
 namespace cuda {
-
-enum ExecOp : uint32_t {
-  OP_COPY = 0,
-  OP_RED_ADD_F32 = 1,      // dst(f32) += src(f32)           (K4: accumulate while moving)
-  OP_RED_ADD_BF16 = 2,     // dst(bf16) += src(bf16)
-  OP_CAST_BF16_TO_F32 = 3, // dst(f32) = src(bf16)           (K5)
-  OP_CAST_F32_TO_BF16 = 4, // dst(bf16) = src(f32)
-  OP_FLUSH = 5,            // K7: fence only
-  OP_ACC_BF16_TO_F32 = 6,  // dst(f32) += src(bf16)          (K4+K5 fused)
-  OP_CAST_BF16_TO_E4M3 = 7,  // dst(fp8 e4m3) = sat(src(bf16) * scale)   (gradient compression, K5)
-  OP_ACC_E4M3_TO_F32 = 8,    // dst(f32) += src(fp8 e4m3) * scale        (decompress + accumulate)
-  OP_CAST_F32_TO_E4M3 = 9,   // dst(fp8 e4m3) = sat(src(f32) * scale)
-};
 
 constexpr int kQueueDepth = 64;
 constexpr int kThreads = 512;
@@ -85,218 +73,6 @@ struct SmemDesc {
   float scale;
   uint32_t pad;
 };
-
-template <int UNROLL>
-__device__ __forceinline__ void copy_vec16(const char* __restrict__ src, char* __restrict__ dst, size_t nvec,
-                                           int tid, int nthreads) {
-  const int4* s = reinterpret_cast<const int4*>(src);
-  int4* d = reinterpret_cast<int4*>(dst);
-  size_t i = tid;
-  const size_t stride = (size_t)nthreads;
-  for (; i + (UNROLL - 1) * stride < nvec; i += UNROLL * stride) {
-    int4 v[UNROLL];
-#pragma unroll
-    for (int u = 0; u < UNROLL; u++) v[u] = ptx::ld_na_v4(s + i + u * stride);   // all loads first (MLP)
-#pragma unroll
-    for (int u = 0; u < UNROLL; u++) ptx::st_na_v4(d + i + u * stride, v[u]);
-  }
-  for (; i < nvec; i += stride) ptx::st_na_v4(d + i, ptx::ld_na_v4(s + i));
-}
-
-// Moves/reduces [0,n) source bytes for one CTA's share.  tid/nthreads are CTA-local.
-__device__ void process_range(uint32_t op, const char* src, char* dst, size_t n, int tid, int nthreads,
-                              float scale = 1.0f) {
-  if (n == 0) return;
-  if (op == OP_COPY) {
-    // align the destination, then go wide if the source agrees
-    size_t head = (16 - ((uintptr_t)dst & 15)) & 15;
-    if (head > n) head = n;
-    for (size_t i = tid; i < head; i += nthreads) dst[i] = src[i];
-    src += head; dst += head; n -= head;
-    if (((uintptr_t)src & 15) == 0) {
-      size_t nvec = n >> 4;
-      copy_vec16<8>(src, dst, nvec, tid, nthreads);
-      size_t done = nvec << 4;
-      for (size_t i = done + tid; i < n; i += nthreads) dst[i] = src[i];
-    } else if ((((uintptr_t)src ^ (uintptr_t)dst) & 3) == 0) {
-      size_t n4 = n >> 2;
-      const uint32_t* s4 = (const uint32_t*)src;
-      uint32_t* d4 = (uint32_t*)dst;
-      for (size_t i = tid; i < n4; i += nthreads) d4[i] = s4[i];
-      for (size_t i = (n4 << 2) + tid; i < n; i += nthreads) dst[i] = src[i];
-    } else {
-      for (size_t i = tid; i < n; i += nthreads) dst[i] = src[i];
-    }
-    return;
-  }
-  if (op == OP_RED_ADD_F32) {
-    size_t ne = n >> 2;
-    const float* s = (const float*)src;
-    float* d = (float*)dst;
-    if ((((uintptr_t)s | (uintptr_t)d) & 15) == 0) {
-      size_t nv = ne >> 2;
-      for (size_t i = tid; i < nv; i += nthreads) {
-        float4 v = ptx::ld_na_f4(reinterpret_cast<const float4*>(s) + i);
-        ptx::red_add_v4_f32(d + 4 * i, v);      // one 16-byte reduction packet over NVLink
-      }
-      for (size_t i = (nv << 2) + tid; i < ne; i += nthreads) ptx::red_add_f32(d + i, s[i]);
-    } else {
-      for (size_t i = tid; i < ne; i += nthreads) ptx::red_add_f32(d + i, s[i]);
-    }
-    return;
-  }
-  if (op == OP_RED_ADD_BF16) {
-    size_t ne = n >> 1;
-    const __nv_bfloat16* s = (const __nv_bfloat16*)src;
-    __nv_bfloat16* d = (__nv_bfloat16*)dst;
-    if ((((uintptr_t)s | (uintptr_t)d) & 15) == 0) {
-      size_t nv = ne >> 3;
-      for (size_t i = tid; i < nv; i += nthreads) {
-        int4 v = ptx::ld_na_v4(reinterpret_cast<const int4*>(s) + i);
-        ptx::red_add_v4_bf16x2(reinterpret_cast<uint32_t*>(d) + 4 * i, v);
-      }
-      for (size_t i = (nv << 3) + tid; i < ne; i += nthreads) atomicAdd(d + i, s[i]);
-    } else {
-      for (size_t i = tid; i < ne; i += nthreads) atomicAdd(d + i, s[i]);
-    }
-    return;
-  }
-  if (op == OP_CAST_BF16_TO_F32 || op == OP_ACC_BF16_TO_F32) {
-    size_t ne = n >> 1;
-    const __nv_bfloat16* s = (const __nv_bfloat16*)src;
-    float* d = (float*)dst;
-    const bool acc = op == OP_ACC_BF16_TO_F32;
-    if ((((uintptr_t)s | (uintptr_t)d) & 15) == 0) {
-      size_t nv = ne >> 3;   // 8 bf16 in, 2 x float4 out
-      for (size_t i = tid; i < nv; i += nthreads) {
-        int4 v = ptx::ld_na_v4(reinterpret_cast<const int4*>(s) + i);
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
-        float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
-        float2 c = __bfloat1622float2(h[2]), e = __bfloat1622float2(h[3]);
-        float4 lo = make_float4(a.x, a.y, b.x, b.y), hi = make_float4(c.x, c.y, e.x, e.y);
-        if (acc) {
-          ptx::red_add_v4_f32(d + 8 * i, lo);
-          ptx::red_add_v4_f32(d + 8 * i + 4, hi);
-        } else {
-          ptx::st_na_f4(reinterpret_cast<float4*>(d) + 2 * i, lo);
-          ptx::st_na_f4(reinterpret_cast<float4*>(d) + 2 * i + 1, hi);
-        }
-      }
-      for (size_t i = (nv << 3) + tid; i < ne; i += nthreads) {
-        float f = __bfloat162float(s[i]);
-        if (acc) ptx::red_add_f32(d + i, f); else d[i] = f;
-      }
-    } else {
-      for (size_t i = tid; i < ne; i += nthreads) {
-        float f = __bfloat162float(s[i]);
-        if (acc) ptx::red_add_f32(d + i, f); else d[i] = f;
-      }
-    }
-    return;
-  }
-  if (op == OP_CAST_F32_TO_BF16) {
-    size_t ne = n >> 2;
-    const float* s = (const float*)src;
-    __nv_bfloat16* d = (__nv_bfloat16*)dst;
-    if ((((uintptr_t)s | (uintptr_t)d) & 15) == 0) {
-      size_t nv = ne >> 3;   // 2 x float4 in, 8 bf16 out
-      for (size_t i = tid; i < nv; i += nthreads) {
-        float4 lo = ptx::ld_na_f4(reinterpret_cast<const float4*>(s) + 2 * i);
-        float4 hi = ptx::ld_na_f4(reinterpret_cast<const float4*>(s) + 2 * i + 1);
-        int4 o;
-        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
-        h[0] = __floats2bfloat162_rn(lo.x, lo.y);
-        h[1] = __floats2bfloat162_rn(lo.z, lo.w);
-        h[2] = __floats2bfloat162_rn(hi.x, hi.y);
-        h[3] = __floats2bfloat162_rn(hi.z, hi.w);
-        ptx::st_na_v4(reinterpret_cast<int4*>(d) + i, o);
-      }
-      for (size_t i = (nv << 3) + tid; i < ne; i += nthreads) d[i] = __float2bfloat16_rn(s[i]);
-    } else {
-      for (size_t i = tid; i < ne; i += nthreads) d[i] = __float2bfloat16_rn(s[i]);
-    }
-    return;
-  }
-  if (op == OP_CAST_BF16_TO_E4M3 || op == OP_CAST_F32_TO_E4M3) {
-    // 8 source elements -> 8 fp8 bytes per step (one 8-byte store), saturating e4m3
-    const bool from_bf16 = op == OP_CAST_BF16_TO_E4M3;
-    size_t ne = from_bf16 ? n >> 1 : n >> 2;
-    unsigned char* d = (unsigned char*)dst;
-    auto q1 = [&](float f) -> unsigned char {
-      return (unsigned char)__nv_cvt_float_to_fp8(f * scale, __NV_SATFINITE, __NV_E4M3);
-    };
-    if ((((uintptr_t)src) & 15) == 0 && (((uintptr_t)d) & 7) == 0) {
-      size_t nv = ne >> 3;
-      for (size_t i = tid; i < nv; i += nthreads) {
-        float f[8];
-        if (from_bf16) {
-          int4 v = ptx::ld_na_v4(reinterpret_cast<const int4*>(src) + i);
-          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
-#pragma unroll
-          for (int k = 0; k < 4; k++) { float2 t = __bfloat1622float2(h[k]); f[2 * k] = t.x; f[2 * k + 1] = t.y; }
-        } else {
-          float4 lo = ptx::ld_na_f4(reinterpret_cast<const float4*>(src) + 2 * i);
-          float4 hi = ptx::ld_na_f4(reinterpret_cast<const float4*>(src) + 2 * i + 1);
-          f[0] = lo.x; f[1] = lo.y; f[2] = lo.z; f[3] = lo.w; f[4] = hi.x; f[5] = hi.y; f[6] = hi.z; f[7] = hi.w;
-        }
-        uint32_t w[2];
-#pragma unroll
-        for (int k = 0; k < 2; k++) {
-          uint32_t a = __nv_cvt_float2_to_fp8x2(make_float2(f[4 * k] * scale, f[4 * k + 1] * scale), __NV_SATFINITE, __NV_E4M3);
-          uint32_t b = __nv_cvt_float2_to_fp8x2(make_float2(f[4 * k + 2] * scale, f[4 * k + 3] * scale), __NV_SATFINITE, __NV_E4M3);
-          w[k] = (a & 0xffffu) | (b << 16);
-        }
-        *reinterpret_cast<uint2*>(d + 8 * i) = make_uint2(w[0], w[1]);
-      }
-      for (size_t i = (nv << 3) + tid; i < ne; i += nthreads)
-        d[i] = q1(from_bf16 ? __bfloat162float(((const __nv_bfloat16*)src)[i]) : ((const float*)src)[i]);
-    } else {
-      for (size_t i = tid; i < ne; i += nthreads)
-        d[i] = q1(from_bf16 ? __bfloat162float(((const __nv_bfloat16*)src)[i]) : ((const float*)src)[i]);
-    }
-    return;
-  }
-  if (op == OP_ACC_E4M3_TO_F32) {
-    size_t ne = n;
-    const unsigned char* s = (const unsigned char*)src;
-    float* d = (float*)dst;
-    auto dq = [&](unsigned char b) -> float {
-      __half_raw h = __nv_cvt_fp8_to_halfraw(b, __NV_E4M3);
-      return __half2float(*reinterpret_cast<__half*>(&h)) * scale;
-    };
-    if ((((uintptr_t)s) & 7) == 0 && (((uintptr_t)d) & 15) == 0) {
-      size_t nv = ne >> 3;
-      for (size_t i = tid; i < nv; i += nthreads) {
-        uint2 v = *reinterpret_cast<const uint2*>(s + 8 * i);
-        const unsigned char* b = reinterpret_cast<const unsigned char*>(&v);
-        float4 lo = make_float4(dq(b[0]), dq(b[1]), dq(b[2]), dq(b[3]));
-        float4 hi = make_float4(dq(b[4]), dq(b[5]), dq(b[6]), dq(b[7]));
-        ptx::red_add_v4_f32(d + 8 * i, lo);
-        ptx::red_add_v4_f32(d + 8 * i + 4, hi);
-      }
-      for (size_t i = (nv << 3) + tid; i < ne; i += nthreads) ptx::red_add_f32(d + i, dq(s[i]));
-    } else {
-      for (size_t i = tid; i < ne; i += nthreads) ptx::red_add_f32(d + i, dq(s[i]));
-    }
-    return;
-  }
-}
-
-// source bytes per indivisible work unit (keeps CTA / chunk cuts vector-aligned on BOTH sides)
-__device__ __host__ inline size_t src_unit_for(uint32_t op) {
-  if (op == OP_CAST_F32_TO_BF16 || op == OP_CAST_BF16_TO_E4M3 || op == OP_RED_ADD_F32) return 32;
-  if (op == OP_CAST_F32_TO_E4M3) return 64;
-  return 16;
-}
-
-// destination offset that corresponds to a source offset
-__device__ __host__ inline size_t dst_offset_for(uint32_t op, size_t src_off) {
-  if (op == OP_CAST_BF16_TO_F32 || op == OP_ACC_BF16_TO_F32) return src_off * 2;
-  if (op == OP_CAST_F32_TO_BF16 || op == OP_CAST_BF16_TO_E4M3) return src_off / 2;
-  if (op == OP_ACC_E4M3_TO_F32) return src_off * 4;
-  if (op == OP_CAST_F32_TO_E4M3) return src_off / 4;
-  return src_off;
-}
 
 // TMA bulk-copy pipeline: one elected thread per CTA moves its share through a ring of
 // shared-memory stages with cp.async.bulk (global->shared, shared->peer global).
@@ -404,13 +180,8 @@ bnet_nvl_stream_kernel(ClusterQ* q, uint64_t idle_ns, uint64_t first_idle_ns, co
 
     if (cur.op != OP_FLUSH) {
       // ---- every CTA takes a contiguous 16-byte aligned share of the source range
-      const size_t unit = src_unit_for(cur.op);
-      size_t units = (cur.nbytes + unit - 1) / unit;
-      size_t per = (units + csize - 1) / csize;
-      size_t b0 = (size_t)crank * per * unit;
-      size_t b1 = b0 + per * unit;
-      if (b0 > cur.nbytes) b0 = cur.nbytes;
-      if (b1 > cur.nbytes) b1 = cur.nbytes;
+      size_t b0, b1;
+      cta_share(cur.op, cur.nbytes, crank, csize, &b0, &b1);
       const char* s = cur.src + b0;
       char* dd = cur.dst + dst_offset_for(cur.op, b0);
       size_t n = b1 - b0;
@@ -455,12 +226,8 @@ __global__ void __launch_bounds__(kThreads, 1) bnet_nvl_oneshot_kernel(OneShotAr
   const uint32_t crank = ptx::cluster_ctarank();
   const uint32_t csize = ptx::cluster_nctarank();
   if (a.op != OP_FLUSH) {
-    const size_t unit = src_unit_for(a.op);
-    size_t units = (a.nbytes + unit - 1) / unit;
-    size_t per = (units + csize - 1) / csize;
-    size_t b0 = (size_t)crank * per * unit, b1 = b0 + per * unit;
-    if (b0 > a.nbytes) b0 = a.nbytes;
-    if (b1 > a.nbytes) b1 = a.nbytes;
+    size_t b0, b1;
+    cta_share(a.op, a.nbytes, crank, csize, &b0, &b1);
     process_range(a.op, a.src + b0, a.dst + dst_offset_for(a.op, b0), b1 - b0, threadIdx.x, kThreads, a.scale);
   }
   __syncthreads();

@@ -92,7 +92,7 @@ def test_config_env_aliases():
     assert d["nstreams"] == 2
 
 
-def test_fused_layer_kernel_bodies_on_an_emulated_grid():
+def test_device_kernel_bodies_on_an_emulated_grid():
     """csrc/cuda/nn_body.cuh compiled by g++ and walked block by block, thread by thread (csrc/tests/nn_emu_test.cc):
     the row walk, batch tails, pool index coding and bias-gradient sums of the sm_100a kernels, without a GPU."""
     import subprocess
@@ -100,6 +100,7 @@ def test_fused_layer_kernel_bodies_on_an_emulated_grid():
     import bagua_net_b200
 
     root = bagua_net_b200.REPO_ROOT
-    subprocess.run(["make", "-s", "build/tests/nn_emu_test"], cwd=root, check=True, capture_output=True)
-    r = subprocess.run([os.path.join(root, "build", "tests", "nn_emu_test")], capture_output=True, text=True)
-    assert r.returncode == 0 and "passed" in r.stdout, r.stdout[-2000:]
+    for name in ("nn_emu_test", "exec_emu_test"):    # fused layer kernels; transport executor (copy/reduce/cast/fp8)
+        subprocess.run(["make", "-s", f"build/tests/{name}"], cwd=root, check=True, capture_output=True)
+        r = subprocess.run([os.path.join(root, "build", "tests", name)], capture_output=True, text=True)
+        assert r.returncode == 0 and "passed" in r.stdout, r.stdout[-2000:]
