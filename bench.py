@@ -59,8 +59,29 @@ class ClockSampler:
         self.rows = []
         self.proc = None
         self.th = None
+        self.nvml_rows = []          # (sm MHz, max MHz, reason bitmask) every ~10 ms through NVML
+        self._nvml_stop = threading.Event()
+        self._nvml_th = None
+
+    def _nvml_loop(self):
+        # same counters nvidia-smi prints, read in-process so that a 100 ms timed region still gets ~10 samples
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self._nvml_stop.is_set():
+                self.nvml_rows.append((float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), mx, int(reasons_fn(h))))
+                self._nvml_stop.wait(0.01)
+        except Exception:
+            pass                      # the nvidia-smi sampler below stays authoritative
 
     def start(self):
+        self._nvml_th = threading.Thread(target=self._nvml_loop, daemon=True)
+        self._nvml_th.start()
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE,
@@ -77,9 +98,29 @@ class ClockSampler:
             if len(parts) >= 8:
                 self.rows.append(parts)
 
+    NVML_REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                    0x80: "hw_power_brake_slowdown"}
+
     def stop(self) -> dict:
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self._nvml_stop.set()
+        if self._nvml_th:
+            self._nvml_th.join(timeout=2)
+        if self.proc:
+            smi = self._stop_smi()
+        else:
+            smi = {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        if self.nvml_rows:
+            sm = [r[0] for r in self.nvml_rows]
+            bits = 0
+            for r in self.nvml_rows:
+                bits |= r[2]
+            reasons = sorted(set(smi.get("reasons") or []) | {n for b, n in self.NVML_REASONS.items() if bits & b})
+            return {"sm_mhz": statistics.median(sm), "sm_max_mhz": self.nvml_rows[0][1],
+                    "reasons": [r for r in reasons if r != "nvidia-smi unavailable"], "samples": len(sm),
+                    "source": "nvml (10 ms period) + nvidia-smi -lms 200", "nvidia_smi_samples": smi.get("samples", 0)}
+        return smi
+
+    def _stop_smi(self) -> dict:
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
