@@ -262,6 +262,32 @@ class BnetDDP(torch.nn.Module):
                 nxt = None
             yield float(loss.item())
 
+    # ------------------------------------------------------------------ checkpoint / resume
+    # Model weights live in ordinary nn.Module tensors (views into the flat heap), so module.state_dict() /
+    # load_state_dict() work unchanged.  The optimizer state is this rank's 1/world shard of the fp32 master
+    # weights and momentum of every bucket.
+    def optimizer_state_dict(self) -> dict:
+        return {"lr": self.lr, "momentum": self.momentum, "weight_decay": self.weight_decay,
+                "world": self.comm.world, "rank": self.comm.rank,
+                "buckets": [{"master": b.master.detach().cpu(), "momentum": b.mom.detach().cpu()} for b in self.buckets]}
+
+    def load_optimizer_state_dict(self, state: dict) -> None:
+        if state["world"] != self.comm.world or state["rank"] != self.comm.rank or len(state["buckets"]) != len(self.buckets):
+            raise ValueError("optimizer state was saved for a different world size / rank / bucket layout")
+        for b, s in zip(self.buckets, state["buckets"]):
+            if s["master"].shape != b.master.shape:
+                raise ValueError("optimizer state shard does not match this bucket")
+            b.master.copy_(s["master"])
+            b.mom.copy_(s["momentum"])
+        self.lr, self.momentum, self.weight_decay = state["lr"], state["momentum"], state["weight_decay"]
+        self._graph = None                    # hyper-parameters are baked into a captured step
+
+    def sync_master_from_params(self) -> None:
+        """After module.load_state_dict(): rebuild the fp32 master shards from the (just loaded) parameters."""
+        for b in self.buckets:
+            shard = b.numel // self.comm.world
+            b.master.copy_(b.param[self.comm.rank * shard:(self.comm.rank + 1) * shard].float())
+
     def set_lr(self, lr: float):
         self.lr = lr
 

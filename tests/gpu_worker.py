@@ -260,6 +260,15 @@ def job_ddp_engine():
     lp = list(e3.train_from_host((xh, yh) for _ in range(6)))
     assert len(lp) == 6 and all(isinstance(v, float) and v == v for v in lp) and max(lp) < lg[0] + 1.0, lp
     assert list(e3.train_from_host(iter(()))) == []
+    # checkpoint / resume: weights through the module, optimizer shards through the engine
+    weights = {k: v.clone() for k, v in m3.state_dict().items()}
+    opt = e3.optimizer_state_dict()
+    after = float(e3.train_step(x, y))
+    m3.load_state_dict(weights)
+    e3.load_optimizer_state_dict(opt)
+    torch.cuda.synchronize()
+    again = float(e3.train_step(x, y))
+    assert abs(again - after) < 5e-2, (after, again)    # same state, same batch -> same loss (bf16 tolerance)
     assert eng.comm.status() == 0 and e2.comm.status() == 0 and e3.comm.status() == 0
     teardown()
 
