@@ -88,13 +88,6 @@ __global__ void __launch_bounds__(256) pool_relu_bwd_bias_grad_kernel(const T* _
   reduce_bias_grad<V>(acc, gb, cvec, smem);
 }
 
-template <typename T>
-static int pick_threads(int cvec) {
-  // a multiple of cvec, at most 256
-  int t = (256 / cvec) * cvec;
-  return t > 0 ? t : cvec;
-}
-
 }  // namespace nn
 }  // namespace bnet
 
