@@ -196,6 +196,114 @@ class SymmComm:
         self.launches += n
 
 
+    # ------------------------------------------------------------------ collectives on ordinary tensors
+    # The kernels above work on heap tensors in place.  These wrappers accept any CUDA tensor: they stage it
+    # through a heap buffer (allocated once, same offset on every rank — every rank must make the same calls)
+    # and use the all-reduce kernels, the barrier kernel and peer mappings of the heap.
+    def _stage(self, min_bytes: int = 0) -> torch.Tensor:
+        if getattr(self, "_stage_buf", None) is None:
+            free = self.heap_bytes - self._bump - (1 << 16)
+            want = max(min(32 << 20, free), 0)
+            if want < 16 * self.world:
+                raise MemoryError("no room left in the symmetric heap for a staging buffer")
+            self._stage_buf = self.alloc(want // (16 * self.world) * (16 * self.world), torch.uint8)
+        return self._stage_buf
+
+    def _chunks(self, flat: torch.Tensor):
+        """(offset, count, heap view of `count` elements padded to the all-reduce quantum) over a flat tensor."""
+        es = flat.element_size()
+        q = 16 * self.world // es if es <= 16 else 1
+        stage = self._stage().view(flat.dtype)
+        cap = stage.numel() // q * q
+        for off in range(0, flat.numel(), cap):
+            m = min(cap, flat.numel() - off)
+            yield off, m, stage[:(m + q - 1) // q * q]
+
+    def all_reduce_tensor(self, t: torch.Tensor, op: str = "sum", algo: str = "auto", stream=None) -> torch.Tensor:
+        """In-place all-reduce of any CUDA tensor (staged through the heap, chunked if larger than the stage)."""
+        if self.world == 1:
+            return t
+        flat = t.reshape(-1) if t.is_contiguous() else t.contiguous().view(-1)
+        with torch.cuda.stream(stream) if stream is not None else _null():
+            for off, m, st in self._chunks(flat):
+                st[:m].copy_(flat[off:off + m])
+                if st.numel() > m:
+                    st[m:].zero_()
+                self.all_reduce(st, op, algo, stream=stream)
+                flat[off:off + m].copy_(st[:m])
+            if flat.data_ptr() != t.data_ptr():
+                t.copy_(flat.view(t.shape))
+        return t
+
+    def broadcast_tensor(self, t: torch.Tensor, src: int = 0) -> torch.Tensor:
+        """Every rank ends up with rank `src`'s values (read over NVLink from src's heap stage)."""
+        if self.world == 1:
+            return t
+        flat = t.reshape(-1) if t.is_contiguous() else t.contiguous().view(-1)
+        for off, m, st in self._chunks(flat):
+            if self.rank == src:
+                st[:m].copy_(flat[off:off + m])
+            self.barrier()                       # src's stage is complete (and everybody is done with the last chunk)
+            if self.rank != src:
+                flat[off:off + m].copy_(self.peer_tensor(st[:m], src))
+            self.barrier()                       # nobody still reads the stage
+        if flat.data_ptr() != t.data_ptr():
+            t.copy_(flat.view(t.shape))
+        return t
+
+    def all_gather_tensor(self, t: torch.Tensor) -> torch.Tensor:
+        """Returns a [world, *t.shape] tensor with every rank's `t`."""
+        out = torch.empty((self.world,) + tuple(t.shape), device=t.device, dtype=t.dtype)
+        if self.world == 1:
+            out[0].copy_(t)
+            return out
+        flat = t.reshape(-1) if t.is_contiguous() else t.contiguous().view(-1)
+        of = out.view(self.world, -1)
+        for off, m, st in self._chunks(flat):
+            st[:m].copy_(flat[off:off + m])
+            self.barrier()
+            for p in range(self.world):
+                of[p, off:off + m].copy_(st[:m] if p == self.rank else self.peer_tensor(st[:m], p))
+            self.barrier()
+        return out
+
+    def reduce_scatter_tensor(self, t: torch.Tensor, op: str = "sum") -> torch.Tensor:
+        """Returns this rank's 1/world slice of the element-wise reduction of every rank's `t` (numel % world == 0):
+        each rank pulls only its own slice from every peer and accumulates in fp32."""
+        if t.numel() % self.world:
+            raise ValueError("reduce_scatter_tensor: numel must be a multiple of the world size")
+        if op not in ("sum", "avg"):
+            raise ValueError("reduce_scatter_tensor supports sum / avg")
+        flat = t.reshape(-1) if t.is_contiguous() else t.contiguous().view(-1)
+        n = flat.numel() // self.world
+        if self.world == 1:
+            return flat.clone()
+        acc = torch.zeros(n, device=t.device, dtype=torch.float32)
+        stage = self._stage().view(flat.dtype)
+        cap = stage.numel()
+        for off in range(0, n, cap // self.world):
+            m = min(cap // self.world, n - off)
+            # stage layout: world slices of m elements, slice p = what rank p will pull
+            for p in range(self.world):
+                stage[p * m:(p + 1) * m].copy_(flat[p * n + off:p * n + off + m])
+            self.barrier()
+            for p in range(self.world):
+                src = stage if p == self.rank else self.peer_tensor(stage[:self.world * m], p)
+                acc[off:off + m] += src[self.rank * m:(self.rank + 1) * m].float()
+            self.barrier()
+        if op == "avg":
+            acc /= self.world
+        return acc.to(t.dtype)
+
+
+class _null:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
 def init_process_group_from_env(backend: str | None = None):
     """torch.distributed bootstrap for one-process-per-GPU launches (torchrun env)."""
     world = int(os.environ.get("WORLD_SIZE", "1"))

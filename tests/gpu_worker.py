@@ -273,6 +273,51 @@ def job_ddp_engine():
     teardown()
 
 
+def job_collectives_any():
+    """all_reduce / broadcast / all_gather / reduce_scatter on ordinary (non-heap) tensors vs torch.distributed."""
+    from bagua_net_b200.parallel import SymmComm
+
+    setup()
+    comm = SymmComm(4 << 20)               # small heap: the 4-6 MB tensors below need several staging chunks
+    torch.manual_seed(100 + RANK)
+    for dtype, n in ((torch.float32, 1), (torch.float32, 1000003), (torch.bfloat16, 4099), (torch.bfloat16, 3 << 20)):
+        x = torch.randn(n, device="cuda").to(dtype)
+        ref = x.float().clone()
+        if WORLD > 1:
+            dist.all_reduce(ref)
+        got = comm.all_reduce_tensor(x.clone())
+        tol = 1e-5 if dtype == torch.float32 else 3e-2
+        assert torch.allclose(got.float(), ref, rtol=tol, atol=tol), f"all_reduce_tensor {dtype} n={n}"
+        b = x.clone()
+        comm.broadcast_tensor(b, src=WORLD - 1)
+        refb = x.clone()
+        if WORLD > 1:
+            dist.broadcast(refb, src=WORLD - 1)
+        assert torch.equal(b, refb), f"broadcast_tensor {dtype} n={n}"
+        ag = comm.all_gather_tensor(x)
+        refs = [torch.empty_like(x) for _ in range(WORLD)]
+        if WORLD > 1:
+            dist.all_gather(refs, x)
+        else:
+            refs = [x]
+        assert torch.equal(ag, torch.stack(refs)), f"all_gather_tensor {dtype} n={n}"
+    y = torch.randn(WORLD * 50001, device="cuda")
+    rs = comm.reduce_scatter_tensor(y)
+    ref = y.clone()
+    if WORLD > 1:
+        dist.all_reduce(ref)
+    assert torch.allclose(rs, ref.view(WORLD, -1)[RANK], rtol=1e-5, atol=1e-5), "reduce_scatter_tensor"
+    m = torch.randn(5, 7, device="cuda").t()          # non-contiguous input
+    refm = m.clone()
+    if WORLD > 1:
+        dist.all_reduce(refm)
+    assert torch.allclose(comm.all_reduce_tensor(m.clone()), refm, rtol=1e-5, atol=1e-5)
+    torch.cuda.synchronize()
+    assert comm.status() == 0
+    print(f"rank {RANK}: collectives on ordinary tensors ok", flush=True)
+    teardown()
+
+
 def job_fused_nn():
     """ConvBiasReLU / ConvBiasReLUPool vs the eager PyTorch chain, forward and backward."""
     from bagua_net_b200.ops import fused_nn

@@ -153,3 +153,8 @@ def test_plugin_nvl_transport_copy_engine_mode():
     for rc, res, err in outs:
         assert res is not None and rc == 0 and res["ok"], (res, err[-3000:])
         assert res["transport"] == "nvl"
+
+
+@pytest.mark.multigpu
+def test_collectives_on_ordinary_tensors_2gpu():
+    _run_worker("collectives_any", 2)
