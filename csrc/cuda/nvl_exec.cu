@@ -212,6 +212,136 @@ bnet_nvl_stream_kernel(ClusterQ* q, uint64_t idle_ns, uint64_t first_idle_ns, co
   if (crank == 0 && tid == 0) ptx::st_release_sys_u32((uint32_t*)&q->state, ST_EXITED);
 }
 
+// ---- single-grid variant (BNET_EXEC_GRID=1) ------------------------------------------------------------------
+// The same per-cluster descriptor queues, but ALL clusters are one grid on ONE stream: a (re)launch is one
+// driver call instead of nclusters, and the executor occupies one hardware work queue instead of one per
+// cluster (other streams of the process cannot end up queued behind a resident kernel of ours).
+// Leaving is a grid-wide decision taken by cluster 0's leader: nothing submitted that is not completed
+// (host counter vs device counter), idle for long enough, no request in flight on any comm.  The Dekker
+// handshake is the same as above with ctl->submitted in the role of the descriptor's seq word.
+struct GridCtl {
+  alignas(64) volatile uint32_t state;       // ST_*
+  alignas(64) volatile uint32_t stop;        // host asks the grid to leave
+  alignas(64) volatile uint64_t submitted;   // host: descriptors published on any queue, ever
+};
+__device__ unsigned long long g_grid_completed;   // device: descriptors completed by any cluster, ever
+__device__ unsigned long long g_grid_last_work;   // device: globaltimer of the latest completion
+__device__ unsigned long long g_grid_quit_epoch;  // device: launch epoch whose clusters have been told to leave
+
+template <bool kUseTma>
+__global__ void __launch_bounds__(kThreads, 1)
+bnet_nvl_grid_kernel(GridCtl* ctl, ClusterQ* const* queues, uint64_t epoch, uint64_t idle_ns, uint64_t first_idle_ns,
+                     const uint32_t* outstanding) {
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  __shared__ SmemDesc sd;
+  __shared__ __align__(8) uint64_t bars[kTmaStages];
+  __shared__ uint32_t phases[kTmaStages];
+
+  const uint32_t crank = ptx::cluster_ctarank();
+  const uint32_t csize = ptx::cluster_nctarank();
+  const uint32_t cid = blockIdx.x / csize;           // which queue this cluster serves
+  ClusterQ* q = queues[cid];
+  const int tid = threadIdx.x;
+  if (kUseTma && tid == 0) {
+    for (int s = 0; s < kTmaStages; s++) {
+      ptx::mbar_init(&bars[s], 1);
+      phases[s] = 0;
+    }
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+
+  uint64_t head = q->head;
+  const uint64_t t_start = ptx::globaltimer();
+  uint64_t idle_limit = first_idle_ns > idle_ns ? first_idle_ns : idle_ns;
+  for (;;) {
+    if (crank == 0 && tid == 0) {
+      SmemDesc loc;
+      loc.quit = 0;
+      loc.pad = 0;
+      uint32_t backoff = 32;
+      Desc* d = &q->d[head % kQueueDepth];
+      for (;;) {
+        if (ptx::ld_acquire_sys_u64(&d->seq) == head + 1) break;
+        if (ptx::ld_relaxed_sys_u32((const uint32_t*)&ctl->stop)) { loc.quit = 1; break; }
+        if (*(volatile unsigned long long*)&g_grid_quit_epoch == epoch) { loc.quit = 1; break; }
+        if (cid == 0) {
+          const uint64_t now = ptx::globaltimer();
+          uint64_t lw = *(volatile unsigned long long*)&g_grid_last_work;
+          if (lw < t_start) lw = t_start;            // completions of earlier launches do not count
+          if (now - lw > idle_limit &&
+              (ptx::ld_relaxed_sys_u32(outstanding) == 0 || now - lw > 10000000000ull)) {
+            ptx::st_release_sys_u32((uint32_t*)&ctl->state, ST_EXITING);
+            ptx::fence_sc_sys();
+            const uint64_t sub = ptx::ld_acquire_sys_u64((const uint64_t*)&ctl->submitted);
+            const uint64_t comp = *(volatile unsigned long long*)&g_grid_completed;
+            if (sub != comp) {
+              // work was published (or is still running on another cluster) while we were deciding: stay
+              ptx::st_release_sys_u32((uint32_t*)&ctl->state, ST_RUNNING);
+              idle_limit = idle_ns;
+              atomicMax(&g_grid_last_work, (unsigned long long)now);
+            } else {
+              atomicExch(&g_grid_quit_epoch, (unsigned long long)epoch);   // the other clusters follow
+              __threadfence();
+              loc.quit = 1;
+              break;
+            }
+          }
+        }
+        __nanosleep(backoff);
+        if (backoff < 1024) backoff <<= 1;
+      }
+      if (!loc.quit) {
+        loc.src = (const char*)d->src;
+        loc.dst = (char*)d->dst;
+        loc.nbytes = d->nbytes;
+        loc.op = d->op;
+        loc.scale = d->scale;
+      } else {
+        loc.src = nullptr; loc.dst = nullptr; loc.nbytes = 0; loc.op = 0; loc.scale = 1.0f;
+      }
+      for (uint32_t r = 0; r < csize; r++) ptx::st_dsmem(&sd, r, loc);
+    }
+    ptx::cluster_sync();
+    const SmemDesc cur = sd;
+    if (cur.quit) break;
+
+    if (cur.op != OP_FLUSH) {
+      size_t b0, b1;
+      cta_share(cur.op, cur.nbytes, crank, csize, &b0, &b1);
+      const char* s = cur.src + b0;
+      char* dd = cur.dst + dst_offset_for(cur.op, b0);
+      size_t n = b1 - b0;
+      bool tma_ok = kUseTma && cur.op == OP_COPY && n >= 16 && ((((uintptr_t)s | (uintptr_t)dd) & 15) == 0);
+      if (tma_ok) {
+        size_t nb = n & ~(size_t)15;
+        if (tid == 0) tma_copy_range(s, dd, nb, (char*)dyn_smem, bars, phases);
+        if (n > nb) process_range(OP_COPY, s + nb, dd + nb, n - nb, tid, kThreads);
+      } else {
+        process_range(cur.op, s, dd, n, tid, kThreads, cur.scale);
+      }
+    }
+    __syncthreads();
+    ptx::cluster_sync();
+    if (crank == 0 && tid == 0) {
+      Desc* d = &q->d[head % kQueueDepth];
+      uint64_t* flag = d->flag;
+      uint64_t fv = d->flag_val;
+      ptx::fence_acq_rel_sys();
+      ptx::st_release_sys_u64(flag, fv);
+      ptx::st_release_sys_u64((uint64_t*)&q->head, head + 1);
+      atomicMax(&g_grid_last_work, (unsigned long long)ptx::globaltimer());
+      __threadfence();
+      atomicAdd(&g_grid_completed, 1ull);          // after the completion word: "completed" implies "signalled"
+      idle_limit = idle_ns;
+    }
+    head++;
+  }
+  // cluster 0 took the decision: it is also the one that reports it (the relaunch is stream-ordered behind
+  // the clusters that are still on their way out)
+  if (cid == 0 && crank == 0 && tid == 0) ptx::st_release_sys_u32((uint32_t*)&ctl->state, ST_EXITED);
+}
+
 // One-shot kernel used when BNET_PERSISTENT=0: a grid of clusters per chunk list.
 struct OneShotArgs {
   const char* src;
@@ -275,6 +405,14 @@ struct Exec {
   std::vector<Stream> streams;
   std::mutex mu;
   ExecStats stats{};
+  // single-grid mode (BNET_EXEC_GRID=1): all clusters in one kernel on one stream
+  bool grid = false;
+  GridCtl* ctl = nullptr;          // pinned host
+  GridCtl* ctl_dev = nullptr;
+  ClusterQ** queues = nullptr;     // pinned host array of the queues' device aliases
+  ClusterQ** queues_dev = nullptr;
+  cudaStream_t grid_stream = nullptr;
+  uint64_t epoch = 0;
 };
 
 std::mutex g_mu;
@@ -375,16 +513,82 @@ Exec* get_exec(int dev) {
       // (the 64-byte flag is deliberately not freed: cudaFreeHost waits for running kernels)
     }
   }
+  if (good && e->persistent && env_int("EXEC_GRID", 0) != 0) {
+    // single-grid mode: control block + the table of queue addresses, one stream, and the same
+    // "load and run once with stop requested" warm-up as above
+    void *cdp = nullptr, *qdp = nullptr;
+    e->ctl = (GridCtl*)host_alloc_mapped(sizeof(GridCtl), &cdp);
+    e->ctl_dev = (GridCtl*)cdp;
+    e->queues = (ClusterQ**)host_alloc_mapped(sizeof(ClusterQ*) * kMaxChunksPerJob, &qdp);
+    e->queues_dev = (ClusterQ**)qdp;
+    bool ok = e->ctl && e->queues &&
+              cudaStreamCreateWithPriority(&e->grid_stream, cudaStreamNonBlocking, hi) == cudaSuccess;
+    if (ok && e->tma)
+      ok = cudaFuncSetAttribute(bnet_nvl_grid_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                kTmaStages * kTmaStageBytes) == cudaSuccess;
+    if (ok) {
+      for (int i = 0; i < e->nclusters; i++) e->queues[i] = e->streams[i].q_dev;
+      __atomic_store_n(&e->ctl->stop, 1u, __ATOMIC_RELEASE);
+      __atomic_store_n(&e->ctl->state, ST_RUNNING, __ATOMIC_RELEASE);
+      GridCtl* cd = e->ctl_dev;
+      ClusterQ** qd = e->queues_dev;
+      uint64_t ep = ++e->epoch, idle = e->idle_ns, wd = 0;
+      const uint32_t* outp = outstanding_dev();
+      void* gargs[] = {&cd, &qd, &ep, &idle, &wd, &outp};
+      const int nblocks = e->nclusters * e->cluster_size;
+      cudaError_t err = e->tma ? launch_cluster(bnet_nvl_grid_kernel<true>, nblocks, e->cluster_size,
+                                                kTmaStages * kTmaStageBytes, e->grid_stream, gargs)
+                               : launch_cluster(bnet_nvl_grid_kernel<false>, nblocks, e->cluster_size, 0, e->grid_stream, gargs);
+      if (err != cudaSuccess || cudaStreamSynchronize(e->grid_stream) != cudaSuccess) ok = false;
+      __atomic_store_n(&e->ctl->stop, 0u, __ATOMIC_RELEASE);
+      __atomic_store_n(&e->ctl->state, ST_EXITED, __ATOMIC_RELEASE);
+    }
+    if (!ok) {
+      cudaGetLastError();
+      BNET_WARN("nvl executor: single-grid mode unavailable, using one kernel per cluster");
+    }
+    e->grid = ok;
+  }
   if (cur != dev && cur >= 0) cudaSetDevice(cur);
   if (!good) cudaGetLastError();
   e->ok = good;
   BNET_INFO("nvl executor on dev %d: %d cluster(s) x %d CTA x %d thr, %s, engine=%s, min chunk %zu, idle %llu us",
-            dev, e->nclusters, e->cluster_size, kThreads, e->persistent ? "persistent" : "one-shot",
+            dev, e->nclusters, e->cluster_size, kThreads, e->grid ? "persistent single grid" : e->persistent ? "persistent" : "one-shot",
             e->ce ? "copy-engine" : e->tma ? "tma" : "ld/st", e->min_chunk, (unsigned long long)(e->idle_ns / 1000));
   return good ? e : nullptr;
 }
 
+int ensure_grid_running(Exec* e, bool arm) {
+  for (int spin = 0;; spin++) {
+    uint32_t st = __atomic_load_n(&e->ctl->state, __ATOMIC_ACQUIRE);
+    if (st == ST_RUNNING) return 0;
+    if (st == ST_EXITING) {   // cluster 0 is deciding; it settles on RUNNING or EXITED
+      if (spin > 20000000) return -1;
+      continue;
+    }
+    __atomic_store_n(&e->ctl->state, ST_RUNNING, __ATOMIC_RELEASE);
+    GridCtl* cd = e->ctl_dev;
+    ClusterQ** qd = e->queues_dev;
+    uint64_t ep = ++e->epoch, idle = e->idle_ns, wd = arm ? e->arm_ns : 0;
+    const uint32_t* outp = outstanding_dev();
+    void* args[] = {&cd, &qd, &ep, &idle, &wd, &outp};
+    const int nblocks = e->nclusters * e->cluster_size;
+    cudaError_t err = e->tma ? launch_cluster(bnet_nvl_grid_kernel<true>, nblocks, e->cluster_size,
+                                              kTmaStages * kTmaStageBytes, e->grid_stream, args)
+                             : launch_cluster(bnet_nvl_grid_kernel<false>, nblocks, e->cluster_size, 0, e->grid_stream, args);
+    if (err != cudaSuccess) {
+      cudaGetLastError();
+      __atomic_store_n(&e->ctl->state, ST_EXITED, __ATOMIC_RELEASE);
+      BNET_WARN("nvl executor: grid launch failed: %s", cudaGetErrorString(err));
+      return -1;
+    }
+    e->stats.launches++;
+    return 0;
+  }
+}
+
 int ensure_running(Exec* e, Stream& s, bool arm = false) {
+  if (e->grid) return ensure_grid_running(e, arm);
   for (int spin = 0;; spin++) {
     uint32_t st = __atomic_load_n(&s.q->state, __ATOMIC_ACQUIRE);
     if (st == ST_RUNNING) return 0;
@@ -460,6 +664,7 @@ int submit(Exec* e, uint32_t op, const void* src, void* dst, size_t nbytes, uint
       d.scale = scale;
       __atomic_store_n(&d.seq, t + 1, __ATOMIC_RELEASE);
       s.q->tail = t + 1;
+      if (e->grid) __atomic_store_n(&e->ctl->submitted, e->ctl->submitted + 1, __ATOMIC_RELEASE);
       __atomic_thread_fence(__ATOMIC_SEQ_CST);   // publish, then look at the kernel's state (Dekker)
       rc = ensure_running(e, s);
       e->stats.persistent++;
@@ -544,8 +749,12 @@ int exec_prepare(int dev) {
   cudaGetDevice(&cur);
   if (cur != e->dev) cudaSetDevice(e->dev);
   int rc = 0;
-  for (Stream& s : e->streams)
-    if (ensure_running(e, s, /*arm=*/true) != 0) rc = -1;
+  if (e->grid) {
+    rc = ensure_grid_running(e, /*arm=*/true);
+  } else {
+    for (Stream& s : e->streams)
+      if (ensure_running(e, s, /*arm=*/true) != 0) rc = -1;
+  }
   if (cur != e->dev && cur >= 0) cudaSetDevice(cur);
   return rc;
 }
@@ -569,6 +778,7 @@ void exec_shutdown() {
     if (!e || !e->ok) continue;
     for (Stream& s : e->streams)
       if (s.q) __atomic_store_n(&s.q->stop, 1u, __ATOMIC_RELEASE);
+    if (e->ctl) __atomic_store_n(&e->ctl->stop, 1u, __ATOMIC_RELEASE);
   }
 }
 

@@ -158,3 +158,10 @@ def test_plugin_nvl_transport_copy_engine_mode():
 @pytest.mark.multigpu
 def test_collectives_on_ordinary_tensors_2gpu():
     _run_worker("collectives_any", 2)
+
+
+@pytest.mark.parametrize("env", [{"BNET_EXEC_GRID": "1"}, {"BNET_EXEC_GRID": "1", "BNET_COPY_ENGINE": "tma"}], ids=["grid", "grid-tma"])
+def test_executor_single_grid_mode(env):
+    """BNET_EXEC_GRID=1: all cluster queues served by ONE resident grid on one stream (one launch per wake-up)."""
+    _run_worker("executor", 1, extra_env=env)
+    _run_worker("executor_idle", 1, extra_env=dict(env, BNET_KERNEL_IDLE_US="100"))
