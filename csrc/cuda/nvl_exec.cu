@@ -269,8 +269,9 @@ bnet_nvl_grid_kernel(GridCtl* ctl, ClusterQ* const* queues, uint64_t epoch, uint
           const uint64_t now = ptx::globaltimer();
           uint64_t lw = *(volatile unsigned long long*)&g_grid_last_work;
           if (lw < t_start) lw = t_start;            // completions of earlier launches do not count
-          if (now - lw > idle_limit &&
-              (ptx::ld_relaxed_sys_u32(outstanding) == 0 || now - lw > 10000000000ull)) {
+          // (globaltimer is read on different SMs: a completion stamped by another cluster may be a few ns "ahead")
+          const uint64_t idle = now > lw ? now - lw : 0;
+          if (idle > idle_limit && (ptx::ld_relaxed_sys_u32(outstanding) == 0 || idle > 10000000000ull)) {
             ptx::st_release_sys_u32((uint32_t*)&ctl->state, ST_EXITING);
             ptx::fence_sc_sys();
             const uint64_t sub = ptx::ld_acquire_sys_u64((const uint64_t*)&ctl->submitted);

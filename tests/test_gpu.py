@@ -141,7 +141,7 @@ def test_nccl_loads_plugin_and_allreduces():
 def test_executor_copy_engine_mode():
     """BNET_COPY_ENGINE=ce: plain copies ride the DMA engines + a stream-ordered completion word; the fused
     reduce/cast ops still use the cluster kernels."""
-    _run_worker("executor", 1, extra_env={"BNET_COPY_ENGINE": "ce"})
+    _run_worker("executor", 1, extra_env={"BNET_COPY_ENGINE": "ce"}, timeout=120)
 
 
 @pytest.mark.multigpu
@@ -163,5 +163,5 @@ def test_collectives_on_ordinary_tensors_2gpu():
 @pytest.mark.parametrize("env", [{"BNET_EXEC_GRID": "1"}, {"BNET_EXEC_GRID": "1", "BNET_COPY_ENGINE": "tma"}], ids=["grid", "grid-tma"])
 def test_executor_single_grid_mode(env):
     """BNET_EXEC_GRID=1: all cluster queues served by ONE resident grid on one stream (one launch per wake-up)."""
-    _run_worker("executor", 1, extra_env=env)
-    _run_worker("executor_idle", 1, extra_env=dict(env, BNET_KERNEL_IDLE_US="100"))
+    _run_worker("executor", 1, extra_env=env, timeout=120)
+    _run_worker("executor_idle", 1, extra_env=dict(env, BNET_KERNEL_IDLE_US="100"), timeout=60)
