@@ -256,20 +256,42 @@ def job_ddp_engine():
     assert e3._graph is not None and e3.kernel_launches - before >= 25 * len(e3.buckets)
     assert isinstance(e3.train_step_from_host(xh, yh), float)
     print(f"rank {RANK}: graph engine loss {lg[0]:.3f} -> {lg[-1]:.3f}", flush=True)
-    # loader-facing loop with the next batch's H2D copy prefetched: one loss per batch, training continues
-    lp = list(e3.train_from_host((xh, yh) for _ in range(6)))
-    assert len(lp) == 6 and all(isinstance(v, float) and v == v for v in lp) and max(lp) < lg[0] + 1.0, lp
-    assert list(e3.train_from_host(iter(()))) == []
-    # checkpoint / resume: weights through the module, optimizer shards through the engine
-    weights = {k: v.clone() for k, v in m3.state_dict().items()}
-    opt = e3.optimizer_state_dict()
-    after = float(e3.train_step(x, y))
-    m3.load_state_dict(weights)
-    e3.load_optimizer_state_dict(opt)
-    torch.cuda.synchronize()
-    again = float(e3.train_step(x, y))
-    assert abs(again - after) < 5e-2, (after, again)    # same state, same batch -> same loss (bf16 tolerance)
     assert eng.comm.status() == 0 and e2.comm.status() == 0 and e3.comm.status() == 0
+    teardown()
+
+
+def job_ddp_api():
+    """Loader-facing loop (prefetched H2D copies) and checkpoint / resume of the engine, eager and graph mode."""
+    from bagua_net_b200.models import build_model
+    from bagua_net_b200.parallel import BnetDDP
+
+    setup()
+    kw = dict(width_div=8, fc_dim=128, image_size=32, num_classes=10, dropout=0.0)
+    for graph in (False, True):
+        torch.manual_seed(1)
+        m3 = build_model("vgg16", fused=True, **kw).cuda().to(torch.bfloat16).to(memory_format=torch.channels_last)
+        e3 = BnetDDP(m3, lr=0.02, momentum=0.9, weight_decay=0.0, bucket_mb=0.25)
+        e3.enable_cuda_graph(graph)
+        torch.manual_seed(5 + RANK)
+        x = torch.randn(8, 3, 32, 32, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        y = torch.randint(0, 10, (8,), device="cuda")
+        xh, yh = x.cpu().pin_memory(), y.cpu().pin_memory()
+        lg = [float(e3.train_step(x, y)) for _ in range(10)]
+        # loader-facing loop with the next batch's H2D copy prefetched: one loss per batch, training continues
+        lp = list(e3.train_from_host((xh, yh) for _ in range(6)))
+        assert len(lp) == 6 and all(isinstance(v, float) and v == v for v in lp) and max(lp) < lg[0] + 1.0, lp
+        assert list(e3.train_from_host(iter(()))) == []
+        # checkpoint / resume: weights through the module, optimizer shards through the engine
+        weights = {k: v.clone() for k, v in m3.state_dict().items()}
+        opt = e3.optimizer_state_dict()
+        after = float(e3.train_step(x, y))
+        m3.load_state_dict(weights)
+        e3.load_optimizer_state_dict(opt)
+        torch.cuda.synchronize()
+        again = float(e3.train_step(x, y))
+        assert abs(again - after) < 5e-2, (after, again)    # same state, same batch -> same loss (bf16 tolerance)
+        assert e3.comm.status() == 0
+        print(f"rank {RANK}: ddp api ok (graph={graph}) losses {lp[:2]}... resume {after:.4f} vs {again:.4f}", flush=True)
     teardown()
 
 

@@ -165,3 +165,12 @@ def test_executor_single_grid_mode(env):
     """BNET_EXEC_GRID=1: all cluster queues served by ONE resident grid on one stream (one launch per wake-up)."""
     _run_worker("executor", 1, extra_env=env, timeout=120)
     _run_worker("executor_idle", 1, extra_env=dict(env, BNET_KERNEL_IDLE_US="100"), timeout=60)
+
+
+def test_ddp_loader_loop_and_checkpoint():
+    _run_worker("ddp_api", 1, timeout=240)
+
+
+@pytest.mark.multigpu
+def test_ddp_loader_loop_and_checkpoint_2gpu():
+    _run_worker("ddp_api", 2, timeout=240)
