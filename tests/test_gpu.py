@@ -137,7 +137,22 @@ def test_nccl_loads_plugin_and_allreduces():
     assert "Using network BNet" in log or "NET/Plugin: Loaded net plugin BNet" in log, log[-4000:]
 
 
-# ------------------------------------------------------------------ newest paths last (a failure here must not hide the rest under -x)
+# ------------------------------------------------------------------ newest paths last (a failure here must not hide the rest under -x);
+# ordered from plain Python compositions of validated kernels to new device-side modes
+def test_ddp_loader_loop_and_checkpoint():
+    _run_worker("ddp_api", 1, timeout=240)
+
+
+@pytest.mark.multigpu
+def test_ddp_loader_loop_and_checkpoint_2gpu():
+    _run_worker("ddp_api", 2, timeout=240)
+
+
+@pytest.mark.multigpu
+def test_collectives_on_ordinary_tensors_2gpu():
+    _run_worker("collectives_any", 2, timeout=240)
+
+
 def test_executor_copy_engine_mode():
     """BNET_COPY_ENGINE=ce: plain copies ride the DMA engines + a stream-ordered completion word; the fused
     reduce/cast ops still use the cluster kernels."""
@@ -155,22 +170,8 @@ def test_plugin_nvl_transport_copy_engine_mode():
         assert res["transport"] == "nvl"
 
 
-@pytest.mark.multigpu
-def test_collectives_on_ordinary_tensors_2gpu():
-    _run_worker("collectives_any", 2)
-
-
 @pytest.mark.parametrize("env", [{"BNET_EXEC_GRID": "1"}, {"BNET_EXEC_GRID": "1", "BNET_COPY_ENGINE": "tma"}], ids=["grid", "grid-tma"])
 def test_executor_single_grid_mode(env):
     """BNET_EXEC_GRID=1: all cluster queues served by ONE resident grid on one stream (one launch per wake-up)."""
     _run_worker("executor", 1, extra_env=env, timeout=120)
     _run_worker("executor_idle", 1, extra_env=dict(env, BNET_KERNEL_IDLE_US="100"), timeout=60)
-
-
-def test_ddp_loader_loop_and_checkpoint():
-    _run_worker("ddp_api", 1, timeout=240)
-
-
-@pytest.mark.multigpu
-def test_ddp_loader_loop_and_checkpoint_2gpu():
-    _run_worker("ddp_api", 2, timeout=240)
