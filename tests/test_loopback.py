@@ -3,6 +3,8 @@
 exported ABI version, both TCP backends, the shared-memory (NVL) transport, 8 requests
 in flight, sizes around the chunking boundaries, receive buffers larger than the message.
 The reference has no such test (BASIC backend tests: none)."""
+import os
+
 import pytest
 
 from conftest import run_pair
@@ -151,3 +153,14 @@ def test_ring_allreduce_over_the_plugin(world, env, args, transport):
         assert rc == 0 and res and res["ok"], err[-2000:]
         assert res["transports"] == [transport]
         assert res["allreduces"] > 0
+
+
+def test_listener_survives_garbage_connections():
+    """Port scanners / half-open connections / random bytes on the listening socket must neither produce a comm
+    nor block the next genuine connect (the reference would read them as stream ids: nthread_…:440-447)."""
+    import subprocess
+    import sys
+
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts", "garbage_connections.py")
+    r = subprocess.run([sys.executable, script], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "ok after garbage" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
