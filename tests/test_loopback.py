@@ -164,3 +164,13 @@ def test_listener_survives_garbage_connections():
     script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts", "garbage_connections.py")
     r = subprocess.run([sys.executable, script], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "ok after garbage" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+@pytest.mark.skipif(not os.path.exists("/proc/net/if_inet6") or " lo" not in open("/proc/net/if_inet6").read(),
+                    reason="no IPv6 loopback address")
+@pytest.mark.parametrize("abi", [4, 8])
+def test_ipv6_listener_handle_is_not_truncated(abi):
+    # the reference copies a 16-byte `struct sockaddr` into the handle, which cuts a sockaddr_in6 (lib.rs:157-158);
+    # ours keeps all 28 bytes even in the 64-byte v4 handle
+    _check(run_pair(["--abi", str(abi), "--sizes", "0,8,1048577", "--inflight", "4", "--rounds", "1"],
+                    env={"BNET_NVL": "0", "NCCL_SOCKET_IFNAME": "lo", "NCCL_SOCKET_FAMILY": "10"}), "tcp-threads")
