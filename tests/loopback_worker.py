@@ -94,6 +94,7 @@ def main() -> int:
     ap.add_argument("--rounds", type=int, default=2)
     ap.add_argument("--mem", default="host", choices=["host", "fakecuda", "cuda"])
     ap.add_argument("--send-mem", default=None, choices=["host", "fakecuda", "cuda"], help="sender's memory kind (default: --mem)")
+    ap.add_argument("--mix", action="store_true", help="sender alternates pinned-host and device buffers message by message")
     ap.add_argument("--die-after", type=int, default=-1, help="sender exits abruptly after N messages")
     ap.add_argument("--expect-error", action="store_true")
     ap.add_argument("--bw", action="store_true", help="print a bandwidth line for the largest size")
@@ -138,7 +139,10 @@ def main() -> int:
                 bufs, reqs, mhs = [], [], []
                 extra = 64 if a.role == 0 else 0       # recv buffer larger than the message
                 for j in range(a.inflight):
-                    b = alloc(size + extra)
+                    if a.mix and a.role == 1:        # LL-style (host) and Simple-style (device) messages on ONE connection
+                        b = HostBuf(size + extra) if (j + rnd) % 2 else FakeCudaBuf(p.lib, size + extra)
+                    else:
+                        b = alloc(size + extra)
                     mh = p.reg_mr(comm, b.addr, size + extra, b.type)
                     if a.role == 1:
                         b.view()[: max(size, 1)] = pattern(size, 1000 * rnd + 7 * j + size % 97)

@@ -112,6 +112,14 @@ def test_nvl_pinned_host_source_goes_direct_when_enabled():
     assert off[1][1]["kernel_chunks"] == 0, off[1][1]
 
 
+@pytest.mark.parametrize("direct", ["0", "1"])
+def test_nvl_ring_and_direct_messages_interleaved_on_one_connection(direct):
+    # NCCL alternates protocols on a connection over time (LL: pinned host source, Simple: device source); ring-path
+    # and direct-path messages must stay FIFO with 8 requests in flight
+    _check(run_pair(["--mem", "fakecuda", "--mix", "--sizes", "0,8,4096,70000,1048577", "--inflight", "8", "--rounds", "3"],
+                    env={"BNET_NVL": "1", "BNET_FAKE_CUDA": "1", "BNET_HOST_SRC_DIRECT": direct}), "nvl")
+
+
 def test_cuda_pointers_over_tcp_are_staged():
     _check(run_pair(["--mem", "fakecuda", "--sizes", "1,4096,1048577,3145729", "--inflight", "4", "--rounds", "1"],
                     env={"BNET_NVL": "0", "BNET_FAKE_CUDA": "1"}), "tcp-threads")
