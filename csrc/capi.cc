@@ -85,7 +85,8 @@ BNET_API int bnet_config_json(char* out, int cap) {
   std::ostringstream o;
   o << "{\"implement\":\"" << c.implement << "\",\"nstreams\":" << c.nstreams << ",\"min_chunksize\":" << c.min_chunksize
     << ",\"async_workers\":" << c.async_workers << ",\"rank\":" << c.rank << ",\"nvl\":" << c.nvl << ",\"gdr\":" << c.gdr
-    << ",\"wire_compat\":" << c.wire_compat << ",\"timeout_ms\":" << c.timeout_ms << "}";
+    << ",\"wire_compat\":" << c.wire_compat << ",\"timeout_ms\":" << c.timeout_ms
+    << ",\"shm_ring_bytes\":" << c.shm_ring_bytes << "}";
   return copy_out(o.str(), out, cap);
 }
 

@@ -104,3 +104,15 @@ def test_device_kernel_bodies_on_an_emulated_grid():
         subprocess.run(["make", "-s", f"build/tests/{name}"], cwd=root, check=True, capture_output=True)
         r = subprocess.run([os.path.join(root, "build", "tests", name)], capture_output=True, text=True)
         assert r.returncode == 0 and "passed" in r.stdout, r.stdout[-2000:]
+
+
+def test_doctor_reports_a_usable_setup_on_cpu():
+    import io
+
+    from bagua_net_b200 import doctor
+
+    buf = io.StringIO()
+    rc = doctor.run(out=buf)
+    text = buf.getvalue()
+    assert rc == 0, text
+    assert "ncclNet tables exported: v3 v4 v5 v6 v7 v8" in text and "NCCL_NET_PLUGIN=bnet" in text
