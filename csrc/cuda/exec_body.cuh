@@ -36,7 +36,12 @@ enum ExecOp : uint32_t {
   OP_CAST_BF16_TO_E4M3 = 7,  // dst(fp8 e4m3) = sat(src(bf16) * scale)   (gradient compression, K5)
   OP_ACC_E4M3_TO_F32 = 8,    // dst(f32) += src(fp8 e4m3) * scale        (decompress + accumulate)
   OP_CAST_F32_TO_E4M3 = 9,   // dst(fp8 e4m3) = sat(src(f32) * scale)
+  OP_CAST_BF16_TO_E5M2 = 10, // the same three with the wide-range e5m2 format
+  OP_ACC_E5M2_TO_F32 = 11,
+  OP_CAST_F32_TO_E5M2 = 12,
 };
+
+BNET_XD bool op_is_e5m2(uint32_t op) { return op >= OP_CAST_BF16_TO_E5M2 && op <= OP_CAST_F32_TO_E5M2; }
 
 namespace xb {   // access primitives: PTX on the device, plain C++ in the emulation
 
@@ -155,17 +160,17 @@ BNET_XD void unpack_bf16x8(const int4& v, float4* lo, float4* hi) {
 
 // source bytes per indivisible work unit (keeps CTA / chunk cuts vector-aligned on BOTH sides)
 BNET_XD size_t src_unit_for(uint32_t op) {
-  if (op == OP_CAST_F32_TO_BF16 || op == OP_CAST_BF16_TO_E4M3 || op == OP_RED_ADD_F32) return 32;
-  if (op == OP_CAST_F32_TO_E4M3) return 64;
+  if (op == OP_CAST_F32_TO_BF16 || op == OP_CAST_BF16_TO_E4M3 || op == OP_CAST_BF16_TO_E5M2 || op == OP_RED_ADD_F32) return 32;
+  if (op == OP_CAST_F32_TO_E4M3 || op == OP_CAST_F32_TO_E5M2) return 64;
   return 16;
 }
 
 // destination offset that corresponds to a source offset
 BNET_XD size_t dst_offset_for(uint32_t op, size_t src_off) {
   if (op == OP_CAST_BF16_TO_F32 || op == OP_ACC_BF16_TO_F32) return src_off * 2;
-  if (op == OP_CAST_F32_TO_BF16 || op == OP_CAST_BF16_TO_E4M3) return src_off / 2;
-  if (op == OP_ACC_E4M3_TO_F32) return src_off * 4;
-  if (op == OP_CAST_F32_TO_E4M3) return src_off / 4;
+  if (op == OP_CAST_F32_TO_BF16 || op == OP_CAST_BF16_TO_E4M3 || op == OP_CAST_BF16_TO_E5M2) return src_off / 2;
+  if (op == OP_ACC_E4M3_TO_F32 || op == OP_ACC_E5M2_TO_F32) return src_off * 4;
+  if (op == OP_CAST_F32_TO_E4M3 || op == OP_CAST_F32_TO_E5M2) return src_off / 4;
   return src_off;
 }
 
@@ -297,21 +302,22 @@ BNET_XD_FN void process_range(uint32_t op, const char* src, char* dst, size_t n,
     }
     return;
   }
-  if (op == OP_CAST_BF16_TO_E4M3 || op == OP_CAST_F32_TO_E4M3) {
-    // 8 source elements -> 8 fp8 bytes per step (one 8-byte store), saturating e4m3
-    const bool from_bf16 = op == OP_CAST_BF16_TO_E4M3;
+  if (op == OP_CAST_BF16_TO_E4M3 || op == OP_CAST_F32_TO_E4M3 || op == OP_CAST_BF16_TO_E5M2 || op == OP_CAST_F32_TO_E5M2) {
+    // 8 source elements -> 8 fp8 bytes per step (one 8-byte store), saturating e4m3 / e5m2
+    const bool from_bf16 = op == OP_CAST_BF16_TO_E4M3 || op == OP_CAST_BF16_TO_E5M2;
+    const __nv_fp8_interpretation_t fmt = op_is_e5m2(op) ? __NV_E5M2 : __NV_E4M3;
     size_t ne = from_bf16 ? n >> 1 : n >> 2;
     unsigned char* d = (unsigned char*)dst;
     auto q1 = [&](float f) -> unsigned char {
-      return (unsigned char)__nv_cvt_float_to_fp8(f * scale, __NV_SATFINITE, __NV_E4M3);
+      return (unsigned char)__nv_cvt_float_to_fp8(f * scale, __NV_SATFINITE, fmt);
     };
     auto pack8 = [&](size_t i, const xb::F8& r) {
       const float f[8] = {r.lo.x, r.lo.y, r.lo.z, r.lo.w, r.hi.x, r.hi.y, r.hi.z, r.hi.w};
       uint32_t w[2];
 #pragma unroll
       for (int k = 0; k < 2; k++) {
-        uint32_t a = __nv_cvt_float2_to_fp8x2(make_float2(f[4 * k] * scale, f[4 * k + 1] * scale), __NV_SATFINITE, __NV_E4M3);
-        uint32_t b = __nv_cvt_float2_to_fp8x2(make_float2(f[4 * k + 2] * scale, f[4 * k + 3] * scale), __NV_SATFINITE, __NV_E4M3);
+        uint32_t a = __nv_cvt_float2_to_fp8x2(make_float2(f[4 * k] * scale, f[4 * k + 1] * scale), __NV_SATFINITE, fmt);
+        uint32_t b = __nv_cvt_float2_to_fp8x2(make_float2(f[4 * k + 2] * scale, f[4 * k + 3] * scale), __NV_SATFINITE, fmt);
         w[k] = (a & 0xffffu) | (b << 16);
       }
       xb::st8(d + 8 * i, make_uint2(w[0], w[1]));
@@ -343,12 +349,13 @@ BNET_XD_FN void process_range(uint32_t op, const char* src, char* dst, size_t n,
     }
     return;
   }
-  if (op == OP_ACC_E4M3_TO_F32) {
+  if (op == OP_ACC_E4M3_TO_F32 || op == OP_ACC_E5M2_TO_F32) {
+    const __nv_fp8_interpretation_t fmt = op_is_e5m2(op) ? __NV_E5M2 : __NV_E4M3;
     size_t ne = n;
     const unsigned char* s = (const unsigned char*)src;
     float* d = (float*)dst;
     auto dq = [&](unsigned char b) -> float {
-      __half_raw h = __nv_cvt_fp8_to_halfraw(b, __NV_E4M3);
+      __half_raw h = __nv_cvt_fp8_to_halfraw(b, fmt);
       __half hh;
       memcpy(&hh, &h, sizeof(hh));
       return __half2float(hh) * scale;

@@ -95,8 +95,8 @@ static float bf(const unsigned char* p, size_t i) { __nv_bfloat16 v; memcpy(&v, 
 static float f32(const unsigned char* p, size_t i) { float v; memcpy(&v, p + 4 * i, 4); return v; }
 static void put_bf(unsigned char* p, size_t i, float f) { __nv_bfloat16 v = __float2bfloat16(f); memcpy(p + 2 * i, &v, 2); }
 static void put_f32(unsigned char* p, size_t i, float f) { memcpy(p + 4 * i, &f, 4); }
-static float e4m3(unsigned char b) {
-  __half_raw h = __nv_cvt_fp8_to_halfraw(b, __NV_E4M3);
+static float fp8(unsigned char b, __nv_fp8_interpretation_t fmt) {
+  __half_raw h = __nv_cvt_fp8_to_halfraw(b, fmt);
   __half hh;
   memcpy(&hh, &h, sizeof(hh));
   return __half2float(hh);
@@ -135,27 +135,42 @@ int main() {
                      for (size_t i = 0; i < n; i++) if (bf(d, i) != __bfloat162float(__float2bfloat16(f32(s, i)))) return i;
                      return (size_t)-1;
                    });
-  const float scale = 16.f;
-  test_elementwise("cast_bf16_to_e4m3", OP_CAST_BF16_TO_E4M3, 2, 1, scale, src_bf, dst_bytes,
-                   [&](const unsigned char* s, const unsigned char*, const unsigned char* d, size_t n) {
-                     for (size_t i = 0; i < n; i++)
-                       if (d[i] != (unsigned char)__nv_cvt_float_to_fp8(bf(s, i) * scale, __NV_SATFINITE, __NV_E4M3)) return i;
-                     return (size_t)-1;
-                   });
-  test_elementwise("cast_f32_to_e4m3", OP_CAST_F32_TO_E4M3, 4, 1, scale, src_f32, dst_bytes,
-                   [&](const unsigned char* s, const unsigned char*, const unsigned char* d, size_t n) {
-                     for (size_t i = 0; i < n; i++)
-                       if (d[i] != (unsigned char)__nv_cvt_float_to_fp8(f32(s, i) * scale, __NV_SATFINITE, __NV_E4M3)) return i;
-                     return (size_t)-1;
-                   });
-  const float inv = 1.f / 16.f;
-  test_elementwise("acc_e4m3_to_f32", OP_ACC_E4M3_TO_F32, 1, 4, inv,
-                   [](unsigned char* p, size_t n) { for (size_t i = 0; i < n; i++) { unsigned char b = (unsigned char)urand(); if ((b & 0x7f) == 0x7f) b &= 0xfe; p[i] = b; } },
-                   dst_f32,
-                   [&](const unsigned char* s, const unsigned char* d0, const unsigned char* d, size_t n) {
-                     for (size_t i = 0; i < n; i++) if (f32(d, i) != f32(d0, i) + e4m3(s[i]) * inv) return i;
-                     return (size_t)-1;
-                   });
+  const float scale = 16.f, inv = 1.f / 16.f;
+  struct { const char* name; __nv_fp8_interpretation_t fmt; uint32_t from_bf16, from_f32, acc; } fmts[] = {
+      {"e4m3", __NV_E4M3, OP_CAST_BF16_TO_E4M3, OP_CAST_F32_TO_E4M3, OP_ACC_E4M3_TO_F32},
+      {"e5m2", __NV_E5M2, OP_CAST_BF16_TO_E5M2, OP_CAST_F32_TO_E5M2, OP_ACC_E5M2_TO_F32}};
+  for (auto& F : fmts) {
+    const __nv_fp8_interpretation_t fmt = F.fmt;
+    char nm[64];
+    snprintf(nm, sizeof(nm), "cast_bf16_to_%s", F.name);
+    test_elementwise(nm, F.from_bf16, 2, 1, scale, src_bf, dst_bytes,
+                     [&](const unsigned char* s, const unsigned char*, const unsigned char* d, size_t n) {
+                       for (size_t i = 0; i < n; i++)
+                         if (d[i] != (unsigned char)__nv_cvt_float_to_fp8(bf(s, i) * scale, __NV_SATFINITE, fmt)) return i;
+                       return (size_t)-1;
+                     });
+    snprintf(nm, sizeof(nm), "cast_f32_to_%s", F.name);
+    test_elementwise(nm, F.from_f32, 4, 1, scale, src_f32, dst_bytes,
+                     [&](const unsigned char* s, const unsigned char*, const unsigned char* d, size_t n) {
+                       for (size_t i = 0; i < n; i++)
+                         if (d[i] != (unsigned char)__nv_cvt_float_to_fp8(f32(s, i) * scale, __NV_SATFINITE, fmt)) return i;
+                       return (size_t)-1;
+                     });
+    snprintf(nm, sizeof(nm), "acc_%s_to_f32", F.name);
+    test_elementwise(nm, F.acc, 1, 4, inv,
+                     [&](unsigned char* p, size_t n) {
+                       for (size_t i = 0; i < n; i++) {          // any finite fp8 code (skip the NaN / Inf encodings)
+                         unsigned char b = (unsigned char)urand();
+                         float v = fp8(b, fmt);
+                         p[i] = (v == v && fabsf(v) < 1e30f) ? b : (unsigned char)0x3c;
+                       }
+                     },
+                     dst_f32,
+                     [&](const unsigned char* s, const unsigned char* d0, const unsigned char* d, size_t n) {
+                       for (size_t i = 0; i < n; i++) if (f32(d, i) != f32(d0, i) + fp8(s[i], fmt) * inv) return i;
+                       return (size_t)-1;
+                     });
+  }
   printf("%s (%d failure%s)\n", g_fail ? "FAILED" : "executor body emulation tests passed", g_fail, g_fail == 1 ? "" : "s");
   return g_fail ? 1 : 0;
 }

@@ -114,6 +114,33 @@ def job_executor():
           f"local copy {big.numel() / dt / 1e9:.1f} GB/s (x2 traffic) stats={native.exec_stats()}", flush=True)
 
 
+def job_executor_e5m2():
+    """fp8 e5m2 variants of the compression ops (wide range, 2 mantissa bits) vs torch.float8_e5m2."""
+    from bagua_net_b200.ops import P2PExecutor
+
+    torch.cuda.set_device(0)
+    ex = P2PExecutor(0)
+    for n in [64, 4096, (1 << 20) + 64]:
+        h = (torch.randn(n, device="cuda") * 3).to(torch.bfloat16)
+        scale = 16.0
+        q = torch.empty(n, device="cuda", dtype=torch.uint8)
+        ex.run("cast_bf16_to_e5m2", h, q, scale=scale)
+        torch.cuda.synchronize()
+        ref_q = (h.float() * scale).clamp(-57344, 57344).to(torch.float8_e5m2)
+        assert torch.equal(q.view(torch.float8_e5m2).float(), ref_q.float()), "cast_bf16_to_e5m2"
+        f32 = torch.randn(n, device="cuda")
+        q2 = torch.empty(n, device="cuda", dtype=torch.uint8)
+        ex.run("cast_f32_to_e5m2", f32, q2, scale=scale)
+        torch.cuda.synchronize()
+        assert torch.equal(q2.view(torch.float8_e5m2).float(), (f32 * scale).clamp(-57344, 57344).to(torch.float8_e5m2).float())
+        acc = torch.randn(n, device="cuda")
+        ref = acc + ref_q.float() / scale
+        ex.run("acc_e5m2_to_f32", q, acc, scale=1.0 / scale)
+        torch.cuda.synchronize()
+        assert torch.allclose(acc, ref, rtol=1e-6, atol=1e-6), "acc_e5m2_to_f32"
+    print("e5m2 ok", flush=True)
+
+
 def job_executor_idle():
     from bagua_net_b200.ops import P2PExecutor
     from bagua_net_b200.utils import native

@@ -153,6 +153,10 @@ def test_collectives_on_ordinary_tensors_2gpu():
     _run_worker("collectives_any", 2, timeout=240)
 
 
+def test_executor_fp8_e5m2_ops():
+    _run_worker("executor_e5m2", 1, timeout=120)
+
+
 def test_executor_copy_engine_mode():
     """BNET_COPY_ENGINE=ce: plain copies ride the DMA engines + a stream-ordered completion word; the fused
     reduce/cast ops still use the cluster kernels."""
