@@ -134,6 +134,10 @@ def run(out=sys.stdout) -> int:
     print("export " + " ".join(f"{k}={v}" for k, v in env.items()), file=out)
     print("# inside ONE box NCCL only uses a net plugin when its own transports are off (benchmarking the plugin):", file=out)
     print("export NCCL_P2P_DISABLE=1 NCCL_SHM_DISABLE=1 NCCL_NVLS_ENABLE=0", file=out)
+    from bagua_net_b200.utils.env import TUNED
+
+    print("# more bytes in flight per channel for large messages (NCCL's proxy pipeline is the limit, not the link):", file=out)
+    print("export " + " ".join(f"{k}={v}" for k, v in TUNED.items()), file=out)
     print("# expect in the log (NCCL_DEBUG=INFO): 'NET/Plugin: Loaded net plugin BNet (v8)' and 'Using network BNet'", file=out)
     return 1 if problems else 0
 

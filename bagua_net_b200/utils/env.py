@@ -13,8 +13,14 @@ import os
 from .. import LIB_DIR
 
 
+# NCCL drives a net plugin through a proxy pipeline of NCCL_BUFFSIZE/8-byte slices per channel; with the default
+# 4 MiB buffers and 2-4 channels that pipeline, not the link, bounds the throughput (measured on 2 x B200:
+# 82 GB/s default -> 211 GB/s with these, profiles/README.md section 4)
+TUNED = {"NCCL_BUFFSIZE": str(32 << 20), "NCCL_MIN_NCHANNELS": "16", "NCCL_PROTO": "Simple"}
+
+
 def nccl_plugin_env(plugin: str = "bnet", force_net: bool = False, gdr: bool = True, debug: bool = False,
-                    extra: dict | None = None) -> dict:
+                    extra: dict | None = None, tuned: bool = False) -> dict:
     """Environment variables (as a dict) that make NCCL >= 2.2x dlopen our plugin.
 
     plugin: "bnet" -> libnccl-net-bnet.so (tables v3..v8); "bnetx" adds the v9/v10 tables.
@@ -40,6 +46,8 @@ def nccl_plugin_env(plugin: str = "bnet", force_net: bool = False, gdr: bool = T
         env["BNET_GDR"] = "0"
     if debug:
         env.update({"NCCL_DEBUG": "INFO", "NCCL_DEBUG_SUBSYS": "INIT,NET,ENV"})
+    if tuned:
+        env.update({k: v for k, v in TUNED.items() if k not in os.environ})
     if extra:
         env.update(extra)
     return env
@@ -52,5 +60,6 @@ def apply(env: dict) -> None:
 if __name__ == "__main__":   # `env $(python -m bagua_net_b200.utils.env) <cmd>` loads the plugin into NCCL
     import sys
 
-    kw = {"force_net": "--no-force" not in sys.argv, "debug": "--debug" in sys.argv, "gdr": "--no-gdr" not in sys.argv}
+    kw = {"force_net": "--no-force" not in sys.argv, "debug": "--debug" in sys.argv, "gdr": "--no-gdr" not in sys.argv,
+          "tuned": "--tuned" in sys.argv}
     print(" ".join(f"{k}={v}" for k, v in nccl_plugin_env(**kw).items()))
