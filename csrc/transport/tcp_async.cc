@@ -9,8 +9,12 @@
 //   * message-serial: message k+1 starts only when message k finished on all
 //     streams; zero-length messages complete right after the header
 //   * worker count from BAGUA_NET_TOKIO_WORKER_THREADS, default MIN_CHUNKSIZE 65535
-// Re-designed: no async runtime — edge-triggered epoll state machines, one per
-// comm, pinned to one of the pool's loops; no per-message task spawning.
+// Re-designed: no async runtime and no per-message task spawning — edge-triggered epoll
+// state machines.  Every comm has a HOME loop that owns all of its sockets and the message
+// state machine.  The chunks of a LARGE message are lent to other loops of the pool for the
+// duration of the chunk, so that several threads copy at once (the reference joins its
+// per-stream futures inside one task, i.e. on one thread at a time); small messages never
+// leave the home loop.
 #include <errno.h>
 #include <string.h>
 #include <sys/epoll.h>
@@ -18,8 +22,10 @@
 #include <sys/socket.h>
 #include <unistd.h>
 
+#include <atomic>
 #include <condition_variable>
 #include <deque>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -32,6 +38,12 @@ namespace bnet {
 namespace {
 
 class AsyncComm;
+
+// what an epoll event (or a kick) refers to: the comm's message state machine (j < 0) or one data stream
+struct Ctx {
+  AsyncComm* comm;
+  int j;
+};
 
 class Loop {
  public:
@@ -49,15 +61,30 @@ class Loop {
     ssize_t r = write(ev_, &one, sizeof(one));
     (void)r;
   }
-  void add(AsyncComm* c);
-  void remove(AsyncComm* c);       // returns once the loop no longer touches c
-  void kick(AsyncComm* c) {        // c has new requests
+  void add(int fd, Ctx* ctx) {
     {
       std::lock_guard<std::mutex> lk(mu_);
-      kicked_.push_back(c);
+      to_add_.push_back({fd, ctx});
     }
     wake();
   }
+  void remove(AsyncComm* c);       // returns once the loop no longer touches c (any of its contexts)
+  void kick(Ctx* ctx) {            // ctx has something to do
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      kicked_.push_back(ctx);
+    }
+    wake();
+  }
+  bool on_this_thread() const { return std::this_thread::get_id() == th_.get_id(); }
+  // temporary registration of a data stream for the duration of one large chunk (epoll_ctl is thread safe)
+  void attach(int fd, Ctx* ctx) {
+    epoll_event e{};
+    e.events = EPOLLIN | EPOLLOUT | EPOLLET | EPOLLRDHUP;
+    e.data.ptr = ctx;
+    epoll_ctl(ep_, EPOLL_CTL_ADD, fd, &e);
+  }
+  void detach(int fd) { epoll_ctl(ep_, EPOLL_CTL_DEL, fd, nullptr); }
 
  private:
   void run();
@@ -65,8 +92,10 @@ class Loop {
   std::thread th_;
   std::mutex mu_;
   std::condition_variable cv_;
-  std::vector<AsyncComm*> to_add_, to_remove_, kicked_;
-  friend class AsyncComm;
+  struct Reg { int fd; Ctx* ctx; };
+  std::vector<Reg> to_add_, regs_;   // regs_: loop thread only
+  std::vector<AsyncComm*> to_remove_;
+  std::vector<Ctx*> kicked_;
 };
 
 class Pool {
@@ -75,16 +104,23 @@ class Pool {
     static Pool* p = new Pool();  // leaked: loops must outlive static destruction order
     return *p;
   }
-  Loop* pick() { return loops_[next_.fetch_add(1) % loops_.size()]; }
+  size_t size() const { return loops_.size(); }
+  size_t pick() { return next_.fetch_add(1) % loops_.size(); }
+  Loop* loop(size_t i) { return loops_[i % loops_.size()]; }
 
  private:
   Pool() {
     int n = Config::get().async_workers;
+    if (n < 1) n = 1;
     for (int i = 0; i < n; i++) loops_.push_back(new Loop());
   }
   std::vector<Loop*> loops_;
   std::atomic<size_t> next_{0};
 };
+
+// Chunks at least this large are handed to another loop of the pool for the duration of the chunk (parallel
+// copies; costs two epoll_ctl calls and two cross-thread wake-ups, ~25 us); smaller ones stay on the home loop.
+constexpr size_t kParallelChunk = 512 * 1024;
 
 class AsyncComm : public Comm {
  public:
@@ -96,12 +132,35 @@ class AsyncComm : public Comm {
       set_nonblocking(fd, true);
       set_nodelay(fd);
     }
-    ch_.resize(fds_.size());
-    loop_ = Pool::get().pick();
-    loop_->add(this);
+    const size_t h = Pool::get().pick();
+    home_ = Pool::get().loop(h);
+    home_ctx_ = {this, -1};
+    ch_ = std::unique_ptr<Ch[]>(new Ch[fds_.size()]);
+    sctx_.resize(fds_.size());
+    sloop_.resize(fds_.size());
+    for (size_t j = 0; j < fds_.size(); j++) {
+      sctx_[j] = {this, (int)j};
+      sloop_[j] = Pool::get().loop(h + j);      // stream 0 stays on the home loop
+    }
+    // every socket is permanently registered with the home loop; a stream is attached to its helper loop only
+    // while a large chunk is in flight on it
+    home_->add(ctrl_, &home_ctx_);
+    for (size_t j = 0; j < fds_.size(); j++) home_->add(fds_[j], &sctx_[j]);
   }
   ~AsyncComm() override {
-    loop_->remove(this);
+    // helper loops first (nobody is inside drive() afterwards), the home loop last (it fails what is queued)
+    for (size_t j = 0; j < fds_.size(); j++)
+      if (ch_[j].armed.load(std::memory_order_acquire) == kHelper) sloop_[j]->detach(fds_[j]);
+    std::vector<Loop*> done;
+    auto once = [&](Loop* l) {
+      for (Loop* d : done)
+        if (d == l) return;
+      done.push_back(l);
+      l->remove(this);
+    };
+    for (Loop* l : sloop_)
+      if (l != home_) once(l);
+    once(home_);
     shutdown(ctrl_, SHUT_RDWR);
     close(ctrl_);
     for (int fd : fds_) {
@@ -131,7 +190,90 @@ class AsyncComm : public Comm {
     return post(REQ_RECV, data, size, tag, mh, out);
   }
 
-  // ---- everything below runs on the loop thread ------------------------------------
+  // ---- event entry point (any loop thread) ------------------------------------------------------------
+  void on_event(Ctx* ctx, Loop* self) {
+    if (ctx->j < 0) on_ready(); else on_stream(ctx->j, self);
+  }
+  bool is_home(const Loop* l) const { return l == home_; }
+
+  // ---- home loop: fail whatever is still queued ---------------------------------------------------------
+  void on_removed() {
+    dead_ = true;
+    if (cur_) finish(kErrRemote);
+    std::lock_guard<std::mutex> lk(in_mu_);
+    for (Request* r : inbox_) {
+      r->fail(kErrRemote);
+      r->ndone.fetch_add(1, std::memory_order_release);
+    }
+    inbox_.clear();
+  }
+
+ private:
+  struct Ch {
+    char* p = nullptr;
+    size_t n = 0, total = 0;
+    uint64_t t0 = 0;
+    std::atomic<int> armed{0};   // who continues the chunk when the socket becomes ready: kIdle / kHome / kHelper
+  };
+  enum { kIdle = 0, kHome = 1, kHelper = 2 };
+  enum IoResult { IO_DONE, IO_BLOCKED, IO_ERROR };
+
+  // move bytes of chunk j until it is done or the socket would block; runs on whichever thread owns stream j
+  IoResult drive(int j, int* err) {
+    Ch& c = ch_[j];
+    while (c.n) {
+      ssize_t n = kind == SEND ? ::send(fds_[j], c.p, c.n, MSG_NOSIGNAL) : ::recv(fds_[j], c.p, c.n, 0);
+      if (n > 0) {
+        c.p += n;
+        c.n -= (size_t)n;
+        continue;
+      }
+      if (n < 0 && errno == EINTR) continue;
+      if (n < 0 && (errno == EAGAIN || errno == EWOULDBLOCK)) return IO_BLOCKED;
+      *err = (n == 0 || errno == ECONNRESET || errno == EPIPE) ? kErrRemote : kErrSystem;
+      return IO_ERROR;
+    }
+    Telemetry& T = Telemetry::get();
+    if (kind == SEND) T.on_chunk_sent(c.total, now_ns() - c.t0); else T.on_chunk_recv(c.total);
+    return IO_DONE;
+  }
+
+  // chunk j finished (or failed) on some thread: the last one wakes the message state machine
+  void chunk_finished(int err) {
+    if (err) {
+      int expected = 0;
+      serr_.compare_exchange_strong(expected, err, std::memory_order_acq_rel);
+    }
+    if (left_.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+      if (home_->on_this_thread()) on_ready(); else home_->kick(&home_ctx_);
+    }
+  }
+
+  // an event or a kick for data stream j, on the home loop or on the helper loop the chunk was handed to
+  void on_stream(int j, Loop* self) {
+    Ch& c = ch_[j];
+    const int owner = c.armed.load(std::memory_order_acquire);
+    if (owner == kIdle || (owner == kHome) != (self == home_)) return;   // not ours to continue
+    int err = 0;
+    IoResult r = drive(j, &err);
+    if (r == IO_BLOCKED) return;                                // edge-triggered: the next event continues
+    if (owner == kHelper) self->detach(fds_[j]);
+    c.armed.store(kIdle, std::memory_order_release);
+    chunk_finished(r == IO_ERROR ? err : 0);
+  }
+
+  // the socket would block on the home loop: its (permanent) registration there delivers the next edge
+  void arm_home(int j) { ch_[j].armed.store(kHome, std::memory_order_release); }
+
+  // hand a large chunk to the stream's helper loop: attach the socket there (reports current readiness at once)
+  // and kick it (it tries the IO immediately, so no edge can be lost)
+  void arm_helper(int j) {
+    ch_[j].armed.store(kHelper, std::memory_order_release);
+    sloop_[j]->attach(fds_[j], &sctx_[j]);
+    sloop_[j]->kick(&sctx_[j]);
+  }
+
+  // home loop: the message state machine
   void on_ready() {
     if (dead_) return;
     for (;;) {
@@ -184,73 +326,67 @@ class AsyncComm : public Comm {
         }
         len_ = len;
         // <= nstreams chunks, chunk j on stream j (tokio_…:392-403)
-        size_t cs = len ? chunk_size(len, p_.min_chunksize, fds_.size()) : 0;
-        left_ = 0;
-        for (size_t j = 0; j < ch_.size(); j++) {
+        const size_t ns = fds_.size();
+        size_t cs = len ? chunk_size(len, p_.min_chunksize, ns) : 0;
+        int nchunks = 0;
+        for (size_t j = 0; j < ns; j++) {
           size_t off = j * cs;
+          Ch& c = ch_[j];
           if (len && off < len) {
-            ch_[j].p = io_base_ + off;
-            ch_[j].n = len - off < cs ? len - off : cs;
-            ch_[j].t0 = now_ns();
-            left_++;
+            c.p = io_base_ + off;
+            c.n = len - off < cs ? len - off : cs;
+            c.t0 = now_ns();
+            nchunks++;
           } else {
-            ch_[j].p = nullptr;
-            ch_[j].n = 0;
+            c.p = nullptr;
+            c.n = 0;
           }
-          ch_[j].total = ch_[j].n;
+          c.total = c.n;
         }
         st_ = DATA;
+        serr_.store(0, std::memory_order_relaxed);
+        // +1: our own reference, dropped below — the message cannot complete while we are still dealing chunks
+        left_.store(nchunks + 1, std::memory_order_release);
+        // lending pays off from three large chunks on (measured on loopback: with two, the single loop that
+        // alternates between the sockets is as fast and needs no cross-thread wake-ups)
+        int big = 0;
+        for (size_t j = 0; j < ns; j++) big += ch_[j].total >= kParallelChunk;
+        const bool lend = big >= 3;
+        for (size_t j = 0; j < ns; j++) {
+          Ch& c = ch_[j];
+          if (!c.total) continue;
+          if (lend && c.total >= kParallelChunk && sloop_[j] != home_) {
+            arm_helper((int)j);                // large: another loop copies it, in parallel with the others
+            continue;
+          }
+          int err = 0;
+          IoResult r = drive((int)j, &err);    // small (or our own stream): right here
+          if (r == IO_BLOCKED) {
+            arm_home((int)j);                  // continue when the socket is ready
+            continue;
+          }
+          if (r == IO_ERROR) note_err(err);
+          left_.fetch_sub(1, std::memory_order_acq_rel);
+        }
+        if (left_.fetch_sub(1, std::memory_order_acq_rel) != 1) return;   // chunks still in flight: the last one wakes us
       }
       if (st_ == DATA) {
-        bool blocked = false;
-        for (size_t j = 0; j < ch_.size() && st_ == DATA; j++) {
-          Ch& c = ch_[j];
-          while (c.n) {
-            ssize_t n = kind == SEND ? ::send(fds_[j], c.p, c.n, MSG_NOSIGNAL) : ::recv(fds_[j], c.p, c.n, 0);
-            if (n > 0) {
-              c.p += n;
-              c.n -= (size_t)n;
-              if (!c.n) {
-                left_--;
-                Telemetry& T = Telemetry::get();
-                if (kind == SEND) T.on_chunk_sent(c.total, now_ns() - c.t0); else T.on_chunk_recv(c.total);
-              }
-              continue;
-            }
-            if (n < 0 && errno == EINTR) continue;
-            if (n < 0 && (errno == EAGAIN || errno == EWOULDBLOCK)) { blocked = true; break; }
-            finish(n == 0 || errno == ECONNRESET || errno == EPIPE ? kErrRemote : kErrSystem);
-            break;
-          }
-        }
-        if (st_ != DATA) continue;
-        if (left_ == 0) {
-          int st = kOk;
-          if (kind == RECV && cuda_cur_ && len_ && cuda::memcpy_sync(cur_->buf, stage_.data(), len_, cur_->mh->dev) != 0) st = kErrCuda;
-          cur_->nbytes.store(len_, std::memory_order_relaxed);
-          finish(st);
-          continue;
-        }
-        if (blocked) return;
+        if (left_.load(std::memory_order_acquire) != 0) return;
+        int st = serr_.load(std::memory_order_acquire);
+        if (!st && kind == RECV && cuda_cur_ && len_ && cuda::memcpy_sync(cur_->buf, stage_.data(), len_, cur_->mh->dev) != 0)
+          st = kErrCuda;
+        if (!st) cur_->nbytes.store(len_, std::memory_order_relaxed);
+        finish(st);
+        continue;
       }
     }
   }
 
-  void on_removed() {   // loop thread: fail whatever is still queued
-    dead_ = true;
-    if (cur_) finish(kErrRemote);
-    std::lock_guard<std::mutex> lk(in_mu_);
-    for (Request* r : inbox_) {
-      r->fail(kErrRemote);
-      r->ndone.fetch_add(1, std::memory_order_release);
-    }
-    inbox_.clear();
+  void note_err(int err) {
+    int expected = 0;
+    serr_.compare_exchange_strong(expected, err, std::memory_order_acq_rel);
   }
 
-  int ctrl_;
-  std::vector<int> fds_;
-
- private:
   int post(ReqKind k, void* data, size_t size, int tag, MemHandle* mh, Request** out) {
     *out = nullptr;
     if ((k == REQ_SEND) != (kind == SEND)) return kErrInvalid;
@@ -263,7 +399,7 @@ class AsyncComm : public Comm {
       std::lock_guard<std::mutex> lk(in_mu_);
       inbox_.push_back(r);
     }
-    loop_->kick(this);
+    home_->kick(&home_ctx_);
     *out = r;
     return kOk;
   }
@@ -278,35 +414,28 @@ class AsyncComm : public Comm {
     st_ = IDLE;
   }
 
-  struct Ch {
-    char* p = nullptr;
-    size_t n = 0, total = 0;
-    uint64_t t0 = 0;
-  };
   enum State { IDLE, HDR, DATA };
+  int ctrl_;
+  std::vector<int> fds_;
   ConnParams p_;
-  Loop* loop_;
+  Loop* home_ = nullptr;
+  Ctx home_ctx_{};
+  std::vector<Ctx> sctx_;
+  std::vector<Loop*> sloop_;
   std::mutex in_mu_;
   std::deque<Request*> inbox_;
-  // loop-thread state
+  std::unique_ptr<Ch[]> ch_;
+  std::atomic<int> left_{0};     // chunks (+1 while the home loop deals them) of the current message still in flight
+  std::atomic<int> serr_{0};     // first stream error of the current message
+  // home-loop state
   State st_ = IDLE;
   Request* cur_ = nullptr;
   uint32_t hdr_ = 0;
   size_t hdr_off_ = 0, len_ = 0;
-  std::vector<Ch> ch_;
-  size_t left_ = 0;
   char* io_base_ = nullptr;
   bool cuda_cur_ = false, dead_ = false;
   std::vector<char> stage_;
 };
-
-void Loop::add(AsyncComm* c) {
-  {
-    std::lock_guard<std::mutex> lk(mu_);
-    to_add_.push_back(c);
-  }
-  wake();
-}
 
 void Loop::remove(AsyncComm* c) {
   std::unique_lock<std::mutex> lk(mu_);
@@ -314,7 +443,7 @@ void Loop::remove(AsyncComm* c) {
   lk.unlock();
   wake();
   lk.lock();
-  // the loop erases c from the list once it has detached it and failed its requests
+  // the loop erases c from the list once it has detached it (and, on its home loop, failed its requests)
   cv_.wait(lk, [&] {
     for (AsyncComm* x : to_remove_)
       if (x == c) return false;
@@ -327,6 +456,7 @@ void Loop::run() {
   for (;;) {
     int n = epoll_wait(ep_, evs.data(), (int)evs.size(), 1000);
     if (n < 0 && errno != EINTR) break;
+    if (n < 0) n = 0;
     bool woke = false;
     for (int i = 0; i < n; i++) {
       if (evs[i].data.ptr == nullptr) { woke = true; continue; }
@@ -335,19 +465,21 @@ void Loop::run() {
       uint64_t v;
       while (read(ev_, &v, sizeof(v)) > 0) {}
     }
-    std::vector<AsyncComm*> add, rem, kick;
+    std::vector<Reg> add;
+    std::vector<AsyncComm*> rem;
+    std::vector<Ctx*> kick;
     {
       std::lock_guard<std::mutex> lk(mu_);
       add.swap(to_add_);
       rem = to_remove_;
       kick.swap(kicked_);
     }
-    for (AsyncComm* c : add) {
+    for (const Reg& r : add) {
       epoll_event e{};
       e.events = EPOLLIN | EPOLLOUT | EPOLLET | EPOLLRDHUP;
-      e.data.ptr = c;
-      epoll_ctl(ep_, EPOLL_CTL_ADD, c->ctrl_, &e);
-      for (int fd : c->fds_) epoll_ctl(ep_, EPOLL_CTL_ADD, fd, &e);
+      e.data.ptr = r.ctx;
+      epoll_ctl(ep_, EPOLL_CTL_ADD, r.fd, &e);
+      regs_.push_back(r);
     }
     auto removed = [&](AsyncComm* c) {
       for (AsyncComm* x : rem)
@@ -355,16 +487,22 @@ void Loop::run() {
       return false;
     };
     for (AsyncComm* c : rem) {
-      epoll_ctl(ep_, EPOLL_CTL_DEL, c->ctrl_, nullptr);
-      for (int fd : c->fds_) epoll_ctl(ep_, EPOLL_CTL_DEL, fd, nullptr);
-      c->on_removed();
+      for (size_t i = 0; i < regs_.size();) {
+        if (regs_[i].ctx->comm == c) {
+          epoll_ctl(ep_, EPOLL_CTL_DEL, regs_[i].fd, nullptr);
+          regs_.erase(regs_.begin() + i);
+        } else {
+          i++;
+        }
+      }
+      if (c->is_home(this)) c->on_removed();
     }
     for (int i = 0; i < n; i++) {
-      AsyncComm* c = (AsyncComm*)evs[i].data.ptr;
-      if (c && !removed(c)) c->on_ready();
+      Ctx* ctx = (Ctx*)evs[i].data.ptr;
+      if (ctx && !removed(ctx->comm)) ctx->comm->on_event(ctx, this);
     }
-    for (AsyncComm* c : kick)
-      if (!removed(c)) c->on_ready();
+    for (Ctx* ctx : kick)
+      if (!removed(ctx->comm)) ctx->comm->on_event(ctx, this);
     if (!rem.empty()) {
       std::lock_guard<std::mutex> lk(mu_);
       for (AsyncComm* c : rem) {
@@ -372,7 +510,7 @@ void Loop::run() {
           if (to_remove_[i] == c) { to_remove_.erase(to_remove_.begin() + i); break; }
         // a kick that raced with the removal must not reach a freed comm
         for (size_t i = 0; i < kicked_.size();)
-          if (kicked_[i] == c) kicked_.erase(kicked_.begin() + i); else i++;
+          if (kicked_[i]->comm == c) kicked_.erase(kicked_.begin() + i); else i++;
       }
       cv_.notify_all();
     }

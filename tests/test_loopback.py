@@ -182,3 +182,20 @@ def test_ipv6_listener_handle_is_not_truncated(abi):
     # ours keeps all 28 bytes even in the 64-byte v4 handle
     _check(run_pair(["--abi", str(abi), "--sizes", "0,8,1048577", "--inflight", "4", "--rounds", "1"],
                     env={"BNET_NVL": "0", "NCCL_SOCKET_IFNAME": "lo", "NCCL_SOCKET_FAMILY": "10"}), "tcp-threads")
+
+
+def test_async_backend_lends_large_chunks_to_other_loops():
+    # >= 3 chunks of >= 512 KiB each: the epoll backend hands the chunks to helper loops of its pool for the
+    # duration of the chunk (tcp_async.cc); message-serial order and byte placement must not change
+    _check(run_pair(["--sizes", "1572864,6291459,16777216,4096", "--inflight", "4", "--rounds", "2"],
+                    env={"BNET_NVL": "0", "BAGUA_NET_IMPLEMENT": "TOKIO", "BAGUA_NET_NSTREAMS": "4"}), "tcp-async")
+    _check(run_pair(["--sizes", "8388608", "--inflight", "8", "--rounds", "2"],
+                    env={"BNET_NVL": "0", "BAGUA_NET_IMPLEMENT": "TOKIO", "BAGUA_NET_NSTREAMS": "8",
+                         "BAGUA_NET_TOKIO_WORKER_THREADS": "3"}), "tcp-async")
+
+
+def test_async_backend_peer_death_while_chunks_are_lent():
+    outs = run_pair(["--sizes", "16777216", "--inflight", "8", "--rounds", "4", "--die-after", "11", "--expect-error"],
+                    env={"BNET_NVL": "0", "BAGUA_NET_IMPLEMENT": "TOKIO", "BAGUA_NET_NSTREAMS": "4"}, timeout=120)
+    rc, res, err = outs[0]          # the receiver must see an error, not hang
+    assert rc == 0 and res is not None and not res["ok"], (res, err[-2000:])
