@@ -3,6 +3,8 @@
 # Builds build/{tsan,asan}/libnccl-net.so (`make tsan`, `make asan` run the C++ tests against them) and then
 # drives the Python two-process loopback / ABI / telemetry tests against the same libraries through
 # BNET_LIB_DIR + LD_PRELOAD of the sanitizer runtime.  Any sanitizer report fails the script.
+# (ODR detection is off: libnccl-net.so and its -bnetx variant export the same tables on purpose, and the doctor
+# test loads both.)
 set -e
 cd "$(dirname "$0")/.."
 GCCLIB=$(dirname "$(/usr/bin/g++ -print-file-name=libtsan.so)")
@@ -15,7 +17,7 @@ for san in tsan asan; do
     pre="$GCCLIB/libtsan.so"; export TSAN_OPTIONS="log_path=$logs/r exitcode=0 report_signal_unsafe=0"
   else
     pre="$GCCLIB/libasan.so $GCCLIB/libubsan.so"
-    export ASAN_OPTIONS="detect_leaks=0 log_path=$logs/r halt_on_error=0" UBSAN_OPTIONS="log_path=$logs/r print_stacktrace=1"
+    export ASAN_OPTIONS="detect_leaks=0 detect_odr_violation=0 log_path=$logs/r halt_on_error=0" UBSAN_OPTIONS="log_path=$logs/r print_stacktrace=1"
   fi
   BNET_LIB_DIR=$PWD/build/$san LD_PRELOAD="$pre" \
     python -m pytest tests/test_loopback.py tests/test_utils.py tests/test_telemetry.py -q -x -k "not v10"

@@ -191,6 +191,7 @@ std::string Telemetry::render_prometheus() const {
   counter("bnet_nvl_bytes_total", M.nvl_bytes_total.load());
   counter("bnet_nvl_kernel_chunks_total", M.nvl_kernel_chunks.load());
   counter("bnet_shm_bytes_total", M.shm_bytes_total.load());
+  counter("bnet_cma_messages_total", M.cma_msgs.load());
   counter("bnet_errors_total", M.errors_total.load());
   return o.str();
 }

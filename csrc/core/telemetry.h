@@ -39,7 +39,7 @@ struct Metrics {
   Histogram isend_nbytes, irecv_nbytes;
   std::atomic<uint64_t> isend_total{0}, irecv_total{0};           // requests
   std::atomic<uint64_t> isend_bytes_total{0}, irecv_bytes_total{0};
-  std::atomic<uint64_t> nvl_bytes_total{0}, nvl_kernel_chunks{0}, shm_bytes_total{0};
+  std::atomic<uint64_t> nvl_bytes_total{0}, nvl_kernel_chunks{0}, shm_bytes_total{0}, cma_msgs{0};
   std::atomic<uint64_t> errors_total{0};
   std::atomic<int64_t> hold_on_request{0};                         // in flight
   std::atomic<uint64_t> last_chunk_bytes_per_s{0};                 // isend_nbytes_per_second

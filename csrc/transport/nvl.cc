@@ -27,6 +27,8 @@
 #include <sys/mman.h>
 #include <sys/socket.h>
 #include <sys/stat.h>
+#include <sys/prctl.h>
+#include <sys/uio.h>
 #include <sys/un.h>
 #include <unistd.h>
 
@@ -49,6 +51,7 @@ constexpr int kMaxMr = 128;
 constexpr uint32_t kNoMr = 0xffffffffu;
 constexpr uint32_t kShmMagic = 0x4e564c31u;  // "NVL1"
 constexpr size_t kRingBudget = 1 << 20;      // bytes copied per progress() call
+constexpr size_t kCmaBudget = 4 << 20;       // bytes pulled per progress() call and request (single-copy path)
 
 struct alignas(64) RecvDesc {
   std::atomic<uint64_t> seq;
@@ -58,14 +61,17 @@ struct alignas(64) RecvDesc {
   uint32_t dst_type;
   int32_t tag;
 };
+enum : uint32_t { PATH_DIRECT = 0, PATH_RING = 1, PATH_CMA = 2 };
 struct alignas(64) Announce {
   std::atomic<uint64_t> seq;
   uint64_t nbytes;
-  uint32_t via_ring;
+  uint32_t via_ring;      // PATH_*
   int32_t err;
+  uint64_t src_addr;      // PATH_CMA: where the payload sits in the sender's address space
 };
 struct alignas(64) Done {
   std::atomic<uint64_t> seq;
+  int32_t err;            // PATH_CMA: the receiver could not pull the payload
 };
 struct alignas(64) MrDesc {
   std::atomic<uint32_t> gen;      // odd = valid
@@ -81,6 +87,10 @@ struct NvlShm {
   alignas(64) std::atomic<uint32_t> receiver_closed;
   alignas(64) std::atomic<uint64_t> ring_w;
   alignas(64) std::atomic<uint64_t> ring_r;
+  // cross-memory attach (single copy for large host messages): the receiver pulls straight from the sender's
+  // buffer with process_vm_readv.  Probed once at accept: 0 = not probed yet, 1 = works, 2 = refused by the kernel
+  alignas(64) std::atomic<uint32_t> cma_state;
+  uint64_t cma_probe_addr, cma_probe_val;
   RecvDesc rdesc[kSlots];
   Announce ann[kSlots];
   Done done[kSlots];
@@ -174,6 +184,19 @@ class NvlComm : public Comm {
       }
     }
     set_nonblocking(uds_, true);
+    cma_min_ = (size_t)env_int("CMA_MIN", 512 << 10);   // below this the ring (cache-resident, pipelined) is as fast
+    if (k == RECV) {
+      // can we read the sender's memory directly?  (same uid + ptrace permission; the sender opted in with
+      // PR_SET_PTRACER_ANY for hosts that run the Yama LSM)
+      uint32_t verdict = 2;
+      if (env_int("CMA", 1) != 0 && shm_->cma_probe_addr) {
+        uint64_t val = 0;
+        iovec l{&val, sizeof(val)}, r{(void*)shm_->cma_probe_addr, sizeof(val)};
+        if (process_vm_readv((pid_t)peer_pid_, &l, 1, &r, 1, 0) == (ssize_t)sizeof(val) && val == shm_->cma_probe_val) verdict = 1;
+      }
+      shm_->cma_state.store(verdict, std::memory_order_release);
+      BNET_DEBUG("nvl accept: cross-memory attach to pid %u %s", peer_pid_, verdict == 1 ? "works" : "unavailable");
+    }
     // all CUDA resource creation happens here, in NCCL's setup phase, never on the data path
     cuda_live_ = cuda::available() && !cuda::fake();
     if (cuda_live_) cuda::exec_prepare(local_dev_);
@@ -589,11 +612,18 @@ class NvlComm : public Comm {
           uint64_t* fd = flags_dev_ + (k % kSlots) * cuda::kMaxChunksPerJob;
           direct = cuda::exec_copy(local_dev_, ksrc, dst, r->size, fh, fd, k + 1, &nchunks) == 0;
         }
+        // large host -> host message: let the receiver pull it straight out of our buffer (one copy, none by us)
+        const bool cma = !direct && !src_cuda && d.dst_type == NCCL_PTR_HOST && r->size >= cma_min_ &&
+                         shm_->cma_state.load(std::memory_order_acquire) == 1;
         a.nbytes = r->size;
-        a.via_ring = direct ? 0 : 1;
+        a.via_ring = direct ? PATH_DIRECT : cma ? PATH_CMA : PATH_RING;
+        a.src_addr = (uint64_t)r->buf;
         a.err = 0;
         a.seq.store(k + 1, std::memory_order_release);
-        if (direct) {
+        if (cma) {
+          r->u[1] = 4;
+          T.m().cma_msgs.fetch_add(1, std::memory_order_relaxed);
+        } else if (direct) {
           r->u[1] = 2;
           r->u[2] = (uint64_t)nchunks;
           T.m().nvl_kernel_chunks.fetch_add((uint64_t)nchunks, std::memory_order_relaxed);
@@ -629,6 +659,20 @@ class NvlComm : public Comm {
           r->u[1] = 3;
         } else {
           ring_busy = true;
+        }
+      } else if (r->u[1] == 4) {
+        Done& dn = shm_->done[k % kSlots];
+        if (dn.seq.load(std::memory_order_acquire) == k + 1) {
+          if (dn.err) {
+            r->fail(dn.err);
+            track(-1);
+            broken.store(dn.err);
+          } else {
+            moved_ += r->size;
+            T.on_chunk_sent(r->size, now_ns() - r->t_post);
+            complete(r, r->size);
+          }
+          r->u[1] = 3;
         }
       } else if (r->u[1] == 2) {
         volatile uint64_t* fh = flags_ + (k % kSlots) * cuda::kMaxChunksPerJob;
@@ -667,9 +711,10 @@ class NvlComm : public Comm {
           continue;
         }
         r->u[4] = a.nbytes;
-        r->u[1] = a.via_ring ? 1 : 2;
+        r->u[1] = a.via_ring == PATH_RING ? 1 : a.via_ring == PATH_CMA ? 4 : 2;
         r->u[2] = 0;
-        if (a.via_ring && a.nbytes == 0) {
+        r->u[5] = a.src_addr;
+        if (a.via_ring == PATH_RING && a.nbytes == 0) {
           complete(r, 0);
           r->u[1] = 3;
           continue;
@@ -697,6 +742,33 @@ class NvlComm : public Comm {
           r->u[1] = 3;
         } else {
           ring_busy = true;   // the ring is a byte stream: later ring messages wait for this one
+        }
+      } else if (r->u[1] == 4) {
+        // pull a bounded piece per call so that one huge message cannot monopolise the proxy thread
+        size_t left = (size_t)(r->u[4] - r->u[2]);
+        size_t want = left < kCmaBudget ? left : kCmaBudget;
+        iovec l{(char*)r->buf + r->u[2], want}, rm{(void*)(r->u[5] + r->u[2]), want};
+        ssize_t n = want ? process_vm_readv((pid_t)peer_pid_, &l, 1, &rm, 1, 0) : 0;
+        Done& dn = shm_->done[k % kSlots];
+        if (n < 0) {
+          BNET_WARN("nvl: process_vm_readv from pid %u failed: %s", peer_pid_, strerror(errno));
+          dn.err = kErrSystem;
+          dn.seq.store(k + 1, std::memory_order_release);
+          r->fail(kErrSystem);
+          track(-1);
+          r->u[1] = 3;
+          broken.store(kErrSystem);
+          continue;
+        }
+        r->u[2] += (uint64_t)n;
+        moved_ += (uint64_t)n;
+        if (r->u[2] == r->u[4]) {
+          dn.err = 0;
+          dn.seq.store(k + 1, std::memory_order_release);   // the sender may reuse its buffer now
+          T.m().shm_bytes_total.fetch_add(r->u[4], std::memory_order_relaxed);
+          T.on_chunk_recv((uint64_t)r->u[4]);
+          complete(r, (size_t)r->u[4]);
+          r->u[1] = 3;
         }
       } else if (r->u[1] == 2) {
         if (shm_->done[k % kSlots].seq.load(std::memory_order_acquire) == k + 1) {
@@ -727,6 +799,7 @@ class NvlComm : public Comm {
   uint64_t* flush_flag_ = nullptr;
   uint64_t* flush_flag_dev_ = nullptr;
   uint64_t flush_seq_ = 0;
+  size_t cma_min_ = 512 << 10;
   std::map<uint32_t, Import> imports_;
   std::vector<Import> stale_;
   std::map<uint32_t, int> fds_;
@@ -816,6 +889,19 @@ Comm* nvl_connect(int dev, const Handle& h) {
   shm->version = kWireVersion;
   shm->total_bytes = total;
   shm->ring_bytes = ring;
+  {
+    // let the receiver verify (and later use) cross-memory attach on us
+    static uint64_t probe_word = 0;
+    static std::once_flag once;
+    std::call_once(once, [] {
+      probe_word = random_u64() | 1;
+#ifdef PR_SET_PTRACER
+      prctl(PR_SET_PTRACER, PR_SET_PTRACER_ANY, 0, 0, 0);   // Yama: allow same-uid peers to read our memory
+#endif
+    });
+    shm->cma_probe_addr = (uint64_t)&probe_word;
+    shm->cma_probe_val = probe_word;
+  }
   std::atomic_thread_fence(std::memory_order_release);
   NvlHello hello{};
   hello.magic = kHandleMagic;

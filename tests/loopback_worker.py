@@ -189,6 +189,8 @@ def main() -> int:
         from bagua_net_b200.utils import native
 
         result["exec"] = native.exec_stats()
+        result["cma_messages"] = sum(int(float(ln.split()[-1])) for ln in native.metrics_text().splitlines()
+                                     if ln.startswith("bnet_cma_messages_total"))
         result["kernel_chunks"] = sum(int(float(ln.split()[-1])) for ln in native.metrics_text().splitlines()
                                       if ln.startswith("bnet_nvl_kernel_chunks_total"))
     except Exception:

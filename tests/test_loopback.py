@@ -94,6 +94,16 @@ def test_nvl_shared_memory_host_buffers():
                     env={"BNET_NVL": "1", "BNET_SHM_RING_BYTES": "1048576"}), "nvl")
 
 
+def test_nvl_large_host_messages_are_pulled_with_one_copy():
+    # same-host, host buffers, >= 512 KiB: the receiver reads the payload straight out of the sender's buffer
+    # (process_vm_readv, probed at accept); smaller messages and BNET_CMA=0 keep using the ring
+    args = ["--sizes", "0,8,524287,524288,1048577,9437184", "--inflight", "8", "--rounds", "2"]
+    on = _check(run_pair(args, env={"BNET_NVL": "1"}), "nvl")
+    assert on[1][1]["cma_messages"] == 8 * 2 * 3, on[1][1]
+    off = _check(run_pair(args, env={"BNET_NVL": "1", "BNET_CMA": "0"}), "nvl")
+    assert off[1][1]["cma_messages"] == 0, off[1][1]
+
+
 def test_nvl_direct_path_with_emulated_device_memory():
     # regMr(NCCL_PTR_CUDA) export/import, FIFO matching and per-chunk completion words,
     # with "device memory" emulated by shm segments (BNET_FAKE_CUDA=1)
