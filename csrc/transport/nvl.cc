@@ -261,6 +261,15 @@ class NvlComm : public Comm {
         BNET_INFO("nvl regMr: %p +%zu not exportable; this buffer will use the bounce ring", data, size);
       }
     }
+    if (kind == SEND && type == NCCL_PTR_HOST && size) {
+      // Is this buffer readable through cross-memory attach?  Ordinary pages are; driver-owned mappings (pinned
+      // CUDA host allocations are VM_PFNMAP on some stacks) are not.  Reading our own first and last byte with
+      // the same system call takes the same get_user_pages path the receiver will take.
+      char probe[2];
+      iovec l[2] = {{&probe[0], 1}, {&probe[1], 1}};
+      iovec rm[2] = {{data, 1}, {(char*)data + size - 1, 1}};
+      mh->cma = process_vm_readv(getpid(), l, 2, rm, 2, 0) == 2 ? 1 : 0;
+    }
     if (kind == SEND && type == NCCL_PTR_HOST && cuda::available()) {
       // BNET_HOST_SRC_DIRECT=1: pinned host sources (NCCL keeps its LL send buffers in host memory) are read by
       // the copy kernel itself and stored straight into the peer GPU, instead of ring + staged H2D copy
@@ -613,8 +622,8 @@ class NvlComm : public Comm {
           direct = cuda::exec_copy(local_dev_, ksrc, dst, r->size, fh, fd, k + 1, &nchunks) == 0;
         }
         // large host -> host message: let the receiver pull it straight out of our buffer (one copy, none by us)
-        const bool cma = !direct && !src_cuda && d.dst_type == NCCL_PTR_HOST && r->size >= cma_min_ &&
-                         shm_->cma_state.load(std::memory_order_acquire) == 1;
+        const bool cma = !direct && !src_cuda && d.dst_type == NCCL_PTR_HOST && r->size >= cma_min_ && r->mh &&
+                         r->mh->cma == 1 && shm_->cma_state.load(std::memory_order_acquire) == 1;
         a.nbytes = r->size;
         a.via_ring = direct ? PATH_DIRECT : cma ? PATH_CMA : PATH_RING;
         a.src_addr = (uint64_t)r->buf;

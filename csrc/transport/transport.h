@@ -66,6 +66,7 @@ struct MemHandle {
   int dev = -1;             // CUDA device of the buffer (staged copies run on worker threads)
   Comm* owner = nullptr;
   void* priv = nullptr;     // transport specific (NVL: export record)
+  int cma = 0;              // NVL sender: 1 = other processes can read this buffer with process_vm_readv
 };
 
 enum ReqKind : uint8_t { REQ_SEND = 0, REQ_RECV = 1, REQ_FLUSH = 2 };
