@@ -258,11 +258,18 @@ void release_export(MemExport* e) {
   }
 }
 
+// `tag` tells two allocations apart that lived at the same address of the exporter at different times (it frees a
+// buffer, maps another one at the same VA, registers it again): the inode behind the POSIX fd, or a hash of the
+// CUDA IPC handle.  Without it the cache would hand out the mapping of the OLD physical memory.
 struct ImportKey {
   uint64_t pid, base;
   int dev;
+  uint64_t tag;
   bool operator<(const ImportKey& o) const {
-    return pid != o.pid ? pid < o.pid : (base != o.base ? base < o.base : dev < o.dev);
+    if (pid != o.pid) return pid < o.pid;
+    if (base != o.base) return base < o.base;
+    if (dev != o.dev) return dev < o.dev;
+    return tag < o.tag;
   }
 };
 struct ImportCookie {
@@ -316,7 +323,14 @@ int import_memory(const MemExport& e, int local_fd, int dev, void** base_out, vo
   }
   // One mapping per (exporter, allocation, importing device) and process: many registered
   // buffers usually live in the same allocation, and a CUDA IPC handle must not be opened twice.
-  ImportKey key{e.pid, e.alloc_base, dev};
+  uint64_t tag = 0;
+  if (e.kind == EXPORT_CUDA_IPC) {
+    tag = fnv1a(e.ipc, sizeof(e.ipc));
+  } else if (e.kind == EXPORT_POSIX_FD && local_fd >= 0) {
+    struct stat st;
+    if (fstat(local_fd, &st) == 0) tag = ((uint64_t)st.st_dev << 32) ^ (uint64_t)st.st_ino;
+  }
+  ImportKey key{e.pid, e.alloc_base, dev, tag};
   {
     std::lock_guard<std::mutex> lk(g_import_mu);
     auto it = g_imports.find(key);

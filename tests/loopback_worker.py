@@ -41,6 +41,8 @@ class FakeCudaBuf:
     def __init__(self, lib, n):
         lib.bnet_fake_cuda_alloc.restype = ctypes.c_void_p
         lib.bnet_fake_cuda_alloc.argtypes = [ctypes.c_size_t]
+        lib.bnet_fake_cuda_free.argtypes = [ctypes.c_void_p]
+        self._lib = lib
         self.n = max(n, 16)
         self.addr = lib.bnet_fake_cuda_alloc(self.n)
         assert self.addr
@@ -49,6 +51,12 @@ class FakeCudaBuf:
 
     def view(self):
         return self.arr
+
+    def close(self):
+        if self.addr:
+            self.arr = None
+            self._lib.bnet_fake_cuda_free(ctypes.c_void_p(self.addr))
+            self.addr = 0
 
 
 class CudaBuf:
@@ -173,6 +181,9 @@ def main() -> int:
                             assert not bufs[j].view()[size:size + extra].any(), "wrote past the message"
                 for j in range(a.inflight):
                     p.dereg_mr(comm, mhs[j])
+                for b in bufs:                      # emulated device segments are shm files: give them back
+                    if hasattr(b, "close"):
+                        b.close()
                 if a.bw and size == max(sizes):
                     result["gbps"] = a.inflight * size / dt / 1e9
         result["ok"] = True

@@ -209,3 +209,26 @@ def test_async_backend_peer_death_while_chunks_are_lent():
                     env={"BNET_NVL": "0", "BAGUA_NET_IMPLEMENT": "TOKIO", "BAGUA_NET_NSTREAMS": "4"}, timeout=120)
     rc, res, err = outs[0]          # the receiver must see an error, not hang
     assert rc == 0 and res is not None and not res["ok"], (res, err[-2000:])
+
+
+def _random_sizes(seed, n):
+    import random
+
+    rnd = random.Random(seed)
+    out = []
+    for _ in range(n):
+        r = rnd.random()
+        out.append(rnd.randint(0, 64) if r < 0.2 else rnd.randint(65, 70000) if r < 0.6 else
+                   rnd.randint(70001, 1200000) if r < 0.9 else rnd.randint(1200001, 5000000))
+    return ",".join(map(str, out))
+
+
+@pytest.mark.parametrize("name,env,extra", [
+    ("tcp-threads", {"BNET_NVL": "0", "BAGUA_NET_NSTREAMS": "3"}, []),
+    ("tcp-async", {"BNET_NVL": "0", "BAGUA_NET_IMPLEMENT": "TOKIO", "BAGUA_NET_NSTREAMS": "5", "BAGUA_NET_MIN_CHUNKSIZE": "100000"}, []),
+    ("nvl", {"BNET_NVL": "1", "BNET_SHM_RING_BYTES": "131072"}, []),
+    ("nvl", {"BNET_NVL": "1", "BNET_FAKE_CUDA": "1", "BNET_HOST_SRC_DIRECT": "1"}, ["--mem", "fakecuda", "--mix"]),
+], ids=["basic", "epoll", "shm-ring+cma", "emulated-device-mix"])
+def test_random_message_sizes(name, env, extra):
+    # 100 messages of random sizes (0 B .. 5 MB), 8 in flight, every byte checked
+    _check(run_pair(["--sizes", _random_sizes(7, 100), "--inflight", "8", "--rounds", "1"] + extra, env=env, timeout=300), name)
