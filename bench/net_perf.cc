@@ -6,6 +6,7 @@
 // src/implement/nthread_per_socket_backend.rs:524-631).
 //
 //   net_perf [-l libnccl-net.so] [-b min] [-e max] [-f factor] [-w window] [-t bytes moved per size, default 2e9] [-c check]
+//            [-m host|fakecuda]
 // honours the BAGUA_NET_* / BNET_* environment (implementation, streams, chunk size, NVL on/off).
 // Output columns: bytes, messages, time, GB/s, messages/s, mean us per message.
 #include <dlfcn.h>
@@ -53,6 +54,7 @@ int main(int argc, char** argv) {
   size_t lo = 64, hi = 64u << 20;
   double factor = 4, budget = 2e9;
   int window = 8, check = 1;
+  bool fake = false;
   for (int i = 1; i + 1 < argc; i += 2) {
     if (!strcmp(argv[i], "-l")) lib = argv[i + 1];
     else if (!strcmp(argv[i], "-b")) lo = parse_size(argv[i + 1]);
@@ -61,6 +63,7 @@ int main(int argc, char** argv) {
     else if (!strcmp(argv[i], "-w")) window = atoi(argv[i + 1]);
     else if (!strcmp(argv[i], "-t")) budget = (double)parse_size(argv[i + 1]);
     else if (!strcmp(argv[i], "-c")) check = atoi(argv[i + 1]);
+    else if (!strcmp(argv[i], "-m")) fake = !strcmp(argv[i + 1], "fakecuda");
     else { fprintf(stderr, "unknown option %s\n", argv[i]); return 2; }
   }
   if (window < 1) window = 1;
@@ -90,12 +93,30 @@ int main(int argc, char** argv) {
     while (!comm) OK(net->connect(0, handle, &comm, nullptr));
   }
 
-  std::vector<unsigned char> buf[8];
+  // -m fakecuda (with BNET_FAKE_CUDA=1): "device" buffers emulated by shm segments — the registered-buffer /
+  // descriptor / completion-word protocol of the NVLink direct path with a memcpy standing in for the kernel,
+  // i.e. the host-side cost per message of that path
+  struct Buf {
+    unsigned char* p = nullptr;
+    std::vector<unsigned char> own;
+    unsigned char* data() { return p; }
+    unsigned char& operator[](size_t i) { return p[i]; }
+  } buf[8];
   void* mh[8];
+  typedef void* (*fake_alloc_t)(size_t);
+  fake_alloc_t fake_alloc = fake ? (fake_alloc_t)dlsym(h, "bnet_fake_cuda_alloc") : nullptr;
+  if (fake && !fake_alloc) { fprintf(stderr, "bnet_fake_cuda_alloc missing\n"); return 2; }
   for (int j = 0; j < window; j++) {
-    buf[j].resize(hi + 64);
-    for (size_t k = 0; k < buf[j].size(); k += 61) buf[j][k] = sender ? (unsigned char)(k * 7 + 3) : 0;
-    OK(net->regMr(comm, buf[j].data(), buf[j].size(), NCCL_PTR_HOST, &mh[j]));
+    const size_t cap = hi + 64;
+    if (fake) {
+      buf[j].p = (unsigned char*)fake_alloc(cap);
+      if (!buf[j].p) { fprintf(stderr, "emulated device allocation failed (BNET_FAKE_CUDA=1 set?)\n"); return 2; }
+    } else {
+      buf[j].own.resize(cap);
+      buf[j].p = buf[j].own.data();
+    }
+    for (size_t k = 0; k < cap; k += 61) buf[j][k] = sender ? (unsigned char)(k * 7 + 3) : 0;
+    OK(net->regMr(comm, buf[j].data(), cap, fake ? NCCL_PTR_CUDA : NCCL_PTR_HOST, &mh[j]));
   }
   if (!sender) printf("# %-10s %10s %9s %9s %12s %10s\n", "bytes", "messages", "time(s)", "GB/s", "messages/s", "us/msg");
 
