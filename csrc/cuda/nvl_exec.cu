@@ -760,6 +760,28 @@ int exec_prepare(int dev) {
   return rc;
 }
 
+void exec_dump() {
+  static const char* names[] = {"EXITED", "RUNNING", "EXITING"};
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (Exec* e : g_exec) {
+    if (!e || !e->ok) continue;
+    fprintf(stderr, "[bnet watchdog] executor dev %d: %s%s%s, %d x %d CTAs, outstanding %u, jobs %llu chunks %llu launches %llu\n",
+            e->dev, e->grid ? "single grid" : e->persistent ? "persistent" : "one-shot", e->tma ? " tma" : "", e->ce ? " copy-engine" : "",
+            e->nclusters, e->cluster_size, g_outstanding_host ? g_outstanding_host->load() : 0u,
+            (unsigned long long)e->stats.jobs, (unsigned long long)e->stats.chunks, (unsigned long long)e->stats.launches);
+    if (e->grid && e->ctl)
+      fprintf(stderr, "[bnet watchdog]   grid state %s stop %u submitted %llu epoch %llu\n", names[e->ctl->state % 3], e->ctl->stop,
+              (unsigned long long)e->ctl->submitted, (unsigned long long)e->epoch);
+    for (size_t i = 0; i < e->streams.size(); i++) {
+      ClusterQ* q = e->streams[i].q;
+      if (!q) continue;
+      fprintf(stderr, "[bnet watchdog]   queue %zu: kernel %s stop %u published %llu completed %llu%s\n", i, names[q->state % 3], q->stop,
+              (unsigned long long)q->tail, (unsigned long long)q->head,
+              cudaStreamQuery(e->streams[i].stream) == cudaSuccess ? " (stream idle)" : " (stream busy)");
+    }
+  }
+}
+
 void exec_stats(ExecStats* out) {
   memset(out, 0, sizeof(*out));
   std::lock_guard<std::mutex> lk(g_mu);

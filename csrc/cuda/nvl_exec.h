@@ -34,6 +34,8 @@ int exec_prepare(int dev);
 // while the count is non-zero so that no kernel launch is needed in the middle of a collective.
 void exec_outstanding_add(int delta);
 void exec_stats(ExecStats* out);
+// Watchdog helper: one line per executor queue (kernel state, published/completed descriptors) to stderr.
+void exec_dump();
 void exec_shutdown();
 
 }  // namespace cuda

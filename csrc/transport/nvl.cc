@@ -833,6 +833,7 @@ void watchdog_register(NvlComm* c) {
         usleep((useconds_t)(thr / 1000));
         std::lock_guard<std::mutex> lk(g_wd_mu);
         for (NvlComm* c : g_wd_comms) c->dump_if_stuck(thr);
+        if (cuda::available() && !cuda::fake()) cuda::exec_dump();
         dumps++;
       }
     }).detach();
