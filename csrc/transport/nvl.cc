@@ -380,12 +380,12 @@ class NvlComm : public Comm {
   void progress() override {}   // test() drives progress under the comm lock
 
   // BNET_WATCHDOG_MS: describe a comm whose oldest request is older than the threshold
-  void dump_if_stuck(uint64_t older_than_ns) {
+  bool dump_if_stuck(uint64_t older_than_ns) {
     std::unique_lock<std::mutex> lk(mu_, std::try_to_lock);
-    if (!lk.owns_lock() || pending_.empty()) return;
+    if (!lk.owns_lock() || pending_.empty()) return false;
     Request* r = pending_.front();
     uint64_t age = now_ns() - r->t_post;
-    if (age < older_than_ns) return;
+    if (age < older_than_ns) return false;
     uint64_t k = r->u[0];
     const RecvDesc& d = shm_->rdesc[k % kSlots];
     fprintf(stderr,
@@ -404,6 +404,7 @@ class NvlComm : public Comm {
       for (uint64_t c = 0; c < r->u[2]; c++) fprintf(stderr, " %llu", (unsigned long long)fh[c]);
       fprintf(stderr, "\n");
     }
+    return true;
   }
 
  private:
@@ -832,8 +833,9 @@ void watchdog_register(NvlComm* c) {
       for (int dumps = 0; dumps < 20;) {
         usleep((useconds_t)(thr / 1000));
         std::lock_guard<std::mutex> lk(g_wd_mu);
-        for (NvlComm* c : g_wd_comms) c->dump_if_stuck(thr);
-        if (cuda::available() && !cuda::fake()) cuda::exec_dump();
+        bool stuck = false;
+        for (NvlComm* c : g_wd_comms) stuck |= c->dump_if_stuck(thr);
+        if (stuck && cuda::available() && !cuda::fake()) cuda::exec_dump();
         dumps++;
       }
     }).detach();
