@@ -72,6 +72,7 @@ const DriverApi& driver() {
     // stream memory operations (copy-engine transport mode): optional as well
     *(void**)(&a.StreamWriteValue64) = dlsym(h, "cuStreamWriteValue64_v2");
     if (!a.StreamWriteValue64) *(void**)(&a.StreamWriteValue64) = dlsym(h, "cuStreamWriteValue64");
+    *(void**)(&a.MemcpyAsync) = dlsym(h, "cuMemcpyAsync");
 #undef BIND
     a.ok = core;
     return a;

@@ -33,6 +33,7 @@ struct DriverApi {
   CUresult (*MulticastUnbind)(CUmemGenericAllocationHandle, CUdevice, size_t, size_t);
   CUresult (*MulticastGetGranularity)(size_t*, const CUmulticastObjectProp*, CUmulticastGranularity_flags);
   CUresult (*StreamWriteValue64)(CUstream, CUdeviceptr, cuuint64_t, unsigned int);   // optional
+  CUresult (*MemcpyAsync)(CUdeviceptr, CUdeviceptr, size_t, CUstream);                // optional
 };
 
 const DriverApi& driver();            // .ok == false when libcuda is missing

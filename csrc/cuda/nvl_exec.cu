@@ -638,7 +638,15 @@ int submit(Exec* e, uint32_t op, const void* src, void* dst, size_t nbytes, uint
     if (e->ce && op == OP_COPY) {
       // copy-engine mode: a DMA copy, then a stream-ordered 64-bit write of the completion word.  No SM is
       // used and nothing stays resident between messages; the price is two driver calls per chunk.
-      cudaError_t err = n ? cudaMemcpyAsync((char*)dst + off, (const char*)src + off, n, cudaMemcpyDefault, s.stream) : cudaSuccess;
+      // (driver-level unified-address copy: the destination is a VMM / IPC mapping of the peer's memory)
+      cudaError_t err = cudaSuccess;
+      if (n) {
+        if (driver().MemcpyAsync)
+          err = driver().MemcpyAsync((CUdeviceptr)((char*)dst + off), (CUdeviceptr)((const char*)src + off), n, (CUstream)s.stream) == CUDA_SUCCESS
+                    ? cudaSuccess : cudaErrorUnknown;
+        else
+          err = cudaMemcpyAsync((char*)dst + off, (const char*)src + off, n, cudaMemcpyDefault, s.stream);
+      }
       if (err != cudaSuccess ||
           driver().StreamWriteValue64((CUstream)s.stream, (CUdeviceptr)(flags_dev + c), flag_value, 0) != CUDA_SUCCESS) {
         cudaGetLastError();
