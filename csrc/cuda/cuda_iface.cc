@@ -99,8 +99,16 @@ std::map<uintptr_t, FakeSeg> g_fake;   // base -> segment
 
 extern "C" __attribute__((visibility("default"))) void* bnet_fake_cuda_alloc(size_t n) {
   static std::atomic<int> ctr{0};
+  static std::once_flag once;
+  std::call_once(once, [] {
+    atexit([] {   // emulated device segments are named shm files: do not leave them behind
+      std::lock_guard<std::mutex> lk(g_fake_mu);
+      for (auto& kv : g_fake) shm_unlink(kv.second.name.c_str());
+    });
+  });
   char name[64];
-  snprintf(name, sizeof(name), "/bnet-fake-%d-%d", (int)getpid(), ctr.fetch_add(1));
+  // pid + counter + random: pids are recycled, and a crashed test may have left its files behind
+  snprintf(name, sizeof(name), "/bnet-fake-%d-%d-%08x", (int)getpid(), ctr.fetch_add(1), (unsigned)random_u64());
   int fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
   if (fd < 0) return nullptr;
   if (ftruncate(fd, (off_t)n) != 0) { close(fd); shm_unlink(name); return nullptr; }

@@ -19,6 +19,23 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "multigpu: needs >= 2 CUDA devices")
 
 
+def pytest_sessionfinish(session, exitstatus):
+    # workers that are killed on purpose (peer-death tests) cannot unlink their emulated device segments
+    import glob
+
+    for f in glob.glob("/dev/shm/bnet-fake-*"):
+        try:
+            pid = int(os.path.basename(f).split("-")[2])
+            os.kill(pid, 0)            # still alive: not ours to remove
+        except (ValueError, IndexError, PermissionError):
+            continue
+        except ProcessLookupError:
+            try:
+                os.unlink(f)
+            except OSError:
+                pass
+
+
 @pytest.fixture(scope="session", autouse=True)
 def native_lib():
     import bagua_net_b200
