@@ -232,3 +232,15 @@ def _random_sizes(seed, n):
 def test_random_message_sizes(name, env, extra):
     # 100 messages of random sizes (0 B .. 5 MB), 8 in flight, every byte checked
     _check(run_pair(["--sizes", _random_sizes(7, 100), "--inflight", "8", "--rounds", "1"] + extra, env=env, timeout=300), name)
+
+
+@pytest.mark.parametrize("env", [{"BNET_NVL": "0"}, {"BNET_NVL": "0", "BAGUA_NET_IMPLEMENT": "TOKIO"}, {"BNET_NVL": "1"}],
+                         ids=["basic", "epoll", "nvl"])
+def test_connection_churn_leaks_nothing(env):
+    # 60 listen/connect/accept/regMr/transfer/close cycles in one process: fds, threads and /dev/shm stay flat
+    import subprocess
+    import sys
+
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts", "fd_leak.py")
+    r = subprocess.run([sys.executable, script, "60"], capture_output=True, text=True, timeout=300, env=dict(os.environ, **env))
+    assert r.returncode == 0 and "no leak" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
