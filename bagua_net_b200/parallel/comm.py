@@ -27,6 +27,17 @@ ALGOS = {"auto": 0, "nvls": 1, "p2p": 2, "oneshot": 3}
 BLOB = 128
 
 
+def _host_identity():
+    import socket
+
+    try:
+        with open("/proc/sys/kernel/random/boot_id") as f:
+            boot = f.read().strip()
+    except OSError:
+        boot = ""
+    return socket.gethostname(), boot
+
+
 class _CudaView:
     """Minimal __cuda_array_interface__ carrier so torch can wrap native memory zero-copy."""
 
@@ -86,6 +97,13 @@ class SymmComm:
         self._chk(self.lib.bnet_coll_create(self.rank, self.world, self.device, heap_bytes, C.byref(h)), "create")
         self.h = h
         if self.world > 1:
+            # the heap is shared through POSIX fds over a unix socket and mapped over NVLink: one host only
+            hosts = [None] * self.world
+            dist.all_gather_object(hosts, _host_identity(), group=group)
+            if len(set(hosts)) > 1:
+                raise RuntimeError("SymmComm needs all ranks of the group on ONE host (NVLink/NVSwitch domain); this group "
+                                   f"spans {sorted(set(h[0] for h in hosts))}. Use one SymmComm per host and torch.distributed "
+                                   "/ NCCL (optionally over the bnet plugin's TCP transport) between hosts.")
             blob = C.create_string_buffer(BLOB)
             self._chk(self.lib.bnet_coll_export(self.h, blob), "export")
             blobs = [None] * self.world
