@@ -222,16 +222,24 @@ class BnetDDP(torch.nn.Module):
             x = x.contiguous(memory_format=torch.channels_last)
         return float(self.train_step(x, y, loss_fn).item())
 
-    def train_from_host(self, batches, loss_fn=None):
+    def train_from_host(self, batches, loss_fn=None, lag: int = 1):
         """Training loop over an iterable of (inputs_pinned, targets_pinned) batches — the loader-facing API.
-        Yields the loss of every step as a float (device→host read per step).  The host→device copy of
-        batch i+1 is issued on a dedicated copy stream right after step i has been enqueued, so the PCIe
-        transfer rides under step i's kernels instead of in front of step i+1 (what a DataLoader prefetcher
-        with pin_memory does for eager PyTorch)."""
+        Yields the loss of every step as a float, in order (one device→host read per step).
+
+        * The host→device copy of batch i+1 is issued on a dedicated copy stream right after step i has been
+          enqueued, so the PCIe transfer rides under step i's kernels instead of in front of step i+1 (what a
+          DataLoader prefetcher with pin_memory does for eager PyTorch).
+        * The loss of step i is copied to pinned memory asynchronously and handed out `lag` steps later (default 1),
+          i.e. after step i+1 has been enqueued: the GPU never waits for the host to read a number.  `lag=0` reads
+          each loss before the next step is launched."""
         dev = self.flat_param.device
         if getattr(self, "_h2d_stream", None) is None:
             self._h2d_stream = torch.cuda.Stream(device=dev)
         copy = self._h2d_stream
+        lag = max(int(lag), 0)
+        if len(getattr(self, "_loss_host", ())) < lag + 2:
+            self._loss_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(lag + 2)]
+        bufs = self._loss_host
 
         def stage(batch):
             xh, yh = batch
@@ -249,6 +257,8 @@ class BnetDDP(torch.nn.Module):
             nxt = stage(next(it))
         except StopIteration:
             return
+        pending = []                    # (event, pinned buffer) of steps whose loss has not been handed out yet
+        step = 0
         while nxt is not None:
             x, y, ev = nxt
             cur = torch.cuda.current_stream()
@@ -256,11 +266,23 @@ class BnetDDP(torch.nn.Module):
             x.record_stream(cur)        # allocated on the copy stream, consumed on the compute stream
             y.record_stream(cur)
             loss = self.train_step(x, y, loss_fn)
+            hb = bufs[step % len(bufs)]
+            step += 1
+            hb.copy_(loss.detach().reshape(1).float(), non_blocking=True)   # this step's loss, D2H, asynchronous
+            done = torch.cuda.Event()
+            done.record(cur)
+            pending.append((done, hb))
             try:
                 nxt = stage(next(it))   # overlaps the step that was just enqueued
             except StopIteration:
                 nxt = None
-            yield float(loss.item())
+            while len(pending) > lag:
+                e, b = pending.pop(0)
+                e.synchronize()
+                yield float(b[0])
+        for e, b in pending:
+            e.synchronize()
+            yield float(b[0])
 
     # ------------------------------------------------------------------ checkpoint / resume
     # Model weights live in ordinary nn.Module tensors (views into the flat heap), so module.state_dict() /
