@@ -116,3 +116,30 @@ def test_doctor_reports_a_usable_setup_on_cpu():
     text = buf.getvalue()
     assert rc == 0, text
     assert "ncclNet tables exported: v3 v4 v5 v6 v7 v8" in text and "NCCL_NET_PLUGIN=bnet" in text
+
+
+def test_bench_clock_sampler_with_a_stubbed_nvml(monkeypatch):
+    """bench.py samples SM clocks / throttle reasons through NVML every 10 ms inside the timed region; here NVML is a
+    stub (no GPU), on the B200 it is the real library and nvidia-smi stays as the fallback."""
+    import importlib.util
+    import time
+    import types
+
+    fake = types.ModuleType("pynvml")
+    fake.NVML_CLOCK_SM = 1
+    fake.nvmlInit = lambda: None
+    fake.nvmlDeviceGetHandleByIndex = lambda i: i
+    fake.nvmlDeviceGetMaxClockInfo = lambda h, c: 1965
+    fake.nvmlDeviceGetClockInfo = lambda h, c: 1950
+    fake.nvmlDeviceGetCurrentClocksThrottleReasons = lambda h: 0x4 | 0x1      # sw_power_cap + gpu idle
+    monkeypatch.setitem(sys.modules, "pynvml", fake)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(root, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    s = mod.ClockSampler(0)
+    s.start()
+    time.sleep(0.15)
+    out = s.stop()
+    assert out["sm_mhz"] == 1950.0 and out["sm_max_mhz"] == 1965.0 and out["samples"] >= 5
+    assert out["reasons"] == ["sw_power_cap"]
