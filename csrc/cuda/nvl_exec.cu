@@ -625,7 +625,9 @@ int submit(Exec* e, uint32_t op, const void* src, void* dst, size_t nbytes, uint
   cudaGetDevice(&cur);
   if (cur != e->dev) cudaSetDevice(e->dev);
   size_t unit = src_unit_for(op) < 64 ? 64 : src_unit_for(op);   // keep chunk cuts vector aligned on both sides
-  size_t cs = chunk_size(nbytes, e->min_chunk, (size_t)e->nclusters);
+  // (copy-engine mode pays two driver calls per chunk: only split what is large enough to keep several engines busy)
+  const size_t min_chunk = (e->ce && op == OP_COPY && e->min_chunk < ((size_t)2 << 20)) ? ((size_t)2 << 20) : e->min_chunk;
+  size_t cs = chunk_size(nbytes, min_chunk, (size_t)e->nclusters);
   cs = (cs + unit - 1) / unit * unit;
   int nchunks = nbytes ? (int)((nbytes + cs - 1) / cs) : 1;
   if (nchunks > kMaxChunksPerJob) nchunks = kMaxChunksPerJob;   // cannot happen: nclusters <= kMaxChunksPerJob
