@@ -122,6 +122,42 @@ class _ConvBiasReLUPool(torch.autograd.Function):
         return gx, gw, gb.to(w.dtype), None, None
 
 
+def self_check(device=None, verbose: bool = False) -> bool:
+    """One small fused block (with and without pooling), forward and backward, against the eager PyTorch chain in
+    bf16.  Cheap (a few ms); lets a training script fall back to eager layers instead of training on wrong
+    gradients if the native kernels misbehave on this machine."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    try:
+        g = torch.Generator(device=dev).manual_seed(1234)
+        for pool in (False, True):
+            blk = ConvBiasReLU(16, 64, 3, 1, 1, pool=pool).to(dev).to(torch.bfloat16).to(memory_format=torch.channels_last)
+            x = torch.randn(3, 16, 20, 20, device=dev, generator=g).to(torch.bfloat16).contiguous(
+                memory_format=torch.channels_last)
+            xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+            ya = blk(xa)
+            yb = torch.relu(blk.conv(xb))
+            if pool:
+                yb = nn.functional.max_pool2d(yb, 2, 2)
+            go = torch.randn(yb.shape, device=dev, generator=g).to(torch.bfloat16)
+            ya.backward(go)
+            ga = [xa.grad.float().clone(), blk.conv.weight.grad.float().clone(), blk.conv.bias.grad.float().clone()]
+            blk.zero_grad(set_to_none=True)
+            yb.backward(go)
+            gb = [xb.grad.float(), blk.conv.weight.grad.float(), blk.conv.bias.grad.float()]
+            torch.cuda.synchronize(dev)
+            errs = [((ya.float() - yb.float()).norm() / yb.float().norm().clamp_min(1e-6)).item()]
+            errs += [((a - b).norm() / b.norm().clamp_min(1e-6)).item() for a, b in zip(ga, gb)]
+            if verbose:
+                print(f"[fused_nn.self_check] pool={pool} relative L2 errors (y, gx, gw, gb): {errs}")
+            if not all(e == e and e < 0.06 for e in errs):
+                return False
+        return True
+    except Exception as e:      # noqa: BLE001 - any failure means "do not use the fused path"
+        if verbose:
+            print(f"[fused_nn.self_check] failed: {e!r}")
+        return False
+
+
 class ConvBiasReLU(nn.Module):
     """3x3 (or any) convolution + bias + ReLU, optionally followed by a 2x2/stride-2 max-pool."""
 

@@ -206,6 +206,19 @@ def main() -> int:
 
     # our arm trains the model built from our fused conv blocks; the stock-NCCL arms train the plain eager model
     fused = args.comm == "bnet" and not args.no_fused and args.model.startswith("vgg")
+    fused_note = None
+    if fused:
+        # the native layer kernels are checked against the eager chain on this very GPU before they are trusted
+        # with the benchmark; all ranks take the same decision
+        from bagua_net_b200.ops import fused_nn
+
+        ok = torch.tensor([1 if fused_nn.self_check(dev) else 0], device=dev, dtype=torch.int32)
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            fused, fused_note = False, "fused conv blocks failed their self-check on this machine: eager layers used"
+            if rank == 0:
+                print(f"[bench] WARNING: {fused_note}", file=sys.stderr)
     model = build_model(args.model, **({"fused": True} if fused else {}))
     model = model.to(dev).to(torch.bfloat16).to(memory_format=torch.channels_last)
     model.train()
@@ -366,7 +379,7 @@ def main() -> int:
             "higher_is_better": True, "scaling": "weak", "vs_baseline": round(img_s / BASELINE_IMG_S, 4),
             "dtype": "bf16", "data": "synthetic (random images/labels, random-init weights)",
             "config": {"model": args.model, "global_batch": world * B, "per_gpu_batch": B, "seq_len": None,
-                       "image": [3, S, S], "parallelism": f"dp{world}", "comm": args.comm, "path": path, "fused_conv_blocks": fused, "cuda_graph": args.comm == "bnet" and not args.no_graph,
+                       "image": [3, S, S], "parallelism": f"dp{world}", "comm": args.comm, "path": path, "fused_conv_blocks": fused, **({"fused_note": fused_note} if fused_note else {}), "cuda_graph": args.comm == "bnet" and not args.no_graph,
                        "optimizer": f"sgd(lr={lr},momentum={mom},wd={wd}) fused into the collective" if args.comm == "bnet"
                        else f"torch.optim.SGD(lr={lr},momentum={mom},wd={wd})",
                        "params": n_params, "bucket_mb": args.bucket_mb,
