@@ -129,9 +129,10 @@ def self_check(device=None, verbose: bool = False) -> bool:
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
     try:
         g = torch.Generator(device=dev).manual_seed(1234)
-        for pool in (False, True):
-            blk = ConvBiasReLU(16, 64, 3, 1, 1, pool=pool).to(dev).to(torch.bfloat16).to(memory_format=torch.channels_last)
-            x = torch.randn(3, 16, 20, 20, device=dev, generator=g).to(torch.bfloat16).contiguous(
+        # narrow and wide channel counts (8 and 64 16-byte channel groups per pixel), with and without pooling
+        for cin, cout, hw, pool in ((16, 64, 20, False), (16, 64, 20, True), (32, 512, 14, False), (32, 512, 14, True)):
+            blk = ConvBiasReLU(cin, cout, 3, 1, 1, pool=pool).to(dev).to(torch.bfloat16).to(memory_format=torch.channels_last)
+            x = torch.randn(3, cin, hw, hw, device=dev, generator=g).to(torch.bfloat16).contiguous(
                 memory_format=torch.channels_last)
             xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
             ya = blk(xa)
@@ -148,7 +149,7 @@ def self_check(device=None, verbose: bool = False) -> bool:
             errs = [((ya.float() - yb.float()).norm() / yb.float().norm().clamp_min(1e-6)).item()]
             errs += [((a - b).norm() / b.norm().clamp_min(1e-6)).item() for a, b in zip(ga, gb)]
             if verbose:
-                print(f"[fused_nn.self_check] pool={pool} relative L2 errors (y, gx, gw, gb): {errs}")
+                print(f"[fused_nn.self_check] {cin}->{cout} {hw}x{hw} pool={pool} relative L2 errors (y, gx, gw, gb): {errs}")
             # (bf16 near-ties route a few pool / ReLU gradients differently than the eager chain: a real indexing bug
             #  shows up as an error of order 1, not of order 0.01)
             if not all(e == e and e < 0.15 for e in errs):
