@@ -428,6 +428,7 @@ def job_fused_nn():
     assert abs(la.item() - lb.item()) < 1e-4, (la.item(), lb.item())
     for pa, pb in zip(a.parameters(), b.parameters()):
         assert (pa.grad - pb.grad).abs().max().item() < 1e-3 * max(1.0, pb.grad.abs().max().item())
+    assert fused_nn.self_check(verbose=True), "the self-check bench.py relies on disagrees with the detailed comparison above"
     print("fused_nn ok", flush=True)
 
 
