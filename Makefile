@@ -78,6 +78,15 @@ $(BUILD)/tests/exec_emu_test: csrc/tests/exec_emu_test.cc csrc/cuda/exec_body.cu
 	@mkdir -p $(dir $@)
 	$(CXX) $(EMU_FLAGS) $< -o $@
 
+# the same emulation tests under Address/UB sanitizers: an out-of-bounds or misaligned access of a kernel body
+# is caught here, on the CPU, instead of poisoning a CUDA context
+emu-asan: csrc/tests/nn_emu_test.cc csrc/tests/exec_emu_test.cc csrc/cuda/nn_body.cuh csrc/cuda/exec_body.cuh
+	@mkdir -p $(BUILD)/asan/tests
+	$(SAN_CXX) $(EMU_FLAGS) -O1 -w $(SAN_FLAGS_asan) csrc/tests/nn_emu_test.cc -o $(BUILD)/asan/tests/nn_emu_test
+	$(SAN_CXX) $(EMU_FLAGS) -O1 -w $(SAN_FLAGS_asan) csrc/tests/exec_emu_test.cc -o $(BUILD)/asan/tests/exec_emu_test
+	$(BUILD)/asan/tests/nn_emu_test
+	$(BUILD)/asan/tests/exec_emu_test
+
 test: $(TEST_BINS) $(BUILD)/tests/nn_emu_test $(BUILD)/tests/exec_emu_test
 	$(BUILD)/tests/unit_tests $(PLUGIN_SO)
 	$(BUILD)/tests/loopback_test $(PLUGIN_SO)
@@ -111,7 +120,7 @@ clean:
 	rm -rf $(BUILD) $(OUT)/*.so
 
 -include $(HOST_OBJS:.o=.d) $(CU_OBJS:.o=.d)
-.PHONY: default test bench sass tar clean
+.PHONY: default test bench sass tar clean emu-asan
 
 # ---- sanitizer builds of the host engine: `make tsan` / `make asan` rebuild every host
 # object with the sanitizer into build/<san>/, link it with the (uninstrumented) kernel objects and run the

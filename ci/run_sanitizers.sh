@@ -9,6 +9,7 @@ set -e
 cd "$(dirname "$0")/.."
 GCCLIB=$(dirname "$(/usr/bin/g++ -print-file-name=libtsan.so)")
 make -j"$(nproc)"
+make emu-asan            # kernel bodies on an emulated grid under ASan/UBSan
 for san in tsan asan; do
   make $san
   for alias in bnet bnetx; do cp -f build/$san/libnccl-net.so build/$san/libnccl-net-$alias.so; done
