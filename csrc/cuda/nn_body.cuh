@@ -243,5 +243,173 @@ BNET_HD void pool_relu_bwd_thread(const T* gp, const uint8_t* idx, T* gz, int N,
   }
 }
 
+// ==== training-mode BatchNorm fused with what follows it in a ResNet block ===========================================
+//   forward : z = conv(x, w)                         (library call)
+//             stats  = per-channel sum, sum of squares of z                                 (bn_stats, 1 read)
+//             y      = relu?( (z - mean) * invstd * gamma + beta  (+ residual) )            (bn_apply, 1-2 reads, 1 write)
+//   backward: dy     = relu? gy * (y > 0) : gy
+//             s1, s2 = per-channel sum of dy, of dy * xhat        (xhat = (z - mean) * invstd)  (bn_bwd_reduce)
+//             gz     = gamma * invstd * (dy - s1/M - xhat * s2/M) ;  gres = dy              (bn_bwd_apply)
+// Same thread/row mapping as relu_bwd_thread: thread (trow, grp) always sees channel group grp, so its channel
+// constants live in registers for the whole walk.
+
+// mean / inverse standard deviation of this thread's V channels from the accumulated sums (biased variance)
+template <int V>
+BNET_HD void bn_moments(const float* stats, int C, int grp, float inv_m, float eps, float* mean, float* invstd, float* var) {
+#pragma unroll
+  for (int k = 0; k < V; k++) {
+    const int c = grp * V + k;
+    const float m = stats[c] * inv_m;
+    float v = stats[C + c] * inv_m - m * m;
+    v = v > 0.f ? v : 0.f;
+    mean[k] = m;
+    var[k] = v;
+#if defined(__CUDA_ARCH__)
+    invstd[k] = rsqrtf(v + eps);
+#else
+    invstd[k] = 1.0f / sqrtf(v + eps);
+#endif
+  }
+}
+
+// acc[0..V) += z ; acc[V..2V) += z*z
+template <typename T, int U>
+BNET_HD void bn_stats_thread(const T* z, size_t rows, int cvec, int rpb, int grp, int trow, size_t block, size_t nblocks,
+                             float* acc) {
+  constexpr int V = Vec<T>::N;
+  using Raw = typename Vec<T>::Raw;
+  const size_t step = nblocks * (size_t)rpb;
+  for (size_t r0 = block * rpb + trow; r0 < rows; r0 += U * step) {
+    Raw raw[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const size_t r = r0 + u * step;
+      raw[u] = load_raw_stream(z + ((r < rows ? r : r0) * cvec + grp) * V);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (r0 + u * step < rows) {
+        float f[V];
+        Vec<T>::unpack(raw[u], f);
+#pragma unroll
+        for (int k = 0; k < V; k++) {
+          acc[k] += f[k];
+          acc[V + k] += f[k] * f[k];
+        }
+      }
+    }
+  }
+}
+
+// y = relu?( z * scale + shift (+ res) ) with per-channel scale/shift held by the thread
+template <typename T, int U>
+BNET_HD void bn_apply_thread(const T* z, const T* res, T* y, size_t rows, int cvec, int rpb, int grp, int trow, size_t block,
+                             size_t nblocks, const float* scale, const float* shift, bool relu) {
+  constexpr int V = Vec<T>::N;
+  using Raw = typename Vec<T>::Raw;
+  const size_t step = nblocks * (size_t)rpb;
+  for (size_t r0 = block * rpb + trow; r0 < rows; r0 += U * step) {
+    Raw zr[U], rr[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const size_t r = r0 + u * step;
+      const size_t off = ((r < rows ? r : r0) * cvec + grp) * V;
+      zr[u] = load_raw_stream(z + off);
+      if (res) rr[u] = load_raw_stream(res + off);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const size_t r = r0 + u * step;
+      if (r < rows) {
+        float f[V], q[V];
+        Vec<T>::unpack(zr[u], f);
+        if (res) Vec<T>::unpack(rr[u], q);
+#pragma unroll
+        for (int k = 0; k < V; k++) {
+          float v = f[k] * scale[k] + shift[k];
+          if (res) v += q[k];
+          f[k] = relu ? fmaxf(v, 0.f) : v;
+        }
+        store_raw_stream(y + (r * cvec + grp) * V, Vec<T>::pack(f));
+      }
+    }
+  }
+}
+
+// acc[0..V) += dy ; acc[V..2V) += dy * xhat
+template <typename T, int U>
+BNET_HD void bn_bwd_reduce_thread(const T* gy, const T* y, const T* z, size_t rows, int cvec, int rpb, int grp, int trow,
+                                  size_t block, size_t nblocks, const float* mean, const float* invstd, bool relu, float* acc) {
+  constexpr int V = Vec<T>::N;
+  using Raw = typename Vec<T>::Raw;
+  const size_t step = nblocks * (size_t)rpb;
+  for (size_t r0 = block * rpb + trow; r0 < rows; r0 += U * step) {
+    Raw gr[U], yr[U], zr[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const size_t r = r0 + u * step;
+      const size_t off = ((r < rows ? r : r0) * cvec + grp) * V;
+      gr[u] = load_raw_stream(gy + off);
+      zr[u] = load_raw_stream(z + off);
+      if (relu) yr[u] = load_raw_stream(y + off);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (r0 + u * step < rows) {
+        float g[V], a[V], f[V];
+        Vec<T>::unpack(gr[u], g);
+        Vec<T>::unpack(zr[u], f);
+        if (relu) Vec<T>::unpack(yr[u], a);
+#pragma unroll
+        for (int k = 0; k < V; k++) {
+          const float dy = (!relu || a[k] > 0.f) ? g[k] : 0.f;
+          acc[k] += dy;
+          acc[V + k] += dy * ((f[k] - mean[k]) * invstd[k]);
+        }
+      }
+    }
+  }
+}
+
+// gz = a * (dy - c1 - xhat * c2) with a = gamma * invstd, c1 = s1 / M, c2 = s2 / M ; gres = dy (when there is a residual)
+template <typename T, int U>
+BNET_HD void bn_bwd_apply_thread(const T* gy, const T* y, const T* z, T* gz, T* gres, size_t rows, int cvec, int rpb, int grp,
+                                 int trow, size_t block, size_t nblocks, const float* mean, const float* invstd, const float* a,
+                                 const float* c1, const float* c2, bool relu) {
+  constexpr int V = Vec<T>::N;
+  using Raw = typename Vec<T>::Raw;
+  const size_t step = nblocks * (size_t)rpb;
+  for (size_t r0 = block * rpb + trow; r0 < rows; r0 += U * step) {
+    Raw gr[U], yr[U], zr[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const size_t r = r0 + u * step;
+      const size_t off = ((r < rows ? r : r0) * cvec + grp) * V;
+      gr[u] = load_raw_stream(gy + off);
+      zr[u] = load_raw_stream(z + off);
+      if (relu) yr[u] = load_raw_stream(y + off);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const size_t r = r0 + u * step;
+      if (r < rows) {
+        float g[V], act[V], f[V], o[V];
+        Vec<T>::unpack(gr[u], g);
+        Vec<T>::unpack(zr[u], f);
+        if (relu) Vec<T>::unpack(yr[u], act);
+#pragma unroll
+        for (int k = 0; k < V; k++) {
+          const float dy = (!relu || act[k] > 0.f) ? g[k] : 0.f;
+          g[k] = dy;
+          o[k] = a[k] * (dy - c1[k] - (f[k] - mean[k]) * invstd[k] * c2[k]);
+        }
+        const size_t off = (r * cvec + grp) * V;
+        store_raw_stream(gz + off, Vec<T>::pack(o));
+        if (gres) store_raw_stream(gres + off, Vec<T>::pack(g));
+      }
+    }
+  }
+}
+
 }  // namespace nn
 }  // namespace bnet

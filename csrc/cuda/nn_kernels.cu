@@ -88,6 +88,105 @@ __global__ void __launch_bounds__(256) pool_relu_bwd_bias_grad_kernel(const T* _
   reduce_bias_grad<V>(acc, gb, cvec, smem);
 }
 
+// ---- BatchNorm (training) + ReLU + residual, four kernels (see nn_body.cuh) ------------------------------------
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ z, float* __restrict__ stats, size_t rows, int cvec) {
+  constexpr int V = Vec<T>::N;
+  extern __shared__ float smem[];
+  float acc[2 * V];
+#pragma unroll
+  for (int k = 0; k < 2 * V; k++) acc[k] = 0.f;
+  bn_stats_thread<T, 4>(z, rows, cvec, blockDim.x / cvec, threadIdx.x % cvec, threadIdx.x / cvec, blockIdx.x, gridDim.x, acc);
+  const int C = cvec * V;
+  reduce_bias_grad<V>(acc, stats, cvec, smem);          // sum
+  __syncthreads();
+  reduce_bias_grad<V>(acc + V, stats + C, cvec, smem);  // sum of squares
+}
+
+// y = relu?(bn(z) (+ res)); block 0 also updates the running statistics (unbiased variance, PyTorch semantics)
+template <typename T>
+__global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ z, const T* __restrict__ res, T* __restrict__ y,
+                                                       const float* __restrict__ stats, const T* __restrict__ gamma,
+                                                       const T* __restrict__ beta, T* __restrict__ running_mean,
+                                                       T* __restrict__ running_var, size_t rows, int cvec, float eps,
+                                                       float momentum, int relu) {
+  constexpr int V = Vec<T>::N;
+  const int C = cvec * V, grp = threadIdx.x % cvec, trow = threadIdx.x / cvec;
+  float mean[V], invstd[V], var[V], scale[V], shift[V];
+  bn_moments<V>(stats, C, grp, 1.0f / (float)rows, eps, mean, invstd, var);
+#pragma unroll
+  for (int k = 0; k < V; k++) {
+    const int c = grp * V + k;
+    scale[k] = to_f<T>(gamma[c]) * invstd[k];
+    shift[k] = to_f<T>(beta[c]) - mean[k] * scale[k];
+  }
+  if (blockIdx.x == 0 && trow == 0 && running_mean) {
+    const float unbias = rows > 1 ? (float)rows / (float)(rows - 1) : 1.0f;
+#pragma unroll
+    for (int k = 0; k < V; k++) {
+      const int c = grp * V + k;
+      running_mean[c] = from_f<T>((1.f - momentum) * to_f<T>(running_mean[c]) + momentum * mean[k]);
+      running_var[c] = from_f<T>((1.f - momentum) * to_f<T>(running_var[c]) + momentum * var[k] * unbias);
+    }
+  }
+  bn_apply_thread<T, 4>(z, res, y, rows, cvec, blockDim.x / cvec, grp, trow, blockIdx.x, gridDim.x, scale, shift, relu != 0);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* __restrict__ gy, const T* __restrict__ y,
+                                                            const T* __restrict__ z, const float* __restrict__ stats,
+                                                            float* __restrict__ gsum, size_t rows, int cvec, float eps, int relu) {
+  constexpr int V = Vec<T>::N;
+  extern __shared__ float smem[];
+  const int C = cvec * V, grp = threadIdx.x % cvec, trow = threadIdx.x / cvec;
+  float mean[V], invstd[V], var[V], acc[2 * V];
+  bn_moments<V>(stats, C, grp, 1.0f / (float)rows, eps, mean, invstd, var);
+#pragma unroll
+  for (int k = 0; k < 2 * V; k++) acc[k] = 0.f;
+  bn_bwd_reduce_thread<T, 2>(gy, y, z, rows, cvec, blockDim.x / cvec, grp, trow, blockIdx.x, gridDim.x, mean, invstd, relu != 0, acc);
+  reduce_bias_grad<V>(acc, gsum, cvec, smem);            // s1 = sum dy
+  __syncthreads();
+  reduce_bias_grad<V>(acc + V, gsum + C, cvec, smem);    // s2 = sum dy * xhat
+}
+
+// gz, gres, and (block 0) the parameter gradients dgamma = s2, dbeta = s1
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__ gy, const T* __restrict__ y,
+                                                           const T* __restrict__ z, T* __restrict__ gz, T* __restrict__ gres,
+                                                           const float* __restrict__ stats, const float* __restrict__ gsum,
+                                                           const T* __restrict__ gamma, T* __restrict__ dgamma,
+                                                           T* __restrict__ dbeta, size_t rows, int cvec, float eps, int relu) {
+  constexpr int V = Vec<T>::N;
+  const int C = cvec * V, grp = threadIdx.x % cvec, trow = threadIdx.x / cvec;
+  const float inv_m = 1.0f / (float)rows;
+  float mean[V], invstd[V], var[V], a[V], c1[V], c2[V];
+  bn_moments<V>(stats, C, grp, inv_m, eps, mean, invstd, var);
+#pragma unroll
+  for (int k = 0; k < V; k++) {
+    const int c = grp * V + k;
+    a[k] = to_f<T>(gamma[c]) * invstd[k];
+    c1[k] = gsum[c] * inv_m;
+    c2[k] = gsum[C + c] * inv_m;
+  }
+  if (blockIdx.x == 0 && trow == 0) {
+#pragma unroll
+    for (int k = 0; k < V; k++) {
+      const int c = grp * V + k;
+      dbeta[c] = from_f<T>(gsum[c]);
+      dgamma[c] = from_f<T>(gsum[C + c]);
+    }
+  }
+  bn_bwd_apply_thread<T, 2>(gy, y, z, gz, gres, rows, cvec, blockDim.x / cvec, grp, trow, blockIdx.x, gridDim.x, mean, invstd, a,
+                            c1, c2, relu != 0);
+}
+
 }  // namespace nn
 }  // namespace bnet
 
@@ -161,5 +260,85 @@ BNET_API int bnet_nn_pool_relu_bwd_bias_grad(const void* gp, const void* idx, vo
                                                                             (__nv_bfloat16*)gz, gb, N, H, W, cvec);
   else
     pool_relu_bwd_bias_grad_kernel<float><<<grid, threads, smem, st>>>((const float*)gp, (const uint8_t*)idx, (float*)gz, gb, N, H, W, cvec);
+  return cudaGetLastError() == cudaSuccess ? 1 : -2;
+}
+
+
+// ---- BatchNorm family.  stats / gsum: 2*C floats ([sum | sumsq], [s1 | s2]) that the caller zeroes before the
+// reduce kernels.  gamma/beta/running stats have the activation dtype.  res, running_*, gres may be NULL.
+namespace {
+struct RowGrid { int threads, grid; size_t smem; };
+RowGrid row_grid(long long rows, int cvec, int V, int accs) {
+  RowGrid g;
+  g.threads = (256 / cvec) * cvec;
+  const int rpb = g.threads / cvec;
+  long long want = (rows + rpb - 1) / rpb;
+  g.grid = (int)(want < 148 * 8 ? want : 148 * 8);
+  if (g.grid < 1) g.grid = 1;
+  g.smem = (size_t)g.threads * V * sizeof(float) * (accs ? 1 : 0);
+  return g;
+}
+}  // namespace
+
+BNET_API int bnet_nn_bn_stats(const void* z, float* stats, long long rows, int C, int dtype, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int V = dtype == 1 ? 8 : 4;
+  if (C % V || C / V > 256 || rows < 1) return -1;
+  const RowGrid g = row_grid(rows, C / V, V, 1);
+  if (dtype == 1) bn_stats_kernel<__nv_bfloat16><<<g.grid, g.threads, g.smem, st>>>((const __nv_bfloat16*)z, stats, (size_t)rows, C / V);
+  else bn_stats_kernel<float><<<g.grid, g.threads, g.smem, st>>>((const float*)z, stats, (size_t)rows, C / V);
+  return cudaGetLastError() == cudaSuccess ? 1 : -2;
+}
+
+BNET_API int bnet_nn_bn_apply(const void* z, const void* res, void* y, const float* stats, const void* gamma, const void* beta,
+                              void* running_mean, void* running_var, long long rows, int C, float eps, float momentum, int relu,
+                              int dtype, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int V = dtype == 1 ? 8 : 4;
+  if (C % V || C / V > 256 || rows < 1) return -1;
+  const RowGrid g = row_grid(rows, C / V, V, 0);
+  if (dtype == 1)
+    bn_apply_kernel<__nv_bfloat16><<<g.grid, g.threads, 0, st>>>((const __nv_bfloat16*)z, (const __nv_bfloat16*)res, (__nv_bfloat16*)y, stats,
+                                                                (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta,
+                                                                (__nv_bfloat16*)running_mean, (__nv_bfloat16*)running_var, (size_t)rows,
+                                                                C / V, eps, momentum, relu);
+  else
+    bn_apply_kernel<float><<<g.grid, g.threads, 0, st>>>((const float*)z, (const float*)res, (float*)y, stats, (const float*)gamma,
+                                                        (const float*)beta, (float*)running_mean, (float*)running_var, (size_t)rows, C / V,
+                                                        eps, momentum, relu);
+  return cudaGetLastError() == cudaSuccess ? 1 : -2;
+}
+
+BNET_API int bnet_nn_bn_bwd_reduce(const void* gy, const void* y, const void* z, const float* stats, float* gsum, long long rows,
+                                   int C, float eps, int relu, int dtype, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int V = dtype == 1 ? 8 : 4;
+  if (C % V || C / V > 256 || rows < 1) return -1;
+  const RowGrid g = row_grid(rows, C / V, V, 1);
+  if (dtype == 1)
+    bn_bwd_reduce_kernel<__nv_bfloat16><<<g.grid, g.threads, g.smem, st>>>((const __nv_bfloat16*)gy, (const __nv_bfloat16*)y,
+                                                                          (const __nv_bfloat16*)z, stats, gsum, (size_t)rows, C / V, eps, relu);
+  else
+    bn_bwd_reduce_kernel<float><<<g.grid, g.threads, g.smem, st>>>((const float*)gy, (const float*)y, (const float*)z, stats, gsum,
+                                                                  (size_t)rows, C / V, eps, relu);
+  return cudaGetLastError() == cudaSuccess ? 1 : -2;
+}
+
+BNET_API int bnet_nn_bn_bwd_apply(const void* gy, const void* y, const void* z, void* gz, void* gres, const float* stats,
+                                  const float* gsum, const void* gamma, void* dgamma, void* dbeta, long long rows, int C, float eps,
+                                  int relu, int dtype, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int V = dtype == 1 ? 8 : 4;
+  if (C % V || C / V > 256 || rows < 1) return -1;
+  const RowGrid g = row_grid(rows, C / V, V, 0);
+  if (dtype == 1)
+    bn_bwd_apply_kernel<__nv_bfloat16><<<g.grid, g.threads, 0, st>>>((const __nv_bfloat16*)gy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z,
+                                                                    (__nv_bfloat16*)gz, (__nv_bfloat16*)gres, stats, gsum,
+                                                                    (const __nv_bfloat16*)gamma, (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta,
+                                                                    (size_t)rows, C / V, eps, relu);
+  else
+    bn_bwd_apply_kernel<float><<<g.grid, g.threads, 0, st>>>((const float*)gy, (const float*)y, (const float*)z, (float*)gz, (float*)gres,
+                                                            stats, gsum, (const float*)gamma, (float*)dgamma, (float*)dbeta, (size_t)rows,
+                                                            C / V, eps, relu);
   return cudaGetLastError() == cudaSuccess ? 1 : -2;
 }

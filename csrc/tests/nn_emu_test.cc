@@ -149,6 +149,130 @@ static void test_pool(int N, int H, int W, int C, int nblocks) {
 }
 
 template <typename T>
+static void test_bn(size_t rows, int C, int nblocks, bool relu, bool with_res) {
+  constexpr int V = Vec<T>::N;
+  const int cvec = C / V;
+  const int threads = (256 / cvec) * cvec, rpb = threads / cvec;
+  const float eps = 1e-5f;
+  const bool bf = sizeof(T) == 2;
+  std::vector<T> z(rows * C), res(rows * C), y(rows * C), gy(rows * C), gz(rows * C), gres(rows * C), gamma(C), beta(C);
+  for (size_t i = 0; i < rows * C; i++) {
+    z[i] = Conv<T>::to(frand() * (1.0f + (float)(i % C) / C) + 0.25f * (float)((i % C) % 5));   // channel-dependent mean / spread
+    res[i] = Conv<T>::to(frand());
+    gy[i] = Conv<T>::to(frand());
+  }
+  for (int c = 0; c < C; c++) {
+    gamma[c] = Conv<T>::to(0.5f + 0.01f * (c % 37));
+    beta[c] = Conv<T>::to(-0.3f + 0.02f * (c % 11));
+  }
+  // ---- statistics
+  std::vector<double> st(2 * C, 0.0);
+  for (int b = 0; b < nblocks; b++)
+    for (int t = 0; t < threads; t++) {
+      float acc[2 * V];
+      for (int k = 0; k < 2 * V; k++) acc[k] = 0.f;
+      bn_stats_thread<T, 4>(z.data(), rows, cvec, rpb, t % cvec, t / cvec, (size_t)b, (size_t)nblocks, acc);
+      for (int k = 0; k < V; k++) {
+        st[(t % cvec) * V + k] += acc[k];
+        st[C + (t % cvec) * V + k] += acc[V + k];
+      }
+    }
+  std::vector<double> rsum(C, 0.0), rsq(C, 0.0);
+  for (size_t i = 0; i < rows * C; i++) {
+    double v = Conv<T>::from(z[i]);
+    rsum[i % C] += v;
+    rsq[i % C] += v * v;
+  }
+  for (int c = 0; c < C; c++) {
+    CHECK(fabs(st[c] - rsum[c]) <= 1e-3 * (1.0 + fabs(rsum[c])), "%s bn sum c=%d %f vs %f", Conv<T>::name(), c, st[c], rsum[c]);
+    CHECK(fabs(st[C + c] - rsq[c]) <= 1e-3 * (1.0 + fabs(rsq[c])), "%s bn sumsq c=%d", Conv<T>::name(), c);
+  }
+  std::vector<float> stats(2 * C);
+  for (int i = 0; i < 2 * C; i++) stats[i] = (float)st[i];
+  const float inv_m = 1.0f / (float)rows;
+  // ---- forward
+  memset(y.data(), 0x7f, y.size() * sizeof(T));
+  for (int b = 0; b < nblocks; b++)
+    for (int t = 0; t < threads; t++) {
+      const int grp = t % cvec;
+      float mean[V], invstd[V], var[V], scale[V], shift[V];
+      bn_moments<V>(stats.data(), C, grp, inv_m, eps, mean, invstd, var);
+      for (int k = 0; k < V; k++) {
+        scale[k] = Conv<T>::from(gamma[grp * V + k]) * invstd[k];
+        shift[k] = Conv<T>::from(beta[grp * V + k]) - mean[k] * scale[k];
+      }
+      bn_apply_thread<T, 4>(z.data(), with_res ? res.data() : nullptr, y.data(), rows, cvec, rpb, grp, t / cvec, (size_t)b,
+                            (size_t)nblocks, scale, shift, relu);
+    }
+  std::vector<double> mean(C), invstd(C);
+  for (int c = 0; c < C; c++) {
+    mean[c] = rsum[c] / rows;
+    double var = rsq[c] / rows - mean[c] * mean[c];
+    invstd[c] = 1.0 / sqrt((var > 0 ? var : 0) + eps);
+  }
+  const double tol_y = bf ? 2e-2 : 2e-4;
+  for (size_t i = 0; i < rows * C; i++) {
+    const int c = (int)(i % C);
+    double v = (Conv<T>::from(z[i]) - mean[c]) * invstd[c] * Conv<T>::from(gamma[c]) + Conv<T>::from(beta[c]);
+    if (with_res) v += Conv<T>::from(res[i]);
+    if (relu && v < 0) v = 0;
+    CHECK(fabs(Conv<T>::from(y[i]) - v) <= tol_y * (1.0 + fabs(v)), "%s bn fwd rows=%zu C=%d i=%zu got %f want %f", Conv<T>::name(), rows, C,
+          i, Conv<T>::from(y[i]), v);
+  }
+  // ---- backward
+  std::vector<double> gs(2 * C, 0.0), r1(C, 0.0), r2(C, 0.0);
+  for (int b = 0; b < nblocks; b++)
+    for (int t = 0; t < threads; t++) {
+      const int grp = t % cvec;
+      float mn[V], is[V], var[V], acc[2 * V];
+      bn_moments<V>(stats.data(), C, grp, inv_m, eps, mn, is, var);
+      for (int k = 0; k < 2 * V; k++) acc[k] = 0.f;
+      bn_bwd_reduce_thread<T, 2>(gy.data(), y.data(), z.data(), rows, cvec, rpb, grp, t / cvec, (size_t)b, (size_t)nblocks, mn, is, relu, acc);
+      for (int k = 0; k < V; k++) {
+        gs[grp * V + k] += acc[k];
+        gs[C + grp * V + k] += acc[V + k];
+      }
+    }
+  for (size_t i = 0; i < rows * C; i++) {
+    const int c = (int)(i % C);
+    double dy = (!relu || Conv<T>::from(y[i]) > 0.f) ? Conv<T>::from(gy[i]) : 0.0;
+    r1[c] += dy;
+    r2[c] += dy * (Conv<T>::from(z[i]) - mean[c]) * invstd[c];
+  }
+  for (int c = 0; c < C; c++) {
+    CHECK(fabs(gs[c] - r1[c]) <= 2e-3 * (1.0 + fabs(r1[c])), "%s bn s1 c=%d %f vs %f", Conv<T>::name(), c, gs[c], r1[c]);
+    CHECK(fabs(gs[C + c] - r2[c]) <= 2e-3 * (1.0 + fabs(r2[c])), "%s bn s2 c=%d %f vs %f", Conv<T>::name(), c, gs[C + c], r2[c]);
+  }
+  std::vector<float> gsum(2 * C);
+  for (int i = 0; i < 2 * C; i++) gsum[i] = (float)gs[i];
+  memset(gz.data(), 0x7f, gz.size() * sizeof(T));
+  memset(gres.data(), 0x7f, gres.size() * sizeof(T));
+  for (int b = 0; b < nblocks; b++)
+    for (int t = 0; t < threads; t++) {
+      const int grp = t % cvec;
+      float mn[V], is[V], var[V], a[V], c1[V], c2[V];
+      bn_moments<V>(stats.data(), C, grp, inv_m, eps, mn, is, var);
+      for (int k = 0; k < V; k++) {
+        a[k] = Conv<T>::from(gamma[grp * V + k]) * is[k];
+        c1[k] = gsum[grp * V + k] * inv_m;
+        c2[k] = gsum[C + grp * V + k] * inv_m;
+      }
+      bn_bwd_apply_thread<T, 2>(gy.data(), y.data(), z.data(), gz.data(), with_res ? gres.data() : nullptr, rows, cvec, rpb, grp,
+                                t / cvec, (size_t)b, (size_t)nblocks, mn, is, a, c1, c2, relu);
+    }
+  const double tol_g = bf ? 2e-2 : 5e-4;
+  for (size_t i = 0; i < rows * C; i++) {
+    const int c = (int)(i % C);
+    double dy = (!relu || Conv<T>::from(y[i]) > 0.f) ? Conv<T>::from(gy[i]) : 0.0;
+    double xhat = (Conv<T>::from(z[i]) - mean[c]) * invstd[c];
+    double want = Conv<T>::from(gamma[c]) * invstd[c] * (dy - r1[c] / rows - xhat * r2[c] / rows);
+    CHECK(fabs(Conv<T>::from(gz[i]) - want) <= tol_g * (1.0 + fabs(want)), "%s bn bwd rows=%zu C=%d i=%zu got %f want %f", Conv<T>::name(),
+          rows, C, i, Conv<T>::from(gz[i]), want);
+    if (with_res) CHECK(same(gres[i], Conv<T>::to((float)dy)), "%s bn gres i=%zu", Conv<T>::name(), i);
+  }
+}
+
+template <typename T>
 static void run_all() {
   constexpr int V = Vec<T>::N;
   // rows chosen around the batch boundaries: fewer rows than one block step, exact multiples, ragged tails
@@ -169,6 +293,19 @@ static void run_all() {
   test_pool<T>(3, 8, 8, 8 * V, 3);
   test_pool<T>(2, 14, 14, 64, 5);
   test_pool<T>(1, 6, 10, 512, 2);
+  // BatchNorm family: channel counts of a ResNet-50 (64 .. 2048), ragged row counts, with/without ReLU and residual
+  const int bnC[] = {V, 64, 256, V * 256 > 2048 ? 2048 : V * 256};
+  for (int C : bnC) {
+    const int rpb = ((256 / (C / V)) * (C / V)) / (C / V);
+    // (a handful of rows per channel makes the variance itself ill-conditioned: start at 33)
+    const size_t rowsv[] = {33, (size_t)rpb * 5 + 33, 257, 1000};
+    for (size_t rows : rowsv) {
+      if (rows * C > (1u << 20)) continue;
+      test_bn<T>(rows, C, 3, true, false);
+      test_bn<T>(rows, C, 2, true, true);
+      test_bn<T>(rows, C, 1, false, false);
+    }
+  }
 }
 
 int main() {
