@@ -4,9 +4,13 @@ from __future__ import annotations
 import torch
 from torch import nn
 
+from ..ops.fused_nn import conv_bn_act
+
 
 class Bottleneck(nn.Module):
     expansion = 4
+
+    fused = False     # set by ResNet(fused=True): conv + BatchNorm + ReLU (+ residual) through bagua_net_b200.ops.fused_nn
 
     def __init__(self, cin, width, stride=1, down=None):
         super().__init__()
@@ -20,6 +24,11 @@ class Bottleneck(nn.Module):
         self.down = down
 
     def forward(self, x):
+        if self.fused:
+            idt = x if self.down is None else conv_bn_act(x, self.down[0], self.down[1], relu=False)
+            out = conv_bn_act(x, self.conv1, self.bn1)
+            out = conv_bn_act(out, self.conv2, self.bn2)
+            return conv_bn_act(out, self.conv3, self.bn3, relu=True, res=idt)
         idt = x if self.down is None else self.down(x)
         out = self.relu(self.bn1(self.conv1(x)))
         out = self.relu(self.bn2(self.conv2(out)))
@@ -29,6 +38,8 @@ class Bottleneck(nn.Module):
 
 class BasicBlock(nn.Module):
     expansion = 1
+
+    fused = False
 
     def __init__(self, cin, width, stride=1, down=None):
         super().__init__()
@@ -40,6 +51,10 @@ class BasicBlock(nn.Module):
         self.down = down
 
     def forward(self, x):
+        if self.fused:
+            idt = x if self.down is None else conv_bn_act(x, self.down[0], self.down[1], relu=False)
+            out = conv_bn_act(x, self.conv1, self.bn1)
+            return conv_bn_act(out, self.conv2, self.bn2, relu=True, res=idt)
         idt = x if self.down is None else self.down(x)
         out = self.relu(self.bn1(self.conv1(x)))
         out = self.bn2(self.conv2(out))
@@ -47,8 +62,9 @@ class BasicBlock(nn.Module):
 
 
 class ResNet(nn.Module):
-    def __init__(self, block, layers, num_classes: int = 1000, base: int = 64):
+    def __init__(self, block, layers, num_classes: int = 1000, base: int = 64, fused: bool = False):
         super().__init__()
+        self.fused = fused
         self.cin = base
         self.conv1 = nn.Conv2d(3, base, 7, 2, 3, bias=False)
         self.bn1 = nn.BatchNorm2d(base)
@@ -66,6 +82,8 @@ class ResNet(nn.Module):
             elif isinstance(m, nn.BatchNorm2d):
                 nn.init.ones_(m.weight)
                 nn.init.zeros_(m.bias)
+            elif isinstance(m, (Bottleneck, BasicBlock)):
+                m.fused = fused
 
     def _make(self, block, width, n, stride):
         down = None
@@ -78,6 +96,10 @@ class ResNet(nn.Module):
         return nn.Sequential(*blocks)
 
     def forward(self, x):
+        if self.fused:
+            x = self.maxpool(conv_bn_act(x, self.conv1, self.bn1))
+            x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
+            return self.fc(torch.flatten(self.avgpool(x), 1))
         x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
         x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
         return self.fc(torch.flatten(self.avgpool(x), 1))

@@ -32,6 +32,11 @@ def _L():
         _lib.bnet_nn_relu_bwd_bias_grad.argtypes = [vp, vp, vp, vp, ll, i, i, vp]
         _lib.bnet_nn_bias_relu_pool_fwd.argtypes = [vp, vp, vp, vp, i, i, i, i, i, vp]
         _lib.bnet_nn_pool_relu_bwd_bias_grad.argtypes = [vp, vp, vp, vp, i, i, i, i, i, vp]
+        f = C.c_float
+        _lib.bnet_nn_bn_stats.argtypes = [vp, vp, ll, i, i, vp]
+        _lib.bnet_nn_bn_apply.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, ll, i, f, f, i, i, vp]
+        _lib.bnet_nn_bn_bwd_reduce.argtypes = [vp, vp, vp, vp, vp, ll, i, f, i, i, vp]
+        _lib.bnet_nn_bn_bwd_apply.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ll, i, f, i, i, vp]
     return _lib
 
 
@@ -122,6 +127,73 @@ class _ConvBiasReLUPool(torch.autograd.Function):
         return gx, gw, gb.to(w.dtype), None, None
 
 
+class _ConvBNAct(torch.autograd.Function):
+    """y = relu?(batch_norm_train(conv(x, w)) (+ res)) — csrc/cuda/nn_kernels.cu, BatchNorm family."""
+
+    @staticmethod
+    def forward(ctx, x, w, gamma, beta, res, running_mean, running_var, stride, padding, eps, momentum, relu):
+        z = _conv(x, w, stride, padding)
+        if not _nhwc(z):
+            z = z.contiguous(memory_format=torch.channels_last)
+        n, c, h, wd = z.shape
+        rows, dt, L = n * h * wd, _DT[z.dtype], _L()
+        stats = torch.zeros(2 * c, device=z.device, dtype=torch.float32)
+        _chk(L.bnet_nn_bn_stats(z.data_ptr(), stats.data_ptr(), rows, c, dt, _stream()), "bn_stats")
+        if res is not None and not _nhwc(res):
+            res = res.contiguous(memory_format=torch.channels_last)
+        y = torch.empty_like(z)
+        _chk(L.bnet_nn_bn_apply(z.data_ptr(), res.data_ptr() if res is not None else None, y.data_ptr(), stats.data_ptr(),
+                                gamma.data_ptr(), beta.data_ptr(),
+                                running_mean.data_ptr() if running_mean is not None else None,
+                                running_var.data_ptr() if running_var is not None else None,
+                                rows, c, eps, momentum, 1 if relu else 0, dt, _stream()), "bn_apply")
+        ctx.save_for_backward(x, w, z, y, gamma, stats)
+        ctx.cfg = (stride, padding, eps, relu, res is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, z, y, gamma, stats = ctx.saved_tensors
+        stride, padding, eps, relu, has_res = ctx.cfg
+        if not _nhwc(gy):
+            gy = gy.contiguous(memory_format=torch.channels_last)
+        n, c, h, wd = z.shape
+        rows, dt, L = n * h * wd, _DT[z.dtype], _L()
+        gsum = torch.zeros(2 * c, device=z.device, dtype=torch.float32)
+        _chk(L.bnet_nn_bn_bwd_reduce(gy.data_ptr(), y.data_ptr(), z.data_ptr(), stats.data_ptr(), gsum.data_ptr(), rows, c, eps,
+                                     1 if relu else 0, dt, _stream()), "bn_bwd_reduce")
+        gz = torch.empty_like(z)
+        gres = torch.empty_like(z) if has_res else None
+        dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(gamma)
+        _chk(L.bnet_nn_bn_bwd_apply(gy.data_ptr(), y.data_ptr(), z.data_ptr(), gz.data_ptr(),
+                                    gres.data_ptr() if has_res else None, stats.data_ptr(), gsum.data_ptr(), gamma.data_ptr(),
+                                    dgamma.data_ptr(), dbeta.data_ptr(), rows, c, eps, 1 if relu else 0, dt, _stream()),
+             "bn_bwd_apply")
+        gx, gw = _conv_backward(gz, x, w, stride, padding, ctx.needs_input_grad[0])
+        return gx, gw, dgamma, dbeta, gres, None, None, None, None, None, None, None
+
+
+def conv_bn_act(x: torch.Tensor, conv: nn.Conv2d, bn: nn.BatchNorm2d, relu: bool = True, res: torch.Tensor | None = None):
+    """relu?(bn(conv(x)) (+ res)) for one ResNet stage.  Training mode with channels_last bf16/fp32 tensors runs the fused
+    kernels (statistics, normalise + affine + residual + ReLU in one pass, two-kernel backward); anything else
+    (eval mode, exotic configurations) takes the eager PyTorch chain."""
+    c = conv.out_channels
+    vec = 8 if x.dtype == torch.bfloat16 else 4
+    if (bn.training and _supported(x, c) and c // vec <= 256 and conv.bias is None and conv.groups == 1
+            and conv.dilation == (1, 1) and bn.affine and bn.track_running_stats and bn.momentum is not None
+            and bn.weight.dtype == x.dtype and bn.running_mean.dtype == x.dtype):
+        if not _nhwc(x):
+            x = x.contiguous(memory_format=torch.channels_last)
+        if bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        return _ConvBNAct.apply(x, conv.weight, bn.weight, bn.bias, res, bn.running_mean, bn.running_var,
+                                list(conv.stride), list(conv.padding), float(bn.eps), float(bn.momentum), bool(relu))
+    y = bn(conv(x))
+    if res is not None:
+        y = y + res
+    return torch.relu(y) if relu else y
+
+
 def self_check(device=None, verbose: bool = False) -> bool:
     """One small fused block (with and without pooling), forward and backward, against the eager PyTorch chain in
     bf16.  Cheap (a few ms); lets a training script fall back to eager layers instead of training on wrong
@@ -158,6 +230,59 @@ def self_check(device=None, verbose: bool = False) -> bool:
     except Exception as e:      # noqa: BLE001 - any failure means "do not use the fused path"
         if verbose:
             print(f"[fused_nn.self_check] failed: {e!r}")
+        return False
+
+
+def self_check_bn(device=None, verbose: bool = False) -> bool:
+    """The BatchNorm family (conv_bn_act) against the eager chain, bf16, forward / backward / running statistics."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    try:
+        g = torch.Generator(device=dev).manual_seed(4321)
+        for cin, cout, hw, k, relu, with_res in ((16, 64, 14, 3, True, False), (64, 256, 8, 1, True, True), (32, 2048, 4, 1, False, False)):
+            conv = nn.Conv2d(cin, cout, k, 1, k // 2, bias=False).to(dev).to(torch.bfloat16).to(memory_format=torch.channels_last)
+            bn_a = nn.BatchNorm2d(cout).to(dev).to(torch.bfloat16)
+            with torch.no_grad():
+                bn_a.weight.copy_(torch.rand(cout, device=dev, generator=g) + 0.5)
+                bn_a.bias.copy_(torch.randn(cout, device=dev, generator=g) * 0.1)
+            import copy
+
+            bn_b = copy.deepcopy(bn_a)
+            x = torch.randn(4, cin, hw, hw, device=dev, generator=g).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            res = torch.randn(4, cout, hw, hw, device=dev, generator=g).to(torch.bfloat16).contiguous(
+                memory_format=torch.channels_last) if with_res else None
+            xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+            ra = res.clone().requires_grad_(True) if with_res else None
+            rb = res.clone().requires_grad_(True) if with_res else None
+            ya = conv_bn_act(xa, conv, bn_a, relu=relu, res=ra)
+            go = torch.randn(ya.shape, device=dev, generator=g).to(torch.bfloat16)
+            ya.backward(go)
+            ga = [xa.grad.float().clone(), conv.weight.grad.float().clone(), bn_a.weight.grad.float().clone(), bn_a.bias.grad.float().clone()]
+            if with_res:
+                ga.append(ra.grad.float().clone())
+            conv.zero_grad(set_to_none=True)
+            yb = bn_b(conv(xb))
+            if with_res:
+                yb = yb + rb
+            if relu:
+                yb = torch.relu(yb)
+            yb.backward(go)
+            gb = [xb.grad.float(), conv.weight.grad.float(), bn_b.weight.grad.float(), bn_b.bias.grad.float()]
+            if with_res:
+                gb.append(rb.grad.float())
+            torch.cuda.synchronize(dev)
+            rel = lambda a, b: ((a - b).norm() / b.norm().clamp_min(1e-6)).item()      # noqa: E731
+            errs = [rel(ya.float(), yb.float())] + [rel(a, b) for a, b in zip(ga, gb)]
+            errs += [rel(bn_a.running_mean.float(), bn_b.running_mean.float()), rel(bn_a.running_var.float(), bn_b.running_var.float())]
+            if verbose:
+                print(f"[fused_nn.self_check_bn] {cin}->{cout} k{k} {hw}x{hw} relu={relu} res={with_res} relative L2 errors: {errs}")
+            if not all(e == e and e < 0.15 for e in errs):
+                return False
+            if int(bn_a.num_batches_tracked.item()) != 1:
+                return False
+        return True
+    except Exception as e:      # noqa: BLE001
+        if verbose:
+            print(f"[fused_nn.self_check_bn] failed: {e!r}")
         return False
 
 

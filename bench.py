@@ -205,18 +205,19 @@ def main() -> int:
     torch.manual_seed(1234)
 
     # our arm trains the model built from our fused conv blocks; the stock-NCCL arms train the plain eager model
-    fused = args.comm == "bnet" and not args.no_fused and args.model.startswith("vgg")
+    fused = args.comm == "bnet" and not args.no_fused and args.model.startswith(("vgg", "resnet"))
     fused_note = None
     if fused:
         # the native layer kernels are checked against the eager chain on this very GPU before they are trusted
         # with the benchmark; all ranks take the same decision
         from bagua_net_b200.ops import fused_nn
 
-        ok = torch.tensor([1 if fused_nn.self_check(dev) else 0], device=dev, dtype=torch.int32)
+        check = fused_nn.self_check if args.model.startswith("vgg") else fused_nn.self_check_bn
+        ok = torch.tensor([1 if check(dev) else 0], device=dev, dtype=torch.int32)
         if world > 1:
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if int(ok.item()) == 0:
-            fused, fused_note = False, "fused conv blocks failed their self-check on this machine: eager layers used"
+            fused, fused_note = False, "fused layer kernels failed their self-check on this machine: eager layers used"
             if rank == 0:
                 print(f"[bench] WARNING: {fused_note}", file=sys.stderr)
     model = build_model(args.model, **({"fused": True} if fused else {}))

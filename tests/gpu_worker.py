@@ -432,6 +432,87 @@ def job_fused_nn():
     print("fused_nn ok", flush=True)
 
 
+def job_fused_bn():
+    """conv_bn_act (training-mode BatchNorm + ReLU + residual fused behind a convolution) vs the eager chain."""
+    import copy
+
+    from bagua_net_b200.models import build_model
+    from bagua_net_b200.ops import fused_nn
+    from bagua_net_b200.ops.fused_nn import conv_bn_act
+
+    torch.cuda.set_device(0)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    for dtype, tol in ((torch.float32, 2e-3), (torch.bfloat16, 6e-2)):
+        for (cin, cout, hw, k, stride, relu, with_res) in [(3, 64, 32, 7, 2, True, False), (64, 64, 16, 3, 1, True, False),
+                                                          (64, 256, 16, 1, 1, True, True), (256, 512, 8, 1, 2, False, False),
+                                                          (128, 2048, 4, 1, 1, True, True)]:
+            if dtype == torch.float32 and cout > 1024:
+                continue                      # fp32: 4 channels per vector, at most 1024 channels
+            torch.manual_seed(cin + cout)
+            conv = torch.nn.Conv2d(cin, cout, k, stride, k // 2, bias=False).cuda().to(dtype).to(memory_format=torch.channels_last)
+            bn_a = torch.nn.BatchNorm2d(cout).cuda().to(dtype)
+            with torch.no_grad():
+                bn_a.weight.copy_(torch.rand(cout) + 0.5)
+                bn_a.bias.copy_(torch.randn(cout) * 0.1)
+            bn_b = copy.deepcopy(bn_a)
+            x = torch.randn(6, cin, hw, hw, device="cuda").to(dtype).contiguous(memory_format=torch.channels_last)
+            ho = (hw + 2 * (k // 2) - k) // stride + 1
+            res = torch.randn(6, cout, ho, ho, device="cuda").to(dtype).contiguous(memory_format=torch.channels_last) if with_res else None
+            xa, xb = x.clone().requires_grad_(cin != 3), x.clone().requires_grad_(cin != 3)
+            ra = res.clone().requires_grad_(True) if with_res else None
+            rb = res.clone().requires_grad_(True) if with_res else None
+            before = fused_nn.LAUNCHES
+            ya = conv_bn_act(xa, conv, bn_a, relu=relu, res=ra)
+            assert fused_nn.LAUNCHES == before + 2, "fused BatchNorm kernels did not run"
+            go = torch.randn_like(ya)
+            ya.backward(go)
+            ga = {"w": conv.weight.grad.float().clone(), "gamma": bn_a.weight.grad.float().clone(), "beta": bn_a.bias.grad.float().clone()}
+            if cin != 3:
+                ga["x"] = xa.grad.float().clone()
+            if with_res:
+                ga["res"] = ra.grad.float().clone()
+            conv.zero_grad(set_to_none=True)
+            yb = bn_b(conv(xb))
+            if with_res:
+                yb = yb + rb
+            if relu:
+                yb = torch.relu(yb)
+            yb.backward(go)
+            gb = {"w": conv.weight.grad.float(), "gamma": bn_b.weight.grad.float(), "beta": bn_b.bias.grad.float()}
+            if cin != 3:
+                gb["x"] = xb.grad.float()
+            if with_res:
+                gb["res"] = rb.grad.float()
+            torch.cuda.synchronize()
+            rel = lambda a, b: ((a - b).norm() / b.norm().clamp_min(1e-6)).item()      # noqa: E731
+            e = rel(ya.float(), yb.float())
+            assert e < tol, f"fwd {dtype} {cin}->{cout}: {e}"
+            for name in ga:
+                e = rel(ga[name], gb[name])
+                assert e < tol, f"bwd {name} {dtype} {cin}->{cout} k{k} relu={relu} res={with_res}: {e}"
+            assert rel(bn_a.running_mean.float(), bn_b.running_mean.float()) < tol
+            assert rel(bn_a.running_var.float(), bn_b.running_var.float()) < tol
+            assert int(bn_a.num_batches_tracked) == int(bn_b.num_batches_tracked) == 1
+    assert fused_nn.self_check_bn(verbose=True)
+    # whole model: fused ResNet-18 == eager ResNet-18 in fp32 (same weights, same batch)
+    torch.manual_seed(5)
+    a = build_model("resnet18", fused=True, num_classes=10).cuda().to(memory_format=torch.channels_last)
+    b = build_model("resnet18", num_classes=10).cuda()
+    b.load_state_dict(a.state_dict())
+    x = torch.randn(8, 3, 64, 64, device="cuda")
+    y = torch.randint(0, 10, (8,), device="cuda")
+    la = torch.nn.functional.cross_entropy(a(x.contiguous(memory_format=torch.channels_last)), y)
+    lb = torch.nn.functional.cross_entropy(b(x), y)
+    la.backward()
+    lb.backward()
+    assert abs(la.item() - lb.item()) < 1e-3, (la.item(), lb.item())
+    for (n1, pa), (n2, pb) in zip(a.named_parameters(), b.named_parameters()):
+        e = ((pa.grad - pb.grad).norm() / pb.grad.norm().clamp_min(1e-6)).item()
+        assert e < 2e-2, f"resnet18 grad {n1}: {e}"
+    print("fused_bn ok", flush=True)
+
+
 def job_pack_cast():
     from bagua_net_b200.ops import pack_cast
     from bagua_net_b200.parallel import SymmComm
