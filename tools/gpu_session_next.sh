@@ -14,6 +14,8 @@ TAILN=6 step gpu_tests 600 python -m pytest tests -q -m gpu -x
 TAILN=40 step nn_kernels 120 python tools/nn_kernel_bench.py
 CUT=2000 TAILN=2 step bench1 300 python bench.py --gpus 1 --steps 30 --warmup 5
 CUT=2000 TAILN=2 step bench1_noprefetch 200 python bench.py --gpus 1 --steps 30 --warmup 5 --no-prefetch --no-extra
+CUT=2000 TAILN=2 step bench1_resnet50 300 python bench.py --gpus 1 --steps 30 --warmup 5 --model resnet50 --no-extra
+CUT=2000 TAILN=2 step bench1_resnet50_eager 300 python bench.py --gpus 1 --steps 30 --warmup 5 --model resnet50 --no-extra --no-fused
 TAILN=30 step step_profile 200 python tools/step_profile.py --fused
 step ncu_nn 400 ncu --set full --clock-control none --import-source on -k "regex:relu_bwd_bias_grad|pool_relu_bwd" -c 6 -o $OUT/nn_bwd python tools/nn_kernel_bench.py --iters 1 --warmup 0
 step ncu_summary 120 bash tools/summarize_ncu.sh $OUT/nn_bwd.ncu-rep $OUT/nn_bwd
