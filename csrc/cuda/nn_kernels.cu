@@ -214,7 +214,8 @@ BNET_API int bnet_nn_relu_bwd_bias_grad(const void* gy, const void* y, void* gz,
   const int cvec = C / V;
   const int threads = (256 / cvec) * cvec;
   const int rpb = threads / cvec;
-  long long want = (rows + rpb - 1) / rpb;
+  // at least 8 rows per thread before another block is worth its C atomics (small late layers: few rows, many channels)
+  long long want = (rows + 8LL * rpb - 1) / (8LL * rpb);
   int grid = (int)(want < 148 * 8 ? want : 148 * 8);
   if (grid < 1) grid = 1;
   size_t smem = (size_t)threads * V * sizeof(float);
@@ -251,7 +252,8 @@ BNET_API int bnet_nn_pool_relu_bwd_bias_grad(const void* gp, const void* idx, vo
   const int threads = (256 / cvec) * cvec;
   const int rpb = threads / cvec;
   long long rows = (long long)N * (H / 2) * (W / 2);
-  long long want = (rows + rpb - 1) / rpb;
+  // at least 8 rows per thread before another block is worth its C atomics (small late layers: few rows, many channels)
+  long long want = (rows + 8LL * rpb - 1) / (8LL * rpb);
   int grid = (int)(want < 148 * 8 ? want : 148 * 8);
   if (grid < 1) grid = 1;
   size_t smem = (size_t)threads * V * sizeof(float);
@@ -272,7 +274,8 @@ RowGrid row_grid(long long rows, int cvec, int V, int accs) {
   RowGrid g;
   g.threads = (256 / cvec) * cvec;
   const int rpb = g.threads / cvec;
-  long long want = (rows + rpb - 1) / rpb;
+  // at least 8 rows per thread before another block is worth its C atomics (small late layers: few rows, many channels)
+  long long want = (rows + 8LL * rpb - 1) / (8LL * rpb);
   g.grid = (int)(want < 148 * 8 ? want : 148 * 8);
   if (g.grid < 1) g.grid = 1;
   g.smem = (size_t)g.threads * V * sizeof(float) * (accs ? 1 : 0);
