@@ -153,6 +153,10 @@ def test_collectives_on_ordinary_tensors_2gpu():
     _run_worker("collectives_any", 2, timeout=240)
 
 
+def test_fused_batchnorm_blocks_match_eager():
+    _run_worker("fused_bn", 1, timeout=240)
+
+
 def test_executor_fp8_e5m2_ops():
     _run_worker("executor_e5m2", 1, timeout=120)
 
@@ -179,7 +183,3 @@ def test_executor_single_grid_mode(env):
     """BNET_EXEC_GRID=1: all cluster queues served by ONE resident grid on one stream (one launch per wake-up)."""
     _run_worker("executor", 1, extra_env=env, timeout=120)
     _run_worker("executor_idle", 1, extra_env=dict(env, BNET_KERNEL_IDLE_US="100"), timeout=60)
-
-
-def test_fused_batchnorm_blocks_match_eager():
-    _run_worker("fused_bn", 1, timeout=240)
