@@ -92,7 +92,42 @@ def main():
             t[1] += us
             print(f"  {name:28s} {c:4d} {hw:4d}x{hw:<3d} {traffic / 1e6:8.1f} {us:8.1f} {gbs:8.0f} {gbs / peak:6.2f}")
         del z
-    print("# per step (all 13 layers):")
+    # ---- BatchNorm family at the ResNet-50 shapes (C, H=W of the convolution output)
+    RESNET = [(64, 112), (64, 56), (256, 56), (128, 28), (512, 28), (256, 14), (1024, 14), (512, 7), (2048, 7)]
+    vp, ll, i, f = fused_nn.C.c_void_p, fused_nn.C.c_longlong, fused_nn.C.c_int, fused_nn.C.c_float
+    print("# BatchNorm family (stats, apply+ReLU+residual, backward reduce, backward apply)")
+    for c, hw in RESNET:
+        rows = N * hw * hw
+        z = torch.randn(N, c, hw, hw, device="cuda", dtype=dt).contiguous(memory_format=torch.channels_last)
+        res, gy = torch.randn_like(z), torch.randn_like(z)
+        y, gz, gres = torch.empty_like(z), torch.empty_like(z), torch.empty_like(z)
+        gamma, beta = torch.ones(c, device="cuda", dtype=dt), torch.zeros(c, device="cuda", dtype=dt)
+        rm, rv = torch.zeros(c, device="cuda", dtype=dt), torch.ones(c, device="cuda", dtype=dt)
+        dg, db = torch.empty_like(gamma), torch.empty_like(gamma)
+        stats = torch.zeros(2 * c, device="cuda", dtype=torch.float32)
+        gsum = torch.zeros(2 * c, device="cuda", dtype=torch.float32)
+        nbytes = rows * c * 2
+        L.bnet_nn_bn_stats(z.data_ptr(), stats.data_ptr(), rows, c, 1, st())
+        cases = [
+            ("bn_stats", nbytes, lambda: L.bnet_nn_bn_stats(z.data_ptr(), stats.data_ptr(), rows, c, 1, st())),
+            ("bn_apply(+res+relu)", 3 * nbytes, lambda: L.bnet_nn_bn_apply(z.data_ptr(), res.data_ptr(), y.data_ptr(), stats.data_ptr(),
+                                                                          gamma.data_ptr(), beta.data_ptr(), rm.data_ptr(), rv.data_ptr(),
+                                                                          rows, c, 1e-5, 0.1, 1, 1, st())),
+            ("bn_bwd_reduce", 3 * nbytes, lambda: L.bnet_nn_bn_bwd_reduce(gy.data_ptr(), y.data_ptr(), z.data_ptr(), stats.data_ptr(),
+                                                                         gsum.data_ptr(), rows, c, 1e-5, 1, 1, st())),
+            ("bn_bwd_apply(+gres)", 5 * nbytes, lambda: L.bnet_nn_bn_bwd_apply(gy.data_ptr(), y.data_ptr(), z.data_ptr(), gz.data_ptr(),
+                                                                              gres.data_ptr(), stats.data_ptr(), gsum.data_ptr(),
+                                                                              gamma.data_ptr(), dg.data_ptr(), db.data_ptr(), rows, c,
+                                                                              1e-5, 1, 1, st())),
+        ]
+        for name, traffic, fn in cases:
+            us = timed(fn, a.iters, a.warmup)
+            gbs = traffic / us / 1e3
+            t = tot.setdefault(name, [0.0, 0.0])
+            t[0] += traffic
+            t[1] += us
+            print(f"  {name:28s} {c:4d} {hw:4d}x{hw:<3d} {traffic / 1e6:8.1f} {us:8.1f} {gbs:8.0f} {gbs / peak:6.2f}")
+    print("# totals over the listed layers:")
     for name, (traffic, us) in tot.items():
         print(f"  {name:28s} {traffic / 1e6:9.1f} MB {us:9.1f} us {traffic / us / 1e3:8.0f} GB/s {traffic / us / 1e3 / peak:6.2f}")
 
