@@ -70,7 +70,7 @@ static void test_relu_bwd(size_t rows, int C, int nblocks) {
     float a = frand();
     y[i] = Conv<T>::to(a > 0.3f ? a : 0.f);     // post-ReLU activations: many exact zeros
   }
-  memset(gz.data(), 0x7f, gz.size() * sizeof(T));   // sentinel: every element must be overwritten
+  memset((void*)gz.data(), 0x7f, gz.size() * sizeof(T));   // sentinel: every element must be overwritten
   std::vector<double> gb(C, 0.0);
   for (int b = 0; b < nblocks; b++)
     for (int t = 0; t < threads; t++) {
@@ -121,7 +121,7 @@ static void test_pool(int N, int H, int W, int C, int nblocks) {
         }
   // ---- backward through the codes
   const int threads = (256 / cvec) * cvec, rpb = threads / cvec;
-  memset(gz.data(), 0x7f, gz.size() * sizeof(T));
+  memset((void*)gz.data(), 0x7f, gz.size() * sizeof(T));
   std::vector<double> gb(C, 0.0), ref(C, 0.0);
   for (int b = 0; b < nblocks; b++)
     for (int t = 0; t < threads; t++) {
@@ -191,7 +191,7 @@ static void test_bn(size_t rows, int C, int nblocks, bool relu, bool with_res) {
   for (int i = 0; i < 2 * C; i++) stats[i] = (float)st[i];
   const float inv_m = 1.0f / (float)rows;
   // ---- forward
-  memset(y.data(), 0x7f, y.size() * sizeof(T));
+  memset((void*)y.data(), 0x7f, y.size() * sizeof(T));
   for (int b = 0; b < nblocks; b++)
     for (int t = 0; t < threads; t++) {
       const int grp = t % cvec;
@@ -245,8 +245,8 @@ static void test_bn(size_t rows, int C, int nblocks, bool relu, bool with_res) {
   }
   std::vector<float> gsum(2 * C);
   for (int i = 0; i < 2 * C; i++) gsum[i] = (float)gs[i];
-  memset(gz.data(), 0x7f, gz.size() * sizeof(T));
-  memset(gres.data(), 0x7f, gres.size() * sizeof(T));
+  memset((void*)gz.data(), 0x7f, gz.size() * sizeof(T));
+  memset((void*)gres.data(), 0x7f, gres.size() * sizeof(T));
   for (int b = 0; b < nblocks; b++)
     for (int t = 0; t < threads; t++) {
       const int grp = t % cvec;
