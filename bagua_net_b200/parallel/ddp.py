@@ -310,6 +310,16 @@ class BnetDDP(torch.nn.Module):
             shard = b.numel // self.comm.world
             b.master.copy_(b.param[self.comm.rank * shard:(self.comm.rank + 1) * shard].float())
 
+    def broadcast_buffers(self, src: int = 0) -> None:
+        """Copy rank `src`'s module buffers (BatchNorm running statistics, ...) to every rank — what torch DDP does
+        before each forward with broadcast_buffers=True.  Call it before evaluation / checkpointing; training itself
+        does not depend on it (batch statistics are local, like in DDP)."""
+        if self.comm.world == 1:
+            return
+        for b in self.module.buffers():
+            if b.is_cuda and b.numel():
+                self.comm.broadcast_tensor(b, src=src)
+
     def set_lr(self, lr: float):
         self.lr = lr
 
