@@ -143,3 +143,85 @@ def test_bench_clock_sampler_with_a_stubbed_nvml(monkeypatch):
     out = s.stop()
     assert out["sm_mhz"] == 1950.0 and out["sm_max_mhz"] == 1965.0 and out["samples"] >= 5
     assert out["reasons"] == ["sw_power_cap"]
+
+
+def test_symmcomm_tensor_collectives_logic_with_emulated_ranks():
+    """all_reduce / broadcast / all_gather / reduce_scatter on ordinary tensors are compositions of the heap kernels,
+    the barrier kernel and peer mappings (bagua_net_b200/parallel/comm.py).  Here the heap is CPU memory, the ranks are
+    threads, the barrier is a threading.Barrier and the all-reduce kernel is a stub — what is checked is the staging,
+    chunking, padding and slicing logic, with a stage small enough to force several chunks."""
+    import threading
+
+    import torch
+
+    from bagua_net_b200.parallel.comm import SymmComm
+
+    world = 4
+    bar = threading.Barrier(world)
+    comms = []
+    for r in range(world):
+        c = object.__new__(SymmComm)
+        c.world, c.rank = world, r
+        c._stage_buf = torch.zeros(16 * world * 40, dtype=torch.uint8)     # 2560 bytes: 640 floats per chunk
+        c.launches = 0
+        comms.append(c)
+    red_lock = threading.Lock()
+    pending = {}
+
+    for c in comms:
+        def peer_tensor(t, peer, c=c):
+            off = t.data_ptr() - c._stage_buf.data_ptr()
+            nbytes = t.numel() * t.element_size()
+            return comms[peer]._stage_buf[off:off + nbytes].view(t.dtype).view(t.shape)
+
+        def barrier(channel=2, stream=None):
+            bar.wait()
+
+        def all_reduce(st, op="sum", algo="auto", stream=None, c=c):
+            assert st.numel() * st.element_size() % (16 * world) == 0, "all-reduce quantum violated"
+            bar.wait()
+            with red_lock:
+                key = st.numel()
+                pending.setdefault(key, []).append(st)
+            bar.wait()
+            if c.rank == 0:
+                total = torch.stack([p.clone().float() for p in pending[st.numel()]]).sum(0)
+                for p in pending[st.numel()]:
+                    p.copy_(total.to(p.dtype))
+                pending.clear()
+            bar.wait()
+            return st
+
+        c.peer_tensor, c.barrier, c.all_reduce = peer_tensor, barrier, all_reduce
+
+    inputs = [torch.arange(3001, dtype=torch.float32) * (r + 1) for r in range(world)]
+    out = [None] * world
+    errs = []
+
+    def run(r):
+        try:
+            c = comms[r]
+            res = {}
+            res["ar"] = c.all_reduce_tensor(inputs[r].clone())
+            b = inputs[r].clone()
+            c.broadcast_tensor(b, src=2)
+            res["bc"] = b
+            res["ag"] = c.all_gather_tensor(inputs[r][:1501])
+            res["rs"] = c.reduce_scatter_tensor(inputs[r][:3000])
+            res["nc"] = c.all_reduce_tensor(torch.arange(35, dtype=torch.float32).view(5, 7).t() * (r + 1))   # non-contiguous
+            out[r] = res
+        except Exception as e:      # noqa: BLE001
+            errs.append(repr(e))
+            bar.abort()
+
+    ths = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t.start() for t in ths]
+    [t.join(60) for t in ths]
+    assert not errs, errs
+    total = sum(inputs)
+    for r in range(world):
+        assert torch.equal(out[r]["ar"], total)
+        assert torch.equal(out[r]["bc"], inputs[2])
+        assert torch.equal(out[r]["ag"], torch.stack([i[:1501] for i in inputs]))
+        assert torch.equal(out[r]["rs"], total[:3000].view(world, -1)[r])
+        assert torch.equal(out[r]["nc"], torch.arange(35, dtype=torch.float32).view(5, 7).t() * 10)
