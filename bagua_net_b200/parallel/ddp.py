@@ -21,6 +21,33 @@ import torch.distributed as dist
 from .comm import SymmComm
 
 
+def plan_buckets(numels, element_size: int, world: int, bucket_mb: float):
+    """Lay parameters out in the flat heap buffers.  Returns ([(start, numel, [(param index, offset), ...]), ...], total).
+
+    * gradients become ready roughly in reverse registration order, so buckets are filled in that order;
+    * every tensor starts on a 16-byte boundary (8 elements) inside the flat buffer;
+    * every bucket is a whole number of 16-byte vectors per rank (`quantum`), so the fused kernel can shard it 1/world;
+    * a bucket closes when the next tensor would push it past `bucket_mb`."""
+    quantum = 16 * world // element_size * 8
+    cap = int(bucket_mb * (1 << 20)) // element_size
+    plan = []
+    start, numel, members = 0, 0, []
+    offset = 0
+    for pi in reversed(range(len(numels))):
+        n = numels[pi]
+        if members and numel + n > cap:
+            numel = (numel + quantum - 1) // quantum * quantum
+            offset += numel
+            plan.append((start, numel, members))
+            start, numel, members = offset, 0, []
+        members.append((pi, start + numel))
+        numel += (n + 7) // 8 * 8
+    numel = (numel + quantum - 1) // quantum * quantum
+    offset += numel
+    plan.append((start, numel, members))
+    return plan, offset
+
+
 class _Bucket:
     __slots__ = ("params", "start", "numel", "ready", "grad", "param", "master", "mom")
 
@@ -55,28 +82,16 @@ class BnetDDP(torch.nn.Module):
         self.dtype = dtype
         es = params[0].element_size()
         world = dist.get_world_size(group) if dist.is_initialized() else 1
-        quantum = 16 * world // es * 8           # elements: whole 16-byte vectors per rank, generously aligned
-        # gradients become ready roughly in reverse registration order: bucket in that order
-        cap = int(bucket_mb * (1 << 20)) // es
+        plan, total = plan_buckets([p.numel() for p in params], es, world, bucket_mb)
         self.buckets: list[_Bucket] = []
-        cur = _Bucket()
-        offset = 0
         layout = []
-        for p in reversed(params):
-            n = p.numel()
-            if cur.params and cur.numel + n > cap:
-                cur.numel = (cur.numel + quantum - 1) // quantum * quantum
-                offset += cur.numel
-                self.buckets.append(cur)
-                cur = _Bucket()
-                cur.start = offset
-            layout.append((p, cur, cur.start + cur.numel))
-            cur.params.append(p)
-            cur.numel += (n + 7) // 8 * 8        # keep every tensor 16-byte aligned inside the flat buffer
-        cur.numel = (cur.numel + quantum - 1) // quantum * quantum
-        offset += cur.numel
-        self.buckets.append(cur)
-        total = offset
+        for start, numel, members in plan:
+            b = _Bucket()
+            b.start, b.numel = start, numel
+            for pi, off in members:
+                b.params.append(params[pi])
+                layout.append((params[pi], b, off))
+            self.buckets.append(b)
 
         dev = params[0].device
         if comm is None:

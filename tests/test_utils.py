@@ -225,3 +225,38 @@ def test_symmcomm_tensor_collectives_logic_with_emulated_ranks():
         assert torch.equal(out[r]["ag"], torch.stack([i[:1501] for i in inputs]))
         assert torch.equal(out[r]["rs"], total[:3000].view(world, -1)[r])
         assert torch.equal(out[r]["nc"], torch.arange(35, dtype=torch.float32).view(5, 7).t() * 10)
+
+
+def test_ddp_bucket_plan_invariants():
+    """Flat-buffer layout of the DDP engine (bagua_net_b200/parallel/ddp.py::plan_buckets)."""
+    import random
+
+    from bagua_net_b200.parallel.ddp import plan_buckets
+
+    rnd = random.Random(3)
+    for world in (1, 2, 4, 8):
+        for es in (2, 4):
+            for bucket_mb in (0.01, 0.25, 64.0):
+                numels = [rnd.choice([1, 3, 64, 1000, 4096, 25088 * 16, 512 * 512 * 9]) for _ in range(rnd.randint(1, 40))]
+                plan, total = plan_buckets(numels, es, world, bucket_mb)
+                quantum = 16 * world // es * 8
+                seen, end = [], 0
+                for start, numel, members in plan:
+                    assert start == end and numel % quantum == 0 and numel > 0
+                    assert (numel // world) * es % 16 == 0                 # every rank's shard is whole 16-byte vectors
+                    pos = start
+                    for pi, off in members:
+                        assert off >= pos and off % 8 == 0 and off + numels[pi] <= start + numel
+                        pos = off + numels[pi]
+                        seen.append(pi)
+                    cap = int(bucket_mb * (1 << 20)) // es
+                    assert len(members) == 1 or sum((numels[pi] + 7) // 8 * 8 for pi, _ in members) <= cap + quantum
+                    end = start + numel
+                assert total == end
+                assert seen == list(reversed(range(len(numels))))           # reverse registration order, nothing lost
+    # the flagship: VGG16's 32 tensors with 64 MB buckets
+    vgg = [64 * 3 * 9, 64, 64 * 64 * 9, 64, 128 * 64 * 9, 128, 128 * 128 * 9, 128, 256 * 128 * 9, 256, 256 * 256 * 9, 256,
+           256 * 256 * 9, 256, 512 * 256 * 9, 512, 512 * 512 * 9, 512, 512 * 512 * 9, 512, 512 * 512 * 9, 512, 512 * 512 * 9, 512,
+           512 * 512 * 9, 512, 25088 * 4096, 4096, 4096 * 4096, 4096, 4096 * 1000, 1000]
+    plan, total = plan_buckets(vgg, 2, 8, 64.0)
+    assert sum(vgg) <= total < sum(vgg) + 40 * 1024 and len(plan) >= 3
