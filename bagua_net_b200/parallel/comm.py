@@ -73,6 +73,7 @@ def _declare(lib):
     lib.bnet_barrier.argtypes = [vp, i, vp]
     lib.bnet_fused_allreduce_sgd.argtypes = [vp, sz, sz, sz, i, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp,
                                              i, i, i, vp]
+    lib.bnet_fused_allreduce_sgd_hp.argtypes = [vp, sz, sz, sz, i, vp, vp, vp, i, i, i, vp]
     lib.bnet_pack_cast.argtypes = [vp, i, vp, i, i, C.c_float, C.c_uint64, vp]
 
 
@@ -200,12 +201,23 @@ class SymmComm:
 
     def fused_allreduce_sgd(self, grad: torch.Tensor, param: torch.Tensor, master: torch.Tensor, mom: torch.Tensor,
                             lr: float, momentum: float, weight_decay: float, grad_scale: float | None = None,
-                            zero_grads: bool = True, channel: int = 0, nblocks: int = 0, stream=None):
+                            zero_grads: bool = True, channel: int = 0, nblocks: int = 0, stream=None,
+                            hp: torch.Tensor | None = None):
         """One kernel: mean-reduce ``grad`` across ranks, SGD-update this rank's fp32 shard
-        (``master``/``mom``: numel/world each) and write the new ``param`` on every rank."""
+        (``master``/``mom``: numel/world each) and write the new ``param`` on every rank.
+        ``hp``: optional 4-element fp32 CUDA tensor {lr, momentum, weight_decay, grad_scale} that the kernel reads when
+        it runs (overrides the scalar arguments) — lets a captured CUDA graph follow a learning-rate schedule."""
         assert grad.numel() == param.numel() and grad.dtype == param.dtype
         assert master.dtype == torch.float32 and mom.dtype == torch.float32
         assert master.numel() * self.world == grad.numel() == mom.numel() * self.world
+        if hp is not None:
+            assert hp.is_cuda and hp.dtype == torch.float32 and hp.numel() >= 4 and hp.is_contiguous()
+            n = self._chk(self.lib.bnet_fused_allreduce_sgd_hp(
+                self.h, self.offset_of(grad), self.offset_of(param), grad.numel(), DT[grad.dtype], C.c_void_p(hp.data_ptr()),
+                C.c_void_p(master.data_ptr()), C.c_void_p(mom.data_ptr()), 1 if zero_grads else 0, channel, nblocks,
+                self._stream(stream)), "fused_allreduce_sgd_hp")
+            self.launches += n
+            return
         gs = (1.0 / self.world) if grad_scale is None else grad_scale
         n = self._chk(self.lib.bnet_fused_allreduce_sgd(
             self.h, self.offset_of(grad), self.offset_of(param), grad.numel(), DT[grad.dtype], lr, momentum,

@@ -152,7 +152,8 @@ class BnetDDP(torch.nn.Module):
         ev.record(cur)
         self.comm_stream.wait_event(ev)          # the bucket's gradients are complete on the compute stream
         self.comm.fused_allreduce_sgd(b.grad, b.param, b.master, b.mom, self.lr, self.momentum, self.weight_decay,
-                                      zero_grads=True, channel=0, nblocks=self.nblocks, stream=self.comm_stream)
+                                      zero_grads=True, channel=0, nblocks=self.nblocks, stream=self.comm_stream,
+                                      hp=getattr(self, "_hp", None))
         b.ready = 0
         self._inflight = True
 
@@ -216,8 +217,9 @@ class BnetDDP(torch.nn.Module):
             return self._eager_step(inputs, targets, loss_fn)
         from ..ops import fused_nn
 
-        key = (tuple(inputs.shape), inputs.dtype, tuple(targets.shape), targets.dtype, loss_fn, self.lr, self.momentum,
-               self.weight_decay)
+        # with the hyper-parameters in device memory (after the first set_lr) the captured step does not depend on them
+        hpkey = "device" if getattr(self, "_hp", None) is not None else (self.lr, self.momentum, self.weight_decay)
+        key = (tuple(inputs.shape), inputs.dtype, tuple(targets.shape), targets.dtype, loss_fn, hpkey)
         if self._graph is None or self._graph_key != key:
             self._capture(inputs, targets, loss_fn, key)
         self._gx.copy_(inputs, non_blocking=True)
@@ -317,7 +319,10 @@ class BnetDDP(torch.nn.Module):
             b.master.copy_(s["master"])
             b.mom.copy_(s["momentum"])
         self.lr, self.momentum, self.weight_decay = state["lr"], state["momentum"], state["weight_decay"]
-        self._graph = None                    # hyper-parameters are baked into a captured step
+        if getattr(self, "_hp", None) is not None:
+            self.set_lr(self.lr)              # hyper-parameters live in device memory: refresh them
+        else:
+            self._graph = None                # hyper-parameters are baked into a captured step
 
     def sync_master_from_params(self) -> None:
         """After module.load_state_dict(): rebuild the fp32 master shards from the (just loaded) parameters."""
@@ -335,8 +340,21 @@ class BnetDDP(torch.nn.Module):
             if b.is_cuda and b.numel():
                 self.comm.broadcast_tensor(b, src=src)
 
-    def set_lr(self, lr: float):
-        self.lr = lr
+    def set_lr(self, lr: float, momentum: float | None = None, weight_decay: float | None = None):
+        """Learning-rate schedule hook.  From the first call on, the fused optimizer kernels read {lr, momentum,
+        weight decay, 1/world} from a 4-float device tensor instead of baked-in launch arguments, so a captured CUDA
+        graph is re-captured once (here) and then follows the schedule with one tiny host→device write per change."""
+        self.lr = float(lr)
+        if momentum is not None:
+            self.momentum = float(momentum)
+        if weight_decay is not None:
+            self.weight_decay = float(weight_decay)
+        vals = [self.lr, self.momentum, self.weight_decay, 1.0 / self.comm.world]
+        if getattr(self, "_hp", None) is None:
+            self._hp = torch.tensor(vals, dtype=torch.float32, device=self.flat_param.device)
+            self._graph = None
+        else:
+            self._hp.copy_(torch.tensor(vals, dtype=torch.float32), non_blocking=False)
 
     @property
     def kernel_launches(self) -> int:

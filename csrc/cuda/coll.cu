@@ -423,7 +423,15 @@ template <int DT, int MODE>
 __global__ void __launch_bounds__(kThreads, 2) bnet_fused_sgd_kernel(CollDev d, size_t goff, size_t poff, size_t nvec,
                                                                  float lr, float mu, float wd, float gscale,
                                                                  float* __restrict__ master, float* __restrict__ mom,
-                                                                 int zero_grads, int chan) {
+                                                                 int zero_grads, int chan, const float* __restrict__ hp) {
+  // hp != NULL: hyper-parameters {lr, momentum, weight decay, gradient scale} live in device memory, so a captured
+  // CUDA graph keeps following a learning-rate schedule without being re-captured
+  if (hp != nullptr) {
+    lr = hp[0];
+    mu = hp[1];
+    wd = hp[2];
+    gscale = hp[3];
+  }
   if constexpr (MODE != 0) rank_barrier(d, chan);
   const size_t per = nvec / d.world;
   const size_t start = (size_t)d.rank * per;
@@ -919,17 +927,37 @@ BNET_API int bnet_barrier(BnetColl* c, int channel, void* stream) {
 
 template <int DT>
 static int run_fused(BnetColl* c, size_t goff, size_t poff, size_t nvec, float lr, float mu, float wd, float gs,
-                     float* master, float* mom, int zero, int chan, int nb, cudaStream_t st) {
+                     float* master, float* mom, int zero, int chan, int nb, cudaStream_t st, const float* hp) {
   if (c->world == 1)
-    return launch(bnet_fused_sgd_kernel<DT, 0>, nb, kThreads, st, c->devp, goff, poff, nvec, lr, mu, wd, gs, master, mom, zero, chan);
+    return launch(bnet_fused_sgd_kernel<DT, 0>, nb, kThreads, st, c->devp, goff, poff, nvec, lr, mu, wd, gs, master, mom, zero, chan, hp);
   if (prefer_nvls(c) && env_int("FUSED_NVLS", 1))
-    return launch(bnet_fused_sgd_kernel<DT, 1>, nb, kThreads, st, c->devp, goff, poff, nvec, lr, mu, wd, gs, master, mom, zero, chan);
-  return launch(bnet_fused_sgd_kernel<DT, 2>, nb, kThreads, st, c->devp, goff, poff, nvec, lr, mu, wd, gs, master, mom, zero, chan);
+    return launch(bnet_fused_sgd_kernel<DT, 1>, nb, kThreads, st, c->devp, goff, poff, nvec, lr, mu, wd, gs, master, mom, zero, chan, hp);
+  return launch(bnet_fused_sgd_kernel<DT, 2>, nb, kThreads, st, c->devp, goff, poff, nvec, lr, mu, wd, gs, master, mom, zero, chan, hp);
 }
+
+static int fused_allreduce_sgd_impl(BnetColl* c, size_t grad_off, size_t param_off, size_t count, int dtype, float lr,
+                                    float momentum, float weight_decay, float grad_scale, float* master, float* mom_buf,
+                                    int zero_grads, int channel, int nblocks, void* stream, const float* hp);
 
 BNET_API int bnet_fused_allreduce_sgd(BnetColl* c, size_t grad_off, size_t param_off, size_t count, int dtype, float lr,
                                       float momentum, float weight_decay, float grad_scale, float* master,
                                       float* mom_buf, int zero_grads, int channel, int nblocks, void* stream) {
+  return fused_allreduce_sgd_impl(c, grad_off, param_off, count, dtype, lr, momentum, weight_decay, grad_scale, master, mom_buf,
+                                  zero_grads, channel, nblocks, stream, nullptr);
+}
+
+// Same, with {lr, momentum, weight_decay, grad_scale} read from 4 floats of device memory at kernel run time.
+BNET_API int bnet_fused_allreduce_sgd_hp(BnetColl* c, size_t grad_off, size_t param_off, size_t count, int dtype,
+                                         const float* hp_dev, float* master, float* mom_buf, int zero_grads, int channel,
+                                         int nblocks, void* stream) {
+  if (!hp_dev || ((uintptr_t)hp_dev & 15)) return fail("hyper-parameter block must be a 16-byte aligned device pointer");
+  return fused_allreduce_sgd_impl(c, grad_off, param_off, count, dtype, 0.f, 0.f, 0.f, 1.f, master, mom_buf, zero_grads, channel,
+                                  nblocks, stream, hp_dev);
+}
+
+static int fused_allreduce_sgd_impl(BnetColl* c, size_t grad_off, size_t param_off, size_t count, int dtype, float lr,
+                                    float momentum, float weight_decay, float grad_scale, float* master, float* mom_buf,
+                                    int zero_grads, int channel, int nblocks, void* stream, const float* hp) {
   if (channel < 0 || channel >= BNET_COLL_CHANNELS) return fail("bad channel");
   if (dtype != BNET_F32 && dtype != BNET_BF16) return fail("fused SGD supports f32 and bf16");
   size_t bytes = count * elsize(dtype);
@@ -941,8 +969,8 @@ BNET_API int bnet_fused_allreduce_sgd(BnetColl* c, size_t grad_off, size_t param
   int nb = pick_blocks(c, nvec / c->world, nblocks, prefer_nvls(c) && env_int("FUSED_NVLS", 1) ? BLK_FUSED_NVLS : BLK_P2P);
   cudaStream_t st = (cudaStream_t)stream;
   size_t goff = kPadBytes + grad_off, poff = kPadBytes + param_off;
-  if (dtype == BNET_F32) return run_fused<BNET_F32>(c, goff, poff, nvec, lr, momentum, weight_decay, grad_scale, master, mom_buf, zero_grads, channel, nb, st);
-  return run_fused<BNET_BF16>(c, goff, poff, nvec, lr, momentum, weight_decay, grad_scale, master, mom_buf, zero_grads, channel, nb, st);
+  if (dtype == BNET_F32) return run_fused<BNET_F32>(c, goff, poff, nvec, lr, momentum, weight_decay, grad_scale, master, mom_buf, zero_grads, channel, nb, st, hp);
+  return run_fused<BNET_BF16>(c, goff, poff, nvec, lr, momentum, weight_decay, grad_scale, master, mom_buf, zero_grads, channel, nb, st, hp);
 }
 
 BNET_API int bnet_pack_cast(const BnetPackItem* items_dev, int n, void* dst, int src_dtype, int dst_dtype, float scale,

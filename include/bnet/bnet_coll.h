@@ -72,6 +72,10 @@ int bnet_barrier(BnetColl* c, int channel, void* stream);
 int bnet_fused_allreduce_sgd(BnetColl* c, size_t grad_off, size_t param_off, size_t count, int dtype, float lr,
                              float momentum, float weight_decay, float grad_scale, float* master, float* mom_buf,
                              int zero_grads, int channel, int nblocks, void* stream);
+/* Same, with {lr, momentum, weight_decay, grad_scale} read from 4 floats of device memory (16-byte aligned) when the
+ * kernel runs: a captured CUDA graph follows a learning-rate schedule without being re-captured. */
+int bnet_fused_allreduce_sgd_hp(BnetColl* c, size_t grad_off, size_t param_off, size_t count, int dtype, const float* hp_dev,
+                                float* master, float* mom_buf, int zero_grads, int channel, int nblocks, void* stream);
 
 /* Multi-tensor pack+cast into the heap (K5): n tensors described on the device. */
 typedef struct {

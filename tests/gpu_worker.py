@@ -322,6 +322,66 @@ def job_ddp_api():
     teardown()
 
 
+def job_lr_schedule():
+    """set_lr: hyper-parameters move to device memory; eager engine == torch SGD under a per-step schedule, and a captured
+    graph follows the schedule without being re-captured."""
+    from bagua_net_b200.models import build_model
+    from bagua_net_b200.parallel import BnetDDP
+
+    setup()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    kw = dict(width_div=8, fc_dim=128, image_size=32, num_classes=10, dropout=0.0)
+    model = build_model("vgg16", **kw).cuda()
+    ref = build_model("vgg16", **kw).cuda()
+    ref.load_state_dict(model.state_dict())
+    model = model.to(memory_format=torch.channels_last)
+    mu, wd = 0.9, 1e-4
+    eng = BnetDDP(model, lr=0.05, momentum=mu, weight_decay=wd, bucket_mb=0.25)
+    opt = torch.optim.SGD(ref.parameters(), lr=0.05, momentum=mu, weight_decay=wd)
+    for step in range(5):
+        lr = 0.05 * (0.7 ** step)
+        eng.set_lr(lr)
+        for g in opt.param_groups:
+            g["lr"] = lr
+        xs, ys = [], []
+        for r in range(WORLD):
+            torch.manual_seed(2000 + 10 * step + r)
+            xs.append(torch.randn(4, 3, 32, 32, device="cuda"))
+            ys.append(torch.randint(0, 10, (4,), device="cuda"))
+        eng.train_step(xs[RANK].contiguous(memory_format=torch.channels_last), ys[RANK])
+        opt.zero_grad()
+        torch.nn.functional.cross_entropy(ref(torch.cat(xs)), torch.cat(ys)).backward()
+        opt.step()
+    torch.cuda.synchronize()
+    worst = max((p1.float() - p2.float()).abs().max().item() for p1, p2 in zip(model.parameters(), ref.parameters()))
+    assert worst < 1e-3, f"engine with a learning-rate schedule diverged from torch SGD: {worst}"
+    # graph mode: one re-capture when the schedule starts, none afterwards
+    torch.manual_seed(1)
+    m2 = build_model("vgg16", fused=True, **kw).cuda().to(torch.bfloat16).to(memory_format=torch.channels_last)
+    e2 = BnetDDP(m2, lr=0.02, momentum=0.9, weight_decay=0.0, bucket_mb=0.25)
+    e2.enable_cuda_graph(True)
+    x = torch.randn(8, 3, 32, 32, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    y = torch.randint(0, 10, (8,), device="cuda")
+    l0 = float(e2.train_step(x, y))
+    e2.set_lr(0.02)
+    float(e2.train_step(x, y))
+    g = e2._graph
+    for step in range(20):
+        e2.set_lr(0.02 * (0.97 ** step))
+        last = float(e2.train_step(x, y))
+        assert e2._graph is g, "the graph was re-captured for a learning-rate change"
+    assert last == last and last < l0, (l0, last)
+    e2.set_lr(0.0)                       # lr = 0: parameters must stop moving
+    before = e2.flat_param.clone()
+    float(e2.train_step(x, y))
+    torch.cuda.synchronize()
+    assert torch.equal(before, e2.flat_param), "lr=0 in device memory was not honoured by the captured step"
+    print(f"rank {RANK}: lr schedule ok (max diff {worst:.2e})", flush=True)
+    teardown()
+
+
 def job_collectives_any():
     """all_reduce / broadcast / all_gather / reduce_scatter on ordinary (non-heap) tensors vs torch.distributed."""
     from bagua_net_b200.parallel import SymmComm

@@ -148,6 +148,10 @@ def test_ddp_loader_loop_and_checkpoint_2gpu():
     _run_worker("ddp_api", 2, timeout=240)
 
 
+def test_lr_schedule_through_device_resident_hyperparameters():
+    _run_worker("lr_schedule", 1, timeout=240)
+
+
 @pytest.mark.multigpu
 def test_collectives_on_ordinary_tensors_2gpu():
     _run_worker("collectives_any", 2, timeout=240)
