@@ -5,6 +5,8 @@
 #   make bench      native benchmarks (all_reduce_perf clone, p2p_bw)
 #   make sass       SASS / PTX / resource listings of every kernel -> docs/sass/
 #   make tar        release tarball like the reference's `make tar`
+#   make install    copy the plugin variants to $(PREFIX)/lib
+#   make tsan asan emu-asan   sanitizer builds + tests (ci/run_sanitizers.sh)
 #
 # Counterpart of the reference build (reference: cc/Makefile:1-26): same product
 # name — NCCL dlopen()s libnccl-net.so from LD_LIBRARY_PATH — but no cargo step.
@@ -116,11 +118,19 @@ sass: $(PLUGIN_SO)
 tar: default
 	tar czf bagua-net-b200_x86_64.tar.gz -C $(OUT) libnccl-net.so libnccl-net-bnet.so libnccl-net-bnetx.so
 
+# `make install PREFIX=/opt/bnet` puts the three plugin variants where LD_LIBRARY_PATH can find them
+PREFIX ?= /usr/local
+install: default
+	install -d $(PREFIX)/lib
+	install -m 0755 $(PLUGIN_SO) $(ALIAS_SO) $(PLUGINX_SO) $(PREFIX)/lib/
+uninstall:
+	rm -f $(PREFIX)/lib/libnccl-net.so $(PREFIX)/lib/libnccl-net-bnet.so $(PREFIX)/lib/libnccl-net-bnetx.so
+
 clean:
 	rm -rf $(BUILD) $(OUT)/*.so
 
 -include $(HOST_OBJS:.o=.d) $(CU_OBJS:.o=.d)
-.PHONY: default test bench sass tar clean emu-asan
+.PHONY: default test bench sass tar clean emu-asan install uninstall
 
 # ---- sanitizer builds of the host engine: `make tsan` / `make asan` rebuild every host
 # object with the sanitizer into build/<san>/, link it with the (uninstrumented) kernel objects and run the
