@@ -49,11 +49,22 @@ class VGG(nn.Module):
         self.features = nn.Sequential(*layers)
         side = image_size // 32
         self.avgpool = nn.AdaptiveAvgPool2d((side, side)) if image_size % 32 else nn.Identity()
-        self.classifier = nn.Sequential(
-            nn.Linear(cin * side * side, fc_dim), nn.ReLU(True), nn.Dropout(dropout),
-            nn.Linear(fc_dim, fc_dim), nn.ReLU(True), nn.Dropout(dropout),
-            nn.Linear(fc_dim, num_classes),
-        )
+        from ..ops import tc_linear
+
+        if fused and tc_linear.enabled():
+            # opt-in (BNET_TC=1): Linear + bias + ReLU as one tcgen05 kernel; Identity keeps the Sequential indices —
+            # and so the state_dict keys — of the stock layout
+            self.classifier = nn.Sequential(
+                tc_linear.TCLinear(cin * side * side, fc_dim, relu=True), nn.Identity(), nn.Dropout(dropout),
+                tc_linear.TCLinear(fc_dim, fc_dim, relu=True), nn.Identity(), nn.Dropout(dropout),
+                tc_linear.TCLinear(fc_dim, num_classes),
+            )
+        else:
+            self.classifier = nn.Sequential(
+                nn.Linear(cin * side * side, fc_dim), nn.ReLU(True), nn.Dropout(dropout),
+                nn.Linear(fc_dim, fc_dim), nn.ReLU(True), nn.Dropout(dropout),
+                nn.Linear(fc_dim, num_classes),
+            )
         for m in self.modules():
             if isinstance(m, nn.Conv2d):
                 nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")

@@ -1,0 +1,245 @@
+"""tcgen05 linear layer and the fused row-parallel (GEMM + all-reduce) linear (csrc/cuda/tc_gemm.cu).
+
+    y = tc_linear.linear(x, w, bias, relu=True)                # bf16 [M,K] x [N,K]^T -> bf16 [M,N], fused bias + ReLU
+    y = tc_linear.row_parallel_linear(x_k, w_k, comm)          # every rank holds a K-shard; fp32 sum lands on EVERY rank
+
+The kernel stages operands with TMA (128-byte swizzle), multiplies with ``tcgen05.mma`` into TMEM and applies the
+epilogue straight out of TMEM; ``row_parallel_linear`` is the "compute step followed by a collective in ONE kernel"
+form: the epilogue adds its fp32 tile into every rank's symmetric-heap output (``multimem.red`` through the NVSwitch
+multicast mapping, ``red.global`` per peer otherwise), so no separate all-reduce runs.
+
+The reference has no compute path — this belongs to the B200 side of the framework.
+
+STATUS (round 1): built and descriptor-checked on the host, never run on hardware yet.  Nothing calls it unless
+``BNET_TC=1``; the GPU tests for it run only with ``BNET_TEST_TC=1``; ``self_check()`` must pass before any caller
+trusts it, and every launch carries a device-side watchdog (``last_error()``)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+from ..utils.native import load
+
+_lib = None
+_err: dict[int, torch.Tensor] = {}
+LAUNCHES = 0
+
+
+class Plan(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("swap", "bn", "stages", "grid_x", "grid_y", "grid_z", "smem_bytes", "k_blocks",
+                                       "k_per_split")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+def _L():
+    global _lib
+    if _lib is None:
+        _lib = load()
+        vp, i = C.c_void_p, C.c_int
+        _lib.bnet_tc_supported.restype = i
+        _lib.bnet_tc_plan.argtypes = [i, i, i, i, i, C.POINTER(Plan)]
+        _lib.bnet_tc_linear.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, i, vp, vp]
+        _lib.bnet_tc_linear_reduce.argtypes = [vp, vp, vp, C.POINTER(vp), i, i, i, i, i, i, i, i, i, vp, vp]
+        _lib.bnet_tc_last_error.restype = C.c_char_p
+        _lib.bnet_tc_smem_desc.restype = C.c_uint64
+        _lib.bnet_tc_smem_desc.argtypes = [C.c_uint32]
+        _lib.bnet_tc_instr_desc.restype = C.c_uint32
+        _lib.bnet_tc_instr_desc.argtypes = [i, i]
+    return _lib
+
+
+def enabled() -> bool:
+    """Opt-in switch for callers (models, bench): the kernel is unvalidated on hardware in this round."""
+    return os.environ.get("BNET_TC", "0") == "1"
+
+
+def supported() -> bool:
+    return torch.cuda.is_available() and bool(_L().bnet_tc_supported())
+
+
+def plan(M: int, N: int, K: int, reduce: bool = False, splits: int = 1) -> dict:
+    """The tiling the kernel would use (host-only; works without a GPU)."""
+    p = Plan()
+    if _L().bnet_tc_plan(M, N, K, 1 if reduce else 0, splits, C.byref(p)) != 0:
+        raise ValueError(_L().bnet_tc_last_error().decode())
+    return p.as_dict()
+
+
+def _err_flag(dev: int) -> torch.Tensor:
+    if dev not in _err:
+        _err[dev] = torch.zeros(1, dtype=torch.int32, device=f"cuda:{dev}")
+    return _err[dev]
+
+
+def last_error(device: int | None = None) -> int:
+    """Synchronises.  0 = every launch so far completed; 1/2/3 = the TMA producer / MMA issuer / epilogue gave up
+    waiting (the watchdog turned a stuck pipeline into this code).  Reading clears it."""
+    dev = torch.cuda.current_device() if device is None else device
+    f = _err_flag(dev)
+    v = int(f.item())
+    if v:
+        f.zero_()
+    return v
+
+
+def _check_operands(x, w, bias):
+    if not (x.is_cuda and w.is_cuda and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16):
+        raise TypeError("tc_linear needs bf16 CUDA tensors")
+    if x.dim() != 2 or w.dim() != 2 or x.shape[1] != w.shape[1]:
+        raise ValueError(f"shapes do not multiply: x {tuple(x.shape)} w {tuple(w.shape)}")
+    if x.stride(1) != 1 or w.stride(1) != 1:
+        raise ValueError("operands must be K-contiguous")
+    if bias is not None and not (bias.is_cuda and bias.dtype == torch.bfloat16 and bias.is_contiguous()
+                                 and bias.numel() == w.shape[0]):
+        raise ValueError("bias must be a contiguous bf16 vector with one entry per output feature")
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, relu: bool = False,
+           out: torch.Tensor | None = None) -> torch.Tensor:
+    """``act(x @ w.T + bias)`` on the tcgen05 tensor cores; x [M,K], w [N,K] (torch ``Linear.weight``), bf16."""
+    global LAUNCHES
+    _check_operands(x, w, bias)
+    M, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
+    assert out.dtype == torch.bfloat16 and out.shape == (M, N) and out.stride(1) == 1
+    L = _L()
+    rc = L.bnet_tc_linear(x.data_ptr(), w.data_ptr(), bias.data_ptr() if bias is not None else None, out.data_ptr(), M, N,
+                          K, x.stride(0), w.stride(0), out.stride(0), 1 if relu else 0,
+                          _err_flag(x.device.index).data_ptr(), _stream())
+    if rc < 0:
+        raise RuntimeError(f"bnet_tc_linear: {L.bnet_tc_last_error().decode()}")
+    LAUNCHES += rc
+    return out
+
+
+class _LinearAct(torch.autograd.Function):
+    """Forward on the tcgen05 kernel (bias and ReLU in its epilogue); the two backward GEMMs need MN-major operands
+    and stay on cuBLAS for now."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, relu):
+        y = linear(x, w, bias, relu)
+        ctx.relu = relu
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, w, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, y = ctx.saved_tensors
+        if ctx.relu:
+            gy = gy * (y > 0).to(gy.dtype)
+        gx = gy @ w if ctx.needs_input_grad[0] else None
+        gw = gy.t() @ x if ctx.needs_input_grad[1] else None
+        gb = gy.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        return gx, gw, gb, None
+
+
+def linear_bias_act(x, w, bias=None, relu=False):
+    """Autograd-aware ``linear``."""
+    return _LinearAct.apply(x, w, bias, relu)
+
+
+_trusted: bool | None = None
+
+
+def trusted() -> bool:
+    """enabled() and a passing self-check on this GPU (evaluated once per process)."""
+    global _trusted
+    if _trusted is None:
+        _trusted = enabled() and self_check()
+    return _trusted
+
+
+class TCLinear(torch.nn.Linear):
+    """``nn.Linear`` (same parameters, same state_dict keys) with an optional fused ReLU whose forward runs on the
+    tcgen05 kernel when ``BNET_TC=1`` and the self-check passed on this GPU; cuBLAS + eager ReLU otherwise."""
+
+    def __init__(self, in_features, out_features, bias=True, relu=False, **kw):
+        super().__init__(in_features, out_features, bias=bias, **kw)
+        self.relu = relu
+
+    def forward(self, x):
+        if (x.is_cuda and x.dtype == torch.bfloat16 and self.weight.dtype == torch.bfloat16 and x.dim() == 2
+                and x.stride(1) == 1 and self.in_features % 8 == 0 and x.stride(0) % 8 == 0 and trusted()):
+            return linear_bias_act(x, self.weight, self.bias, self.relu)
+        y = torch.nn.functional.linear(x, self.weight, self.bias)
+        return torch.relu(y) if self.relu else y
+
+    def extra_repr(self):
+        return super().extra_repr() + f", relu={self.relu}, tcgen05={'on' if enabled() else 'off'}"
+
+
+def row_parallel_linear(x: torch.Tensor, w: torch.Tensor, comm, bias: torch.Tensor | None = None,
+                        out: torch.Tensor | None = None, splits: int = 1) -> torch.Tensor:
+    """Row-parallel linear: rank r holds x[:, K_r] and w[:, K_r]; returns fp32 ``sum_r x_r @ w_r.T (+ bias)`` on every
+    rank, produced by ONE kernel per rank whose epilogue adds into all ranks' outputs over NVLink.
+
+    ``out`` must come from ``comm.alloc`` (same offset on every rank); pass it back in to reuse the buffer.  Two rank
+    barriers bracket the kernel: outputs are zero before anyone adds, and all adds have landed before anyone reads."""
+    global LAUNCHES
+    _check_operands(x, w, bias)
+    M, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = comm.alloc(M * N, torch.float32).view(M, N)
+    assert out.dtype == torch.float32 and out.shape == (M, N) and out.is_contiguous()
+    off = comm.offset_of(out)
+    out.zero_()
+    comm.barrier()
+    if comm.world > 1 and comm.has_multicast:
+        ptrs, mc = [int(comm.lib.bnet_coll_mc_heap(comm.h)) + off], 1
+    else:
+        ptrs = [int(comm.lib.bnet_coll_peer_heap(comm.h, r)) + off if r != comm.rank else out.data_ptr()
+                for r in range(comm.world)]
+        mc = 0
+    arr = (C.c_void_p * len(ptrs))(*ptrs)
+    L = _L()
+    b = bias if (bias is not None and comm.rank == 0) else None       # added once, not once per rank
+    rc = L.bnet_tc_linear_reduce(x.data_ptr(), w.data_ptr(), b.data_ptr() if b is not None else None, arr, len(ptrs), mc,
+                                 M, N, K, x.stride(0), w.stride(0), out.stride(0), splits,
+                                 _err_flag(x.device.index).data_ptr(), _stream())
+    if rc < 0:
+        raise RuntimeError(f"bnet_tc_linear_reduce: {L.bnet_tc_last_error().decode()}")
+    LAUNCHES += rc
+    comm.barrier()
+    return out
+
+
+def self_check(verbose: bool = False) -> bool:
+    """Run the kernel on a few shapes (both operand orientations, ragged M/N/K, bias, ReLU) against an fp32 PyTorch
+    reference.  False — never an exception — when it is unsupported, errs, trips the watchdog or is numerically off."""
+    try:
+        if not supported():
+            return False
+        g = torch.Generator(device="cuda").manual_seed(7)
+        for (M, N, K, relu) in [(32, 256, 512, True), (48, 200, 264, False), (256, 384, 1024, True), (130, 136, 72, False)]:
+            x = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+            w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+            b = torch.randn(N, device="cuda", generator=g).bfloat16()
+            y = linear(x, w, b, relu)
+            if last_error():
+                return False
+            ref = x.float() @ w.float().t() + b.float()
+            if relu:
+                ref = torch.relu(ref)
+            err = (y.float() - ref).abs().max().item()
+            if verbose:
+                print(f"tc_linear {M}x{N}x{K} relu={relu}: max abs err {err:.4f}")
+            if not (err < 0.06):
+                return False
+        return True
+    except Exception as e:  # noqa: BLE001 — the caller falls back to cuBLAS
+        if verbose:
+            print(f"tc_linear self-check failed: {e!r}")
+        return False

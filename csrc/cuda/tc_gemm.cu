@@ -1,0 +1,450 @@
+// Tensor-core linear layer for sm_100a: TMA -> shared memory -> tcgen05.mma -> TMEM -> fused epilogue.
+//
+//   D[i, j] = sum_k A[i, k] * B[j, k]        A: "lane" operand, 128 rows per tile (one per TMEM lane)
+//                                            B: "column" operand, BN rows per tile (the MMA N dimension)
+//
+// Both operands are K-major bf16 matrices (a torch Linear's activation [M,K] and weight [N,K] as they are), so either
+// can take either role: with a large batch x is A and w is B; with a small batch (M <= 64) the roles swap so that the
+// 128 TMEM lanes are filled by output features instead of 3/4 padding rows.
+//
+// One CTA = one output tile, 6 warps, warp-specialised (guide "Anatomy of a Blackwell GEMM kernel"):
+//   warp 0, one lane   TMA producer: cp.async.bulk.tensor.2d of a [128 x 64] A box and a [BN x 64] B box per stage,
+//                      128-byte swizzle, completion on the stage's `full` mbarrier
+//   warp 1             allocates BN TMEM columns; one lane issues 4 tcgen05.mma (K = 16 each) per stage and
+//                      tcgen05.commit's the stage's `empty` mbarrier; after the last K block commits `acc_full`
+//   warps 2-5          epilogue: tcgen05.ld 32 lanes x 16 columns at a time -> bias / ReLU -> bf16 store, or (reduce
+//                      mode) fp32 adds into every rank's output: multimem.red through the NVSwitch multicast mapping
+//                      or red.global per peer.  Warp w may only touch TMEM lanes 32*(w%4) .. +31.
+//
+// Every mbarrier wait carries a watchdog (kWatchdogNs): a pipeline that stops — a descriptor the hardware rejects, a
+// lost TMA completion — sets *err and lets every role fall through to the teardown instead of hanging the GPU.
+//
+// STATUS: not yet run on hardware (see include/bnet/bnet_tc.h).  Descriptor packing is unit-tested against CuTe.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <mutex>
+#include <string>
+
+#include "bnet/bnet_tc.h"
+#include "cuda/driver_api.h"
+#include "cuda/ptx.cuh"
+
+#define BNET_API extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+using namespace bnet;
+
+constexpr int kBM = 128;               // UMMA M: one accumulator row per TMEM lane
+constexpr int kBK = 64;                // 64 bf16 = 128 bytes = one swizzle-128B row
+constexpr int kUmmaK = 16;             // fixed for 16-bit inputs
+constexpr int kThreads = 192;
+constexpr int kABytes = kBM * kBK * 2; // 16 KiB per stage
+constexpr uint64_t kWatchdogNs = 2000000000ull;
+
+thread_local std::string g_err;
+
+// ------------------------------------------------------------------------------------------------ descriptors
+// Instruction descriptor, .kind::f16 (bit positions: cute/arch/mma_sm100_desc.hpp `InstrDescriptor`):
+//   [4,6) D format (1 = f32)  [7,10) A format (1 = bf16)  [10,13) B format (1 = bf16)
+//   15 / 16 A / B major (0 = K-major)   [17,23) N >> 3   [24,29) M >> 4
+__host__ __device__ constexpr uint32_t instr_desc_bf16_f32(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(n >> 3) << 17) | (uint32_t(m >> 4) << 24);
+}
+
+// Shared-memory matrix descriptor of a K-major tile whose rows are 128 bytes, stored densely and swizzled by the
+// hardware in 8-row x 128-byte atoms (what TMA writes with CU_TENSOR_MAP_SWIZZLE_128B):
+//   [0,14) start address >> 4   [16,30) leading byte offset >> 4 (unused for swizzled K-major layouts; 1 like CuTe)
+//   [32,46) stride byte offset >> 4 = 1024 B between 8-row groups   [46,48) version = 1   [61,64) layout = 2 (SW128)
+__host__ __device__ constexpr uint64_t smem_desc_sw128(uint32_t smem_addr) {
+  return uint64_t((smem_addr >> 4) & 0x3FFF) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) |
+         (uint64_t(2) << 61);
+}
+
+// ------------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// false = the watchdog fired (and *err now says which role gave up)
+__device__ __forceinline__ bool mbar_wait_wd(uint32_t bar, uint32_t parity, int* err, int role) {
+  if (mbar_try_wait(bar, parity)) return true;
+  const uint64_t t0 = ptx::globaltimer();
+  while (!mbar_try_wait(bar, parity)) {
+    if (ptx::globaltimer() - t0 > kWatchdogNs) {
+      atomicCAS(err, 0, role);
+      return false;
+    }
+  }
+  return true;
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" :: "l"(map) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem] * B[smem]; accumulate == 0 overwrites D
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// mbarrier arrives once every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+// this warp's 32 TMEM lanes x 16 consecutive fp32 columns: v[t] = D[lane, col + t]
+__device__ __forceinline__ void tmem_ld_16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void multimem_red_add_f32(float* mc, float v) {
+  asm volatile("multimem.red.relaxed.sys.global.add.f32 [%0], %1;" :: "l"(mc), "f"(v) : "memory");
+}
+__device__ __forceinline__ void multimem_red_add_v4_f32(float* mc, const float4& v) {
+  asm volatile("multimem.red.relaxed.sys.global.add.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+struct TcArgs {
+  int rows_a, rows_b;        // valid rows of the lane / column operand
+  int k_blocks;              // ceil(K / 64)
+  int k_per_split;           // K blocks handled by one grid.z slice
+  int ldo;                   // elements between output rows
+  int act;
+  const __nv_bfloat16* bias; // indexed by the output FEATURE (column of out), may be null
+  void* outs[BNET_TC_MAX_OUTS];
+  int n_outs;                // reduce mode: how many output mappings (1 when multicast)
+  int multicast;
+  int* err;
+};
+
+template <int BN>
+struct Smem {
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+};
+
+// kSwap:   false -> A = x (lane i = batch row m), B = w (column j = feature n); out[m, n] = out[i * ldo + j]
+//          true  -> A = w (lane i = feature n),   B = x (column j = batch row m); out[m, n] = out[j * ldo + i]
+// kReduce: fp32 adds into args.outs[] instead of a bf16 store
+template <int BN, int kStages, bool kSwap, bool kReduce>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcArgs args) {
+  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M = 128");
+  static_assert((BN & (BN - 1)) == 0 && BN >= 32, "TMEM allocations are powers of two >= 32 columns");
+  extern __shared__ uint8_t smem_raw[];
+  // swizzle-128B atoms must start on 1024-byte boundaries of the shared window
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* const tiles = smem_raw + (base - raw);
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(tiles + kStages * Smem<BN>::kStageBytes);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kStages, acc_full = empty0 + 8 * kStages;
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int a_row0 = blockIdx.y * kBM, b_row0 = blockIdx.x * BN;
+  const int kb_begin = blockIdx.z * args.k_per_split;
+  const int kb_end = min(kb_begin + args.k_per_split, args.k_blocks);
+  const int nkb = kb_end - kb_begin;       // >= 1 by construction of the grid
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < kStages; s++) {
+      ptx::mbar_init(bars + s, 1);               // full: the producer's arrive.expect_tx (+ TMA bytes)
+      ptx::mbar_init(bars + kStages + s, 1);     // empty: one tcgen05.commit
+    }
+    ptx::mbar_init(bars + 2 * kStages, 1);       // accumulator complete
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), BN);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < nkb; i++) {
+        const int s = i % kStages;
+        const uint32_t round = i / kStages;
+        if (round > 0 && !mbar_wait_wd(empty0 + 8 * s, (round - 1) & 1, args.err, 1)) break;
+        const uint32_t a_dst = base + s * Smem<BN>::kStageBytes;
+        mbar_expect_tx(full0 + 8 * s, Smem<BN>::kStageBytes);
+        tma_load_2d(a_dst, &map_a, full0 + 8 * s, (kb_begin + i) * kBK, a_row0);
+        tma_load_2d(a_dst + kABytes, &map_b, full0 + 8 * s, (kb_begin + i) * kBK, b_row0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = instr_desc_bf16_f32(kBM, BN);
+      bool alive = true;
+      for (int i = 0; i < nkb && alive; i++) {
+        const int s = i % kStages;
+        alive = mbar_wait_wd(full0 + 8 * s, (i / kStages) & 1, args.err, 2);
+        if (!alive) break;
+        tc_fence_after_sync();
+        const uint32_t a_src = base + s * Smem<BN>::kStageBytes;
+        const uint64_t da = smem_desc_sw128(a_src), db = smem_desc_sw128(a_src + kABytes);
+#pragma unroll
+        for (int k = 0; k < kBK / kUmmaK; k++) {
+          // +32 bytes (2 x 16-byte units) along K inside the 128-byte swizzle row per K = 16 slice
+          umma_bf16(tmem_d, da + uint64_t(k * (kUmmaK * 2 / 16)), db + uint64_t(k * (kUmmaK * 2 / 16)), idesc,
+                    (i | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(empty0 + 8 * s);              // the stage may be refilled once these MMAs have read it
+      }
+      if (alive) umma_commit(acc_full);
+    }
+  } else {
+    // ---- epilogue: 4 warps x 32 lanes = the tile's 128 accumulator rows
+    const int q = warp & 3;                        // the TMEM lane quarter this warp may read
+    const int i_glob = a_row0 + q * 32 + lane;     // row of the lane operand this thread owns
+    if (mbar_wait_wd(acc_full, 0, args.err, 3)) {
+      tc_fence_after_sync();
+      float bias_i = 0.f;
+      const bool add_bias = args.bias != nullptr && (!kReduce || blockIdx.z == 0);
+      if (kSwap && add_bias && i_glob < args.rows_a) bias_i = __bfloat162float(args.bias[i_glob]);
+#pragma unroll 1
+      for (int c = 0; c < BN / 16; c++) {
+        uint32_t v[16];
+        __syncwarp();                                 // tcgen05.ld is .sync.aligned: reconverge after the guarded stores
+        tmem_ld_16(tmem_d + (uint32_t(q * 32) << 16) + uint32_t(c * 16), v);   // warp-collective: no divergence above
+        const int j0 = b_row0 + c * 16;
+        if (i_glob >= args.rows_a || j0 >= args.rows_b) continue;
+        float f[16];
+#pragma unroll
+        for (int t = 0; t < 16; t++) {
+          float b = kSwap ? bias_i : ((add_bias && j0 + t < args.rows_b) ? __bfloat162float(args.bias[j0 + t]) : 0.f);
+          f[t] = __uint_as_float(v[t]) + b;
+          if (!kReduce && args.act == BNET_TC_ACT_RELU) f[t] = fmaxf(f[t], 0.f);
+        }
+        if constexpr (!kReduce) {
+          __nv_bfloat16* out = static_cast<__nv_bfloat16*>(args.outs[0]);
+          if constexpr (kSwap) {
+            // out[(j0 + t) * ldo + i]: for every t the warp writes 32 consecutive features
+#pragma unroll
+            for (int t = 0; t < 16; t++)
+              if (j0 + t < args.rows_b) out[size_t(j0 + t) * args.ldo + i_glob] = __float2bfloat16_rn(f[t]);
+          } else {
+            __nv_bfloat16* row = out + size_t(i_glob) * args.ldo + j0;
+            if (j0 + 16 <= args.rows_b && (reinterpret_cast<uintptr_t>(row) & 15) == 0) {
+              uint32_t w[8];
+#pragma unroll
+              for (int t = 0; t < 8; t++) {
+                __nv_bfloat162 p = __floats2bfloat162_rn(f[2 * t], f[2 * t + 1]);
+                w[t] = *reinterpret_cast<uint32_t*>(&p);
+              }
+              reinterpret_cast<uint4*>(row)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+              reinterpret_cast<uint4*>(row)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+            } else {
+#pragma unroll
+              for (int t = 0; t < 16; t++)
+                if (j0 + t < args.rows_b) row[t] = __float2bfloat16_rn(f[t]);
+            }
+          }
+        } else {
+          // fp32 adds into EVERY rank's output: the all-reduce of the row-parallel layer, tile by tile
+          for (int o = 0; o < args.n_outs; o++) {
+            float* out = static_cast<float*>(args.outs[o]);
+            if constexpr (kSwap) {
+#pragma unroll
+              for (int t = 0; t < 16; t++) {
+                if (j0 + t >= args.rows_b) continue;
+                float* p = out + size_t(j0 + t) * args.ldo + i_glob;
+                if (args.multicast) multimem_red_add_f32(p, f[t]); else ptx::red_add_f32(p, f[t]);
+              }
+            } else {
+              float* row = out + size_t(i_glob) * args.ldo + j0;
+              const bool vec = j0 + 16 <= args.rows_b && (reinterpret_cast<uintptr_t>(row) & 15) == 0;
+#pragma unroll
+              for (int t = 0; t < 16; t += 4) {
+                if (vec) {
+                  const float4 x = make_float4(f[t], f[t + 1], f[t + 2], f[t + 3]);
+                  if (args.multicast) multimem_red_add_v4_f32(row + t, x); else ptx::red_add_v4_f32(row + t, x);
+                } else {
+                  for (int u = t; u < t + 4; u++) {
+                    if (j0 + u >= args.rows_b) continue;
+                    if (args.multicast) multimem_red_add_f32(row + u, f[u]); else ptx::red_add_f32(row + u, f[u]);
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // ---- teardown: every TMEM read and MMA is ordered before the barrier, then the allocating warp frees the columns
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_d, BN);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    else
+      (void)cudaGetLastError();
+  });
+  return fn;
+}
+
+// a [rows x K] bf16 matrix, K contiguous, `ld` elements between rows; boxes of [box_rows x 64], 128-byte swizzle;
+// rows / columns outside the matrix read as zero, so ragged M, N and K need no special case in the kernel
+bool make_map(CUtensorMap* map, const void* ptr, int rows, int K, int ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { g_err = "the CUDA driver does not export cuTensorMapEncodeTiled"; return false; }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (size_t(ld) * 2) % 16) {
+    g_err = "operands must be 16-byte aligned with a row pitch that is a multiple of 8 elements";
+    return false;
+  }
+  const cuuint64_t dims[2] = {cuuint64_t(K), cuuint64_t(rows)};
+  const cuuint64_t strides[1] = {cuuint64_t(ld) * 2};
+  const cuuint32_t box[2] = {cuuint32_t(kBK), cuuint32_t(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { g_err = "cuTensorMapEncodeTiled failed: " + std::to_string(int(r)); return false; }
+  return true;
+}
+
+template <int BN, int kStages, bool kSwap, bool kReduce>
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs& a, const BnetTcPlan& p, cudaStream_t st) {
+  auto kern = tc_linear_kernel<BN, kStages, kSwap, kReduce>;
+  static std::once_flag once;
+  static cudaError_t attr_rc = cudaSuccess;
+  const int smem = p.smem_bytes;
+  std::call_once(once, [&] { attr_rc = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
+  if (attr_rc != cudaSuccess) { g_err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(attr_rc); return -1; }
+  kern<<<dim3(p.grid_x, p.grid_y, p.grid_z), kThreads, smem, st>>>(ma, mb, a);
+  cudaError_t rc = cudaGetLastError();
+  if (rc != cudaSuccess) { g_err = std::string("tc_linear launch: ") + cudaGetErrorString(rc); return -1; }
+  return 1;
+}
+
+constexpr int stages_for(int bn) { return bn <= 64 ? 6 : 5; }
+
+int run(const void* x, const void* w, const void* bias, void* const* outs, int n_outs, int multicast, bool reduce, int M,
+        int N, int K, int ldx, int ldw, int ldo, int act, int splits, int* err_dev, void* stream) {
+  BnetTcPlan p;
+  if (bnet_tc_plan(M, N, K, reduce ? 1 : 0, splits, &p) != 0) return -1;
+  if (!err_dev) { g_err = "err_dev is required"; return -1; }
+  if (n_outs < 1 || n_outs > BNET_TC_MAX_OUTS) { g_err = "n_outs out of range"; return -1; }
+  // lane operand = 128-row boxes, column operand = bn-row boxes
+  const void* pa = p.swap ? w : x; const void* pb = p.swap ? x : w;
+  const int rows_a = p.swap ? N : M, rows_b = p.swap ? M : N, lda = p.swap ? ldw : ldx, ldb = p.swap ? ldx : ldw;
+  CUtensorMap ma, mb;
+  if (!make_map(&ma, pa, rows_a, K, lda, kBM) || !make_map(&mb, pb, rows_b, K, ldb, p.bn)) return -1;
+  TcArgs a{};
+  a.rows_a = rows_a; a.rows_b = rows_b; a.k_blocks = p.k_blocks; a.k_per_split = p.k_per_split; a.ldo = ldo; a.act = act;
+  a.bias = static_cast<const __nv_bfloat16*>(bias);
+  for (int i = 0; i < n_outs; i++) a.outs[i] = outs[i];
+  a.n_outs = n_outs; a.multicast = multicast; a.err = err_dev;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define BNET_TC_CASE(BN, SWAP)                                                                         \
+  if (p.bn == BN && bool(p.swap) == SWAP)                                                              \
+    return reduce ? launch<BN, stages_for(BN), SWAP, true>(ma, mb, a, p, st)                           \
+                  : launch<BN, stages_for(BN), SWAP, false>(ma, mb, a, p, st);
+  BNET_TC_CASE(32, true)
+  BNET_TC_CASE(64, true)
+  BNET_TC_CASE(128, false)
+#undef BNET_TC_CASE
+  g_err = "no kernel for this plan";
+  return -1;
+}
+
+}  // namespace
+
+BNET_API const char* bnet_tc_last_error(void) { return g_err.c_str(); }
+BNET_API uint64_t bnet_tc_smem_desc(uint32_t smem_addr) { return smem_desc_sw128(smem_addr); }
+BNET_API uint32_t bnet_tc_instr_desc(int m, int n) { return instr_desc_bf16_f32(m, n); }
+
+BNET_API int bnet_tc_supported(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return (major == 10 && encode_fn() != nullptr) ? 1 : 0;
+}
+
+BNET_API int bnet_tc_plan(int M, int N, int K, int reduce, int splits, BnetTcPlan* p) {
+  if (!p || M < 1 || N < 1 || K < 1) { g_err = "bad problem size"; return -1; }
+  if (K % 8) { g_err = "K must be a multiple of 8 (16-byte TMA row pitch)"; return -1; }
+  p->swap = M <= 64 ? 1 : 0;
+  p->bn = p->swap ? (M <= 32 ? 32 : 64) : 128;
+  p->stages = stages_for(p->bn);
+  const int rows_a = p->swap ? N : M, rows_b = p->swap ? M : N;
+  p->grid_x = (rows_b + p->bn - 1) / p->bn;
+  p->grid_y = (rows_a + kBM - 1) / kBM;
+  p->k_blocks = (K + kBK - 1) / kBK;
+  int z = (reduce && splits > 1) ? splits : 1;
+  if (z > p->k_blocks) z = p->k_blocks;
+  p->k_per_split = (p->k_blocks + z - 1) / z;
+  p->grid_z = (p->k_blocks + p->k_per_split - 1) / p->k_per_split;   // no empty slices
+  // tiles + alignment slack + (2 * stages + 1) mbarriers + the TMEM address slot
+  p->smem_bytes = p->stages * (kABytes + p->bn * kBK * 2) + 1024 + (2 * p->stages + 1) * 8 + 16;
+  if (p->grid_y > 65535 || p->grid_z > 65535) { g_err = "problem too large for one launch"; return -1; }
+  return 0;
+}
+
+BNET_API int bnet_tc_linear(const void* x, const void* w, const void* bias, void* out, int M, int N, int K, int ldx, int ldw,
+                            int ldo, int act, int* err_dev, void* stream) {
+  void* outs[1] = {out};
+  return run(x, w, bias, outs, 1, 0, false, M, N, K, ldx, ldw, ldo, act, 1, err_dev, stream);
+}
+
+BNET_API int bnet_tc_linear_reduce(const void* x, const void* w, const void* bias, void* const* outs, int n_outs, int multicast,
+                                   int M, int N, int K, int ldx, int ldw, int ldo, int splits, int* err_dev, void* stream) {
+  return run(x, w, bias, outs, n_outs, multicast, true, M, N, K, ldx, ldw, ldo, BNET_TC_ACT_NONE, splits, err_dev, stream);
+}

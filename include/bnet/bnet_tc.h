@@ -1,0 +1,64 @@
+/*
+ * bnet tensor-core linear — tcgen05 / TMEM / TMA GEMM with a fused epilogue, optionally fused with the all-reduce
+ * of a row-parallel (tensor-parallel) linear layer.
+ *
+ *   out[M,N] = act(x[M,K] . w[N,K]^T + bias[N])                       bnet_tc_linear        (bf16 in, bf16 out)
+ *   outs[r][M,N] += x[M,K] . w[N,K]^T (+ bias)   for every rank r      bnet_tc_linear_reduce (bf16 in, fp32 out)
+ *
+ * The second form is the "GEMM -> all-reduce in ONE kernel" of a row-parallel layer: every rank multiplies its K-shard
+ * and the epilogue adds the fp32 tile straight into the symmetric-heap output of EVERY rank — one multimem.red per
+ * vector through the NVSwitch multicast mapping, or one red.global per peer over NVLink — so the transfer of tile t
+ * overlaps the math of tile t+1.  The caller zeroes the output, runs a rank barrier before and after (bnet_barrier).
+ *
+ * The reference has no counterpart (it moves bytes for NCCL): this is the B200 "compute step followed
+ * by a collective" path.  STATUS: compiles for sm_100a and its descriptor packing is checked against the CuTe
+ * definitions on the host (tests/test_utils.py), but it has not run on hardware yet — it is off unless BNET_TC=1 and
+ * every launch carries a watchdog that turns a stuck pipeline into an error code instead of a hang.
+ */
+#ifndef BNET_TC_H_
+#define BNET_TC_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { BNET_TC_ACT_NONE = 0, BNET_TC_ACT_RELU = 1 };
+#define BNET_TC_MAX_OUTS 16
+
+/* 1 when the driver exposes cuTensorMapEncodeTiled and the current device is compute capability 10.x */
+int bnet_tc_supported(void);
+
+/* How a problem is tiled (pure host function; also used by the tests).  Returns 0 and fills the plan, or -1. */
+typedef struct BnetTcPlan {
+  int swap;       /* 1: w rows fill the 128 TMEM lanes and x rows are the MMA N dimension (small batch) */
+  int bn;         /* MMA N (tile width of the other operand): 32, 64 or 128 */
+  int stages;     /* TMA -> MMA shared-memory pipeline depth */
+  int grid_x, grid_y, grid_z;
+  int smem_bytes;
+  int k_blocks;   /* 64-element K blocks in total */
+  int k_per_split;
+} BnetTcPlan;
+int bnet_tc_plan(int M, int N, int K, int reduce, int splits, BnetTcPlan* plan);
+
+/* err_dev: one int in device memory, 0 before the launch; non-zero afterwards = the watchdog tripped (value = role). */
+int bnet_tc_linear(const void* x, const void* w, const void* bias, void* out, int M, int N, int K, int ldx, int ldw,
+                   int ldo, int act, int* err_dev, void* stream);
+
+/* outs: n_outs device pointers to fp32 [M, ldo] buffers (this rank's mapping of every rank's output), or ONE multicast
+ * pointer when multicast != 0.  splits > 1 additionally splits K over grid.z (the adds make it free). */
+int bnet_tc_linear_reduce(const void* x, const void* w, const void* bias, void* const* outs, int n_outs, int multicast,
+                          int M, int N, int K, int ldx, int ldw, int ldo, int splits, int* err_dev, void* stream);
+
+/* The 64-bit shared-memory matrix descriptor (K-major, 128-byte swizzle) and the 32-bit instruction descriptor
+ * (bf16 x bf16 -> fp32) the kernel issues, exposed so a host test can compare them with the CuTe definitions. */
+uint64_t bnet_tc_smem_desc(uint32_t smem_addr);
+uint32_t bnet_tc_instr_desc(int m, int n);
+
+const char* bnet_tc_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

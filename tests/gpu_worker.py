@@ -573,6 +573,69 @@ def job_fused_bn():
     print("fused_bn ok", flush=True)
 
 
+def job_tc_linear():
+    """tcgen05 linear (csrc/cuda/tc_gemm.cu) vs an fp32 PyTorch reference: both operand orientations, ragged M/N/K,
+    bias, ReLU, non-trivial row pitches, and the autograd wrapper."""
+    from bagua_net_b200.ops import tc_linear
+
+    setup()
+    assert tc_linear.supported(), "tcgen05 linear reports unsupported on this GPU / driver"
+    assert tc_linear.self_check(verbose=True), "tc_linear self-check failed"
+    torch.manual_seed(3)
+    for (M, N, K) in [(1, 8, 8), (32, 4096, 25088), (64, 1000, 4096), (65, 520, 200), (512, 512, 4096), (1000, 1000, 1000)]:
+        x = torch.randn(M, K, device="cuda").bfloat16()
+        w = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16()
+        b = torch.randn(N, device="cuda").bfloat16()
+        for relu in (False, True):
+            y = tc_linear.linear(x, w, b, relu)
+            assert tc_linear.last_error() == 0, f"watchdog tripped at {M}x{N}x{K}"
+            ref = x.float() @ w.float().t() + b.float()
+            ref = torch.relu(ref) if relu else ref
+            err = (y.float() - ref).abs().max().item()
+            assert err < 0.08, f"tc_linear {M}x{N}x{K} relu={relu}: max abs err {err}"
+    # strided views (row pitch != K), no bias
+    big = torch.randn(96, 1024, device="cuda").bfloat16()
+    x, w = big[:40, 128:640], big[40:, 128:640]
+    y = tc_linear.linear(x, w)
+    assert tc_linear.last_error() == 0
+    assert (y.float() - x.float() @ w.float().t()).abs().max().item() < 0.5
+    # autograd wrapper against eager
+    x = torch.randn(32, 256, device="cuda").bfloat16().requires_grad_()
+    w = (torch.randn(128, 256, device="cuda") / 16).bfloat16().requires_grad_()
+    b = torch.randn(128, device="cuda").bfloat16().requires_grad_()
+    y = tc_linear.linear_bias_act(x, w, b, True)
+    y.float().square().sum().backward()
+    x2, w2, b2 = (t.detach().clone().requires_grad_() for t in (x, w, b))
+    torch.relu(torch.nn.functional.linear(x2, w2, b2)).float().square().sum().backward()
+    for a, r, name in ((x.grad, x2.grad, "dx"), (w.grad, w2.grad, "dw"), (b.grad, b2.grad, "db")):
+        rel = (a.float() - r.float()).norm() / (r.float().norm() + 1e-6)
+        assert rel < 0.05, f"{name}: rel err {rel}"
+    print(f"tc_linear ok, launches={tc_linear.LAUNCHES}")
+
+
+def job_tc_row_parallel():
+    """GEMM + all-reduce in one kernel: every rank multiplies its K-shard, the epilogue adds into every rank's output."""
+    from bagua_net_b200.ops import tc_linear
+    from bagua_net_b200.parallel import SymmComm
+
+    setup()
+    comm = SymmComm(64 << 20)
+    torch.manual_seed(11)                                  # same full problem on every rank
+    for (M, N, K, splits) in [(32, 512, 1024, 1), (32, 512, 4096, 4), (256, 384, 2048, 1), (130, 200, 512, 2)]:
+        xf = torch.randn(M, K * WORLD, device="cuda").bfloat16()
+        wf = (torch.randn(N, K * WORLD, device="cuda") / (K * WORLD) ** 0.5).bfloat16()
+        b = torch.randn(N, device="cuda").bfloat16()
+        x, w = xf[:, RANK * K:(RANK + 1) * K], wf[:, RANK * K:(RANK + 1) * K]
+        out = tc_linear.row_parallel_linear(x, w, comm, bias=b, splits=splits)
+        assert tc_linear.last_error() == 0, f"watchdog tripped at {M}x{N}x{K}"
+        ref = xf.float() @ wf.float().t() + b.float()
+        err = (out - ref).abs().max().item()
+        assert err < 0.05, f"row_parallel {M}x{N}x{K} splits={splits}: max abs err {err}"
+    torch.cuda.synchronize()
+    assert comm.status() == 0
+    print(f"tc_row_parallel ok (multicast={comm.has_multicast})")
+
+
 def job_pack_cast():
     from bagua_net_b200.ops import pack_cast
     from bagua_net_b200.parallel import SymmComm

@@ -187,3 +187,20 @@ def test_executor_single_grid_mode(env):
     """BNET_EXEC_GRID=1: all cluster queues served by ONE resident grid on one stream (one launch per wake-up)."""
     _run_worker("executor", 1, extra_env=env, timeout=120)
     _run_worker("executor_idle", 1, extra_env=dict(env, BNET_KERNEL_IDLE_US="100"), timeout=60)
+
+
+# ------------------------------------------------------------------ tcgen05 linear / fused GEMM + all-reduce
+# Written without access to a GPU and not yet validated on hardware: opt in with BNET_TEST_TC=1 (see
+# include/bnet/bnet_tc.h).  The kernel's waits carry a watchdog, so a wrong pipeline fails instead of hanging.
+_tc = pytest.mark.skipif(os.environ.get("BNET_TEST_TC") != "1", reason="set BNET_TEST_TC=1 to run the unvalidated tcgen05 path")
+
+
+@_tc
+def test_tcgen05_linear_matches_fp32_reference():
+    _run_worker("tc_linear", 1, timeout=240)
+
+
+@_tc
+@pytest.mark.multigpu
+def test_tcgen05_row_parallel_linear_2gpu():
+    _run_worker("tc_row_parallel", 2, timeout=240)

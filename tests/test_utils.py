@@ -10,6 +10,8 @@ import pytest
 
 from bagua_net_b200 import utils
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 
 def test_parse_user_pass_addr():
     assert utils.parse_user_pass_and_addr("nagle:1984@127.0.0.1:9090") == ("nagle", "1984", "127.0.0.1:9090")
@@ -260,3 +262,49 @@ def test_ddp_bucket_plan_invariants():
            512 * 512 * 9, 512, 25088 * 4096, 4096, 4096 * 4096, 4096, 4096 * 1000, 1000]
     plan, total = plan_buckets(vgg, 2, 8, 64.0)
     assert sum(vgg) <= total < sum(vgg) + 40 * 1024 and len(plan) >= 3
+
+
+def _cutlass_include():
+    import glob
+    import site
+
+    for sp in site.getsitepackages():
+        for cand in glob.glob(os.path.join(sp, "*", "data", "cutlass", "include")) + \
+                glob.glob(os.path.join(sp, "*", "3rdparty", "cutlass", "include")):
+            if os.path.exists(os.path.join(cand, "cute", "arch", "mma_sm100_desc.hpp")):
+                return cand
+    return None
+
+
+def test_tcgen05_descriptors_match_cute_and_plans_are_sane():
+    """The tcgen05 linear kernel (csrc/cuda/tc_gemm.cu) packs its instruction / shared-memory descriptors by hand;
+    csrc/tests/tc_desc_test.cc compares them with the CuTe bit-field definitions and checks the tiling plans."""
+    inc = _cutlass_include()
+    if inc is None:
+        pytest.skip("no CUTLASS headers with sm100 support in this environment")
+    from bagua_net_b200 import LIB_DIR, LIB_NAME
+    from bagua_net_b200.utils.native import load
+
+    load()
+    exe = os.path.join(ROOT, "build", "tests", "tc_desc_test")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.run([cxx, "-std=c++17", "-O1", f"-I{inc}", f"-I{ROOT}/include", "-I/usr/local/cuda/include",
+                    os.path.join(ROOT, "csrc", "tests", "tc_desc_test.cc"), "-ldl", "-o", exe], check=True, timeout=300)
+    r = subprocess.run([exe, os.path.join(LIB_DIR, LIB_NAME)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_tc_linear_python_plan_and_gating(monkeypatch):
+    from bagua_net_b200.ops import tc_linear
+
+    monkeypatch.delenv("BNET_TC", raising=False)
+    assert not tc_linear.enabled()                       # unvalidated on hardware: strictly opt-in
+    p = tc_linear.plan(32, 4096, 25088)                  # VGG16 fc1 at the flagship batch: weights fill the TMEM lanes
+    assert p["swap"] == 1 and p["bn"] == 32 and p["grid_y"] == 32 and p["k_blocks"] == 392
+    p = tc_linear.plan(4096, 4096, 4096, reduce=True, splits=4)
+    assert p["swap"] == 0 and p["bn"] == 128 and p["grid_z"] == 4 and p["k_per_split"] == 16
+    assert p["smem_bytes"] + 1024 <= 227 * 1024
+    with pytest.raises(ValueError):
+        tc_linear.plan(32, 64, 100)
+    assert tc_linear.self_check() is False or __import__("torch").cuda.is_available()   # no GPU here: a clean False
