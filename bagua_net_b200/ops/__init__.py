@@ -5,6 +5,8 @@
 * ``pack_cast``                          — multi-tensor pack with dtype cast into a flat buffer
 * ``ConvBiasReLU``                       — conv + fused bias/ReLU/max-pool forward and backward passes
 * ``p2p``                                — the NVLink transport's copy / reduce / cast executor
+* ``tc_linear``                          — tcgen05/TMEM/TMA linear (+bias+ReLU) and the fused row-parallel GEMM + all-reduce
+                                           (opt-in: BNET_TC=1; import it as ``bagua_net_b200.ops.tc_linear``)
 """
 from .collectives import all_reduce, all_reduce_oneshot, fused_allreduce_sgd, pack_cast  # noqa: F401
 from .fused_nn import ConvBiasReLU  # noqa: F401
