@@ -29,7 +29,7 @@ LAUNCHES = 0
 
 class Plan(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("swap", "bn", "stages", "grid_x", "grid_y", "grid_z", "smem_bytes", "k_blocks",
-                                       "k_per_split")]
+                                       "k_per_split", "ctas")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

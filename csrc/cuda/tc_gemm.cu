@@ -140,6 +140,7 @@ __device__ __forceinline__ void multimem_red_add_v4_f32(float* mc, const float4&
 // ------------------------------------------------------------------------------------------------ kernel
 struct TcArgs {
   int rows_a, rows_b;        // valid rows of the lane / column operand
+  int tiles_a, n_tiles;      // 128-row blocks of the lane operand; output tiles in total (tile t = (t % tiles_a, t / tiles_a))
   int k_blocks;              // ceil(K / 64)
   int k_per_split;           // K blocks handled by one grid.z slice
   int ldo;                   // elements between output rows
@@ -157,25 +158,35 @@ struct Smem {
   static constexpr int kStageBytes = kABytes + kBBytes;
 };
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+
 // kSwap:   false -> A = x (lane i = batch row m), B = w (column j = feature n); out[m, n] = out[i * ldo + j]
 //          true  -> A = w (lane i = feature n),   B = x (column j = batch row m); out[m, n] = out[j * ldo + i]
 // kReduce: fp32 adds into args.outs[] instead of a bf16 store
+//
+// Persistent over output tiles: CTA c takes tiles c, c + gridDim.x, ... (consecutive CTAs share the column operand's
+// block, so it is read from HBM once and from L2 afterwards).  The shared-memory ring runs straight through tile
+// boundaries, and the accumulator is double-buffered in TMEM (2 x BN columns): the epilogue of tile t drains one half
+// while the MMAs of tile t+1 fill the other.  With gridDim.x == n_tiles every CTA simply does one tile.
 template <int BN, int kStages, bool kSwap, bool kReduce>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcArgs args) {
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M = 128");
   static_assert((BN & (BN - 1)) == 0 && BN >= 32, "TMEM allocations are powers of two >= 32 columns");
+  constexpr uint32_t kTmemCols = 2 * BN;          // two accumulator stages
   extern __shared__ uint8_t smem_raw[];
   // swizzle-128B atoms must start on 1024-byte boundaries of the shared window
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* const tiles = smem_raw + (base - raw);
   uint64_t* const bars = reinterpret_cast<uint64_t*>(tiles + kStages * Smem<BN>::kStageBytes);
-  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kStages, acc_full = empty0 + 8 * kStages;
-  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kStages;
+  const uint32_t acc_full0 = empty0 + 8 * kStages, acc_empty0 = acc_full0 + 16;
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int a_row0 = blockIdx.y * kBM, b_row0 = blockIdx.x * BN;
   const int kb_begin = blockIdx.z * args.k_per_split;
   const int kb_end = min(kb_begin + args.k_per_split, args.k_blocks);
   const int nkb = kb_end - kb_begin;       // >= 1 by construction of the grid
@@ -187,93 +198,118 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       ptx::mbar_init(bars + s, 1);               // full: the producer's arrive.expect_tx (+ TMA bytes)
       ptx::mbar_init(bars + kStages + s, 1);     // empty: one tcgen05.commit
     }
-    ptx::mbar_init(bars + 2 * kStages, 1);       // accumulator complete
+    for (int s = 0; s < 2; s++) {
+      ptx::mbar_init(bars + 2 * kStages + s, 1);       // accumulator stage complete: one tcgen05.commit
+      ptx::mbar_init(bars + 2 * kStages + 2 + s, 128); // accumulator stage drained: every epilogue thread
+    }
     ptx::fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), BN);
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem_d = *tmem_slot;
+  const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int i = 0; i < nkb; i++) {
-        const int s = i % kStages;
-        const uint32_t round = i / kStages;
-        if (round > 0 && !mbar_wait_wd(empty0 + 8 * s, (round - 1) & 1, args.err, 1)) break;
-        const uint32_t a_dst = base + s * Smem<BN>::kStageBytes;
-        mbar_expect_tx(full0 + 8 * s, Smem<BN>::kStageBytes);
-        tma_load_2d(a_dst, &map_a, full0 + 8 * s, (kb_begin + i) * kBK, a_row0);
-        tma_load_2d(a_dst + kABytes, &map_b, full0 + 8 * s, (kb_begin + i) * kBK, b_row0);
+      uint32_t g = 0;                              // k-blocks issued by this CTA so far (ring position)
+      bool alive = true;
+      for (int t = blockIdx.x; t < args.n_tiles && alive; t += gridDim.x) {
+        const int a_row0 = (t % args.tiles_a) * kBM, b_row0 = (t / args.tiles_a) * BN;
+        for (int i = 0; i < nkb; i++, g++) {
+          const uint32_t s = g % kStages, round = g / kStages;
+          if (round > 0 && !mbar_wait_wd(empty0 + 8 * s, (round - 1) & 1, args.err, 1)) { alive = false; break; }
+          const uint32_t a_dst = base + s * Smem<BN>::kStageBytes;
+          mbar_expect_tx(full0 + 8 * s, Smem<BN>::kStageBytes);
+          tma_load_2d(a_dst, &map_a, full0 + 8 * s, (kb_begin + i) * kBK, a_row0);
+          tma_load_2d(a_dst + kABytes, &map_b, full0 + 8 * s, (kb_begin + i) * kBK, b_row0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = instr_desc_bf16_f32(kBM, BN);
+      uint32_t g = 0, lt = 0;                      // ring position; tiles done by this CTA
       bool alive = true;
-      for (int i = 0; i < nkb && alive; i++) {
-        const int s = i % kStages;
-        alive = mbar_wait_wd(full0 + 8 * s, (i / kStages) & 1, args.err, 2);
-        if (!alive) break;
+      for (int t = blockIdx.x; t < args.n_tiles && alive; t += gridDim.x, lt++) {
+        const uint32_t as = lt & 1, use = lt >> 1;
+        // the epilogue must have drained this accumulator stage (two tiles ago) before it is overwritten
+        if (use > 0 && !mbar_wait_wd(acc_empty0 + 8 * as, (use - 1) & 1, args.err, 2)) break;
         tc_fence_after_sync();
-        const uint32_t a_src = base + s * Smem<BN>::kStageBytes;
-        const uint64_t da = smem_desc_sw128(a_src), db = smem_desc_sw128(a_src + kABytes);
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int i = 0; i < nkb; i++, g++) {
+          const uint32_t s = g % kStages;
+          alive = mbar_wait_wd(full0 + 8 * s, (g / kStages) & 1, args.err, 2);
+          if (!alive) break;
+          tc_fence_after_sync();
+          const uint32_t a_src = base + s * Smem<BN>::kStageBytes;
+          const uint64_t da = smem_desc_sw128(a_src), db = smem_desc_sw128(a_src + kABytes);
 #pragma unroll
-        for (int k = 0; k < kBK / kUmmaK; k++) {
-          // +32 bytes (2 x 16-byte units) along K inside the 128-byte swizzle row per K = 16 slice
-          umma_bf16(tmem_d, da + uint64_t(k * (kUmmaK * 2 / 16)), db + uint64_t(k * (kUmmaK * 2 / 16)), idesc,
-                    (i | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < kBK / kUmmaK; k++) {
+            // +32 bytes (2 x 16-byte units) along K inside the 128-byte swizzle row per K = 16 slice
+            umma_bf16(tmem_d, da + uint64_t(k * (kUmmaK * 2 / 16)), db + uint64_t(k * (kUmmaK * 2 / 16)), idesc,
+                      (i | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty0 + 8 * s);            // the stage may be refilled once these MMAs have read it
         }
-        umma_commit(empty0 + 8 * s);              // the stage may be refilled once these MMAs have read it
+        if (alive) umma_commit(acc_full0 + 8 * as);
       }
-      if (alive) umma_commit(acc_full);
     }
   } else {
     // ---- epilogue: 4 warps x 32 lanes = the tile's 128 accumulator rows
     const int q = warp & 3;                        // the TMEM lane quarter this warp may read
-    const int i_glob = a_row0 + q * 32 + lane;     // row of the lane operand this thread owns
-    if (mbar_wait_wd(acc_full, 0, args.err, 3)) {
+    const bool add_bias = args.bias != nullptr && (!kReduce || blockIdx.z == 0);
+    uint32_t lt = 0;
+    for (int t = blockIdx.x; t < args.n_tiles; t += gridDim.x, lt++) {
+      const uint32_t as = lt & 1;
+      const int a_row0 = (t % args.tiles_a) * kBM, b_row0 = (t / args.tiles_a) * BN;
+      const int i_glob = a_row0 + q * 32 + lane;   // row of the lane operand this thread owns
+      if (!mbar_wait_wd(acc_full0 + 8 * as, (lt >> 1) & 1, args.err, 3)) break;
       tc_fence_after_sync();
+      const uint32_t tmem_d = tmem_base + as * BN;
       float bias_i = 0.f;
-      const bool add_bias = args.bias != nullptr && (!kReduce || blockIdx.z == 0);
       if (kSwap && add_bias && i_glob < args.rows_a) bias_i = __bfloat162float(args.bias[i_glob]);
 #pragma unroll 1
       for (int c = 0; c < BN / 16; c++) {
         uint32_t v[16];
         __syncwarp();                                 // tcgen05.ld is .sync.aligned: reconverge after the guarded stores
-        tmem_ld_16(tmem_d + (uint32_t(q * 32) << 16) + uint32_t(c * 16), v);   // warp-collective: no divergence above
+        tmem_ld_16(tmem_d + (uint32_t(q * 32) << 16) + uint32_t(c * 16), v);
+        if (c == BN / 16 - 1) {
+          // the whole accumulator stage is in registers: hand it back to the MMA warp before the stores
+          tc_fence_before_sync();
+          mbar_arrive(acc_empty0 + 8 * as);
+        }
         const int j0 = b_row0 + c * 16;
         if (i_glob >= args.rows_a || j0 >= args.rows_b) continue;
         float f[16];
 #pragma unroll
-        for (int t = 0; t < 16; t++) {
-          float b = kSwap ? bias_i : ((add_bias && j0 + t < args.rows_b) ? __bfloat162float(args.bias[j0 + t]) : 0.f);
-          f[t] = __uint_as_float(v[t]) + b;
-          if (!kReduce && args.act == BNET_TC_ACT_RELU) f[t] = fmaxf(f[t], 0.f);
+        for (int u = 0; u < 16; u++) {
+          float b = kSwap ? bias_i : ((add_bias && j0 + u < args.rows_b) ? __bfloat162float(args.bias[j0 + u]) : 0.f);
+          f[u] = __uint_as_float(v[u]) + b;
+          if (!kReduce && args.act == BNET_TC_ACT_RELU) f[u] = fmaxf(f[u], 0.f);
         }
         if constexpr (!kReduce) {
           __nv_bfloat16* out = static_cast<__nv_bfloat16*>(args.outs[0]);
           if constexpr (kSwap) {
-            // out[(j0 + t) * ldo + i]: for every t the warp writes 32 consecutive features
+            // out[(j0 + u) * ldo + i]: for every u the warp writes 32 consecutive features
 #pragma unroll
-            for (int t = 0; t < 16; t++)
-              if (j0 + t < args.rows_b) out[size_t(j0 + t) * args.ldo + i_glob] = __float2bfloat16_rn(f[t]);
+            for (int u = 0; u < 16; u++)
+              if (j0 + u < args.rows_b) out[size_t(j0 + u) * args.ldo + i_glob] = __float2bfloat16_rn(f[u]);
           } else {
             __nv_bfloat16* row = out + size_t(i_glob) * args.ldo + j0;
             if (j0 + 16 <= args.rows_b && (reinterpret_cast<uintptr_t>(row) & 15) == 0) {
               uint32_t w[8];
 #pragma unroll
-              for (int t = 0; t < 8; t++) {
-                __nv_bfloat162 p = __floats2bfloat162_rn(f[2 * t], f[2 * t + 1]);
-                w[t] = *reinterpret_cast<uint32_t*>(&p);
+              for (int u = 0; u < 8; u++) {
+                __nv_bfloat162 p = __floats2bfloat162_rn(f[2 * u], f[2 * u + 1]);
+                w[u] = *reinterpret_cast<uint32_t*>(&p);
               }
               reinterpret_cast<uint4*>(row)[0] = make_uint4(w[0], w[1], w[2], w[3]);
               reinterpret_cast<uint4*>(row)[1] = make_uint4(w[4], w[5], w[6], w[7]);
             } else {
 #pragma unroll
-              for (int t = 0; t < 16; t++)
-                if (j0 + t < args.rows_b) row[t] = __float2bfloat16_rn(f[t]);
+              for (int u = 0; u < 16; u++)
+                if (j0 + u < args.rows_b) row[u] = __float2bfloat16_rn(f[u]);
             }
           }
         } else {
@@ -282,23 +318,23 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             float* out = static_cast<float*>(args.outs[o]);
             if constexpr (kSwap) {
 #pragma unroll
-              for (int t = 0; t < 16; t++) {
-                if (j0 + t >= args.rows_b) continue;
-                float* p = out + size_t(j0 + t) * args.ldo + i_glob;
-                if (args.multicast) multimem_red_add_f32(p, f[t]); else ptx::red_add_f32(p, f[t]);
+              for (int u = 0; u < 16; u++) {
+                if (j0 + u >= args.rows_b) continue;
+                float* p = out + size_t(j0 + u) * args.ldo + i_glob;
+                if (args.multicast) multimem_red_add_f32(p, f[u]); else ptx::red_add_f32(p, f[u]);
               }
             } else {
               float* row = out + size_t(i_glob) * args.ldo + j0;
               const bool vec = j0 + 16 <= args.rows_b && (reinterpret_cast<uintptr_t>(row) & 15) == 0;
 #pragma unroll
-              for (int t = 0; t < 16; t += 4) {
+              for (int u = 0; u < 16; u += 4) {
                 if (vec) {
-                  const float4 x = make_float4(f[t], f[t + 1], f[t + 2], f[t + 3]);
-                  if (args.multicast) multimem_red_add_v4_f32(row + t, x); else ptx::red_add_v4_f32(row + t, x);
+                  const float4 x = make_float4(f[u], f[u + 1], f[u + 2], f[u + 3]);
+                  if (args.multicast) multimem_red_add_v4_f32(row + u, x); else ptx::red_add_v4_f32(row + u, x);
                 } else {
-                  for (int u = t; u < t + 4; u++) {
-                    if (j0 + u >= args.rows_b) continue;
-                    if (args.multicast) multimem_red_add_f32(row + u, f[u]); else ptx::red_add_f32(row + u, f[u]);
+                  for (int e = u; e < u + 4; e++) {
+                    if (j0 + e >= args.rows_b) continue;
+                    if (args.multicast) multimem_red_add_f32(row + e, f[e]); else ptx::red_add_f32(row + e, f[e]);
                   }
                 }
               }
@@ -314,7 +350,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   __syncthreads();
   if (warp == 1) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_d, BN);
+    tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -366,13 +402,25 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs& a, const 
   const int smem = p.smem_bytes;
   std::call_once(once, [&] { attr_rc = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
   if (attr_rc != cudaSuccess) { g_err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(attr_rc); return -1; }
-  kern<<<dim3(p.grid_x, p.grid_y, p.grid_z), kThreads, smem, st>>>(ma, mb, a);
+  kern<<<dim3(p.ctas, 1, p.grid_z), kThreads, smem, st>>>(ma, mb, a);
   cudaError_t rc = cudaGetLastError();
   if (rc != cudaSuccess) { g_err = std::string("tc_linear launch: ") + cudaGetErrorString(rc); return -1; }
   return 1;
 }
 
 constexpr int stages_for(int bn) { return bn <= 64 ? 6 : 5; }
+
+// SMs of the current device; 148 (B200) when there is none to ask (host-only planning in the CPU tests)
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
+      n = v;
+    else { (void)cudaGetLastError(); n = 148; }
+  }
+  return n;
+}
 
 int run(const void* x, const void* w, const void* bias, void* const* outs, int n_outs, int multicast, bool reduce, int M,
         int N, int K, int ldx, int ldw, int ldo, int act, int splits, int* err_dev, void* stream) {
@@ -386,7 +434,7 @@ int run(const void* x, const void* w, const void* bias, void* const* outs, int n
   CUtensorMap ma, mb;
   if (!make_map(&ma, pa, rows_a, K, lda, kBM) || !make_map(&mb, pb, rows_b, K, ldb, p.bn)) return -1;
   TcArgs a{};
-  a.rows_a = rows_a; a.rows_b = rows_b; a.k_blocks = p.k_blocks; a.k_per_split = p.k_per_split; a.ldo = ldo; a.act = act;
+  a.rows_a = rows_a; a.rows_b = rows_b; a.tiles_a = p.grid_y; a.n_tiles = p.grid_x * p.grid_y; a.k_blocks = p.k_blocks; a.k_per_split = p.k_per_split; a.ldo = ldo; a.act = act;
   a.bias = static_cast<const __nv_bfloat16*>(bias);
   for (int i = 0; i < n_outs; i++) a.outs[i] = outs[i];
   a.n_outs = n_outs; a.multicast = multicast; a.err = err_dev;
@@ -432,9 +480,13 @@ BNET_API int bnet_tc_plan(int M, int N, int K, int reduce, int splits, BnetTcPla
   if (z > p->k_blocks) z = p->k_blocks;
   p->k_per_split = (p->k_blocks + z - 1) / z;
   p->grid_z = (p->k_blocks + p->k_per_split - 1) / p->k_per_split;   // no empty slices
-  // tiles + alignment slack + (2 * stages + 1) mbarriers + the TMEM address slot
-  p->smem_bytes = p->stages * (kABytes + p->bn * kBK * 2) + 1024 + (2 * p->stages + 1) * 8 + 16;
-  if (p->grid_y > 65535 || p->grid_z > 65535) { g_err = "problem too large for one launch"; return -1; }
+  // tiles + alignment slack + (2 * stages + 4) mbarriers + the TMEM address slot
+  p->smem_bytes = p->stages * (kABytes + p->bn * kBK * 2) + 1024 + (2 * p->stages + 4) * 8 + 16;
+  if (p->grid_z > 65535 || (long long)p->grid_x * p->grid_y > 0x7fffffffLL) { g_err = "problem too large for one launch"; return -1; }
+  // persistent once there are more tiles than SMs: one CTA per SM (shared memory allows no second one anyway)
+  const int n_tiles = p->grid_x * p->grid_y;
+  const int per_slice = sm_count() / p->grid_z > 0 ? sm_count() / p->grid_z : 1;
+  p->ctas = n_tiles < per_slice ? n_tiles : per_slice;
   return 0;
 }
 

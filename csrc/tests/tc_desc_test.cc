@@ -63,18 +63,21 @@ int main(int argc, char** argv) {
       {4096, 4096, 4096, 1, 1, 0, 128, 32, 32, 1},
       {32, 4096, 25088, 1, 4, 1, 32, 1, 32, 4},     // split-K on top of the cross-rank adds
       {8, 16, 64, 1, 8, 1, 32, 1, 1, 1},            // one K block: nothing to split
+      {8192, 8192, 8192, 0, 1, 0, 128, 64, 64, 1},  // 4096 tiles on 148 SMs: persistent
   };
   for (const Case& c : cases) {
     BnetTcPlan p;
     if (plan(c.M, c.N, c.K, c.reduce, c.splits, &p) != 0 || p.swap != c.swap || p.bn != c.bn || p.grid_x != c.gx ||
         p.grid_y != c.gy || p.grid_z != c.gz || p.smem_bytes + 1024 > 232448 || p.k_per_split * p.grid_z < p.k_blocks ||
-        p.k_per_split * (p.grid_z - 1) >= p.k_blocks) {
+        p.k_per_split * (p.grid_z - 1) >= p.k_blocks || p.ctas < 1 || p.ctas > p.grid_x * p.grid_y ||
+        p.ctas * p.grid_z > 148 + p.grid_z) {
       printf("plan %dx%dx%d: swap %d bn %d grid %d %d %d smem %d\n", c.M, c.N, c.K, p.swap, p.bn, p.grid_x, p.grid_y, p.grid_z,
              p.smem_bytes);
       bad++;
     }
   }
   BnetTcPlan p;
+  if (plan(8192, 8192, 8192, 0, 1, &p) != 0 || p.ctas != 148) { printf("persistent plan: ctas %d\n", p.ctas); bad++; }
   if (plan(32, 64, 100, 0, 1, &p) == 0) { printf("K = 100 must be rejected (row pitch not a multiple of 16 bytes)\n"); bad++; }
   printf("tc_desc_test: %s\n", bad ? "FAILED" : "ok");
   return bad ? 1 : 0;

@@ -35,10 +35,11 @@ typedef struct BnetTcPlan {
   int swap;       /* 1: w rows fill the 128 TMEM lanes and x rows are the MMA N dimension (small batch) */
   int bn;         /* MMA N (tile width of the other operand): 32, 64 or 128 */
   int stages;     /* TMA -> MMA shared-memory pipeline depth */
-  int grid_x, grid_y, grid_z;
+  int grid_x, grid_y, grid_z;   /* tiles along the column operand, tiles along the lane operand, K slices */
   int smem_bytes;
   int k_blocks;   /* 64-element K blocks in total */
   int k_per_split;
+  int ctas;       /* CTAs launched per K slice: min(tiles, SMs / K slices); each walks tiles ctas apart (persistent) */
 } BnetTcPlan;
 int bnet_tc_plan(int M, int N, int K, int reduce, int splits, BnetTcPlan* plan);
 
