@@ -408,7 +408,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs& a, const 
   return 1;
 }
 
-constexpr int stages_for(int bn) { return bn <= 64 ? 6 : 5; }
+constexpr int stages_for(int bn) { return bn <= 64 ? 6 : (bn <= 128 ? 5 : 4); }
 
 // SMs of the current device; 148 (B200) when there is none to ask (host-only planning in the CPU tests)
 int sm_count() {
@@ -446,6 +446,7 @@ int run(const void* x, const void* w, const void* bias, void* const* outs, int n
   BNET_TC_CASE(32, true)
   BNET_TC_CASE(64, true)
   BNET_TC_CASE(128, false)
+  BNET_TC_CASE(256, false)
 #undef BNET_TC_CASE
   g_err = "no kernel for this plan";
   return -1;
@@ -471,6 +472,9 @@ BNET_API int bnet_tc_plan(int M, int N, int K, int reduce, int splits, BnetTcPla
   if (K % 8) { g_err = "K must be a multiple of 8 (16-byte TMA row pitch)"; return -1; }
   p->swap = M <= 64 ? 1 : 0;
   p->bn = p->swap ? (M <= 32 ? 32 : 64) : 128;
+  // 128 x 256 tiles (the whole TMEM: 2 x 256 accumulator columns) once they still fill every SM: half the MMA issues and
+  // 1.5x the arithmetic intensity per shared-memory byte of a 128 x 128 tile
+  if (!p->swap && (long long)((N + 255) / 256) * ((M + kBM - 1) / kBM) >= sm_count()) p->bn = 256;
   p->stages = stages_for(p->bn);
   const int rows_a = p->swap ? N : M, rows_b = p->swap ? M : N;
   p->grid_x = (rows_b + p->bn - 1) / p->bn;

@@ -60,10 +60,11 @@ int main(int argc, char** argv) {
       {32, 4096, 25088, 0, 1, 1, 32, 1, 32, 1},     // VGG16 classifier fc1 at batch 32: weights fill the lanes
       {64, 4096, 4096, 0, 1, 1, 64, 1, 32, 1},
       {256, 1000, 4096, 0, 1, 0, 128, 8, 2, 1},
-      {4096, 4096, 4096, 1, 1, 0, 128, 32, 32, 1},
+      {4096, 4096, 4096, 1, 1, 0, 256, 16, 32, 1},     // 512 tiles of 128 x 256 >= 148 SMs
+      {1024, 4096, 4096, 0, 1, 0, 128, 32, 8, 1},      // 128 tiles of 128 x 256 would leave SMs idle: stay at 128 x 128
       {32, 4096, 25088, 1, 4, 1, 32, 1, 32, 4},     // split-K on top of the cross-rank adds
       {8, 16, 64, 1, 8, 1, 32, 1, 1, 1},            // one K block: nothing to split
-      {8192, 8192, 8192, 0, 1, 0, 128, 64, 64, 1},  // 4096 tiles on 148 SMs: persistent
+      {8192, 8192, 8192, 0, 1, 0, 256, 32, 64, 1},  // 2048 tiles on 148 SMs: persistent
   };
   for (const Case& c : cases) {
     BnetTcPlan p;

@@ -33,7 +33,7 @@ int bnet_tc_supported(void);
 /* How a problem is tiled (pure host function; also used by the tests).  Returns 0 and fills the plan, or -1. */
 typedef struct BnetTcPlan {
   int swap;       /* 1: w rows fill the 128 TMEM lanes and x rows are the MMA N dimension (small batch) */
-  int bn;         /* MMA N (tile width of the other operand): 32, 64 or 128 */
+  int bn;         /* MMA N (tile width of the other operand): 32 / 64 (swapped), 128 or 256 */
   int stages;     /* TMA -> MMA shared-memory pipeline depth */
   int grid_x, grid_y, grid_z;   /* tiles along the column operand, tiles along the lane operand, K slices */
   int smem_bytes;

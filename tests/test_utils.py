@@ -303,7 +303,7 @@ def test_tc_linear_python_plan_and_gating(monkeypatch):
     p = tc_linear.plan(32, 4096, 25088)                  # VGG16 fc1 at the flagship batch: weights fill the TMEM lanes
     assert p["swap"] == 1 and p["bn"] == 32 and p["grid_y"] == 32 and p["k_blocks"] == 392
     p = tc_linear.plan(4096, 4096, 4096, reduce=True, splits=4)
-    assert p["swap"] == 0 and p["bn"] == 128 and p["grid_z"] == 4 and p["k_per_split"] == 16
+    assert p["swap"] == 0 and p["bn"] == 256 and p["grid_z"] == 4 and p["k_per_split"] == 16 and p["ctas"] == 37
     assert p["smem_bytes"] + 1024 <= 227 * 1024
     with pytest.raises(ValueError):
         tc_linear.plan(32, 64, 100)
