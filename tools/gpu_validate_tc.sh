@@ -23,6 +23,7 @@ y = t.linear(x, w); torch.cuda.synchronize()
 print("no-swap: err flag", t.last_error(), "max abs err", (y.float() - x.float() @ w.float().t()).abs().max().item())
 print("self_check", t.self_check(verbose=True))
 PY
+TAILN=60 step probe 200 python tools/tc_probe.py
 step sanitizer 300 compute-sanitizer --tool memcheck python -c "
 import torch
 from bagua_net_b200.ops import tc_linear as t
