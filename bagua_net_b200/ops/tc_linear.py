@@ -44,6 +44,8 @@ def _L():
         _lib.bnet_tc_plan.argtypes = [i, i, i, i, i, C.POINTER(Plan)]
         _lib.bnet_tc_linear.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, i, vp, vp]
         _lib.bnet_tc_linear_reduce.argtypes = [vp, vp, vp, C.POINTER(vp), i, i, i, i, i, i, i, i, i, vp, vp]
+        _lib.bnet_tc_linear_dgrad.argtypes = [vp, vp, vp, i, i, i, i, i, i, vp, vp]
+        _lib.bnet_tc_linear_wgrad.argtypes = [vp, vp, vp, i, i, i, i, i, i, vp, vp]
         _lib.bnet_tc_last_error.restype = C.c_char_p
         _lib.bnet_tc_smem_desc.restype = C.c_uint64
         _lib.bnet_tc_smem_desc.argtypes = [C.c_uint32]
@@ -122,9 +124,51 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, r
     return out
 
 
+def linear_dgrad(gy: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """``gy @ w`` (dX of a linear layer): gy [M,N], w [N,K] as stored — w is read MN-major, no transpose is made."""
+    global LAUNCHES
+    M, N = gy.shape
+    K = w.shape[1]
+    assert gy.dtype == w.dtype == torch.bfloat16 and w.shape[0] == N and gy.stride(1) == 1 and w.stride(1) == 1
+    dx = torch.empty((M, K), dtype=torch.bfloat16, device=gy.device)
+    L = _L()
+    rc = L.bnet_tc_linear_dgrad(gy.data_ptr(), w.data_ptr(), dx.data_ptr(), M, N, K, gy.stride(0), w.stride(0), dx.stride(0),
+                                _err_flag(gy.device.index).data_ptr(), _stream())
+    if rc < 0:
+        raise RuntimeError(f"bnet_tc_linear_dgrad: {L.bnet_tc_last_error().decode()}")
+    LAUNCHES += rc
+    return dx
+
+
+def linear_wgrad(gy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """``gy.T @ x`` (dW of a linear layer): gy [M,N], x [M,K] as stored — both read MN-major (the batch is the reduction)."""
+    global LAUNCHES
+    M, N = gy.shape
+    K = x.shape[1]
+    assert gy.dtype == x.dtype == torch.bfloat16 and x.shape[0] == M and gy.stride(1) == 1 and x.stride(1) == 1
+    dw = torch.empty((N, K), dtype=torch.bfloat16, device=gy.device)
+    L = _L()
+    rc = L.bnet_tc_linear_wgrad(gy.data_ptr(), x.data_ptr(), dw.data_ptr(), M, N, K, gy.stride(0), x.stride(0), dw.stride(0),
+                                _err_flag(gy.device.index).data_ptr(), _stream())
+    if rc < 0:
+        raise RuntimeError(f"bnet_tc_linear_wgrad: {L.bnet_tc_last_error().decode()}")
+    LAUNCHES += rc
+    return dw
+
+
+def _bwd_on_tc(gy, x, w) -> bool:
+    """The backward GEMMs run on the tcgen05 kernel too (BNET_TC_BWD=0 keeps them on cuBLAS) when the operands meet the
+    TMA constraints: 16-byte row pitches, and more than 64 output features for dW."""
+    if os.environ.get("BNET_TC_BWD", "1") != "1":
+        return False
+    N, K = w.shape
+    return (gy.is_contiguous() and N > 64 and N % 8 == 0 and K % 8 == 0 and x.stride(1) == 1 and x.stride(0) % 8 == 0
+            and w.stride(1) == 1 and w.stride(0) % 8 == 0)
+
+
 class _LinearAct(torch.autograd.Function):
-    """Forward on the tcgen05 kernel (bias and ReLU in its epilogue); the two backward GEMMs need MN-major operands
-    and stay on cuBLAS for now."""
+    """Forward on the tcgen05 kernel (bias and ReLU in its epilogue); dX and dW on the same kernel with MN-major
+    operands (no transposed copies), or on cuBLAS when the shapes do not meet the TMA constraints."""
 
     @staticmethod
     def forward(ctx, x, w, bias, relu):
@@ -139,8 +183,13 @@ class _LinearAct(torch.autograd.Function):
         x, w, y = ctx.saved_tensors
         if ctx.relu:
             gy = gy * (y > 0).to(gy.dtype)
-        gx = gy @ w if ctx.needs_input_grad[0] else None
-        gw = gy.t() @ x if ctx.needs_input_grad[1] else None
+        gy = gy.contiguous()
+        tc = _bwd_on_tc(gy, x, w)
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            gx = linear_dgrad(gy, w) if tc else gy @ w
+        if ctx.needs_input_grad[1]:
+            gw = linear_wgrad(gy, x) if tc else gy.t() @ x
         gb = gy.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
         return gx, gw, gb, None
 
@@ -238,6 +287,18 @@ def self_check(verbose: bool = False) -> bool:
                 print(f"tc_linear {M}x{N}x{K} relu={relu}: max abs err {err:.4f}")
             if not (err < 0.06):
                 return False
+            if N > 64 and os.environ.get("BNET_TC_BWD", "1") == "1":       # the backward GEMMs (MN-major operands)
+                gy = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+                dx, dw = linear_dgrad(gy, w), linear_wgrad(gy, x)
+                if last_error():
+                    return False
+                e1 = (dx.float() - gy.float() @ w.float()).abs().max().item()
+                rdw = gy.float().t() @ x.float()
+                e2 = ((dw.float() - rdw).abs().max() / rdw.abs().max().clamp_min(1e-6)).item()
+                if verbose:
+                    print(f"tc_linear dgrad max abs err {e1:.4f}, wgrad max rel err {e2:.4f}")
+                if not (e1 < 0.1 and e2 < 0.02):
+                    return False
         return True
     except Exception as e:  # noqa: BLE001 — the caller falls back to cuBLAS
         if verbose:

@@ -3,9 +3,13 @@
 //   D[i, j] = sum_k A[i, k] * B[j, k]        A: "lane" operand, 128 rows per tile (one per TMEM lane)
 //                                            B: "column" operand, BN rows per tile (the MMA N dimension)
 //
-// Both operands are K-major bf16 matrices (a torch Linear's activation [M,K] and weight [N,K] as they are), so either
-// can take either role: with a large batch x is A and w is B; with a small batch (M <= 64) the roles swap so that the
-// 128 TMEM lanes are filled by output features instead of 3/4 padding rows.
+// Forward: both operands are K-major bf16 matrices (a torch Linear's activation [M,K] and weight [N,K] as they are), so
+// either can take either role: with a large batch x is A and w is B; with a small batch (M <= 64) the roles swap so that
+// the 128 TMEM lanes are filled by output features instead of 3/4 padding rows.
+// Backward: dX = gY . W reduces over N and dW = gY^T . X reduces over M, so W, gY and X appear with the reduction
+// dimension OUTER ("MN-major" operands).  Those are staged as [64 reduction rows x 64 MN elements] TMA boxes (one per 64
+// MN elements of the tile, 8 KiB each) and described to the MMA with the MN-major form of the shared-memory descriptor;
+// no transposed copy of any tensor is ever made.
 //
 // One CTA = one output tile, 6 warps, warp-specialised (guide "Anatomy of a Blackwell GEMM kernel"):
 //   warp 0, one lane   TMA producer: cp.async.bulk.tensor.2d of a [128 x 64] A box and a [BN x 64] B box per stage,
@@ -51,8 +55,9 @@ thread_local std::string g_err;
 // Instruction descriptor, .kind::f16 (bit positions: cute/arch/mma_sm100_desc.hpp `InstrDescriptor`):
 //   [4,6) D format (1 = f32)  [7,10) A format (1 = bf16)  [10,13) B format (1 = bf16)
 //   15 / 16 A / B major (0 = K-major)   [17,23) N >> 3   [24,29) M >> 4
-__host__ __device__ constexpr uint32_t instr_desc_bf16_f32(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(n >> 3) << 17) | (uint32_t(m >> 4) << 24);
+__host__ __device__ constexpr uint32_t instr_desc_bf16_f32(int m, int n, bool a_mn = false, bool b_mn = false) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(a_mn) << 15) | (uint32_t(b_mn) << 16) | (uint32_t(n >> 3) << 17) |
+         (uint32_t(m >> 4) << 24);
 }
 
 // Shared-memory matrix descriptor of a K-major tile whose rows are 128 bytes, stored densely and swizzled by the
@@ -61,6 +66,15 @@ __host__ __device__ constexpr uint32_t instr_desc_bf16_f32(int m, int n) {
 //   [32,46) stride byte offset >> 4 = 1024 B between 8-row groups   [46,48) version = 1   [61,64) layout = 2 (SW128)
 __host__ __device__ constexpr uint64_t smem_desc_sw128(uint32_t smem_addr) {
   return uint64_t((smem_addr >> 4) & 0x3FFF) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) |
+         (uint64_t(2) << 61);
+}
+
+// The same for an MN-major tile staged as [64 reduction rows x 128 bytes] boxes, one per 64 MN elements, 8 KiB apart:
+//   leading byte offset = 8192 B between 64-element MN atoms, stride byte offset = 1024 B between 8-row reduction groups
+//   (CuTe: make_umma_desc<Major::MN> of tile_to_shape(Layout_MN_SW128_Atom<bf16>, (MN, 64), Step<_2,_1>) -> LBO 512, SBO 64).
+// One K = 16 slice is two 8-row groups further: +2048 B.
+__host__ __device__ constexpr uint64_t smem_desc_sw128_mn(uint32_t smem_addr) {
+  return uint64_t((smem_addr >> 4) & 0x3FFF) | (uint64_t(8192 >> 4) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) |
          (uint64_t(2) << 61);
 }
 
@@ -170,11 +184,13 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // block, so it is read from HBM once and from L2 afterwards).  The shared-memory ring runs straight through tile
 // boundaries, and the accumulator is double-buffered in TMEM (2 x BN columns): the epilogue of tile t drains one half
 // while the MMAs of tile t+1 fill the other.  With gridDim.x == n_tiles every CTA simply does one tile.
-template <int BN, int kStages, bool kSwap, bool kReduce>
+// kAMn / kBMn: the lane / column operand is MN-major (reduction dimension outer) instead of K-major
+template <int BN, int kStages, bool kSwap, bool kReduce, bool kAMn, bool kBMn>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcArgs args) {
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M = 128");
   static_assert((BN & (BN - 1)) == 0 && BN >= 32, "TMEM allocations are powers of two >= 32 columns");
+  static_assert(!kBMn || BN % 64 == 0, "an MN-major operand is staged in 64-element atoms");
   constexpr uint32_t kTmemCols = 2 * BN;          // two accumulator stages
   extern __shared__ uint8_t smem_raw[];
   // swizzle-128B atoms must start on 1024-byte boundaries of the shared window
@@ -221,14 +237,28 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if (round > 0 && !mbar_wait_wd(empty0 + 8 * s, (round - 1) & 1, args.err, 1)) { alive = false; break; }
           const uint32_t a_dst = base + s * Smem<BN>::kStageBytes;
           mbar_expect_tx(full0 + 8 * s, Smem<BN>::kStageBytes);
-          tma_load_2d(a_dst, &map_a, full0 + 8 * s, (kb_begin + i) * kBK, a_row0);
-          tma_load_2d(a_dst + kABytes, &map_b, full0 + 8 * s, (kb_begin + i) * kBK, b_row0);
+          const int r0 = (kb_begin + i) * kBK;     // first reduction index of this block
+          if constexpr (!kAMn) {
+            tma_load_2d(a_dst, &map_a, full0 + 8 * s, r0, a_row0);
+          } else {
+#pragma unroll
+            for (int h = 0; h < kBM / 64; h++) tma_load_2d(a_dst + h * 8192, &map_a, full0 + 8 * s, a_row0 + 64 * h, r0);
+          }
+          if constexpr (!kBMn) {
+            tma_load_2d(a_dst + kABytes, &map_b, full0 + 8 * s, r0, b_row0);
+          } else {
+#pragma unroll
+            for (int h = 0; h < BN / 64; h++) tma_load_2d(a_dst + kABytes + h * 8192, &map_b, full0 + 8 * s, b_row0 + 64 * h, r0);
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = instr_desc_bf16_f32(kBM, BN);
+      constexpr uint32_t idesc = instr_desc_bf16_f32(kBM, BN, kAMn, kBMn);
+      // descriptor advance per K = 16 slice, in 16-byte units: 32 B along the swizzled row (K-major), or two 8-row groups
+      // = 2048 B (MN-major)
+      constexpr uint64_t kStepA = kAMn ? 2048 / 16 : kUmmaK * 2 / 16, kStepB = kBMn ? 2048 / 16 : kUmmaK * 2 / 16;
       uint32_t g = 0, lt = 0;                      // ring position; tiles done by this CTA
       bool alive = true;
       for (int t = blockIdx.x; t < args.n_tiles && alive; t += gridDim.x, lt++) {
@@ -243,13 +273,11 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if (!alive) break;
           tc_fence_after_sync();
           const uint32_t a_src = base + s * Smem<BN>::kStageBytes;
-          const uint64_t da = smem_desc_sw128(a_src), db = smem_desc_sw128(a_src + kABytes);
+          const uint64_t da = kAMn ? smem_desc_sw128_mn(a_src) : smem_desc_sw128(a_src);
+          const uint64_t db = kBMn ? smem_desc_sw128_mn(a_src + kABytes) : smem_desc_sw128(a_src + kABytes);
 #pragma unroll
-          for (int k = 0; k < kBK / kUmmaK; k++) {
-            // +32 bytes (2 x 16-byte units) along K inside the 128-byte swizzle row per K = 16 slice
-            umma_bf16(tmem_d, da + uint64_t(k * (kUmmaK * 2 / 16)), db + uint64_t(k * (kUmmaK * 2 / 16)), idesc,
-                      (i | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < kBK / kUmmaK; k++)
+            umma_bf16(tmem_d, da + uint64_t(k) * kStepA, db + uint64_t(k) * kStepB, idesc, (i | k) != 0 ? 1u : 0u);
           umma_commit(empty0 + 8 * s);            // the stage may be refilled once these MMAs have read it
         }
         if (alive) umma_commit(acc_full0 + 8 * as);
@@ -374,29 +402,33 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// a [rows x K] bf16 matrix, K contiguous, `ld` elements between rows; boxes of [box_rows x 64], 128-byte swizzle;
-// rows / columns outside the matrix read as zero, so ragged M, N and K need no special case in the kernel
-bool make_map(CUtensorMap* map, const void* ptr, int rows, int K, int ld, int box_rows) {
+// One GEMM operand: `rows` entries along its MN dimension (the one that survives), `red` along the reduction.
+//   K-major  (mn = 0): element (i, r) at ptr[i * ld + r]  -> boxes of [box_mn rows x 64 r], 128-byte swizzle
+//   MN-major (mn = 1): element (i, r) at ptr[r * ld + i]  -> boxes of [64 r rows x 64 i]
+// Rows / columns outside the matrix read as zero, so ragged extents need no special case in the kernel.
+struct Operand { const void* ptr; int rows; int ld; int mn; };
+
+bool make_map(CUtensorMap* map, const Operand& o, int red, int box_mn) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) { g_err = "the CUDA driver does not export cuTensorMapEncodeTiled"; return false; }
-  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (size_t(ld) * 2) % 16) {
+  if ((reinterpret_cast<uintptr_t>(o.ptr) & 15) || (size_t(o.ld) * 2) % 16) {
     g_err = "operands must be 16-byte aligned with a row pitch that is a multiple of 8 elements";
     return false;
   }
-  const cuuint64_t dims[2] = {cuuint64_t(K), cuuint64_t(rows)};
-  const cuuint64_t strides[1] = {cuuint64_t(ld) * 2};
-  const cuuint32_t box[2] = {cuuint32_t(kBK), cuuint32_t(box_rows)};
+  const cuuint64_t dims[2] = {cuuint64_t(o.mn ? o.rows : red), cuuint64_t(o.mn ? red : o.rows)};
+  const cuuint64_t strides[1] = {cuuint64_t(o.ld) * 2};
+  const cuuint32_t box[2] = {cuuint32_t(kBK), cuuint32_t(o.mn ? kBK : box_mn)};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(o.ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { g_err = "cuTensorMapEncodeTiled failed: " + std::to_string(int(r)); return false; }
   return true;
 }
 
-template <int BN, int kStages, bool kSwap, bool kReduce>
+template <int BN, int kStages, bool kSwap, bool kReduce, bool kAMn, bool kBMn>
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs& a, const BnetTcPlan& p, cudaStream_t st) {
-  auto kern = tc_linear_kernel<BN, kStages, kSwap, kReduce>;
+  auto kern = tc_linear_kernel<BN, kStages, kSwap, kReduce, kAMn, kBMn>;
   static std::once_flag once;
   static cudaError_t attr_rc = cudaSuccess;
   const int smem = p.smem_bytes;
@@ -422,54 +454,11 @@ int sm_count() {
   return n;
 }
 
-int run(const void* x, const void* w, const void* bias, void* const* outs, int n_outs, int multicast, bool reduce, int M,
-        int N, int K, int ldx, int ldw, int ldo, int act, int splits, int* err_dev, void* stream) {
-  BnetTcPlan p;
-  if (bnet_tc_plan(M, N, K, reduce ? 1 : 0, splits, &p) != 0) return -1;
-  if (!err_dev) { g_err = "err_dev is required"; return -1; }
-  if (n_outs < 1 || n_outs > BNET_TC_MAX_OUTS) { g_err = "n_outs out of range"; return -1; }
-  // lane operand = 128-row boxes, column operand = bn-row boxes
-  const void* pa = p.swap ? w : x; const void* pb = p.swap ? x : w;
-  const int rows_a = p.swap ? N : M, rows_b = p.swap ? M : N, lda = p.swap ? ldw : ldx, ldb = p.swap ? ldx : ldw;
-  CUtensorMap ma, mb;
-  if (!make_map(&ma, pa, rows_a, K, lda, kBM) || !make_map(&mb, pb, rows_b, K, ldb, p.bn)) return -1;
-  TcArgs a{};
-  a.rows_a = rows_a; a.rows_b = rows_b; a.tiles_a = p.grid_y; a.n_tiles = p.grid_x * p.grid_y; a.k_blocks = p.k_blocks; a.k_per_split = p.k_per_split; a.ldo = ldo; a.act = act;
-  a.bias = static_cast<const __nv_bfloat16*>(bias);
-  for (int i = 0; i < n_outs; i++) a.outs[i] = outs[i];
-  a.n_outs = n_outs; a.multicast = multicast; a.err = err_dev;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define BNET_TC_CASE(BN, SWAP)                                                                         \
-  if (p.bn == BN && bool(p.swap) == SWAP)                                                              \
-    return reduce ? launch<BN, stages_for(BN), SWAP, true>(ma, mb, a, p, st)                           \
-                  : launch<BN, stages_for(BN), SWAP, false>(ma, mb, a, p, st);
-  BNET_TC_CASE(32, true)
-  BNET_TC_CASE(64, true)
-  BNET_TC_CASE(128, false)
-  BNET_TC_CASE(256, false)
-#undef BNET_TC_CASE
-  g_err = "no kernel for this plan";
-  return -1;
-}
-
-}  // namespace
-
-BNET_API const char* bnet_tc_last_error(void) { return g_err.c_str(); }
-BNET_API uint64_t bnet_tc_smem_desc(uint32_t smem_addr) { return smem_desc_sw128(smem_addr); }
-BNET_API uint32_t bnet_tc_instr_desc(int m, int n) { return instr_desc_bf16_f32(m, n); }
-
-BNET_API int bnet_tc_supported(void) {
-  int dev = 0, major = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
-    (void)cudaGetLastError();
-    return 0;
-  }
-  return (major == 10 && encode_fn() != nullptr) ? 1 : 0;
-}
-
-BNET_API int bnet_tc_plan(int M, int N, int K, int reduce, int splits, BnetTcPlan* p) {
-  if (!p || M < 1 || N < 1 || K < 1) { g_err = "bad problem size"; return -1; }
-  if (K % 8) { g_err = "K must be a multiple of 8 (16-byte TMA row pitch)"; return -1; }
+// Tiling of D[rows_a, rows_b] = A . B^T over `red`: `batch` is the extent that decides the orientation (the forward's
+// and dX's batch dimension M; pass a large value for dW, whose both extents are feature counts).
+int plan_gemm(int rows_lane_if_noswap, int rows_col_if_noswap, int red, int reduce, int splits, BnetTcPlan* p) {
+  // the caller passes the problem as (batch-like extent, feature-like extent): swap puts the features on the lanes
+  const int M = rows_lane_if_noswap, N = rows_col_if_noswap;
   p->swap = M <= 64 ? 1 : 0;
   p->bn = p->swap ? (M <= 32 ? 32 : 64) : 128;
   // 128 x 256 tiles (the whole TMEM: 2 x 256 accumulator columns) once they still fill every SM: half the MMA issues and
@@ -479,7 +468,7 @@ BNET_API int bnet_tc_plan(int M, int N, int K, int reduce, int splits, BnetTcPla
   const int rows_a = p->swap ? N : M, rows_b = p->swap ? M : N;
   p->grid_x = (rows_b + p->bn - 1) / p->bn;
   p->grid_y = (rows_a + kBM - 1) / kBM;
-  p->k_blocks = (K + kBK - 1) / kBK;
+  p->k_blocks = (red + kBK - 1) / kBK;
   int z = (reduce && splits > 1) ? splits : 1;
   if (z > p->k_blocks) z = p->k_blocks;
   p->k_per_split = (p->k_blocks + z - 1) / z;
@@ -494,13 +483,94 @@ BNET_API int bnet_tc_plan(int M, int N, int K, int reduce, int splits, BnetTcPla
   return 0;
 }
 
+// `batch` / `feat`: the two operands in problem order (out[batch index, feature index]); the plan decides which of them
+// rides the TMEM lanes.  bias is indexed by the feature.
+int run(const Operand& batch, const Operand& feat, int red, const void* bias, void* const* outs, int n_outs, int multicast,
+        bool reduce, int ldo, int act, int splits, int* err_dev, void* stream) {
+  BnetTcPlan p;
+  if (batch.rows < 1 || feat.rows < 1 || red < 1) { g_err = "bad problem size"; return -1; }
+  if (plan_gemm(batch.rows, feat.rows, red, reduce ? 1 : 0, splits, &p) != 0) return -1;
+  if (!err_dev) { g_err = "err_dev is required"; return -1; }
+  if (n_outs < 1 || n_outs > BNET_TC_MAX_OUTS) { g_err = "n_outs out of range"; return -1; }
+  const Operand& oa = p.swap ? feat : batch;     // lane operand: 128-row tiles
+  const Operand& ob = p.swap ? batch : feat;     // column operand: bn-row tiles
+  CUtensorMap ma, mb;
+  if (!make_map(&ma, oa, red, kBM) || !make_map(&mb, ob, red, p.bn)) return -1;
+  TcArgs a{};
+  a.rows_a = oa.rows; a.rows_b = ob.rows; a.tiles_a = p.grid_y; a.n_tiles = p.grid_x * p.grid_y;
+  a.k_blocks = p.k_blocks; a.k_per_split = p.k_per_split; a.ldo = ldo; a.act = act;
+  a.bias = static_cast<const __nv_bfloat16*>(bias);
+  for (int i = 0; i < n_outs; i++) a.outs[i] = outs[i];
+  a.n_outs = n_outs; a.multicast = multicast; a.err = err_dev;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool amn = oa.mn != 0, bmn = ob.mn != 0, swap = p.swap != 0;
+#define BNET_TC_CASE(BN, SWAP, RED, AMN, BMN)                                          \
+  if (p.bn == BN && swap == SWAP && reduce == RED && amn == AMN && bmn == BMN)        \
+    return launch<BN, stages_for(BN), SWAP, RED, AMN, BMN>(ma, mb, a, p, st);
+  // forward (K-major x K-major), plain and with the cross-rank adds
+  BNET_TC_CASE(32, true, false, false, false)   BNET_TC_CASE(32, true, true, false, false)
+  BNET_TC_CASE(64, true, false, false, false)   BNET_TC_CASE(64, true, true, false, false)
+  BNET_TC_CASE(128, false, false, false, false) BNET_TC_CASE(128, false, true, false, false)
+  BNET_TC_CASE(256, false, false, false, false) BNET_TC_CASE(256, false, true, false, false)
+  // dX = gY . W: gY K-major; W MN-major — on the columns (large batch) or on the lanes (small batch)
+  BNET_TC_CASE(128, false, false, false, true)  BNET_TC_CASE(256, false, false, false, true)
+  BNET_TC_CASE(32, true, false, true, false)    BNET_TC_CASE(64, true, false, true, false)
+  // dW = gY^T . X: both MN-major
+  BNET_TC_CASE(128, false, false, true, true)   BNET_TC_CASE(256, false, false, true, true)
+#undef BNET_TC_CASE
+  g_err = "no kernel for this plan";
+  return -1;
+}
+
+}  // namespace
+
+BNET_API const char* bnet_tc_last_error(void) { return g_err.c_str(); }
+BNET_API uint64_t bnet_tc_smem_desc(uint32_t smem_addr) { return smem_desc_sw128(smem_addr); }
+BNET_API uint64_t bnet_tc_smem_desc_mn(uint32_t smem_addr) { return smem_desc_sw128_mn(smem_addr); }
+BNET_API uint32_t bnet_tc_instr_desc(int m, int n) { return instr_desc_bf16_f32(m, n); }
+BNET_API uint32_t bnet_tc_instr_desc2(int m, int n, int a_mn, int b_mn) { return instr_desc_bf16_f32(m, n, a_mn != 0, b_mn != 0); }
+
+BNET_API int bnet_tc_supported(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return (major == 10 && encode_fn() != nullptr) ? 1 : 0;
+}
+
+BNET_API int bnet_tc_plan(int M, int N, int K, int reduce, int splits, BnetTcPlan* p) {
+  if (!p || M < 1 || N < 1 || K < 1) { g_err = "bad problem size"; return -1; }
+  if (K % 8) { g_err = "K must be a multiple of 8 (16-byte TMA row pitch)"; return -1; }
+  return plan_gemm(M, N, K, reduce, splits, p);
+}
+
 BNET_API int bnet_tc_linear(const void* x, const void* w, const void* bias, void* out, int M, int N, int K, int ldx, int ldw,
                             int ldo, int act, int* err_dev, void* stream) {
   void* outs[1] = {out};
-  return run(x, w, bias, outs, 1, 0, false, M, N, K, ldx, ldw, ldo, act, 1, err_dev, stream);
+  return run(Operand{x, M, ldx, 0}, Operand{w, N, ldw, 0}, K, bias, outs, 1, 0, false, ldo, act, 1, err_dev, stream);
 }
 
 BNET_API int bnet_tc_linear_reduce(const void* x, const void* w, const void* bias, void* const* outs, int n_outs, int multicast,
                                    int M, int N, int K, int ldx, int ldw, int ldo, int splits, int* err_dev, void* stream) {
-  return run(x, w, bias, outs, n_outs, multicast, true, M, N, K, ldx, ldw, ldo, BNET_TC_ACT_NONE, splits, err_dev, stream);
+  return run(Operand{x, M, ldx, 0}, Operand{w, N, ldw, 0}, K, bias, outs, n_outs, multicast, true, ldo, BNET_TC_ACT_NONE, splits,
+             err_dev, stream);
+}
+
+// dx[M, K] = gy[M, N] . w[N, K]: the reduction runs over N, so w is read with its rows as the reduction (MN-major)
+BNET_API int bnet_tc_linear_dgrad(const void* gy, const void* w, void* dx, int M, int N, int K, int ldgy, int ldw, int lddx,
+                                  int* err_dev, void* stream) {
+  void* outs[1] = {dx};
+  return run(Operand{gy, M, ldgy, 0}, Operand{w, K, ldw, 1}, N, nullptr, outs, 1, 0, false, lddx, BNET_TC_ACT_NONE, 1, err_dev,
+             stream);
+}
+
+// dw[N, K] = gy[M, N]^T . x[M, K]: the reduction runs over the batch; both operands are MN-major.  dw's two extents are
+// feature counts, so the plan never swaps when N > 64 (and a layer with <= 64 outputs simply takes the swapped tiles).
+BNET_API int bnet_tc_linear_wgrad(const void* gy, const void* x, void* dw, int M, int N, int K, int ldgy, int ldx, int lddw,
+                                  int* err_dev, void* stream) {
+  void* outs[1] = {dw};
+  if (N <= 64) { g_err = "wgrad needs more than 64 output features (use cuBLAS for tiny layers)"; return -1; }
+  return run(Operand{gy, N, ldgy, 1}, Operand{x, K, ldx, 1}, M, nullptr, outs, 1, 0, false, lddw, BNET_TC_ACT_NONE, 1, err_dev,
+             stream);
 }

@@ -9,7 +9,9 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <cute/tensor.hpp>
 #include <cute/arch/mma_sm100_desc.hpp>
+#include <cute/atom/mma_traits_sm100.hpp>
 
 #include "bnet/bnet_tc.h"
 
@@ -20,7 +22,9 @@ int main(int argc, char** argv) {
   auto smem_desc = reinterpret_cast<uint64_t (*)(uint32_t)>(dlsym(h, "bnet_tc_smem_desc"));
   auto instr_desc = reinterpret_cast<uint32_t (*)(int, int)>(dlsym(h, "bnet_tc_instr_desc"));
   auto plan = reinterpret_cast<int (*)(int, int, int, int, int, BnetTcPlan*)>(dlsym(h, "bnet_tc_plan"));
-  if (!smem_desc || !instr_desc || !plan) { fprintf(stderr, "missing bnet_tc_* symbols\n"); return 2; }
+  auto smem_desc_mn = reinterpret_cast<uint64_t (*)(uint32_t)>(dlsym(h, "bnet_tc_smem_desc_mn"));
+  auto instr_desc2 = reinterpret_cast<uint32_t (*)(int, int, int, int)>(dlsym(h, "bnet_tc_instr_desc2"));
+  if (!smem_desc || !instr_desc || !plan || !smem_desc_mn || !instr_desc2) { fprintf(stderr, "missing bnet_tc_* symbols\n"); return 2; }
   int bad = 0;
 
   // ---- instruction descriptor: bf16 x bf16 -> f32, both operands K-major, M = 128, N in {32, 64, 128, 256}
@@ -53,6 +57,41 @@ int main(int argc, char** argv) {
     UMMA::SmemDescriptor k1 = d;
     k1.start_address_ = uint16_t((addr + 32) >> 4);
     if (got + 2 != uint64_t(k1)) { printf("smem desc K advance @%x\n", addr); bad++; }
+  }
+
+  // ---- MN-major operands (the backward GEMMs): instruction descriptor major bits and the descriptor CuTe derives for the
+  //      layout our TMA boxes produce — 64-element MN atoms 8 KiB apart, 8-row reduction groups 1 KiB apart, i.e.
+  //      tile_to_shape(Layout_MN_SW128_Atom, (MN, 64), Step<_2,_1>)  (make_umma_desc prints a note about the start address
+  //      on the host; only the layout fields are compared)
+  {
+    using T = bfloat16_t;
+    struct { int a, b; uint32_t want; } majors[] = {
+        {0, 1, uint32_t(UMMA::make_instr_desc<T, T, float, 128, 128, UMMA::Major::K, UMMA::Major::MN>())},
+        {1, 0, uint32_t(UMMA::make_instr_desc<T, T, float, 128, 128, UMMA::Major::MN, UMMA::Major::K>())},
+        {1, 1, uint32_t(UMMA::make_instr_desc<T, T, float, 128, 128, UMMA::Major::MN, UMMA::Major::MN>())},
+    };
+    for (auto& m : majors)
+      if (instr_desc2(128, 128, m.a, m.b) != m.want) { printf("instr desc majors %d %d: got %08x want %08x\n", m.a, m.b, instr_desc2(128, 128, m.a, m.b), m.want); bad++; }
+    alignas(1024) static T buf[256 * 64];
+    auto check_mn = [&](auto shape, const char* name) {
+      auto t = make_tensor(make_smem_ptr(buf), tile_to_shape(UMMA::Layout_MN_SW128_Atom<T>{}, shape, Step<_2, _1>{}));
+      UMMA::SmemDescriptor want = UMMA::make_umma_desc<UMMA::Major::MN>(t);
+      UMMA::SmemDescriptor got;
+      got.desc_ = smem_desc_mn(0x4000);
+      if (got.leading_byte_offset_ != want.leading_byte_offset_ || got.stride_byte_offset_ != want.stride_byte_offset_ ||
+          got.layout_type_ != want.layout_type_ || got.version_ != want.version_ || got.start_address_ != (0x4000 >> 4) ||
+          got.base_offset_ != 0 || got.lbo_mode_ != 0) {
+        printf("MN-major smem desc (%s): got lbo %u sbo %u layout %u, CuTe lbo %u sbo %u layout %u\n", name,
+               unsigned(got.leading_byte_offset_), unsigned(got.stride_byte_offset_), unsigned(got.layout_type_),
+               unsigned(want.leading_byte_offset_), unsigned(want.stride_byte_offset_), unsigned(want.layout_type_));
+        bad++;
+      }
+      // a K = 16 slice starts two 8-row groups (2048 B) further: layout(0, 16) in elements * 2 B
+      if (int(t.layout()(0, 16)) * 2 != 2048) { printf("MN-major K slice offset (%s): %d\n", name, int(t.layout()(0, 16)) * 2); bad++; }
+      if (int(t.layout()(64, 0)) * 2 != 8192 && size<0>(shape) > 64) { printf("MN-major atom offset (%s): %d\n", name, int(t.layout()(64, 0)) * 2); bad++; }
+    };
+    check_mn(Shape<_128, _64>{}, "128x64");
+    check_mn(Shape<_256, _64>{}, "256x64");
   }
 
   // ---- tiling plans

@@ -52,10 +52,21 @@ int bnet_tc_linear(const void* x, const void* w, const void* bias, void* out, in
 int bnet_tc_linear_reduce(const void* x, const void* w, const void* bias, void* const* outs, int n_outs, int multicast,
                           int M, int N, int K, int ldx, int ldw, int ldo, int splits, int* err_dev, void* stream);
 
+/* The two backward GEMMs of the same layer, without materialising any transpose (the operands whose reduction dimension
+ * is the outer one are staged as MN-major tiles):
+ *   dx[M,K] = gy[M,N] . w[N,K]            dw[N,K] = gy[M,N]^T . x[M,K]   (N > 64)
+ * bf16 in, fp32 accumulate, bf16 out. */
+int bnet_tc_linear_dgrad(const void* gy, const void* w, void* dx, int M, int N, int K, int ldgy, int ldw, int lddx, int* err_dev,
+                         void* stream);
+int bnet_tc_linear_wgrad(const void* gy, const void* x, void* dw, int M, int N, int K, int ldgy, int ldx, int lddw, int* err_dev,
+                         void* stream);
+
 /* The 64-bit shared-memory matrix descriptor (K-major, 128-byte swizzle) and the 32-bit instruction descriptor
  * (bf16 x bf16 -> fp32) the kernel issues, exposed so a host test can compare them with the CuTe definitions. */
 uint64_t bnet_tc_smem_desc(uint32_t smem_addr);
+uint64_t bnet_tc_smem_desc_mn(uint32_t smem_addr);            /* MN-major tile staged as 64 x 64 boxes */
 uint32_t bnet_tc_instr_desc(int m, int n);
+uint32_t bnet_tc_instr_desc2(int m, int n, int a_mn_major, int b_mn_major);
 
 const char* bnet_tc_last_error(void);
 

@@ -593,6 +593,17 @@ def job_tc_linear():
             ref = torch.relu(ref) if relu else ref
             err = (y.float() - ref).abs().max().item()
             assert err < 0.08, f"tc_linear {M}x{N}x{K} relu={relu}: max abs err {err}"
+    # the backward GEMMs: W, gY and X read MN-major, both orientations of dX, ragged extents
+    for (M, N, K) in [(32, 4096, 1024), (64, 136, 264), (200, 72, 520), (512, 1024, 768), (1000, 1000, 1000)]:
+        gy = torch.randn(M, N, device="cuda").bfloat16()
+        w = (torch.randn(N, K, device="cuda") / N ** 0.5).bfloat16()
+        x = torch.randn(M, K, device="cuda").bfloat16()
+        dx, dw = tc_linear.linear_dgrad(gy, w), tc_linear.linear_wgrad(gy, x)
+        assert tc_linear.last_error() == 0, f"watchdog tripped in the backward GEMMs at {M}x{N}x{K}"
+        e1 = (dx.float() - gy.float() @ w.float()).abs().max().item()
+        ref = gy.float().t() @ x.float()
+        e2 = ((dw.float() - ref).abs().max() / ref.abs().max()).item()
+        assert e1 < 0.1 and e2 < 0.02, f"backward {M}x{N}x{K}: dgrad abs err {e1}, wgrad rel err {e2}"
     # strided views (row pitch != K), no bias
     big = torch.randn(96, 1024, device="cuda").bfloat16()
     x, w = big[:40, 128:640], big[40:, 128:640]

@@ -12,6 +12,7 @@ Probes (all exact in bf16 / fp32, so any mismatch is a layout or synchronisation
   swz       A[i, k] = 1 iff k == (i * 7) % 64  (a different column per row), B[j, k] = k
                                  -> TMA swizzle vs. UMMA descriptor swizzle agree (D[i, j] = (i * 7) % 64)
   ragged    M, N, K off the tile grid -> TMA zero fill and the epilogue guards
+  dgrad / wgrad  the MN-major operand path (64 x 64 boxes, LBO / SBO of the MN-major descriptor), exact integers
   tiles     many tiles per CTA (persistent loop, both accumulator stages), checked tile by tile
 """
 from __future__ import annotations
@@ -98,6 +99,27 @@ def main():
         x = torch.randint(-2, 3, (M, K), device=dev, generator=g).float()
         w = torch.randint(-2, 3, (N, K), device=dev, generator=g).float()
         run("ragged", x, w)
+    # backward GEMMs (MN-major operands): exact integers, both orientations of dX
+    for (M, N, K) in ((128, 128, 128), (32, 128, 128), (256, 192, 320), (48, 200, 264)):
+        gy = torch.randint(-2, 3, (M, N), device=dev, generator=g).float()
+        w = torch.randint(-2, 3, (N, K), device=dev, generator=g).float()
+        x = torch.randint(-2, 3, (M, K), device=dev, generator=g).float()
+        for name, got, ref in (("dgrad", tc_linear.linear_dgrad(gy.bfloat16(), w.bfloat16()), gy @ w),
+                               ("wgrad", tc_linear.linear_wgrad(gy.bfloat16(), x.bfloat16()), gy.t() @ x)):
+            flag = tc_linear.last_error()
+            bad = got.float() != ref.bfloat16().float()
+            ok = flag == 0 and not bool(bad.any())
+            msg = f"[{'ok' if ok else 'FAIL'}] {name}: M={M} N={N} K={K}"
+            if flag:
+                msg += f"  watchdog role {flag}"
+            if bool(bad.any()):
+                idx = bad.nonzero()
+                msg += (f"  {int(bad.sum())} wrong of {bad.numel()}; rows {idx[:, 0].unique()[:8].tolist()} cols "
+                        f"{idx[:, 1].unique()[:8].tolist()}; first D{idx[0].tolist()} = "
+                        f"{got[idx[0][0], idx[0][1]].item()} expected {ref[idx[0][0], idx[0][1]].item()}")
+            print(msg)
+            if not ok:
+                FAILED.append(name)
     # persistent loop: far more tiles than SMs; report the first wrong TILE
     M, N, K = 4096, 8192, 192
     x = torch.randint(-2, 3, (M, K), device=dev, generator=g).float()
