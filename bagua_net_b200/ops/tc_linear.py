@@ -2,6 +2,8 @@
 
     y = tc_linear.linear(x, w, bias, relu=True)                # bf16 [M,K] x [N,K]^T -> bf16 [M,N], fused bias + ReLU
     y = tc_linear.row_parallel_linear(x_k, w_k, comm)          # every rank holds a K-shard; fp32 sum lands on EVERY rank
+    y = tc_linear.linear_reduce_scatter(x_k, w_k, comm)        # ... or only on the rank that owns each row block
+    y = tc_linear.allgather_linear(x_rows, w, comm)            # x sharded by rows: peers' shards are TMA-loaded over NVLink
 
 The kernel stages operands with TMA (128-byte swizzle), multiplies with ``tcgen05.mma`` into TMEM and applies the
 epilogue straight out of TMEM; ``row_parallel_linear`` is the "compute step followed by a collective in ONE kernel"
@@ -46,6 +48,8 @@ def _L():
         _lib.bnet_tc_linear_reduce.argtypes = [vp, vp, vp, C.POINTER(vp), i, i, i, i, i, i, i, i, i, vp, vp]
         _lib.bnet_tc_linear_dgrad.argtypes = [vp, vp, vp, i, i, i, i, i, i, vp, vp]
         _lib.bnet_tc_linear_wgrad.argtypes = [vp, vp, vp, i, i, i, i, i, i, vp, vp]
+        _lib.bnet_tc_allgather_linear.argtypes = [C.POINTER(vp), i, i, vp, vp, vp, i, i, i, i, i, i, vp, vp]
+        _lib.bnet_tc_linear_reduce_scatter.argtypes = [vp, vp, vp, C.POINTER(vp), i, i, i, i, i, i, i, i, vp, vp]
         _lib.bnet_tc_last_error.restype = C.c_char_p
         _lib.bnet_tc_smem_desc.restype = C.c_uint64
         _lib.bnet_tc_smem_desc.argtypes = [C.c_uint32]
@@ -260,6 +264,69 @@ def row_parallel_linear(x: torch.Tensor, w: torch.Tensor, comm, bias: torch.Tens
                                  _err_flag(x.device.index).data_ptr(), _stream())
     if rc < 0:
         raise RuntimeError(f"bnet_tc_linear_reduce: {L.bnet_tc_last_error().decode()}")
+    LAUNCHES += rc
+    comm.barrier()
+    return out
+
+
+def _peer_ptrs(comm, t):
+    off = comm.offset_of(t)
+    return [int(comm.lib.bnet_coll_peer_heap(comm.h, r)) + off if r != comm.rank else t.data_ptr() for r in range(comm.world)]
+
+
+def allgather_linear(x_shard: torch.Tensor, w: torch.Tensor, comm, bias: torch.Tensor | None = None, relu: bool = False,
+                     sync: bool = True) -> torch.Tensor:
+    """``act(all_gather(x_shard) @ w.T + bias)`` in ONE kernel: x is sharded by rows over the ranks (sequence / batch
+    parallel input of a column-parallel layer); ``x_shard`` [rows, K] must come from ``comm.alloc`` (same offset on every
+    rank) with rows a multiple of 128.  Each tile's operand is loaded by TMA straight from the owning rank's memory over
+    NVLink — the gathered activation is never materialised.  Returns bf16 [world * rows, N].
+    ``sync``: rank barriers before (every shard is written) and after (nobody overwrites a shard still being read)."""
+    global LAUNCHES
+    _check_operands(x_shard, w, bias)
+    rows, K = x_shard.shape
+    N = w.shape[0]
+    ptrs = _peer_ptrs(comm, x_shard)
+    out = torch.empty((rows * comm.world, N), dtype=torch.bfloat16, device=x_shard.device)
+    if sync:
+        comm.barrier()
+    arr = (C.c_void_p * len(ptrs))(*ptrs)
+    L = _L()
+    rc = L.bnet_tc_allgather_linear(arr, len(ptrs), rows, w.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                    out.data_ptr(), N, K, x_shard.stride(0), w.stride(0), out.stride(0), 1 if relu else 0,
+                                    _err_flag(x_shard.device.index).data_ptr(), _stream())
+    if rc < 0:
+        raise RuntimeError(f"bnet_tc_allgather_linear: {L.bnet_tc_last_error().decode()}")
+    LAUNCHES += rc
+    if sync:
+        comm.barrier()
+    return out
+
+
+def linear_reduce_scatter(x: torch.Tensor, w: torch.Tensor, comm, bias: torch.Tensor | None = None,
+                          out: torch.Tensor | None = None, splits: int = 1) -> torch.Tensor:
+    """Row-parallel linear whose result stays sharded: rank r ends up with rows [r*M/world, (r+1)*M/world) of
+    ``sum_r x_r @ w_r.T (+ bias)`` as fp32 [M / world, N].  ONE kernel per rank: every output tile is added straight into
+    its owner's symmetric-heap buffer (``red.global.add.v4.f32`` over NVLink) — GEMM -> reduce-scatter fused."""
+    global LAUNCHES
+    _check_operands(x, w, bias)
+    M, K = x.shape
+    N = w.shape[0]
+    if M % comm.world:
+        raise ValueError("the batch must divide by the number of ranks")
+    if out is None:
+        out = comm.alloc(M // comm.world * N, torch.float32).view(M // comm.world, N)
+    assert out.dtype == torch.float32 and out.shape == (M // comm.world, N) and out.is_contiguous()
+    ptrs = _peer_ptrs(comm, out)
+    out.zero_()
+    comm.barrier()
+    arr = (C.c_void_p * len(ptrs))(*ptrs)
+    L = _L()
+    b = bias if (bias is not None and comm.rank == 0) else None
+    rc = L.bnet_tc_linear_reduce_scatter(x.data_ptr(), w.data_ptr(), b.data_ptr() if b is not None else None, arr, len(ptrs),
+                                         M, N, K, x.stride(0), w.stride(0), out.stride(0), splits,
+                                         _err_flag(x.device.index).data_ptr(), _stream())
+    if rc < 0:
+        raise RuntimeError(f"bnet_tc_linear_reduce_scatter: {L.bnet_tc_last_error().decode()}")
     LAUNCHES += rc
     comm.barrier()
     return out

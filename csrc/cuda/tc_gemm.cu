@@ -163,8 +163,15 @@ struct TcArgs {
   void* outs[BNET_TC_MAX_OUTS];
   int n_outs;                // reduce mode: how many output mappings (1 when multicast)
   int multicast;
+  int gather_rows;           // > 0: the batch operand is split over maps.batch[p], gather_rows rows each (all-gather fused
+                             //      into the operand loads: rank p's shard is read from its memory over NVLink by TMA)
+  int scatter_rows;          // > 0 (reduce mode): batch row m belongs to rank m / scatter_rows — the tile is added into
+                             //      THAT rank's output only, at local row m % scatter_rows (reduce-scatter epilogue)
   int* err;
 };
+
+// the batch operand's tensor maps: one, or one per rank when its row blocks live on different GPUs
+struct TcBatchMaps { CUtensorMap m[BNET_TC_MAX_PEERS]; };
 
 template <int BN>
 struct Smem {
@@ -187,7 +194,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // kAMn / kBMn: the lane / column operand is MN-major (reduction dimension outer) instead of K-major
 template <int BN, int kStages, bool kSwap, bool kReduce, bool kAMn, bool kBMn>
 __global__ void __launch_bounds__(kThreads, 1)
-tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcArgs args) {
+tc_linear_kernel(const __grid_constant__ TcBatchMaps maps_batch, const __grid_constant__ CUtensorMap map_feat, const TcArgs args) {
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M = 128");
   static_assert((BN & (BN - 1)) == 0 && BN >= 32, "TMEM allocations are powers of two >= 32 columns");
   static_assert(!kBMn || BN % 64 == 0, "an MN-major operand is staged in 64-element atoms");
@@ -208,8 +215,8 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int nkb = kb_end - kb_begin;       // >= 1 by construction of the grid
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_a);
-    tma_prefetch_desc(&map_b);
+    tma_prefetch_desc(&maps_batch.m[0]);
+    tma_prefetch_desc(&map_feat);
     for (int s = 0; s < kStages; s++) {
       ptx::mbar_init(bars + s, 1);               // full: the producer's arrive.expect_tx (+ TMA bytes)
       ptx::mbar_init(bars + kStages + s, 1);     // empty: one tcgen05.commit
@@ -231,7 +238,15 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       uint32_t g = 0;                              // k-blocks issued by this CTA so far (ring position)
       bool alive = true;
       for (int t = blockIdx.x; t < args.n_tiles && alive; t += gridDim.x) {
-        const int a_row0 = (t % args.tiles_a) * kBM, b_row0 = (t / args.tiles_a) * BN;
+        int a_row0 = (t % args.tiles_a) * kBM, b_row0 = (t / args.tiles_a) * BN;
+        // which operand is the batch: the lanes (plain) or the columns (swapped); with a gathered batch the tile's rows
+        // come from ONE rank's shard (gather_rows is a multiple of the tile height) at a row offset inside that shard
+        const CUtensorMap* map_a = kSwap ? &map_feat : &maps_batch.m[0];
+        const CUtensorMap* map_b = kSwap ? &maps_batch.m[0] : &map_feat;
+        if (args.gather_rows > 0) {
+          if constexpr (kSwap) { map_b = &maps_batch.m[b_row0 / args.gather_rows]; b_row0 %= args.gather_rows; }
+          else { map_a = &maps_batch.m[a_row0 / args.gather_rows]; a_row0 %= args.gather_rows; }
+        }
         for (int i = 0; i < nkb; i++, g++) {
           const uint32_t s = g % kStages, round = g / kStages;
           if (round > 0 && !mbar_wait_wd(empty0 + 8 * s, (round - 1) & 1, args.err, 1)) { alive = false; break; }
@@ -239,16 +254,16 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           mbar_expect_tx(full0 + 8 * s, Smem<BN>::kStageBytes);
           const int r0 = (kb_begin + i) * kBK;     // first reduction index of this block
           if constexpr (!kAMn) {
-            tma_load_2d(a_dst, &map_a, full0 + 8 * s, r0, a_row0);
+            tma_load_2d(a_dst, map_a, full0 + 8 * s, r0, a_row0);
           } else {
 #pragma unroll
-            for (int h = 0; h < kBM / 64; h++) tma_load_2d(a_dst + h * 8192, &map_a, full0 + 8 * s, a_row0 + 64 * h, r0);
+            for (int h = 0; h < kBM / 64; h++) tma_load_2d(a_dst + h * 8192, map_a, full0 + 8 * s, a_row0 + 64 * h, r0);
           }
           if constexpr (!kBMn) {
-            tma_load_2d(a_dst + kABytes, &map_b, full0 + 8 * s, r0, b_row0);
+            tma_load_2d(a_dst + kABytes, map_b, full0 + 8 * s, r0, b_row0);
           } else {
 #pragma unroll
-            for (int h = 0; h < BN / 64; h++) tma_load_2d(a_dst + kABytes + h * 8192, &map_b, full0 + 8 * s, b_row0 + 64 * h, r0);
+            for (int h = 0; h < BN / 64; h++) tma_load_2d(a_dst + kABytes + h * 8192, map_b, full0 + 8 * s, b_row0 + 64 * h, r0);
           }
         }
       }
@@ -341,18 +356,24 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
           }
         } else {
-          // fp32 adds into EVERY rank's output: the all-reduce of the row-parallel layer, tile by tile
-          for (int o = 0; o < args.n_outs; o++) {
-            float* out = static_cast<float*>(args.outs[o]);
+          // fp32 adds into EVERY rank's output (the all-reduce of the row-parallel layer, tile by tile), or with
+          // scatter_rows into the output of the rank that owns the batch row (reduce-scatter)
+          const int o_begin = 0, o_end = args.scatter_rows > 0 ? 1 : args.n_outs;
+          for (int oi = o_begin; oi < o_end; oi++) {
             if constexpr (kSwap) {
 #pragma unroll
               for (int u = 0; u < 16; u++) {
-                if (j0 + u >= args.rows_b) continue;
-                float* p = out + size_t(j0 + u) * args.ldo + i_glob;
+                int m = j0 + u;                      // batch row
+                if (m >= args.rows_b) continue;
+                int o = oi;
+                if (args.scatter_rows > 0) { o = m / args.scatter_rows; m -= o * args.scatter_rows; }
+                float* p = static_cast<float*>(args.outs[o]) + size_t(m) * args.ldo + i_glob;
                 if (args.multicast) multimem_red_add_f32(p, f[u]); else ptx::red_add_f32(p, f[u]);
               }
             } else {
-              float* row = out + size_t(i_glob) * args.ldo + j0;
+              int m = i_glob, o = oi;
+              if (args.scatter_rows > 0) { o = m / args.scatter_rows; m -= o * args.scatter_rows; }
+              float* row = static_cast<float*>(args.outs[o]) + size_t(m) * args.ldo + j0;
               const bool vec = j0 + 16 <= args.rows_b && (reinterpret_cast<uintptr_t>(row) & 15) == 0;
 #pragma unroll
               for (int u = 0; u < 16; u += 4) {
@@ -427,14 +448,14 @@ bool make_map(CUtensorMap* map, const Operand& o, int red, int box_mn) {
 }
 
 template <int BN, int kStages, bool kSwap, bool kReduce, bool kAMn, bool kBMn>
-int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs& a, const BnetTcPlan& p, cudaStream_t st) {
+int launch(const TcBatchMaps& mbatch, const CUtensorMap& mfeat, const TcArgs& a, const BnetTcPlan& p, cudaStream_t st) {
   auto kern = tc_linear_kernel<BN, kStages, kSwap, kReduce, kAMn, kBMn>;
   static std::once_flag once;
   static cudaError_t attr_rc = cudaSuccess;
   const int smem = p.smem_bytes;
   std::call_once(once, [&] { attr_rc = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
   if (attr_rc != cudaSuccess) { g_err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(attr_rc); return -1; }
-  kern<<<dim3(p.ctas, 1, p.grid_z), kThreads, smem, st>>>(ma, mb, a);
+  kern<<<dim3(p.ctas, 1, p.grid_z), kThreads, smem, st>>>(mbatch, mfeat, a);
   cudaError_t rc = cudaGetLastError();
   if (rc != cudaSuccess) { g_err = std::string("tc_linear launch: ") + cudaGetErrorString(rc); return -1; }
   return 1;
@@ -485,8 +506,11 @@ int plan_gemm(int rows_lane_if_noswap, int rows_col_if_noswap, int red, int redu
 
 // `batch` / `feat`: the two operands in problem order (out[batch index, feature index]); the plan decides which of them
 // rides the TMEM lanes.  bias is indexed by the feature.
+// `shards` (optional): the batch operand's row blocks live in n_shards separate allocations of batch.rows / n_shards rows
+// each (the other ranks' symmetric heaps); `scatter_ranks` > 0 (reduce mode): outs[r] receives only the rows rank r owns.
 int run(const Operand& batch, const Operand& feat, int red, const void* bias, void* const* outs, int n_outs, int multicast,
-        bool reduce, int ldo, int act, int splits, int* err_dev, void* stream) {
+        bool reduce, int ldo, int act, int splits, int* err_dev, void* stream, const void* const* shards = nullptr,
+        int n_shards = 0, int scatter_ranks = 0) {
   BnetTcPlan p;
   if (batch.rows < 1 || feat.rows < 1 || red < 1) { g_err = "bad problem size"; return -1; }
   if (plan_gemm(batch.rows, feat.rows, red, reduce ? 1 : 0, splits, &p) != 0) return -1;
@@ -494,9 +518,28 @@ int run(const Operand& batch, const Operand& feat, int red, const void* bias, vo
   if (n_outs < 1 || n_outs > BNET_TC_MAX_OUTS) { g_err = "n_outs out of range"; return -1; }
   const Operand& oa = p.swap ? feat : batch;     // lane operand: 128-row tiles
   const Operand& ob = p.swap ? batch : feat;     // column operand: bn-row tiles
-  CUtensorMap ma, mb;
-  if (!make_map(&ma, oa, red, kBM) || !make_map(&mb, ob, red, p.bn)) return -1;
+  TcBatchMaps mbatch;
+  CUtensorMap mfeat;
   TcArgs a{};
+  const int batch_box = p.swap ? p.bn : kBM;     // rows of one box of the batch operand
+  if (n_shards > 0) {
+    if (n_shards > BNET_TC_MAX_PEERS || batch.rows % n_shards) { g_err = "bad shard count"; return -1; }
+    a.gather_rows = batch.rows / n_shards;
+    if (a.gather_rows % batch_box) { g_err = "rows per shard must be a multiple of the tile height (128)"; return -1; }
+    for (int r = 0; r < n_shards; r++) {
+      Operand o = batch;
+      o.ptr = shards[r];
+      o.rows = a.gather_rows;
+      if (!make_map(&mbatch.m[r], o, red, batch_box)) return -1;
+    }
+  } else if (!make_map(&mbatch.m[0], batch, red, batch_box)) {
+    return -1;
+  }
+  if (!make_map(&mfeat, feat, red, p.swap ? kBM : p.bn)) return -1;
+  if (scatter_ranks > 0) {
+    if (!reduce || multicast || n_outs != scatter_ranks || batch.rows % scatter_ranks) { g_err = "bad reduce-scatter arguments"; return -1; }
+    a.scatter_rows = batch.rows / scatter_ranks;
+  }
   a.rows_a = oa.rows; a.rows_b = ob.rows; a.tiles_a = p.grid_y; a.n_tiles = p.grid_x * p.grid_y;
   a.k_blocks = p.k_blocks; a.k_per_split = p.k_per_split; a.ldo = ldo; a.act = act;
   a.bias = static_cast<const __nv_bfloat16*>(bias);
@@ -506,7 +549,7 @@ int run(const Operand& batch, const Operand& feat, int red, const void* bias, vo
   const bool amn = oa.mn != 0, bmn = ob.mn != 0, swap = p.swap != 0;
 #define BNET_TC_CASE(BN, SWAP, RED, AMN, BMN)                                          \
   if (p.bn == BN && swap == SWAP && reduce == RED && amn == AMN && bmn == BMN)        \
-    return launch<BN, stages_for(BN), SWAP, RED, AMN, BMN>(ma, mb, a, p, st);
+    return launch<BN, stages_for(BN), SWAP, RED, AMN, BMN>(mbatch, mfeat, a, p, st);
   // forward (K-major x K-major), plain and with the cross-rank adds
   BNET_TC_CASE(32, true, false, false, false)   BNET_TC_CASE(32, true, true, false, false)
   BNET_TC_CASE(64, true, false, false, false)   BNET_TC_CASE(64, true, true, false, false)
@@ -573,4 +616,23 @@ BNET_API int bnet_tc_linear_wgrad(const void* gy, const void* x, void* dw, int M
   if (N <= 64) { g_err = "wgrad needs more than 64 output features (use cuBLAS for tiny layers)"; return -1; }
   return run(Operand{gy, N, ldgy, 1}, Operand{x, K, ldx, 1}, M, nullptr, outs, 1, 0, false, lddw, BNET_TC_ACT_NONE, 1, err_dev,
              stream);
+}
+
+// out[n_shards * rows_per_shard, N] = act([x_0; x_1; ...] . w^T + bias): the all-gather of a sequence/batch-sharded
+// activation fused into the GEMM's operand loads — shard r is read straight from x_shards[r] (rank r's symmetric heap,
+// mapped over NVLink) by TMA, tile by tile, while the tensor cores work on the previous tile.
+BNET_API int bnet_tc_allgather_linear(const void* const* x_shards, int n_shards, int rows_per_shard, const void* w, const void* bias,
+                                      void* out, int N, int K, int ldx, int ldw, int ldo, int act, int* err_dev, void* stream) {
+  void* outs[1] = {out};
+  if (n_shards < 1 || rows_per_shard < 1) { g_err = "bad shard arguments"; return -1; }
+  return run(Operand{x_shards[0], n_shards * rows_per_shard, ldx, 0}, Operand{w, N, ldw, 0}, K, bias, outs, 1, 0, false, ldo, act, 1,
+             err_dev, stream, x_shards, n_shards, 0);
+}
+
+// outs[r][M / n_ranks, N] += rows [r * M / n_ranks, (r + 1) * M / n_ranks) of x . w^T: GEMM + reduce-scatter in one kernel
+// (every rank calls it with its K-shard; each output tile travels once, to its owner).
+BNET_API int bnet_tc_linear_reduce_scatter(const void* x, const void* w, const void* bias, void* const* outs, int n_ranks, int M,
+                                           int N, int K, int ldx, int ldw, int ldo, int splits, int* err_dev, void* stream) {
+  return run(Operand{x, M, ldx, 0}, Operand{w, N, ldw, 0}, K, bias, outs, n_ranks, 0, true, ldo, BNET_TC_ACT_NONE, splits, err_dev,
+             stream, nullptr, 0, n_ranks);
 }

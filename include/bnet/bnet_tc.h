@@ -26,6 +26,7 @@ extern "C" {
 
 enum { BNET_TC_ACT_NONE = 0, BNET_TC_ACT_RELU = 1 };
 #define BNET_TC_MAX_OUTS 16
+#define BNET_TC_MAX_PEERS 8
 
 /* 1 when the driver exposes cuTensorMapEncodeTiled and the current device is compute capability 10.x */
 int bnet_tc_supported(void);
@@ -51,6 +52,16 @@ int bnet_tc_linear(const void* x, const void* w, const void* bias, void* out, in
  * pointer when multicast != 0.  splits > 1 additionally splits K over grid.z (the adds make it free). */
 int bnet_tc_linear_reduce(const void* x, const void* w, const void* bias, void* const* outs, int n_outs, int multicast,
                           int M, int N, int K, int ldx, int ldw, int ldo, int splits, int* err_dev, void* stream);
+
+/* all-gather -> GEMM: the activation is sharded by rows over n_shards ranks (rows_per_shard a multiple of 128);
+ * x_shards[r] is this rank's mapping of rank r's shard (symmetric heap).  out[n_shards * rows_per_shard, N], bf16. */
+int bnet_tc_allgather_linear(const void* const* x_shards, int n_shards, int rows_per_shard, const void* w, const void* bias,
+                             void* out, int N, int K, int ldx, int ldw, int ldo, int act, int* err_dev, void* stream);
+
+/* GEMM -> reduce-scatter: like bnet_tc_linear_reduce, but rank r's output (outs[r], fp32 [M / n_ranks, ldo]) receives
+ * only the rows it owns.  M must divide by n_ranks. */
+int bnet_tc_linear_reduce_scatter(const void* x, const void* w, const void* bias, void* const* outs, int n_ranks, int M, int N,
+                                  int K, int ldx, int ldw, int ldo, int splits, int* err_dev, void* stream);
 
 /* The two backward GEMMs of the same layer, without materialising any transpose (the operands whose reduction dimension
  * is the outer one are staged as MN-major tiles):

@@ -642,6 +642,29 @@ def job_tc_row_parallel():
         ref = xf.float() @ wf.float().t() + b.float()
         err = (out - ref).abs().max().item()
         assert err < 0.05, f"row_parallel {M}x{N}x{K} splits={splits}: max abs err {err}"
+    # GEMM -> reduce-scatter: each rank keeps only its row block of the sum
+    for (M, N, K, splits) in [(32 * WORLD, 512, 1024, 1), (128 * WORLD, 384, 2048, 2)]:
+        xf = torch.randn(M, K * WORLD, device="cuda").bfloat16()
+        wf = (torch.randn(N, K * WORLD, device="cuda") / (K * WORLD) ** 0.5).bfloat16()
+        x, w = xf[:, RANK * K:(RANK + 1) * K], wf[:, RANK * K:(RANK + 1) * K]
+        out = tc_linear.linear_reduce_scatter(x, w, comm, splits=splits)
+        assert tc_linear.last_error() == 0
+        ref = (xf.float() @ wf.float().t())[RANK * (M // WORLD):(RANK + 1) * (M // WORLD)]
+        err = (out - ref).abs().max().item()
+        assert err < 0.05, f"reduce_scatter {M}x{N}x{K}: max abs err {err}"
+    # all-gather -> GEMM: the activation is sharded by rows, peers' shards are read by TMA over NVLink
+    for (rows, N, K) in [(128, 512, 1024), (256, 1000, 520)]:
+        torch.manual_seed(21)
+        xf = torch.randn(rows * WORLD, K, device="cuda").bfloat16()
+        w = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16()
+        b = torch.randn(N, device="cuda").bfloat16()
+        shard = comm.alloc(rows * K, torch.bfloat16).view(rows, K)
+        shard.copy_(xf[RANK * rows:(RANK + 1) * rows])
+        y = tc_linear.allgather_linear(shard, w, comm, bias=b, relu=True)
+        assert tc_linear.last_error() == 0
+        ref = torch.relu(xf.float() @ w.float().t() + b.float())
+        err = (y.float() - ref).abs().max().item()
+        assert err < 0.08, f"allgather_linear {rows}x{N}x{K}: max abs err {err}"
     torch.cuda.synchronize()
     assert comm.status() == 0
     print(f"tc_row_parallel ok (multicast={comm.has_multicast})")
