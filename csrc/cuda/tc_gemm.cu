@@ -35,18 +35,16 @@
 #include "bnet/bnet_tc.h"
 #include "cuda/driver_api.h"
 #include "cuda/ptx.cuh"
+#include "cuda/tc_body.cuh"
 
 #define BNET_API extern "C" __attribute__((visibility("default")))
 
 namespace {
 
 using namespace bnet;
+using namespace bnet::tc;              // tile constants, TcArgs, plan / setup, per-tile index logic (tc_body.cuh)
 
-constexpr int kBM = 128;               // UMMA M: one accumulator row per TMEM lane
-constexpr int kBK = 64;                // 64 bf16 = 128 bytes = one swizzle-128B row
-constexpr int kUmmaK = 16;             // fixed for 16-bit inputs
 constexpr int kThreads = 192;
-constexpr int kABytes = kBM * kBK * 2; // 16 KiB per stage
 constexpr uint64_t kWatchdogNs = 2000000000ull;
 
 thread_local std::string g_err;
@@ -152,22 +150,26 @@ __device__ __forceinline__ void multimem_red_add_v4_f32(float* mc, const float4&
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
-struct TcArgs {
-  int rows_a, rows_b;        // valid rows of the lane / column operand
-  int tiles_a, n_tiles;      // 128-row blocks of the lane operand; output tiles in total (tile t = (t % tiles_a, t / tiles_a))
-  int k_blocks;              // ceil(K / 64)
-  int k_per_split;           // K blocks handled by one grid.z slice
-  int ldo;                   // elements between output rows
-  int act;
-  const __nv_bfloat16* bias; // indexed by the output FEATURE (column of out), may be null
-  void* outs[BNET_TC_MAX_OUTS];
-  int n_outs;                // reduce mode: how many output mappings (1 when multicast)
-  int multicast;
-  int gather_rows;           // > 0: the batch operand is split over maps.batch[p], gather_rows rows each (all-gather fused
-                             //      into the operand loads: rank p's shard is read from its memory over NVLink by TMA)
-  int scatter_rows;          // > 0 (reduce mode): batch row m belongs to rank m / scatter_rows — the tile is added into
-                             //      THAT rank's output only, at local row m % scatter_rows (reduce-scatter epilogue)
-  int* err;
+// the epilogue's memory operations (tc_body.cuh::epilogue_chunk)
+struct DeviceOut {
+  __device__ __forceinline__ void st16(uint16_t* p, uint16_t v) const { *p = v; }
+  __device__ __forceinline__ void st16x16(uint16_t* row, const float (&f)[16]) const {
+    uint32_t w[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      __nv_bfloat162 p = __floats2bfloat162_rn(f[2 * u], f[2 * u + 1]);
+      w[u] = *reinterpret_cast<uint32_t*>(&p);
+    }
+    reinterpret_cast<uint4*>(row)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    reinterpret_cast<uint4*>(row)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+  __device__ __forceinline__ void add1(float* p, float v, bool multicast) const {
+    if (multicast) multimem_red_add_f32(p, v); else ptx::red_add_f32(p, v);
+  }
+  __device__ __forceinline__ void add4(float* p, const float* f, bool multicast) const {
+    const float4 x = make_float4(f[0], f[1], f[2], f[3]);
+    if (multicast) multimem_red_add_v4_f32(p, x); else ptx::red_add_v4_f32(p, x);
+  }
 };
 
 // the batch operand's tensor maps: one, or one per rank when its row blocks live on different GPUs
@@ -238,33 +240,19 @@ tc_linear_kernel(const __grid_constant__ TcBatchMaps maps_batch, const __grid_co
       uint32_t g = 0;                              // k-blocks issued by this CTA so far (ring position)
       bool alive = true;
       for (int t = blockIdx.x; t < args.n_tiles && alive; t += gridDim.x) {
-        int a_row0 = (t % args.tiles_a) * kBM, b_row0 = (t / args.tiles_a) * BN;
-        // which operand is the batch: the lanes (plain) or the columns (swapped); with a gathered batch the tile's rows
-        // come from ONE rank's shard (gather_rows is a multiple of the tile height) at a row offset inside that shard
-        const CUtensorMap* map_a = kSwap ? &map_feat : &maps_batch.m[0];
-        const CUtensorMap* map_b = kSwap ? &maps_batch.m[0] : &map_feat;
-        if (args.gather_rows > 0) {
-          if constexpr (kSwap) { map_b = &maps_batch.m[b_row0 / args.gather_rows]; b_row0 %= args.gather_rows; }
-          else { map_a = &maps_batch.m[a_row0 / args.gather_rows]; a_row0 %= args.gather_rows; }
-        }
+        // the operand that is the batch rides the lanes (plain) or the columns (swapped); when it is gathered, the tile's
+        // rows come from ONE rank's map, at a row offset inside that rank's shard (tc_body.cuh::tile_coord)
+        const TileCoord tc = tile_coord<BN, kSwap>(args, t);
+        const CUtensorMap* map_a = kSwap ? &map_feat : &maps_batch.m[tc.a_map];
+        const CUtensorMap* map_b = kSwap ? &maps_batch.m[tc.b_map] : &map_feat;
         for (int i = 0; i < nkb; i++, g++) {
           const uint32_t s = g % kStages, round = g / kStages;
           if (round > 0 && !mbar_wait_wd(empty0 + 8 * s, (round - 1) & 1, args.err, 1)) { alive = false; break; }
-          const uint32_t a_dst = base + s * Smem<BN>::kStageBytes;
-          mbar_expect_tx(full0 + 8 * s, Smem<BN>::kStageBytes);
-          const int r0 = (kb_begin + i) * kBK;     // first reduction index of this block
-          if constexpr (!kAMn) {
-            tma_load_2d(a_dst, map_a, full0 + 8 * s, r0, a_row0);
-          } else {
-#pragma unroll
-            for (int h = 0; h < kBM / 64; h++) tma_load_2d(a_dst + h * 8192, map_a, full0 + 8 * s, a_row0 + 64 * h, r0);
-          }
-          if constexpr (!kBMn) {
-            tma_load_2d(a_dst + kABytes, map_b, full0 + 8 * s, r0, b_row0);
-          } else {
-#pragma unroll
-            for (int h = 0; h < BN / 64; h++) tma_load_2d(a_dst + kABytes + h * 8192, map_b, full0 + 8 * s, b_row0 + 64 * h, r0);
-          }
+          const uint32_t a_dst = base + s * Smem<BN>::kStageBytes, bar = full0 + 8 * s;
+          mbar_expect_tx(bar, Smem<BN>::kStageBytes);
+          stage_loads<BN, kAMn, kBMn>(tc, (kb_begin + i) * kBK, [&](int operand, int offset, int c0, int c1) {
+            tma_load_2d(a_dst + (operand ? kABytes : 0) + offset, operand ? map_b : map_a, bar, c0, c1);
+          });
         }
       }
     }
@@ -305,13 +293,11 @@ tc_linear_kernel(const __grid_constant__ TcBatchMaps maps_batch, const __grid_co
     uint32_t lt = 0;
     for (int t = blockIdx.x; t < args.n_tiles; t += gridDim.x, lt++) {
       const uint32_t as = lt & 1;
-      const int a_row0 = (t % args.tiles_a) * kBM, b_row0 = (t / args.tiles_a) * BN;
-      const int i_glob = a_row0 + q * 32 + lane;   // row of the lane operand this thread owns
+      const TileCoord tc = tile_coord<BN, kSwap>(args, t);
+      const int i_glob = tc.a_row0 + q * 32 + lane;   // row of the lane operand this thread owns
       if (!mbar_wait_wd(acc_full0 + 8 * as, (lt >> 1) & 1, args.err, 3)) break;
       tc_fence_after_sync();
       const uint32_t tmem_d = tmem_base + as * BN;
-      float bias_i = 0.f;
-      if (kSwap && add_bias && i_glob < args.rows_a) bias_i = __bfloat162float(args.bias[i_glob]);
 #pragma unroll 1
       for (int c = 0; c < BN / 16; c++) {
         uint32_t v[16];
@@ -322,74 +308,10 @@ tc_linear_kernel(const __grid_constant__ TcBatchMaps maps_batch, const __grid_co
           tc_fence_before_sync();
           mbar_arrive(acc_empty0 + 8 * as);
         }
-        const int j0 = b_row0 + c * 16;
-        if (i_glob >= args.rows_a || j0 >= args.rows_b) continue;
-        float f[16];
+        float acc[16];
 #pragma unroll
-        for (int u = 0; u < 16; u++) {
-          float b = kSwap ? bias_i : ((add_bias && j0 + u < args.rows_b) ? __bfloat162float(args.bias[j0 + u]) : 0.f);
-          f[u] = __uint_as_float(v[u]) + b;
-          if (!kReduce && args.act == BNET_TC_ACT_RELU) f[u] = fmaxf(f[u], 0.f);
-        }
-        if constexpr (!kReduce) {
-          __nv_bfloat16* out = static_cast<__nv_bfloat16*>(args.outs[0]);
-          if constexpr (kSwap) {
-            // out[(j0 + u) * ldo + i]: for every u the warp writes 32 consecutive features
-#pragma unroll
-            for (int u = 0; u < 16; u++)
-              if (j0 + u < args.rows_b) out[size_t(j0 + u) * args.ldo + i_glob] = __float2bfloat16_rn(f[u]);
-          } else {
-            __nv_bfloat16* row = out + size_t(i_glob) * args.ldo + j0;
-            if (j0 + 16 <= args.rows_b && (reinterpret_cast<uintptr_t>(row) & 15) == 0) {
-              uint32_t w[8];
-#pragma unroll
-              for (int u = 0; u < 8; u++) {
-                __nv_bfloat162 p = __floats2bfloat162_rn(f[2 * u], f[2 * u + 1]);
-                w[u] = *reinterpret_cast<uint32_t*>(&p);
-              }
-              reinterpret_cast<uint4*>(row)[0] = make_uint4(w[0], w[1], w[2], w[3]);
-              reinterpret_cast<uint4*>(row)[1] = make_uint4(w[4], w[5], w[6], w[7]);
-            } else {
-#pragma unroll
-              for (int u = 0; u < 16; u++)
-                if (j0 + u < args.rows_b) row[u] = __float2bfloat16_rn(f[u]);
-            }
-          }
-        } else {
-          // fp32 adds into EVERY rank's output (the all-reduce of the row-parallel layer, tile by tile), or with
-          // scatter_rows into the output of the rank that owns the batch row (reduce-scatter)
-          const int o_begin = 0, o_end = args.scatter_rows > 0 ? 1 : args.n_outs;
-          for (int oi = o_begin; oi < o_end; oi++) {
-            if constexpr (kSwap) {
-#pragma unroll
-              for (int u = 0; u < 16; u++) {
-                int m = j0 + u;                      // batch row
-                if (m >= args.rows_b) continue;
-                int o = oi;
-                if (args.scatter_rows > 0) { o = m / args.scatter_rows; m -= o * args.scatter_rows; }
-                float* p = static_cast<float*>(args.outs[o]) + size_t(m) * args.ldo + i_glob;
-                if (args.multicast) multimem_red_add_f32(p, f[u]); else ptx::red_add_f32(p, f[u]);
-              }
-            } else {
-              int m = i_glob, o = oi;
-              if (args.scatter_rows > 0) { o = m / args.scatter_rows; m -= o * args.scatter_rows; }
-              float* row = static_cast<float*>(args.outs[o]) + size_t(m) * args.ldo + j0;
-              const bool vec = j0 + 16 <= args.rows_b && (reinterpret_cast<uintptr_t>(row) & 15) == 0;
-#pragma unroll
-              for (int u = 0; u < 16; u += 4) {
-                if (vec) {
-                  const float4 x = make_float4(f[u], f[u + 1], f[u + 2], f[u + 3]);
-                  if (args.multicast) multimem_red_add_v4_f32(row + u, x); else ptx::red_add_v4_f32(row + u, x);
-                } else {
-                  for (int e = u; e < u + 4; e++) {
-                    if (j0 + e >= args.rows_b) continue;
-                    if (args.multicast) multimem_red_add_f32(row + e, f[e]); else ptx::red_add_f32(row + e, f[e]);
-                  }
-                }
-              }
-            }
-          }
-        }
+        for (int u = 0; u < 16; u++) acc[u] = __uint_as_float(v[u]);
+        epilogue_chunk<kSwap, kReduce>(args, i_glob, tc.b_row0 + c * 16, acc, add_bias, DeviceOut{});
       }
     }
   }
@@ -423,24 +345,20 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// One GEMM operand: `rows` entries along its MN dimension (the one that survives), `red` along the reduction.
-//   K-major  (mn = 0): element (i, r) at ptr[i * ld + r]  -> boxes of [box_mn rows x 64 r], 128-byte swizzle
-//   MN-major (mn = 1): element (i, r) at ptr[r * ld + i]  -> boxes of [64 r rows x 64 i]
-// Rows / columns outside the matrix read as zero, so ragged extents need no special case in the kernel.
-struct Operand { const void* ptr; int rows; int ld; int mn; };
-
-bool make_map(CUtensorMap* map, const Operand& o, int red, int box_mn) {
+// MapDesc (tc_body.cuh) -> CUtensorMap: 2-D bf16, boxes of [box1 x box0], 128-byte swizzle; rows / columns outside the
+// matrix read as zero, so ragged extents need no special case in the kernel
+bool make_map(CUtensorMap* map, const MapDesc& d) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) { g_err = "the CUDA driver does not export cuTensorMapEncodeTiled"; return false; }
-  if ((reinterpret_cast<uintptr_t>(o.ptr) & 15) || (size_t(o.ld) * 2) % 16) {
+  if ((reinterpret_cast<uintptr_t>(d.ptr) & 15) || (size_t(d.pitch_elems) * 2) % 16) {
     g_err = "operands must be 16-byte aligned with a row pitch that is a multiple of 8 elements";
     return false;
   }
-  const cuuint64_t dims[2] = {cuuint64_t(o.mn ? o.rows : red), cuuint64_t(o.mn ? red : o.rows)};
-  const cuuint64_t strides[1] = {cuuint64_t(o.ld) * 2};
-  const cuuint32_t box[2] = {cuuint32_t(kBK), cuuint32_t(o.mn ? kBK : box_mn)};
+  const cuuint64_t dims[2] = {cuuint64_t(d.dim0), cuuint64_t(d.dim1)};
+  const cuuint64_t strides[1] = {cuuint64_t(d.pitch_elems) * 2};
+  const cuuint32_t box[2] = {cuuint32_t(d.box0), cuuint32_t(d.box1)};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(o.ptr), dims, strides, box, estr,
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d.ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { g_err = "cuTensorMapEncodeTiled failed: " + std::to_string(int(r)); return false; }
@@ -461,8 +379,6 @@ int launch(const TcBatchMaps& mbatch, const CUtensorMap& mfeat, const TcArgs& a,
   return 1;
 }
 
-constexpr int stages_for(int bn) { return bn <= 64 ? 6 : (bn <= 128 ? 5 : 4); }
-
 // SMs of the current device; 148 (B200) when there is none to ask (host-only planning in the CPU tests)
 int sm_count() {
   static int n = 0;
@@ -475,78 +391,27 @@ int sm_count() {
   return n;
 }
 
-// Tiling of D[rows_a, rows_b] = A . B^T over `red`: `batch` is the extent that decides the orientation (the forward's
-// and dX's batch dimension M; pass a large value for dW, whose both extents are feature counts).
-int plan_gemm(int rows_lane_if_noswap, int rows_col_if_noswap, int red, int reduce, int splits, BnetTcPlan* p) {
-  // the caller passes the problem as (batch-like extent, feature-like extent): swap puts the features on the lanes
-  const int M = rows_lane_if_noswap, N = rows_col_if_noswap;
-  p->swap = M <= 64 ? 1 : 0;
-  p->bn = p->swap ? (M <= 32 ? 32 : 64) : 128;
-  // 128 x 256 tiles (the whole TMEM: 2 x 256 accumulator columns) once they still fill every SM: half the MMA issues and
-  // 1.5x the arithmetic intensity per shared-memory byte of a 128 x 128 tile
-  if (!p->swap && (long long)((N + 255) / 256) * ((M + kBM - 1) / kBM) >= sm_count()) p->bn = 256;
-  p->stages = stages_for(p->bn);
-  const int rows_a = p->swap ? N : M, rows_b = p->swap ? M : N;
-  p->grid_x = (rows_b + p->bn - 1) / p->bn;
-  p->grid_y = (rows_a + kBM - 1) / kBM;
-  p->k_blocks = (red + kBK - 1) / kBK;
-  int z = (reduce && splits > 1) ? splits : 1;
-  if (z > p->k_blocks) z = p->k_blocks;
-  p->k_per_split = (p->k_blocks + z - 1) / z;
-  p->grid_z = (p->k_blocks + p->k_per_split - 1) / p->k_per_split;   // no empty slices
-  // tiles + alignment slack + (2 * stages + 4) mbarriers + the TMEM address slot
-  p->smem_bytes = p->stages * (kABytes + p->bn * kBK * 2) + 1024 + (2 * p->stages + 4) * 8 + 16;
-  if (p->grid_z > 65535 || (long long)p->grid_x * p->grid_y > 0x7fffffffLL) { g_err = "problem too large for one launch"; return -1; }
-  // persistent once there are more tiles than SMs: one CTA per SM (shared memory allows no second one anyway)
-  const int n_tiles = p->grid_x * p->grid_y;
-  const int per_slice = sm_count() / p->grid_z > 0 ? sm_count() / p->grid_z : 1;
-  p->ctas = n_tiles < per_slice ? n_tiles : per_slice;
-  return 0;
-}
-
 // `batch` / `feat`: the two operands in problem order (out[batch index, feature index]); the plan decides which of them
-// rides the TMEM lanes.  bias is indexed by the feature.
-// `shards` (optional): the batch operand's row blocks live in n_shards separate allocations of batch.rows / n_shards rows
-// each (the other ranks' symmetric heaps); `scatter_ranks` > 0 (reduce mode): outs[r] receives only the rows rank r owns.
+// rides the TMEM lanes.  bias is indexed by the feature.  All the index logic is tc_body.cuh::setup_problem (pure, unit-
+// tested on the CPU); here the map descriptions are encoded and the instantiation is picked.
 int run(const Operand& batch, const Operand& feat, int red, const void* bias, void* const* outs, int n_outs, int multicast,
         bool reduce, int ldo, int act, int splits, int* err_dev, void* stream, const void* const* shards = nullptr,
         int n_shards = 0, int scatter_ranks = 0) {
-  BnetTcPlan p;
-  if (batch.rows < 1 || feat.rows < 1 || red < 1) { g_err = "bad problem size"; return -1; }
-  if (plan_gemm(batch.rows, feat.rows, red, reduce ? 1 : 0, splits, &p) != 0) return -1;
-  if (!err_dev) { g_err = "err_dev is required"; return -1; }
-  if (n_outs < 1 || n_outs > BNET_TC_MAX_OUTS) { g_err = "n_outs out of range"; return -1; }
-  const Operand& oa = p.swap ? feat : batch;     // lane operand: 128-row tiles
-  const Operand& ob = p.swap ? batch : feat;     // column operand: bn-row tiles
-  TcBatchMaps mbatch;
-  CUtensorMap mfeat;
-  TcArgs a{};
-  const int batch_box = p.swap ? p.bn : kBM;     // rows of one box of the batch operand
-  if (n_shards > 0) {
-    if (n_shards > BNET_TC_MAX_PEERS || batch.rows % n_shards) { g_err = "bad shard count"; return -1; }
-    a.gather_rows = batch.rows / n_shards;
-    if (a.gather_rows % batch_box) { g_err = "rows per shard must be a multiple of the tile height (128)"; return -1; }
-    for (int r = 0; r < n_shards; r++) {
-      Operand o = batch;
-      o.ptr = shards[r];
-      o.rows = a.gather_rows;
-      if (!make_map(&mbatch.m[r], o, red, batch_box)) return -1;
-    }
-  } else if (!make_map(&mbatch.m[0], batch, red, batch_box)) {
+  Problem pr;
+  if (const char* e = setup_problem(batch, feat, red, bias, outs, n_outs, multicast, reduce, ldo, act, splits, err_dev, shards,
+                                    n_shards, scatter_ranks, sm_count(), &pr)) {
+    g_err = e;
     return -1;
   }
-  if (!make_map(&mfeat, feat, red, p.swap ? kBM : p.bn)) return -1;
-  if (scatter_ranks > 0) {
-    if (!reduce || multicast || n_outs != scatter_ranks || batch.rows % scatter_ranks) { g_err = "bad reduce-scatter arguments"; return -1; }
-    a.scatter_rows = batch.rows / scatter_ranks;
-  }
-  a.rows_a = oa.rows; a.rows_b = ob.rows; a.tiles_a = p.grid_y; a.n_tiles = p.grid_x * p.grid_y;
-  a.k_blocks = p.k_blocks; a.k_per_split = p.k_per_split; a.ldo = ldo; a.act = act;
-  a.bias = static_cast<const __nv_bfloat16*>(bias);
-  for (int i = 0; i < n_outs; i++) a.outs[i] = outs[i];
-  a.n_outs = n_outs; a.multicast = multicast; a.err = err_dev;
+  TcBatchMaps mbatch;
+  CUtensorMap mfeat;
+  for (int r = 0; r < pr.n_batch_maps; r++)
+    if (!make_map(&mbatch.m[r], pr.batch_maps[r])) return -1;
+  if (!make_map(&mfeat, pr.feat_map)) return -1;
+  const BnetTcPlan& p = pr.plan;
+  const TcArgs& a = pr.args;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bool amn = oa.mn != 0, bmn = ob.mn != 0, swap = p.swap != 0;
+  const bool amn = pr.a_mn, bmn = pr.b_mn, swap = p.swap != 0;
 #define BNET_TC_CASE(BN, SWAP, RED, AMN, BMN)                                          \
   if (p.bn == BN && swap == SWAP && reduce == RED && amn == AMN && bmn == BMN)        \
     return launch<BN, stages_for(BN), SWAP, RED, AMN, BMN>(mbatch, mfeat, a, p, st);
@@ -585,7 +450,8 @@ BNET_API int bnet_tc_supported(void) {
 BNET_API int bnet_tc_plan(int M, int N, int K, int reduce, int splits, BnetTcPlan* p) {
   if (!p || M < 1 || N < 1 || K < 1) { g_err = "bad problem size"; return -1; }
   if (K % 8) { g_err = "K must be a multiple of 8 (16-byte TMA row pitch)"; return -1; }
-  return plan_gemm(M, N, K, reduce, splits, p);
+  if (plan_gemm(M, N, K, reduce, splits, sm_count(), p) != 0) { g_err = "problem too large for one launch"; return -1; }
+  return 0;
 }
 
 BNET_API int bnet_tc_linear(const void* x, const void* w, const void* bias, void* out, int M, int N, int K, int ldx, int ldw,

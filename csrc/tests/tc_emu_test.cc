@@ -1,0 +1,291 @@
+// The tcgen05 linear kernel's index logic (csrc/cuda/tc_body.cuh) on an emulated TMA / MMA / TMEM, no GPU needed.
+//
+// What runs here is the code the kernel runs: setup_problem (orientation, tensor-map descriptions, kernel arguments),
+// tile_coord (tile -> rows, gathered shard), stage_loads (which TMA boxes, at which coordinates, where in the stage) and
+// epilogue_chunk (bias / ReLU / bf16 store, cross-rank adds, reduce-scatter).  What is emulated: the TMA engine (a box
+// copy with zero fill), the MMA (a dot product over the stage as the shared-memory descriptors describe it: K-major
+// rows, or MN-major 64 x 64 atoms 8 KiB apart) and TMEM (a float array).  Every mode is compared with a plain GEMM.
+//
+//   make build/tests/tc_emu_test && build/tests/tc_emu_test
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <vector>
+
+#include "cuda/tc_body.cuh"
+
+using namespace bnet::tc;
+
+static int g_failures = 0;
+#define CHECK(cond, ...) do { if (!(cond)) { printf("FAIL %s:%d: ", __FILE__, __LINE__); printf(__VA_ARGS__); printf("\n"); g_failures++; } } while (0)
+
+static uint32_t g_rng = 12345;
+static float rnd() { g_rng = g_rng * 1664525u + 1013904223u; return float(int((g_rng >> 9) % 9) - 4) * 0.25f; }   // exact in bf16
+
+struct Mat {   // bf16 matrix with a row pitch
+  int rows, cols, ld;
+  std::vector<uint16_t> v;
+  Mat(int r, int c, int pad = 0) : rows(r), cols(c), ld(c + pad), v(size_t(r) * (c + pad) + 8, 0x7fc0 /* NaN in the padding */) {
+    for (int i = 0; i < r; i++) for (int j = 0; j < c; j++) v[size_t(i) * ld + j] = f32_to_bf16(rnd());
+  }
+  float at(int i, int j) const { return bf16_to_f32(v[size_t(i) * ld + j]); }
+  const void* ptr() const { return v.data(); }
+};
+
+// ---- emulated hardware ---------------------------------------------------------------------------------------------------
+static void tma_box(const MapDesc& d, int c0, int c1, uint16_t* dst) {
+  const uint16_t* src = static_cast<const uint16_t*>(d.ptr);
+  for (int r = 0; r < d.box1; r++)
+    for (int c = 0; c < d.box0; c++) {
+      const long long x = c0 + c, y = c1 + r;
+      dst[r * d.box0 + c] = (x >= 0 && x < d.dim0 && y >= 0 && y < d.dim1) ? src[y * d.pitch_elems + x] : 0;
+    }
+}
+
+// element (i, k) of an operand's stage area, as the shared-memory descriptor of its major describes it
+static float stage_at(const uint16_t* area, bool mn, int i, int k) {
+  return bf16_to_f32(mn ? area[(i / 64) * (kAtomBytes / 2) + k * 64 + i % 64] : area[i * kBK + k]);
+}
+
+struct HostOut {
+  float* mc_base = nullptr;                 // multicast: the pointer the kernel was given ...
+  std::vector<float*> replicas;             // ... stands for these buffers (the switch replicates the add)
+  void st16(uint16_t* p, uint16_t v) const { *p = v; }
+  void st16x16(uint16_t* row, const float (&f)[16]) const { for (int u = 0; u < 16; u++) row[u] = f32_to_bf16(f[u]); }
+  void add1(float* p, float v, bool multicast) const {
+    if (!multicast) { *p += v; return; }
+    for (float* r : replicas) r[p - mc_base] += v;
+  }
+  void add4(float* p, const float* f, bool multicast) const { for (int u = 0; u < 4; u++) add1(p + u, f[u], multicast); }
+};
+
+template <int BN, bool kSwap, bool kReduce, bool kAMn, bool kBMn>
+static void run_kernel(const Problem& pr, const HostOut& out) {
+  const TcArgs& args = pr.args;
+  const BnetTcPlan& p = pr.plan;
+  std::vector<uint16_t> stage_a(kABytes / 2), stage_b(BN * kBK);
+  std::vector<float> tmem(size_t(kBM) * BN);
+  for (int z = 0; z < p.grid_z; z++) {
+    const int kb_begin = z * args.k_per_split;
+    const int kb_end = kb_begin + args.k_per_split < args.k_blocks ? kb_begin + args.k_per_split : args.k_blocks;
+    CHECK(kb_end > kb_begin, "empty K slice %d", z);
+    for (int cta = 0; cta < p.ctas; cta++) {
+      for (int t = cta; t < args.n_tiles; t += p.ctas) {
+        const TileCoord tc = tile_coord<BN, kSwap>(args, t);
+        std::fill(tmem.begin(), tmem.end(), 0.f);
+        for (int kb = kb_begin; kb < kb_end; kb++) {
+          std::fill(stage_a.begin(), stage_a.end(), uint16_t(0x7fc0));     // stale data must never be read
+          std::fill(stage_b.begin(), stage_b.end(), uint16_t(0x7fc0));
+          int bytes = 0;
+          stage_loads<BN, kAMn, kBMn>(tc, kb * kBK, [&](int operand, int offset, int c0, int c1) {
+            const MapDesc& d = operand == 0 ? (kSwap ? pr.feat_map : pr.batch_maps[tc.a_map])
+                                            : (kSwap ? pr.batch_maps[tc.b_map] : pr.feat_map);
+            tma_box(d, c0, c1, (operand ? stage_b.data() : stage_a.data()) + offset / 2);
+            bytes += d.box0 * d.box1 * 2;
+          });
+          CHECK(bytes == kABytes + BN * kBK * 2, "expect_tx bytes %d", bytes);
+          for (int i = 0; i < kBM; i++)
+            for (int j = 0; j < BN; j++) {
+              float s = 0.f;
+              for (int k = 0; k < kBK; k++) s += stage_at(stage_a.data(), kAMn, i, k) * stage_at(stage_b.data(), kBMn, j, k);
+              tmem[size_t(i) * BN + j] += s;
+            }
+        }
+        const bool add_bias = args.bias != nullptr && (!kReduce || z == 0);
+        for (int warp = 2; warp < 6; warp++)
+          for (int lane = 0; lane < 32; lane++) {
+            const int q = warp & 3, i_local = q * 32 + lane;
+            for (int c = 0; c < BN / 16; c++) {
+              float acc[16];
+              for (int u = 0; u < 16; u++) acc[u] = tmem[size_t(i_local) * BN + c * 16 + u];
+              epilogue_chunk<kSwap, kReduce>(args, tc.a_row0 + i_local, tc.b_row0 + c * 16, acc, add_bias, out);
+            }
+          }
+      }
+    }
+  }
+}
+
+static bool dispatch(const Problem& pr, bool reduce, const HostOut& out) {
+  const BnetTcPlan& p = pr.plan;
+  const bool swap = p.swap != 0, amn = pr.a_mn, bmn = pr.b_mn;
+#define CASE(BN, SWAP, RED, AMN, BMN) \
+  if (p.bn == BN && swap == SWAP && reduce == RED && amn == AMN && bmn == BMN) { run_kernel<BN, SWAP, RED, AMN, BMN>(pr, out); return true; }
+  CASE(32, true, false, false, false)   CASE(32, true, true, false, false)
+  CASE(64, true, false, false, false)   CASE(64, true, true, false, false)
+  CASE(128, false, false, false, false) CASE(128, false, true, false, false)
+  CASE(256, false, false, false, false) CASE(256, false, true, false, false)
+  CASE(128, false, false, false, true)  CASE(256, false, false, false, true)
+  CASE(32, true, false, true, false)    CASE(64, true, false, true, false)
+  CASE(128, false, false, true, true)   CASE(256, false, false, true, true)
+#undef CASE
+  return false;
+}
+
+static bool close(float got, double want) { return fabs(got - want) <= 0.02 + 0.01 * fabs(want); }
+
+// ---- scenarios -----------------------------------------------------------------------------------------------------------
+static void forward(int M, int N, int K, bool bias, bool relu, int sms, int pad) {
+  Mat x(M, K, pad), w(N, K, pad ? 8 : 0), b(1, N);
+  std::vector<uint16_t> out(size_t(M) * (N + 8) + 16, 0xdead);
+  uint16_t* o = out.data();
+  while (reinterpret_cast<uintptr_t>(o) & 15) o++;
+  void* outs[1] = {o};
+  int err = 0;
+  Problem pr;
+  const char* e = setup_problem(Operand{x.ptr(), M, x.ld, 0}, Operand{w.ptr(), N, w.ld, 0}, K, bias ? b.ptr() : nullptr, outs, 1, 0,
+                                false, N + 8, relu ? BNET_TC_ACT_RELU : 0, 1, &err, nullptr, 0, 0, sms, &pr);
+  CHECK(e == nullptr, "setup: %s", e ? e : "");
+  if (e) return;
+  CHECK(dispatch(pr, false, HostOut{}), "no kernel for forward %dx%dx%d", M, N, K);
+  int bad = 0;
+  for (int m = 0; m < M; m++)
+    for (int n = 0; n < N; n++) {
+      double r = bias ? b.at(0, n) : 0.0;
+      for (int k = 0; k < K; k++) r += double(x.at(m, k)) * w.at(n, k);
+      if (relu && r < 0) r = 0;
+      if (!close(bf16_to_f32(o[size_t(m) * (N + 8) + n]), r)) bad++;
+    }
+  for (int m = 0; m < M; m++)
+    for (int n = N; n < N + 8; n++)
+      if (o[size_t(m) * (N + 8) + n] != 0xdead) bad++;       // nothing written past the row
+  CHECK(bad == 0, "forward M=%d N=%d K=%d bias=%d relu=%d sms=%d (swap %d bn %d ctas %d): %d wrong", M, N, K, bias, relu, sms,
+        pr.plan.swap, pr.plan.bn, pr.plan.ctas, bad);
+}
+
+static void reduce(int M, int N, int K, int n_outs, bool multicast, int splits, int scatter, bool bias) {
+  Mat x(M, K), w(N, K), b(1, N);
+  const int rows_out = scatter ? M / scatter : M;
+  const int n_bufs = scatter ? scatter : n_outs;
+  std::vector<std::vector<float>> bufs(n_bufs, std::vector<float>(size_t(rows_out) * N + 4, 0.f));
+  std::vector<float*> ptrs;
+  for (auto& v : bufs) { float* p = v.data(); while (reinterpret_cast<uintptr_t>(p) & 15) p++; ptrs.push_back(p); }
+  HostOut ho;
+  void* outs[BNET_TC_MAX_OUTS];
+  int n = 0;
+  if (multicast) { ho.mc_base = ptrs[0]; ho.replicas = ptrs; outs[0] = ptrs[0]; n = 1; }
+  else { for (float* p : ptrs) outs[n++] = p; }
+  int err = 0;
+  Problem pr;
+  const char* e = setup_problem(Operand{x.ptr(), M, x.ld, 0}, Operand{w.ptr(), N, w.ld, 0}, K, bias ? b.ptr() : nullptr, outs, n,
+                                multicast ? 1 : 0, true, N, 0, splits, &err, nullptr, 0, scatter, 148, &pr);
+  CHECK(e == nullptr, "setup: %s", e ? e : "");
+  if (e) return;
+  CHECK(dispatch(pr, true, ho), "no kernel for reduce %dx%dx%d", M, N, K);
+  int bad = 0;
+  for (int m = 0; m < M; m++)
+    for (int nn = 0; nn < N; nn++) {
+      double r = bias ? b.at(0, nn) : 0.0;
+      for (int k = 0; k < K; k++) r += double(x.at(m, k)) * w.at(nn, k);
+      for (int o = 0; o < n_bufs; o++) {
+        double want = r;
+        int row = m;
+        if (scatter) { want = (m / rows_out == o) ? r : 0.0; row = m % rows_out; if (m / rows_out != o) continue; }
+        if (!close(ptrs[o][size_t(row) * N + nn], want)) bad++;
+      }
+    }
+  CHECK(bad == 0, "reduce M=%d N=%d K=%d outs=%d mc=%d splits=%d scatter=%d (swap %d bn %d z %d): %d wrong", M, N, K, n_outs,
+        multicast, splits, scatter, pr.plan.swap, pr.plan.bn, pr.plan.grid_z, bad);
+}
+
+static void gather(int shards, int rows, int N, int K) {
+  std::vector<Mat> xs;
+  for (int r = 0; r < shards; r++) xs.emplace_back(rows, K);
+  Mat w(N, K), b(1, N);
+  const int M = shards * rows;
+  std::vector<uint16_t> out(size_t(M) * N + 16, 0);
+  uint16_t* o = out.data();
+  while (reinterpret_cast<uintptr_t>(o) & 15) o++;
+  void* outs[1] = {o};
+  const void* sp[BNET_TC_MAX_PEERS];
+  for (int r = 0; r < shards; r++) sp[r] = xs[r].ptr();
+  int err = 0;
+  Problem pr;
+  const char* e = setup_problem(Operand{sp[0], M, K, 0}, Operand{w.ptr(), N, w.ld, 0}, K, b.ptr(), outs, 1, 0, false, N, 0, 1, &err, sp,
+                                shards, 0, 5, &pr);
+  CHECK(e == nullptr, "setup: %s", e ? e : "");
+  if (e) return;
+  CHECK(dispatch(pr, false, HostOut{}), "no kernel for gather");
+  int bad = 0;
+  for (int m = 0; m < M; m++)
+    for (int n = 0; n < N; n++) {
+      double r = b.at(0, n);
+      for (int k = 0; k < K; k++) r += double(xs[m / rows].at(m % rows, k)) * w.at(n, k);
+      if (!close(bf16_to_f32(o[size_t(m) * N + n]), r)) bad++;
+    }
+  CHECK(bad == 0, "all-gather linear %d x %d rows, N=%d K=%d: %d wrong", shards, rows, N, K, bad);
+}
+
+static void backward(int M, int N, int K) {
+  Mat gy(M, N), w(N, K), x(M, K);
+  std::vector<uint16_t> dxv(size_t(M) * K + 16, 0), dwv(size_t(N) * K + 16, 0);
+  uint16_t *dx = dxv.data(), *dw = dwv.data();
+  while (reinterpret_cast<uintptr_t>(dx) & 15) dx++;
+  while (reinterpret_cast<uintptr_t>(dw) & 15) dw++;
+  int err = 0;
+  Problem pr;
+  void* o1[1] = {dx};
+  const char* e = setup_problem(Operand{gy.ptr(), M, gy.ld, 0}, Operand{w.ptr(), K, w.ld, 1}, N, nullptr, o1, 1, 0, false, K, 0, 1, &err,
+                                nullptr, 0, 0, 148, &pr);
+  CHECK(e == nullptr, "dgrad setup: %s", e ? e : "");
+  if (!e) {
+    CHECK(dispatch(pr, false, HostOut{}), "no kernel for dgrad %dx%dx%d (swap %d bn %d)", M, N, K, pr.plan.swap, pr.plan.bn);
+    int bad = 0;
+    for (int m = 0; m < M; m++)
+      for (int k = 0; k < K; k++) {
+        double r = 0;
+        for (int n = 0; n < N; n++) r += double(gy.at(m, n)) * w.at(n, k);
+        if (!close(bf16_to_f32(dx[size_t(m) * K + k]), r)) bad++;
+      }
+    CHECK(bad == 0, "dgrad M=%d N=%d K=%d (swap %d): %d wrong", M, N, K, pr.plan.swap, bad);
+  }
+  if (N <= 64) return;
+  void* o2[1] = {dw};
+  e = setup_problem(Operand{gy.ptr(), N, gy.ld, 1}, Operand{x.ptr(), K, x.ld, 1}, M, nullptr, o2, 1, 0, false, K, 0, 1, &err, nullptr, 0, 0,
+                    148, &pr);
+  CHECK(e == nullptr, "wgrad setup: %s", e ? e : "");
+  if (e) return;
+  CHECK(dispatch(pr, false, HostOut{}), "no kernel for wgrad %dx%dx%d", M, N, K);
+  int bad = 0;
+  for (int n = 0; n < N; n++)
+    for (int k = 0; k < K; k++) {
+      double r = 0;
+      for (int m = 0; m < M; m++) r += double(gy.at(m, n)) * x.at(m, k);
+      if (!close(bf16_to_f32(dw[size_t(n) * K + k]), r)) bad++;
+    }
+  CHECK(bad == 0, "wgrad M=%d N=%d K=%d: %d wrong", M, N, K, bad);
+}
+
+int main() {
+  // forward: both orientations, ragged extents, row pitches, one tile per CTA and persistent (few "SMs")
+  forward(32, 256, 512, true, true, 148, 0);
+  forward(48, 200, 264, true, false, 148, 16);
+  forward(1, 8, 8, false, false, 148, 0);
+  forward(64, 130, 72, true, true, 2, 0);
+  forward(130, 136, 72, true, false, 148, 8);
+  forward(257, 129, 200, false, true, 3, 0);
+  forward(300, 520, 136, true, true, 4, 0);
+  forward(256, 512, 64, true, false, 2, 0);           // 128 x 256 tiles (2 x 2 of them >= 2 SMs)
+  // GEMM + all-reduce: per-peer adds, multicast, split-K, bias once
+  reduce(32, 136, 264, 3, false, 1, 0, true);
+  reduce(32, 136, 520, 2, false, 4, 0, true);
+  reduce(130, 200, 264, 3, false, 2, 0, false);
+  reduce(40, 72, 136, 1, true, 1, 0, true);
+  reduce(256, 136, 200, 1, true, 3, 0, true);
+  // GEMM + reduce-scatter
+  reduce(96, 136, 264, 0, false, 1, 3, true);
+  reduce(512, 72, 136, 0, false, 2, 4, false);
+  reduce(48, 200, 72, 0, false, 1, 2, true);
+  // all-gather + GEMM
+  gather(2, 128, 136, 200);
+  gather(3, 256, 72, 72);
+  // backward GEMMs: MN-major operands, both orientations of dX
+  backward(32, 136, 264);
+  backward(64, 72, 136);
+  backward(130, 200, 72);
+  backward(256, 320, 192);
+  backward(40, 64, 128);
+  printf("tc_emu_test: %s (%d failures)\n", g_failures ? "FAILED" : "passed", g_failures);
+  return g_failures ? 1 : 0;
+}

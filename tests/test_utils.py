@@ -102,7 +102,8 @@ def test_device_kernel_bodies_on_an_emulated_grid():
     import bagua_net_b200
 
     root = bagua_net_b200.REPO_ROOT
-    for name in ("nn_emu_test", "exec_emu_test"):    # fused layer kernels; transport executor (copy/reduce/cast/fp8)
+    # fused layer kernels; transport executor (copy/reduce/cast/fp8); tcgen05 linear (tiling, TMA boxes, epilogues)
+    for name in ("nn_emu_test", "exec_emu_test", "tc_emu_test"):
         subprocess.run(["make", "-s", f"build/tests/{name}"], cwd=root, check=True, capture_output=True)
         r = subprocess.run([os.path.join(root, "build", "tests", name)], capture_output=True, text=True)
         assert r.returncode == 0 and "passed" in r.stdout, r.stdout[-2000:]
