@@ -206,11 +206,64 @@ def linear_bias_act(x, w, bias=None, relu=False):
 _trusted: bool | None = None
 
 
+def _isolated_self_check(timeout: float = 180.0) -> bool:
+    """``self_check()`` in a child process: a kernel that faults (a poisoned CUDA context) or hangs past its own watchdog
+    must not take the training process with it.  The verdict is cached per (library build, GPU model) under
+    ``$BNET_CACHE_DIR`` (default ``~/.cache/bnet``), so only the first process on a machine pays for it."""
+    import hashlib
+    import json
+    import subprocess
+    import sys
+
+    from .. import LIB_DIR, LIB_NAME, REPO_ROOT
+
+    lib = os.path.join(LIB_DIR, LIB_NAME)
+    try:
+        key = f"{os.path.getmtime(lib):.0f}-{os.path.getsize(lib)}-{torch.cuda.get_device_name()}-{torch.version.cuda}"
+    except Exception:  # noqa: BLE001
+        return False
+    cache_dir = os.environ.get("BNET_CACHE_DIR") or os.path.join(os.path.expanduser("~"), ".cache", "bnet")
+    path = os.path.join(cache_dir, "tc_self_check_" + hashlib.sha1(key.encode()).hexdigest()[:16] + ".json")
+    try:
+        with open(path) as f:
+            return bool(json.load(f)["ok"])
+    except Exception:  # noqa: BLE001 — no verdict yet
+        pass
+    env = dict(os.environ, PYTHONPATH=REPO_ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""),
+               CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", ""))
+    if not env["CUDA_VISIBLE_DEVICES"]:
+        env.pop("CUDA_VISIBLE_DEVICES")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):     # the child is a plain 1-GPU process
+        env.pop(k, None)
+    code = ("import sys, torch; torch.cuda.set_device(%d); from bagua_net_b200.ops import tc_linear; "
+            "sys.exit(0 if tc_linear.self_check() else 1)" % torch.cuda.current_device())
+    try:
+        ok = subprocess.run([sys.executable, "-c", code], env=env, timeout=timeout, stdout=subprocess.DEVNULL,
+                            stderr=subprocess.DEVNULL).returncode == 0
+    except Exception:  # noqa: BLE001 — timeout, spawn failure: not trusted
+        ok = False
+    try:
+        os.makedirs(cache_dir, exist_ok=True)
+        tmp = f"{path}.{os.getpid()}"
+        with open(tmp, "w") as f:
+            json.dump({"ok": ok, "key": key}, f)
+        os.replace(tmp, path)
+    except OSError:
+        pass
+    return ok
+
+
 def trusted() -> bool:
-    """enabled() and a passing self-check on this GPU (evaluated once per process)."""
+    """enabled() and a passing self-check on this GPU, run in a child process and evaluated once per process
+    (``BNET_TC_INPROC_CHECK=1`` runs the check in this process instead)."""
     global _trusted
     if _trusted is None:
-        _trusted = enabled() and self_check()
+        if not (enabled() and supported()):
+            _trusted = False
+        elif os.environ.get("BNET_TC_INPROC_CHECK") == "1":
+            _trusted = self_check()
+        else:
+            _trusted = _isolated_self_check()
     return _trusted
 
 

@@ -309,3 +309,22 @@ def test_tc_linear_python_plan_and_gating(monkeypatch):
     with pytest.raises(ValueError):
         tc_linear.plan(32, 64, 100)
     assert tc_linear.self_check() is False or __import__("torch").cuda.is_available()   # no GPU here: a clean False
+
+
+def test_tc_self_check_runs_isolated_and_is_cached(monkeypatch, tmp_path):
+    """The opt-in tcgen05 path is only trusted after its self-check passed in a CHILD process (a faulting kernel must not
+    poison the trainer's CUDA context); the verdict is cached per library build and GPU model."""
+    import glob
+
+    import torch
+
+    from bagua_net_b200.ops import tc_linear
+
+    monkeypatch.setenv("BNET_CACHE_DIR", str(tmp_path))
+    monkeypatch.setattr(torch.cuda, "get_device_name", lambda *a: "Fake B200")
+    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+    assert tc_linear._isolated_self_check(timeout=120) is False        # no GPU in the child either: a clean "no"
+    files = glob.glob(str(tmp_path / "tc_self_check_*.json"))
+    assert len(files) == 1 and json.load(open(files[0]))["ok"] is False
+    json.dump({"ok": True}, open(files[0], "w"))                        # a cached verdict is honoured without a child
+    assert tc_linear._isolated_self_check(timeout=0.001) is True
