@@ -157,6 +157,36 @@ def maybe_reexec_for_plugin(args):
     os.execve(sys.executable, [sys.executable] + sys.argv, env)
 
 
+def isolated_self_check(name: str, local: int, timeout: float = 240.0):
+    """Run bagua_net_b200.ops.fused_nn.<name>() on GPU `local` in a CHILD process, so that a kernel that faults there
+    (a poisoned CUDA context) costs the fused layers, not the whole benchmark.
+    True / False = the check's verdict (a child killed by a signal counts as False);
+    None = the child could not do its job for an unrelated reason (start-up error, timeout): check in-process instead."""
+    root = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "LOCAL_WORLD_SIZE", "GROUP_RANK", "MASTER_ADDR", "MASTER_PORT",
+              "TORCHELASTIC_RUN_ID"):
+        env.pop(k, None)                        # the child is a plain single-GPU process
+    code = ("import sys\n"
+            "try:\n"
+            "    import torch\n"
+            f"    torch.cuda.set_device({int(local)})\n"
+            "    from bagua_net_b200.ops import fused_nn\n"
+            "except Exception:\n"
+            "    sys.exit(4)\n"
+            f"sys.exit(0 if fused_nn.{name}() else 3)\n")
+    try:
+        rc = subprocess.run([sys.executable, "-c", code], env=env, timeout=timeout, stdout=subprocess.DEVNULL,
+                            stderr=subprocess.DEVNULL).returncode
+    except Exception:                           # noqa: BLE001 - timeout, spawn failure
+        return None
+    if rc == 0:
+        return True
+    if rc == 3 or rc < 0:
+        return False
+    return None
+
+
 def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -213,7 +243,10 @@ def main() -> int:
         from bagua_net_b200.ops import fused_nn
 
         check = fused_nn.self_check if args.model.startswith("vgg") else fused_nn.self_check_bn
-        ok = torch.tensor([1 if check(dev) else 0], device=dev, dtype=torch.int32)
+        verdict = None if os.environ.get("BNET_BENCH_INPROC_CHECK") == "1" else isolated_self_check(check.__name__, local)
+        if verdict is None:
+            verdict = check(dev)
+        ok = torch.tensor([1 if verdict else 0], device=dev, dtype=torch.int32)
         if world > 1:
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if int(ok.item()) == 0:

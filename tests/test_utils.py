@@ -328,3 +328,34 @@ def test_tc_self_check_runs_isolated_and_is_cached(monkeypatch, tmp_path):
     assert len(files) == 1 and json.load(open(files[0]))["ok"] is False
     json.dump({"ok": True}, open(files[0], "w"))                        # a cached verdict is honoured without a child
     assert tc_linear._isolated_self_check(timeout=0.001) is True
+
+
+def test_bench_isolated_self_check_classifies_child_outcomes(monkeypatch):
+    """bench.py trusts the fused layer kernels only after their self-check ran in a child process: verdicts (exit 0 / 3,
+    or death by signal) are final, anything else falls back to the in-process check."""
+    import importlib.util
+    import types
+
+    spec = importlib.util.spec_from_file_location("bench_under_test2", os.path.join(ROOT, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    seen = {}
+
+    def fake_run(cmd, env=None, timeout=None, **kw):
+        seen["env"], seen["code"] = env, cmd[-1]
+        if fake_run.rc == "timeout":
+            raise subprocess.TimeoutExpired(cmd, timeout)
+        return types.SimpleNamespace(returncode=fake_run.rc)
+
+    monkeypatch.setattr(mod.subprocess, "run", fake_run)
+    monkeypatch.setenv("RANK", "3")
+    monkeypatch.setenv("WORLD_SIZE", "8")
+    for rc, want in ((0, True), (3, False), (-11, False), (-6, False), (4, None), (1, None), ("timeout", None)):
+        fake_run.rc = rc
+        assert mod.isolated_self_check("self_check", 5) is want, rc
+    assert "RANK" not in seen["env"] and "WORLD_SIZE" not in seen["env"] and ROOT in seen["env"]["PYTHONPATH"]
+    assert "set_device(5)" in seen["code"] and "fused_nn.self_check()" in seen["code"]
+    compile(seen["code"], "<child>", "exec")
+    # and for real, without a GPU: the child cannot even select a device -> "unrelated reason" -> None
+    monkeypatch.undo()
+    assert mod.isolated_self_check("self_check", 0, timeout=120) is None
