@@ -11,19 +11,27 @@
 // MN elements of the tile, 8 KiB each) and described to the MMA with the MN-major form of the shared-memory descriptor;
 // no transposed copy of any tensor is ever made.
 //
-// One CTA = one output tile, 6 warps, warp-specialised (guide "Anatomy of a Blackwell GEMM kernel"):
-//   warp 0, one lane   TMA producer: cp.async.bulk.tensor.2d of a [128 x 64] A box and a [BN x 64] B box per stage,
-//                      128-byte swizzle, completion on the stage's `full` mbarrier
-//   warp 1             allocates BN TMEM columns; one lane issues 4 tcgen05.mma (K = 16 each) per stage and
-//                      tcgen05.commit's the stage's `empty` mbarrier; after the last K block commits `acc_full`
+// Persistent CTAs (one per SM once there are more tiles than SMs), 6 warps, warp-specialised (guide "Anatomy of a
+// Blackwell GEMM kernel"); the ring of shared-memory stages runs through tile boundaries:
+//   warp 0, one lane   TMA producer: per stage one [128 x 64] lane box and one [BN x 64] column box (K-major operands) or
+//                      [64 x 64] boxes per 64 MN elements (MN-major operands), 128-byte swizzle, completion on the
+//                      stage's `full` mbarrier; a gathered batch operand is loaded from the owning rank's tensor map
+//   warp 1             allocates 2 x BN TMEM columns (two accumulator stages); one lane issues 4 tcgen05.mma (K = 16
+//                      each) per stage and tcgen05.commit's the stage's `empty` mbarrier; after a tile's last K block it
+//                      commits `acc_full[stage]`, and before reusing a stage it waits for `acc_empty[stage]`
 //   warps 2-5          epilogue: tcgen05.ld 32 lanes x 16 columns at a time -> bias / ReLU -> bf16 store, or (reduce
-//                      mode) fp32 adds into every rank's output: multimem.red through the NVSwitch multicast mapping
-//                      or red.global per peer.  Warp w may only touch TMEM lanes 32*(w%4) .. +31.
+//                      mode) fp32 adds into every rank's output — multimem.red through the NVSwitch multicast mapping
+//                      or red.global per peer — or into the owner's output only (reduce-scatter); arrives on
+//                      `acc_empty[stage]` as soon as the accumulator is in registers.  Warp w may only touch TMEM
+//                      lanes 32*(w%4) .. +31.
+// The index logic (tiling, TMA coordinates, epilogue addressing) is csrc/cuda/tc_body.cuh, shared with the CPU
+// emulation test; the mbarrier protocol is mirrored by tests/test_tc_pipeline_model.py.
 //
 // Every mbarrier wait carries a watchdog (kWatchdogNs): a pipeline that stops — a descriptor the hardware rejects, a
 // lost TMA completion — sets *err and lets every role fall through to the teardown instead of hanging the GPU.
 //
-// STATUS: not yet run on hardware (see include/bnet/bnet_tc.h).  Descriptor packing is unit-tested against CuTe.
+// STATUS: not yet run on hardware (see include/bnet/bnet_tc.h).  Descriptor packing is unit-tested against CuTe
+// (csrc/tests/tc_desc_test.cc).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
