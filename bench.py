@@ -281,9 +281,9 @@ def main() -> int:
             assert n == steps
 
         def launches():
-            from bagua_net_b200.ops import fused_nn
+            from bagua_net_b200.ops import fused_nn, tc_linear
 
-            return comm.launches + fused_nn.LAUNCHES
+            return comm.launches + fused_nn.LAUNCHES + tc_linear.LAUNCHES
         path = ("nvls" if (comm.has_multicast and world > 2) else "p2p") if world > 1 else "single"
     else:
         if args.comm == "nccl-plugin":
