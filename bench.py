@@ -160,8 +160,9 @@ def maybe_reexec_for_plugin(args):
 def isolated_self_check(name: str, local: int, timeout: float = 240.0):
     """Run bagua_net_b200.ops.fused_nn.<name>() on GPU `local` in a CHILD process, so that a kernel that faults there
     (a poisoned CUDA context) costs the fused layers, not the whole benchmark.
-    True / False = the check's verdict (a child killed by a signal counts as False);
-    None = the child could not do its job for an unrelated reason (start-up error, timeout): check in-process instead."""
+    True / False = the check's verdict (a child killed by a signal, or still running after `timeout` seconds — a hung
+    kernel — counts as False);
+    None = the child could not do its job for an unrelated reason (start-up error): check in-process instead."""
     root = os.path.dirname(os.path.abspath(__file__))
     env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "LOCAL_WORLD_SIZE", "GROUP_RANK", "MASTER_ADDR", "MASTER_PORT",
@@ -178,7 +179,9 @@ def isolated_self_check(name: str, local: int, timeout: float = 240.0):
     try:
         rc = subprocess.run([sys.executable, "-c", code], env=env, timeout=timeout, stdout=subprocess.DEVNULL,
                             stderr=subprocess.DEVNULL).returncode
-    except Exception:                           # noqa: BLE001 - timeout, spawn failure
+    except subprocess.TimeoutExpired:           # (subprocess.run has killed the child)
+        return False
+    except Exception:                           # noqa: BLE001 - spawn failure
         return None
     if rc == 0:
         return True

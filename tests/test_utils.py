@@ -350,7 +350,7 @@ def test_bench_isolated_self_check_classifies_child_outcomes(monkeypatch):
     monkeypatch.setattr(mod.subprocess, "run", fake_run)
     monkeypatch.setenv("RANK", "3")
     monkeypatch.setenv("WORLD_SIZE", "8")
-    for rc, want in ((0, True), (3, False), (-11, False), (-6, False), (4, None), (1, None), ("timeout", None)):
+    for rc, want in ((0, True), (3, False), (-11, False), (-6, False), (4, None), (1, None), ("timeout", False)):
         fake_run.rc = rc
         assert mod.isolated_self_check("self_check", 5) is want, rc
     assert "RANK" not in seen["env"] and "WORLD_SIZE" not in seen["env"] and ROOT in seen["env"]["PYTHONPATH"]
