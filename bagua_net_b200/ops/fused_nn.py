@@ -202,7 +202,9 @@ def self_check(device=None, verbose: bool = False) -> bool:
     try:
         g = torch.Generator(device=dev).manual_seed(1234)
         # narrow and wide channel counts (8 and 64 16-byte channel groups per pixel), with and without pooling
-        for cin, cout, hw, pool in ((16, 64, 20, False), (16, 64, 20, True), (32, 512, 14, False), (32, 512, 14, True)):
+        # ... and two layers at the benchmark's own spatial sizes (millions of rows: the capped, grid-striding launch)
+        for cin, cout, hw, pool in ((16, 64, 20, False), (16, 64, 20, True), (32, 512, 14, False), (32, 512, 14, True),
+                                    (16, 64, 224, True), (32, 128, 112, False)):
             blk = ConvBiasReLU(cin, cout, 3, 1, 1, pool=pool).to(dev).to(torch.bfloat16).to(memory_format=torch.channels_last)
             x = torch.randn(3, cin, hw, hw, device=dev, generator=g).to(torch.bfloat16).contiguous(
                 memory_format=torch.channels_last)
