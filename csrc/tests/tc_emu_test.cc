@@ -286,6 +286,17 @@ int main() {
   backward(130, 200, 72);
   backward(256, 320, 192);
   backward(40, 64, 128);
+  // randomised extents (multiples of 8 where TMA needs them), every mode
+  for (int it = 0; it < 40; it++) {
+    auto r = [&](int lo, int hi) { g_rng = g_rng * 1664525u + 1013904223u; return lo + int((g_rng >> 8) % uint32_t(hi - lo + 1)); };
+    const int M = r(1, 300), N = r(1, 40) * 8, K = r(1, 40) * 8, sms = r(1, 6);
+    forward(M, N, K, r(0, 1), r(0, 1), sms, r(0, 1) * 8);
+    if (it % 4 == 0) reduce(M, N, K, r(1, 4), false, r(1, 5), 0, r(0, 1));
+    if (it % 4 == 1) reduce(M, N, K, 1, true, r(1, 3), 0, r(0, 1));
+    if (it % 4 == 2) { const int ranks = r(2, 4); reduce(M * ranks, N, K, 0, false, r(1, 3), ranks, r(0, 1)); }
+    if (it % 4 == 3) backward(r(1, 40) * 8, N, K);
+    if (it % 8 == 5) gather(r(2, 4), 128 * r(1, 2), N, K);
+  }
   printf("tc_emu_test: %s (%d failures)\n", g_failures ? "FAILED" : "passed", g_failures);
   return g_failures ? 1 : 0;
 }
