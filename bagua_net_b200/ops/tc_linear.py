@@ -108,9 +108,21 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _auto_splits(M: int, N: int, K: int) -> int:
+    """Small-batch layers are weight streaming: with M <= 64 a [M, N] output has only N / 128 tiles — 32 CTAs for the VGG
+    classifier — and one SM cannot pull its 128 x K weight slab at more than a fraction of HBM speed.  Splitting K over
+    grid.z puts every SM to work; the partial tiles meet as fp32 adds in a small workspace."""
+    if M > 64 or K < 2048:
+        return 1
+    tiles = (N + 127) // 128
+    sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    return max(1, min(8, sms // max(tiles, 1), K // 1024))
+
+
 def linear(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, relu: bool = False,
-           out: torch.Tensor | None = None) -> torch.Tensor:
-    """``act(x @ w.T + bias)`` on the tcgen05 tensor cores; x [M,K], w [N,K] (torch ``Linear.weight``), bf16."""
+           out: torch.Tensor | None = None, splits: int | None = None) -> torch.Tensor:
+    """``act(x @ w.T + bias)`` on the tcgen05 tensor cores; x [M,K], w [N,K] (torch ``Linear.weight``), bf16.
+    ``splits``: K slices (None = automatic, see ``_auto_splits``; 1 = one pass with the epilogue fused in the kernel)."""
     global LAUNCHES
     _check_operands(x, w, bias)
     M, K = x.shape
@@ -119,6 +131,24 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, r
         out = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
     assert out.dtype == torch.bfloat16 and out.shape == (M, N) and out.stride(1) == 1
     L = _L()
+    if splits is None:
+        splits = _auto_splits(M, N, K)
+    if splits > 1:
+        # split-K: fp32 partial sums into a zeroed workspace (the kernel's reduce epilogue with a single, local target),
+        # then bias / ReLU / bf16 on the small result
+        ws = torch.zeros((M, N), dtype=torch.float32, device=x.device)
+        arr = (C.c_void_p * 1)(ws.data_ptr())
+        rc = L.bnet_tc_linear_reduce(x.data_ptr(), w.data_ptr(), None, arr, 1, 0, M, N, K, x.stride(0), w.stride(0), N, splits,
+                                     _err_flag(x.device.index).data_ptr(), _stream())
+        if rc < 0:
+            raise RuntimeError(f"bnet_tc_linear_reduce (split-K): {L.bnet_tc_last_error().decode()}")
+        LAUNCHES += rc
+        if bias is not None:
+            ws += bias.float()
+        if relu:
+            ws.relu_()
+        out.copy_(ws)
+        return out
     rc = L.bnet_tc_linear(x.data_ptr(), w.data_ptr(), bias.data_ptr() if bias is not None else None, out.data_ptr(), M, N,
                           K, x.stride(0), w.stride(0), out.stride(0), 1 if relu else 0,
                           _err_flag(x.device.index).data_ptr(), _stream())
@@ -396,7 +426,7 @@ def self_check(verbose: bool = False) -> bool:
             x = torch.randn(M, K, device="cuda", generator=g).bfloat16()
             w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
             b = torch.randn(N, device="cuda", generator=g).bfloat16()
-            y = linear(x, w, b, relu)
+            y = linear(x, w, b, relu, splits=1)
             if last_error():
                 return False
             ref = x.float() @ w.float().t() + b.float()

@@ -586,13 +586,13 @@ def job_tc_linear():
         x = torch.randn(M, K, device="cuda").bfloat16()
         w = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16()
         b = torch.randn(N, device="cuda").bfloat16()
-        for relu in (False, True):
-            y = tc_linear.linear(x, w, b, relu)
+        for relu, splits in ((False, 1), (True, 1), (True, None), (False, 3)):   # fused epilogue; automatic / forced split-K
+            y = tc_linear.linear(x, w, b, relu, splits=splits)
             assert tc_linear.last_error() == 0, f"watchdog tripped at {M}x{N}x{K}"
             ref = x.float() @ w.float().t() + b.float()
             ref = torch.relu(ref) if relu else ref
             err = (y.float() - ref).abs().max().item()
-            assert err < 0.08, f"tc_linear {M}x{N}x{K} relu={relu}: max abs err {err}"
+            assert err < 0.08, f"tc_linear {M}x{N}x{K} relu={relu} splits={splits}: max abs err {err}"
     # the backward GEMMs: W, gY and X read MN-major, both orientations of dX, ragged extents
     for (M, N, K) in [(32, 4096, 1024), (64, 136, 264), (200, 72, 520), (512, 1024, 768), (1000, 1000, 1000)]:
         gy = torch.randn(M, N, device="cuda").bfloat16()

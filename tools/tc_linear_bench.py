@@ -61,11 +61,13 @@ def main():
         ref = torch.relu(torch.nn.functional.linear(x, w, b))
         err = (y.float() - ref.float()).abs().max().item()
         t_ours = timed(lambda: tc_linear.linear(x, w, b, True, out=y), a.iters, a.warmup)
+        t_one = timed(lambda: tc_linear.linear(x, w, b, True, out=y, splits=1), a.iters, a.warmup) if M <= 64 else t_ours
         t_ref = timed(lambda: torch.relu_(torch.nn.functional.linear(x, w, b)), a.iters, a.warmup)
         flops = 2.0 * M * N * K
         nbytes = 2.0 * (M * K + N * K + M * N)
         print(f"  {shp:>22s} {t_ours:9.1f} {flops / t_ours / 1e6:7.0f} {nbytes / t_ours / 1e3:7.0f} {t_ref:10.1f} "
-              f"{flops / t_ref / 1e6:7.0f} {t_ref / t_ours:11.2f} {err:8.4f}" + (f"  WATCHDOG {flag}" if flag else ""))
+              f"{flops / t_ref / 1e6:7.0f} {t_ref / t_ours:11.2f} {err:8.4f}" + (f"  (no split-K: {t_one:.1f} us)" if M <= 64 else "")
+              + (f"  WATCHDOG {flag}" if flag else ""))
     return 0
 
 
