@@ -422,11 +422,13 @@ def self_check(verbose: bool = False) -> bool:
         if not supported():
             return False
         g = torch.Generator(device="cuda").manual_seed(7)
-        for (M, N, K, relu) in [(32, 256, 512, True), (48, 200, 264, False), (256, 384, 1024, True), (130, 136, 72, False)]:
+        # (the last shape is a small-batch, long-K layer: the automatic split-K path; the others run the fused epilogue)
+        for (M, N, K, relu) in [(32, 256, 512, True), (48, 200, 264, False), (256, 384, 1024, True), (130, 136, 72, False),
+                                (32, 512, 4096, True)]:
             x = torch.randn(M, K, device="cuda", generator=g).bfloat16()
             w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
             b = torch.randn(N, device="cuda", generator=g).bfloat16()
-            y = linear(x, w, b, relu, splits=1)
+            y = linear(x, w, b, relu, splits=None if K >= 4096 else 1)
             if last_error():
                 return False
             ref = x.float() @ w.float().t() + b.float()
