@@ -328,6 +328,7 @@ tc_linear_kernel(const __grid_constant__ TcBatchMaps maps_batch, const __grid_co
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) {
+    __syncwarp();                       // lane 0 spent the kernel in the MMA loop: tcgen05.dealloc is .sync.aligned
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, kTmemCols);
   }
