@@ -109,9 +109,17 @@ def resnet18(**kw) -> ResNet:
     return ResNet(BasicBlock, [2, 2, 2, 2], **kw)
 
 
+def resnet34(**kw) -> ResNet:
+    return ResNet(BasicBlock, [3, 4, 6, 3], **kw)
+
+
 def resnet50(**kw) -> ResNet:
     return ResNet(Bottleneck, [3, 4, 6, 3], **kw)
 
 
 def resnet101(**kw) -> ResNet:
     return ResNet(Bottleneck, [3, 4, 23, 3], **kw)
+
+
+def resnet152(**kw) -> ResNet:
+    return ResNet(Bottleneck, [3, 8, 36, 3], **kw)

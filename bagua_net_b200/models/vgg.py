@@ -79,6 +79,14 @@ class VGG(nn.Module):
         return self.classifier(torch.flatten(x, 1))
 
 
+def vgg11(**kw) -> VGG:
+    return VGG("vgg11", **kw)
+
+
+def vgg13(**kw) -> VGG:
+    return VGG("vgg13", **kw)
+
+
 def vgg16(**kw) -> VGG:
     return VGG("vgg16", **kw)
 
