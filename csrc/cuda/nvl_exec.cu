@@ -369,6 +369,51 @@ __global__ void __launch_bounds__(kThreads, 1) bnet_nvl_oneshot_kernel(OneShotAr
   }
 }
 
+// ---- per-message kernel: the default behind NCCL's isend (BNET_EXEC_MODE=msg) --------------------------------
+// ONE launch moves a whole message: cluster c takes chunk c (the striping rule of the reference, applied to
+// clusters), the CTAs of a cluster split the chunk, and the LAST CTA of the grid to finish publishes completion —
+// to the sender (its request's completion word) and, when the mailbox is device-visible, straight to the
+// receiver (done[k] of the connection's mailbox), so the receiver's test() does not wait for the sender's proxy
+// thread to notice.  Nothing stays resident between messages: a device-wide synchronisation of the application
+// (cudaFree, cudaDeviceSynchronize) waits for at most the messages in flight, and a collective never depends on a
+// kernel that has to be told to leave.
+struct MsgArgs {
+  const char* src;
+  char* dst;
+  uint64_t nbytes;      // bytes of SOURCE
+  uint64_t chunk;       // source bytes per cluster (multiple of the op's unit)
+  uint64_t* flag;       // sender-side completion word (pinned host memory)
+  uint64_t flag_val;
+  uint64_t* flag2;      // optional receiver-side completion word (mailbox, pinned host memory)
+  uint64_t flag2_val;
+  uint32_t* counter;    // device memory, zero on entry, reset to zero by the last CTA
+  uint32_t op;
+  float scale;
+};
+__global__ void __launch_bounds__(kThreads, 1) bnet_nvl_msg_kernel(MsgArgs a) {
+  const uint32_t crank = ptx::cluster_ctarank();
+  const uint32_t csize = ptx::cluster_nctarank();
+  const uint32_t cid = blockIdx.x / csize;
+  if (a.op != OP_FLUSH) {
+    const size_t off = (size_t)cid * a.chunk;
+    const size_t n = off >= a.nbytes ? 0 : (a.nbytes - off < a.chunk ? a.nbytes - off : a.chunk);
+    size_t b0, b1;
+    cta_share(a.op, n, crank, csize, &b0, &b1);
+    process_range(a.op, a.src + off + b0, a.dst + dst_offset_for(a.op, off + b0), b1 - b0, threadIdx.x, kThreads, a.scale);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ptx::fence_acq_rel_sys();                       // this CTA's (peer) stores before its arrival
+    const uint32_t prev = atomicAdd(a.counter, 1u);
+    if (prev == gridDim.x - 1) {                    // every other CTA has arrived (and fenced) before us
+      *(volatile uint32_t*)a.counter = 0;           // ready for the next message that gets this counter
+      ptx::fence_acq_rel_sys();
+      if (a.flag2) ptx::st_release_sys_u64(a.flag2, a.flag2_val);
+      ptx::st_release_sys_u64(a.flag, a.flag_val);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ host side
 namespace {
 
@@ -391,10 +436,19 @@ const uint32_t* outstanding_dev() {
   return g_outstanding_dev;
 }
 
+// How a job reaches the GPU.  The transport (NCCL's isend) defaults to MODE_MSG: one launch per message and
+// nothing resident; the extension API (P2PExecutor, benchmarks) defaults to the persistent cluster queues.
+enum ExecMode : int { MODE_DEFAULT = -1, MODE_MSG = 0, MODE_PERSISTENT = 1, MODE_ONESHOT = 2, MODE_CE = 3 };
+constexpr int kMsgCounters = 4096;   // completion counters of per-message launches (ring; far more than in flight)
+
 struct Exec {
   int dev = -1;
   bool ok = false;
   bool persistent = true;
+  int transport_mode = MODE_MSG;   // what exec_copy()/exec_flush() use (behind NCCL)
+  int ext_mode = MODE_PERSISTENT;  // what bnet_exec_op() uses
+  uint32_t* counters = nullptr;    // device memory, kMsgCounters words, all zero between messages
+  uint64_t msg_seq = 0;
   bool tma = false;
   bool ce = false;             // BNET_COPY_ENGINE=ce: DMA copy engines + stream memory ops, no kernels at all
   int nclusters = 4;
@@ -418,6 +472,11 @@ struct Exec {
 
 std::mutex g_mu;
 Exec* g_exec[64] = {nullptr};
+
+const char* mode_name(int m) {
+  return m == MODE_MSG ? "per-message launch" : m == MODE_PERSISTENT ? "resident cluster kernels" : m == MODE_ONESHOT ? "launch per chunk"
+         : m == MODE_CE ? "copy engines" : "default";
+}
 
 template <typename K>
 cudaError_t launch_cluster(K kernel, int nblocks, int cluster, size_t smem, cudaStream_t st, void** args) {
@@ -453,6 +512,28 @@ Exec* get_exec(int dev) {
   e->persistent = env_int("PERSISTENT", 1) != 0;
   e->tma = env_str("COPY_ENGINE", "ldst") == "tma";
   e->ce = env_str("COPY_ENGINE", "ldst") == "ce" && driver().ok && driver().StreamWriteValue64 != nullptr;
+  {
+    // BNET_EXEC_MODE=msg|persistent|oneshot|ce picks the mode for BOTH users; the older knobs keep their meaning
+    // (BNET_PERSISTENT=0 -> one launch per chunk, =1 -> resident cluster kernels, BNET_COPY_ENGINE=ce -> DMA engines)
+    const std::string m = env_str("EXEC_MODE", "");
+    const std::string pers = env_str("PERSISTENT", "");
+    int forced = MODE_DEFAULT;
+    if (m == "msg") forced = MODE_MSG;
+    else if (m == "persistent") forced = MODE_PERSISTENT;
+    else if (m == "oneshot") forced = MODE_ONESHOT;
+    else if (m == "ce") forced = MODE_CE;
+    else if (!m.empty()) BNET_WARN("unknown BNET_EXEC_MODE '%s' (msg, persistent, oneshot or ce)", m.c_str());
+    if (forced == MODE_DEFAULT && e->ce) forced = MODE_CE;
+    if (forced == MODE_DEFAULT && !pers.empty()) forced = e->persistent ? MODE_PERSISTENT : MODE_ONESHOT;
+    if (forced == MODE_DEFAULT && env_int("EXEC_GRID", 0) != 0) forced = MODE_PERSISTENT;
+    if (forced == MODE_CE && !(driver().ok && driver().StreamWriteValue64 != nullptr)) {
+      BNET_WARN("copy-engine mode needs cuStreamWriteValue64; using per-message kernels");
+      forced = MODE_MSG;
+    }
+    if (forced != MODE_DEFAULT) e->transport_mode = e->ext_mode = forced;
+    e->ce = e->transport_mode == MODE_CE;
+    e->persistent = e->transport_mode == MODE_PERSISTENT || e->ext_mode == MODE_PERSISTENT;
+  }
   e->idle_ns = (uint64_t)env_int("KERNEL_IDLE_US", 1000) * 1000ull;
   e->arm_ns = (uint64_t)env_int("KERNEL_ARM_MS", 50) * 1000000ull;
   int cur = -1;
@@ -483,13 +564,31 @@ Exec* get_exec(int dev) {
     cudaFuncGetAttributes(&fa, bnet_nvl_stream_kernel<false>);
     cudaFuncGetAttributes(&fa, bnet_nvl_stream_kernel<true>);
     cudaFuncGetAttributes(&fa, bnet_nvl_oneshot_kernel);
+    cudaFuncGetAttributes(&fa, bnet_nvl_msg_kernel);
+    if (cudaMalloc((void**)&e->counters, kMsgCounters * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMemsetAsync(e->counters, 0, kMsgCounters * sizeof(uint32_t), e->streams[0].stream) != cudaSuccess) {
+      cudaGetLastError();
+      e->counters = nullptr;
+      good = false;
+    }
     void* wdp = nullptr;
-    uint64_t* wflag = (uint64_t*)host_alloc_mapped(64, &wdp);
+    uint64_t* wflag = good ? (uint64_t*)host_alloc_mapped(64, &wdp) : nullptr;
     if (wflag) {
       OneShotArgs a{nullptr, nullptr, 0, (uint64_t*)wdp, 1, OP_FLUSH, 1.0f};
       void* args[] = {&a};
       cudaError_t err = launch_cluster(bnet_nvl_oneshot_kernel, e->cluster_size, e->cluster_size, 0, e->streams[0].stream, args);
+      {
+        // the per-message kernel: load it, run it once (two clusters, fence only) and check its completion protocol
+        MsgArgs m{nullptr, nullptr, 0, 64, (uint64_t*)wdp + 1, 7, (uint64_t*)wdp + 2, 9, e->counters, OP_FLUSH, 1.0f};
+        void* margs[] = {&m};
+        cudaError_t e3 = launch_cluster(bnet_nvl_msg_kernel, 2 * e->cluster_size, e->cluster_size, 0, e->streams[0].stream, margs);
+        if (e3 == cudaSuccess) e3 = cudaStreamSynchronize(e->streams[0].stream);
+        if (e3 != cudaSuccess || ((volatile uint64_t*)wflag)[1] != 7 || ((volatile uint64_t*)wflag)[2] != 9) {
+          if (err == cudaSuccess) err = e3 != cudaSuccess ? e3 : cudaErrorUnknown;
+        }
+      }
       for (Stream& s : e->streams) {
+        if (!e->persistent) break;
         // persistent kernel: start it with stop already requested so it loads, runs and leaves
         __atomic_store_n(&s.q->stop, 1u, __ATOMIC_RELEASE);
         __atomic_store_n(&s.q->state, ST_RUNNING, __ATOMIC_RELEASE);
@@ -553,8 +652,8 @@ Exec* get_exec(int dev) {
   if (cur != dev && cur >= 0) cudaSetDevice(cur);
   if (!good) cudaGetLastError();
   e->ok = good;
-  BNET_INFO("nvl executor on dev %d: %d cluster(s) x %d CTA x %d thr, %s, engine=%s, min chunk %zu, idle %llu us",
-            dev, e->nclusters, e->cluster_size, kThreads, e->grid ? "persistent single grid" : e->persistent ? "persistent" : "one-shot",
+  BNET_INFO("nvl executor on dev %d: %d cluster(s) x %d CTA x %d thr, transport mode %s, engine=%s, min chunk %zu, idle %llu us",
+            dev, e->nclusters, e->cluster_size, kThreads, e->grid ? "persistent single grid" : mode_name(e->transport_mode),
             e->ce ? "copy-engine" : e->tma ? "tma" : "ld/st", e->min_chunk, (unsigned long long)(e->idle_ns / 1000));
   return good ? e : nullptr;
 }
@@ -618,26 +717,52 @@ int ensure_running(Exec* e, Stream& s, bool arm = false) {
   }
 }
 
-int submit(Exec* e, uint32_t op, const void* src, void* dst, size_t nbytes, uint64_t* flags_dev, uint64_t flag_value,
-           int* nchunks_out, float scale = 1.0f) {
+int submit(Exec* e, int mode, uint32_t op, const void* src, void* dst, size_t nbytes, uint64_t* flags_dev, uint64_t flag_value,
+           int* nchunks_out, float scale = 1.0f, uint64_t* flag2_dev = nullptr, uint64_t flag2_value = 0) {
   std::lock_guard<std::mutex> lk(e->mu);
   int cur = -1;
   cudaGetDevice(&cur);
   if (cur != e->dev) cudaSetDevice(e->dev);
+  if (mode == MODE_DEFAULT) mode = e->ext_mode;
+  if (mode == MODE_CE && op != OP_COPY) mode = MODE_MSG;            // fused ops need SMs
+  if (mode == MODE_PERSISTENT && !e->persistent) mode = MODE_MSG;   // resident kernels were not set up
   size_t unit = src_unit_for(op) < 64 ? 64 : src_unit_for(op);   // keep chunk cuts vector aligned on both sides
   // (copy-engine mode pays two driver calls per chunk: only split what is large enough to keep several engines busy)
-  const size_t min_chunk = (e->ce && op == OP_COPY && e->min_chunk < ((size_t)2 << 20)) ? ((size_t)2 << 20) : e->min_chunk;
+  const size_t min_chunk = (mode == MODE_CE && e->min_chunk < ((size_t)2 << 20)) ? ((size_t)2 << 20) : e->min_chunk;
   size_t cs = chunk_size(nbytes, min_chunk, (size_t)e->nclusters);
   cs = (cs + unit - 1) / unit * unit;
   int nchunks = nbytes ? (int)((nbytes + cs - 1) / cs) : 1;
   if (nchunks > kMaxChunksPerJob) nchunks = kMaxChunksPerJob;   // cannot happen: nclusters <= kMaxChunksPerJob
   int rc = 0;
+  if (mode == MODE_MSG) {
+    // one launch for the whole message: cluster c moves chunk c, the last CTA to finish signals.  The stream
+    // rotates per MESSAGE (the cursor persists, like the reference's stream cursor), so consecutive messages of
+    // one or several connections overlap on the device.
+    Stream& s = e->streams[e->rr];
+    e->rr = (e->rr + 1) % e->streams.size();
+    MsgArgs a{(const char*)src, (char*)dst, nbytes, cs, flags_dev, flag_value, flag2_dev, flag2_value,
+              e->counters + (e->msg_seq++ % kMsgCounters), op, scale};
+    void* args[] = {&a};
+    cudaError_t err = launch_cluster(bnet_nvl_msg_kernel, nchunks * e->cluster_size, e->cluster_size, 0, s.stream, args);
+    if (err != cudaSuccess) {
+      cudaGetLastError();
+      BNET_WARN("nvl executor: message launch failed: %s", cudaGetErrorString(err));
+      rc = -1;
+    }
+    e->stats.launches++;
+    e->stats.chunks += nchunks;
+    e->stats.jobs++;
+    e->stats.bytes += nbytes;
+    if (cur != e->dev && cur >= 0) cudaSetDevice(cur);
+    *nchunks_out = 1;   // one completion word per message
+    return rc;
+  }
   for (int c = 0; c < nchunks && rc == 0; c++) {
     size_t off = (size_t)c * cs;
     size_t n = nbytes ? (nbytes - off < cs ? nbytes - off : cs) : 0;
     Stream& s = e->streams[e->rr];
     e->rr = (e->rr + 1) % e->streams.size();
-    if (e->ce && op == OP_COPY) {
+    if (mode == MODE_CE) {
       // copy-engine mode: a DMA copy, then a stream-ordered 64-bit write of the completion word.  No SM is
       // used and nothing stays resident between messages; the price is two driver calls per chunk.
       // (driver-level unified-address copy: the destination is a VMM / IPC mapping of the peer's memory)
@@ -658,7 +783,7 @@ int submit(Exec* e, uint32_t op, const void* src, void* dst, size_t nbytes, uint
       e->stats.chunks++;
       continue;
     }
-    if (e->persistent) {
+    if (mode == MODE_PERSISTENT) {
       uint64_t t = s.q->tail;
       uint64_t spins = 0;
       while (t - __atomic_load_n(&s.q->head, __ATOMIC_ACQUIRE) >= (uint64_t)kQueueDepth) {
@@ -701,7 +826,7 @@ int submit(Exec* e, uint32_t op, const void* src, void* dst, size_t nbytes, uint
 }  // namespace
 
 int exec_copy(int dev, const void* src, void* dst, size_t nbytes, volatile uint64_t* flags_host, uint64_t* flags_dev,
-              uint64_t flag_value, int* nchunks) {
+              uint64_t flag_value, int* nchunks, uint64_t* flag2_dev, uint64_t flag2_value) {
   if (fake()) {   // CPU emulation: synchronous copy, same completion protocol
     memcpy(dst, src, nbytes);
     size_t cs = chunk_size(nbytes, (size_t)env_int("DEV_MIN_CHUNKSIZE", 262144), 4);
@@ -712,7 +837,7 @@ int exec_copy(int dev, const void* src, void* dst, size_t nbytes, volatile uint6
   }
   Exec* e = get_exec(dev);
   if (!e) return -1;
-  return submit(e, OP_COPY, src, dst, nbytes, flags_dev, flag_value, nchunks);
+  return submit(e, e->transport_mode, OP_COPY, src, dst, nbytes, flags_dev, flag_value, nchunks, 1.0f, flag2_dev, flag2_value);
 }
 
 int exec_flush(int dev, volatile uint64_t* flag_host, uint64_t* flag_dev, uint64_t flag_value) {
@@ -723,24 +848,35 @@ int exec_flush(int dev, volatile uint64_t* flag_host, uint64_t* flag_dev, uint64
   Exec* e = get_exec(dev);
   if (!e) return -1;
   int n = 0;
-  return submit(e, OP_FLUSH, nullptr, nullptr, 0, flag_dev, flag_value, &n);
+  return submit(e, e->transport_mode == MODE_CE ? MODE_MSG : e->transport_mode, OP_FLUSH, nullptr, nullptr, 0, flag_dev, flag_value, &n);
 }
 
 // Extension entry point: fused move+reduce / move+cast between registered buffers
 // (used by tests, bench/p2p_bw and the Python ops layer).
 extern "C" __attribute__((visibility("default"))) int bnet_exec_op(int dev, uint32_t op, const void* src, void* dst, size_t src_bytes,
                             volatile uint64_t* flags_host, uint64_t* flags_dev, uint64_t flag_value, int* nchunks) {
-  if (op == OP_COPY) return exec_copy(dev, src, dst, src_bytes, flags_host, flags_dev, flag_value, nchunks);
+  if (fake()) return exec_copy(dev, src, dst, src_bytes, flags_host, flags_dev, flag_value, nchunks);
   Exec* e = get_exec(dev);
   if (!e) return -1;
-  return submit(e, op, src, dst, src_bytes, flags_dev, flag_value, nchunks);
+  return submit(e, MODE_DEFAULT, op, src, dst, src_bytes, flags_dev, flag_value, nchunks);
 }
 
 extern "C" __attribute__((visibility("default"))) int bnet_exec_op_scaled(int dev, uint32_t op, const void* src, void* dst, size_t src_bytes,
                                    uint64_t* flags_dev, uint64_t flag_value, float scale, int* nchunks) {
   Exec* e = get_exec(dev);
   if (!e) return -1;
-  return submit(e, op, src, dst, src_bytes, flags_dev, flag_value, nchunks, scale);
+  return submit(e, MODE_DEFAULT, op, src, dst, src_bytes, flags_dev, flag_value, nchunks, scale);
+}
+
+int exec_op_mode(int dev, int mode, uint32_t op, const void* src, void* dst, size_t src_bytes, uint64_t* flags_dev,
+                 uint64_t flag_value, float scale, int* nchunks) {
+  Exec* e = get_exec(dev);
+  if (!e) return -1;
+  return submit(e, mode, op, src, dst, src_bytes, flags_dev, flag_value, nchunks, scale);
+}
+extern "C" __attribute__((visibility("default"))) int bnet_exec_op_mode(int dev, int mode, uint32_t op, const void* src, void* dst,
+                                 size_t src_bytes, uint64_t* flags_dev, uint64_t flag_value, float scale, int* nchunks) {
+  return exec_op_mode(dev, mode, op, src, dst, src_bytes, flags_dev, flag_value, scale, nchunks);
 }
 
 void exec_outstanding_add(int delta) {
@@ -751,7 +887,7 @@ int exec_prepare(int dev) {
   if (fake()) return 0;
   Exec* e = get_exec(dev);
   if (!e) return -1;
-  if (!e->persistent || e->arm_ns == 0 || e->ce) return 0;   // (copy-engine mode keeps nothing resident)
+  if (e->transport_mode != MODE_PERSISTENT || e->arm_ns == 0) return 0;   // only the resident-kernel mode has anything to arm
   // Arm: have the stream kernels resident BEFORE the first message so that the data path
   // needs no kernel launch (one that could be held up by a device-synchronising call
   // elsewhere in the process while the NCCL kernel it serves is already waiting).
@@ -776,7 +912,7 @@ void exec_dump() {
   for (Exec* e : g_exec) {
     if (!e || !e->ok) continue;
     fprintf(stderr, "[bnet watchdog] executor dev %d: %s%s%s, %d x %d CTAs, outstanding %u, jobs %llu chunks %llu launches %llu\n",
-            e->dev, e->grid ? "single grid" : e->persistent ? "persistent" : "one-shot", e->tma ? " tma" : "", e->ce ? " copy-engine" : "",
+            e->dev, e->grid ? "single grid" : mode_name(e->transport_mode), e->tma ? " tma" : "", e->ce ? " copy-engine" : "",
             e->nclusters, e->cluster_size, g_outstanding_host ? g_outstanding_host->load() : 0u,
             (unsigned long long)e->stats.jobs, (unsigned long long)e->stats.chunks, (unsigned long long)e->stats.launches);
     if (e->grid && e->ctl)

@@ -24,8 +24,14 @@ struct ExecStats {
 // flags_host/flags_dev: the same kMaxChunksPerJob words seen from host and device.
 // On return *nchunks words will eventually hold `flag_value`.
 // Returns 0 on success, <0 on failure (caller falls back to the bounce ring).
+// flag2_dev (optional): a second completion word the kernel publishes BEFORE the first — the receiver-visible
+// done[k] of the connection's mailbox — honoured by the per-message mode; callers must not rely on it.
 int exec_copy(int dev, const void* src, void* dst, size_t nbytes, volatile uint64_t* flags_host,
-              uint64_t* flags_dev, uint64_t flag_value, int* nchunks);
+              uint64_t* flags_dev, uint64_t flag_value, int* nchunks, uint64_t* flag2_dev = nullptr,
+              uint64_t flag2_value = 0);
+// extension entry point with an explicit mode (-1 default, 0 per-message launch, 1 resident queues, 2 launch per chunk, 3 copy engines)
+int exec_op_mode(int dev, int mode, uint32_t op, const void* src, void* dst, size_t src_bytes, uint64_t* flags_dev,
+                 uint64_t flag_value, float scale, int* nchunks);
 // Device-side fence used by iflush (K7): completes `flag` once prior peer stores are visible.
 int exec_flush(int dev, volatile uint64_t* flag_host, uint64_t* flag_dev, uint64_t flag_value);
 // Create streams / queues / pinned memory for `dev` now (setup phase) instead of at the first job.

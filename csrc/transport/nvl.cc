@@ -177,6 +177,7 @@ class NvlComm : public Comm {
     if (cuda::available()) {
       void* dp = nullptr;
       shm_registered_ = cuda::host_register(shm_, shm_bytes_, &dp) == 0;
+      if (shm_registered_) shm_dev_ = (char*)dp;
       if (k == SEND) {
         void* fdp = nullptr;
         flags_ = (uint64_t*)cuda::host_alloc_mapped(sizeof(uint64_t) * kSlots * cuda::kMaxChunksPerJob, &fdp);
@@ -620,7 +621,10 @@ class NvlComm : public Comm {
         if (dst) {
           uint64_t* fh = flags_ + (k % kSlots) * cuda::kMaxChunksPerJob;
           uint64_t* fd = flags_dev_ + (k % kSlots) * cuda::kMaxChunksPerJob;
-          direct = cuda::exec_copy(local_dev_, ksrc, dst, r->size, fh, fd, k + 1, &nchunks) == 0;
+          // the kernel itself publishes done[k] to the receiver when it can see the mailbox (one proxy hop less);
+          // the host repeats the store when it notices completion, which also covers the other executor modes
+          uint64_t* done_dev = shm_dev_ ? (uint64_t*)(shm_dev_ + ((char*)&shm_->done[k % kSlots].seq - (char*)shm_)) : nullptr;
+          direct = cuda::exec_copy(local_dev_, ksrc, dst, r->size, fh, fd, k + 1, &nchunks, done_dev, k + 1) == 0;
         }
         // large host -> host message: let the receiver pull it straight out of our buffer (one copy, none by us)
         const bool cma = !direct && !src_cuda && d.dst_type == NCCL_PTR_HOST && r->size >= cma_min_ && r->mh &&
@@ -799,6 +803,7 @@ class NvlComm : public Comm {
   uint32_t peer_pid_;
   int peer_dev_, local_dev_ = -1;
   bool shm_registered_ = false, uds_eof_ = false, cuda_live_ = false;
+  char* shm_dev_ = nullptr;     // device alias of the mailbox (kernels publish done[k] straight to the receiver)
   std::mutex mu_;
   std::deque<Request*> pending_;
   uint64_t seq_ = 0;
