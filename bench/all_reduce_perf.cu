@@ -64,9 +64,16 @@ __global__ void check_kernel(const T* p, size_t n, float expect, int* bad) {
     if (fabsf((float)p[i] - expect) > 1e-2f * fabsf(expect) + 1e-3f) atomicAdd(bad, 1);
 }
 
+static int g_hostid_per_rank = 0;
+
 template <typename T>
 static int run_rank(int rank, int nranks, Shared* sh, size_t minb, size_t maxb, double factor, int iters, int warm,
                     ncclDataType_t dt, const char* dtname, int check) {
+  if (g_hostid_per_rank) {   // -H: every rank claims to be its own host, so NCCL routes EVERYTHING through the net plugin
+    char hid[64];
+    snprintf(hid, sizeof(hid), "bnet-vhost-%d", rank);
+    setenv("NCCL_HOSTID", hid, 1);
+  }
   int ndev = 0;
   CUDACHECK(cudaGetDeviceCount(&ndev));
   CUDACHECK(cudaSetDevice(rank % ndev));
@@ -152,6 +159,7 @@ int main(int argc, char** argv) {
     else if (!strcmp(argv[i], "-g") && i + 1 < argc) ++i;   // accepted for nccl-tests compatibility (1 GPU per process)
     else if (!strcmp(argv[i], "-c") && i + 1 < argc) check = atoi(argv[++i]);
     else if (!strcmp(argv[i], "-d") && i + 1 < argc) dtype = argv[++i];
+    else if (!strcmp(argv[i], "-H")) g_hostid_per_rank = 1;
   }
   if (factor <= 1) factor = 2;
   if (nranks <= 0) {

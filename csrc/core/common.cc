@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <sys/syscall.h>
 #include <unistd.h>
 
 #include <fstream>
@@ -221,6 +222,74 @@ uint64_t host_hash() {
     return v ? v : 1;
   }();
   return h;
+}
+
+// ---- call breadcrumbs
+namespace {
+constexpr int kTraceThreads = 128, kTraceDepth = 4;
+struct TraceSlot {
+  std::atomic<uint32_t> claimed{0};
+  std::atomic<int> depth{0};
+  std::atomic<uint64_t> tid{0};
+  std::atomic<const char*> what[kTraceDepth];
+  std::atomic<uint64_t> since[kTraceDepth];
+};
+TraceSlot g_trace[kTraceThreads];
+int trace_slot() {
+  thread_local int slot = -2;
+  if (slot != -2) return slot;
+  slot = -1;
+  for (int i = 0; i < kTraceThreads; i++) {
+    uint32_t z = 0;
+    if (g_trace[i].claimed.compare_exchange_strong(z, 1)) {
+      g_trace[i].tid.store((uint64_t)syscall(SYS_gettid), std::memory_order_relaxed);
+      slot = i;
+      break;
+    }
+  }
+  return slot;   // (slots are never returned: threads that enter the plugin are few and long-lived)
+}
+}  // namespace
+
+CallScope::CallScope(const char* what) : slot_(trace_slot()), depth_(-1) {
+  if (slot_ < 0) return;
+  TraceSlot& t = g_trace[slot_];
+  int d = t.depth.load(std::memory_order_relaxed);
+  if (d < kTraceDepth) {
+    t.what[d].store(what, std::memory_order_relaxed);
+    t.since[d].store(now_ns(), std::memory_order_relaxed);
+    depth_ = d;
+  }
+  t.depth.store(d + 1, std::memory_order_release);
+}
+CallScope::~CallScope() {
+  if (slot_ < 0) return;
+  TraceSlot& t = g_trace[slot_];
+  t.depth.store(t.depth.load(std::memory_order_relaxed) - 1, std::memory_order_release);
+}
+int calltrace_dump(uint64_t older_than_ns) {
+  int n = 0;
+  uint64_t now = now_ns();
+  for (int i = 0; i < kTraceThreads; i++) {
+    TraceSlot& t = g_trace[i];
+    if (!t.claimed.load(std::memory_order_acquire)) continue;
+    int d = t.depth.load(std::memory_order_acquire);
+    if (d <= 0) continue;
+    if (d > kTraceDepth) d = kTraceDepth;
+    uint64_t t0 = t.since[0].load(std::memory_order_relaxed);
+    if (now - t0 < older_than_ns) continue;
+    char line[512];
+    int off = snprintf(line, sizeof(line), "[bnet watchdog] pid %d thread %llu inside the plugin:", (int)getpid(),
+                       (unsigned long long)t.tid.load(std::memory_order_relaxed));
+    for (int k = 0; k < d && off < (int)sizeof(line) - 64; k++) {
+      const char* w = t.what[k].load(std::memory_order_relaxed);
+      off += snprintf(line + off, sizeof(line) - off, " %s%s (%.1f ms)", k ? "> " : "", w ? w : "?",
+                      (now - t.since[k].load(std::memory_order_relaxed)) / 1e6);
+    }
+    fprintf(stderr, "%s\n", line);
+    n++;
+  }
+  return n;
 }
 
 uint64_t random_u64() {

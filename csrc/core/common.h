@@ -85,6 +85,18 @@ uint64_t fnv1a(const void* p, size_t n, uint64_t seed = 1469598103934665603ull);
 uint64_t host_hash();         // hostname + boot id; equal <=> same OS instance
 uint64_t random_u64();
 
+// ---- call breadcrumbs -----------------------------------------------------------
+// Where is every thread that is inside the plugin right now?  A CallScope costs two relaxed stores; the
+// watchdog prints the scopes that have been open for too long (a proxy thread stuck in a CUDA launch behind a
+// device-synchronising call of the application shows up here, not in any request state).
+struct CallScope {
+  explicit CallScope(const char* what);
+  ~CallScope();
+  int slot_, depth_;
+};
+// prints every open scope older than `older_than_ns` to stderr; returns how many it printed
+int calltrace_dump(uint64_t older_than_ns);
+
 // ---- chunking (reference: src/utils.rs:200-205) ---------------------------------
 inline size_t chunk_size(size_t total, size_t min_chunksize, size_t expected_nchunks) {
   if (expected_nchunks == 0) expected_nchunks = 1;

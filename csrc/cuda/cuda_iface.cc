@@ -200,6 +200,7 @@ void* host_device_alias(const void* host_ptr) {
 
 // ------------------------------------------------------------------ export / import
 int export_memory(const void* ptr, size_t size, MemExport* out) {
+  CallScope cs_("export memory");
   memset(out, 0, sizeof(*out));
   out->pid = (uint64_t)getpid();
   out->fd = -1;
@@ -293,6 +294,7 @@ static std::mutex g_import_mu;
 static std::map<ImportKey, ImportCookie*> g_imports;
 
 int import_memory(const MemExport& e, int local_fd, int dev, void** base_out, void** cookie_out) {
+  CallScope cs_("import peer memory");
   *base_out = nullptr;
   *cookie_out = nullptr;
   if (fake_mode()) {
@@ -493,6 +495,7 @@ void host_free_mapped(void* p) {
 
 // ------------------------------------------------------------------ staged copies
 int memcpy_sync(void* dst, const void* src, size_t n, int dev) {
+  CallScope cs_("staged cudaMemcpyAsync+sync");
   if (fake_mode()) {
     memcpy(dst, src, n);
     return 0;

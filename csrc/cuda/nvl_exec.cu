@@ -499,6 +499,8 @@ Exec* get_exec(int dev) {
   if (dev < 0 || dev >= 64) return nullptr;
   std::lock_guard<std::mutex> lk(g_mu);
   if (g_exec[dev]) return g_exec[dev]->ok ? g_exec[dev] : nullptr;
+  CallScope cs_("executor setup");
+  if (g_exec[dev]) return g_exec[dev]->ok ? g_exec[dev] : nullptr;
   Exec* e = new Exec();
   g_exec[dev] = e;
   e->dev = dev;
@@ -719,6 +721,7 @@ int ensure_running(Exec* e, Stream& s, bool arm = false) {
 
 int submit(Exec* e, int mode, uint32_t op, const void* src, void* dst, size_t nbytes, uint64_t* flags_dev, uint64_t flag_value,
            int* nchunks_out, float scale = 1.0f, uint64_t* flag2_dev = nullptr, uint64_t flag2_value = 0) {
+  CallScope cs_("exec submit");
   std::lock_guard<std::mutex> lk(e->mu);
   int cur = -1;
   cudaGetDevice(&cur);
@@ -743,7 +746,11 @@ int submit(Exec* e, int mode, uint32_t op, const void* src, void* dst, size_t nb
     MsgArgs a{(const char*)src, (char*)dst, nbytes, cs, flags_dev, flag_value, flag2_dev, flag2_value,
               e->counters + (e->msg_seq++ % kMsgCounters), op, scale};
     void* args[] = {&a};
-    cudaError_t err = launch_cluster(bnet_nvl_msg_kernel, nchunks * e->cluster_size, e->cluster_size, 0, s.stream, args);
+    cudaError_t err;
+    {
+      CallScope cl_("cudaLaunchKernelEx(msg)");
+      err = launch_cluster(bnet_nvl_msg_kernel, nchunks * e->cluster_size, e->cluster_size, 0, s.stream, args);
+    }
     if (err != cudaSuccess) {
       cudaGetLastError();
       BNET_WARN("nvl executor: message launch failed: %s", cudaGetErrorString(err));

@@ -11,6 +11,7 @@
 //     returning ncclInternalError (:145-149)
 //   * v5+ connect/accept never block on the peer: they return *comm == NULL
 //     until the connection is ready
+#include <stdlib.h>
 #include <string.h>
 
 #include "bnet/nccl_net_abi.h"
@@ -49,10 +50,33 @@ ncclResult_t fill_common(int dev, DeviceProps* p, char** name, char** pci) {
   return ncclSuccess;
 }
 
+// NCCL drives a net plugin through a proxy pipeline of NCCL_BUFFSIZE/8-byte slices per channel, and for small and
+// medium messages it prefers the LL protocol, whose buffers live in host memory (so they ride our shared-memory
+// ring, not NVLink).  Over this transport the measured optimum is the Simple protocol with large slices and many
+// channels (profiles/README.md section 4).  NCCL reads these variables after the plugin's init(), so a default can
+// be supplied here; anything the user has set wins, BNET_TUNE_NCCL=0 leaves the environment alone.
+void tune_nccl_env() {
+  if (env_int("TUNE_NCCL", 1) == 0) return;
+  const Config& cfg = Config::get();
+  if (!cfg.nvl || !cfg.gdr || !Engine::get().cuda_ok()) return;
+  struct KV { const char* k; const char* v; };
+  static const KV defaults[] = {
+      {"NCCL_PROTO", "Simple"},
+      {"NCCL_BUFFSIZE", "33554432"},
+      {"NCCL_MIN_NCHANNELS", "16"},
+  };
+  for (const KV& d : defaults)
+    if (!getenv(d.k)) {
+      setenv(d.k, d.v, 0);
+      BNET_INFO("init: %s=%s (transport default; set it yourself or BNET_TUNE_NCCL=0 to override)", d.k, d.v);
+    }
+}
+
 ncclResult_t do_init(ncclDebugLogger_t logfn) {
   if (logfn) log_set_nccl_logger(logfn);
   int st = Engine::get().init();
   if (st) BNET_WARN("init failed: %s", status_str(st));
+  else tune_nccl_env();
   return to_nccl(st);
 }
 
@@ -63,6 +87,7 @@ ncclResult_t do_devices(int* ndev) {
 }
 
 ncclResult_t do_listen(int dev, void* handle, size_t cap, void** lcomm) {
+  CallScope cs_("listen");
   ListenComm* l = nullptr;
   int st = Engine::get().listen(dev, handle, cap, &l);
   if (st) {
@@ -74,6 +99,7 @@ ncclResult_t do_listen(int dev, void* handle, size_t cap, void** lcomm) {
 }
 
 ncclResult_t do_connect(int dev, void* handle, void** scomm) {
+  CallScope cs_("connect");
   Comm* c = nullptr;
   int st = Engine::get().connect(dev, handle, &c);
   if (st) {
@@ -86,6 +112,7 @@ ncclResult_t do_connect(int dev, void* handle, void** scomm) {
 }
 
 ncclResult_t do_accept(void* lcomm, void** rcomm, bool blocking) {
+  CallScope cs_("accept");
   if (!lcomm) return ncclInvalidArgument;
   Comm* c = nullptr;
   int st = Engine::get().accept(static_cast<ListenComm*>(lcomm), &c, blocking);
@@ -99,6 +126,7 @@ ncclResult_t do_accept(void* lcomm, void** rcomm, bool blocking) {
 }
 
 ncclResult_t do_regmr(void* comm, void* data, size_t size, int type, void** mhandle) {
+  CallScope cs_("regMr");
   if (!comm || !mhandle) return ncclInvalidArgument;
   MemHandle* mh = nullptr;
   int st = static_cast<Comm*>(comm)->reg_mr(data, size, type, &mh);
@@ -111,12 +139,14 @@ ncclResult_t do_regmr(void* comm, void* data, size_t size, int type, void** mhan
 }
 
 ncclResult_t do_deregmr(void* comm, void* mhandle) {
+  CallScope cs_("deregMr");
   if (!comm) return ncclInvalidArgument;
   if (!mhandle) return ncclSuccess;
   return to_nccl(static_cast<Comm*>(comm)->dereg_mr(static_cast<MemHandle*>(mhandle)));
 }
 
 ncclResult_t do_isend(void* scomm, void* data, size_t size, int tag, void* mh, void** request) {
+  CallScope cs_("isend");
   if (!scomm || !request) return ncclInvalidArgument;
   Request* r = nullptr;
   int st = static_cast<Comm*>(scomm)->isend(data, size, tag, static_cast<MemHandle*>(mh), &r);
@@ -130,6 +160,7 @@ ncclResult_t do_isend(void* scomm, void* data, size_t size, int tag, void* mh, v
 }
 
 ncclResult_t do_irecv(void* rcomm, void* data, size_t size, int tag, void* mh, void** request) {
+  CallScope cs_("irecv");
   if (!rcomm || !request) return ncclInvalidArgument;
   Request* r = nullptr;
   int st = static_cast<Comm*>(rcomm)->irecv(data, size, tag, static_cast<MemHandle*>(mh), &r);
@@ -143,6 +174,7 @@ ncclResult_t do_irecv(void* rcomm, void* data, size_t size, int tag, void* mh, v
 }
 
 ncclResult_t do_iflush(void* rcomm, void* data, size_t size, void* mh, void** request) {
+  CallScope cs_("iflush");
   if (!rcomm || !request) return ncclInvalidArgument;
   Request* r = nullptr;
   int st = static_cast<Comm*>(rcomm)->iflush(data, size, static_cast<MemHandle*>(mh), &r);
@@ -152,6 +184,7 @@ ncclResult_t do_iflush(void* rcomm, void* data, size_t size, void* mh, void** re
 }
 
 ncclResult_t do_test(void* request, int* done, int* size) {
+  CallScope cs_("test");
   if (!request || !done) return ncclInvalidArgument;
   Request* r = static_cast<Request*>(request);
   size_t sz = 0;
@@ -166,6 +199,7 @@ ncclResult_t do_test(void* request, int* done, int* size) {
 }
 
 ncclResult_t do_close(void* comm) {
+  CallScope cs_("close");
   delete static_cast<Comm*>(comm);
   return ncclSuccess;
 }

@@ -826,22 +826,31 @@ std::mutex g_wd_mu;
 std::vector<NvlComm*> g_wd_comms;
 bool g_wd_started = false;
 
+// BNET_WATCHDOG_MS (default 20000, 0 = off): a request older than this gets its connection's state printed to
+// stderr, together with every thread that has been inside a plugin call for that long and the executor's state.
+// It only describes; failing a stuck request is BNET_TIMEOUT_MS's job.
 void watchdog_register(NvlComm* c) {
-  static const long long ms = env_int("WATCHDOG_MS", 0);
+  static const long long ms = env_int("WATCHDOG_MS", 20000);
   if (ms <= 0) return;
   std::lock_guard<std::mutex> lk(g_wd_mu);
   g_wd_comms.push_back(c);
   if (!g_wd_started) {
     g_wd_started = true;
     std::thread([] {
-      const uint64_t thr = (uint64_t)env_int("WATCHDOG_MS", 0) * 1000000ull;
-      for (int dumps = 0; dumps < 20;) {
-        usleep((useconds_t)(thr / 1000));
-        std::lock_guard<std::mutex> lk(g_wd_mu);
+      const uint64_t thr = (uint64_t)ms * 1000000ull;
+      for (int dumps = 0; dumps < 12;) {
+        usleep((useconds_t)(thr / 2000));
         bool stuck = false;
-        for (NvlComm* c : g_wd_comms) stuck |= c->dump_if_stuck(thr);
-        if (stuck && cuda::available() && !cuda::fake()) cuda::exec_dump();
-        dumps++;
+        {
+          std::lock_guard<std::mutex> lk(g_wd_mu);
+          for (NvlComm* c : g_wd_comms) stuck |= c->dump_if_stuck(thr);
+        }
+        if (calltrace_dump(thr) > 0) stuck = true;
+        if (stuck) {
+          if (cuda::available() && !cuda::fake()) cuda::exec_dump();
+          dumps++;
+          usleep((useconds_t)(thr / 1000));   // one report per period is enough
+        }
       }
     }).detach();
   }
