@@ -52,18 +52,20 @@ $(PLUGINX_OBJ): csrc/plugin/plugin.cc
 	@mkdir -p $(dir $@)
 	$(CXX) $(CXXFLAGS) -DBNET_EXPORT_V9_V10 -c $< -o $@
 
+# (link to a temporary name, then rename: a process that dlopen()s the library while another one is
+#  rebuilding it never sees a half-written file)
 $(PLUGIN_SO): $(HOST_OBJS) $(CU_OBJS) $(PLUGIN_OBJ)
 	@mkdir -p $(OUT)
-	$(NVCC) $(ARCH) $(LDFLAGS) -o $@ $^
+	$(NVCC) $(ARCH) $(LDFLAGS) -o $@.tmp $^ && mv -f $@.tmp $@
 
 # same engine, additionally exports the v9/v10 tables (select with NCCL_NET_PLUGIN=bnetx)
 $(PLUGINX_SO): $(HOST_OBJS) $(CU_OBJS) $(PLUGINX_OBJ)
 	@mkdir -p $(OUT)
-	$(NVCC) $(ARCH) $(LDFLAGS) -o $@ $^
+	$(NVCC) $(ARCH) $(LDFLAGS) -o $@.tmp $^ && mv -f $@.tmp $@
 
 # NCCL_NET_PLUGIN=bnet  ->  libnccl-net-bnet.so
 $(ALIAS_SO): $(PLUGIN_SO)
-	cp -f $< $@
+	cp -f $< $@.tmp && mv -f $@.tmp $@
 
 TEST_BINS := $(BUILD)/tests/unit_tests $(BUILD)/tests/loopback_test
 $(BUILD)/tests/%: csrc/tests/%.cc $(PLUGIN_SO)

@@ -30,6 +30,23 @@ def build_native(verbose: bool = False, jobs: int | None = None, force: bool = F
     so = os.path.join(LIB_DIR, LIB_NAME)
     if not force and not is_stale():
         return so
+    # One builder at a time across PROCESSES: under torchrun every rank of a fresh checkout gets here at once, and
+    # `make` in one build directory from several processes corrupts objects.  The others wait on the lock, then find
+    # the library up to date.  (make links to a temporary name and renames, so nobody dlopens a half-written file.)
+    import fcntl
+
+    os.makedirs(os.path.join(REPO_ROOT, "build"), exist_ok=True)
+    with open(os.path.join(REPO_ROOT, "build", ".build.lock"), "w") as lockf:
+        fcntl.flock(lockf, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():
+                return so
+            return _run_make(so, verbose, jobs)
+        finally:
+            fcntl.flock(lockf, fcntl.LOCK_UN)
+
+
+def _run_make(so: str, verbose: bool, jobs: int | None) -> str:
     jobs = jobs or min(16, os.cpu_count() or 4)
     cmd = ["make", "-C", REPO_ROOT, f"-j{jobs}"]
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)

@@ -194,8 +194,27 @@ class BnetDDP(torch.nn.Module):
         side = torch.cuda.Stream()
         side.wait_stream(cur)
         with torch.cuda.stream(side):               # warm-up on a side stream (cuDNN autotune, allocator)
+            # The warm-up runs REAL steps (the fused optimizer included: every rank has to take part in its
+            # barriers), so everything a step mutates is saved first and put back afterwards — parameters, fp32
+            # master weights, momentum, module buffers (BatchNorm running statistics).  A (re)capture therefore
+            # leaves the training trajectory exactly where eager mode would have it; checkpoint/resume stays
+            # step-exact.
+            saved = [self.flat_param.clone()] + [t.clone() for b in self.buckets for t in (b.master, b.mom)]
+            bufs = [t for t in self.module.buffers() if t.is_cuda and t.numel()]
+            saved_bufs = [t.clone() for t in bufs]
             for _ in range(2):
                 self._eager_step(self._gx, self._gy, loss_fn)
+            torch.cuda.current_stream().synchronize()
+            if self.comm.world > 1:
+                dist.barrier()                      # nobody restores while a peer's kernel still writes parameters
+            it = iter(saved)
+            self.flat_param.copy_(next(it))
+            for b in self.buckets:
+                b.master.copy_(next(it))
+                b.mom.copy_(next(it))
+            for t, s in zip(bufs, saved_bufs):
+                t.copy_(s)
+            del saved, saved_bufs
         cur.wait_stream(side)
         torch.cuda.synchronize()
         if self.comm.world > 1:
@@ -219,7 +238,9 @@ class BnetDDP(torch.nn.Module):
 
         # with the hyper-parameters in device memory (after the first set_lr) the captured step does not depend on them
         hpkey = "device" if getattr(self, "_hp", None) is not None else (self.lr, self.momentum, self.weight_decay)
-        key = (tuple(inputs.shape), inputs.dtype, tuple(targets.shape), targets.dtype, loss_fn, hpkey)
+        # (a lambda written inline is a new function object every call, but always the same code object)
+        fn_key = (getattr(loss_fn, "__code__", loss_fn), getattr(loss_fn, "__closure__", None) is None or id(loss_fn))
+        key = (tuple(inputs.shape), inputs.dtype, tuple(targets.shape), targets.dtype, fn_key, hpkey)
         if self._graph is None or self._graph_key != key:
             self._capture(inputs, targets, loss_fn, key)
         self._gx.copy_(inputs, non_blocking=True)

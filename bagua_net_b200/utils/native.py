@@ -22,7 +22,7 @@ def load(name: str = LIB_NAME) -> ctypes.CDLL:
         if not os.path.exists(path):
             from .._build import build_native
 
-            build_native()
+            build_native()      # takes an inter-process file lock: ranks of one job do not build concurrently
         lib = ctypes.CDLL(path, mode=ctypes.RTLD_GLOBAL)
         _declare(lib)
         _libs[name] = lib

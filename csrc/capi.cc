@@ -93,6 +93,18 @@ BNET_API int bnet_config_json(char* out, int cap) {
 BNET_API int bnet_metrics_text(char* out, int cap) { return copy_out(Telemetry::get().render_prometheus(), out, cap); }
 BNET_API int bnet_trace_json(char* out, int cap) { return copy_out(Telemetry::get().render_trace_json(), out, cap); }
 BNET_API int bnet_telemetry_flush() { return Telemetry::get().flush(); }
+// the collector wire formats, rendered from the beginning of the span ring (tests decode them)
+BNET_API int bnet_trace_jaeger_thrift(char* out, int cap) {
+  uint64_t cur = 0;
+  std::string b = Telemetry::get().render_jaeger_thrift(&cur);
+  if ((int)b.size() > cap) return -1;
+  memcpy(out, b.data(), b.size());
+  return (int)b.size();
+}
+BNET_API int bnet_trace_otlp_json(char* out, int cap) {
+  uint64_t cur = 0;
+  return copy_out(Telemetry::get().render_otlp_json(&cur), out, cap);
+}
 BNET_API int bnet_http_send(const char* method, const char* hostport, const char* path, const char* body,
                             const char* user, const char* pass) {
   return Telemetry::http_send(method, hostport, path, "text/plain", body ? body : "", user ? user : "", pass ? pass : "", 1000);

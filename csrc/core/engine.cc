@@ -173,7 +173,11 @@ int Engine::init() {
     p.max_recvs = 1;
     props_.push_back(p);
   }
-  Telemetry::get();  // start exporters
+  {
+    std::string names;   // root span attribute like the reference's `socket_devs` (nthread_…:132-137)
+    for (size_t i = 0; i < devs_.size(); i++) names += (i ? "," : "") + devs_[i].name;
+    Telemetry::get().set_root_attribute(names);   // (also starts the exporters)
+  }
   BNET_INFO("engine up: %zu device(s), implement=%s nstreams=%d min_chunksize=%zu nvl=%d cuda=%d",
             devs_.size(), cfg.implement.c_str(), cfg.nstreams, cfg.min_chunksize, cfg.nvl, (int)cuda_ok_);
   inited_ = true;

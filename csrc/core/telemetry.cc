@@ -42,9 +42,16 @@ struct Telemetry::Impl {
   std::mutex span_mu;
   std::vector<Span> open;     // indexed by id % kOpenSlots
   std::vector<Span> done;     // ring
-  size_t done_head = 0, done_count = 0, exported = 0;
+  size_t done_head = 0, done_count = 0;
+  uint64_t done_total = 0;            // spans ever finished (export cursors are positions in this sequence)
+  uint64_t sent_jaeger = 0, sent_otlp = 0;
   std::atomic<uint64_t> next_id{1};
   uint64_t root_id = 0;
+  std::string otlp_addr;
+  uint64_t trace_hi = 0, trace_lo = 0;   // 128-bit trace id of this plugin instance (one trace per process, like the
+  uint64_t span_salt = 0;                // reference's root span per BaguaNet instance, nthread_…:132-137)
+  int64_t epoch_off_ns = 0;              // realtime - now_ns() at start: span timestamps are exported in Unix time
+  std::string root_devs;                 // attribute "socket_devs" of the root span
   // push thread
   std::thread pusher;
   std::mutex mu;
@@ -70,6 +77,15 @@ Telemetry::Telemetry() : impl_(new Impl) {
   I.rank = cfg.rank;
   I.t_start = now_ns();
   I.jaeger_addr = env_str("JAEGER_ADDRESS", "");
+  I.otlp_addr = env_str("OTLP_ADDRESS", "");
+  {
+    timespec ts;
+    clock_gettime(CLOCK_REALTIME, &ts);
+    I.epoch_off_ns = (int64_t)ts.tv_sec * 1000000000ll + ts.tv_nsec - (int64_t)I.t_start;
+    I.trace_hi = random_u64();
+    I.trace_lo = random_u64() | 1;
+    I.span_salt = random_u64() & ~0xffffffffull;   // span ids: salt | per-process counter (never zero)
+  }
   I.prom_addr = env_str("PROMETHEUS_ADDRESS", "");
   I.trace_file = env_str("TRACE_FILE", "");
   I.metrics_file = env_str("METRICS_FILE", "");
@@ -78,14 +94,15 @@ Telemetry::Telemetry() : impl_(new Impl) {
   // reference gate: exporters only on ranks 0..7 (nthread_…:109-111); file sinks are always allowed
   bool rank_ok = I.rank >= 0 && I.rank <= 7;
   if (!rank_ok) I.jaeger_addr.clear();
-  tracing_ = !I.jaeger_addr.empty() || !I.trace_file.empty();
+  if (!rank_ok) I.otlp_addr.clear();
+  tracing_ = !I.jaeger_addr.empty() || !I.otlp_addr.empty() || !I.trace_file.empty();
   if (tracing_) {
     I.open.resize(kOpenSlots);
     I.done.resize(kDoneRing);
     I.root_id = span_begin(SPAN_ROOT, 0, 0, 0);
   }
   if (!I.prom_addr.empty() && !parse_user_pass_and_addr(I.prom_addr, &I.prom)) I.prom_addr.clear();
-  if (!I.prom_addr.empty() || !I.metrics_file.empty()) {
+  if (!I.prom_addr.empty() || !I.metrics_file.empty() || !I.jaeger_addr.empty() || !I.otlp_addr.empty()) {
     I.pusher = std::thread([this] {
       Impl& I = *impl_;
       std::unique_lock<std::mutex> lk(I.mu);
@@ -136,6 +153,7 @@ void Telemetry::span_end(uint64_t span_id, uint64_t nbytes) {
   I.done[(I.done_head + I.done_count) % kDoneRing] = s;
   if (I.done_count < kDoneRing) I.done_count++;
   else I.done_head = (I.done_head + 1) % kDoneRing;
+  I.done_total++;
   s.id = 0;
 }
 
@@ -225,6 +243,124 @@ std::string Telemetry::render_trace_json() const {
   return o.str();
 }
 
+
+// ---- trace export in the collectors' own wire formats -------------------------------------------------------
+// The reference ships its spans through opentelemetry-jaeger's collector pipeline: HTTP POST of a Thrift-binary
+// `jaeger.thrift` Batch to http://<addr>/api/traces (reference nthread_…:113-130).  That is what
+// BAGUA_NET_JAEGER_ADDRESS speaks here as well (hand-encoded TBinaryProtocol, no Thrift library needed);
+// BNET_OTLP_ADDRESS additionally speaks OTLP/HTTP JSON (POST /v1/traces), which current Jaeger and every
+// OpenTelemetry collector ingest.  Both export only the spans finished since the previous export.
+namespace {
+struct ThriftOut {
+  std::string b;
+  void u8(uint8_t v) { b.push_back((char)v); }
+  void i16(uint16_t v) { u8(v >> 8); u8(v & 0xff); }
+  void i32(uint32_t v) { for (int s = 24; s >= 0; s -= 8) u8((v >> s) & 0xff); }
+  void i64(uint64_t v) { for (int s = 56; s >= 0; s -= 8) u8((v >> s) & 0xff); }
+  void field(uint8_t type, uint16_t id) { u8(type); i16(id); }
+  void str(const std::string& v) { i32((uint32_t)v.size()); b += v; }
+  void stop() { u8(0); }
+};
+enum : uint8_t { T_BOOL = 2, T_DOUBLE = 4, T_I32 = 8, T_I64 = 10, T_STRING = 11, T_STRUCT = 12, T_LIST = 15 };
+void tag_str(ThriftOut& o, const char* k, const std::string& v) {
+  o.field(T_STRING, 1); o.str(k);
+  o.field(T_I32, 2); o.i32(0);        // TagType STRING
+  o.field(T_STRING, 3); o.str(v);
+  o.stop();
+}
+void tag_long(ThriftOut& o, const char* k, int64_t v) {
+  o.field(T_STRING, 1); o.str(k);
+  o.field(T_I32, 2); o.i32(3);        // TagType LONG
+  o.field(T_I64, 6); o.i64((uint64_t)v);
+  o.stop();
+}
+std::string hex(uint64_t v) {
+  char b[17];
+  snprintf(b, sizeof(b), "%016llx", (unsigned long long)v);
+  return b;
+}
+}  // namespace
+
+std::string Telemetry::span_display_name(int kind, uint64_t comm_id) const {
+  const Impl& I = *impl_;
+  std::string n = span_name((SpanKind)kind);
+  n += "-";
+  n += std::to_string(kind == SPAN_ROOT ? (uint64_t)(I.rank < 0 ? 0 : I.rank) : comm_id);
+  return n;
+}
+
+// jaeger.thrift Batch{1: Process{1: serviceName, 2: tags}, 2: list<Span>} of the spans finished after *cursor
+std::string Telemetry::render_jaeger_thrift(uint64_t* cursor) const {
+  Impl& I = *impl_;
+  std::lock_guard<std::mutex> lk(I.span_mu);
+  uint64_t first_kept = I.done_total - I.done_count;
+  uint64_t from = *cursor < first_kept ? first_kept : *cursor;
+  uint32_t n = (uint32_t)(I.done_total - from);
+  ThriftOut o;
+  o.field(T_STRUCT, 1);
+  o.field(T_STRING, 1); o.str("bagua-net");
+  o.field(T_LIST, 2); o.u8(T_STRUCT); o.i32(2);
+  tag_long(o, "rank", I.rank);
+  tag_str(o, "plugin", "bnet");
+  o.stop();
+  o.field(T_LIST, 2); o.u8(T_STRUCT); o.i32(n);
+  const uint64_t root_span = I.span_salt | (I.root_id & 0xffffffffull);
+  for (uint64_t k = from; k < I.done_total; k++) {
+    const Span& s = I.done[(I.done_head + (k - first_kept)) % kDoneRing];
+    o.field(T_I64, 1); o.i64(I.trace_lo);
+    o.field(T_I64, 2); o.i64(I.trace_hi);
+    o.field(T_I64, 3); o.i64(I.span_salt | (s.id & 0xffffffffull));
+    o.field(T_I64, 4); o.i64(s.kind == SPAN_ROOT ? 0 : root_span);
+    o.field(T_STRING, 5); o.str(span_display_name(s.kind, s.comm_id));
+    o.field(T_I32, 7); o.i32(1);   // sampled
+    o.field(T_I64, 8); o.i64((uint64_t)(((int64_t)s.t0 + I.epoch_off_ns) / 1000));
+    o.field(T_I64, 9); o.i64((s.t1 - s.t0) / 1000);
+    if (s.kind == SPAN_ROOT) {
+      o.field(T_LIST, 10); o.u8(T_STRUCT); o.i32(1);
+      tag_str(o, "socket_devs", I.root_devs);
+    } else {
+      o.field(T_LIST, 10); o.u8(T_STRUCT); o.i32(2);
+      tag_long(o, "id", (int64_t)s.req_id);
+      tag_long(o, "nbytes", (int64_t)s.nbytes);
+    }
+    o.stop();
+  }
+  o.stop();
+  *cursor = I.done_total;
+  return n ? o.b : std::string();
+}
+
+// OTLP/HTTP JSON ExportTraceServiceRequest of the spans finished after *cursor
+std::string Telemetry::render_otlp_json(uint64_t* cursor) const {
+  Impl& I = *impl_;
+  std::lock_guard<std::mutex> lk(I.span_mu);
+  uint64_t first_kept = I.done_total - I.done_count;
+  uint64_t from = *cursor < first_kept ? first_kept : *cursor;
+  if (from == I.done_total) { *cursor = I.done_total; return std::string(); }
+  const std::string trace_id = hex(I.trace_hi) + hex(I.trace_lo);
+  const uint64_t root_span = I.span_salt | (I.root_id & 0xffffffffull);
+  std::ostringstream o;
+  o << "{\"resourceSpans\":[{\"resource\":{\"attributes\":[{\"key\":\"service.name\",\"value\":{\"stringValue\":\"bagua-net\"}},"
+    << "{\"key\":\"rank\",\"value\":{\"intValue\":\"" << I.rank << "\"}}]},\"scopeSpans\":[{\"scope\":{\"name\":\"bnet\"},\"spans\":[";
+  bool first = true;
+  for (uint64_t k = from; k < I.done_total; k++) {
+    const Span& s = I.done[(I.done_head + (k - first_kept)) % kDoneRing];
+    if (!first) o << ",";
+    first = false;
+    o << "{\"traceId\":\"" << trace_id << "\",\"spanId\":\"" << hex(I.span_salt | (s.id & 0xffffffffull)) << "\"";
+    if (s.kind != SPAN_ROOT) o << ",\"parentSpanId\":\"" << hex(root_span) << "\"";
+    o << ",\"name\":\"" << span_display_name(s.kind, s.comm_id) << "\",\"kind\":" << (s.kind == SPAN_ISEND ? 4 : s.kind == SPAN_IRECV ? 5 : 1)
+      << ",\"startTimeUnixNano\":\"" << (int64_t)s.t0 + I.epoch_off_ns << "\",\"endTimeUnixNano\":\"" << (int64_t)s.t1 + I.epoch_off_ns
+      << "\",\"attributes\":[{\"key\":\"id\",\"value\":{\"intValue\":\"" << s.req_id << "\"}},{\"key\":\"nbytes\",\"value\":{\"intValue\":\""
+      << s.nbytes << "\"}}]}";
+  }
+  o << "]}]}]}";
+  *cursor = I.done_total;
+  return o.str();
+}
+
+void Telemetry::set_root_attribute(const std::string& socket_devs) { impl_->root_devs = socket_devs; }
+
 int Telemetry::http_send(const std::string& method, const std::string& hostport, const std::string& path,
                          const std::string& ctype, const std::string& body, const std::string& user,
                          const std::string& pass, int timeout_ms) {
@@ -282,8 +418,8 @@ int Telemetry::flush() {
     }
   }
   if (tracing_) {
-    std::string js = render_trace_json();
     if (!I.trace_file.empty()) {
+      std::string js = render_trace_json();
       FILE* f = fopen(I.trace_file.c_str(), "w");
       if (f) {
         fwrite(js.data(), 1, js.size(), f);
@@ -292,8 +428,24 @@ int Telemetry::flush() {
       }
     }
     if (!I.jaeger_addr.empty()) {
-      int st = http_send("POST", I.jaeger_addr, "/api/traces", "application/json", js, "", "", 500);
-      if (st >= 200 && st < 300) ok++;
+      uint64_t cur = I.sent_jaeger;
+      std::string batch = render_jaeger_thrift(&cur);
+      if (batch.empty()) {
+        I.sent_jaeger = cur;
+      } else {
+        int st = http_send("POST", I.jaeger_addr, "/api/traces?format=jaeger.thrift", "application/x-thrift", batch, "", "", 500);
+        if (st >= 200 && st < 300) { ok++; I.sent_jaeger = cur; }   // not accepted: the same spans go out again next time
+      }
+    }
+    if (!I.otlp_addr.empty()) {
+      uint64_t cur = I.sent_otlp;
+      std::string body = render_otlp_json(&cur);
+      if (body.empty()) {
+        I.sent_otlp = cur;
+      } else {
+        int st = http_send("POST", I.otlp_addr, "/v1/traces", "application/json", body, "", "", 500);
+        if (st >= 200 && st < 300) { ok++; I.sent_otlp = cur; }
+      }
     }
   }
   return ok;

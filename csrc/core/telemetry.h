@@ -13,6 +13,9 @@
 // Re-designed: lock-free counters, a bounded span ring, a >=100 ms push period
 // (the reference pushes every 200 us), file sinks for boxes without network
 // (BNET_TRACE_FILE = Chrome trace JSON, BNET_METRICS_FILE = text exposition).
+// Trace wire formats: BAGUA_NET_JAEGER_ADDRESS -> Jaeger collector, Thrift-binary jaeger.thrift Batch POSTed to
+// /api/traces (what the reference's opentelemetry-jaeger pipeline sends); BNET_OTLP_ADDRESS -> OTLP/HTTP JSON
+// POSTed to /v1/traces.
 #pragma once
 #include <atomic>
 #include <cstdint>
@@ -63,7 +66,12 @@ class Telemetry {
   void on_chunk_recv(uint64_t nbytes);
 
   std::string render_prometheus() const;   // text exposition
-  std::string render_trace_json() const;   // Chrome trace-event JSON of finished spans
+  std::string render_trace_json() const;   // Chrome trace-event JSON of finished spans (BNET_TRACE_FILE)
+  // collector wire formats; *cursor = how many finished spans the caller has exported already (advanced on return)
+  std::string render_jaeger_thrift(uint64_t* cursor) const;   // jaeger.thrift Batch, TBinaryProtocol
+  std::string render_otlp_json(uint64_t* cursor) const;       // OTLP/HTTP JSON ExportTraceServiceRequest
+  void set_root_attribute(const std::string& socket_devs);    // attribute of the root span (reference nthread_…:132-137)
+  std::string span_display_name(int kind, uint64_t comm_id) const;
   int flush();                              // write files / push now; returns #sinks that succeeded
   void shutdown();                          // stop push thread, final flush
 

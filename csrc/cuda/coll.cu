@@ -443,10 +443,17 @@ __global__ void __launch_bounds__(kThreads, 2) bnet_fused_sgd_kernel(CollDev d, 
   for (; i < per; i += stride)
     fused_sgd_batch<DT, MODE, 1>(d, goff, poff, start, i, stride, lr, mu, wd, gscale, master, mom);
   if constexpr (MODE != 0) rank_barrier(d, chan);
-  if (zero_grads) {   // every peer has finished reading our gradients: reset them for the next backward
+  if (zero_grads) {
+    // Reset our gradients for the next backward.  The barrier above only pairs CTA b with CTA b of the peers (CTAs
+    // of a grid start staggered when the kernel runs under backward on the side stream), so CTA b may only zero
+    // what CTA b of some rank has READ: shard p, vectors p*per + i for exactly the i this CTA walks above.  Zeroing
+    // with a flat index would hand vectors of shard p >= 1 to a different CTA than the one rank p reads them with.
     int4* gz = reinterpret_cast<int4*>(d.heap[d.rank] + goff);
     const int4 z = make_int4(0, 0, 0, 0);
-    for (size_t j = (size_t)blockIdx.x * kThreads + threadIdx.x; j < nvec; j += stride) ptx::st_na_v4(gz + j, z);
+    for (int p = 0; p < d.world; p++)
+      for (size_t j = (size_t)blockIdx.x * kThreads + threadIdx.x; j < per; j += stride) ptx::st_na_v4(gz + (size_t)p * per + j, z);
+    // vectors beyond per*world are read by nobody
+    for (size_t j = per * d.world + (size_t)blockIdx.x * kThreads + threadIdx.x; j < nvec; j += stride) ptx::st_na_v4(gz + j, z);
   }
 }
 

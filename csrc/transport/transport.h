@@ -93,7 +93,13 @@ struct Request {
   bool nvtx_open = false;
   uint64_t u[6] = {0, 0, 0, 0, 0, 0};   // transport scratch
 
-  bool complete() const { return ndone.load(std::memory_order_acquire) == nsub.load(std::memory_order_acquire); }
+  // ndone FIRST, nsub second (two sequenced statements): a dispatcher may still be announcing sub-tasks while
+  // workers complete them; reading nsub first could pair a stale nsub with a later ndone and report "done" early
+  bool complete() const {
+    const uint32_t d = ndone.load(std::memory_order_acquire);
+    const uint32_t n = nsub.load(std::memory_order_acquire);
+    return d == n;
+  }
   void fail(int st) {
     int z = 0;
     err.compare_exchange_strong(z, st);

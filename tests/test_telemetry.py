@@ -15,8 +15,9 @@ class _Sink(http.server.BaseHTTPRequestHandler):
 
     def _take(self):
         n = int(self.headers.get("Content-Length", "0"))
-        body = self.rfile.read(n).decode()
-        _Sink.hits.append((self.command, self.path, self.headers.get("Authorization"), body))
+        raw = self.rfile.read(n)
+        body = raw if self.headers.get("Content-Type") == "application/x-thrift" else raw.decode()
+        _Sink.hits.append((self.command, self.path, self.headers.get("Authorization"), body, self.headers.get("Content-Type")))
         self.send_response(200)
         self.send_header("Content-Length", "0")
         self.end_headers()
@@ -25,6 +26,81 @@ class _Sink(http.server.BaseHTTPRequestHandler):
 
     def log_message(self, *a):
         pass
+
+
+# ---- a minimal TBinaryProtocol reader: enough to check a jaeger.thrift Batch against its schema -------------
+import struct  # noqa: E402
+
+T_BOOL, T_BYTE, T_DOUBLE, T_I16, T_I32, T_I64, T_STRING, T_STRUCT, T_LIST = 2, 3, 4, 6, 8, 10, 11, 12, 15
+
+
+class _Thrift:
+    def __init__(self, data: bytes):
+        self.d, self.p = data, 0
+
+    def take(self, fmt):
+        v = struct.unpack_from(">" + fmt, self.d, self.p)
+        self.p += struct.calcsize(">" + fmt)
+        return v[0]
+
+    def value(self, t):
+        if t == T_BOOL or t == T_BYTE:
+            return self.take("b")
+        if t == T_DOUBLE:
+            return self.take("d")
+        if t == T_I16:
+            return self.take("h")
+        if t == T_I32:
+            return self.take("i")
+        if t == T_I64:
+            return self.take("q")
+        if t == T_STRING:
+            n = self.take("i")
+            v = self.d[self.p:self.p + n]
+            self.p += n
+            return v.decode()
+        if t == T_STRUCT:
+            return self.struct()
+        if t == T_LIST:
+            et, n = self.take("b"), self.take("i")
+            return [self.value(et) for _ in range(n)]
+        raise AssertionError(f"unexpected thrift type {t}")
+
+    def struct(self):
+        out = {}
+        while True:
+            t = self.take("b")
+            if t == 0:
+                return out
+            fid = self.take("h")
+            out[fid] = (t, self.value(t))
+
+
+def _check_jaeger_batch(raw: bytes):
+    """jaeger.thrift: Batch{1: Process{1: serviceName, 2: list<Tag>}, 2: list<Span>};
+    Span{1,2: traceId low/high i64, 3: spanId, 4: parentSpanId, 5: operationName, 7: flags i32, 8: startTime us, 9: duration us,
+    10: list<Tag>}; Tag{1: key, 2: vType i32, 3: vStr | 6: vLong}."""
+    rd = _Thrift(raw)
+    batch = rd.struct()
+    assert rd.p == len(raw), "trailing bytes after the Batch"
+    assert batch[1][0] == T_STRUCT and batch[2][0] == T_LIST
+    proc = batch[1][1]
+    assert proc[1] == (T_STRING, "bagua-net")
+    spans = batch[2][1]
+    assert spans
+    names = []
+    for sp in spans:
+        for fid, ty in ((1, T_I64), (2, T_I64), (3, T_I64), (4, T_I64), (5, T_STRING), (7, T_I32), (8, T_I64), (9, T_I64)):
+            assert sp[fid][0] == ty, (fid, sp[fid])
+        assert sp[3][1] != 0 and sp[9][1] >= 0
+        assert sp[8][1] > 1_600_000_000_000_000, "startTime must be microseconds since the Unix epoch"
+        tags = {t[1][1]: t for t in sp[10][1]}
+        for t in tags.values():
+            assert t[2][0] == T_I32 and ((t[2][1] == 0 and 3 in t) or (t[2][1] == 3 and 6 in t))
+        names.append((sp[5][1], sp[3][1]))
+        if not sp[5][1].startswith("BaguaNet-"):
+            assert {"id", "nbytes"} <= set(tags) and sp[4][1] != 0     # children point at the root span
+    return names
 
 
 def _server():
@@ -70,8 +146,15 @@ def test_pushgateway_push_with_basic_auth_and_jaeger_gate():
     assert all(p[1] == "/metrics/job/BaguaNet/rank/3" for p in puts)       # job + rank label like the reference
     assert puts[0][2] == "Basic " + base64.b64encode(b"alice:s3cret").decode()
     assert "isend_nbytes_bucket" in puts[-1][3]
-    posts = [h for h in _Sink.hits if h[0] == "POST" and h[1] == "/api/traces"]
-    assert posts and "traceEvents" in posts[-1][3]
+    # the Jaeger collector endpoint gets a Thrift-binary jaeger.thrift Batch, like the reference's
+    # opentelemetry-jaeger pipeline sends (nthread_…:113-130)
+    posts = [h for h in _Sink.hits if h[0] == "POST" and h[1].startswith("/api/traces")]
+    assert posts and all(h[4] == "application/x-thrift" for h in posts)
+    pairs = [n for h in posts for n in _check_jaeger_batch(h[3])]
+    names = [n for n, _ in pairs]
+    kids = [pr for pr in pairs if pr[0].startswith(("isend-", "irecv-"))]
+    assert len(kids) == 32 and len(set(kids)) == 32       # 16 sends + 16 receives, every span exported exactly once
+    assert any(n == "BaguaNet-3" for n in names)          # root span, exported at shutdown
 
     # ranks outside 0..7 do not export traces (reference gate: nthread_…:109-111)
     srv, port = _server()
@@ -107,3 +190,32 @@ def test_metrics_counters_in_process():
     p.close_send(s), p.close_recv(r), p.close_listen(l)
     os.environ.pop("BNET_NVL")
     utils.reload_config()
+
+
+def test_otlp_http_json_export():
+    """BNET_OTLP_ADDRESS: OTLP/HTTP JSON to /v1/traces (what OpenTelemetry collectors and current Jaeger ingest)."""
+    srv, port = _server()
+    try:
+        env = {"BNET_NVL": "0", "RANK": "0", "BNET_OTLP_ADDRESS": f"127.0.0.1:{port}", "BNET_METRICS_INTERVAL_MS": "100"}
+        outs = run_pair(["--sizes", "4096,70000", "--inflight", "2", "--rounds", "2"], env=env)
+        assert all(rc == 0 and res["ok"] for rc, res, _ in outs)
+    finally:
+        srv.shutdown()
+    posts = [h for h in _Sink.hits if h[0] == "POST" and h[1] == "/v1/traces"]
+    assert posts
+    spans = []
+    for h in posts:
+        doc = json.loads(h[3])
+        for rs in doc["resourceSpans"]:
+            attrs = {a["key"]: a["value"] for a in rs["resource"]["attributes"]}
+            assert attrs["service.name"] == {"stringValue": "bagua-net"}
+            for ss in rs["scopeSpans"]:
+                spans += ss["spans"]
+    assert spans
+    for sp in spans:
+        assert len(sp["traceId"]) == 32 and len(sp["spanId"]) == 16 and int(sp["traceId"], 16) and int(sp["spanId"], 16)
+        assert int(sp["endTimeUnixNano"]) >= int(sp["startTimeUnixNano"]) > 1_600_000_000_000_000_000
+        assert {a["key"] for a in sp["attributes"]} >= {"id", "nbytes"}
+    kids = [sp for sp in spans if sp["name"].startswith(("isend-", "irecv-"))]
+    assert len(kids) == 16 and all(len(sp["parentSpanId"]) == 16 for sp in kids)     # 8 sends + 8 receives
+    assert len({(sp["traceId"], sp["spanId"]) for sp in kids}) == 16                   # every span exactly once
