@@ -149,6 +149,18 @@ _TABLES = {3: NetV4, 4: NetV4, 5: None, 6: NetV6, 8: NetV8, 10: NetV10}
 _PROPS = {3: PropsV4, 4: PropsV4, 6: PropsV6, 8: PropsV8, 10: PropsV9}
 
 
+# ncclProfilerCallback_t(void** eHandle, int type, void* pHandle, int64_t pluginId, void* extData)
+PROFILER_CB = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int64, C.c_void_p)
+
+
+class ProfilerEventDescr(C.Structure):   # include/bnet/bnet_profiler.h: bnetProfilerEventDescr_v1_t
+    _fields_ = [("type", C.c_uint8), ("path", C.c_uint8), ("reserved", C.c_uint16), ("tag", C.c_int32),
+                ("comm_id", C.c_uint64), ("request_id", C.c_uint64), ("length", C.c_size_t)]
+
+
+BNET_PROFILER_PLUGIN_ID = (0x42 << 16) | 1
+
+
 class PluginError(RuntimeError):
     def __init__(self, what: str, code: int):
         super().__init__(f"{what} -> ncclResult {code}")
@@ -170,9 +182,11 @@ class NetPlugin:
         if rc != ncclSuccess:
             raise PluginError(what, rc)
 
-    def init(self):
+    def init(self, profiler=None):
+        """profiler (v10 only): a PROFILER_CB(...) object — NCCL's ncclProfilerCallback_t — kept alive by the caller."""
         if self.version >= 10:
-            self._chk("init", self.tab.init(None, None))
+            self._prof = profiler
+            self._chk("init", self.tab.init(None, C.cast(profiler, C.c_void_p) if profiler is not None else None))
         else:
             self._chk("init", self.tab.init(None))
 
@@ -240,10 +254,10 @@ class NetPlugin:
     def dereg_mr(self, comm, mh):
         self._chk("deregMr", self.tab.deregMr(comm, mh))
 
-    def isend(self, comm, addr: int, size: int, mh=None, tag: int = 0):
+    def isend(self, comm, addr: int, size: int, mh=None, tag: int = 0, phandle: int | None = None):
         req = C.c_void_p()
         if self.version >= 10:
-            rc = self.tab.isend(comm, C.c_void_p(addr), size, tag, mh, None, C.byref(req))
+            rc = self.tab.isend(comm, C.c_void_p(addr), size, tag, mh, C.c_void_p(phandle) if phandle else None, C.byref(req))
         elif self.version >= 5:
             rc = self.tab.isend(comm, C.c_void_p(addr), size, tag, mh, C.byref(req))
         else:
@@ -251,7 +265,7 @@ class NetPlugin:
         self._chk("isend", rc)
         return req if req.value else None
 
-    def irecv(self, comm, addr: int, size: int, mh=None, tag: int = 0):
+    def irecv(self, comm, addr: int, size: int, mh=None, tag: int = 0, phandle: int | None = None):
         req = C.c_void_p()
         if self.version >= 5:
             data = (C.c_void_p * 1)(addr)
@@ -259,7 +273,8 @@ class NetPlugin:
             mhs = (C.c_void_p * 1)(mh.value if mh is not None and mh.value else None)
             if self.version >= 10:
                 sizes = (C.c_size_t * 1)(size)
-                rc = self.tab.irecv(comm, 1, data, sizes, tags, mhs, None, C.byref(req))
+                phs = (C.c_void_p * 1)(phandle) if phandle else None
+                rc = self.tab.irecv(comm, 1, data, sizes, tags, mhs, phs, C.byref(req))
             else:
                 sizes = (C.c_int * 1)(size)
                 rc = self.tab.irecv(comm, 1, data, sizes, tags, mhs, C.byref(req))

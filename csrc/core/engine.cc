@@ -8,10 +8,45 @@
 
 #include <nvtx3/nvToolsExt.h>
 
+#include "bnet/bnet_profiler.h"
 #include "core/telemetry.h"
 #include "cuda/cuda_iface.h"
 
 namespace bnet {
+
+// ------------------------------------------------------------------ NCCL profiler hook (ncclNet v10)
+static std::atomic<ncclProfilerCallback_t> g_prof_fn{nullptr};
+
+void profiler_set_callback(ncclProfilerCallback_t fn) { g_prof_fn.store(fn, std::memory_order_release); }
+
+static void prof_fill(const Request* r, bnetProfilerEventDescr_v1_t* d, bool stop) {
+  memset(d, 0, sizeof(*d));
+  d->type = r->kind == REQ_SEND ? BNET_PROF_ISEND : BNET_PROF_IRECV;
+  d->path = stop ? r->prof_path : 0;
+  d->tag = r->tag;
+  d->comm_id = r->comm ? r->comm->id : 0;
+  d->request_id = r->id;
+  d->length = stop ? (size_t)r->nbytes.load(std::memory_order_relaxed) : r->size;
+}
+
+void profiler_start(Request* r, void* parent_handle) {
+  ncclProfilerCallback_t fn = g_prof_fn.load(std::memory_order_acquire);
+  if (!fn || !parent_handle || !r || r->kind == REQ_FLUSH) return;
+  bnetProfilerEventDescr_v1_t d;
+  prof_fill(r, &d, false);
+  void* eh = nullptr;
+  if (fn(&eh, 0 /* start */, parent_handle, BNET_PROFILER_PLUGIN_ID, &d) == ncclSuccess) r->prof_event = eh;
+}
+
+void profiler_stop(Request* r) {
+  ncclProfilerCallback_t fn = g_prof_fn.load(std::memory_order_acquire);
+  if (!fn || !r->prof_event) return;
+  bnetProfilerEventDescr_v1_t d;
+  prof_fill(r, &d, true);
+  void* eh = r->prof_event;
+  r->prof_event = nullptr;
+  fn(&eh, 1 /* stop */, nullptr, BNET_PROFILER_PLUGIN_ID, &d);
+}
 
 // ------------------------------------------------------------------ Comm base
 static std::atomic<uint64_t> g_comm_ids{1};
@@ -73,6 +108,8 @@ Request* Comm::alloc_req(ReqKind k, void* buf, size_t size, int tag, MemHandle* 
       r.mh = mh;
       r.id = rid;
       r.t_post = now_ns();
+      r.prof_event = nullptr;
+      r.prof_path = 0;
       memset(r.u, 0, sizeof(r.u));
       if (nvtx_on() && k != REQ_FLUSH) {
         char nm[64];
@@ -93,6 +130,7 @@ Request* Comm::alloc_req(ReqKind k, void* buf, size_t size, int tag, MemHandle* 
 
 void Comm::free_req(Request* r) {
   Telemetry& T = Telemetry::get();
+  if (r->prof_event) profiler_stop(r);
   if (r->nvtx_open) {
     nvtxRangeEnd(r->nvtx);
     r->nvtx_open = false;

@@ -59,6 +59,11 @@ class ListenComm : public Comm {
   std::mutex mu;
 };
 
+// ncclNet v10: events of this plugin inside NCCL's profiler (include/bnet/bnet_profiler.h)
+void profiler_set_callback(ncclProfilerCallback_t fn);
+void profiler_start(Request* r, void* parent_handle);   // no-op without a callback or a parent handle
+void profiler_stop(Request* r);
+
 class Engine {
  public:
   static Engine& get();

@@ -316,7 +316,11 @@ ncclResult_t v6_regmr_dmabuf(void* c, void* d, size_t size, int type, uint64_t, 
 }
 ncclResult_t v6_isend(void* c, void* d, int size, int tag, void* mh, void** req) { return do_isend(c, d, (size_t)size, tag, mh, req); }
 ncclResult_t v9_isend(void* c, void* d, size_t size, int tag, void* mh, void** req) { return do_isend(c, d, size, tag, mh, req); }
-ncclResult_t v10_isend(void* c, void* d, size_t size, int tag, void* mh, void*, void** req) { return do_isend(c, d, size, tag, mh, req); }
+ncclResult_t v10_isend(void* c, void* d, size_t size, int tag, void* mh, void* ph, void** req) {
+  ncclResult_t r = do_isend(c, d, size, tag, mh, req);
+  if (r == ncclSuccess && *req && ph) profiler_start(static_cast<Request*>(*req), ph);
+  return r;
+}
 ncclResult_t v6_irecv(void* c, int n, void** data, int* sizes, int* tags, void** mhs, void** req) {
   if (n != 1) return ncclInvalidUsage;   // maxRecvs = 1
   return do_irecv(c, data[0], (size_t)sizes[0], tags ? tags[0] : 0, mhs ? mhs[0] : nullptr, req);
@@ -325,8 +329,10 @@ ncclResult_t v9_irecv(void* c, int n, void** data, size_t* sizes, int* tags, voi
   if (n != 1) return ncclInvalidUsage;
   return do_irecv(c, data[0], sizes[0], tags ? tags[0] : 0, mhs ? mhs[0] : nullptr, req);
 }
-ncclResult_t v10_irecv(void* c, int n, void** data, size_t* sizes, int* tags, void** mhs, void**, void** req) {
-  return v9_irecv(c, n, data, sizes, tags, mhs, req);
+ncclResult_t v10_irecv(void* c, int n, void** data, size_t* sizes, int* tags, void** mhs, void** phs, void** req) {
+  ncclResult_t r = v9_irecv(c, n, data, sizes, tags, mhs, req);
+  if (r == ncclSuccess && *req && phs && phs[0]) profiler_start(static_cast<Request*>(*req), phs[0]);
+  return r;
 }
 ncclResult_t v6_iflush(void* c, int n, void** data, int* sizes, void** mhs, void** req) {
   if (n != 1) return ncclInvalidUsage;
@@ -334,7 +340,10 @@ ncclResult_t v6_iflush(void* c, int n, void** data, int* sizes, void** mhs, void
 }
 ncclResult_t v7_get_device_mr(void*, void*, void**) { return ncclInternalError; }
 ncclResult_t v7_irecv_consumed(void*, int, void*) { return ncclSuccess; }
-ncclResult_t v10_init(ncclDebugLogger_t f, ncclProfilerCallback_t) { return do_init(f); }
+ncclResult_t v10_init(ncclDebugLogger_t f, ncclProfilerCallback_t prof) {
+  profiler_set_callback(prof);   // events of ours inside NCCL's profiler: include/bnet/bnet_profiler.h
+  return do_init(f);
+}
 
 }  // namespace
 

@@ -631,6 +631,7 @@ class NvlComm : public Comm {
                          r->mh->cma == 1 && shm_->cma_state.load(std::memory_order_acquire) == 1;
         a.nbytes = r->size;
         a.via_ring = direct ? PATH_DIRECT : cma ? PATH_CMA : PATH_RING;
+        r->prof_path = direct ? 3 : cma ? 2 : 1;   // BNET_PROF_PATH_* (include/bnet/bnet_profiler.h)
         a.src_addr = (uint64_t)r->buf;
         a.err = 0;
         a.seq.store(k + 1, std::memory_order_release);
@@ -725,6 +726,7 @@ class NvlComm : public Comm {
           continue;
         }
         r->u[4] = a.nbytes;
+        r->prof_path = a.via_ring == PATH_RING ? 1 : a.via_ring == PATH_CMA ? 2 : 3;
         r->u[1] = a.via_ring == PATH_RING ? 1 : a.via_ring == PATH_CMA ? 4 : 2;
         r->u[2] = 0;
         r->u[5] = a.src_addr;

@@ -91,6 +91,8 @@ struct Request {
   uint64_t t_post = 0;
   uint64_t nvtx = 0;
   bool nvtx_open = false;
+  void* prof_event = nullptr;   // event opened in NCCL's profiler (ncclNet v10), closed when test() reports done
+  uint8_t prof_path = 0;        // BNET_PROF_PATH_* for the stop record
   uint64_t u[6] = {0, 0, 0, 0, 0, 0};   // transport scratch
 
   // ndone FIRST, nsub second (two sequenced statements): a dispatcher may still be announcing sub-tasks while

@@ -47,6 +47,47 @@ def test_abi_v10_table():
     assert not hasattr(lib, "ncclNetPlugin_v10")      # default build stays on well-known layouts
 
 
+def test_v10_profiler_callback_brackets_every_request():
+    """ncclNet v10: init() receives NCCL's profiler callback, isend/irecv a parent event handle; the plugin opens one
+    event per request under it and closes it when test() reports completion (include/bnet/bnet_profiler.h)."""
+    import ctypes as C
+
+    import numpy as np
+
+    from bagua_net_b200.utils.abi import BNET_PROFILER_PLUGIN_ID, PROFILER_CB, NetPlugin, ProfilerEventDescr
+
+    events = []
+    handles = iter(range(0x1000, 0x2000))
+
+    def cb(ehandle, typ, phandle, plugin_id, ext):
+        d = C.cast(ext, C.POINTER(ProfilerEventDescr)).contents
+        if typ == 0:
+            ehandle[0] = next(handles)
+        events.append((typ, ehandle[0], phandle, plugin_id, d.type, d.path, d.length, d.comm_id))
+        return 0
+
+    prof = PROFILER_CB(cb)
+    p = NetPlugin(10, "libnccl-net-bnetx.so")
+    p.init(profiler=prof)
+    h, l = p.listen(0)
+    s = p.connect(h)
+    r = p.accept(l)
+    src, dst = np.arange(70000, dtype=np.uint8), np.zeros(70000, dtype=np.uint8)
+    rq = p.irecv(r, dst.ctypes.data, 70000, phandle=0xAAAA)
+    sq = p.isend(s, src.ctypes.data, 70000, phandle=0xBBBB)
+    q2 = p.isend(s, src.ctypes.data, 16)                      # no parent handle: no profiler event
+    r2 = p.irecv(r, dst.ctypes.data, 16)
+    assert p.wait(sq) == 70000 and p.wait(rq) == 70000 and p.wait(q2) == 16 and p.wait(r2) == 16
+    p.close_send(s), p.close_recv(r), p.close_listen(l)
+    starts = [e for e in events if e[0] == 0]
+    stops = [e for e in events if e[0] == 1]
+    assert len(starts) == 2 and len(stops) == 2
+    assert {e[2] for e in starts} == {0xAAAA, 0xBBBB} and all(e[3] == BNET_PROFILER_PLUGIN_ID for e in events)
+    assert {e[1] for e in starts} == {e[1] for e in stops}               # every event that was opened is closed
+    assert {e[4] for e in starts} == {0, 1}                                # one isend, one irecv
+    assert all(e[6] == 70000 for e in stops) and all(e[5] in (0, 1, 2, 3) for e in stops)
+
+
 @pytest.mark.parametrize("nstreams", [1, 2, 8])
 @pytest.mark.parametrize("impl", ["BASIC", "TOKIO"])
 def test_tcp_backends_and_nstreams(impl, nstreams):
