@@ -191,24 +191,54 @@ int Engine::init() {
     BNET_WARN("unknown BAGUA_NET_IMPLEMENT '%s' (expected BASIC or TOKIO)", cfg.implement.c_str());
     return kErrInvalid;
   }
-  devs_ = find_interfaces();
+  // Device model.  The reference has one NCCL device per NIC (reference nthread_…:241-257).
+  // On an NVSwitch box the "NIC" of a GPU is its own NVLink port, so when the device path is usable every visible
+  // GPU gets a virtual device whose pciPath IS the GPU's: NCCL's topology then puts it next to that GPU — each rank
+  // picks its own device and enables GPUDirect without NCCL_NET_GDR_LEVEL overrides.  Every virtual device keeps a
+  // TCP side on a real interface (cross-host peers, fallbacks); the plain NIC devices follow after them.
+  std::vector<NetIf> nics = find_interfaces();
   cuda_ok_ = cfg.gdr && cuda::available();
+  devs_.clear();
+  gpu_of_dev_.clear();
   props_.clear();
   long long speed_override = env_int("SPEED_MBPS", 0);
-  for (size_t i = 0; i < devs_.size(); i++) {
+  const bool gpu_devs = env_int("GPU_DEVICES", cuda::fake() ? 0 : 1) != 0 && cfg.nvl && cuda_ok_ && !nics.empty();
+  if (gpu_devs) {
+    for (int g = 0; g < cuda::device_count(); g++) {
+      std::string busid;
+      std::string path = cuda::device_pci_path(g, &busid);
+      NetIf nif = nics[(size_t)g % nics.size()];
+      DeviceProps p;
+      p.name = "bnet-gpu" + std::to_string(g);
+      p.pci_path = path;
+      p.guid = fnv1a(busid.data(), busid.size()) ^ (uint64_t)g;
+      p.ptr_support = NCCL_PTR_HOST | NCCL_PTR_CUDA;
+      p.speed_mbps = speed_override > 0 ? (int)speed_override : 7200000;   // 900 GB/s per direction (NVLink 5)
+      p.port = 0;
+      p.latency_us = 0;
+      p.max_comms = 65536;
+      p.max_recvs = 1;
+      devs_.push_back(nif);
+      gpu_of_dev_.push_back(g);
+      props_.push_back(p);
+    }
+  }
+  for (size_t i = 0; i < nics.size(); i++) {
     DeviceProps p;
-    p.name = devs_[i].name;
-    p.pci_path = devs_[i].pci_path;
+    p.name = nics[i].name;
+    p.pci_path = nics[i].pci_path;
     p.guid = i;  // reference: guid = device index (nthread_…:250)
     p.ptr_support = NCCL_PTR_HOST | (cuda_ok_ ? NCCL_PTR_CUDA : 0);
-    p.speed_mbps = devs_[i].speed_mbps;
+    p.speed_mbps = nics[i].speed_mbps;
     // With the NVLink path available the "wire" is NVLink 5, not the NIC.
-    if (cfg.nvl && cuda_ok_) p.speed_mbps = 1600000;
+    if (cfg.nvl && cuda_ok_ && !gpu_devs) p.speed_mbps = 1600000;
     if (speed_override > 0) p.speed_mbps = (int)speed_override;
     p.port = 0;
     p.latency_us = 0;
     p.max_comms = 65536;
     p.max_recvs = 1;
+    devs_.push_back(nics[i]);
+    gpu_of_dev_.push_back(-1);
     props_.push_back(p);
   }
   {
@@ -216,8 +246,9 @@ int Engine::init() {
     for (size_t i = 0; i < devs_.size(); i++) names += (i ? "," : "") + devs_[i].name;
     Telemetry::get().set_root_attribute(names);   // (also starts the exporters)
   }
-  BNET_INFO("engine up: %zu device(s), implement=%s nstreams=%d min_chunksize=%zu nvl=%d cuda=%d",
-            devs_.size(), cfg.implement.c_str(), cfg.nstreams, cfg.min_chunksize, cfg.nvl, (int)cuda_ok_);
+  BNET_INFO("engine up: %zu device(s) (%d GPU-virtual + %zu NIC), implement=%s nstreams=%d min_chunksize=%zu nvl=%d cuda=%d",
+            devs_.size(), gpu_devs ? cuda::device_count() : 0, nics.size(), cfg.implement.c_str(), cfg.nstreams,
+            cfg.min_chunksize, cfg.nvl, (int)cuda_ok_);
   inited_ = true;
   return kOk;
 }
@@ -262,7 +293,7 @@ int Engine::listen(int dev, void* handle_out, size_t handle_cap, ListenComm** ou
     h.host_hash = host_hash();
     h.listen_nonce = random_u64();
     h.pid = (uint32_t)getpid();
-    h.cuda_dev = cuda_ok_ ? cuda::current_device() : -1;
+    h.cuda_dev = gpu_of_dev(dev) >= 0 ? gpu_of_dev(dev) : (cuda_ok_ ? cuda::current_device() : -1);
     if (cfg.implement == "TOKIO") h.flags |= HF_ASYNC;
     if (cfg.nvl && nvl_available()) {
       // abstract unix socket: intra-host rendezvous for the shared-memory/NVLink transport

@@ -75,13 +75,15 @@ class Engine {
   int accept(ListenComm* l, Comm** out, bool blocking);          // *out == nullptr: not ready yet
   const std::vector<NetIf>& devices() const { return devs_; }
   bool cuda_ok() const { return cuda_ok_; }
+  int gpu_of_dev(int dev) const { return dev >= 0 && dev < (int)gpu_of_dev_.size() ? gpu_of_dev_[dev] : -1; }
 
  private:
   Engine() = default;
   std::mutex mu_;
   bool inited_ = false;
   bool cuda_ok_ = false;
-  std::vector<NetIf> devs_;
+  std::vector<NetIf> devs_;             // per NCCL device: the interface its TCP side listens on
+  std::vector<int> gpu_of_dev_;         // per NCCL device: the GPU it stands for, -1 for a plain NIC device
   std::vector<DeviceProps> props_;
 };
 

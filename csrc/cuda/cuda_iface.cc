@@ -8,7 +8,10 @@
 #include "cuda/cuda_iface.h"
 
 #include <cuda_runtime_api.h>
+#include <ctype.h>
 #include <dlfcn.h>
+#include <limits.h>
+#include <stdlib.h>
 #include <fcntl.h>
 #include <string.h>
 #include <sys/mman.h>
@@ -184,6 +187,26 @@ bool pointer_is_device(const void* p, int* dev_out) {
   }
   if (dev_out) *dev_out = a.device;
   return a.type == cudaMemoryTypeDevice;
+}
+
+std::string device_pci_path(int dev, std::string* busid_out) {
+  if (busid_out) busid_out->clear();
+  if (fake_mode()) {
+    if (busid_out) *busid_out = "0000:00:00.0";
+    return "";
+  }
+  if (!available() || dev < 0 || dev >= device_count()) return "";
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof(bus), dev) != cudaSuccess) {
+    cudaGetLastError();
+    return "";
+  }
+  for (char* c = bus; *c; c++) *c = (char)tolower(*c);
+  if (busid_out) *busid_out = bus;
+  char buf[4096];
+  std::string p = std::string("/sys/bus/pci/devices/") + bus;
+  if (realpath(p.c_str(), buf)) return buf;
+  return "";
 }
 
 void* host_device_alias(const void* host_ptr) {

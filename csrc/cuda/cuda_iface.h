@@ -5,6 +5,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <string>
 
 namespace bnet {
 namespace cuda {
@@ -14,6 +15,8 @@ bool fake();                      // BNET_FAKE_CUDA=1: host-memory emulation for
 int device_count();
 int current_device();             // -1 when unavailable
 bool pointer_is_device(const void* p, int* dev_out);
+// sysfs path of GPU `dev` ("/sys/devices/pci0000:16/…/0000:1b:00.0"), "" when unknown; `busid_out` gets "0000:1b:00.0"
+std::string device_pci_path(int dev, std::string* busid_out = nullptr);
 // device-side alias of pinned/registered host memory (nullptr when the GPU cannot read it directly)
 void* host_device_alias(const void* host_ptr);
 

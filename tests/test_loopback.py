@@ -285,3 +285,33 @@ def test_connection_churn_leaks_nothing(env):
     script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts", "fd_leak.py")
     r = subprocess.run([sys.executable, script, "60"], capture_output=True, text=True, timeout=300, env=dict(os.environ, **env))
     assert r.returncode == 0 and "no leak" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+def test_per_gpu_virtual_devices():
+    """Device model of SURVEY section 5.8: one virtual net device per GPU (pciPath = the GPU's, so NCCL places it next to
+    that GPU and enables GPUDirect on its own), NIC devices after them.  Checked here with the emulated CUDA side."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    code = ("import json\n"
+            "from bagua_net_b200.utils.abi import NetPlugin\n"
+            "p = NetPlugin(8); p.init(); n = p.devices()\n"
+            "print(json.dumps([p.get_properties(i) for i in range(n)]))\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, BNET_FAKE_CUDA="1", BNET_GPU_DEVICES="1", BNET_NVL="1", PYTHONPATH=root)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr[-2000:]
+    props = json.loads(out.stdout.splitlines()[-1])
+    assert len(props) >= 2
+    g = props[0]
+    assert g["name"] == "bnet-gpu0" and g["ptrSupport"] == 3 and g["speed"] == 7200000 and g["maxRecvs"] == 1
+    assert all(not p["name"].startswith("bnet-gpu") for p in props[1:])           # the NIC devices follow
+    assert len({p["guid"] for p in props}) == len(props)
+    # and the default without a GPU: NIC devices only, like the reference (nthread_…:241-257)
+    env2 = dict(os.environ, BNET_GPU_DEVICES="1", PYTHONPATH=root)
+    env2.pop("BNET_FAKE_CUDA", None)
+    out = subprocess.run([sys.executable, "-c", code], env=env2, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert not any(p["name"].startswith("bnet-gpu") for p in json.loads(out.stdout.splitlines()[-1]))
