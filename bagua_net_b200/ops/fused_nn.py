@@ -64,19 +64,81 @@ def _conv(x, w, stride, padding):
 
 
 def _conv_backward(gz, x, w, stride, padding, need_x):
+    """(gx, gw) of the convolution.  3x3 / stride 1 / pad 1 layers whose shape the autotuner gave to the tcgen05 kernel
+    (ops/tc_conv.py) take their input gradient from it — the filter is read as stored, MN-major, taps flipped — and only
+    the filter gradient from cuDNN."""
+    if need_x and _is_3x3_s1p1(w, stride, padding):
+        from . import tc_conv
+
+        def lib():
+            return torch.ops.aten.convolution_backward(gz, x, w, None, stride, padding, [1, 1], False, [0, 0], 1,
+                                                       [True, False, False])[0]
+
+        if tc_conv.choose("dgrad", gz, w, lib, lambda: tc_conv.conv3x3_dgrad(gz, w), tc_conv.close) == "tc":
+            gx = tc_conv.conv3x3_dgrad(gz, w)
+            gw = torch.ops.aten.convolution_backward(gz, x, w, None, stride, padding, [1, 1], False, [0, 0], 1,
+                                                     [False, True, False])[1]
+            return gx, gw
     gx, gw, _ = torch.ops.aten.convolution_backward(gz, x, w, None, stride, padding, [1, 1], False, [0, 0], 1,
                                                     [need_x, True, False])
     return gx, gw
 
 
-class _ConvBiasReLU(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, w, b, stride, padding):
+_zeros: dict = {}
+
+
+def _zero_bias(b: torch.Tensor) -> torch.Tensor:
+    key = (b.device, b.dtype, b.numel())
+    if key not in _zeros:
+        _zeros[key] = torch.zeros_like(b)
+    return _zeros[key]
+
+
+def _tc_fwd_chosen(x, w, b, stride, padding) -> bool:
+    """Did (or does, on first sight of this shape) the autotuner give this layer's forward convolution to the tcgen05 kernel?"""
+    from . import tc_conv
+
+    def lib():
         z = _conv(x, w, stride, padding)
         if not _nhwc(z):
             z = z.contiguous(memory_format=torch.channels_last)
         n, c, h, wd = z.shape
         _chk(_L().bnet_nn_bias_relu(z.data_ptr(), b.data_ptr(), n * h * wd, c, _DT[z.dtype], _stream()), "bias_relu")
+        return z
+
+    return tc_conv.choose("fwd", x, w, lib, lambda: tc_conv.conv3x3(x, w, b, relu=True), tc_conv.close) == "tc"
+
+
+def _is_3x3_s1p1(w, stride, padding) -> bool:
+    return tuple(w.shape[2:]) == (3, 3) and list(stride) == [1, 1] and list(padding) == [1, 1]
+
+
+def _conv_bias_relu(x, w, b, stride, padding):
+    """relu(conv(x, w) + b), NHWC: ONE tcgen05 kernel (bias + ReLU applied from TMEM) where the autotuner picked it for this
+    shape, otherwise cuDNN's convolution followed by our in-place bias + ReLU pass."""
+    def lib():
+        z = _conv(x, w, stride, padding)
+        if not _nhwc(z):
+            z = z.contiguous(memory_format=torch.channels_last)
+        n, c, h, wd = z.shape
+        _chk(_L().bnet_nn_bias_relu(z.data_ptr(), b.data_ptr(), n * h * wd, c, _DT[z.dtype], _stream()), "bias_relu")
+        return z
+
+    if _is_3x3_s1p1(w, stride, padding) and x.dtype == torch.bfloat16:
+        from . import tc_conv
+
+        def tc():
+            return tc_conv.conv3x3(x, w, b, relu=True)
+
+        if tc_conv.choose("fwd", x, w, lib, tc, tc_conv.close) == "tc":
+            return tc()
+    return lib()
+
+
+class _ConvBiasReLU(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, stride, padding):
+        z = _conv_bias_relu(x, w, b, stride, padding)
         ctx.save_for_backward(x, w, z)
         ctx.conv = (stride, padding)
         return z
@@ -99,13 +161,21 @@ class _ConvBiasReLU(torch.autograd.Function):
 class _ConvBiasReLUPool(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, stride, padding):
-        z = _conv(x, w, stride, padding)
-        if not _nhwc(z):
-            z = z.contiguous(memory_format=torch.channels_last)
+        pool_bias = b
+        if _is_3x3_s1p1(w, stride, padding) and x.dtype == torch.bfloat16 and _tc_fwd_chosen(x, w, b, stride, padding):
+            # the tcgen05 convolution has bias + ReLU in its epilogue: the pool pass sees relu(z + b) and adds nothing
+            from . import tc_conv
+
+            z = tc_conv.conv3x3(x, w, b, relu=True)
+            pool_bias = _zero_bias(b)
+        else:
+            z = _conv(x, w, stride, padding)
+            if not _nhwc(z):
+                z = z.contiguous(memory_format=torch.channels_last)
         n, c, h, wd = z.shape
         p = torch.empty((n, c, h // 2, wd // 2), device=z.device, dtype=z.dtype, memory_format=torch.channels_last)
         idx = torch.empty(n * (h // 2) * (wd // 2) * c, device=z.device, dtype=torch.uint8)
-        _chk(_L().bnet_nn_bias_relu_pool_fwd(z.data_ptr(), b.data_ptr(), p.data_ptr(), idx.data_ptr(), n, h, wd, c,
+        _chk(_L().bnet_nn_bias_relu_pool_fwd(z.data_ptr(), pool_bias.data_ptr(), p.data_ptr(), idx.data_ptr(), n, h, wd, c,
                                              _DT[z.dtype], _stream()), "bias_relu_pool_fwd")
         ctx.save_for_backward(x, w, idx)
         ctx.conv = (stride, padding)

@@ -46,6 +46,7 @@ def _L():
         _lib.bnet_tc_plan.argtypes = [i, i, i, i, i, C.POINTER(Plan)]
         _lib.bnet_tc_linear.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, i, vp, vp]
         _lib.bnet_tc_linear_reduce.argtypes = [vp, vp, vp, C.POINTER(vp), i, i, i, i, i, i, i, i, i, vp, vp]
+        _lib.bnet_tc_linear_splitk.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, vp, vp]
         _lib.bnet_tc_linear_dgrad.argtypes = [vp, vp, vp, i, i, i, i, i, i, vp, vp]
         _lib.bnet_tc_linear_wgrad.argtypes = [vp, vp, vp, i, i, i, i, i, i, vp, vp]
         _lib.bnet_tc_allgather_linear.argtypes = [C.POINTER(vp), i, i, vp, vp, vp, i, i, i, i, i, i, vp, vp]
@@ -59,8 +60,9 @@ def _L():
 
 
 def enabled() -> bool:
-    """Opt-in switch for callers (models, bench): the kernel is unvalidated on hardware in this round."""
-    return os.environ.get("BNET_TC", "0") == "1"
+    """Switch for callers (models, bench).  On by default since the kernel passed its probes on B200 hardware
+    (profiles/r2/tc_probe_1gpu.txt); BNET_TC=0 keeps every linear layer on cuBLAS."""
+    return os.environ.get("BNET_TC", "1") == "1"
 
 
 def supported() -> bool:
@@ -119,6 +121,20 @@ def _auto_splits(M: int, N: int, K: int) -> int:
     return max(1, min(8, sms // max(tiles, 1), K // 1024))
 
 
+_scratch: dict = {}
+
+
+def _splitk_scratch(device, M: int, N: int):
+    """fp32 [M, N] workspace + one counter per output tile, shared by every split-K call of that shape on that device
+    (calls on one stream are ordered; the kernel hands both back all-zero)."""
+    key = (device.index, M, N)
+    if key not in _scratch:
+        tiles = ((N + 31) // 32) * ((M + 31) // 32) + 64        # upper bound on the tile count of any plan
+        _scratch[key] = (torch.zeros((M, N), dtype=torch.float32, device=device),
+                         torch.zeros(tiles, dtype=torch.int32, device=device))
+    return _scratch[key]
+
+
 def linear(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, relu: bool = False,
            out: torch.Tensor | None = None, splits: int | None = None) -> torch.Tensor:
     """``act(x @ w.T + bias)`` on the tcgen05 tensor cores; x [M,K], w [N,K] (torch ``Linear.weight``), bf16.
@@ -134,20 +150,16 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, r
     if splits is None:
         splits = _auto_splits(M, N, K)
     if splits > 1:
-        # split-K: fp32 partial sums into a zeroed workspace (the kernel's reduce epilogue with a single, local target),
-        # then bias / ReLU / bf16 on the small result
-        ws = torch.zeros((M, N), dtype=torch.float32, device=x.device)
-        arr = (C.c_void_p * 1)(ws.data_ptr())
-        rc = L.bnet_tc_linear_reduce(x.data_ptr(), w.data_ptr(), None, arr, 1, 0, M, N, K, x.stride(0), w.stride(0), N, splits,
-                                     _err_flag(x.device.index).data_ptr(), _stream())
+        # split-K with the finish inside the kernel: the K slices add fp32 partial tiles into a workspace, the slice that
+        # arrives last at a tile applies bias / ReLU, writes bf16 and re-zeroes what it read — ONE launch.  The workspace
+        # and the tile counters are zero between calls by construction, so they are allocated (and cleared) once.
+        ws, counters = _splitk_scratch(x.device, M, N)
+        rc = L.bnet_tc_linear_splitk(x.data_ptr(), w.data_ptr(), bias.data_ptr() if bias is not None else None, out.data_ptr(),
+                                     ws.data_ptr(), counters.data_ptr(), M, N, K, x.stride(0), w.stride(0), out.stride(0),
+                                     1 if relu else 0, splits, _err_flag(x.device.index).data_ptr(), _stream())
         if rc < 0:
-            raise RuntimeError(f"bnet_tc_linear_reduce (split-K): {L.bnet_tc_last_error().decode()}")
+            raise RuntimeError(f"bnet_tc_linear_splitk: {L.bnet_tc_last_error().decode()}")
         LAUNCHES += rc
-        if bias is not None:
-            ws += bias.float()
-        if relu:
-            ws.relu_()
-        out.copy_(ws)
         return out
     rc = L.bnet_tc_linear(x.data_ptr(), w.data_ptr(), bias.data_ptr() if bias is not None else None, out.data_ptr(), M, N,
                           K, x.stride(0), w.stride(0), out.stride(0), 1 if relu else 0,

@@ -11,9 +11,14 @@ measures the same metric on N B200s of one box:
 
 --comm bnet (default)   our engine: flat symmetric buckets + ONE fused kernel per bucket
                         (NVLS in-switch reduce + SGD + parameter broadcast), overlapped with backward
---comm nccl             torch DDP over stock NCCL + torch.optim.SGD         (comparison line)
---comm nccl-plugin      torch DDP over NCCL forced through our ncclNet plugin (BASELINE config #3)
+--comm nccl-plugin      torch DDP over NCCL forced through our ncclNet plugin (BASELINE config #3/#4) — the SAME
+                        fused model, captured in a CUDA graph like the default arm, so only the communication differs
+--comm nccl             the same again over stock NCCL (P2P/NVLS): the comparison line for both
 --impl reference        the unmodified reference: cannot be built offline (needs cargo + 191 crates)
+
+At N > 1 the default run also measures the two DDP arms in child processes (bounded by a timeout) and reports them
+under extra.nccl_plugin / extra.nccl_stock next to the headline: img/s, the all-reduce bus bandwidth 8 B - 128 MiB
+over that path, and a cross-rank parameter checksum.  --no-arms skips them.
 
 Prints ONE JSON line on rank 0 (contract in the task statement).
 """
@@ -149,10 +154,6 @@ def maybe_reexec_for_plugin(args):
 
     env = dict(os.environ)
     env.update(nccl_plugin_env(force_net=True))
-    # keep the transport's stream kernels resident across iterations: a (re)launch in the middle of a
-    # collective can be held up by a cudaFree elsewhere in the process (profiles/blocking_calls.txt)
-    env.setdefault("BNET_KERNEL_IDLE_US", "2000000")
-    env.setdefault("BNET_KERNEL_ARM_MS", "2000")
     env["BNET_BENCH_REEXEC"] = "1"
     os.execve(sys.executable, [sys.executable] + sys.argv, env)
 
@@ -190,6 +191,63 @@ def isolated_self_check(name: str, local: int, timeout: float = 240.0):
     return None
 
 
+ARM_SIZES = (8, 1 << 10, 64 << 10, 1 << 20, 16 << 20, 128 << 20)   # all-reduce message sizes of the DDP arms (bytes)
+
+
+def run_child_arm(comm_name: str, args, rank: int, world: int, port_offset: int, timeout: float):
+    """One DDP arm (`--comm nccl-plugin` / `--comm nccl`) as a child process per rank: own CUDA context, own NCCL
+    (with or without the plugin on LD_LIBRARY_PATH), own rendezvous port.  Every rank of the parent job calls this at
+    the same time; rank 0 returns the child's JSON (or a status dict), the others None.  A child that outlives
+    `timeout` is killed (its exact pid) — a stalled transport costs this arm, not the benchmark."""
+    import tempfile
+
+    env = dict(os.environ)
+    env["MASTER_PORT"] = str(int(os.environ.get("MASTER_PORT", "29500")) + port_offset)
+    env["BNET_BENCH_CHILD"] = "1"
+    env["BNET_BENCH_FUSED_VERDICT"] = "0" if args.no_fused or getattr(args, "fused_failed", False) else "1"
+    env.pop("BNET_BENCH_REEXEC", None)
+    env.pop("TORCHELASTIC_RUN_ID", None)
+    out_path = os.path.join(tempfile.gettempdir(), f"bnet_bench_arm_{comm_name}_{os.getppid()}_{env['MASTER_PORT']}.json")
+    if rank == 0 and os.path.exists(out_path):
+        os.unlink(out_path)
+    cmd = [sys.executable, os.path.abspath(__file__), "--comm", comm_name, "--gpus", str(world), "--steps", str(min(args.steps, 10)),
+           "--warmup", "3", "--model", args.model, "--batch", str(args.batch), "--image", str(args.image), "--no-e2e",
+           "--no-arms", "--child-json", out_path]
+    if args.no_fused:
+        cmd.append("--no-fused")
+    if args.no_graph:
+        cmd.append("--no-graph")
+    log_path = out_path.replace(".json", f".rank{rank}.log")
+    t0 = time.time()
+    status = "ok"
+    with open(log_path, "w") as logf:
+        proc = subprocess.Popen(cmd, env=env, stdout=logf, stderr=subprocess.STDOUT)
+        try:
+            rc = proc.wait(timeout=timeout)
+            if rc != 0:
+                status = f"exit code {rc}"
+        except subprocess.TimeoutExpired:
+            proc.kill()
+            proc.wait()
+            status = f"timeout after {int(timeout)} s (killed)"
+    if rank != 0:
+        return None
+    res = {"status": status, "wall_s": round(time.time() - t0, 1)}
+    try:
+        with open(out_path) as f:
+            res.update(json.load(f))
+    except Exception:                            # noqa: BLE001
+        if status == "ok":
+            res["status"] = "no result written"
+        try:
+            with open(log_path) as f:
+                tail = [ln.strip() for ln in f.read().splitlines() if ln.strip() and "Warning" not in ln]
+            res["log_tail"] = tail[-6:]
+        except Exception:                        # noqa: BLE001
+            pass
+    return res
+
+
 def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -203,9 +261,12 @@ def main() -> int:
     ap.add_argument("--bucket-mb", type=float, default=64.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the all-reduce busbw side measurement")
+    ap.add_argument("--no-arms", action="store_true", help="N > 1: skip the NCCL-over-plugin / stock-NCCL DDP arms")
+    ap.add_argument("--arm-timeout", type=float, default=210.0, help="seconds one DDP arm (child processes) may take")
     ap.add_argument("--no-prefetch", action="store_true", help="e2e: per-step API instead of the prefetching loop")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel of the step individually (no CUDA graph)")
     ap.add_argument("--no-fused", action="store_true", help="eager bias/ReLU/pool instead of the fused sm_100a conv blocks")
+    ap.add_argument("--child-json", default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -230,15 +291,13 @@ def main() -> int:
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     init_process_group_from_env("nccl")
-    # (the NCCL-over-plugin arm keeps cuDNN's autotuner off: its emptyCache() -> cudaFree in the middle of
-    #  a collective holds up the transport's kernel launches)
-    torch.backends.cudnn.benchmark = args.comm != "nccl-plugin"
+    torch.backends.cudnn.benchmark = True
     torch.backends.cuda.matmul.allow_tf32 = True
     torch.backends.cudnn.allow_tf32 = True
     torch.manual_seed(1234)
 
-    # our arm trains the model built from our fused conv blocks; the stock-NCCL arms train the plain eager model
-    fused = args.comm == "bnet" and not args.no_fused and args.model.startswith(("vgg", "resnet"))
+    # every arm trains the SAME model: the one built from our fused conv blocks (when they pass their self-check)
+    fused = not args.no_fused and args.model.startswith(("vgg", "resnet"))
     fused_note = None
     if fused:
         # the native layer kernels are checked against the eager chain on this very GPU before they are trusted
@@ -246,14 +305,19 @@ def main() -> int:
         from bagua_net_b200.ops import fused_nn
 
         check = fused_nn.self_check if args.model.startswith("vgg") else fused_nn.self_check_bn
-        verdict = None if os.environ.get("BNET_BENCH_INPROC_CHECK") == "1" else isolated_self_check(check.__name__, local)
-        if verdict is None:
-            verdict = check(dev)
+        inherited = os.environ.get("BNET_BENCH_FUSED_VERDICT")     # a child arm: the parent has run the check on this GPU
+        if inherited in ("0", "1"):
+            verdict = inherited == "1"
+        else:
+            verdict = None if os.environ.get("BNET_BENCH_INPROC_CHECK") == "1" else isolated_self_check(check.__name__, local)
+            if verdict is None:
+                verdict = check(dev)
         ok = torch.tensor([1 if verdict else 0], device=dev, dtype=torch.int32)
         if world > 1:
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if int(ok.item()) == 0:
             fused, fused_note = False, "fused layer kernels failed their self-check on this machine: eager layers used"
+            args.fused_failed = True
             if rank == 0:
                 print(f"[bench] WARNING: {fused_note}", file=sys.stderr)
     model = build_model(args.model, **({"fused": True} if fused else {}))
@@ -261,6 +325,16 @@ def main() -> int:
     model.train()
     lr, mom, wd = 0.01, 0.9, 1e-4
     n_params = sum(p.numel() for p in model.parameters())
+    B, S = args.batch, args.image
+    x_dev = torch.randn(B, 3, S, S, device=dev, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    y_dev = torch.randint(0, 1000, (B,), device=dev)
+    graph_used = False
+    graph_note = None
+
+    def our_launches():
+        from bagua_net_b200.ops import fused_nn, tc_linear
+
+        return fused_nn.LAUNCHES + tc_linear.LAUNCHES
 
     if args.comm == "bnet":
         engine = BnetDDP(model, lr=lr, momentum=mom, weight_decay=wd, bucket_mb=args.bucket_mb,
@@ -268,6 +342,7 @@ def main() -> int:
         comm = engine.comm
         if not args.no_graph:
             engine.enable_cuda_graph(True)
+            graph_used = True
 
         def step_dev(x, y):
             return engine.train_step(x, y)
@@ -284,32 +359,73 @@ def main() -> int:
             assert n == steps
 
         def launches():
-            from bagua_net_b200.ops import fused_nn, tc_linear
+            return comm.launches + our_launches()
 
-            return comm.launches + fused_nn.LAUNCHES + tc_linear.LAUNCHES
+        def param_vector():
+            return engine.flat_param
         path = ("nvls" if (comm.has_multicast and world > 2) else "p2p") if world > 1 else "single"
     else:
-        if args.comm == "nccl-plugin":
-            # Let cuDNN pick its algorithms (and torch's allocator settle) BEFORE any collective is in
-            # flight: the benchmark search ends in emptyCache() -> cudaFree, and a cudaFree holds up every
-            # kernel launch in the process (profiles/blocking_calls.txt) — including the transport's.
-            xw = torch.randn(args.batch, 3, args.image, args.image, device=dev, dtype=torch.bfloat16)
-            xw = xw.contiguous(memory_format=torch.channels_last)
-            for _ in range(2):
-                torch.nn.functional.cross_entropy(model(xw).float(), torch.zeros(args.batch, dtype=torch.long, device=dev)).backward()
-            model.zero_grad(set_to_none=True)
-            del xw
-            torch.cuda.synchronize()
-        ddp = (torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
-               if world > 1 else model)
-        opt = torch.optim.SGD(model.parameters(), lr=lr, momentum=mom, weight_decay=wd)
+        # ---- torch DDP over NCCL (stock, or forced through the bnet plugin) ----------------------------------------
+        # Let cuDNN pick its algorithms (and torch's allocator settle) BEFORE any collective is in flight: the
+        # autotuner's emptyCache() -> cudaFree waits for the device, and a collective that is waiting for a peer which
+        # is itself stuck behind such a call is the classic NCCL dead-lock (NCCL documents it for its own kernels).
+        for _ in range(2):
+            torch.nn.functional.cross_entropy(model(x_dev).float(), y_dev).backward()
+        model.zero_grad(set_to_none=True)
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                # DDP built (and warmed up) on a side stream: required for capture
+            ddp = (torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
+                   if world > 1 else model)
+            opt = torch.optim.SGD(model.parameters(), lr=lr, momentum=mom, weight_decay=wd)
+            gx, gy = x_dev.clone(), y_dev.clone()
+
+            def eager_step(x, y):
+                opt.zero_grad(set_to_none=True)
+                loss = torch.nn.functional.cross_entropy(ddp(x).float(), y)
+                loss.backward()
+                opt.step()
+                return loss.detach()
+
+            for _ in range(4 if world == 1 else 11):  # (DDP wants 11 eager iterations before a capture)
+                eager_step(gx, gy)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = None
+        if not args.no_graph:
+            try:
+                l0 = our_launches()
+                opt.zero_grad(set_to_none=True)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    gloss = torch.nn.functional.cross_entropy(ddp(gx).float(), gy)
+                    gloss.backward()
+                    opt.step()
+                graph_launches = our_launches() - l0
+                graph.replay()
+                torch.cuda.synchronize()
+                graph_used = True
+            except Exception as ex:               # noqa: BLE001 - keep the arm alive without the graph
+                graph = None
+                graph_note = f"capture failed ({type(ex).__name__}: {str(ex)[:120]}): eager launches"
+                torch.cuda.synchronize()
+        ok = torch.tensor([1 if graph is not None else 0], device=dev, dtype=torch.int32)
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)     # every rank replays, or none does
+        if int(ok.item()) == 0:
+            graph, graph_used = None, False
 
         def step_dev(x, y):
-            opt.zero_grad(set_to_none=True)
-            loss = torch.nn.functional.cross_entropy(ddp(x).float(), y)
-            loss.backward()
-            opt.step()
-            return loss.detach()
+            if graph is None:
+                return eager_step(x, y)
+            from bagua_net_b200.ops import fused_nn
+
+            gx.copy_(x, non_blocking=True)
+            gy.copy_(y, non_blocking=True)
+            graph.replay()
+            fused_nn.LAUNCHES += graph_launches
+            return gloss
 
         def step_host(xh, yh):
             x = xh.to(dev, non_blocking=True).contiguous(memory_format=torch.channels_last)
@@ -317,12 +433,13 @@ def main() -> int:
             return float(step_dev(x, y).item())
 
         def launches():
-            return 0
+            return our_launches()
+
+        def param_vector():
+            return torch.cat([p.detach().reshape(-1).float() for p in model.parameters()])
+        comm = None
         path = args.comm
 
-    B, S = args.batch, args.image
-    x_dev = torch.randn(B, 3, S, S, device=dev, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
-    y_dev = torch.randint(0, 1000, (B,), device=dev)
     # pinned, already in the layout the model consumes (NHWC): the H2D copy is one plain DMA
     x_host = torch.randn(B, 3, S, S, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last).pin_memory()
     y_host = torch.randint(0, 1000, (B,)).pin_memory()
@@ -366,6 +483,16 @@ def main() -> int:
     ms_step = ms_total / args.steps
     img_s = world * B / (ms_step / 1e3)
 
+    # ---- cross-rank numerics: after the timed steps every rank must hold the same parameters ----
+    pv = param_vector()
+    csum = torch.stack([pv.double().sum(), pv.double().abs().sum()])
+    checksum = {"sum": float(csum[0].item()), "abs_sum": float(csum[1].item()), "finite": bool(torch.isfinite(csum).all().item())}
+    if world > 1:
+        allc = [torch.zeros_like(csum) for _ in range(world)]
+        dist.all_gather(allc, csum)
+        checksum["ranks_agree"] = all(bool(torch.equal(allc[0], c)) for c in allc)
+    del pv
+
     # ---- end to end through the public API: pinned-host batch in, loss value out, every step ----
     e2e = None
     if not args.no_e2e:
@@ -387,7 +514,7 @@ def main() -> int:
                "h2d_bytes_per_step": x_host.numel() * x_host.element_size() + y_host.numel() * y_host.element_size(),
                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "api": api}
 
-    # ---- side measurement: all-reduce bus bandwidth of the fused path (BASELINE.json config #5) ----
+    # ---- side measurement: all-reduce bus bandwidth (BASELINE.json configs #2 / #5) ----
     extra = {}
     if args.comm == "bnet" and world > 1 and not args.no_extra:
         try:
@@ -408,27 +535,82 @@ def main() -> int:
                                                           for k, v in bw.items()}
         except Exception as ex:   # the headline number must survive a failing side measurement
             extra["allreduce_error"] = str(ex)[:200]
+    if args.comm != "bnet" and world > 1 and not args.no_extra:
+        # the nccl-tests sweep of the reference's README (all_reduce_perf -b 8 -e 128M), through torch.distributed:
+        # bf16 sum, device-timed, max over ranks; busbw = algbw * 2(n-1)/n
+        try:
+            bw, lat = {}, {}
+            for nbytes in ARM_SIZES:
+                t = torch.ones(max(nbytes // 2, 1), device=dev, dtype=torch.bfloat16)
+                iters = 20 if nbytes <= (16 << 20) else 8
+                for _ in range(3):
+                    dist.all_reduce(t)
+                ms, _ = timed(lambda: dist.all_reduce(t), iters)
+                us = ms / iters * 1e3
+                lat[str(nbytes)] = round(us, 1)
+                bw[str(nbytes)] = round(nbytes / (us * 1e-6) / 1e9 * 2 * (world - 1) / world, 2)
+                del t
+            extra["allreduce_busbw_gbs_bf16"] = bw
+            extra["allreduce_time_us"] = lat
+            # numerics of the path itself: sum of rank-patterned data against the closed form
+            t = torch.full((1 << 20,), float(rank + 1), device=dev, dtype=torch.float32)
+            dist.all_reduce(t)
+            extra["allreduce_exact"] = bool((t == float(world * (world + 1) // 2)).all().item())
+        except Exception as ex:   # noqa: BLE001
+            extra["allreduce_error"] = str(ex)[:200]
+
+    # ---- N > 1: the DDP arms over NCCL (through the plugin / stock) in child processes ----
+    arms = {}
+    if args.comm == "bnet" and world > 1 and not args.no_arms and not os.environ.get("BNET_BENCH_CHILD"):
+        sync_all()
+        for i, (key, comm_name) in enumerate((("nccl_plugin", "nccl-plugin"), ("nccl_stock", "nccl"))):
+            res = run_child_arm(comm_name, args, rank, world, 101 + 37 * i, args.arm_timeout)
+            if world > 1:
+                dist.barrier()
+            if rank == 0:
+                arms[key] = res
 
     if rank == 0:
+        opt_desc = (f"sgd(lr={lr},momentum={mom},wd={wd}) fused into the collective" if args.comm == "bnet"
+                    else f"torch.optim.SGD(lr={lr},momentum={mom},wd={wd})")
         out = {
             "metric": f"{args.model}_train_img_per_sec", "value": round(img_s, 2), "unit": "img/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": round(img_s / BASELINE_IMG_S, 4),
             "dtype": "bf16", "data": "synthetic (random images/labels, random-init weights)",
             "config": {"model": args.model, "global_batch": world * B, "per_gpu_batch": B, "seq_len": None,
-                       "image": [3, S, S], "parallelism": f"dp{world}", "comm": args.comm, "path": path, "fused_conv_blocks": fused, **({"fused_note": fused_note} if fused_note else {}), "cuda_graph": args.comm == "bnet" and not args.no_graph,
-                       "optimizer": f"sgd(lr={lr},momentum={mom},wd={wd}) fused into the collective" if args.comm == "bnet"
-                       else f"torch.optim.SGD(lr={lr},momentum={mom},wd={wd})",
-                       "params": n_params, "bucket_mb": args.bucket_mb,
+                       "image": [3, S, S], "parallelism": f"dp{world}", "comm": args.comm, "path": path,
+                       "fused_conv_blocks": fused, **({"fused_note": fused_note} if fused_note else {}),
+                       "cuda_graph": graph_used, **({"graph_note": graph_note} if graph_note else {}),
+                       "optimizer": opt_desc, "params": n_params, "bucket_mb": args.bucket_mb,
                        "l2": "no explicit flush: per-step working set (553 MB params+grads, activations) exceeds the 126 MB L2",
                        "baseline": "4046.6 img/s on 32xV100/100GbE (reference README.md:68)"},
             "clocks": clocks, "gpu_launches": nlaunch, "wall_ms_per_step": round(wall_total / args.steps, 3),
+            "param_checksum": checksum,
         }
         if e2e:
             out["e2e"] = {k: (round(v, 3) if isinstance(v, float) else v) for k, v in e2e.items()}
+        for key, res in arms.items():
+            if res is None:
+                continue
+            # keep the arm compact: its headline, its sweep, its checks
+            keep = {k: res.get(k) for k in ("status", "wall_s", "value", "ms_per_step", "log_tail") if res.get(k) is not None}
+            cfg = res.get("config") or {}
+            keep.update({k: cfg.get(k) for k in ("comm", "cuda_graph", "fused_conv_blocks", "graph_note") if cfg.get(k) is not None})
+            ex = res.get("extra") or {}
+            keep.update({k: ex[k] for k in ("allreduce_busbw_gbs_bf16", "allreduce_time_us", "allreduce_exact", "allreduce_error")
+                         if k in ex})
+            if res.get("param_checksum"):
+                keep["param_checksum"] = res["param_checksum"]
+            extra[key] = keep
         if extra:
             out["extra"] = extra
-        print(json.dumps(out), flush=True)
+        line = json.dumps(out)
+        if args.child_json:
+            with open(args.child_json + ".tmp", "w") as f:
+                f.write(line)
+            os.replace(args.child_json + ".tmp", args.child_json)
+        print(line, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -19,8 +19,22 @@
 #include <sys/wait.h>
 #include <unistd.h>
 
+#include <execinfo.h>
+#include <signal.h>
+
 #include <atomic>
 #include <vector>
+
+// a rank that dies of a signal says where (the plugin is loaded into this process: its frames show up here)
+static void crash_handler(int sig) {
+  void* frames[64];
+  int n = backtrace(frames, 64);
+  char msg[96];
+  int len = snprintf(msg, sizeof(msg), "\n[all_reduce_perf] pid %d: signal %d, backtrace:\n", (int)getpid(), sig);
+  if (write(2, msg, len) < 0) {}
+  backtrace_symbols_fd(frames, n, 2);
+  _exit(128 + sig);
+}
 
 #define CUDACHECK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { fprintf(stderr, "CUDA %s:%d %s\n", __FILE__, __LINE__, cudaGetErrorString(e)); exit(2); } } while (0)
 #define NCCLCHECK(x) do { ncclResult_t r = (x); if (r != ncclSuccess) { fprintf(stderr, "NCCL %s:%d %s\n", __FILE__, __LINE__, ncclGetErrorString(r)); exit(3); } } while (0)
@@ -173,6 +187,11 @@ int main(int argc, char** argv) {
   for (int r = 0; r < nranks; r++) {   // fork BEFORE any CUDA call
     pid_t p = fork();
     if (p == 0) {
+      setvbuf(stdout, nullptr, _IOLBF, 0);
+      signal(SIGSEGV, crash_handler);
+      signal(SIGBUS, crash_handler);
+      signal(SIGABRT, crash_handler);
+      signal(SIGFPE, crash_handler);
       int rc;
       if (!strcmp(dtype, "half")) rc = run_rank<__half>(r, nranks, sh, minb, maxb, factor, iters, warm, ncclFloat16, "half", check);
       else if (!strcmp(dtype, "bfloat16")) rc = run_rank<__nv_bfloat16>(r, nranks, sh, minb, maxb, factor, iters, warm, ncclBfloat16, "bf16", check);
@@ -185,7 +204,11 @@ int main(int argc, char** argv) {
   for (pid_t p : kids) {
     int stt = 0;
     waitpid(p, &stt, 0);
-    if (!WIFEXITED(stt) || WEXITSTATUS(stt) != 0) bad++;
+    if (!WIFEXITED(stt) || WEXITSTATUS(stt) != 0) {
+      bad++;
+      if (WIFSIGNALED(stt)) fprintf(stderr, "[all_reduce_perf] rank process %d killed by signal %d\n", (int)p, WTERMSIG(stt));
+      else fprintf(stderr, "[all_reduce_perf] rank process %d exited with code %d\n", (int)p, WEXITSTATUS(stt));
+    }
   }
   return bad ? 1 : 0;
 }

@@ -210,7 +210,13 @@ int Engine::init() {
       NetIf nif = nics[(size_t)g % nics.size()];
       DeviceProps p;
       p.name = "bnet-gpu" + std::to_string(g);
-      p.pci_path = path;
+      // NCCL builds its topology from pciPath: the last component must be a PCI leaf that is NOT the GPU itself (a <pci>
+      // node with both a <gpu> and a <nic> child loses the GPU's link to its parent in ncclTopoAddPci).  There is no such
+      // leaf for a virtual NVLink "NIC", so by default the device carries no PCI path (NCCL attaches it to the CPU, like
+      // any virtual NIC) and the plugin supplies NCCL_NET_GDR_LEVEL=SYS itself (plugin.cc: tune_nccl_env), which is what
+      // lets NCCL hand us device pointers.  BNET_GPU_DEVICE_PCI=gpu keeps the GPU's own path for experiments.
+      static const bool own_path = env_str("GPU_DEVICE_PCI", "none") == "gpu";
+      p.pci_path = own_path ? path : std::string();
       p.guid = fnv1a(busid.data(), busid.size()) ^ (uint64_t)g;
       p.ptr_support = NCCL_PTR_HOST | NCCL_PTR_CUDA;
       p.speed_mbps = speed_override > 0 ? (int)speed_override : 7200000;   // 900 GB/s per direction (NVLink 5)
@@ -293,7 +299,7 @@ int Engine::listen(int dev, void* handle_out, size_t handle_cap, ListenComm** ou
     h.host_hash = host_hash();
     h.listen_nonce = random_u64();
     h.pid = (uint32_t)getpid();
-    h.cuda_dev = gpu_of_dev(dev) >= 0 ? gpu_of_dev(dev) : (cuda_ok_ ? cuda::current_device() : -1);
+    h.cuda_dev = cuda_ok_ ? cuda::current_device() : -1;   // (NCCL may pick any of the equidistant virtual devices)
     if (cfg.implement == "TOKIO") h.flags |= HF_ASYNC;
     if (cfg.nvl && nvl_available()) {
       // abstract unix socket: intra-host rendezvous for the shared-memory/NVLink transport

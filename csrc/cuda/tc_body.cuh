@@ -42,7 +42,28 @@ BNET_TC_HD uint16_t f32_to_bf16(float f) {        // round to nearest even, NaN 
   return uint16_t(u >> 16);
 }
 
+// 3x3 / stride 1 / pad 1 convolution as an implicit GEMM (NHWC activations, [Cout][3][3][Cin] filters = the
+// channels_last memory of a torch Conv2d weight):
+//     out[pixel, co] = sum over (tap, ci) of  in[pixel shifted by tap, ci] * w[co, tap, ci]
+// The lane operand's 128 rows are a PATCH of output pixels: bw x bh pixels of bn images (bw * bh * bn == 128).  For
+// reduction block kb = tap * cpb + cb the patch's input values are ONE 4-D TMA box {64 channels, bw, bh, bn} at
+// (cb * 64, w0 + dw[tap], h0 + dh[tap], n0): out-of-bounds coordinates (the padding, ragged patches) are zero-filled by
+// the TMA unit, and the box lands in shared memory as the same [128 rows x 128 bytes] swizzled image a 2-D box would
+// write, so the MMA side does not know it is a convolution.  The column operand is the filter matrix [Cout][9 * Cin]:
+//   forward  K-major,  k-block kb starts at column kb * 64 (tap-major, then ci)
+//   dgrad    the roles of Cin / Cout swap and the taps flip: filters are read MN-major (reduction = co, outer):
+//            one [64 co x 64 ci] box per 64 output columns at (tap * Cin + ci0, cb * 64)
+struct ConvGeom {
+  int N, H, W;               // output (== input) image batch / height / width
+  int bw, bh, bn;            // patch: bw * bh * bn == 128
+  int tiles_w, tiles_h, tiles_n;
+  int cpb;                   // 64-channel blocks of the reduction per tap
+  int col_pitch;             // dgrad: elements between taps in a filter row (= Cin of the forward layer)
+  signed char dh[9], dw[9];  // input offset of tap t relative to the output pixel
+};
+
 struct TcArgs {
+  ConvGeom conv;             // (only read by the convolution instantiations)
   int rows_a, rows_b;        // valid rows of the lane / column operand
   int tiles_a, n_tiles;      // 128-row blocks of the lane operand; output tiles in total (tile t = (t % tiles_a, t / tiles_a))
   int k_blocks;              // ceil(reduction / 64)
@@ -58,6 +79,13 @@ struct TcArgs {
   int scatter_rows;          // > 0 (reduce mode): batch row m belongs to rank m / scatter_rows — the tile is added into
                              //      THAT rank's output only, at local row m % scatter_rows (reduce-scatter epilogue)
   int* err;
+  // split-K with the finish fused into the kernel ("fix-up"): outs[0] is an fp32 workspace that is all zero on entry; the
+  // K slices add their partial tiles into it, count themselves in fix_counters[tile], and the slice that arrives last
+  // reads the sums back (they sit in L2), applies bias / activation, writes the bf16 result and re-zeroes what it read —
+  // one launch, no memset, no separate epilogue pass.  fix_out == nullptr: plain reduce mode.
+  void* fix_out;
+  int* fix_counters;
+  int fix_ldo;
 };
 
 // One GEMM operand: `rows` entries along its MN dimension (the one that survives), the reduction along the other.
@@ -202,6 +230,133 @@ BNET_TC_HD void stage_loads(const TileCoord& c, int r0, F&& ld) {
   } else {
     for (int h = 0; h < BN / 64; h++) ld(1, h * kAtomBytes, c.b_ld0 + 64 * h, r0);
   }
+}
+
+// ---- convolution: tile decode, TMA boxes of a k-block, accumulator row -> output pixel ---------------------------------
+struct ConvTile { int w0, h0, n0, b_row0; };
+
+template <int BN>
+BNET_TC_HD ConvTile conv_tile(const TcArgs& args, int t) {
+  const ConvGeom& g = args.conv;
+  int ta = t % args.tiles_a;
+  ConvTile c;
+  c.b_row0 = (t / args.tiles_a) * BN;
+  c.w0 = (ta % g.tiles_w) * g.bw;
+  ta /= g.tiles_w;
+  c.h0 = (ta % g.tiles_h) * g.bh;
+  c.n0 = (ta / g.tiles_h) * g.bn;
+  return c;
+}
+
+// lda(byte offset, c0 = channel, c1 = w, c2 = h, c3 = n): the patch box;  ldb(byte offset, c0, c1): the filter boxes
+template <int BN, bool kBMn, class FA, class FB>
+BNET_TC_HD void conv_stage_loads(const TcArgs& args, const ConvTile& c, int kb, FA&& lda, FB&& ldb) {
+  const ConvGeom& g = args.conv;
+  const int tap = kb / g.cpb, cb = kb - tap * g.cpb;
+  lda(0, cb * kBK, c.w0 + g.dw[tap], c.h0 + g.dh[tap], c.n0);
+  if (!kBMn) {
+    ldb(0, kb * kBK, c.b_row0);
+  } else {
+    for (int h = 0; h < BN / 64; h++) ldb(h * kAtomBytes, tap * g.col_pitch + c.b_row0 + 64 * h, cb * kBK);
+  }
+}
+
+// accumulator row r (0..127) of a patch -> row of the [N*H*W, C] output matrix, or -1 when the pixel is outside the image
+BNET_TC_HD long long conv_out_row(const TcArgs& args, const ConvTile& c, int r) {
+  const ConvGeom& g = args.conv;
+  const int wi = r % g.bw, hi = (r / g.bw) % g.bh, ni = r / (g.bw * g.bh);
+  const int w = c.w0 + wi, h = c.h0 + hi, n = c.n0 + ni;
+  if (w >= g.W || h >= g.H || n >= g.N) return -1;
+  return ((long long)n * g.H + h) * g.W + w;
+}
+
+// the patch that wastes the fewest accumulator rows (ties: the widest), bw * bh * bn == 128, all powers of two
+inline void conv_pick_patch(int N, int H, int W, int* bw, int* bh, int* bn) {
+  long long best = -1;
+  for (int w = 1; w <= 128; w *= 2)
+    for (int h = 1; w * h <= 128; h *= 2) {
+      const int n = 128 / (w * h);
+      if (w > 256 || h > 256 || n > 256) continue;
+      const long long tiles = (long long)((W + w - 1) / w) * ((H + h - 1) / h) * ((N + n - 1) / n);
+      if (best < 0 || tiles < best || (tiles == best && w > *bw)) { best = tiles; *bw = w; *bh = h; *bn = n; }
+    }
+}
+
+// What cuTensorMapEncodeTiled is told about an NHWC activation: dims {C, W, H, N}, boxes {64, bw, bh, bn}
+struct MapDesc4 { const void* ptr; int C, W, H, N; int bw, bh, bn; };
+
+struct ConvProblem {
+  BnetTcPlan plan;
+  TcArgs args;
+  MapDesc4 x_map;
+  MapDesc w_map;
+  bool dgrad;
+};
+
+// out[N,H,W,Cn] = act(conv3x3(x[N,H,W,Cred], w) + bias), stride 1, pad 1 (pure: no CUDA calls).
+//   dgrad == 0: w = [Cn][3][3][Cred]  (forward)
+//   dgrad == 1: w = [Cred][3][3][Cn]  (the FORWARD layer's filter read MN-major with flipped taps: x is the output gradient,
+//               out the input gradient; Cred = the forward layer's Cout, Cn its Cin)
+inline const char* setup_conv(const void* x, const void* w, const void* bias, void* out, int N, int H, int W, int Cred, int Cn, int act,
+                              int dgrad, int* err_dev, int sm_count, ConvProblem* cp) {
+  if (N < 1 || H < 1 || W < 1 || Cred < 64 || Cred % 64 || Cn < 8 || Cn % 8)
+    return "conv3x3: the reduction channels must be a multiple of 64 and the output channels a multiple of 8";
+  if (dgrad && Cn % 64) return "conv3x3 dgrad: the input channels must be a multiple of 64";
+  if (!err_dev) return "err_dev is required";
+  if ((long long)N * H * W > 0x7fffffffLL) return "too many pixels for one launch";
+  cp->dgrad = dgrad != 0;
+  TcArgs& a = cp->args;
+  memset(&a, 0, sizeof(a));
+  ConvGeom& g = a.conv;
+  g.N = N; g.H = H; g.W = W;
+  conv_pick_patch(N, H, W, &g.bw, &g.bh, &g.bn);
+  g.tiles_w = (W + g.bw - 1) / g.bw;
+  g.tiles_h = (H + g.bh - 1) / g.bh;
+  g.tiles_n = (N + g.bn - 1) / g.bn;
+  g.cpb = Cred / 64;
+  g.col_pitch = Cn;
+  for (int t = 0; t < 9; t++) {
+    const int kh = t / 3, kw = t % 3;
+    g.dh[t] = (signed char)(dgrad ? 1 - kh : kh - 1);
+    g.dw[t] = (signed char)(dgrad ? 1 - kw : kw - 1);
+  }
+  const int tiles_a = g.tiles_w * g.tiles_h * g.tiles_n;
+  const int bn_cols = (Cn >= 256 && (long long)tiles_a * ((Cn + 255) / 256) >= sm_count) ? 256 : (Cn > 64 ? 128 : 64);
+  BnetTcPlan& p = cp->plan;
+  memset(&p, 0, sizeof(p));
+  p.swap = 0;
+  p.bn = bn_cols;
+  p.stages = stages_for(bn_cols);
+  p.grid_x = (Cn + bn_cols - 1) / bn_cols;
+  p.grid_y = tiles_a;
+  p.grid_z = 1;
+  p.k_blocks = 9 * g.cpb;
+  p.k_per_split = p.k_blocks;
+  p.smem_bytes = p.stages * (kABytes + bn_cols * kBK * 2) + 1024 + (2 * p.stages + 4) * 8 + 16;
+  const long long n_tiles = (long long)p.grid_x * p.grid_y;
+  if (n_tiles > 0x7fffffffLL) return "too many tiles";
+  p.ctas = n_tiles < sm_count ? (int)n_tiles : sm_count;
+  a.rows_a = N * H * W;
+  a.rows_b = Cn;
+  a.tiles_a = tiles_a;
+  a.n_tiles = (int)n_tiles;
+  a.k_blocks = p.k_blocks;
+  a.k_per_split = p.k_per_split;
+  a.ldo = Cn;
+  a.act = act;
+  a.bias = static_cast<const uint16_t*>(bias);
+  a.outs[0] = out;
+  a.n_outs = 1;
+  a.err = err_dev;
+  cp->x_map = MapDesc4{x, Cred, W, H, N, g.bw, g.bh, g.bn};
+  MapDesc& wd = cp->w_map;
+  wd.ptr = w;
+  wd.pitch_elems = 9LL * (dgrad ? Cn : Cred);
+  wd.dim0 = wd.pitch_elems;
+  wd.dim1 = dgrad ? Cred : Cn;
+  wd.box0 = kBK;
+  wd.box1 = dgrad ? kBK : bn_cols;
+  return nullptr;
 }
 
 // One epilogue step of one thread: 16 consecutive accumulator columns (j0 .. j0+15) of accumulator row i_glob.

@@ -116,6 +116,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" :: "l"(map) : "memory");
 }
@@ -202,12 +207,14 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // boundaries, and the accumulator is double-buffered in TMEM (2 x BN columns): the epilogue of tile t drains one half
 // while the MMAs of tile t+1 fill the other.  With gridDim.x == n_tiles every CTA simply does one tile.
 // kAMn / kBMn: the lane / column operand is MN-major (reduction dimension outer) instead of K-major
-template <int BN, int kStages, bool kSwap, bool kReduce, bool kAMn, bool kBMn>
+// kConv: the lane operand is a 3x3 convolution's input patch, loaded as 4-D TMA boxes (tc_body.cuh::ConvGeom)
+template <int BN, int kStages, bool kSwap, bool kReduce, bool kAMn, bool kBMn, bool kConv = false>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_linear_kernel(const __grid_constant__ TcBatchMaps maps_batch, const __grid_constant__ CUtensorMap map_feat, const TcArgs args) {
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M = 128");
   static_assert((BN & (BN - 1)) == 0 && BN >= 32, "TMEM allocations are powers of two >= 32 columns");
   static_assert(!kBMn || BN % 64 == 0, "an MN-major operand is staged in 64-element atoms");
+  static_assert(!kConv || (!kSwap && !kAMn && !kReduce), "convolution: pixels ride the lanes, K-major patches, bf16 store");
   constexpr uint32_t kTmemCols = 2 * BN;          // two accumulator stages
   extern __shared__ uint8_t smem_raw[];
   // swizzle-128B atoms must start on 1024-byte boundaries of the shared window
@@ -218,6 +225,7 @@ tc_linear_kernel(const __grid_constant__ TcBatchMaps maps_batch, const __grid_co
   const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kStages;
   const uint32_t acc_full0 = empty0 + 8 * kStages, acc_empty0 = acc_full0 + 16;
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint32_t* const last_slot = tmem_slot + 1;      // split-K fix-up: "this CTA's slice was the last one of the tile"
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kb_begin = blockIdx.z * args.k_per_split;
@@ -253,14 +261,22 @@ tc_linear_kernel(const __grid_constant__ TcBatchMaps maps_batch, const __grid_co
         const TileCoord tc = tile_coord<BN, kSwap>(args, t);
         const CUtensorMap* map_a = kSwap ? &map_feat : &maps_batch.m[tc.a_map];
         const CUtensorMap* map_b = kSwap ? &maps_batch.m[tc.b_map] : &map_feat;
+        ConvTile ct{};
+        if constexpr (kConv) ct = conv_tile<BN>(args, t);
         for (int i = 0; i < nkb; i++, g++) {
           const uint32_t s = g % kStages, round = g / kStages;
           if (round > 0 && !mbar_wait_wd(empty0 + 8 * s, (round - 1) & 1, args.err, 1)) { alive = false; break; }
           const uint32_t a_dst = base + s * Smem<BN>::kStageBytes, bar = full0 + 8 * s;
           mbar_expect_tx(bar, Smem<BN>::kStageBytes);
-          stage_loads<BN, kAMn, kBMn>(tc, (kb_begin + i) * kBK, [&](int operand, int offset, int c0, int c1) {
-            tma_load_2d(a_dst + (operand ? kABytes : 0) + offset, operand ? map_b : map_a, bar, c0, c1);
-          });
+          if constexpr (kConv) {
+            conv_stage_loads<BN, kBMn>(args, ct, kb_begin + i,
+                [&](int offset, int c0, int c1, int c2, int c3) { tma_load_4d(a_dst + offset, &maps_batch.m[0], bar, c0, c1, c2, c3); },
+                [&](int offset, int c0, int c1) { tma_load_2d(a_dst + kABytes + offset, &map_feat, bar, c0, c1); });
+          } else {
+            stage_loads<BN, kAMn, kBMn>(tc, (kb_begin + i) * kBK, [&](int operand, int offset, int c0, int c1) {
+              tma_load_2d(a_dst + (operand ? kABytes : 0) + offset, operand ? map_b : map_a, bar, c0, c1);
+            });
+          }
         }
       }
     }
@@ -297,12 +313,20 @@ tc_linear_kernel(const __grid_constant__ TcBatchMaps maps_batch, const __grid_co
   } else {
     // ---- epilogue: 4 warps x 32 lanes = the tile's 128 accumulator rows
     const int q = warp & 3;                        // the TMEM lane quarter this warp may read
-    const bool add_bias = args.bias != nullptr && (!kReduce || blockIdx.z == 0);
+    const bool fix = kReduce && args.fix_out != nullptr;
+    const bool add_bias = args.bias != nullptr && (!kReduce || blockIdx.z == 0) && !fix;
     uint32_t lt = 0;
     for (int t = blockIdx.x; t < args.n_tiles; t += gridDim.x, lt++) {
       const uint32_t as = lt & 1;
-      const TileCoord tc = tile_coord<BN, kSwap>(args, t);
-      const int i_glob = tc.a_row0 + q * 32 + lane;   // row of the lane operand this thread owns
+      TileCoord tc = tile_coord<BN, kSwap>(args, t);
+      int i_glob = tc.a_row0 + q * 32 + lane;         // row of the lane operand this thread owns
+      if constexpr (kConv) {
+        // the lane is a pixel of the tile's patch: its row in the [N*H*W, Cout] output, or "past the end" outside the image
+        const ConvTile ct = conv_tile<BN>(args, t);
+        const long long row = conv_out_row(args, ct, q * 32 + lane);
+        i_glob = row < 0 ? args.rows_a : (int)row;
+        tc.b_row0 = ct.b_row0;
+      }
       if (!mbar_wait_wd(acc_full0 + 8 * as, (lt >> 1) & 1, args.err, 3)) break;
       tc_fence_after_sync();
       const uint32_t tmem_d = tmem_base + as * BN;
@@ -320,6 +344,42 @@ tc_linear_kernel(const __grid_constant__ TcBatchMaps maps_batch, const __grid_co
 #pragma unroll
         for (int u = 0; u < 16; u++) acc[u] = __uint_as_float(v[u]);
         epilogue_chunk<kSwap, kReduce>(args, i_glob, tc.b_row0 + c * 16, acc, add_bias, DeviceOut{});
+      }
+      if constexpr (kReduce) {
+        if (fix) {
+          // ---- split-K fix-up: the last K slice to arrive finishes the tile (see TcArgs::fix_out)
+          __threadfence();                                                   // this thread's adds, device-wide
+          asm volatile("bar.sync 1, 128;" ::: "memory");                     // ... and those of all 128 epilogue threads
+          if (threadIdx.x == 64) *last_slot = (atomicAdd(args.fix_counters + t, 1) == (int)gridDim.z - 1) ? 1u : 0u;
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (*(volatile uint32_t*)last_slot) {
+            __threadfence();
+            TcArgs fa = args;
+            fa.outs[0] = args.fix_out;
+            fa.ldo = args.fix_ldo;
+            float* ws = static_cast<float*>(args.outs[0]);
+            if (i_glob < args.rows_a) {
+#pragma unroll 1
+              for (int c = 0; c < BN / 16; c++) {
+                const int j0 = tc.b_row0 + c * 16;
+                if (j0 >= args.rows_b) break;
+                float acc[16];
+#pragma unroll
+                for (int u = 0; u < 16; u++) {
+                  acc[u] = 0.f;
+                  if (j0 + u < args.rows_b) {
+                    float* p = kSwap ? ws + size_t(j0 + u) * args.ldo + i_glob : ws + size_t(i_glob) * args.ldo + j0 + u;
+                    acc[u] = __ldcg(p);
+                    __stcg(p, 0.f);                                           // the workspace is clean for the next call
+                  }
+                }
+                epilogue_chunk<kSwap, false>(fa, i_glob, j0, acc, args.bias != nullptr, DeviceOut{});
+              }
+            }
+            if (threadIdx.x == 64) args.fix_counters[t] = 0;
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");                     // last_slot is reused by the next tile
+        }
       }
     }
   }
@@ -374,9 +434,9 @@ bool make_map(CUtensorMap* map, const MapDesc& d) {
   return true;
 }
 
-template <int BN, int kStages, bool kSwap, bool kReduce, bool kAMn, bool kBMn>
+template <int BN, int kStages, bool kSwap, bool kReduce, bool kAMn, bool kBMn, bool kConv = false>
 int launch(const TcBatchMaps& mbatch, const CUtensorMap& mfeat, const TcArgs& a, const BnetTcPlan& p, cudaStream_t st) {
-  auto kern = tc_linear_kernel<BN, kStages, kSwap, kReduce, kAMn, kBMn>;
+  auto kern = tc_linear_kernel<BN, kStages, kSwap, kReduce, kAMn, kBMn, kConv>;
   static std::once_flag once;
   static cudaError_t attr_rc = cudaSuccess;
   const int smem = p.smem_bytes;
@@ -405,13 +465,16 @@ int sm_count() {
 // tested on the CPU); here the map descriptions are encoded and the instantiation is picked.
 int run(const Operand& batch, const Operand& feat, int red, const void* bias, void* const* outs, int n_outs, int multicast,
         bool reduce, int ldo, int act, int splits, int* err_dev, void* stream, const void* const* shards = nullptr,
-        int n_shards = 0, int scatter_ranks = 0) {
+        int n_shards = 0, int scatter_ranks = 0, void* fix_out = nullptr, int* fix_counters = nullptr, int fix_ldo = 0) {
   Problem pr;
   if (const char* e = setup_problem(batch, feat, red, bias, outs, n_outs, multicast, reduce, ldo, act, splits, err_dev, shards,
                                     n_shards, scatter_ranks, sm_count(), &pr)) {
     g_err = e;
     return -1;
   }
+  pr.args.fix_out = fix_out;
+  pr.args.fix_counters = fix_counters;
+  pr.args.fix_ldo = fix_ldo;
   TcBatchMaps mbatch;
   CUtensorMap mfeat;
   for (int r = 0; r < pr.n_batch_maps; r++)
@@ -436,6 +499,47 @@ int run(const Operand& batch, const Operand& feat, int red, const void* bias, vo
   BNET_TC_CASE(128, false, false, true, true)   BNET_TC_CASE(256, false, false, true, true)
 #undef BNET_TC_CASE
   g_err = "no kernel for this plan";
+  return -1;
+}
+
+
+// 4-D map over an NHWC activation {C, W, H, N}: boxes of {64 channels, bw, bh, bn}, 128-byte swizzle, zero fill
+bool make_map_nhwc(CUtensorMap* map, const MapDesc4& d) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { g_err = "the CUDA driver does not export cuTensorMapEncodeTiled"; return false; }
+  if ((reinterpret_cast<uintptr_t>(d.ptr) & 15) || d.C % 8) { g_err = "activations must be 16-byte aligned with C a multiple of 8"; return false; }
+  const cuuint64_t dims[4] = {cuuint64_t(d.C), cuuint64_t(d.W), cuuint64_t(d.H), cuuint64_t(d.N)};
+  const cuuint64_t strides[3] = {cuuint64_t(d.C) * 2, cuuint64_t(d.W) * d.C * 2, cuuint64_t(d.H) * d.W * d.C * 2};
+  const cuuint32_t box[4] = {cuuint32_t(kBK), cuuint32_t(d.bw), cuuint32_t(d.bh), cuuint32_t(d.bn)};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d.ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { g_err = "cuTensorMapEncodeTiled (NHWC) failed: " + std::to_string(int(r)); return false; }
+  return true;
+}
+
+// the index logic is tc_body.cuh::setup_conv (pure, emulated on the CPU by tc_emu_test); here the maps are encoded and the
+// instantiation is picked
+int run_conv(const void* x, const void* w, const void* bias, void* out, int N, int H, int W, int Cred, int Cn, int act, int dgrad,
+             int* err_dev, void* stream) {
+  ConvProblem cp;
+  if (const char* e = setup_conv(x, w, bias, out, N, H, W, Cred, Cn, act, dgrad, err_dev, sm_count(), &cp)) {
+    g_err = e;
+    return -1;
+  }
+  TcBatchMaps mbatch;
+  CUtensorMap mfeat;
+  if (!make_map_nhwc(&mbatch.m[0], cp.x_map)) return -1;
+  if (!make_map(&mfeat, cp.w_map)) return -1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const BnetTcPlan& p = cp.plan;
+#define BNET_CONV_CASE(BN, BMN) \
+  if (p.bn == BN && cp.dgrad == BMN) return launch<BN, stages_for(BN), false, false, false, BMN, true>(mbatch, mfeat, cp.args, p, st);
+  BNET_CONV_CASE(64, false) BNET_CONV_CASE(128, false) BNET_CONV_CASE(256, false)
+  BNET_CONV_CASE(64, true)  BNET_CONV_CASE(128, true)  BNET_CONV_CASE(256, true)
+#undef BNET_CONV_CASE
+  g_err = "no convolution kernel for this plan";
   return -1;
 }
 
@@ -475,6 +579,17 @@ BNET_API int bnet_tc_linear_reduce(const void* x, const void* w, const void* bia
              err_dev, stream);
 }
 
+// Split-K with the finish inside the kernel: `ws` is an fp32 [M, N] workspace and `counters` one int per output tile
+// (bnet_tc_plan: grid_x * grid_y), BOTH all zero on entry — the kernel leaves them all zero again, so they are allocated
+// and cleared once.  out = act(x . w^T + bias) in bf16, one launch.
+BNET_API int bnet_tc_linear_splitk(const void* x, const void* w, const void* bias, void* out, float* ws, int* counters, int M, int N,
+                                   int K, int ldx, int ldw, int ldo, int act, int splits, int* err_dev, void* stream) {
+  void* outs[1] = {ws};
+  if (!ws || !counters) { g_err = "split-K needs a workspace and tile counters"; return -1; }
+  return run(Operand{x, M, ldx, 0}, Operand{w, N, ldw, 0}, K, bias, outs, 1, 0, true, N, act, splits, err_dev, stream, nullptr, 0, 0,
+             out, counters, ldo);
+}
+
 // dx[M, K] = gy[M, N] . w[N, K]: the reduction runs over N, so w is read with its rows as the reduction (MN-major)
 BNET_API int bnet_tc_linear_dgrad(const void* gy, const void* w, void* dx, int M, int N, int K, int ldgy, int ldw, int lddx,
                                   int* err_dev, void* stream) {
@@ -510,4 +625,18 @@ BNET_API int bnet_tc_linear_reduce_scatter(const void* x, const void* w, const v
                                            int N, int K, int ldx, int ldw, int ldo, int splits, int* err_dev, void* stream) {
   return run(Operand{x, M, ldx, 0}, Operand{w, N, ldw, 0}, K, bias, outs, n_ranks, 0, true, ldo, BNET_TC_ACT_NONE, splits, err_dev,
              stream, nullptr, 0, n_ranks);
+}
+
+// 3x3 / stride 1 / pad 1 convolution on the same kernel (implicit GEMM: 4-D TMA boxes of the NHWC activation, the padding
+// is the TMA unit's zero fill), bias and ReLU in the epilogue.  bf16 NHWC in and out, filters as torch stores a
+// channels_last Conv2d weight ([Cout][3][3][Cin]).  Cin must be a multiple of 64, Cout of 8.
+BNET_API int bnet_tc_conv3x3(const void* x, const void* w, const void* bias, void* out, int N, int H, int W, int Cin, int Cout,
+                             int act, int* err_dev, void* stream) {
+  return run_conv(x, w, bias, out, N, H, W, Cin, Cout, act, 0, err_dev, stream);
+}
+// dx[N,H,W,Cin] = conv3x3 of gy[N,H,W,Cout] with the same filter w[Cout][3][3][Cin], taps flipped, filter read MN-major
+// (no transposed / rotated copy of the filter is made).  Cout and Cin must be multiples of 64.
+BNET_API int bnet_tc_conv3x3_dgrad(const void* gy, const void* w, void* dx, int N, int H, int W, int Cin, int Cout, int* err_dev,
+                                   void* stream) {
+  return run_conv(gy, w, nullptr, dx, N, H, W, Cout, Cin, BNET_TC_ACT_NONE, 1, err_dev, stream);
 }

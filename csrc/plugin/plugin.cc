@@ -12,6 +12,8 @@
 //   * v5+ connect/accept never block on the peer: they return *comm == NULL
 //     until the connection is ready
 #include <stdlib.h>
+
+#include <deque>
 #include <string.h>
 
 #include "bnet/nccl_net_abi.h"
@@ -31,8 +33,10 @@ const char kName[] = "BNet";
 struct PropStrings {
   std::string name, pci;
 };
-std::vector<PropStrings>& prop_cache() {
-  static std::vector<PropStrings>* v = new std::vector<PropStrings>();
+// (a deque: growing it never moves the strings NCCL already holds pointers into — short names live INSIDE the
+//  std::string object, so a reallocating vector would leave NCCL with dangling name pointers)
+std::deque<PropStrings>& prop_cache() {
+  static std::deque<PropStrings>* v = new std::deque<PropStrings>();
   return *v;
 }
 std::mutex g_prop_mu;
@@ -43,8 +47,8 @@ ncclResult_t fill_common(int dev, DeviceProps* p, char** name, char** pci) {
   std::lock_guard<std::mutex> lk(g_prop_mu);
   auto& c = prop_cache();
   if ((int)c.size() <= dev) c.resize(dev + 1);
-  c[dev].name = p->name;
-  c[dev].pci = p->pci_path;
+  if (c[dev].name != p->name) c[dev].name = p->name;          // (unchanged strings keep their buffers)
+  if (c[dev].pci != p->pci_path) c[dev].pci = p->pci_path;
   *name = const_cast<char*>(c[dev].name.c_str());
   *pci = c[dev].pci.empty() ? nullptr : const_cast<char*>(c[dev].pci.c_str());
   return ncclSuccess;
@@ -64,6 +68,9 @@ void tune_nccl_env() {
       {"NCCL_PROTO", "Simple"},
       {"NCCL_BUFFSIZE", "33554432"},
       {"NCCL_MIN_NCHANNELS", "16"},
+      // our "NIC" is the GPU's own NVLink port: device pointers are welcome wherever NCCL's topology puts the device
+      {"NCCL_NET_GDR_LEVEL", "SYS"},
+      {"NCCL_NET_GDR_READ", "1"},
   };
   for (const KV& d : defaults)
     if (!getenv(d.k)) {

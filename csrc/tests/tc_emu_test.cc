@@ -257,7 +257,125 @@ static void backward(int M, int N, int K) {
   CHECK(bad == 0, "wgrad M=%d N=%d K=%d: %d wrong", M, N, K, bad);
 }
 
+// ---- convolution (implicit GEMM): 4-D boxes with zero fill, the same MMA / TMEM emulation -------------------------------
+static void tma_box4(const MapDesc4& d, int c0, int c1, int c2, int c3, uint16_t* dst) {
+  const uint16_t* src = static_cast<const uint16_t*>(d.ptr);
+  size_t o = 0;
+  for (int n = 0; n < d.bn; n++)
+    for (int h = 0; h < d.bh; h++)
+      for (int w = 0; w < d.bw; w++)
+        for (int c = 0; c < kBK; c++) {
+          const long long cc = c0 + c, ww = c1 + w, hh = c2 + h, nn = c3 + n;
+          const bool in = cc >= 0 && cc < d.C && ww >= 0 && ww < d.W && hh >= 0 && hh < d.H && nn >= 0 && nn < d.N;
+          dst[o++] = in ? src[((nn * d.H + hh) * d.W + ww) * d.C + cc] : 0;
+        }
+}
+
+template <int BN, bool kBMn>
+static void run_conv_kernel(const ConvProblem& cp, const HostOut& out) {
+  const TcArgs& args = cp.args;
+  const BnetTcPlan& p = cp.plan;
+  std::vector<uint16_t> stage_a(kABytes / 2), stage_b(BN * kBK);
+  std::vector<float> tmem(size_t(kBM) * BN);
+  CHECK(args.conv.bw * args.conv.bh * args.conv.bn == kBM, "patch %d x %d x %d", args.conv.bw, args.conv.bh, args.conv.bn);
+  for (int cta = 0; cta < p.ctas; cta++)
+    for (int t = cta; t < args.n_tiles; t += p.ctas) {
+      const ConvTile ct = conv_tile<BN>(args, t);
+      std::fill(tmem.begin(), tmem.end(), 0.f);
+      for (int kb = 0; kb < args.k_blocks; kb++) {
+        std::fill(stage_a.begin(), stage_a.end(), uint16_t(0x7fc0));
+        std::fill(stage_b.begin(), stage_b.end(), uint16_t(0x7fc0));
+        int bytes = 0;
+        conv_stage_loads<BN, kBMn>(args, ct, kb,
+            [&](int offset, int c0, int c1, int c2, int c3) { tma_box4(cp.x_map, c0, c1, c2, c3, stage_a.data() + offset / 2); bytes += kABytes; },
+            [&](int offset, int c0, int c1) { tma_box(cp.w_map, c0, c1, stage_b.data() + offset / 2); bytes += cp.w_map.box0 * cp.w_map.box1 * 2; });
+        CHECK(bytes == kABytes + BN * kBK * 2, "conv expect_tx bytes %d", bytes);
+        for (int i = 0; i < kBM; i++)
+          for (int j = 0; j < BN; j++) {
+            float s = 0.f;
+            for (int k = 0; k < kBK; k++) s += stage_at(stage_a.data(), false, i, k) * stage_at(stage_b.data(), kBMn, j, k);
+            tmem[size_t(i) * BN + j] += s;
+          }
+      }
+      for (int r = 0; r < kBM; r++) {
+        const long long row = conv_out_row(args, ct, r);
+        const int i_glob = row < 0 ? args.rows_a : (int)row;
+        for (int c = 0; c < BN / 16; c++) {
+          float acc[16];
+          for (int u = 0; u < 16; u++) acc[u] = tmem[size_t(r) * BN + c * 16 + u];
+          epilogue_chunk<false, false>(args, i_glob, ct.b_row0 + c * 16, acc, args.bias != nullptr, out);
+        }
+      }
+    }
+}
+
+static void conv(int N, int H, int W, int Cin, int Cout, bool relu, int sms) {
+  // x [N,H,W,Cin], w [Cout][3][3][Cin], y [N,H,W,Cout]
+  Mat x(N * H * W, Cin), w(Cout, 9 * Cin), b(1, Cout);
+  std::vector<uint16_t> yv(size_t(N) * H * W * Cout + 16, 0xdead);
+  uint16_t* y = yv.data();
+  while (reinterpret_cast<uintptr_t>(y) & 15) y++;
+  int err = 0;
+  ConvProblem cp;
+  const char* e = setup_conv(x.ptr(), w.ptr(), b.ptr(), y, N, H, W, Cin, Cout, relu ? BNET_TC_ACT_RELU : 0, 0, &err, sms, &cp);
+  CHECK(e == nullptr, "conv setup: %s", e ? e : "");
+  if (e) return;
+  if (cp.plan.bn == 64) run_conv_kernel<64, false>(cp, HostOut{});
+  else if (cp.plan.bn == 128) run_conv_kernel<128, false>(cp, HostOut{});
+  else run_conv_kernel<256, false>(cp, HostOut{});
+  int bad = 0;
+  for (int n = 0; n < N; n++)
+    for (int h = 0; h < H; h++)
+      for (int ww = 0; ww < W; ww++)
+        for (int co = 0; co < Cout; co++) {
+          double r = b.at(0, co);
+          for (int kh = 0; kh < 3; kh++)
+            for (int kw = 0; kw < 3; kw++) {
+              const int hh = h + kh - 1, w2 = ww + kw - 1;
+              if (hh < 0 || hh >= H || w2 < 0 || w2 >= W) continue;
+              for (int ci = 0; ci < Cin; ci++) r += double(x.at((n * H + hh) * W + w2, ci)) * w.at(co, (kh * 3 + kw) * Cin + ci);
+            }
+          if (relu && r < 0) r = 0;
+          if (!close(bf16_to_f32(y[(size_t(n * H + h) * W + ww) * Cout + co]), r)) bad++;
+        }
+  CHECK(bad == 0, "conv fwd N=%d %dx%d %d->%d (patch %dx%dx%d bn %d ctas %d): %d wrong", N, H, W, Cin, Cout, cp.args.conv.bw,
+        cp.args.conv.bh, cp.args.conv.bn, cp.plan.bn, cp.plan.ctas, bad);
+  // dgrad: gy [N,H,W,Cout] -> dx [N,H,W,Cin] with the same filter
+  if (Cout % 64 || Cin % 64) return;
+  Mat gy(N * H * W, Cout);
+  std::vector<uint16_t> dv(size_t(N) * H * W * Cin + 16, 0xdead);
+  uint16_t* dx = dv.data();
+  while (reinterpret_cast<uintptr_t>(dx) & 15) dx++;
+  e = setup_conv(gy.ptr(), w.ptr(), nullptr, dx, N, H, W, Cout, Cin, 0, 1, &err, sms, &cp);
+  CHECK(e == nullptr, "conv dgrad setup: %s", e ? e : "");
+  if (e) return;
+  if (cp.plan.bn == 64) run_conv_kernel<64, true>(cp, HostOut{});
+  else if (cp.plan.bn == 128) run_conv_kernel<128, true>(cp, HostOut{});
+  else run_conv_kernel<256, true>(cp, HostOut{});
+  bad = 0;
+  for (int n = 0; n < N; n++)
+    for (int h = 0; h < H; h++)
+      for (int ww = 0; ww < W; ww++)
+        for (int ci = 0; ci < Cin; ci++) {
+          double r = 0;
+          for (int kh = 0; kh < 3; kh++)
+            for (int kw = 0; kw < 3; kw++) {
+              const int ho = h - kh + 1, wo = ww - kw + 1;      // the output pixel that read x[h, w] through tap (kh, kw)
+              if (ho < 0 || ho >= H || wo < 0 || wo >= W) continue;
+              for (int co = 0; co < Cout; co++) r += double(gy.at((n * H + ho) * W + wo, co)) * w.at(co, (kh * 3 + kw) * Cin + ci);
+            }
+          if (!close(bf16_to_f32(dx[(size_t(n * H + h) * W + ww) * Cin + ci]), r)) bad++;
+        }
+  CHECK(bad == 0, "conv dgrad N=%d %dx%d %d->%d (bn %d): %d wrong", N, H, W, Cin, Cout, cp.plan.bn, bad);
+}
+
 int main() {
+  // 3x3 convolutions: exact patches, ragged patches (7x7, 14x14 with odd batch), several images per patch, persistent CTAs
+  conv(2, 8, 16, 64, 64, true, 148);
+  conv(3, 7, 7, 64, 128, false, 3);
+  conv(1, 14, 14, 128, 64, true, 2);
+  conv(5, 4, 4, 64, 72, true, 148);
+  conv(2, 10, 6, 64, 320, false, 1);
   // forward: both orientations, ragged extents, row pitches, one tile per CTA and persistent (few "SMs")
   forward(32, 256, 512, true, true, 148, 0);
   forward(48, 200, 264, true, false, 148, 16);

@@ -48,6 +48,13 @@ int bnet_tc_plan(int M, int N, int K, int reduce, int splits, BnetTcPlan* plan);
 int bnet_tc_linear(const void* x, const void* w, const void* bias, void* out, int M, int N, int K, int ldx, int ldw,
                    int ldo, int act, int* err_dev, void* stream);
 
+/* Split-K for weight-streaming (small batch) layers with the finish fused into the kernel: K is cut into `splits` slices
+ * so that every SM streams weights; partial tiles meet as fp32 adds in `ws` ([M, N] floats), and the slice that arrives
+ * last at a tile (counted in `counters`, one int per output tile) applies bias / activation and writes the bf16 result.
+ * `ws` and `counters` must be all zero on entry and are all zero again on exit.  One launch. */
+int bnet_tc_linear_splitk(const void* x, const void* w, const void* bias, void* out, float* ws, int* counters, int M, int N, int K,
+                          int ldx, int ldw, int ldo, int act, int splits, int* err_dev, void* stream);
+
 /* outs: n_outs device pointers to fp32 [M, ldo] buffers (this rank's mapping of every rank's output), or ONE multicast
  * pointer when multicast != 0.  splits > 1 additionally splits K over grid.z (the adds make it free). */
 int bnet_tc_linear_reduce(const void* x, const void* w, const void* bias, void* const* outs, int n_outs, int multicast,
@@ -71,6 +78,16 @@ int bnet_tc_linear_dgrad(const void* gy, const void* w, void* dx, int M, int N, 
                          void* stream);
 int bnet_tc_linear_wgrad(const void* gy, const void* x, void* dw, int M, int N, int K, int ldgy, int ldx, int lddw, int* err_dev,
                          void* stream);
+
+/* 3x3 / stride 1 / pad 1 convolution as an implicit GEMM on the same kernel: the 128 accumulator rows of a tile are a
+ * patch of output pixels whose (shifted) inputs arrive as 4-D TMA boxes of the NHWC activation — padding = the TMA unit's
+ * zero fill — and bias + ReLU are applied from TMEM.  bf16 NHWC activations, filters [Cout][3][3][Cin] (the memory of a
+ * channels_last torch Conv2d weight).  Cin % 64 == 0, Cout % 8 == 0.  dgrad reads the SAME filter MN-major with flipped
+ * taps (Cin % 64 == 0 and Cout % 64 == 0). */
+int bnet_tc_conv3x3(const void* x, const void* w, const void* bias, void* out, int N, int H, int W, int Cin, int Cout, int act,
+                    int* err_dev, void* stream);
+int bnet_tc_conv3x3_dgrad(const void* gy, const void* w, void* dx, int N, int H, int W, int Cin, int Cout, int* err_dev,
+                          void* stream);
 
 /* The 64-bit shared-memory matrix descriptor (K-major, 128-byte swizzle) and the 32-bit instruction descriptor
  * (bf16 x bf16 -> fp32) the kernel issues, exposed so a host test can compare them with the CuTe definitions. */

@@ -300,7 +300,11 @@ def test_tc_linear_python_plan_and_gating(monkeypatch):
     from bagua_net_b200.ops import tc_linear
 
     monkeypatch.delenv("BNET_TC", raising=False)
-    assert not tc_linear.enabled()                       # unvalidated on hardware: strictly opt-in
+    assert tc_linear.enabled()                           # validated on B200 (profiles/r2): on unless BNET_TC=0 ...
+    monkeypatch.setenv("BNET_TC", "0")
+    assert not tc_linear.enabled()
+    monkeypatch.delenv("BNET_TC", raising=False)
+    assert not tc_linear.trusted()                       # ... and still only trusted after its self-check passed on a GPU
     p = tc_linear.plan(32, 4096, 25088)                  # VGG16 fc1 at the flagship batch: weights fill the TMEM lanes
     assert p["swap"] == 1 and p["bn"] == 32 and p["grid_y"] == 32 and p["k_blocks"] == 392
     p = tc_linear.plan(4096, 4096, 4096, reduce=True, splits=4)
