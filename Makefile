@@ -26,7 +26,7 @@ LDFLAGS   := -shared -cudart static -Xcompiler -pthread -ldl -lrt
 
 HOST_SRCS := csrc/core/common.cc csrc/core/netif.cc csrc/core/telemetry.cc csrc/core/engine.cc \
              csrc/transport/tcp_threads.cc csrc/transport/tcp_async.cc csrc/transport/nvl.cc \
-             csrc/cuda/cuda_iface.cc csrc/capi.cc
+             csrc/cuda/cuda_iface.cc csrc/coll/transport_ring.cc csrc/capi.cc
 CU_SRCS   := $(wildcard csrc/cuda/*.cu)
 
 HOST_OBJS := $(patsubst csrc/%.cc,$(BUILD)/%.o,$(HOST_SRCS))
@@ -50,7 +50,7 @@ $(BUILD)/%.cu.o: csrc/%.cu
 
 $(PLUGINX_OBJ): csrc/plugin/plugin.cc
 	@mkdir -p $(dir $@)
-	$(CXX) $(CXXFLAGS) -DBNET_EXPORT_V9_V10 -c $< -o $@
+	$(CXX) $(CXXFLAGS) -DBNET_EXPORT_V9_V10 -MMD -MP -c $< -o $@
 
 # (link to a temporary name, then rename: a process that dlopen()s the library while another one is
 #  rebuilding it never sees a half-written file)
@@ -138,7 +138,8 @@ uninstall:
 clean:
 	rm -rf $(BUILD) $(OUT)/*.so
 
--include $(HOST_OBJS:.o=.d) $(CU_OBJS:.o=.d)
+# (the two plugin objects too: a header change that moves a vtable slot must rebuild the ABI shims with it)
+-include $(HOST_OBJS:.o=.d) $(CU_OBJS:.o=.d) $(PLUGIN_OBJ:.o=.d) $(PLUGINX_OBJ:.o=.d)
 .PHONY: default test bench sass tar clean emu-asan install uninstall
 
 # ---- sanitizer builds of the host engine: `make tsan` / `make asan` rebuild every host

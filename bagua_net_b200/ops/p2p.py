@@ -71,3 +71,25 @@ class P2PExecutor:
     def run(self, op: str, src: torch.Tensor, dst: torch.Tensor, scale: float | None = None):
         self.wait(self.submit(op, src, dst, scale=scale))
         return dst
+
+    MODES = {"default": -1, "msg": 0, "persistent": 1, "oneshot": 2, "ce": 3}
+
+    def run_mode(self, mode: str, op: str, src: torch.Tensor, dst: torch.Tensor, scale: float = 1.0):
+        """The same job through an explicit executor mode: "msg" = one launch per message (what NCCL's isend uses),
+        "persistent" = resident cluster queues, "oneshot" = one launch per chunk, "ce" = DMA copy engines."""
+        if not hasattr(self.lib, "_bnet_mode_decl"):
+            self.lib.bnet_exec_op_mode.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+                                                   C.c_uint64, C.c_float, C.POINTER(C.c_int)]
+            self.lib._bnet_mode_decl = True
+        torch.cuda.current_stream(self.device).synchronize()
+        self.seq += 1
+        slot = self.slot
+        self.slot = (self.slot + 1) % 64
+        base = self.flags.data_ptr() + slot * self.MAX_CHUNKS * 8
+        n = C.c_int(0)
+        rc = self.lib.bnet_exec_op_mode(self.device, self.MODES[mode], OPS[op], C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()),
+                                        src.numel() * src.element_size(), C.c_void_p(base), self.seq, float(scale), C.byref(n))
+        if rc != 0:
+            raise RuntimeError(f"bnet_exec_op_mode({mode}, {op}) failed")
+        self.wait((slot, n.value, self.seq))
+        return dst

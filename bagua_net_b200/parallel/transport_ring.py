@@ -1,0 +1,126 @@
+"""All-reduce that rides the transport (csrc/coll/transport_ring.cc): a ring over the plugin's own connections whose
+reduce-scatter hops are *fused isends* — the sending GPU's kernel accumulates into the next rank's buffer while it moves
+the data over NVLink (``red.global.add``), so there is no reduce kernel and no staging buffer anywhere.
+
+    ring = TransportRing()                      # every rank; uses torch.distributed to pass the connection handles
+    buf = ring.buffer(numel, torch.bfloat16)    # device memory registered with both connections
+    ring.all_reduce(buf)                        # in-place sum
+
+The reference only moves bytes for NCCL; this is the collective BASELINE.json's north star asks
+to ride the new transport, next to the symmetric-heap collectives of ``SymmComm``."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from ..utils.native import load
+
+HANDLE_BYTES = 128
+_DT = {torch.float32: 0, torch.bfloat16: 1}
+
+
+def _lib():
+    lib = load()
+    if not hasattr(lib, "_tring_decl"):
+        vp, i = C.c_void_p, C.c_int
+        lib.bnet_tring_create.argtypes = [i, i, i, vp, C.POINTER(vp)]
+        lib.bnet_tring_connect.argtypes = [vp, vp, i]
+        lib.bnet_tring_register.argtypes = [vp, vp, C.c_size_t]
+        lib.bnet_tring_allreduce.argtypes = [vp, vp, C.c_size_t, i, C.c_size_t, i, i]
+        lib.bnet_tring_stats.argtypes = [vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+        lib.bnet_tring_destroy.argtypes = [vp]
+        lib.bnet_tring_last_error.argtypes = [vp]
+        lib.bnet_tring_last_error.restype = C.c_char_p
+        lib.bnet_tring_transport.argtypes = [vp]
+        lib.bnet_tring_transport.restype = C.c_char_p
+        lib._tring_decl = True
+    return lib
+
+
+class RingCore:
+    """The native ring without torch: callers exchange the 128-byte handles themselves (used by the CPU tests)."""
+
+    def __init__(self, rank: int, world: int, net_dev: int = 0):
+        self.lib = _lib()
+        self.rank, self.world = rank, world
+        self._h = C.c_void_p()
+        self._handle = C.create_string_buffer(HANDLE_BYTES)
+        if self.lib.bnet_tring_create(rank, world, net_dev, self._handle, C.byref(self._h)) != 0:
+            raise RuntimeError("bnet_tring_create failed")
+
+    @property
+    def handle(self) -> bytes:
+        return bytes(self._handle.raw)
+
+    def _err(self) -> str:
+        return self.lib.bnet_tring_last_error(self._h).decode()
+
+    def connect(self, next_handle: bytes, timeout_ms: int = 30000):
+        buf = C.create_string_buffer(next_handle, HANDLE_BYTES)
+        if self.lib.bnet_tring_connect(self._h, buf, timeout_ms) != 0:
+            raise RuntimeError(f"ring connect: {self._err()}")
+
+    @property
+    def transport(self) -> str:
+        return self.lib.bnet_tring_transport(self._h).decode()
+
+    def register(self, ptr: int, nbytes: int):
+        if self.lib.bnet_tring_register(self._h, C.c_void_p(ptr), nbytes) != 0:
+            raise RuntimeError(f"ring register: {self._err()}")
+
+    def all_reduce(self, ptr: int, count: int, dtype_code: int, piece_bytes: int = 2 << 20, inflight: int = 16,
+                   timeout_ms: int = 60000):
+        if self.lib.bnet_tring_allreduce(self._h, C.c_void_p(ptr), count, dtype_code, piece_bytes, inflight, timeout_ms) != 0:
+            raise RuntimeError(f"ring all-reduce: {self._err()}")
+
+    def stats(self) -> dict:
+        m, b = C.c_ulonglong(0), C.c_ulonglong(0)
+        self.lib.bnet_tring_stats(self._h, C.byref(m), C.byref(b))
+        return {"messages": int(m.value), "bytes_sent": int(b.value)}
+
+    def close(self):
+        if self._h:
+            self.lib.bnet_tring_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+class TransportRing:
+    """Ring all-reduce over the bnet transport between the ranks of a torch.distributed group (one GPU per rank)."""
+
+    def __init__(self, group=None, net_dev: int = 0):
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world < 2:
+            raise ValueError("a ring needs at least two ranks")
+        self.core = RingCore(self.rank, self.world, net_dev)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, self.core.handle, group=group)
+        self.core.connect(handles[(self.rank + 1) % self.world])
+        dist.barrier(group=group)
+        self._buf = None
+
+    @property
+    def transport(self) -> str:
+        return self.core.transport
+
+    def buffer(self, numel: int, dtype=torch.bfloat16, device=None) -> torch.Tensor:
+        """Device memory the ring can reduce in place (registered: the previous rank's kernels write it over NVLink)."""
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        t = torch.zeros(numel, dtype=dtype, device=device)
+        self.core.register(t.data_ptr(), t.numel() * t.element_size())
+        self._buf = t
+        return t
+
+    def all_reduce(self, t: torch.Tensor, piece_bytes: int = 2 << 20, inflight: int = 16) -> torch.Tensor:
+        """In-place sum over the ranks.  `t` must lie inside the registered buffer.  The caller's stream is synchronised
+        first (the transport's kernels run on their own streams, like under NCCL's proxy)."""
+        if t.dtype not in _DT:
+            raise TypeError("transport ring all-reduce supports fp32 and bf16")
+        torch.cuda.current_stream(t.device).synchronize()
+        self.core.all_reduce(t.data_ptr(), t.numel(), _DT[t.dtype], piece_bytes, inflight)
+        return t
+
+    def close(self):
+        self.core.close()

@@ -80,6 +80,10 @@ int Comm::dereg_mr(MemHandle* mh) {
 }
 int Comm::isend(const void*, size_t, int, MemHandle*, Request**) { return kErrInvalid; }
 int Comm::irecv(void*, size_t, int, MemHandle*, Request**) { return kErrInvalid; }
+int Comm::isend_op(const void* data, size_t size, int tag, MemHandle* mh, uint32_t op, float, Request** out) {
+  if (op != 0) return kErrInvalid;          // plain transports move bytes, nothing else
+  return isend(data, size, tag, mh, out);
+}
 int Comm::iflush(void*, size_t, MemHandle*, Request** out) {
   // Host destinations need no flush: complete immediately.
   Request* r = alloc_req(REQ_FLUSH, nullptr, 0, 0, nullptr);

@@ -832,19 +832,30 @@ int submit(Exec* e, int mode, uint32_t op, const void* src, void* dst, size_t nb
 
 }  // namespace
 
-int exec_copy(int dev, const void* src, void* dst, size_t nbytes, volatile uint64_t* flags_host, uint64_t* flags_dev,
-              uint64_t flag_value, int* nchunks, uint64_t* flag2_dev, uint64_t flag2_value) {
-  if (fake()) {   // CPU emulation: synchronous copy, same completion protocol
-    memcpy(dst, src, nbytes);
+// One message of the transport: OP_COPY for NCCL's isend, any other ExecOp for the fused-collective extension
+// (bnet_isend_op): the receiver's buffer is accumulated into / converted on the way instead of overwritten.
+int exec_transfer(int dev, uint32_t op, float scale, const void* src, void* dst, size_t nbytes, volatile uint64_t* flags_host,
+                  uint64_t* flags_dev, uint64_t flag_value, int* nchunks, uint64_t* flag2_dev, uint64_t flag2_value) {
+  if (fake()) {   // CPU emulation: the kernels' own per-CTA body run by one "thread", same completion protocol
+    if (op == OP_COPY) memcpy(dst, src, nbytes);
+    else process_range(op, (const char*)src, (char*)dst, nbytes, 0, 1, scale);
     size_t cs = chunk_size(nbytes, (size_t)env_int("DEV_MIN_CHUNKSIZE", 262144), 4);
     int n = nbytes ? (int)((nbytes + cs - 1) / cs) : 1;
+    if (op != OP_COPY) n = 1;
     for (int i = 0; i < n; i++) flags_host[i] = flag_value;
     *nchunks = n;
     return 0;
   }
   Exec* e = get_exec(dev);
   if (!e) return -1;
-  return submit(e, e->transport_mode, OP_COPY, src, dst, nbytes, flags_dev, flag_value, nchunks, 1.0f, flag2_dev, flag2_value);
+  return submit(e, e->transport_mode, op, src, dst, nbytes, flags_dev, flag_value, nchunks, scale, flag2_dev, flag2_value);
+}
+
+size_t exec_dst_bytes(uint32_t op, size_t src_bytes) { return dst_offset_for(op, src_bytes); }
+
+int exec_copy(int dev, const void* src, void* dst, size_t nbytes, volatile uint64_t* flags_host, uint64_t* flags_dev,
+              uint64_t flag_value, int* nchunks, uint64_t* flag2_dev, uint64_t flag2_value) {
+  return exec_transfer(dev, OP_COPY, 1.0f, src, dst, nbytes, flags_host, flags_dev, flag_value, nchunks, flag2_dev, flag2_value);
 }
 
 int exec_flush(int dev, volatile uint64_t* flag_host, uint64_t* flag_dev, uint64_t flag_value) {

@@ -298,8 +298,14 @@ class NvlComm : public Comm {
 
   // ---- posting ------------------------------------------------------------------------
   int isend(const void* data, size_t size, int tag, MemHandle* mh, Request** out) override {
+    return isend_op(data, size, tag, mh, 0 /* OP_COPY */, 1.0f, out);
+  }
+
+  // op != 0: the sender's kernel accumulates into / converts into the receiver's posted buffer (K4 / K5 fused with the move)
+  int isend_op(const void* data, size_t size, int tag, MemHandle* mh, uint32_t op, float scale, Request** out) override {
     *out = nullptr;
     if (kind != SEND) return kErrInvalid;
+    if (op != 0 && !(mh && mh->type == NCCL_PTR_CUDA)) return kErrInvalid;   // fused ops exist on the device path only
     std::lock_guard<std::mutex> lk(mu_);
     int b = broken.load(std::memory_order_acquire);
     if (b) return b;
@@ -308,6 +314,8 @@ class NvlComm : public Comm {
     track(+1);
     r->u[0] = seq_++;   // message index
     r->u[1] = 0;        // stage
+    r->u[4] = op;
+    memcpy(&r->u[5], &scale, sizeof(scale));
     pending_.push_back(r);
     progress_locked();
     *out = r;
@@ -594,9 +602,11 @@ class NvlComm : public Comm {
         RecvDesc& d = shm_->rdesc[k % kSlots];
         if (d.seq.load(std::memory_order_acquire) != k + 1) break;  // FIFO: later messages wait too
         Announce& a = shm_->ann[k % kSlots];
-        if (r->size > d.capacity) {
-          BNET_WARN("nvl isend: %zu bytes do not fit the posted receive (%llu)", r->size, (unsigned long long)d.capacity);
-          a.nbytes = r->size;
+        const uint32_t op = (uint32_t)r->u[4];
+        const size_t dst_bytes = op ? cuda::exec_dst_bytes(op, r->size) : r->size;
+        if (dst_bytes > d.capacity) {
+          BNET_WARN("nvl isend: %zu bytes do not fit the posted receive (%llu)", dst_bytes, (unsigned long long)d.capacity);
+          a.nbytes = dst_bytes;
           a.via_ring = 0;
           a.err = kErrInvalid;
           a.seq.store(k + 1, std::memory_order_release);
@@ -624,12 +634,26 @@ class NvlComm : public Comm {
           // the kernel itself publishes done[k] to the receiver when it can see the mailbox (one proxy hop less);
           // the host repeats the store when it notices completion, which also covers the other executor modes
           uint64_t* done_dev = shm_dev_ ? (uint64_t*)(shm_dev_ + ((char*)&shm_->done[k % kSlots].seq - (char*)shm_)) : nullptr;
-          direct = cuda::exec_copy(local_dev_, ksrc, dst, r->size, fh, fd, k + 1, &nchunks, done_dev, k + 1) == 0;
+          float scale = 1.0f;
+          memcpy(&scale, &r->u[5], sizeof(scale));
+          direct = cuda::exec_transfer(local_dev_, op, scale, ksrc, dst, r->size, fh, fd, k + 1, &nchunks, done_dev, k + 1) == 0;
+        }
+        if (op != 0 && !direct) {
+          // a fused op cannot fall back to the byte paths: tell the receiver, fail the request
+          BNET_WARN("nvl isend_op: op %u needs registered CUDA buffers on both sides (direct path unavailable)", op);
+          a.nbytes = dst_bytes;
+          a.via_ring = 0;
+          a.err = kErrInvalid;
+          a.seq.store(k + 1, std::memory_order_release);
+          r->fail(kErrInvalid);
+          track(-1);
+          r->u[1] = 3;
+          continue;
         }
         // large host -> host message: let the receiver pull it straight out of our buffer (one copy, none by us)
         const bool cma = !direct && !src_cuda && d.dst_type == NCCL_PTR_HOST && r->size >= cma_min_ && r->mh &&
                          r->mh->cma == 1 && shm_->cma_state.load(std::memory_order_acquire) == 1;
-        a.nbytes = r->size;
+        a.nbytes = dst_bytes;
         a.via_ring = direct ? PATH_DIRECT : cma ? PATH_CMA : PATH_RING;
         r->prof_path = direct ? 3 : cma ? 2 : 1;   // BNET_PROF_PATH_* (include/bnet/bnet_profiler.h)
         a.src_addr = (uint64_t)r->buf;

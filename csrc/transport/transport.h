@@ -125,6 +125,10 @@ struct Comm {
   virtual int reg_mr(void* data, size_t size, int type, MemHandle** out);
   virtual int dereg_mr(MemHandle* mh);
   virtual int isend(const void* data, size_t size, int tag, MemHandle* mh, Request** out);
+  // Extension (the north star's "fused isend"): like isend, but the receiver's posted buffer is combined with the
+  // payload instead of overwritten — `op` is an ExecOp (csrc/cuda/exec_body.cuh): accumulate (K4), cast (K5), both.
+  // Only the device path can do that (registered CUDA buffers on both sides); everything else returns kErrInvalid.
+  virtual int isend_op(const void* data, size_t size, int tag, MemHandle* mh, uint32_t op, float scale, Request** out);
   virtual int irecv(void* data, size_t size, int tag, MemHandle* mh, Request** out);
   virtual int iflush(void* data, size_t size, MemHandle* mh, Request** out);
   // done/size semantics of ncclNet test(); frees the request when *done

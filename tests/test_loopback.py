@@ -316,3 +316,41 @@ def test_per_gpu_virtual_devices():
     out = subprocess.run([sys.executable, "-c", code], env=env2, capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr[-2000:]
     assert not any(p["name"].startswith("bnet-gpu") for p in json.loads(out.stdout.splitlines()[-1]))
+
+
+def _run_tring(world, count, dtype, piece, inflight, timeout=180):
+    import json
+    import subprocess
+    import sys
+    import tempfile
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, BNET_FAKE_CUDA="1", BNET_NVL="1", PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    with tempfile.TemporaryDirectory() as d:
+        procs = [subprocess.Popen([sys.executable, os.path.join(root, "tests", "tring_worker.py"), str(r), str(world), d, str(count),
+                                   dtype, str(piece), str(inflight)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+                 for r in range(world)]
+        outs = []
+        for p in procs:
+            try:
+                o, e = p.communicate(timeout=timeout)
+            except subprocess.TimeoutExpired:
+                for q in procs:
+                    q.kill()
+                raise
+            assert p.returncode == 0, e[-3000:]
+            outs.append(json.loads([ln for ln in o.splitlines() if ln.startswith("{")][-1]))
+    return outs
+
+
+@pytest.mark.parametrize("world,count,dtype,piece,inflight", [
+    (2, 1 << 16, "f32", 16384, 4), (3, 100003, "f32", 8192, 8), (4, 1 << 18, "bf16", 65536, 16), (5, 7, "f32", 4096, 2),
+    (8, 300000, "bf16", 32768, 16)])
+def test_transport_ring_allreduce_with_fused_isend_reduce(world, count, dtype, piece, inflight):
+    """The all-reduce that rides the transport: reduce-scatter hops are isend_op(OP_RED_ADD_*) — the receiver's registered
+    buffer is accumulated into by the sender's kernel (here: its CPU emulation) — all-gather hops plain isends; pieces
+    pipeline around the ring with many requests in flight.  Bit-exact against the closed-form sum."""
+    outs = _run_tring(world, count, dtype, piece, inflight)
+    assert all(o["ok"] for o in outs), outs
+    assert all(o["transport"] == "nvl" for o in outs)
+    assert all(o["stats"]["messages"] >= 2 * (world - 1) for o in outs)
