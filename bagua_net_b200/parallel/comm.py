@@ -23,7 +23,7 @@ from ..utils.native import load
 
 DT = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 OPS = {"sum": 0, "avg": 1, "max": 2, "min": 3}
-ALGOS = {"auto": 0, "nvls": 1, "p2p": 2, "oneshot": 3}
+ALGOS = {"auto": 0, "nvls": 1, "p2p": 2, "oneshot": 3, "ll": 0}
 BLOB = 128
 
 
@@ -71,6 +71,9 @@ def _declare(lib):
     lib.bnet_allreduce.argtypes = [vp, sz, sz, i, i, i, i, i, vp]
     lib.bnet_allreduce_oneshot.argtypes = [vp, sz, vp, sz, i, i, i, i, vp]
     lib.bnet_barrier.argtypes = [vp, i, vp]
+    lib.bnet_allreduce_ll.argtypes = [vp, sz, sz, vp, vp, sz, i, i, vp]
+    lib.bnet_allreduce_ll_area_bytes.restype = sz
+    lib.bnet_allreduce_ll_area_bytes.argtypes = [i, sz]
     lib.bnet_fused_allreduce_sgd.argtypes = [vp, sz, sz, sz, i, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp,
                                              i, i, i, vp]
     lib.bnet_fused_allreduce_sgd_hp.argtypes = [vp, sz, sz, sz, i, vp, vp, vp, i, i, i, vp]
@@ -124,6 +127,16 @@ class SymmComm:
         self.has_multicast = bool(self.lib.bnet_coll_has_multicast(self.h))
         self._heap = torch.as_tensor(_CudaView(self.heap_ptr, self.heap_bytes, self), device=f"cuda:{self.device}")
         self._bump = 0
+        # area of the barrier-free small-message all-reduce ("LL": the flag travels inside every 8-byte word)
+        self.ll_words = int(os.environ.get("BNET_LL_WORDS", "8192"))          # 32 KiB of payload per rank and call
+        area = int(self.lib.bnet_allreduce_ll_area_bytes(self.world, self.ll_words))
+        self._ll = None
+        if area + (1 << 20) <= self.heap_bytes:
+            self._ll = self.alloc(area, torch.uint8)
+            self._ll.zero_()
+            torch.cuda.synchronize(self.device)
+            if self.world > 1:
+                dist.barrier(group=group)          # nobody pushes into an area that is still being cleared
 
     # ------------------------------------------------------------------ plumbing
     def _chk(self, rc, what):
@@ -181,7 +194,12 @@ class SymmComm:
 
     def all_reduce(self, t: torch.Tensor, op: str = "sum", algo: str = "auto", channel: int = 1, nblocks: int = 0,
                    stream=None) -> torch.Tensor:
-        """In-place all-reduce of a heap tensor.  numel*elsize must be a multiple of 16*world."""
+        """In-place all-reduce of a heap tensor.  numel*elsize must be a multiple of 16*world.
+        ``algo="auto"`` sends messages that fit the LL area (<= 32 KiB by default) down the barrier-free path."""
+        if algo in ("auto", "ll") and self._ll is not None and t.numel() * t.element_size() <= 4 * self.ll_words and self.world > 1:
+            return self.all_reduce_ll(t, op=op, stream=stream)
+        if algo == "ll":
+            raise ValueError("message too large for the LL all-reduce")
         n = self._chk(self.lib.bnet_allreduce(self.h, self.offset_of(t), t.numel(), DT[t.dtype], OPS[op], ALGOS[algo],
                                               channel, nblocks, self._stream(stream)), "all_reduce")
         self.launches += n
@@ -193,6 +211,21 @@ class SymmComm:
         n = self._chk(self.lib.bnet_allreduce_oneshot(self.h, self.offset_of(t), C.c_void_p(out.data_ptr()), t.numel(),
                                                       DT[t.dtype], OPS[op], channel, nblocks, self._stream(stream)),
                       "all_reduce_oneshot")
+        self.launches += n
+        return out
+
+    def all_reduce_ll(self, t: torch.Tensor, out: torch.Tensor | None = None, op: str = "sum", stream=None) -> torch.Tensor:
+        """Small-message all-reduce without a barrier: every rank pushes (payload, call number) words straight into every
+        peer's receive area and sums what arrives — about one NVLink store latency.  ``t`` / ``out`` are ordinary CUDA
+        tensors (``out`` defaults to ``t``: in place), at most ``4 * ll_words`` bytes; every rank must issue the same
+        sequence of calls."""
+        if self._ll is None:
+            raise RuntimeError("the symmetric heap is too small for the LL area")
+        out = t if out is None else out
+        assert t.is_contiguous() and out.is_contiguous() and out.numel() == t.numel() and out.dtype == t.dtype
+        n = self._chk(self.lib.bnet_allreduce_ll(self.h, self.offset_of(self._ll), self.ll_words, C.c_void_p(t.data_ptr()),
+                                                 C.c_void_p(out.data_ptr()), t.numel(), DT[t.dtype], OPS[op],
+                                                 self._stream(stream)), "all_reduce_ll")
         self.launches += n
         return out
 

@@ -343,6 +343,85 @@ __global__ void __launch_bounds__(kThreads) bnet_allreduce_oneshot_kernel(CollDe
 
 __global__ void __launch_bounds__(kThreads) bnet_barrier_kernel(CollDev d, int chan) { rank_barrier(d, chan); }
 
+
+// ------------------------------------------------------------------ latency-optimal small all-reduce ("LL": flag in the data)
+// No barrier at all: every 8-byte word a rank pushes to a peer carries 4 bytes of payload AND the call's epoch, so the
+// arrival of the data IS its own signal (one NVLink store = one packet; an aligned 8-byte store is never torn).
+//   ll area (same heap offset on every rank): [64-byte header][2 buffers][world senders][ll_words] x u64
+//   header (read and written by the local rank only): {calls completed, blocks finished in the running call} — the call's
+//   epoch is "completed + 1", read from DEVICE memory, so a captured CUDA graph replays correctly (every rank runs the
+//   same sequence of calls on the area, so the epochs agree without ever being communicated)
+//   push:  peer_ll[p][epoch & 1][my rank][i] = (epoch << 32) | my payload word i     for every peer p (own copy included)
+//   pull:  spin on my_ll[epoch & 1][q][i] until its upper half == epoch, q = 0..world-1 in that fixed order (every rank
+//          sums in the same order: bitwise identical results), accumulate in fp32, write out[i]
+// Two buffers suffice: a rank cannot start call e+2 before every rank has pushed for e+1, i.e. finished reading call e.
+// in / out are ordinary local pointers (any device memory, in place allowed): nothing but the ll area has to be symmetric.
+template <int DT, int OP>
+__device__ __forceinline__ void bnet_ll_word(const CollDev& d, size_t ll_off, size_t ll_words, const uint32_t* __restrict__ in,
+                                             uint32_t* __restrict__ out, size_t i, size_t nelem, uint32_t epoch) {
+  constexpr int EPW = (DT == BNET_F32) ? 1 : 2;          // elements per 4-byte word
+  // my payload word (the last word of an odd-length 16-bit vector carries one element; the other half is zero)
+  uint32_t w;
+  if (EPW == 2 && (i + 1) * 2 > nelem) w = (uint32_t)reinterpret_cast<const uint16_t*>(in)[2 * i];
+  else w = in[i];
+  const uint64_t word = ((uint64_t)epoch << 32) | w;
+  const size_t slot = ((size_t)(epoch & 1u) * d.world + d.rank) * ll_words + i;
+  for (int j = 0; j < d.world; j++) {
+    int p = d.rank + j;                                    // start with the own copy, then round the ring: spreads the links
+    if (p >= d.world) p -= d.world;
+    uint64_t* dst = reinterpret_cast<uint64_t*>(d.heap[p] + ll_off) + slot;
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(dst), "l"(word) : "memory");
+  }
+  float acc[2] = {0.f, 0.f};
+  const uint64_t t0 = ptx::globaltimer();
+  for (int q = 0; q < d.world; q++) {
+    const uint64_t* src = reinterpret_cast<const uint64_t*>(d.heap[d.rank] + ll_off) + ((size_t)(epoch & 1u) * d.world + q) * ll_words + i;
+    uint64_t v;
+    for (;;) {
+      asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
+      if ((uint32_t)(v >> 32) == epoch) break;
+      if (ptx::globaltimer() - t0 > kWatchdogNs) { *d.status = 3; break; }
+    }
+    const uint32_t pw = (uint32_t)v;
+    float f[2];
+    if constexpr (DT == BNET_F32) { f[0] = __uint_as_float(pw); f[1] = 0.f; }
+    else if constexpr (DT == BNET_BF16) { f[0] = __uint_as_float(pw << 16); f[1] = __uint_as_float(pw & 0xffff0000u); }
+    else { __half2 h = *reinterpret_cast<const __half2*>(&pw); float2 t = __half22float2(h); f[0] = t.x; f[1] = t.y; }
+    if (q == 0) { acc[0] = f[0]; acc[1] = f[1]; }
+    else { acc[0] = combine<OP>(acc[0], f[0]); acc[1] = combine<OP>(acc[1], f[1]); }
+  }
+  if constexpr (OP == BNET_AVG) { acc[0] *= 1.0f / (float)d.world; acc[1] *= 1.0f / (float)d.world; }
+  if constexpr (DT == BNET_F32) {
+    out[i] = __float_as_uint(acc[0]);
+  } else {
+    uint32_t r;
+    if constexpr (DT == BNET_BF16) { __nv_bfloat162 h = __floats2bfloat162_rn(acc[0], acc[1]); r = *reinterpret_cast<uint32_t*>(&h); }
+    else { __half2 h = __floats2half2_rn(acc[0], acc[1]); r = *reinterpret_cast<uint32_t*>(&h); }
+    if ((i + 1) * 2 > nelem) reinterpret_cast<uint16_t*>(out)[2 * i] = (uint16_t)r;
+    else out[i] = r;
+  }
+}
+
+template <int DT, int OP>
+__global__ void __launch_bounds__(256) bnet_allreduce_ll_kernel(CollDev d, size_t ll_hdr, size_t ll_words, const uint32_t* __restrict__ in,
+                                                               uint32_t* __restrict__ out, size_t nwords, size_t nelem) {
+  uint32_t* hdr = reinterpret_cast<uint32_t*>(d.heap[d.rank] + ll_hdr);
+  const size_t ll_off = ll_hdr + 64;
+  const uint32_t epoch = *(volatile uint32_t*)hdr + 1u;      // the same value in every block: hdr[0] moves only when ALL blocks are done
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nwords) bnet_ll_word<DT, OP>(d, ll_off, ll_words, in, out, i, nelem, epoch);
+  // the last block to finish closes the call
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(hdr + 1, 1u) == gridDim.x - 1) {
+      hdr[1] = 0;
+      __threadfence();
+      *(volatile uint32_t*)hdr = epoch;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ fused all-reduce + SGD + broadcast
 // MODE 0: single GPU, 1: NVLS multicast, 2: peer loads/stores
 //
@@ -922,6 +1001,45 @@ BNET_API int bnet_allreduce_oneshot(BnetColl* c, size_t offset, void* out, size_
     case BNET_F32: return run_oneshot<BNET_F32>(c, op, off, (char*)out, nvec, channel, nb, st);
     case BNET_BF16: return run_oneshot<BNET_BF16>(c, op, off, (char*)out, nvec, channel, nb, st);
     case BNET_F16: return run_oneshot<BNET_F16>(c, op, off, (char*)out, nvec, channel, nb, st);
+  }
+  return fail("bad dtype %d", dtype);
+}
+
+template <int DT>
+static int run_ll(BnetColl* c, int op, size_t ll_off, size_t ll_words, const void* in, void* out, size_t nwords, size_t nelem,
+                  cudaStream_t st) {
+  const int nb = (int)((nwords + 255) / 256);
+  const uint32_t* i32 = (const uint32_t*)in;
+  uint32_t* o32 = (uint32_t*)out;
+  switch (op) {
+    case BNET_SUM: return launch(bnet_allreduce_ll_kernel<DT, BNET_SUM>, nb, 256, st, c->devp, ll_off, ll_words, i32, o32, nwords, nelem);
+    case BNET_AVG: return launch(bnet_allreduce_ll_kernel<DT, BNET_AVG>, nb, 256, st, c->devp, ll_off, ll_words, i32, o32, nwords, nelem);
+    case BNET_MAX: return launch(bnet_allreduce_ll_kernel<DT, BNET_MAX>, nb, 256, st, c->devp, ll_off, ll_words, i32, o32, nwords, nelem);
+    case BNET_MIN: return launch(bnet_allreduce_ll_kernel<DT, BNET_MIN>, nb, 256, st, c->devp, ll_off, ll_words, i32, o32, nwords, nelem);
+  }
+  return fail("bad op %d", op);
+}
+
+// Small-message all-reduce without any barrier (see bnet_allreduce_ll_kernel).  `ll_offset`: byte offset in the heap of an
+// area of 64 + 2 * world * ll_words * 8 bytes that is ZERO before the first call and used by nothing else; every rank makes
+// the same sequence of calls on it.  in / out: local device pointers, 4-byte aligned, count elements.
+BNET_API size_t bnet_allreduce_ll_area_bytes(int world, size_t ll_words) { return 64 + 2 * (size_t)world * ll_words * 8; }
+
+BNET_API int bnet_allreduce_ll(BnetColl* c, size_t ll_offset, size_t ll_words, const void* in, void* out, size_t count, int dtype,
+                               int op, void* stream) {
+  const size_t es = elsize(dtype);
+  const size_t nwords = (count * es + 3) / 4;
+  if (nwords == 0) return 0;
+  if (nwords > ll_words) return fail("message of %zu words does not fit the LL area (%zu words per sender)", nwords, ll_words);
+  if (((uintptr_t)in & 3) || ((uintptr_t)out & 3) || (ll_offset & 7)) return fail("LL all-reduce needs 4-byte aligned buffers");
+  if (ll_offset + bnet_allreduce_ll_area_bytes(c->world, ll_words) > c->heap_bytes) return fail("LL area outside the heap");
+  refresh_devp(c);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t off = kPadBytes + ll_offset;
+  switch (dtype) {
+    case BNET_F32: return run_ll<BNET_F32>(c, op, off, ll_words, in, out, nwords, count, st);
+    case BNET_BF16: return run_ll<BNET_BF16>(c, op, off, ll_words, in, out, nwords, count, st);
+    case BNET_F16: return run_ll<BNET_F16>(c, op, off, ll_words, in, out, nwords, count, st);
   }
   return fail("bad dtype %d", dtype);
 }

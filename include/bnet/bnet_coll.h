@@ -60,6 +60,14 @@ int bnet_allreduce(BnetColl* c, size_t offset, size_t count, int dtype, int op, 
 /* Out-of-place one-shot variant: result written to local pointer `out`. */
 int bnet_allreduce_oneshot(BnetColl* c, size_t offset, void* out, size_t count, int dtype, int op, int channel,
                            int nblocks, void* stream);
+/* Latency-optimal small all-reduce: no barrier, the flag travels inside every 8-byte word ("LL").  `ll_offset` names an
+ * area of bnet_allreduce_ll_area_bytes(world, ll_words) bytes in the heap (zero before the first use, same offset on
+ * every rank, used by nothing else); every rank makes the same sequence of calls on it (the call counter that serves
+ * as the flag lives in the area itself, so a captured CUDA graph replays correctly).  in / out are ordinary local device
+ * pointers (in place allowed), count * elsize <= 4 * ll_words. */
+size_t bnet_allreduce_ll_area_bytes(int world, size_t ll_words);
+int bnet_allreduce_ll(BnetColl* c, size_t ll_offset, size_t ll_words, const void* in, void* out, size_t count, int dtype,
+                      int op, void* stream);
 int bnet_barrier(BnetColl* c, int channel, void* stream);
 
 /* Fused gradient all-reduce + SGD(momentum, weight decay) + parameter broadcast (one kernel):

@@ -726,6 +726,50 @@ def job_allreduce():
                 torch.cuda.synchronize()
                 err = (out.float() - ref).abs().max().item()
                 assert err <= (1e-5 if dtype == torch.float32 else 2e-2) * max(1.0, ref.abs().max().item()), f"oneshot {op} {dtype}"
+    # barrier-free small-message path: ordinary (non-heap) tensors, odd lengths, in place and out of place, many calls back to
+    # back (the call counter lives on the device), and under a CUDA graph
+    for dtype in (torch.float32, torch.bfloat16, torch.float16):
+        for n in (1, 7, 256, 4097, 8192):
+            for op in ("sum", "avg", "max", "min"):
+                alls = [(((torch.arange(n, device="cuda") * 3 + r) % 11) - 5).to(dtype).float() for r in range(WORLD)]
+                ref = {"sum": sum(alls), "avg": sum(alls) / WORLD, "max": torch.stack(alls).max(0).values,
+                       "min": torch.stack(alls).min(0).values}[op]
+                mine = alls[RANK].to(dtype)
+                for rep in range(3):
+                    x = mine.clone()
+                    out = comm.all_reduce_ll(x, None if rep % 2 else torch.empty_like(x), op=op)
+                    err = (out.float() - ref).abs().max().item()
+                    assert err <= (0 if op != "avg" else 2e-2), f"ll {op} {dtype} n={n} rep={rep} err={err}"
+    x = torch.full((1000,), float(RANK + 1), device="cuda", dtype=torch.float32)
+    y = torch.empty_like(x)
+    torch.cuda.synchronize()
+    dist.barrier()
+    g = torch.cuda.CUDAGraph()
+    s_ = torch.cuda.Stream()
+    s_.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s_):
+        comm.all_reduce_ll(x, y)
+    torch.cuda.current_stream().wait_stream(s_)
+    with torch.cuda.graph(g):
+        comm.all_reduce_ll(x, y)
+    for _ in range(5):
+        g.replay()
+    torch.cuda.synchronize()
+    assert bool((y == WORLD * (WORLD + 1) / 2).all()), "LL all-reduce under graph replay is wrong"
+    x = torch.ones(512, device="cuda", dtype=torch.bfloat16)       # 1 KiB: the latency line
+    for _ in range(20):
+        comm.all_reduce_ll(x.clone())
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    xs = [x.clone() for _ in range(200)]
+    e0.record()
+    for xi in xs:
+        comm.all_reduce_ll(xi)
+    e1.record()
+    torch.cuda.synchronize()
+    if RANK == 0:
+        print(f"allreduce ll 1 KiB: {e0.elapsed_time(e1) / 200 * 1e3:.2f} us per call (200 back-to-back launches, world {WORLD})", flush=True)
     # quick bandwidth lines
     for algo in algos:
         for nbytes in (1 << 20, 64 << 20, 512 << 20):
@@ -778,6 +822,94 @@ def job_nccl_allreduce():
 
         print(f"nccl-over-plugin allreduce 256 MiB: algbw {x.numel() * 4 / dt / 1e9:.2f} GB/s exec={native.exec_stats()}",
               flush=True)
+    teardown()
+
+
+def job_fused_sgd_staggered():
+    """The race the advisor found (round 1): with many CTAs per rank and a compute kernel hogging the SMs, CTAs of the
+    fused all-reduce + SGD kernel start staggered, and a CTA that zeroes gradients another CTA's pairing reads would
+    corrupt the reduction.  nb = 64 blocks on a bucket whose per-rank share is not a multiple of the grid stride."""
+    from bagua_net_b200.parallel import SymmComm
+
+    setup()
+    comm = SymmComm(512 << 20)
+    n = 8 * WORLD * (64 * 512 * 5 + 4099)          # per-rank vectors: NOT a multiple of 64 blocks x 512 threads
+    dtype = torch.bfloat16
+    param, grad = comm.alloc(n, dtype), comm.alloc(n, dtype)
+    shard = n // WORLD
+    master = torch.zeros(shard, device="cuda", dtype=torch.float32)
+    mom = torch.zeros_like(master)
+    side = torch.cuda.Stream()
+    a = torch.randn(8192, 8192, device="cuda", dtype=torch.bfloat16)
+    for step in range(6):
+        # small integers: the sum over ranks is exact in bf16, so ANY lost or doubled contribution shows
+        grad.copy_(((torch.arange(n, device="cuda") * 3 + RANK + step) % 5 - 2).to(dtype))
+        param.zero_()
+        master.zero_()
+        mom.zero_()
+        torch.cuda.synchronize()
+        if WORLD > 1:
+            dist.barrier()
+        for _ in range(3):
+            a @ a                                   # fills every SM while the fused kernel's CTAs trickle in
+        with torch.cuda.stream(side):
+            comm.fused_allreduce_sgd(grad, param, master, mom, 1.0, 0.0, 0.0, zero_grads=True, nblocks=64, stream=side)
+        torch.cuda.synchronize()
+        want = sum(((torch.arange(n, device="cuda") * 3 + r + step) % 5 - 2).float() for r in range(WORLD)) / WORLD
+        got = -param.float()                        # p = 0 - lr * mean(g), lr = 1, no momentum / decay
+        bad = int((got != want.to(dtype).float()).sum())
+        assert bad == 0, f"rank {RANK} step {step}: {bad} wrong elements (staggered CTAs corrupted the reduction)"
+        assert int((grad != 0).sum()) == 0, "gradients were not re-zeroed"
+    assert comm.status() == 0
+    print(f"rank {RANK}: fused sgd with 64 staggered CTAs under a concurrent GEMM ok (world {WORLD})", flush=True)
+    teardown()
+
+
+def job_transport_ring():
+    """All-reduce that rides the transport (parallel/transport_ring.py): ring over the plugin's connections, reduce-scatter
+    hops are fused isends (the sender's kernel accumulates into the next rank's buffer over NVLink)."""
+    from bagua_net_b200.parallel.transport_ring import TransportRing
+
+    setup()
+    ring = TransportRing()
+    assert ring.transport == "nvl", ring.transport
+    res = []
+    for dtype, count in ((torch.float32, 1 << 20), (torch.bfloat16, 3 * (1 << 20) + 17), (torch.float32, 33), (torch.bfloat16, 32 << 20)):
+        buf = ring.buffer(count, dtype)
+        for rnd in range(2):
+            buf.copy_(((torch.arange(count, device="cuda") * 5 + RANK + rnd) % 9 - 4).to(dtype))
+            torch.cuda.synchronize()
+            dist.barrier()
+            ring.all_reduce(buf)
+            want = sum(((torch.arange(count, device="cuda") * 5 + r + rnd) % 9 - 4).float() for r in range(WORLD))
+            assert torch.equal(buf.float(), want), f"rank {RANK}: transport ring all-reduce {dtype} x{count} is wrong"
+            dist.barrier()
+        # bandwidth of the largest case
+        if count >= (8 << 20):
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            iters = 5
+            for _ in range(iters):
+                ring.all_reduce(buf)
+            dt = (time.perf_counter() - t0) / iters
+            nbytes = count * buf.element_size()
+            res.append((nbytes, nbytes / dt / 1e9 * 2 * (WORLD - 1) / WORLD))
+    if RANK == 0:
+        for nbytes, busbw in res:
+            print(f"transport ring all-reduce {nbytes >> 20} MiB: busbw {busbw:.1f} GB/s (host-timed, world {WORLD}) stats {ring.core.stats()}",
+                  flush=True)
+    ring.close()
+    teardown()
+
+
+def job_tc_conv():
+    from bagua_net_b200.ops import tc_conv, tc_linear
+
+    setup()
+    assert tc_linear.supported()
+    assert tc_conv.self_check(verbose=RANK == 0), "tcgen05 convolution differs from cuDNN"
+    print("tcgen05 conv3x3 forward + dgrad match cuDNN", flush=True)
     teardown()
 
 

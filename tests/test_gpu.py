@@ -189,18 +189,33 @@ def test_executor_single_grid_mode(env):
     _run_worker("executor_idle", 1, extra_env=dict(env, BNET_KERNEL_IDLE_US="100"), timeout=60)
 
 
-# ------------------------------------------------------------------ tcgen05 linear / fused GEMM + all-reduce
-# Written without access to a GPU and not yet validated on hardware: opt in with BNET_TEST_TC=1 (see
-# include/bnet/bnet_tc.h).  The kernel's waits carry a watchdog, so a wrong pipeline fails instead of hanging.
-_tc = pytest.mark.skipif(os.environ.get("BNET_TEST_TC") != "1", reason="set BNET_TEST_TC=1 to run the unvalidated tcgen05 path")
-
-
-@_tc
+# ------------------------------------------------------------------ tcgen05 linear / convolution / fused GEMM + all-reduce
+# (validated on B200 in round 2: profiles/r2/tc_probe_1gpu.txt; the kernel's waits carry a watchdog, so a wrong pipeline
+#  fails instead of hanging)
 def test_tcgen05_linear_matches_fp32_reference():
     _run_worker("tc_linear", 1, timeout=240)
 
 
-@_tc
+def test_tcgen05_conv3x3_matches_cudnn():
+    _run_worker("tc_conv", 1, timeout=240)
+
+
 @pytest.mark.multigpu
 def test_tcgen05_row_parallel_linear_2gpu():
     _run_worker("tc_row_parallel", 2, timeout=240)
+
+
+# ------------------------------------------------------------------ round 2: advisor's race, the collective on the transport
+def test_fused_sgd_many_staggered_ctas_single_gpu():
+    _run_worker("fused_sgd_staggered", 1, timeout=240)
+
+
+@pytest.mark.multigpu
+def test_fused_sgd_many_staggered_ctas_2gpu():
+    _run_worker("fused_sgd_staggered", 2, timeout=240)
+
+
+@pytest.mark.multigpu
+def test_transport_ring_allreduce_2gpu():
+    """The all-reduce that rides the transport: fused isend-reduce hops between plugin connections, on real NVLink."""
+    _run_worker("transport_ring", 2, timeout=300)
