@@ -296,16 +296,19 @@ def _isolated_self_check(timeout: float = 180.0) -> bool:
 
 
 def trusted() -> bool:
-    """enabled() and a passing self-check on this GPU, run in a child process and evaluated once per process
-    (``BNET_TC_INPROC_CHECK=1`` runs the check in this process instead)."""
+    """enabled() and a passing self-check on this GPU, evaluated once per process.  The check runs in this process (about
+    a second; every wait in the kernel carries a watchdog, so a wrong pipeline is an error code, not a hang);
+    ``BNET_TC_ISOLATED_CHECK=1`` runs it in a child process instead (fault isolation, verdict cached per build and GPU)."""
     global _trusted
     if _trusted is None:
         if not (enabled() and supported()):
             _trusted = False
-        elif os.environ.get("BNET_TC_INPROC_CHECK") == "1":
-            _trusted = self_check()
-        else:
+        elif os.environ.get("BNET_TC_ISOLATED_CHECK") == "1":
             _trusted = _isolated_self_check()
+        else:
+            if torch.cuda.is_current_stream_capturing():
+                return False            # (not decided yet, and a capture is no place to decide)
+            _trusted = self_check()
     return _trusted
 
 

@@ -37,6 +37,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 BASELINE_IMG_S = 4046.6   # reference README.md:68 (32 x V100, 100 GbE, with bagua-net)
+_T0 = time.time()
+
+
+def note(msg: str) -> None:
+    """Progress on stderr (rank 0): where the wall-clock of a run goes, and where a stuck run stopped."""
+    if os.environ.get("RANK", "0") == "0":
+        tag = "child " if os.environ.get("BNET_BENCH_CHILD") else ""
+        print(f"[bench {tag}+{time.time() - _T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
 
 
 def reference_arm(args):
@@ -207,7 +215,9 @@ def run_child_arm(comm_name: str, args, rank: int, world: int, port_offset: int,
     env["BNET_BENCH_FUSED_VERDICT"] = "0" if args.no_fused or getattr(args, "fused_failed", False) else "1"
     env.pop("BNET_BENCH_REEXEC", None)
     env.pop("TORCHELASTIC_RUN_ID", None)
-    out_path = os.path.join(tempfile.gettempdir(), f"bnet_bench_arm_{comm_name}_{os.getppid()}_{env['MASTER_PORT']}.json")
+    log_dir = os.environ.get("BNET_BENCH_LOG_DIR") or tempfile.gettempdir()
+    os.makedirs(log_dir, exist_ok=True)
+    out_path = os.path.join(log_dir, f"bnet_bench_arm_{comm_name}_{os.getppid()}_{env['MASTER_PORT']}.json")
     if rank == 0 and os.path.exists(out_path):
         os.unlink(out_path)
     cmd = [sys.executable, os.path.abspath(__file__), "--comm", comm_name, "--gpus", str(world), "--steps", str(min(args.steps, 10)),
@@ -262,7 +272,7 @@ def main() -> int:
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the all-reduce busbw side measurement")
     ap.add_argument("--no-arms", action="store_true", help="N > 1: skip the NCCL-over-plugin / stock-NCCL DDP arms")
-    ap.add_argument("--arm-timeout", type=float, default=210.0, help="seconds one DDP arm (child processes) may take")
+    ap.add_argument("--arm-timeout", type=float, default=150.0, help="seconds one DDP arm (child processes) may take")
     ap.add_argument("--no-prefetch", action="store_true", help="e2e: per-step API instead of the prefetching loop")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel of the step individually (no CUDA graph)")
     ap.add_argument("--no-fused", action="store_true", help="eager bias/ReLU/pool instead of the fused sm_100a conv blocks")
@@ -273,6 +283,11 @@ def main() -> int:
     if args.warmup < 3:
         args.warmup = 3
     maybe_reexec_for_plugin(args)
+    if os.environ.get("BNET_BENCH_CHILD") or os.environ.get("BNET_BENCH_STACKS"):
+        import faulthandler
+
+        # a child arm that is still running shortly before its parent kills it says where it is stuck
+        faulthandler.dump_traceback_later(float(os.environ.get("BNET_BENCH_STACKS", "120")), exit=False, file=sys.stderr)
 
     import torch
     import torch.distributed as dist
@@ -290,7 +305,9 @@ def main() -> int:
         return 2
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    note(f"start: comm={args.comm} model={args.model} world={world}")
     init_process_group_from_env("nccl")
+    note("process group up")
     torch.backends.cudnn.benchmark = True
     torch.backends.cuda.matmul.allow_tf32 = True
     torch.backends.cudnn.allow_tf32 = True
@@ -309,9 +326,12 @@ def main() -> int:
         if inherited in ("0", "1"):
             verdict = inherited == "1"
         else:
-            verdict = None if os.environ.get("BNET_BENCH_INPROC_CHECK") == "1" else isolated_self_check(check.__name__, local)
+            # in-process by default (about a second); BNET_BENCH_ISOLATED_CHECK=1 runs it in a child process instead, so
+            # that a faulting kernel costs the fused layers and not the benchmark (+20-40 s of process start-up)
+            verdict = isolated_self_check(check.__name__, local) if os.environ.get("BNET_BENCH_ISOLATED_CHECK") == "1" else None
             if verdict is None:
                 verdict = check(dev)
+        note(f"fused layer self-check: {verdict}")
         ok = torch.tensor([1 if verdict else 0], device=dev, dtype=torch.int32)
         if world > 1:
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
@@ -388,10 +408,12 @@ def main() -> int:
                 opt.step()
                 return loss.detach()
 
+            note("DDP built; eager iterations")
             for _ in range(4 if world == 1 else 11):  # (DDP wants 11 eager iterations before a capture)
                 eager_step(gx, gy)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        note("eager iterations done")
         graph = None
         if not args.no_graph:
             try:
@@ -471,8 +493,11 @@ def main() -> int:
         return float(t[0].item()), float(t[1].item())
 
     # ---- device-resident inputs (the synthetic benchmark the reference quotes) ----------------
+    note(f"engine ready (cuda graph: {graph_used}{', ' + graph_note if graph_note else ''}); warm-up")
     for _ in range(args.warmup):
         step_dev(x_dev, y_dev)
+    torch.cuda.synchronize()
+    note("timed region")
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -483,6 +508,7 @@ def main() -> int:
     ms_step = ms_total / args.steps
     img_s = world * B / (ms_step / 1e3)
 
+    note(f"timed: {ms_step:.3f} ms/step")
     # ---- cross-rank numerics: after the timed steps every rank must hold the same parameters ----
     pv = param_vector()
     csum = torch.stack([pv.double().sum(), pv.double().abs().sum()])
@@ -564,7 +590,9 @@ def main() -> int:
     if args.comm == "bnet" and world > 1 and not args.no_arms and not os.environ.get("BNET_BENCH_CHILD"):
         sync_all()
         for i, (key, comm_name) in enumerate((("nccl_plugin", "nccl-plugin"), ("nccl_stock", "nccl"))):
+            note(f"arm {comm_name}: child processes (timeout {args.arm_timeout:.0f} s)")
             res = run_child_arm(comm_name, args, rank, world, 101 + 37 * i, args.arm_timeout)
+            note(f"arm {comm_name}: {res.get('status') if res else None}")
             if world > 1:
                 dist.barrier()
             if rank == 0:

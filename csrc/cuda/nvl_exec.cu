@@ -390,12 +390,27 @@ struct MsgArgs {
   uint32_t op;
   float scale;
 };
-__global__ void __launch_bounds__(kThreads, 1) bnet_nvl_msg_kernel(MsgArgs a) {
+// Several messages in ONE launch: NCCL's proxy posts one isend per channel in a burst, and a launch per message costs the
+// proxy thread ~6 us each (measured: 16 channels x 2 steps = ~190 us floor for every size up to 8 MiB).  The transport
+// therefore collects the messages of a burst and launches them together: cluster c belongs to message i when
+// first[i] <= c < first[i+1]; every message keeps its own completion counter and words.
+constexpr int kMsgBatch = 16;
+struct MsgBatch {
+  int n;
+  int first[kMsgBatch + 1];   // first cluster of message i (prefix sums); first[n] = clusters in the grid
+  MsgArgs m[kMsgBatch];
+};
+__global__ void __launch_bounds__(kThreads, 1) bnet_nvl_msg_kernel(const __grid_constant__ MsgBatch b) {
   const uint32_t crank = ptx::cluster_ctarank();
   const uint32_t csize = ptx::cluster_nctarank();
-  const uint32_t cid = blockIdx.x / csize;
+  const int cid = (int)(blockIdx.x / csize);
+  int i = 0;
+  while (i + 1 < b.n && cid >= b.first[i + 1]) i++;
+  const MsgArgs& a = b.m[i];
+  const uint32_t lc = (uint32_t)(cid - b.first[i]);                 // this cluster's chunk of message i
+  const uint32_t nctas = (uint32_t)(b.first[i + 1] - b.first[i]) * csize;
   if (a.op != OP_FLUSH) {
-    const size_t off = (size_t)cid * a.chunk;
+    const size_t off = (size_t)lc * a.chunk;
     const size_t n = off >= a.nbytes ? 0 : (a.nbytes - off < a.chunk ? a.nbytes - off : a.chunk);
     size_t b0, b1;
     cta_share(a.op, n, crank, csize, &b0, &b1);
@@ -405,7 +420,7 @@ __global__ void __launch_bounds__(kThreads, 1) bnet_nvl_msg_kernel(MsgArgs a) {
   if (threadIdx.x == 0) {
     ptx::fence_acq_rel_sys();                       // this CTA's (peer) stores before its arrival
     const uint32_t prev = atomicAdd(a.counter, 1u);
-    if (prev == gridDim.x - 1) {                    // every other CTA has arrived (and fenced) before us
+    if (prev == nctas - 1) {                        // every other CTA of this message has arrived (and fenced) before us
       *(volatile uint32_t*)a.counter = 0;           // ready for the next message that gets this counter
       ptx::fence_acq_rel_sys();
       if (a.flag2) ptx::st_release_sys_u64(a.flag2, a.flag2_val);
@@ -449,6 +464,9 @@ struct Exec {
   int ext_mode = MODE_PERSISTENT;  // what bnet_exec_op() uses
   uint32_t* counters = nullptr;    // device memory, kMsgCounters words, all zero between messages
   uint64_t msg_seq = 0;
+  MsgBatch batch{};                // messages collected since the last launch (transport path only)
+  std::atomic<int> batch_n{0};     // == batch.n, readable without the lock (exec_kick's fast path)
+  uint64_t batch_t0 = 0;
   bool tma = false;
   bool ce = false;             // BNET_COPY_ENGINE=ce: DMA copy engines + stream memory ops, no kernels at all
   int nclusters = 4;
@@ -581,11 +599,17 @@ Exec* get_exec(int dev) {
       cudaError_t err = launch_cluster(bnet_nvl_oneshot_kernel, e->cluster_size, e->cluster_size, 0, e->streams[0].stream, args);
       {
         // the per-message kernel: load it, run it once (two clusters, fence only) and check its completion protocol
-        MsgArgs m{nullptr, nullptr, 0, 64, (uint64_t*)wdp + 1, 7, (uint64_t*)wdp + 2, 9, e->counters, OP_FLUSH, 1.0f};
-        void* margs[] = {&m};
-        cudaError_t e3 = launch_cluster(bnet_nvl_msg_kernel, 2 * e->cluster_size, e->cluster_size, 0, e->streams[0].stream, margs);
+        // (two messages, three clusters: the batch lookup, both counters and all four completion words)
+        MsgBatch wb{};
+        wb.n = 2;
+        wb.first[0] = 0; wb.first[1] = 2; wb.first[2] = 3;
+        wb.m[0] = MsgArgs{nullptr, nullptr, 0, 64, (uint64_t*)wdp + 1, 7, (uint64_t*)wdp + 2, 9, e->counters, OP_FLUSH, 1.0f};
+        wb.m[1] = MsgArgs{nullptr, nullptr, 0, 64, (uint64_t*)wdp + 3, 7, nullptr, 0, e->counters + 1, OP_FLUSH, 1.0f};
+        void* margs[] = {&wb};
+        cudaError_t e3 = launch_cluster(bnet_nvl_msg_kernel, 3 * e->cluster_size, e->cluster_size, 0, e->streams[0].stream, margs);
         if (e3 == cudaSuccess) e3 = cudaStreamSynchronize(e->streams[0].stream);
-        if (e3 != cudaSuccess || ((volatile uint64_t*)wflag)[1] != 7 || ((volatile uint64_t*)wflag)[2] != 9) {
+        if (e3 != cudaSuccess || ((volatile uint64_t*)wflag)[1] != 7 || ((volatile uint64_t*)wflag)[2] != 9 ||
+            ((volatile uint64_t*)wflag)[3] != 7) {
           if (err == cudaSuccess) err = e3 != cudaSuccess ? e3 : cudaErrorUnknown;
         }
       }
@@ -719,8 +743,32 @@ int ensure_running(Exec* e, Stream& s, bool arm = false) {
   }
 }
 
+// launches what MODE_MSG submissions have collected (e->mu held, e->dev current)
+int flush_batch_locked(Exec* e) {
+  MsgBatch& b = e->batch;
+  if (b.n == 0) return 0;
+  Stream& s = e->streams[e->rr];                    // the stream rotates per launch: successive bursts overlap on the device
+  e->rr = (e->rr + 1) % e->streams.size();
+  void* args[] = {&b};
+  cudaError_t err;
+  {
+    CallScope cl_("cudaLaunchKernelEx(msg batch)");
+    err = launch_cluster(bnet_nvl_msg_kernel, b.first[b.n] * e->cluster_size, e->cluster_size, 0, s.stream, args);
+  }
+  e->stats.launches++;
+  e->stats.batched += (uint64_t)b.n;
+  b.n = 0;
+  e->batch_n.store(0, std::memory_order_release);
+  if (err != cudaSuccess) {
+    cudaGetLastError();
+    BNET_WARN("nvl executor: message launch failed: %s", cudaGetErrorString(err));
+    return -1;
+  }
+  return 0;
+}
+
 int submit(Exec* e, int mode, uint32_t op, const void* src, void* dst, size_t nbytes, uint64_t* flags_dev, uint64_t flag_value,
-           int* nchunks_out, float scale = 1.0f, uint64_t* flag2_dev = nullptr, uint64_t flag2_value = 0) {
+           int* nchunks_out, float scale = 1.0f, uint64_t* flag2_dev = nullptr, uint64_t flag2_value = 0, int defer_launch = 0) {
   CallScope cs_("exec submit");
   std::lock_guard<std::mutex> lk(e->mu);
   int cur = -1;
@@ -738,25 +786,18 @@ int submit(Exec* e, int mode, uint32_t op, const void* src, void* dst, size_t nb
   if (nchunks > kMaxChunksPerJob) nchunks = kMaxChunksPerJob;   // cannot happen: nclusters <= kMaxChunksPerJob
   int rc = 0;
   if (mode == MODE_MSG) {
-    // one launch for the whole message: cluster c moves chunk c, the last CTA to finish signals.  The stream
-    // rotates per MESSAGE (the cursor persists, like the reference's stream cursor), so consecutive messages of
-    // one or several connections overlap on the device.
-    Stream& s = e->streams[e->rr];
-    e->rr = (e->rr + 1) % e->streams.size();
+    // The message joins the pending batch; the batch is launched when it is full, when the caller asked for an immediate
+    // launch (extension API), or by exec_kick() — which the transport calls from test(), i.e. right after NCCL's proxy has
+    // posted the isends of one pass over its channels.  One launch then carries all of them.
     MsgArgs a{(const char*)src, (char*)dst, nbytes, cs, flags_dev, flag_value, flag2_dev, flag2_value,
               e->counters + (e->msg_seq++ % kMsgCounters), op, scale};
-    void* args[] = {&a};
-    cudaError_t err;
-    {
-      CallScope cl_("cudaLaunchKernelEx(msg)");
-      err = launch_cluster(bnet_nvl_msg_kernel, nchunks * e->cluster_size, e->cluster_size, 0, s.stream, args);
-    }
-    if (err != cudaSuccess) {
-      cudaGetLastError();
-      BNET_WARN("nvl executor: message launch failed: %s", cudaGetErrorString(err));
-      rc = -1;
-    }
-    e->stats.launches++;
+    MsgBatch& b = e->batch;
+    if (b.n == 0) { b.first[0] = 0; e->batch_t0 = now_ns(); }
+    b.m[b.n] = a;
+    b.first[b.n + 1] = b.first[b.n] + nchunks;
+    b.n++;
+    e->batch_n.store(b.n, std::memory_order_release);
+    if (defer_launch == 0 || b.n == kMsgBatch) rc = flush_batch_locked(e);
     e->stats.chunks += nchunks;
     e->stats.jobs++;
     e->stats.bytes += nbytes;
@@ -848,7 +889,22 @@ int exec_transfer(int dev, uint32_t op, float scale, const void* src, void* dst,
   }
   Exec* e = get_exec(dev);
   if (!e) return -1;
-  return submit(e, e->transport_mode, op, src, dst, nbytes, flags_dev, flag_value, nchunks, scale, flag2_dev, flag2_value);
+  static const int batching = (int)env_int("MSG_BATCH", 1);     // BNET_MSG_BATCH=0: one launch per message, immediately
+  return submit(e, e->transport_mode, op, src, dst, nbytes, flags_dev, flag_value, nchunks, scale, flag2_dev, flag2_value, batching);
+}
+
+// Launch whatever the transport has queued for `dev` (called from test(): cheap when nothing is pending).
+void exec_kick(int dev) {
+  if (dev < 0 || dev >= 64) return;
+  Exec* e = g_exec[dev];
+  if (!e || !e->ok || e->batch_n.load(std::memory_order_acquire) == 0) return;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (e->batch.n == 0) return;
+  int cur = -1;
+  cudaGetDevice(&cur);
+  if (cur != e->dev) cudaSetDevice(e->dev);
+  flush_batch_locked(e);
+  if (cur != e->dev && cur >= 0) cudaSetDevice(cur);
 }
 
 size_t exec_dst_bytes(uint32_t op, size_t src_bytes) { return dst_offset_for(op, src_bytes); }
@@ -956,6 +1012,7 @@ void exec_stats(ExecStats* out) {
     out->bytes += e->stats.bytes;
     out->launches += e->stats.launches;
     out->persistent += e->stats.persistent;
+    out->batched += e->stats.batched;
   }
 }
 

@@ -19,6 +19,7 @@ constexpr int kMaxChunksPerJob = 16;
 
 struct ExecStats {
   uint64_t jobs, chunks, bytes, launches, persistent;
+  uint64_t batched;      // messages that left in a multi-message launch (per-message mode)
 };
 
 // flags_host/flags_dev: the same kMaxChunksPerJob words seen from host and device.
@@ -32,6 +33,8 @@ int exec_copy(int dev, const void* src, void* dst, size_t nbytes, volatile uint6
 // the general form: `op` is an ExecOp of csrc/cuda/exec_body.cuh (0 = copy); nbytes counts SOURCE bytes
 int exec_transfer(int dev, uint32_t op, float scale, const void* src, void* dst, size_t nbytes, volatile uint64_t* flags_host,
                   uint64_t* flags_dev, uint64_t flag_value, int* nchunks, uint64_t* flag2_dev = nullptr, uint64_t flag2_value = 0);
+// per-message mode collects the isends of a burst; this launches them (the transport calls it from test())
+void exec_kick(int dev);
 // destination bytes an op writes for `src_bytes` of input (casts change the size)
 size_t exec_dst_bytes(uint32_t op, size_t src_bytes);
 // extension entry point with an explicit mode (-1 default, 0 per-message launch, 1 resident queues, 2 launch per chunk, 3 copy engines)

@@ -376,6 +376,7 @@ class NvlComm : public Comm {
   }
 
   int test(Request* r, int* done, size_t* size) override {
+    if (cuda_live_) cuda::exec_kick(local_dev_);   // launch the isends of this burst (one kernel for all of them)
     {
       std::lock_guard<std::mutex> lk(mu_);
       if (r->kind == REQ_FLUSH && r->u[3] == 1 && !r->complete() &&
