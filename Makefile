@@ -26,7 +26,7 @@ LDFLAGS   := -shared -cudart static -Xcompiler -pthread -ldl -lrt
 
 HOST_SRCS := csrc/core/common.cc csrc/core/netif.cc csrc/core/telemetry.cc csrc/core/engine.cc \
              csrc/transport/tcp_threads.cc csrc/transport/tcp_async.cc csrc/transport/nvl.cc \
-             csrc/cuda/cuda_iface.cc csrc/coll/transport_ring.cc csrc/capi.cc
+             csrc/cuda/cuda_iface.cc csrc/coll/transport_ring.cc csrc/plugin/tuner.cc csrc/capi.cc
 CU_SRCS   := $(wildcard csrc/cuda/*.cu)
 
 HOST_OBJS := $(patsubst csrc/%.cc,$(BUILD)/%.o,$(HOST_SRCS))
@@ -63,9 +63,10 @@ $(PLUGINX_SO): $(HOST_OBJS) $(CU_OBJS) $(PLUGINX_OBJ)
 	@mkdir -p $(OUT)
 	$(NVCC) $(ARCH) $(LDFLAGS) -o $@.tmp $^ && mv -f $@.tmp $@
 
-# NCCL_NET_PLUGIN=bnet  ->  libnccl-net-bnet.so
+# NCCL_NET_PLUGIN=bnet  ->  libnccl-net-bnet.so ;  NCCL_TUNER_PLUGIN=bnet  ->  libnccl-tuner-bnet.so (same library)
 $(ALIAS_SO): $(PLUGIN_SO)
 	cp -f $< $@.tmp && mv -f $@.tmp $@
+	cp -f $< $(OUT)/libnccl-tuner-bnet.so.tmp && mv -f $(OUT)/libnccl-tuner-bnet.so.tmp $(OUT)/libnccl-tuner-bnet.so
 
 TEST_BINS := $(BUILD)/tests/unit_tests $(BUILD)/tests/loopback_test
 $(BUILD)/tests/%: csrc/tests/%.cc $(PLUGIN_SO)

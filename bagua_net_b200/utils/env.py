@@ -31,6 +31,9 @@ def nccl_plugin_env(plugin: str = "bnet", force_net: bool = False, gdr: bool = T
         "NCCL_NET_PLUGIN": plugin,
         "NCCL_NET": "BNet",
     }
+    if os.environ.get("BNET_TUNER", "1") != "0" and plugin == "bnet":
+        # protocol choice per message size over this transport (csrc/plugin/tuner.cc): libnccl-tuner-bnet.so
+        env["NCCL_TUNER_PLUGIN"] = "bnet"
     if "CUDA_DEVICE_MAX_CONNECTIONS" not in os.environ:
         # the transport keeps up to 8 resident stream kernels, each on its own CUDA stream; with the default
         # of 8 hardware work queues per context other streams (NCCL's, the staging copies) can end up queued

@@ -75,6 +75,7 @@ void tune_nccl_env() {
   for (const KV& d : defaults)
     if (!getenv(d.k)) {
       setenv(d.k, d.v, 0);
+      if (!strcmp(d.k, "NCCL_PROTO")) setenv("BNET_PROTO_DEFAULTED", "1", 1);   // (the tuner plugin may widen it again)
       BNET_INFO("init: %s=%s (transport default; set it yourself or BNET_TUNE_NCCL=0 to override)", d.k, d.v);
     }
 }

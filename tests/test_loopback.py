@@ -354,3 +354,62 @@ def test_transport_ring_allreduce_with_fused_isend_reduce(world, count, dtype, p
     assert all(o["ok"] for o in outs), outs
     assert all(o["transport"] == "nvl" for o in outs)
     assert all(o["stats"]["messages"] >= 2 * (world - 1) for o in outs)
+
+
+def test_nccl_tuner_plugin_picks_the_protocol_by_size():
+    """ncclTunerPlugin_v3/_v4 inside the net plugin library (csrc/plugin/tuner.cc): over this transport LL for tiny messages,
+    Simple above, LL128 never — and no opinion at all when the device path is off."""
+    import json
+    import subprocess
+    import sys
+
+    code = r'''
+import ctypes as C, json, os
+from bagua_net_b200.utils.abi import NetPlugin
+from bagua_net_b200.utils.native import load
+lib = load()
+NetPlugin(8).init()                      # the net plugin's init ran in this process (NCCL does that before the tuner's)
+LOG = C.c_void_p
+class T4(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("init", C.CFUNCTYPE(C.c_int, C.c_size_t, C.c_size_t, LOG, C.POINTER(C.c_void_p))),
+                ("getCollInfo", C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int))),
+                ("destroy", C.CFUNCTYPE(C.c_int, C.c_void_p))]
+class T3(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("init", C.CFUNCTYPE(C.c_int, C.c_size_t, C.c_size_t, LOG, C.POINTER(C.c_void_p))),
+                ("getCollInfo", C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int))),
+                ("destroy", C.CFUNCTYPE(C.c_int, C.c_void_p))]
+out = {}
+for ver, T in ((4, T4), (3, T3)):
+    t = T.in_dll(lib, f"ncclTunerPlugin_v{ver}")
+    ctx = C.c_void_p()
+    assert t.init(8, 1, None, C.byref(ctx)) == 0
+    res = {}
+    for nbytes in (64, 8192, 8193, 1 << 20):
+        table = (C.c_float * 21)(*([10.0] * 21))          # 7 algorithms x 3 protocols
+        table[3 * 4 + 0] = -1.0                            # NCCL does not offer algorithm 4 with LL
+        nch = C.c_int(0)
+        args = [ctx, 4, nbytes, 1, C.cast(table, C.c_void_p), 7, 3] + ([0] if ver == 4 else []) + [C.byref(nch)]
+        assert t.getCollInfo(*args) == 0
+        res[nbytes] = [round(v, 1) for v in table]
+    assert t.destroy(ctx) == 0
+    out[ver] = res
+print(json.dumps({"name": T4.in_dll(lib, "ncclTunerPlugin_v4").name.decode(), "out": out}))
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for fake, active in (("1", True), ("0", False)):
+        env = dict(os.environ, BNET_FAKE_CUDA=fake, BNET_NVL="1", PYTHONPATH=root)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr[-3000:]
+        d = json.loads(r.stdout.splitlines()[-1])
+        assert d["name"] == "BNet"
+        for ver in ("4", "3"):
+            small, edge, above, big = (d["out"][ver][k] for k in ("64", "8192", "8193", "1048576"))
+            if not active:
+                assert small == big == [10.0] * 12 + [-1.0] + [10.0] * 8      # no device path: the table is left alone
+                continue
+            for row in range(7):
+                ll, ll128, simple = (small[3 * row + p] for p in range(3))
+                assert ll128 == -1.0
+                assert (ll, simple) == ((10.0, -1.0) if row != 4 else (-1.0, 10.0))   # LL where offered, else Simple stays
+                assert edge[3 * row:3 * row + 3] == small[3 * row:3 * row + 3]
+                assert above[3 * row:3 * row + 3] == [-1.0, -1.0, 10.0] and big[3 * row:3 * row + 3] == [-1.0, -1.0, 10.0]
