@@ -229,24 +229,10 @@ ncclResult_t v4_listen(int dev, void* h, void** l) { return do_listen(dev, h, NC
 ncclResult_t v4_connect(int dev, void* h, void** s) { return do_connect(dev, h, s); }
 ncclResult_t v4_accept(void* l, void** r) { return do_accept(l, r, /*blocking=*/true); }
 ncclResult_t v4_regmr(void* c, void* d, int size, int type, void** mh) { return do_regmr(c, d, (size_t)size, type, mh); }
-ncclResult_t v4_isend(void* c, void* d, int size, void* mh, void** req) {
-  // v4 has no "try again" contract in the reference (queues are unbounded there):
-  // wait for a request slot instead of returning NULL.
-  for (;;) {
-    ncclResult_t r = do_isend(c, d, (size_t)size, 0, mh, req);
-    if (r || *req) return r;
-    static_cast<Comm*>(c)->progress();
-    sched_yield();
-  }
-}
-ncclResult_t v4_irecv(void* c, void* d, int size, void* mh, void** req) {
-  for (;;) {
-    ncclResult_t r = do_irecv(c, d, (size_t)size, 0, mh, req);
-    if (r || *req) return r;
-    static_cast<Comm*>(c)->progress();
-    sched_yield();
-  }
-}
+// v3/v4: "may return request == NULL if the call cannot be performed (or would block)" — NCCL retries.  The reference never
+// does (its queues are unbounded); here a full request pool says so instead of holding NCCL's proxy thread in a spin.
+ncclResult_t v4_isend(void* c, void* d, int size, void* mh, void** req) { return do_isend(c, d, (size_t)size, 0, mh, req); }
+ncclResult_t v4_irecv(void* c, void* d, int size, void* mh, void** req) { return do_irecv(c, d, (size_t)size, 0, mh, req); }
 ncclResult_t v4_iflush(void* c, void* d, int size, void* mh, void** req) { return do_iflush(c, d, (size_t)size, mh, req); }
 ncclResult_t v3_flush(void* c, void* d, int size, void* mh) {
   void* req = nullptr;
