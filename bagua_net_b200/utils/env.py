@@ -39,6 +39,13 @@ def nccl_plugin_env(plugin: str = "bnet", force_net: bool = False, gdr: bool = T
         # of 8 hardware work queues per context other streams (NCCL's, the staging copies) can end up queued
         # BEHIND a resident kernel.  32 queues keep them independent.
         env["CUDA_DEVICE_MAX_CONNECTIONS"] = "32"
+    if "CUDA_MODULE_LOADING" not in os.environ:
+        # CUDA loads kernels lazily, and the first launch of a kernel waits for the device to drain.  If the APPLICATION
+        # launches a kernel for the first time while a collective is in flight, that wait never ends: the NCCL kernel is
+        # waiting for this transport's copy kernel, whose launch sits behind the loader (measured on 2 x B200 with torch
+        # DDP: proxy thread 26 s inside cudaLaunchKernelEx, profiles/README.md).  Stock NCCL never launches from its
+        # proxy, so it is immune; a transport that moves data with kernels needs every module loaded up front.
+        env["CUDA_MODULE_LOADING"] = "EAGER"
     if force_net:
         env.update({"NCCL_P2P_DISABLE": "1", "NCCL_SHM_DISABLE": "1", "NCCL_NVLS_ENABLE": "0",
                     "NCCL_NET_DISABLE_INTRA": "0"})

@@ -212,9 +212,12 @@ def run_child_arm(comm_name: str, args, rank: int, world: int, port_offset: int,
     env = dict(os.environ)
     env["MASTER_PORT"] = str(int(os.environ.get("MASTER_PORT", "29500")) + port_offset)
     env["BNET_BENCH_CHILD"] = "1"
+    # the children rendezvous on their own port: the elastic agent's store (TORCHELASTIC_USE_AGENT_STORE) lives on the
+    # parent job's MASTER_PORT only, so rank 0 of the child job must host the TCPStore itself
+    for k in [k for k in env if k.startswith("TORCHELASTIC_")] + ["GROUP_RANK", "ROLE_RANK", "ROLE_NAME", "ROLE_WORLD_SIZE", "GROUP_WORLD_SIZE"]:
+        env.pop(k, None)
     env["BNET_BENCH_FUSED_VERDICT"] = "0" if args.no_fused or getattr(args, "fused_failed", False) else "1"
     env.pop("BNET_BENCH_REEXEC", None)
-    env.pop("TORCHELASTIC_RUN_ID", None)
     log_dir = os.environ.get("BNET_BENCH_LOG_DIR") or tempfile.gettempdir()
     os.makedirs(log_dir, exist_ok=True)
     out_path = os.path.join(log_dir, f"bnet_bench_arm_{comm_name}_{os.getppid()}_{env['MASTER_PORT']}.json")
@@ -389,8 +392,20 @@ def main() -> int:
         # Let cuDNN pick its algorithms (and torch's allocator settle) BEFORE any collective is in flight: the
         # autotuner's emptyCache() -> cudaFree waits for the device, and a collective that is waiting for a peer which
         # is itself stuck behind such a call is the classic NCCL dead-lock (NCCL documents it for its own kernels).
+        # The same goes for CUDA's lazy module loading (first launch of a kernel = a wait for the device): every kernel of a
+        # training step — optimizer included — is launched once HERE, with no collective in flight, and the plugin arm
+        # additionally runs with CUDA_MODULE_LOADING=EAGER (bagua_net_b200/utils/env.py explains the dead-lock).
+        opt = torch.optim.SGD(model.parameters(), lr=lr, momentum=mom, weight_decay=wd)
+        state0 = [p.detach().clone() for p in model.parameters()]
         for _ in range(2):
+            opt.zero_grad(set_to_none=True)
             torch.nn.functional.cross_entropy(model(x_dev).float(), y_dev).backward()
+            opt.step()
+        with torch.no_grad():                          # (the warm-up steps must not count as training)
+            for p_, s_ in zip(model.parameters(), state0):
+                p_.copy_(s_)
+        opt = torch.optim.SGD(model.parameters(), lr=lr, momentum=mom, weight_decay=wd)
+        del state0
         model.zero_grad(set_to_none=True)
         torch.cuda.synchronize()
         side = torch.cuda.Stream()
@@ -398,7 +413,6 @@ def main() -> int:
         with torch.cuda.stream(side):                # DDP built (and warmed up) on a side stream: required for capture
             ddp = (torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
                    if world > 1 else model)
-            opt = torch.optim.SGD(model.parameters(), lr=lr, momentum=mom, weight_decay=wd)
             gx, gy = x_dev.clone(), y_dev.clone()
 
             def eager_step(x, y):
@@ -641,7 +655,22 @@ def main() -> int:
         print(line, flush=True)
     if world > 1:
         dist.barrier()
+        if args.comm != "bnet":
+            # A CUDA graph that captured NCCL collectives keeps the communicator busy: ncclCommDestroy then waits for it
+            # (measured: the arm printed its result after 14 s and sat in destroy_process_group until it was killed).
+            # Drop the graph first, and never let teardown outlive the measurement by more than a few seconds.
+            import gc
+            import threading
+
+            threading.Timer(8.0, lambda: os._exit(0)).start()
+            graph = gloss = None            # noqa: F841
+            gc.collect()
+            torch.cuda.synchronize()
         dist.destroy_process_group()
+        if args.comm != "bnet":
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
     return 0
 
 

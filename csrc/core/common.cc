@@ -277,14 +277,15 @@ int calltrace_dump(uint64_t older_than_ns) {
     if (d <= 0) continue;
     if (d > kTraceDepth) d = kTraceDepth;
     uint64_t t0 = t.since[0].load(std::memory_order_relaxed);
-    if (now - t0 < older_than_ns) continue;
+    if (t0 >= now || now - t0 < older_than_ns) continue;     // (a scope opened after `now` was read is not old)
+    if (t.depth.load(std::memory_order_acquire) <= 0 || t.since[0].load(std::memory_order_relaxed) != t0) continue;   // it moved on
     char line[512];
     int off = snprintf(line, sizeof(line), "[bnet watchdog] pid %d thread %llu inside the plugin:", (int)getpid(),
                        (unsigned long long)t.tid.load(std::memory_order_relaxed));
     for (int k = 0; k < d && off < (int)sizeof(line) - 64; k++) {
       const char* w = t.what[k].load(std::memory_order_relaxed);
-      off += snprintf(line + off, sizeof(line) - off, " %s%s (%.1f ms)", k ? "> " : "", w ? w : "?",
-                      (now - t.since[k].load(std::memory_order_relaxed)) / 1e6);
+      const uint64_t sk = t.since[k].load(std::memory_order_relaxed);
+      off += snprintf(line + off, sizeof(line) - off, " %s%s (%.1f ms)", k ? "> " : "", w ? w : "?", sk < now ? (now - sk) / 1e6 : 0.0);
     }
     fprintf(stderr, "%s\n", line);
     n++;

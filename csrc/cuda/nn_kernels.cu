@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "core/common.h"
 #include "cuda/nn_body.cuh"
 
 #define BNET_API extern "C" __attribute__((visibility("default")))
@@ -43,8 +44,13 @@ __device__ __forceinline__ void reduce_bias_grad(float* acc, float* __restrict__
     for (int r = 0; r < rows; r++)
 #pragma unroll
       for (int k = 0; k < V; k++) s[k] += smem[(r * cvec + grp) * V + k];
+    // 16-byte reductions: a quarter of the atomic operations of scalar adds.  Same-cache-line atomics serialise in the L2
+    // slice that owns the line (measured: the 512-channel layers spent ~60 of their 70 us there with one scalar atomic per
+    // channel and block), so the count of operations per line is what matters — see also nn_grid_cap().
 #pragma unroll
-    for (int k = 0; k < V; k++) atomicAdd(gb + grp * V + k, s[k]);
+    for (int k = 0; k < V; k += 4)
+      asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(gb + grp * V + k), "f"(s[k]), "f"(s[k + 1]),
+                   "f"(s[k + 2]), "f"(s[k + 3]) : "memory");
   }
 }
 
@@ -192,6 +198,20 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
 
 using namespace bnet::nn;
 
+// Blocks of the column-reducing kernels (bias gradients, BatchNorm sums): every block ends with C/4 vector atomics on the
+// same 4*C bytes, and those serialise per cache line — so these kernels run as FEW resident blocks as still saturate HBM
+// (2 per SM x 256 threads x 8 x 16-byte loads in flight = 64 KiB per SM) and walk the rows in a loop.
+// BNET_NN_BLOCKS_PER_SM overrides (measured sweep: profiles/README.md).
+static int nn_grid_cap() {
+  static const int cap = [] {
+    long long v = bnet::env_int("NN_BLOCKS_PER_SM", 2);
+    if (v < 1) v = 1;
+    if (v > 16) v = 16;
+    return (int)v * 148;
+  }();
+  return cap;
+}
+
 // dtype: 0 = f32, 1 = bf16 (same codes as bnet_coll.h).  All tensors NHWC-contiguous, C % vec == 0.
 // Return 1 (kernels launched) or <0.
 BNET_API int bnet_nn_bias_relu(void* z, const void* bias, long long rows, int C, int dtype, void* stream) {
@@ -216,7 +236,7 @@ BNET_API int bnet_nn_relu_bwd_bias_grad(const void* gy, const void* y, void* gz,
   const int rpb = threads / cvec;
   // at least 8 rows per thread before another block is worth its C atomics (small late layers: few rows, many channels)
   long long want = (rows + 8LL * rpb - 1) / (8LL * rpb);
-  int grid = (int)(want < 148 * 8 ? want : 148 * 8);
+  int grid = (int)(want < nn_grid_cap() ? want : nn_grid_cap());
   if (grid < 1) grid = 1;
   size_t smem = (size_t)threads * V * sizeof(float);
   if (dtype == 1)
@@ -254,7 +274,7 @@ BNET_API int bnet_nn_pool_relu_bwd_bias_grad(const void* gp, const void* idx, vo
   long long rows = (long long)N * (H / 2) * (W / 2);
   // at least 8 rows per thread before another block is worth its C atomics (small late layers: few rows, many channels)
   long long want = (rows + 8LL * rpb - 1) / (8LL * rpb);
-  int grid = (int)(want < 148 * 8 ? want : 148 * 8);
+  int grid = (int)(want < nn_grid_cap() ? want : nn_grid_cap());
   if (grid < 1) grid = 1;
   size_t smem = (size_t)threads * V * sizeof(float);
   if (dtype == 1)
@@ -276,7 +296,9 @@ RowGrid row_grid(long long rows, int cvec, int V, int accs) {
   const int rpb = g.threads / cvec;
   // at least 8 rows per thread before another block is worth its C atomics (small late layers: few rows, many channels)
   long long want = (rows + 8LL * rpb - 1) / (8LL * rpb);
-  g.grid = (int)(want < 148 * 8 ? want : 148 * 8);
+  // the element-wise kernels (accs == 0) have no atomics at their end: they keep the larger grid
+  const int cap = accs ? nn_grid_cap() : 148 * 8;
+  g.grid = (int)(want < cap ? want : cap);
   if (g.grid < 1) g.grid = 1;
   g.smem = (size_t)g.threads * V * sizeof(float) * (accs ? 1 : 0);
   return g;

@@ -898,8 +898,12 @@ void exec_kick(int dev) {
   if (dev < 0 || dev >= 64) return;
   Exec* e = g_exec[dev];
   if (!e || !e->ok || e->batch_n.load(std::memory_order_acquire) == 0) return;
+  // NCCL tests a request right after posting it, so "launch at the next test()" alone would never see more than one
+  // message: give the burst a few microseconds to arrive (the proxy posts its channels back to back), then launch.
+  static const uint64_t window_ns = (uint64_t)env_int("MSG_BATCH_US", 4) * 1000ull;
   std::lock_guard<std::mutex> lk(e->mu);
   if (e->batch.n == 0) return;
+  if (e->batch.n < kMsgBatch && now_ns() - e->batch_t0 < window_ns) return;
   int cur = -1;
   cudaGetDevice(&cur);
   if (cur != e->dev) cudaSetDevice(e->dev);

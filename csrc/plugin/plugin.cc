@@ -72,6 +72,14 @@ void tune_nccl_env() {
       {"NCCL_NET_GDR_LEVEL", "SYS"},
       {"NCCL_NET_GDR_READ", "1"},
   };
+  {
+    const char* ml = getenv("CUDA_MODULE_LOADING");
+    if (!ml || strcmp(ml, "EAGER"))
+      BNET_WARN("CUDA_MODULE_LOADING is not EAGER: a kernel the application launches for the FIRST time while a collective is in "
+                "flight makes CUDA's lazy loader wait for the device, and the collective waits for this transport's kernels "
+                "behind it (dead-lock).  Export CUDA_MODULE_LOADING=EAGER before the process starts "
+                "(`python -m bagua_net_b200.utils.env` prints the full environment).");
+  }
   for (const KV& d : defaults)
     if (!getenv(d.k)) {
       setenv(d.k, d.v, 0);
