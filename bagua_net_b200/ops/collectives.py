@@ -8,22 +8,25 @@ import torch
 from ..parallel.comm import DT, SymmComm
 
 
-def all_reduce(comm: SymmComm, t: torch.Tensor, op: str = "sum", algo: str = "auto", **kw) -> torch.Tensor:
-    """In-place all-reduce of a tensor allocated with ``comm.alloc``.
-    algo: "nvls" (in-switch multimem reduction), "p2p" (peer loads + peer stores) or "auto"."""
-    return comm.all_reduce(t, op=op, algo=algo, **kw)
+def all_reduce(comm: SymmComm, t: torch.Tensor, op: str = "sum", algo: str = "auto", stream=None) -> torch.Tensor:
+    """In-place all-reduce of ANY CUDA tensor over the symmetric-memory kernels, by the cheapest route that applies:
 
+    * small messages (<= 4 * comm.ll_words bytes, any memory): the barrier-free LL kernel — one NVLink store latency;
+    * tensors that live in the symmetric heap (``comm.alloc``) with a size the kernels can shard (a multiple of
+      16 bytes * world): in place, NVLS in-switch reduction or peer loads/stores (``algo``);
+    * everything else: staged through the heap in chunks (``comm.all_reduce_tensor``).
 
-def all_reduce_oneshot(comm: SymmComm, t: torch.Tensor, out: torch.Tensor | None = None, op: str = "sum", **kw):
-    """Latency-optimal out-of-place all-reduce: every rank reads every peer once."""
-    if out is None:
-        out = torch.empty_like(t)
-    return comm.all_reduce_oneshot(t, out, op=op, **kw)
-
-
-def fused_allreduce_sgd(comm: SymmComm, grad, param, master, mom, lr, momentum=0.0, weight_decay=0.0, **kw):
-    """grad mean-reduce + SGD(momentum, wd) on the fp32 shard + parameter broadcast, one kernel."""
-    return comm.fused_allreduce_sgd(grad, param, master, mom, lr, momentum, weight_decay, **kw)
+    ``algo`` only steers the heap kernels ("nvls", "p2p", "auto")."""
+    if comm.world == 1:
+        return t
+    nbytes = t.numel() * t.element_size()
+    if algo == "auto" and getattr(comm, "_ll", None) is not None and t.is_contiguous() and nbytes <= 4 * comm.ll_words \
+            and t.dtype in DT and op in ("sum", "avg", "max", "min"):
+        return comm.all_reduce_ll(t, op=op, stream=stream)
+    in_heap = t.is_contiguous() and comm.heap_ptr <= t.data_ptr() and t.data_ptr() + nbytes <= comm.heap_ptr + comm.heap_bytes
+    if in_heap and nbytes % (16 * comm.world) == 0 and (t.data_ptr() - comm.heap_ptr) % 16 == 0:
+        return comm.all_reduce(t, op=op, algo=algo if algo != "auto" else "auto", stream=stream)
+    return comm.all_reduce_tensor(t, op=op, algo=algo, stream=stream)
 
 
 class _Item(C.Structure):
