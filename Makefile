@@ -66,7 +66,7 @@ $(PLUGINX_SO): $(HOST_OBJS) $(CU_OBJS) $(PLUGINX_OBJ)
 # NCCL_NET_PLUGIN=bnet  ->  libnccl-net-bnet.so ;  NCCL_TUNER_PLUGIN=bnet  ->  libnccl-tuner-bnet.so (same library)
 $(ALIAS_SO): $(PLUGIN_SO)
 	cp -f $< $@.tmp && mv -f $@.tmp $@
-	cp -f $< $(OUT)/libnccl-tuner-bnet.so.tmp && mv -f $(OUT)/libnccl-tuner-bnet.so.tmp $(OUT)/libnccl-tuner-bnet.so
+	ln -sf libnccl-net-bnet.so $(OUT)/libnccl-tuner-bnet.so
 
 TEST_BINS := $(BUILD)/tests/unit_tests $(BUILD)/tests/loopback_test
 $(BUILD)/tests/%: csrc/tests/%.cc $(PLUGIN_SO)

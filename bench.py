@@ -530,6 +530,7 @@ def main() -> int:
     if world > 1:
         allc = [torch.zeros_like(csum) for _ in range(world)]
         dist.all_gather(allc, csum)
+        torch.cuda.synchronize()      # (no first-time kernel launch while a collective is in flight: lazy module loading)
         checksum["ranks_agree"] = all(bool(torch.equal(allc[0], c)) for c in allc)
     del pv
 
@@ -594,7 +595,9 @@ def main() -> int:
             extra["allreduce_time_us"] = lat
             # numerics of the path itself: sum of rank-patterned data against the closed form
             t = torch.full((1 << 20,), float(rank + 1), device=dev, dtype=torch.float32)
+            torch.cuda.synchronize()
             dist.all_reduce(t)
+            torch.cuda.synchronize()
             extra["allreduce_exact"] = bool((t == float(world * (world + 1) // 2)).all().item())
         except Exception as ex:   # noqa: BLE001
             extra["allreduce_error"] = str(ex)[:200]
@@ -604,8 +607,10 @@ def main() -> int:
     if args.comm == "bnet" and world > 1 and not args.no_arms and not os.environ.get("BNET_BENCH_CHILD"):
         sync_all()
         for i, (key, comm_name) in enumerate((("nccl_plugin", "nccl-plugin"), ("nccl_stock", "nccl"))):
-            note(f"arm {comm_name}: child processes (timeout {args.arm_timeout:.0f} s)")
-            res = run_child_arm(comm_name, args, rank, world, 101 + 37 * i, args.arm_timeout)
+            # (the plugin arm runs with CUDA_MODULE_LOADING=EAGER — see utils/env.py — which costs torch ~100 s of start-up)
+            tmo = args.arm_timeout * (2.0 if comm_name == "nccl-plugin" else 1.0)
+            note(f"arm {comm_name}: child processes (timeout {tmo:.0f} s)")
+            res = run_child_arm(comm_name, args, rank, world, 101 + 37 * i, tmo)
             note(f"arm {comm_name}: {res.get('status') if res else None}")
             if world > 1:
                 dist.barrier()

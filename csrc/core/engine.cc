@@ -1,5 +1,6 @@
 #include "core/engine.h"
 
+#include <dlfcn.h>
 #include <errno.h>
 #include <poll.h>
 #include <string.h>
@@ -186,9 +187,22 @@ Engine& Engine::get() {
   return *e;
 }
 
+// The library starts threads (watchdog, telemetry push, TCP workers) that must never find their code unmapped: NCCL
+// dlclose()s a plugin library when the last communicator goes away (and may have opened it under two names, net + tuner).
+static void pin_library() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  Dl_info info;
+  if (dladdr((void*)&pin_library, &info) && info.dli_fname) {
+    if (!dlopen(info.dli_fname, RTLD_NOW | RTLD_NODELETE)) BNET_DEBUG("could not pin %s: %s", info.dli_fname, dlerror());
+  }
+}
+
 int Engine::init() {
   std::lock_guard<std::mutex> lk(mu_);
   if (inited_) return kOk;
+  pin_library();
   const Config& cfg = Config::get();
   if (cfg.implement != "BASIC" && cfg.implement != "TOKIO") {
     // the reference returns a null backend here (src/lib.rs:20-29)

@@ -467,6 +467,7 @@ struct Exec {
   MsgBatch batch{};                // messages collected since the last launch (transport path only)
   std::atomic<int> batch_n{0};     // == batch.n, readable without the lock (exec_kick's fast path)
   uint64_t batch_t0 = 0;
+  uint64_t last_submit_ns = 0, burst_until_ns = 0;   // the batching window only applies while isends arrive back to back
   bool tma = false;
   bool ce = false;             // BNET_COPY_ENGINE=ce: DMA copy engines + stream memory ops, no kernels at all
   int nclusters = 4;
@@ -792,12 +793,19 @@ int submit(Exec* e, int mode, uint32_t op, const void* src, void* dst, size_t nb
     MsgArgs a{(const char*)src, (char*)dst, nbytes, cs, flags_dev, flag_value, flag2_dev, flag2_value,
               e->counters + (e->msg_seq++ % kMsgCounters), op, scale};
     MsgBatch& b = e->batch;
-    if (b.n == 0) { b.first[0] = 0; e->batch_t0 = now_ns(); }
+    {
+      // two isends within 3 us of each other = NCCL's proxy is walking its channels: batch for the next 2 ms.  A lone
+      // message (small collectives on one channel) is launched at once, so the window costs it nothing.
+      const uint64_t t = now_ns();
+      if (t - e->last_submit_ns < 3000) e->burst_until_ns = t + 2000000;
+      e->last_submit_ns = t;
+      if (b.n == 0) { b.first[0] = 0; e->batch_t0 = t; }
+    }
     b.m[b.n] = a;
     b.first[b.n + 1] = b.first[b.n] + nchunks;
     b.n++;
     e->batch_n.store(b.n, std::memory_order_release);
-    if (defer_launch == 0 || b.n == kMsgBatch) rc = flush_batch_locked(e);
+    if (defer_launch == 0 || b.n == kMsgBatch || now_ns() >= e->burst_until_ns) rc = flush_batch_locked(e);
     e->stats.chunks += nchunks;
     e->stats.jobs++;
     e->stats.bytes += nbytes;
@@ -903,7 +911,7 @@ void exec_kick(int dev) {
   static const uint64_t window_ns = (uint64_t)env_int("MSG_BATCH_US", 4) * 1000ull;
   std::lock_guard<std::mutex> lk(e->mu);
   if (e->batch.n == 0) return;
-  if (e->batch.n < kMsgBatch && now_ns() - e->batch_t0 < window_ns) return;
+  if (e->batch.n < kMsgBatch && now_ns() - e->batch_t0 < window_ns && now_ns() < e->burst_until_ns) return;
   int cur = -1;
   cudaGetDevice(&cur);
   if (cur != e->dev) cudaSetDevice(e->dev);

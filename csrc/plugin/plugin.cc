@@ -80,11 +80,16 @@ void tune_nccl_env() {
                 "behind it (dead-lock).  Export CUDA_MODULE_LOADING=EAGER before the process starts "
                 "(`python -m bagua_net_b200.utils.env` prints the full environment).");
   }
+  // with our tuner plugin in charge (NCCL_TUNER_PLUGIN=bnet) LL stays available — the tuner confines it to tiny messages
+  // — but LL128 is excluded either way (it needs a 128-byte store atomicity a copy kernel does not preserve)
+  const char* tp = getenv("NCCL_TUNER_PLUGIN");
+  const bool our_tuner = tp && strstr(tp, "bnet") && env_int("TUNER", 1) != 0;
   for (const KV& d : defaults)
     if (!getenv(d.k)) {
-      setenv(d.k, d.v, 0);
-      if (!strcmp(d.k, "NCCL_PROTO")) setenv("BNET_PROTO_DEFAULTED", "1", 1);   // (the tuner plugin may widen it again)
-      BNET_INFO("init: %s=%s (transport default; set it yourself or BNET_TUNE_NCCL=0 to override)", d.k, d.v);
+      const char* v = (!strcmp(d.k, "NCCL_PROTO") && our_tuner) ? "LL,Simple" : d.v;
+      setenv(d.k, v, 0);
+      if (!strcmp(d.k, "NCCL_PROTO")) setenv("BNET_PROTO_DEFAULTED", "1", 1);
+      BNET_INFO("init: %s=%s (transport default; set it yourself or BNET_TUNE_NCCL=0 to override)", d.k, v);
     }
 }
 

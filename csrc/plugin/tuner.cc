@@ -36,8 +36,14 @@ ncclResult_t tuner_init(size_t nRanks, size_t nNodes, ncclDebugLogger_t logFunct
   if (logFunction) log_set_nccl_logger(logFunction);
   TunerCtx* c = new TunerCtx();
   const Config& cfg = Config::get();
-  // only when NCCL's traffic actually rides our device path (the net plugin's init ran in this process and found CUDA)
-  c->active = env_int("TUNER", 1) != 0 && cfg.nvl && cfg.gdr && Engine::get().cuda_ok();
+  // Only when NCCL's traffic actually rides our device path.  (NCCL may have loaded this library a second time under the
+  // tuner's file name — a separate instance with its own engine singleton — so the verdict is derived from scratch here:
+  // same configuration, same CUDA probe, and bnet selected as the network.)
+  const char* net = getenv("NCCL_NET");
+  const char* netp = getenv("NCCL_NET_PLUGIN");
+  const bool ours = (net && strstr(net, "BNet")) || (netp && strstr(netp, "bnet")) || Engine::get().cuda_ok();
+  Engine::get().init();
+  c->active = env_int("TUNER", 1) != 0 && cfg.nvl && cfg.gdr && ours && Engine::get().cuda_ok();
   c->ll_max = (size_t)env_int("TUNER_LL_MAX", 8192);
   if (c->active) {
     // the protocol choice is ours now: lift the blanket "Simple only" default the net plugin's init supplied (if it was us)
