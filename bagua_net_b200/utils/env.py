@@ -20,7 +20,7 @@ TUNED = {"NCCL_BUFFSIZE": str(32 << 20), "NCCL_MIN_NCHANNELS": "16", "NCCL_PROTO
 
 
 def nccl_plugin_env(plugin: str = "bnet", force_net: bool = False, gdr: bool = True, debug: bool = False,
-                    extra: dict | None = None, tuned: bool = False) -> dict:
+                    extra: dict | None = None, tuned: bool = False, eager_modules: bool = True) -> dict:
     """Environment variables (as a dict) that make NCCL >= 2.2x dlopen our plugin.
 
     plugin: "bnet" -> libnccl-net-bnet.so (tables v3..v8); "bnetx" adds the v9/v10 tables.
@@ -39,12 +39,15 @@ def nccl_plugin_env(plugin: str = "bnet", force_net: bool = False, gdr: bool = T
         # of 8 hardware work queues per context other streams (NCCL's, the staging copies) can end up queued
         # BEHIND a resident kernel.  32 queues keep them independent.
         env["CUDA_DEVICE_MAX_CONNECTIONS"] = "32"
-    if "CUDA_MODULE_LOADING" not in os.environ:
+    if eager_modules and "CUDA_MODULE_LOADING" not in os.environ:
         # CUDA loads kernels lazily, and the first launch of a kernel waits for the device to drain.  If the APPLICATION
         # launches a kernel for the first time while a collective is in flight, that wait never ends: the NCCL kernel is
         # waiting for this transport's copy kernel, whose launch sits behind the loader (measured on 2 x B200 with torch
         # DDP: proxy thread 26 s inside cudaLaunchKernelEx, profiles/README.md).  Stock NCCL never launches from its
         # proxy, so it is immune; a transport that moves data with kernels needs every module loaded up front.
+        # The price is start-up time (torch + cuDNN + cuBLAS hold gigabytes of kernels: 100 s per process measured with
+        # 2 ranks, 260 s with 4).  eager_modules=False leaves loading lazy: then the APPLICATION has to launch each of
+        # its kernels once while no collective is in flight (bench.py does: warm-up steps + a single-rank DDP dry run).
         env["CUDA_MODULE_LOADING"] = "EAGER"
     if force_net:
         env.update({"NCCL_P2P_DISABLE": "1", "NCCL_SHM_DISABLE": "1", "NCCL_NVLS_ENABLE": "0",

@@ -161,7 +161,12 @@ def maybe_reexec_for_plugin(args):
     from bagua_net_b200.utils.env import nccl_plugin_env
 
     env = dict(os.environ)
-    env.update(nccl_plugin_env(force_net=True))
+    # CUDA_MODULE_LOADING: the helper's default (EAGER) is the safe choice for an arbitrary application, at the price of
+    # minutes of start-up per process with torch's kernel libraries.  This benchmark launches every kernel of its step
+    # once before a collective can be in flight (warm-up steps, single-rank DDP dry run), so lazy loading is safe HERE;
+    # BNET_BENCH_MODULE_LOADING=eager brings the helper's default back.
+    eager = os.environ.get("BNET_BENCH_MODULE_LOADING", "lazy").lower() == "eager"
+    env.update(nccl_plugin_env(force_net=True, eager_modules=eager))
     env["BNET_BENCH_REEXEC"] = "1"
     os.execve(sys.executable, [sys.executable] + sys.argv, env)
 
@@ -410,6 +415,24 @@ def main() -> int:
         torch.cuda.synchronize()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
+        if world > 1:
+            # DDP's OWN kernels (bucket copies, the 1/world scaling, the bucket rebuild after the first iteration) get their
+            # first launch here, through a process group of this rank alone: its collectives never wait for a peer, so a
+            # module load that synchronises the context has nothing to dead-lock with.  (new_group is collective: every
+            # rank creates every group.)  No optimizer step, the gradients are dropped afterwards.
+            solo = [dist.new_group([r]) for r in range(world)][rank]
+            with torch.cuda.stream(side):
+                dry = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], process_group=solo,
+                                                                gradient_as_bucket_view=True)
+                for _ in range(3):
+                    torch.nn.functional.cross_entropy(dry(x_dev).float(), y_dev).backward()
+                t_ = torch.ones(1024, device=dev, dtype=torch.bfloat16)
+                t_.div_(float(world)).mul_(1.0 / world)
+                torch.cat([t_, t_]).float().sum().item()
+            del dry, t_
+            model.zero_grad(set_to_none=True)
+            torch.cuda.synchronize()
+            note("DDP dry run on a single-rank group done")
         with torch.cuda.stream(side):                # DDP built (and warmed up) on a side stream: required for capture
             ddp = (torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
                    if world > 1 else model)
@@ -607,8 +630,10 @@ def main() -> int:
     if args.comm == "bnet" and world > 1 and not args.no_arms and not os.environ.get("BNET_BENCH_CHILD"):
         sync_all()
         for i, (key, comm_name) in enumerate((("nccl_plugin", "nccl-plugin"), ("nccl_stock", "nccl"))):
-            # (the plugin arm runs with CUDA_MODULE_LOADING=EAGER — see utils/env.py — which costs torch ~100 s of start-up)
-            tmo = args.arm_timeout * (2.0 if comm_name == "nccl-plugin" else 1.0)
+            # (BNET_BENCH_MODULE_LOADING=eager: every process of the plugin arm loads all of torch's kernels up front,
+            # 100 s at 2 ranks and 260 s at 4 — see maybe_reexec_for_plugin)
+            slow = comm_name == "nccl-plugin" and os.environ.get("BNET_BENCH_MODULE_LOADING", "lazy").lower() == "eager"
+            tmo = args.arm_timeout * (3.0 if slow else 1.0)
             note(f"arm {comm_name}: child processes (timeout {tmo:.0f} s)")
             res = run_child_arm(comm_name, args, rank, world, 101 + 37 * i, tmo)
             note(f"arm {comm_name}: {res.get('status') if res else None}")

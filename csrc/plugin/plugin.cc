@@ -75,10 +75,11 @@ void tune_nccl_env() {
   {
     const char* ml = getenv("CUDA_MODULE_LOADING");
     if (!ml || strcmp(ml, "EAGER"))
-      BNET_WARN("CUDA_MODULE_LOADING is not EAGER: a kernel the application launches for the FIRST time while a collective is in "
+      BNET_INFO("CUDA_MODULE_LOADING is not EAGER: a kernel the application launches for the FIRST time while a collective is in "
                 "flight makes CUDA's lazy loader wait for the device, and the collective waits for this transport's kernels "
-                "behind it (dead-lock).  Export CUDA_MODULE_LOADING=EAGER before the process starts "
-                "(`python -m bagua_net_b200.utils.env` prints the full environment).");
+                "behind it (dead-lock).  Either launch every kernel of a step once before the first collective (a warm-up "
+                "step without the process group), or export CUDA_MODULE_LOADING=EAGER before the process starts and pay "
+                "its start-up time (`python -m bagua_net_b200.utils.env` prints the full environment).");
   }
   // with our tuner plugin in charge (NCCL_TUNER_PLUGIN=bnet) LL stays available — the tuner confines it to tiny messages
   // — but LL128 is excluded either way (it needs a 128-byte store atomicity a copy kernel does not preserve)
