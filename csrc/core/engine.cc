@@ -12,6 +12,7 @@
 #include "bnet/bnet_profiler.h"
 #include "core/telemetry.h"
 #include "cuda/cuda_iface.h"
+#include "cuda/nvl_exec.h"
 
 namespace bnet {
 
@@ -203,6 +204,16 @@ int Engine::init() {
   std::lock_guard<std::mutex> lk(mu_);
   if (inited_) return kOk;
   pin_library();
+  if (env_int("EXEC_STATS", 0) != 0) {
+    // BNET_EXEC_STATS=1: one line per process at exit — how many messages the device executor moved and in how many launches
+    atexit([] {
+      cuda::ExecStats st;
+      cuda::exec_stats(&st);
+      fprintf(stderr, "[bnet stats] pid %d: %llu messages, %llu chunks, %.1f MiB, %llu kernel launches, %llu messages left in "
+                      "multi-message launches\n", (int)getpid(), (unsigned long long)st.jobs, (unsigned long long)st.chunks,
+              st.bytes / 1048576.0, (unsigned long long)st.launches, (unsigned long long)st.batched);
+    });
+  }
   const Config& cfg = Config::get();
   if (cfg.implement != "BASIC" && cfg.implement != "TOKIO") {
     // the reference returns a null backend here (src/lib.rs:20-29)
@@ -211,8 +222,9 @@ int Engine::init() {
   }
   // Device model.  The reference has one NCCL device per NIC (reference nthread_…:241-257).
   // On an NVSwitch box the "NIC" of a GPU is its own NVLink port, so when the device path is usable every visible
-  // GPU gets a virtual device whose pciPath IS the GPU's: NCCL's topology then puts it next to that GPU — each rank
-  // picks its own device and enables GPUDirect without NCCL_NET_GDR_LEVEL overrides.  Every virtual device keeps a
+  // GPU gets a virtual device of its own (guid per GPU, NVLink speed).  It carries NO pciPath: a <nic> under the GPU's
+  // own <pci> node crashes NCCL's topology code (profiles/README.md R2.2), so GPUDirect is enabled by the
+  // NCCL_NET_GDR_LEVEL=SYS default the plugin's init supplies instead of by PCI distance.  Every virtual device keeps a
   // TCP side on a real interface (cross-host peers, fallbacks); the plain NIC devices follow after them.
   std::vector<NetIf> nics = find_interfaces();
   cuda_ok_ = cfg.gdr && cuda::available();
