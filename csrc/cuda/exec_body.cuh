@@ -76,6 +76,15 @@ BNET_XD uint2 ld8(const void* p) {          // p is 8-byte aligned
   return r;
 #endif
 }
+BNET_XD uint32_t ld4(const void* p) {       // p is 4-byte aligned
+#if defined(__CUDA_ARCH__)
+  return *reinterpret_cast<const uint32_t*>(p);
+#else
+  uint32_t r;
+  memcpy(&r, p, 4);
+  return r;
+#endif
+}
 BNET_XD void st8(void* p, const uint2& v) {  // p is 8-byte aligned
 #if defined(__CUDA_ARCH__)
   *reinterpret_cast<uint2*>(p) = v;
@@ -235,18 +244,40 @@ BNET_XD_FN void process_range(uint32_t op, const char* src, char* dst, size_t n,
     const bool acc = op == OP_ACC_BF16_TO_F32;
     if ((((uintptr_t)s | (uintptr_t)d) & 15) == 0) {
       size_t nv = ne >> 3;   // 8 bf16 in, 2 x float4 out
-      xb::batched<8, int4>(nv, tid, nthreads, [&](size_t i) { return xb::ld16(reinterpret_cast<const int4*>(s) + i); },
+      // Lane-interleaved inside blocks of 32 vectors (256 elements): vector l of a block takes elements [4l, 4l+4) and
+      // [128+4l, 128+4l+4).  Each of a warp's two output instructions then covers 512 CONTIGUOUS bytes (whole sectors,
+      // full NVLink packets) instead of 16 bytes out of every 32 — the plain mapping ran at half the red.add rate
+      // (ncu + timing: profiles/README.md R2.6).
+      const size_t nblk = nv & ~(size_t)31;
+      xb::batched<8, int4>(nblk, tid, nthreads,
+                           [&](size_t i) {
+                             const char* p = (const char*)s + (i & ~(size_t)31) * 16 + (i & 31) * 8;
+                             const uint2 a = xb::ld8(p), b = xb::ld8(p + 256);
+                             return make_int4((int)a.x, (int)a.y, (int)b.x, (int)b.y);
+                           },
                            [&](size_t i, const int4& v) {
                              float4 lo, hi;
                              xb::unpack_bf16x8(v, &lo, &hi);
+                             float* o = d + (i & ~(size_t)31) * 8 + (i & 31) * 4;
                              if (acc) {
-                               xb::red_v4_f32(d + 8 * i, lo);
-                               xb::red_v4_f32(d + 8 * i + 4, hi);
+                               xb::red_v4_f32(o, lo);
+                               xb::red_v4_f32(o + 128, hi);
                              } else {
-                               xb::st16f(reinterpret_cast<float4*>(d) + 2 * i, lo);
-                               xb::st16f(reinterpret_cast<float4*>(d) + 2 * i + 1, hi);
+                               xb::st16f(reinterpret_cast<float4*>(o), lo);
+                               xb::st16f(reinterpret_cast<float4*>(o + 128), hi);
                              }
                            });
+      for (size_t i = nblk + tid; i < nv; i += nthreads) {      // the last, incomplete block: vector i = elements [8i, 8i+8)
+        float4 lo, hi;
+        xb::unpack_bf16x8(xb::ld16(reinterpret_cast<const int4*>(s) + i), &lo, &hi);
+        if (acc) {
+          xb::red_v4_f32(d + 8 * i, lo);
+          xb::red_v4_f32(d + 8 * i + 4, hi);
+        } else {
+          xb::st16f(reinterpret_cast<float4*>(d) + 2 * i, lo);
+          xb::st16f(reinterpret_cast<float4*>(d) + 2 * i + 1, hi);
+        }
+      }
       for (size_t i = (nv << 3) + tid; i < ne; i += nthreads) {
         float f = __bfloat162float(s[i]);
         if (acc) xb::red_f32(d + i, f); else d[i] = f;
@@ -348,14 +379,30 @@ BNET_XD_FN void process_range(uint32_t op, const char* src, char* dst, size_t n,
     };
     if ((((uintptr_t)s) & 7) == 0 && (((uintptr_t)d) & 15) == 0) {
       size_t nv = ne >> 3;
-      xb::batched<8, uint2>(nv, tid, nthreads,
-                            [&](size_t i) { return xb::ld8(s + 8 * i); },
+      // same lane interleave as the bf16 path: vector l of a 32-vector block = bytes [4l, 4l+4) and [128+4l, 128+4l+4)
+      const size_t nblk = nv & ~(size_t)31;
+      xb::batched<8, uint2>(nblk, tid, nthreads,
+                            [&](size_t i) {
+                              const unsigned char* p = s + (i & ~(size_t)31) * 8 + (i & 31) * 4;
+                              uint2 r;
+                              r.x = xb::ld4(p);
+                              r.y = xb::ld4(p + 128);
+                              return r;
+                            },
                             [&](size_t i, const uint2& v) {
                               unsigned char b[8];
                               memcpy(b, &v, 8);
-                              xb::red_v4_f32(d + 8 * i, make_float4(dq(b[0]), dq(b[1]), dq(b[2]), dq(b[3])));
-                              xb::red_v4_f32(d + 8 * i + 4, make_float4(dq(b[4]), dq(b[5]), dq(b[6]), dq(b[7])));
+                              float* o = d + (i & ~(size_t)31) * 8 + (i & 31) * 4;
+                              xb::red_v4_f32(o, make_float4(dq(b[0]), dq(b[1]), dq(b[2]), dq(b[3])));
+                              xb::red_v4_f32(o + 128, make_float4(dq(b[4]), dq(b[5]), dq(b[6]), dq(b[7])));
                             });
+      for (size_t i = nblk + tid; i < nv; i += nthreads) {
+        const uint2 v = xb::ld8(s + 8 * i);
+        unsigned char b[8];
+        memcpy(b, &v, 8);
+        xb::red_v4_f32(d + 8 * i, make_float4(dq(b[0]), dq(b[1]), dq(b[2]), dq(b[3])));
+        xb::red_v4_f32(d + 8 * i + 4, make_float4(dq(b[4]), dq(b[5]), dq(b[6]), dq(b[7])));
+      }
       for (size_t i = (nv << 3) + tid; i < ne; i += nthreads) xb::red_f32(d + i, dq(s[i]));
     } else {
       for (size_t i = tid; i < ne; i += nthreads) xb::red_f32(d + i, dq(s[i]));

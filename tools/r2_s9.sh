@@ -8,7 +8,7 @@ exec > >(tee $OUT/session.log) 2>&1
 echo "== session $TAG ngpus=$NG $(date -u)"
 BASE="$(python -m bagua_net_b200.utils.env) BNET_WATCHDOG_MS=5000 NCCL_DEBUG=WARN BNET_EXEC_STATS=1"
 ARP="build/bench/all_reduce_perf -N $NG -d bfloat16 -b 32M -e 128M -f 4 -n 8 -w 2"
-run() { local name=$1; shift; echo "---- [$name] $(date -u +%T) $*"; timeout -k 3 25 env $BASE "$@" $ARP > $OUT/$name.log 2>&1; echo "rc=$?"; grep -E "^ +[0-9]+ +[0-9]+ +bf16|bnet stats" $OUT/$name.log | head -4 | cut -c1-200; }
+run() { local name=$1; shift; echo "---- [$name] $(date -u +%T) $*"; timeout -k 3 19 env $BASE "$@" $ARP > $OUT/$name.log 2>&1; echo "rc=$?"; grep -E "^ +[0-9]+ +[0-9]+ +bf16|bnet stats" $OUT/$name.log | head -4 | cut -c1-200; }
 run base
 run window20 BNET_MSG_BATCH_US=20
 run ch8 NCCL_MIN_NCHANNELS=8 NCCL_MAX_NCHANNELS=8
