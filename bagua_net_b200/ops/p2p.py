@@ -12,7 +12,7 @@ from ..utils.native import load
 
 OPS = {"copy": 0, "red_add_f32": 1, "red_add_bf16": 2, "cast_bf16_to_f32": 3, "cast_f32_to_bf16": 4, "flush": 5,
        "acc_bf16_to_f32": 6, "cast_bf16_to_e4m3": 7, "acc_e4m3_to_f32": 8, "cast_f32_to_e4m3": 9,
-       "cast_bf16_to_e5m2": 10, "acc_e5m2_to_f32": 11, "cast_f32_to_e5m2": 12}
+       "cast_bf16_to_e5m2": 10, "acc_e5m2_to_f32": 11, "cast_f32_to_e5m2": 12, "cast_e4m3_to_f32": 13, "cast_e5m2_to_f32": 14}
 
 
 class P2PExecutor:

@@ -19,6 +19,8 @@ from ..utils.native import load
 
 HANDLE_BYTES = 128
 _DT = {torch.float32: 0, torch.bfloat16: 1}
+WIRE_FORMATS = {"bf16": 1, "e4m3": 2, "e5m2": 3}       # what travels between the ranks of a compressed all-reduce
+_WIRE_BYTES = {"bf16": 2, "e4m3": 1, "e5m2": 1}
 
 
 def _lib():
@@ -29,6 +31,8 @@ def _lib():
         lib.bnet_tring_connect.argtypes = [vp, vp, i]
         lib.bnet_tring_register.argtypes = [vp, vp, C.c_size_t]
         lib.bnet_tring_allreduce.argtypes = [vp, vp, C.c_size_t, i, C.c_size_t, i, i]
+        lib.bnet_tring_register_wire.argtypes = [vp, vp, C.c_size_t, i]
+        lib.bnet_tring_allreduce_compressed.argtypes = [vp, vp, C.c_size_t, i, C.c_float, i, C.c_size_t, i, i]
         lib.bnet_tring_stats.argtypes = [vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
         lib.bnet_tring_destroy.argtypes = [vp]
         lib.bnet_tring_last_error.argtypes = [vp]
@@ -75,6 +79,17 @@ class RingCore:
         if self.lib.bnet_tring_allreduce(self._h, C.c_void_p(ptr), count, dtype_code, piece_bytes, inflight, timeout_ms) != 0:
             raise RuntimeError(f"ring all-reduce: {self._err()}")
 
+    def register_wire(self, ptr: int, nbytes: int, device_memory: bool = True):
+        """The wire-format mirror of the data buffer (count * 2 bytes for bf16, count bytes for fp8)."""
+        if self.lib.bnet_tring_register_wire(self._h, C.c_void_p(ptr), nbytes, 2 if device_memory else 1) != 0:
+            raise RuntimeError(f"ring register_wire: {self._err()}")
+
+    def all_reduce_compressed(self, ptr: int, count: int, wire: str = "bf16", scale: float = 1.0, fused: bool = True,
+                              piece_elems: int = 1 << 19, inflight: int = 16, timeout_ms: int = 60000):
+        if self.lib.bnet_tring_allreduce_compressed(self._h, C.c_void_p(ptr), count, WIRE_FORMATS[wire], float(scale),
+                                                    1 if fused else 0, piece_elems, inflight, timeout_ms) != 0:
+            raise RuntimeError(f"compressed ring all-reduce: {self._err()}")
+
     def stats(self) -> dict:
         m, b = C.c_ulonglong(0), C.c_ulonglong(0)
         self.lib.bnet_tring_stats(self._h, C.byref(m), C.byref(b))
@@ -120,6 +135,27 @@ class TransportRing:
             raise TypeError("transport ring all-reduce supports fp32 and bf16")
         torch.cuda.current_stream(t.device).synchronize()
         self.core.all_reduce(t.data_ptr(), t.numel(), _DT[t.dtype], piece_bytes, inflight)
+        return t
+
+    def all_reduce_compressed(self, t: torch.Tensor, wire: str = "bf16", scale: float = 1.0, fused: bool | None = None,
+                              piece_elems: int = 1 << 19, inflight: int = 16) -> torch.Tensor:
+        """In-place sum of an fp32 tensor with a narrower format on the wire: "bf16" (half the bytes), "e4m3" / "e5m2"
+        (a quarter; values are multiplied by `scale` before quantisation and by 1/scale on the way back — choose it so
+        that the partial sums stay inside the format: |x| * scale <= 448 for e4m3, 57344 for e5m2).  Every rank ends with
+        the same bits.  On the NVLink transport the quantisation is fused into the send (`fused`, default there): the
+        sending GPU's kernel converts while it moves, so NVLink carries the narrow format and nothing is staged."""
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise TypeError("compressed all-reduce works on contiguous fp32 tensors")
+        if wire not in WIRE_FORMATS:
+            raise ValueError(f"wire format {wire!r} (one of {sorted(WIRE_FORMATS)})")
+        need = t.numel() * _WIRE_BYTES[wire]
+        if getattr(self, "_wire", None) is None or self._wire.numel() < need:
+            self._wire = torch.zeros(max(need, 64), dtype=torch.uint8, device=t.device)
+            self.core.register_wire(self._wire.data_ptr(), self._wire.numel(), device_memory=True)
+        if fused is None:
+            fused = self.transport == "nvl"
+        torch.cuda.current_stream(t.device).synchronize()
+        self.core.all_reduce_compressed(t.data_ptr(), t.numel(), wire, scale, fused, piece_elems, inflight)
         return t
 
     def close(self):

@@ -8,7 +8,7 @@
 //   net_perf [-l libnccl-net.so] [-b min] [-e max] [-f factor] [-w window] [-t bytes moved per size, default 2e9] [-c check]
 //            [-m host|fakecuda]
 // honours the BAGUA_NET_* / BNET_* environment (implementation, streams, chunk size, NVL on/off).
-// Output columns: bytes, messages, time, GB/s, messages/s, mean us per message.
+// Output columns: bytes, messages, time, GB/s, messages/s, mean us per message, longest gap between completions (@ message).
 #include <dlfcn.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -118,7 +118,7 @@ int main(int argc, char** argv) {
     for (size_t k = 0; k < cap; k += 61) buf[j][k] = sender ? (unsigned char)(k * 7 + 3) : 0;
     OK(net->regMr(comm, buf[j].data(), cap, fake ? NCCL_PTR_CUDA : NCCL_PTR_HOST, &mh[j]));
   }
-  if (!sender) printf("# %-10s %10s %9s %9s %12s %10s\n", "bytes", "messages", "time(s)", "GB/s", "messages/s", "us/msg");
+  if (!sender) printf("# %-10s %10s %9s %9s %12s %10s %11s\n", "bytes", "messages", "time(s)", "GB/s", "messages/s", "us/msg", "max gap us");
 
   for (double fs = (double)lo; (size_t)fs <= hi; fs *= factor) {
     const size_t size = (size_t)fs;
@@ -140,8 +140,9 @@ int main(int argc, char** argv) {
       while (!done) OK(net->test(r, &done, nullptr));
     }
     void* req[8] = {nullptr};
-    long long posted = 0, completed = 0;
+    long long posted = 0, completed = 0, gap_at = 0;
     const double t0 = now_s();
+    double last_done = t0, max_gap = 0;   // longest wait between two completions: stalls hide in an average
     while (completed < count) {
       for (int j = 0; j < window && posted < count; j++) {   // post while the window has room
         if (req[j]) continue;
@@ -163,12 +164,17 @@ int main(int argc, char** argv) {
         if (check && !sender && size > 61 && buf[j][61] != (unsigned char)(61 * 7 + 3)) sh->errors++;
         req[j] = nullptr;
         completed++;
+        if ((completed & 15) == 0 || completed < 64) {
+          const double t = now_s();
+          if (t - last_done > max_gap) { max_gap = t - last_done; gap_at = completed; }
+          last_done = t;
+        }
       }
     }
     const double dt = now_s() - t0;
     if (!sender) {
-      printf("%-12zu %10lld %9.3f %9.3f %12.0f %10.2f\n", size, completed, dt, completed * (double)size / dt / 1e9,
-             completed / dt, dt / completed * 1e6);
+      printf("%-12zu %10lld %9.3f %9.3f %12.0f %10.2f %11.1f @%lld\n", size, completed, dt, completed * (double)size / dt / 1e9,
+             completed / dt, dt / completed * 1e6, max_gap * 1e6, gap_at);
       fflush(stdout);
     }
   }

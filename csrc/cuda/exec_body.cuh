@@ -27,7 +27,7 @@
 namespace bnet {
 namespace cuda {
 
-BNET_XD bool op_is_e5m2(uint32_t op) { return op >= OP_CAST_BF16_TO_E5M2 && op <= OP_CAST_F32_TO_E5M2; }
+BNET_XD bool op_is_e5m2(uint32_t op) { return (op >= OP_CAST_BF16_TO_E5M2 && op <= OP_CAST_F32_TO_E5M2) || op == OP_CAST_E5M2_TO_F32; }
 
 namespace xb {   // access primitives: PTX on the device, plain C++ in the emulation
 
@@ -164,7 +164,7 @@ BNET_XD size_t src_unit_for(uint32_t op) {
 BNET_XD size_t dst_offset_for(uint32_t op, size_t src_off) {
   if (op == OP_CAST_BF16_TO_F32 || op == OP_ACC_BF16_TO_F32) return src_off * 2;
   if (op == OP_CAST_F32_TO_BF16 || op == OP_CAST_BF16_TO_E4M3 || op == OP_CAST_BF16_TO_E5M2) return src_off / 2;
-  if (op == OP_ACC_E4M3_TO_F32 || op == OP_ACC_E5M2_TO_F32) return src_off * 4;
+  if (op == OP_ACC_E4M3_TO_F32 || op == OP_ACC_E5M2_TO_F32 || op == OP_CAST_E4M3_TO_F32 || op == OP_CAST_E5M2_TO_F32) return src_off * 4;
   if (op == OP_CAST_F32_TO_E4M3 || op == OP_CAST_F32_TO_E5M2) return src_off / 4;
   return src_off;
 }
@@ -366,8 +366,9 @@ BNET_XD_FN void process_range(uint32_t op, const char* src, char* dst, size_t n,
     }
     return;
   }
-  if (op == OP_ACC_E4M3_TO_F32 || op == OP_ACC_E5M2_TO_F32) {
+  if (op == OP_ACC_E4M3_TO_F32 || op == OP_ACC_E5M2_TO_F32 || op == OP_CAST_E4M3_TO_F32 || op == OP_CAST_E5M2_TO_F32) {
     const __nv_fp8_interpretation_t fmt = op_is_e5m2(op) ? __NV_E5M2 : __NV_E4M3;
+    const bool acc = op == OP_ACC_E4M3_TO_F32 || op == OP_ACC_E5M2_TO_F32;   // else: overwrite (plain decompression)
     size_t ne = n;
     const unsigned char* s = (const unsigned char*)src;
     float* d = (float*)dst;
@@ -376,6 +377,13 @@ BNET_XD_FN void process_range(uint32_t op, const char* src, char* dst, size_t n,
       __half hh;
       memcpy(&hh, &h, sizeof(hh));
       return __half2float(hh) * scale;
+    };
+    auto put4 = [&](float* o, const unsigned char* b) {
+      const float4 v = make_float4(dq(b[0]), dq(b[1]), dq(b[2]), dq(b[3]));
+      if (acc) xb::red_v4_f32(o, v); else xb::st16f(reinterpret_cast<float4*>(o), v);
+    };
+    auto put1 = [&](float* o, unsigned char b) {
+      if (acc) xb::red_f32(o, dq(b)); else *o = dq(b);
     };
     if ((((uintptr_t)s) & 7) == 0 && (((uintptr_t)d) & 15) == 0) {
       size_t nv = ne >> 3;
@@ -393,19 +401,19 @@ BNET_XD_FN void process_range(uint32_t op, const char* src, char* dst, size_t n,
                               unsigned char b[8];
                               memcpy(b, &v, 8);
                               float* o = d + (i & ~(size_t)31) * 8 + (i & 31) * 4;
-                              xb::red_v4_f32(o, make_float4(dq(b[0]), dq(b[1]), dq(b[2]), dq(b[3])));
-                              xb::red_v4_f32(o + 128, make_float4(dq(b[4]), dq(b[5]), dq(b[6]), dq(b[7])));
+                              put4(o, b);
+                              put4(o + 128, b + 4);
                             });
       for (size_t i = nblk + tid; i < nv; i += nthreads) {
         const uint2 v = xb::ld8(s + 8 * i);
         unsigned char b[8];
         memcpy(b, &v, 8);
-        xb::red_v4_f32(d + 8 * i, make_float4(dq(b[0]), dq(b[1]), dq(b[2]), dq(b[3])));
-        xb::red_v4_f32(d + 8 * i + 4, make_float4(dq(b[4]), dq(b[5]), dq(b[6]), dq(b[7])));
+        put4(d + 8 * i, b);
+        put4(d + 8 * i + 4, b + 4);
       }
-      for (size_t i = (nv << 3) + tid; i < ne; i += nthreads) xb::red_f32(d + i, dq(s[i]));
+      for (size_t i = (nv << 3) + tid; i < ne; i += nthreads) put1(d + i, s[i]);
     } else {
-      for (size_t i = tid; i < ne; i += nthreads) xb::red_f32(d + i, dq(s[i]));
+      for (size_t i = tid; i < ne; i += nthreads) put1(d + i, s[i]);
     }
     return;
   }

@@ -20,6 +20,9 @@ enum ExecOp : uint32_t {
   OP_CAST_BF16_TO_E5M2 = 10, // the same three with the wide-range e5m2 format
   OP_ACC_E5M2_TO_F32 = 11,
   OP_CAST_F32_TO_E5M2 = 12,
+  OP_CAST_E4M3_TO_F32 = 13,  // dst(f32) = src(fp8 e4m3) * scale         (decompress, overwriting: the all-gather half of a
+  OP_CAST_E5M2_TO_F32 = 14,  //                                            compressed all-reduce)
+  OP_COUNT = 15,
 };
 
 }  // namespace cuda

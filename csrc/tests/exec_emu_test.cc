@@ -136,9 +136,9 @@ int main() {
                      return (size_t)-1;
                    });
   const float scale = 16.f, inv = 1.f / 16.f;
-  struct { const char* name; __nv_fp8_interpretation_t fmt; uint32_t from_bf16, from_f32, acc; } fmts[] = {
-      {"e4m3", __NV_E4M3, OP_CAST_BF16_TO_E4M3, OP_CAST_F32_TO_E4M3, OP_ACC_E4M3_TO_F32},
-      {"e5m2", __NV_E5M2, OP_CAST_BF16_TO_E5M2, OP_CAST_F32_TO_E5M2, OP_ACC_E5M2_TO_F32}};
+  struct { const char* name; __nv_fp8_interpretation_t fmt; uint32_t from_bf16, from_f32, acc, to_f32; } fmts[] = {
+      {"e4m3", __NV_E4M3, OP_CAST_BF16_TO_E4M3, OP_CAST_F32_TO_E4M3, OP_ACC_E4M3_TO_F32, OP_CAST_E4M3_TO_F32},
+      {"e5m2", __NV_E5M2, OP_CAST_BF16_TO_E5M2, OP_CAST_F32_TO_E5M2, OP_ACC_E5M2_TO_F32, OP_CAST_E5M2_TO_F32}};
   for (auto& F : fmts) {
     const __nv_fp8_interpretation_t fmt = F.fmt;
     char nm[64];
@@ -168,6 +168,20 @@ int main() {
                      dst_f32,
                      [&](const unsigned char* s, const unsigned char* d0, const unsigned char* d, size_t n) {
                        for (size_t i = 0; i < n; i++) if (f32(d, i) != f32(d0, i) + fp8(s[i], fmt) * inv) return i;
+                       return (size_t)-1;
+                     });
+    snprintf(nm, sizeof(nm), "cast_%s_to_f32", F.name);
+    test_elementwise(nm, F.to_f32, 1, 4, inv,
+                     [&](unsigned char* p, size_t n) {
+                       for (size_t i = 0; i < n; i++) {
+                         unsigned char b = (unsigned char)urand();
+                         float v = fp8(b, fmt);
+                         p[i] = (v == v && fabsf(v) < 1e30f) ? b : (unsigned char)0x3c;
+                       }
+                     },
+                     dst_f32,
+                     [&](const unsigned char* s, const unsigned char*, const unsigned char* d, size_t n) {
+                       for (size_t i = 0; i < n; i++) if (f32(d, i) != fp8(s[i], fmt) * inv) return i;
                        return (size_t)-1;
                      });
   }

@@ -103,6 +103,10 @@ def job_executor():
             ex.run("acc_e4m3_to_f32", q, acc, scale=1.0 / scale)
             torch.cuda.synchronize()
             assert torch.allclose(acc, ref, rtol=1e-6, atol=1e-6), "acc_e4m3_to_f32"
+            dec = torch.full((n,), 7.0, device="cuda")
+            ex.run("cast_e4m3_to_f32", q, dec, scale=1.0 / scale)      # plain decompression (overwrites)
+            torch.cuda.synchronize()
+            assert torch.equal(dec, ref_q.float() / scale), "cast_e4m3_to_f32"
     # bandwidth line (device-local copy through the transport kernel)
     big = torch.empty(256 << 20, device="cuda", dtype=torch.uint8).random_(0, 255)
     out = torch.empty_like(big)
@@ -139,6 +143,10 @@ def job_executor_e5m2():
         ex.run("acc_e5m2_to_f32", q, acc, scale=1.0 / scale)
         torch.cuda.synchronize()
         assert torch.allclose(acc, ref, rtol=1e-6, atol=1e-6), "acc_e5m2_to_f32"
+        dec = torch.full((n,), 7.0, device="cuda")
+        ex.run("cast_e5m2_to_f32", q, dec, scale=1.0 / scale)
+        torch.cuda.synchronize()
+        assert torch.equal(dec, ref_q.float() / scale), "cast_e5m2_to_f32"
     print("e5m2 ok", flush=True)
 
 
@@ -900,6 +908,40 @@ def job_transport_ring():
         for nbytes, busbw in res:
             print(f"transport ring all-reduce {nbytes >> 20} MiB: busbw {busbw:.1f} GB/s (host-timed, world {WORLD}) stats {ring.core.stats()}",
                   flush=True)
+    ring.close()
+    teardown()
+
+
+def job_transport_ring_compressed():
+    """fp32 all-reduce with bf16 / fp8 on the wire (TransportRing.all_reduce_compressed): the quantisation rides the isend
+    (fused) or runs as a local executor pass (unfused); every rank must end with the same bits."""
+    from bagua_net_b200.parallel.transport_ring import TransportRing
+
+    setup()
+    ring = TransportRing()
+    assert ring.transport == "nvl", ring.transport
+    count = (4 << 20) + 1000
+    buf = ring.buffer(count, torch.float32)
+    gen = lambda r, rnd: (((torch.arange(count, device="cuda") * 7 + r * 3 + rnd) % 4) - 1).float() * 0.25   # noqa: E731
+    for rnd, (wire, fused) in enumerate((("bf16", True), ("e4m3", True), ("e4m3", False), ("e5m2", True))):
+        buf.copy_(gen(RANK, rnd))
+        torch.cuda.synchronize()
+        dist.barrier()
+        ring.all_reduce_compressed(buf, wire=wire, scale=4.0, fused=fused)
+        want = sum(gen(r, rnd) for r in range(WORLD))
+        if wire == "e5m2":
+            assert (buf - want).abs().max().item() <= 1.5
+        else:
+            assert torch.equal(buf, want), f"rank {RANK}: compressed all-reduce ({wire}, fused={fused}) is wrong"
+        ref = buf.clone()
+        dist.broadcast(ref, 0)
+        assert torch.equal(ref, buf), f"rank {RANK}: ranks disagree after the compressed all-reduce ({wire})"
+        st = ring.core.stats()
+        wes = 2 if wire == "bf16" else 1
+        assert st["bytes_sent"] <= 2 * (WORLD - 1) * (count // WORLD + 128) * wes, st
+        dist.barrier()
+    if RANK == 0:
+        print(f"compressed transport-ring all-reduce ok (world {WORLD})", flush=True)
     ring.close()
     teardown()
 

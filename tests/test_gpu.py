@@ -219,3 +219,8 @@ def test_fused_sgd_many_staggered_ctas_2gpu():
 def test_transport_ring_allreduce_2gpu():
     """The all-reduce that rides the transport: fused isend-reduce hops between plugin connections, on real NVLink."""
     _run_worker("transport_ring", 2, timeout=300)
+
+
+@pytest.mark.multigpu
+def test_transport_ring_compressed_allreduce_2gpu():
+    _run_worker("transport_ring_compressed", 2)

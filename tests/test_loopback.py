@@ -318,7 +318,7 @@ def test_per_gpu_virtual_devices():
     assert not any(p["name"].startswith("bnet-gpu") for p in json.loads(out.stdout.splitlines()[-1]))
 
 
-def _run_tring(world, count, dtype, piece, inflight, timeout=180):
+def _run_tring(world, count, dtype, piece, inflight, timeout=180, extra_env=None):
     import json
     import subprocess
     import sys
@@ -326,6 +326,7 @@ def _run_tring(world, count, dtype, piece, inflight, timeout=180):
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, BNET_FAKE_CUDA="1", BNET_NVL="1", PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    env.update(extra_env or {})
     with tempfile.TemporaryDirectory() as d:
         procs = [subprocess.Popen([sys.executable, os.path.join(root, "tests", "tring_worker.py"), str(r), str(world), d, str(count),
                                    dtype, str(piece), str(inflight)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
@@ -354,6 +355,36 @@ def test_transport_ring_allreduce_with_fused_isend_reduce(world, count, dtype, p
     assert all(o["ok"] for o in outs), outs
     assert all(o["transport"] == "nvl" for o in outs)
     assert all(o["stats"]["messages"] >= 2 * (world - 1) for o in outs)
+
+
+@pytest.mark.parametrize("world,count,wire,fused,piece,inflight", [
+    (2, 1 << 16, "bf16", 1, 16384, 4), (3, 100003, "e4m3", 1, 8192, 8), (4, 1 << 18, "e4m3", 0, 65536, 16),
+    (5, 777, "bf16", 0, 4096, 2), (8, 300000, "e4m3", 1, 32768, 16), (4, 50000, "e5m2", 1, 4096, 8)])
+def test_transport_ring_compressed_allreduce(world, count, wire, fused, piece, inflight):
+    """fp32 all-reduce with a narrower format on the wire (K5: the cast fused into the transport).  Fused mode: every
+    reduce-scatter hop is isend_op(OP_CAST_F32_TO_<wire>) into the next rank's wire mirror, the receiver accumulates from
+    it (OP_ACC_<wire>_TO_F32); unfused mode quantises locally and sends the narrow bytes with a plain isend.  The all-gather
+    forwards the owner's quantised segment unchanged, so all ranks end with identical bits; the link carries
+    count * wire_bytes * 2(n-1)/n bytes per rank instead of 4x / 2x that."""
+    outs = _run_tring(world, count, f"c:{wire}:{fused}", piece, inflight)
+    assert all(o["ok"] for o in outs), outs
+    assert all(o["transport"] == "nvl" for o in outs)
+    assert len({o["digest"] for o in outs}) == 1, "ranks disagree on the result"
+    wes = 2 if wire == "bf16" else 1
+    seg = -(-count // world)
+    for o in outs:     # what left each rank: 2(n-1) segments in the wire format (segments are padded to 64 elements)
+        assert o["stats"]["bytes_sent"] <= 2 * (world - 1) * (seg + 64) * wes
+        assert o["stats"]["bytes_sent"] >= 2 * (world - 1) * (seg - 64 * world) * wes * 0.9
+
+
+@pytest.mark.parametrize("impl", ["BASIC", "TOKIO"])
+def test_transport_ring_compressed_allreduce_over_tcp(impl):
+    """The same compressed all-reduce between hosts: the NVLink transport off, the narrow bytes travel over the TCP streams
+    (unfused mode: quantise into the wire mirror, plain isend) — where a 4x smaller message pays most."""
+    outs = _run_tring(3, 70001, "c:e4m3:0", 8192, 8, extra_env={"BNET_NVL": "0", "TRING_WIRE_HOST": "1", "BNET_IMPLEMENT": impl})
+    assert all(o["ok"] for o in outs), outs
+    assert all(o["transport"].startswith("tcp") for o in outs), outs
+    assert len({o["digest"] for o in outs}) == 1
 
 
 def test_nccl_tuner_plugin_picks_the_protocol_by_size():

@@ -1,7 +1,8 @@
 """One rank of the transport-ring all-reduce test (tests/test_loopback.py::test_transport_ring_*): the ring rides the
 plugin's NVL transport with emulated device memory (BNET_FAKE_CUDA=1), so the fused isend-reduce protocol — op codes
 in the request, accumulate into the receiver's registered buffer, FIFO matching, piece pipelining — runs without a GPU.
-usage: tring_worker.py <rank> <world> <dir> <count> <dtype f32|bf16> <piece_bytes> <inflight> [rounds]"""
+usage: tring_worker.py <rank> <world> <dir> <count> <dtype f32|bf16> <piece_bytes> <inflight> [rounds]
+       dtype "c:<wire>:<fused 0|1>" runs the compressed all-reduce (fp32 data, bf16 / e4m3 / e5m2 on the wire)."""
 import ctypes as C
 import json
 import os
@@ -21,7 +22,9 @@ from bagua_net_b200.utils.native import load  # noqa: E402
 lib = load()
 lib.bnet_fake_cuda_alloc.restype = C.c_void_p
 lib.bnet_fake_cuda_alloc.argtypes = [C.c_size_t]
-es = 4 if dtype == "f32" else 2
+compressed = dtype.startswith("c:")
+wire, fused = (dtype.split(":")[1], dtype.split(":")[2] == "1") if compressed else (None, False)
+es = 2 if dtype == "bf16" else 4
 nbytes = max(count * es, 64)
 ptr = lib.bnet_fake_cuda_alloc(nbytes + 64)
 assert ptr
@@ -37,12 +40,25 @@ while not os.path.exists(nxt):
     assert time.time() - t0 < 60
     time.sleep(0.01)
 core.connect(open(nxt, "rb").read())
-core.register(ptr, nbytes)
+if not compressed or fused:
+    core.register(ptr, nbytes)
+if compressed:
+    wbytes = max(count * (2 if wire == "bf16" else 1), 64)
+    wptr = lib.bnet_fake_cuda_alloc(wbytes + 64)
+    assert wptr
+    core.register_wire(wptr, wbytes, device_memory=os.environ.get("TRING_WIRE_HOST") != "1")
 
 ok = True
 for rnd in range(rounds):
     # small integers: exact in bf16 and in any summation order
-    if dtype == "f32":
+    if compressed:
+        # values {-1, 0, 1, 2} x 0.25: every partial sum of up to 8 ranks is k/4 with |k| <= 16 — exact in bf16 and, scaled by
+        # 4, an integer <= 16 that e4m3 (3 mantissa bits) and e5m2 (2 bits: {0..4, 6, 8, 12, 16} only) may have to round
+        a = np.frombuffer(raw, dtype=np.float32, count=count)
+        gen = lambda r: (((np.arange(count) * 7 + r * 3 + rnd) % 4) - 1).astype(np.float32) * 0.25   # noqa: E731
+        a[:] = gen(rank)
+        want = sum(gen(r) for r in range(world)).astype(np.float32)
+    elif dtype == "f32":
         a = np.frombuffer(raw, dtype=np.float32, count=count)
         a[:] = ((np.arange(count) * 7 + rank * 3 + rnd) % 17 - 8).astype(np.float32)
         want = sum(((np.arange(count) * 7 + r * 3 + rnd) % 17 - 8) for r in range(world)).astype(np.float32)
@@ -56,16 +72,25 @@ for rnd in range(rounds):
     for r in range(world):
         while not os.path.exists(os.path.join(d, f"ready{rnd}_{r}")):
             time.sleep(0.002)
-    core.all_reduce(ptr, count, 0 if dtype == "f32" else 1, piece, inflight)
-    if dtype == "f32":
+    if compressed:
+        core.all_reduce_compressed(ptr, count, wire, 4.0, fused, piece, inflight)
+    else:
+        core.all_reduce(ptr, count, 0 if dtype == "f32" else 1, piece, inflight)
+    if dtype == "f32" or compressed:
         got = np.frombuffer(raw, dtype=np.float32, count=count).copy()
     else:
         got = (np.frombuffer(raw, dtype=np.uint16, count=count).astype(np.uint32) << 16).view(np.float32)
-    ok = ok and bool(np.array_equal(got, want))
+    if compressed and wire == "e5m2":
+        # 2 mantissa bits: a partial sum may be rounded at every hop; the result stays within the format's spacing of the
+        # true sum, and — what the protocol promises — it is the SAME on every rank (checked by the parent through `digest`)
+        ok = ok and bool(np.all(np.abs(got - want) <= 1.5))
+    else:
+        ok = ok and bool(np.array_equal(got, want))
+    digest = int(np.frombuffer(got.tobytes(), dtype=np.uint32).astype(np.uint64).sum() % (1 << 61))
     open(os.path.join(d, f"done{rnd}_{rank}"), "w").close()
     for r in range(world):
         while not os.path.exists(os.path.join(d, f"done{rnd}_{r}")):
             time.sleep(0.002)
 st = core.stats()
-print(json.dumps({"ok": ok, "transport": core.transport, "stats": st}))
+print(json.dumps({"ok": ok, "transport": core.transport, "stats": st, "digest": digest}))
 core.close()
