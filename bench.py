@@ -56,7 +56,8 @@ def reference_arm(args):
     probe = os.path.join(ROOT, "baseline", "_ref")
     if os.path.isdir(probe) and any(f.endswith(".so") for _, _, fs in os.walk(probe) for f in fs):
         why = "baseline/_ref exists but holds no loadable ncclNet v6+ plugin"
-    print(json.dumps({"impl": "reference", "unavailable": why}), flush=True)
+    if os.environ.get("RANK", "0") == "0":          # (launched under torchrun for N > 1: one line, from rank 0)
+        print(json.dumps({"impl": "reference", "unavailable": why}), flush=True)
     return 0
 
 

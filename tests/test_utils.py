@@ -363,3 +363,21 @@ def test_bench_isolated_self_check_classifies_child_outcomes(monkeypatch):
     # and for real, without a GPU: the child cannot even select a device -> "unrelated reason" -> None
     monkeypatch.undo()
     assert mod.isolated_self_check("self_check", 0, timeout=120) is None
+
+
+def test_shell_scripts_parse():
+    """Every shell script of the repo at least parses (the GPU session runner cannot be exercised without a GPU)."""
+    import glob
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    scripts = sorted(glob.glob(os.path.join(root, "tools", "*.sh")) + glob.glob(os.path.join(root, "ci", "*.sh")))
+    assert scripts
+    for s in scripts:
+        r = subprocess.run(["bash", "-n", s], capture_output=True, text=True)
+        assert r.returncode == 0, f"{s}: {r.stderr}"
+    # the recipe names documented in the header of the session runner are the ones its case statement knows
+    src = open(os.path.join(root, "tools", "gpu_session.sh")).read()
+    header = [ln.split()[1] for ln in src.splitlines() if ln.startswith("#   ") and len(ln.split()) > 2 and ln[4] != " " and not ln.startswith("#   gpurun")]
+    for name in header:
+        assert f"{name})" in src or f"|{name})" in src or f"{name}|" in src, name
