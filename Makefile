@@ -26,7 +26,7 @@ LDFLAGS   := -shared -cudart static -Xcompiler -pthread -ldl -lrt
 
 HOST_SRCS := csrc/core/common.cc csrc/core/netif.cc csrc/core/telemetry.cc csrc/core/engine.cc \
              csrc/transport/tcp_threads.cc csrc/transport/tcp_async.cc csrc/transport/nvl.cc \
-             csrc/cuda/cuda_iface.cc csrc/coll/transport_ring.cc csrc/plugin/tuner.cc csrc/capi.cc
+             csrc/cuda/cuda_iface.cc csrc/coll/transport_ring.cc csrc/coll/transport_mesh.cc csrc/plugin/tuner.cc csrc/capi.cc
 CU_SRCS   := $(wildcard csrc/cuda/*.cu)
 
 HOST_OBJS := $(patsubst csrc/%.cc,$(BUILD)/%.o,$(HOST_SRCS))

@@ -39,6 +39,16 @@ def _lib():
         lib.bnet_tring_last_error.restype = C.c_char_p
         lib.bnet_tring_transport.argtypes = [vp]
         lib.bnet_tring_transport.restype = C.c_char_p
+        lib.bnet_tmesh_create.argtypes = [i, i, i, vp, C.POINTER(vp)]
+        lib.bnet_tmesh_connect.argtypes = [vp, vp, i]
+        lib.bnet_tmesh_register.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t]
+        lib.bnet_tmesh_allreduce.argtypes = [vp, vp, vp, C.c_size_t, i, i, C.c_size_t, i, i]
+        lib.bnet_tmesh_stats.argtypes = [vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+        lib.bnet_tmesh_destroy.argtypes = [vp]
+        lib.bnet_tmesh_last_error.argtypes = [vp]
+        lib.bnet_tmesh_last_error.restype = C.c_char_p
+        lib.bnet_tmesh_transport.argtypes = [vp]
+        lib.bnet_tmesh_transport.restype = C.c_char_p
         lib._tring_decl = True
     return lib
 
@@ -157,6 +167,105 @@ class TransportRing:
         torch.cuda.current_stream(t.device).synchronize()
         self.core.all_reduce_compressed(t.data_ptr(), t.numel(), wire, scale, fused, piece_elems, inflight)
         return t
+
+    def close(self):
+        self.core.close()
+
+
+class MeshCore:
+    """The native one-shot all-reduce over a full mesh of plugin connections (csrc/coll/transport_mesh.cc) without torch:
+    callers exchange the 128-byte handles themselves (used by the CPU tests)."""
+
+    def __init__(self, rank: int, world: int, net_dev: int = 0):
+        self.lib = _lib()
+        self.rank, self.world = rank, world
+        self._h = C.c_void_p()
+        self._handle = C.create_string_buffer(HANDLE_BYTES)
+        if self.lib.bnet_tmesh_create(rank, world, net_dev, self._handle, C.byref(self._h)) != 0:
+            raise RuntimeError("bnet_tmesh_create failed")
+
+    @property
+    def handle(self) -> bytes:
+        return bytes(self._handle.raw)
+
+    def _err(self) -> str:
+        return self.lib.bnet_tmesh_last_error(self._h).decode()
+
+    def connect(self, handles: list, timeout_ms: int = 30000):
+        assert len(handles) == self.world
+        blob = C.create_string_buffer(b"".join(bytes(h).ljust(HANDLE_BYTES, b"\0") for h in handles), HANDLE_BYTES * self.world)
+        if self.lib.bnet_tmesh_connect(self._h, blob, timeout_ms) != 0:
+            raise RuntimeError(f"mesh connect: {self._err()}")
+
+    @property
+    def transport(self) -> str:
+        return self.lib.bnet_tmesh_transport(self._h).decode()
+
+    def register(self, in_ptr: int, in_bytes: int, out_ptr: int, out_bytes: int):
+        if self.lib.bnet_tmesh_register(self._h, C.c_void_p(in_ptr), in_bytes, C.c_void_p(out_ptr), out_bytes) != 0:
+            raise RuntimeError(f"mesh register: {self._err()}")
+
+    def all_reduce(self, in_ptr: int, out_ptr: int, count: int, in_dtype: int, out_dtype: int, piece_bytes: int = 1 << 20,
+                   inflight: int = 8, timeout_ms: int = 60000):
+        if self.lib.bnet_tmesh_allreduce(self._h, C.c_void_p(in_ptr), C.c_void_p(out_ptr), count, in_dtype, out_dtype, piece_bytes,
+                                         inflight, timeout_ms) != 0:
+            raise RuntimeError(f"mesh all-reduce: {self._err()}")
+
+    def stats(self) -> dict:
+        m, b = C.c_ulonglong(0), C.c_ulonglong(0)
+        self.lib.bnet_tmesh_stats(self._h, C.byref(m), C.byref(b))
+        return {"messages": int(m.value), "bytes_sent": int(b.value)}
+
+    def close(self):
+        if self._h:
+            self.lib.bnet_tmesh_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+class TransportMesh:
+    """One-shot all-reduce over the bnet transport: every rank sends its input to every peer once and the sending GPU's
+    kernel accumulates it into the peer's output while it moves (``red.global.add`` over NVLink).  One network step — the
+    latency-optimal companion of :class:`TransportRing` for messages up to a few MiB.
+
+        mesh = TransportMesh()
+        x, y = mesh.buffers(numel, torch.bfloat16, torch.float32)     # registered input / output
+        x.copy_(grad); mesh.all_reduce(x, y)                           # y = sum over ranks of x, accumulated in fp32
+    """
+
+    def __init__(self, group=None, net_dev: int = 0):
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world < 2:
+            raise ValueError("a mesh needs at least two ranks")
+        self.core = MeshCore(self.rank, self.world, net_dev)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, self.core.handle, group=group)
+        self.core.connect(handles)
+        dist.barrier(group=group)
+        self._in = self._out = None
+
+    @property
+    def transport(self) -> str:
+        return self.core.transport
+
+    def buffers(self, numel: int, in_dtype=torch.bfloat16, out_dtype=None, device=None):
+        out_dtype = in_dtype if out_dtype is None else out_dtype
+        if (in_dtype, out_dtype) not in ((torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16), (torch.bfloat16, torch.float32)):
+            raise TypeError("supported: fp32 -> fp32, bf16 -> bf16, bf16 -> fp32")
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        self._in = torch.zeros(numel, dtype=in_dtype, device=device)
+        self._out = torch.zeros(numel, dtype=out_dtype, device=device)
+        self.core.register(self._in.data_ptr(), self._in.numel() * self._in.element_size(), self._out.data_ptr(),
+                           self._out.numel() * self._out.element_size())
+        return self._in, self._out
+
+    def all_reduce(self, x: torch.Tensor, out: torch.Tensor, piece_bytes: int = 1 << 20, inflight: int = 8) -> torch.Tensor:
+        """out = sum over ranks of x (both inside the registered buffers, same number of elements)."""
+        if x.numel() != out.numel() or x.dtype not in _DT or out.dtype not in _DT:
+            raise TypeError("mesh all-reduce: fp32 / bf16 tensors of equal length")
+        torch.cuda.current_stream(x.device).synchronize()
+        self.core.all_reduce(x.data_ptr(), out.data_ptr(), x.numel(), _DT[x.dtype], _DT[out.dtype], piece_bytes, inflight)
+        return out
 
     def close(self):
         self.core.close()

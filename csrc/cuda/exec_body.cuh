@@ -92,26 +92,50 @@ BNET_XD void st8(void* p, const uint2& v) {  // p is 8-byte aligned
   memcpy(p, &v, 8);
 #endif
 }
-// fire-and-forget reductions at system scope (one packet over NVLink, no return value)
+// fire-and-forget reductions at system scope (one packet over NVLink, no return value).  The host versions are atomic too
+// (compare-and-swap on the element's bits): in the emulation several sender PROCESSES may accumulate into one shared
+// buffer at the same time, exactly like several GPUs into one output (csrc/coll/transport_mesh.cc).
+#if !defined(__CUDA_ARCH__)
+inline void host_atomic_add_f32(float* p, float v) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(p);
+  uint32_t old = __atomic_load_n(u, __ATOMIC_RELAXED), want;
+  do {
+    float f;
+    memcpy(&f, &old, 4);
+    f += v;
+    memcpy(&want, &f, 4);
+  } while (!__atomic_compare_exchange_n(u, &old, want, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+}
+inline void host_atomic_add_bf16(__nv_bfloat16* p, __nv_bfloat16 v) {
+  uint16_t* u = reinterpret_cast<uint16_t*>(p);
+  uint16_t old = __atomic_load_n(u, __ATOMIC_RELAXED), want;
+  do {
+    __nv_bfloat16 b;
+    memcpy((void*)&b, &old, 2);
+    b = __float2bfloat16(__bfloat162float(b) + __bfloat162float(v));
+    memcpy(&want, (const void*)&b, 2);
+  } while (!__atomic_compare_exchange_n(u, &old, want, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+}
+#endif
 BNET_XD void red_f32(float* p, float v) {
 #if defined(__CUDA_ARCH__)
   asm volatile("red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 #else
-  *p += v;
+  host_atomic_add_f32(p, v);
 #endif
 }
 BNET_XD void red_v4_f32(float* p, const float4& v) {
 #if defined(__CUDA_ARCH__)
   asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 #else
-  p[0] += v.x; p[1] += v.y; p[2] += v.z; p[3] += v.w;
+  host_atomic_add_f32(p, v.x); host_atomic_add_f32(p + 1, v.y); host_atomic_add_f32(p + 2, v.z); host_atomic_add_f32(p + 3, v.w);
 #endif
 }
 BNET_XD void red_bf16(__nv_bfloat16* p, __nv_bfloat16 v) {
 #if defined(__CUDA_ARCH__)
   atomicAdd(p, v);
 #else
-  *p = __float2bfloat16(__bfloat162float(*p) + __bfloat162float(v));
+  host_atomic_add_bf16(p, v);
 #endif
 }
 BNET_XD void red_v4_bf16x2(uint32_t* p, const int4& v) {

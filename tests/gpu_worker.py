@@ -946,6 +946,42 @@ def job_transport_ring_compressed():
     teardown()
 
 
+def job_transport_mesh():
+    """One-shot all-reduce over a full mesh of plugin connections (TransportMesh): one network step, the senders' kernels
+    accumulate into every peer's output over NVLink."""
+    from bagua_net_b200.parallel.transport_ring import TransportMesh
+
+    setup()
+    mesh = TransportMesh()
+    assert mesh.transport == "nvl", mesh.transport
+    res = []
+    for idt, odt, count in ((torch.float32, torch.float32, 1 << 18), (torch.bfloat16, torch.float32, (1 << 20) + 24),
+                            (torch.bfloat16, torch.bfloat16, 4096), (torch.float32, torch.float32, 9)):
+        x, y = mesh.buffers(count, idt, odt)
+        for rnd in range(2):
+            x.copy_(((torch.arange(count, device="cuda") * 5 + RANK + rnd) % 9 - 4).to(idt))
+            y.fill_(99)
+            torch.cuda.synchronize()
+            dist.barrier()
+            mesh.all_reduce(x, y)
+            want = sum(((torch.arange(count, device="cuda") * 5 + r + rnd) % 9 - 4).float() for r in range(WORLD))
+            assert torch.equal(y.float(), want), f"rank {RANK}: mesh all-reduce {idt}->{odt} x{count} is wrong"
+            dist.barrier()
+        if count >= (1 << 18):
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            iters = 10
+            for _ in range(iters):
+                mesh.all_reduce(x, y)
+            res.append((count * x.element_size(), (time.perf_counter() - t0) / iters))
+    if RANK == 0:
+        for nbytes, dt in res:
+            print(f"transport mesh one-shot all-reduce {nbytes >> 10} KiB: {dt * 1e6:.1f} us per call (host-timed, world {WORLD})", flush=True)
+    mesh.close()
+    teardown()
+
+
 def job_tc_conv():
     from bagua_net_b200.ops import tc_conv, tc_linear
 

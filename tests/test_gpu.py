@@ -224,3 +224,8 @@ def test_transport_ring_allreduce_2gpu():
 @pytest.mark.multigpu
 def test_transport_ring_compressed_allreduce_2gpu():
     _run_worker("transport_ring_compressed", 2)
+
+
+@pytest.mark.multigpu
+def test_transport_mesh_oneshot_allreduce_2gpu():
+    _run_worker("transport_mesh", 2)

@@ -387,6 +387,45 @@ def test_transport_ring_compressed_allreduce_over_tcp(impl):
     assert len({o["digest"] for o in outs}) == 1
 
 
+def _run_tmesh(world, count, idt, odt, piece, inflight, timeout=180):
+    import json
+    import subprocess
+    import sys
+    import tempfile
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, BNET_FAKE_CUDA="1", BNET_NVL="1", PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    with tempfile.TemporaryDirectory() as d:
+        procs = [subprocess.Popen([sys.executable, os.path.join(root, "tests", "tmesh_worker.py"), str(r), str(world), d, str(count),
+                                   idt, odt, str(piece), str(inflight)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+                 for r in range(world)]
+        outs = []
+        for p in procs:
+            try:
+                o, e = p.communicate(timeout=timeout)
+            except subprocess.TimeoutExpired:
+                for q in procs:
+                    q.kill()
+                raise
+            assert p.returncode == 0, e[-3000:]
+            outs.append(json.loads([ln for ln in o.splitlines() if ln.startswith("{")][-1]))
+    return outs
+
+
+@pytest.mark.parametrize("world,count,idt,odt,piece,inflight", [
+    (2, 1 << 16, "f32", "f32", 16384, 4), (3, 100003, "bf16", "f32", 8192, 8), (4, 1 << 17, "bf16", "bf16", 65536, 8),
+    (5, 7, "f32", "f32", 4096, 2), (8, 50000, "bf16", "f32", 16384, 8)])
+def test_transport_mesh_oneshot_allreduce(world, count, idt, odt, piece, inflight):
+    """The latency-optimal companion of the ring: a full mesh of plugin connections, ONE network step — every rank's
+    kernel accumulates its input into every peer's output (isend_op(OP_RED_ADD_* / OP_ACC_BF16_TO_F32)), after a local
+    pass initialised the output with the rank's own contribution.  Exact against the closed-form sum; the input is intact."""
+    outs = _run_tmesh(world, count, idt, odt, piece, inflight)
+    assert all(o["ok"] for o in outs), outs
+    assert all(o["transport"] == "nvl" for o in outs)
+    ies = 4 if idt == "f32" else 2
+    assert all(o["stats"]["bytes_sent"] == (world - 1) * count * ies for o in outs), outs
+
+
 def test_nccl_tuner_plugin_picks_the_protocol_by_size():
     """ncclTunerPlugin_v3/_v4 inside the net plugin library (csrc/plugin/tuner.cc): over this transport LL for tiny messages,
     Simple above, LL128 never — and no opinion at all when the device path is off."""

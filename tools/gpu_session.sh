@@ -82,7 +82,9 @@ for recipe in "$@"; do
   coll)
     TAILN=12 step coll_allreduce 240 $TR --master-port 29641 tests/gpu_worker.py allreduce
     TAILN=6 step transport_ring 200 $TR --master-port 29642 tests/gpu_worker.py transport_ring
-    TAILN=4 step fused_sgd_staggered 150 $TR --master-port 29643 tests/gpu_worker.py fused_sgd_staggered ;;
+    TAILN=4 step fused_sgd_staggered 150 $TR --master-port 29643 tests/gpu_worker.py fused_sgd_staggered
+    TAILN=4 step transport_mesh 150 $TR --master-port 29645 tests/gpu_worker.py transport_mesh
+    TAILN=4 step transport_ring_compressed 150 $TR --master-port 29646 tests/gpu_worker.py transport_ring_compressed ;;
   sweep)
     TAILN=30 step allreduce_sweep 400 $TR --master-port 29644 bench/allreduce_sweep.py ;;
   tc)
