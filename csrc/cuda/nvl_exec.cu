@@ -397,12 +397,14 @@ struct MsgArgs {
 constexpr int kMsgBatch = 16;
 struct MsgBatch {
   int n;
+  int group;                  // 0: CTAs are grouped by the hardware cluster; > 0: logical groups of that many consecutive CTAs
+                              // in a plain launch (BNET_MSG_CLUSTER=0: no co-scheduling constraint on a busy GPU)
   int first[kMsgBatch + 1];   // first cluster of message i (prefix sums); first[n] = clusters in the grid
   MsgArgs m[kMsgBatch];
 };
 __global__ void __launch_bounds__(kThreads, 1) bnet_nvl_msg_kernel(const __grid_constant__ MsgBatch b) {
-  const uint32_t crank = ptx::cluster_ctarank();
-  const uint32_t csize = ptx::cluster_nctarank();
+  const uint32_t csize = b.group > 0 ? (uint32_t)b.group : ptx::cluster_nctarank();
+  const uint32_t crank = b.group > 0 ? blockIdx.x % csize : ptx::cluster_ctarank();
   const int cid = (int)(blockIdx.x / csize);
   int i = 0;
   while (i + 1 < b.n && cid >= b.first[i + 1]) i++;
@@ -468,6 +470,7 @@ struct Exec {
   std::atomic<int> batch_n{0};     // == batch.n, readable without the lock (exec_kick's fast path)
   uint64_t batch_t0 = 0;
   uint64_t last_submit_ns = 0, burst_until_ns = 0;   // the batching window only applies while isends arrive back to back
+  bool msg_cluster = true;     // BNET_MSG_CLUSTER=0: the per-message kernel is launched without a cluster dimension
   bool tma = false;
   bool ce = false;             // BNET_COPY_ENGINE=ce: DMA copy engines + stream memory ops, no kernels at all
   int nclusters = 4;
@@ -531,6 +534,7 @@ Exec* get_exec(int dev) {
   e->min_chunk = (size_t)env_int("DEV_MIN_CHUNKSIZE", (long long)(cfg.min_chunksize < 262144 ? cfg.min_chunksize : 262144));
   if (e->min_chunk < 16) e->min_chunk = 16;
   e->persistent = env_int("PERSISTENT", 1) != 0;
+  e->msg_cluster = env_int("MSG_CLUSTER", 1) != 0;
   e->tma = env_str("COPY_ENGINE", "ldst") == "tma";
   e->ce = env_str("COPY_ENGINE", "ldst") == "ce" && driver().ok && driver().StreamWriteValue64 != nullptr;
   {
@@ -603,11 +607,13 @@ Exec* get_exec(int dev) {
         // (two messages, three clusters: the batch lookup, both counters and all four completion words)
         MsgBatch wb{};
         wb.n = 2;
+        wb.group = e->msg_cluster ? 0 : e->cluster_size;
         wb.first[0] = 0; wb.first[1] = 2; wb.first[2] = 3;
         wb.m[0] = MsgArgs{nullptr, nullptr, 0, 64, (uint64_t*)wdp + 1, 7, (uint64_t*)wdp + 2, 9, e->counters, OP_FLUSH, 1.0f};
         wb.m[1] = MsgArgs{nullptr, nullptr, 0, 64, (uint64_t*)wdp + 3, 7, nullptr, 0, e->counters + 1, OP_FLUSH, 1.0f};
         void* margs[] = {&wb};
-        cudaError_t e3 = launch_cluster(bnet_nvl_msg_kernel, 3 * e->cluster_size, e->cluster_size, 0, e->streams[0].stream, margs);
+        cudaError_t e3 = launch_cluster(bnet_nvl_msg_kernel, 3 * e->cluster_size, e->msg_cluster ? e->cluster_size : 1, 0,
+                                        e->streams[0].stream, margs);
         if (e3 == cudaSuccess) e3 = cudaStreamSynchronize(e->streams[0].stream);
         if (e3 != cudaSuccess || ((volatile uint64_t*)wflag)[1] != 7 || ((volatile uint64_t*)wflag)[2] != 9 ||
             ((volatile uint64_t*)wflag)[3] != 7) {
@@ -750,11 +756,12 @@ int flush_batch_locked(Exec* e) {
   if (b.n == 0) return 0;
   Stream& s = e->streams[e->rr];                    // the stream rotates per launch: successive bursts overlap on the device
   e->rr = (e->rr + 1) % e->streams.size();
+  b.group = e->msg_cluster ? 0 : e->cluster_size;
   void* args[] = {&b};
   cudaError_t err;
   {
     CallScope cl_("cudaLaunchKernelEx(msg batch)");
-    err = launch_cluster(bnet_nvl_msg_kernel, b.first[b.n] * e->cluster_size, e->cluster_size, 0, s.stream, args);
+    err = launch_cluster(bnet_nvl_msg_kernel, b.first[b.n] * e->cluster_size, e->msg_cluster ? e->cluster_size : 1, 0, s.stream, args);
   }
   e->stats.launches++;
   e->stats.batched += (uint64_t)b.n;

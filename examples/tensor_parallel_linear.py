@@ -1,10 +1,11 @@
-"""Tensor-parallel linear layers whose collective is fused into the GEMM kernel (csrc/cuda/tc_gemm.cu; opt-in, BNET_TC=1):
+"""Tensor-parallel linear layers whose collective is fused into the GEMM kernel (csrc/cuda/tc_gemm.cu; `BNET_TC=0` disables):
 
   row-parallel     y = sum_r x[:, K_r] @ w[:, K_r].T        epilogue adds every tile into all ranks' outputs (all-reduce)
   reduce-scatter   same, each rank keeps its row block       epilogue sends a tile only to its owner
   all-gather       y = [x_0; x_1; ...] @ w.T                 peers' row shards are TMA-loaded over NVLink as operands
 
-The kernel has not been validated on hardware yet: it refuses to be used unless its self-check passes."""
+The kernel checks itself against an fp32 reference on this GPU before it is used (`tc_linear.self_check`); the row-parallel
+variant is covered by `tests/test_gpu.py::test_tcgen05_row_parallel_linear_2gpu`."""
 import torch
 
 from bagua_net_b200.ops import tc_linear
@@ -16,7 +17,7 @@ def main():
     comm = SymmComm(256 << 20)
     if not (tc_linear.enabled() and tc_linear.self_check(verbose=comm.rank == 0)):
         if comm.rank == 0:
-            print("tcgen05 path not enabled (BNET_TC=1) or its self-check failed on this GPU")
+            print("tcgen05 path disabled (BNET_TC=0), unsupported on this GPU, or its self-check failed")
         return
     M, N, K = 512, 4096, 8192
     torch.manual_seed(0)

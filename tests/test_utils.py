@@ -381,3 +381,24 @@ def test_shell_scripts_parse():
     header = [ln.split()[1] for ln in src.splitlines() if ln.startswith("#   ") and len(ln.split()) > 2 and ln[4] != " " and not ln.startswith("#   gpurun")]
     for name in header:
         assert f"{name})" in src or f"|{name})" in src or f"{name}|" in src, name
+
+
+def test_plugin_environment_helper(monkeypatch):
+    """What `python -m bagua_net_b200.utils.env` hands to NCCL: the plugin + tuner names, forced net transport, GDR, and the
+    module-loading mode (eager by default; lazy on request; never overriding what the user exported)."""
+    from bagua_net_b200.utils.env import nccl_plugin_env
+
+    for k in ("CUDA_MODULE_LOADING", "CUDA_DEVICE_MAX_CONNECTIONS", "BNET_TUNER", "NCCL_BUFFSIZE"):
+        monkeypatch.delenv(k, raising=False)
+    e = nccl_plugin_env(force_net=True)
+    assert e["NCCL_NET_PLUGIN"] == "bnet" and e["NCCL_NET"] == "BNet" and e["NCCL_TUNER_PLUGIN"] == "bnet"
+    assert e["NCCL_P2P_DISABLE"] == "1" and e["NCCL_SHM_DISABLE"] == "1" and e["NCCL_NET_GDR_LEVEL"] == "SYS"
+    assert e["CUDA_MODULE_LOADING"] == "EAGER" and e["LD_LIBRARY_PATH"].split(os.pathsep)[0].endswith("lib")
+    assert "CUDA_MODULE_LOADING" not in nccl_plugin_env(eager_modules=False)
+    monkeypatch.setenv("CUDA_MODULE_LOADING", "LAZY")
+    assert "CUDA_MODULE_LOADING" not in nccl_plugin_env()            # the user's choice stands
+    monkeypatch.setenv("BNET_TUNER", "0")
+    assert "NCCL_TUNER_PLUGIN" not in nccl_plugin_env()
+    assert nccl_plugin_env(gdr=False)["BNET_GDR"] == "0"
+    assert nccl_plugin_env(tuned=True)["NCCL_BUFFSIZE"] == str(32 << 20)
+    assert "NCCL_TUNER_PLUGIN" not in nccl_plugin_env(plugin="bnetx")

@@ -71,7 +71,7 @@ for recipe in "$@"; do
   stock)
     TAILN=16 step stock 150 $ARP $SWEEP ;;
   knobs)
-    i=0; IFS=';' read -ra VARIANTS <<< "${KNOBS:-BNET_MSG_BATCH_US=20;NCCL_MIN_NCHANNELS=8,NCCL_MAX_NCHANNELS=8;NCCL_BUFFSIZE=8388608}"
+    i=0; IFS=';' read -ra VARIANTS <<< "${KNOBS:-BNET_MSG_BATCH_US=20;NCCL_MIN_NCHANNELS=8,NCCL_MAX_NCHANNELS=8;NCCL_BUFFSIZE=8388608;BNET_MSG_CLUSTER=0;BNET_EXEC_MODE=ce}"
     TAILN=4 step knob_base 90 env $PLUG BNET_EXEC_STATS=1 $ARP -b 32M -e 128M -f 4 -n 8 -w 2
     for v in "${VARIANTS[@]}"; do i=$((i+1)); echo "variant $i: $v"; TAILN=4 step knob_$i 90 env $PLUG BNET_EXEC_STATS=1 ${v//,/ } $ARP -b 32M -e 128M -f 4 -n 8 -w 2; done ;;
   debug)
