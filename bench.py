@@ -18,7 +18,9 @@ measures the same metric on N B200s of one box:
 
 At N > 1 the default run also measures the two DDP arms in child processes (bounded by a timeout) and reports them
 under extra.nccl_plugin / extra.nccl_stock next to the headline: img/s, the all-reduce bus bandwidth 8 B - 128 MiB
-over that path, and a cross-rank parameter checksum.  --no-arms skips them.
+over that path, and a cross-rank parameter checksum.  --no-arms skips them.  The run then repeats the arms on ResNet-50
+(BASELINE config #4; extra.resnet50_bnet at any N, extra.resnet50_nccl_plugin / _nccl_stock at N > 1) as short child
+jobs that only start while the run is younger than --resnet-deadline; --no-resnet skips them.
 
 Prints ONE JSON line on rank 0 (contract in the task statement).
 """
@@ -208,7 +210,7 @@ def isolated_self_check(name: str, local: int, timeout: float = 240.0):
 ARM_SIZES = (8, 1 << 10, 64 << 10, 1 << 20, 16 << 20, 128 << 20)   # all-reduce message sizes of the DDP arms (bytes)
 
 
-def run_child_arm(comm_name: str, args, rank: int, world: int, port_offset: int, timeout: float):
+def run_child_arm(comm_name: str, args, rank: int, world: int, port_offset: int, timeout: float, model: str | None = None):
     """One DDP arm (`--comm nccl-plugin` / `--comm nccl`) as a child process per rank: own CUDA context, own NCCL
     (with or without the plugin on LD_LIBRARY_PATH), own rendezvous port.  Every rank of the parent job calls this at
     the same time; rank 0 returns the child's JSON (or a status dict), the others None.  A child that outlives
@@ -222,15 +224,19 @@ def run_child_arm(comm_name: str, args, rank: int, world: int, port_offset: int,
     # parent job's MASTER_PORT only, so rank 0 of the child job must host the TCPStore itself
     for k in [k for k in env if k.startswith("TORCHELASTIC_")] + ["GROUP_RANK", "ROLE_RANK", "ROLE_NAME", "ROLE_WORLD_SIZE", "GROUP_WORLD_SIZE"]:
         env.pop(k, None)
-    env["BNET_BENCH_FUSED_VERDICT"] = "0" if args.no_fused or getattr(args, "fused_failed", False) else "1"
+    model = model or args.model
+    if model == args.model:
+        env["BNET_BENCH_FUSED_VERDICT"] = "0" if args.no_fused or getattr(args, "fused_failed", False) else "1"
+    else:
+        env.pop("BNET_BENCH_FUSED_VERDICT", None)   # another model family: the child checks its own layer kernels
     env.pop("BNET_BENCH_REEXEC", None)
     log_dir = os.environ.get("BNET_BENCH_LOG_DIR") or tempfile.gettempdir()
     os.makedirs(log_dir, exist_ok=True)
-    out_path = os.path.join(log_dir, f"bnet_bench_arm_{comm_name}_{os.getppid()}_{env['MASTER_PORT']}.json")
+    out_path = os.path.join(log_dir, f"bnet_bench_arm_{model}_{comm_name}_{os.getppid()}_{env['MASTER_PORT']}.json")
     if rank == 0 and os.path.exists(out_path):
         os.unlink(out_path)
     cmd = [sys.executable, os.path.abspath(__file__), "--comm", comm_name, "--gpus", str(world), "--steps", str(min(args.steps, 10)),
-           "--warmup", "3", "--model", args.model, "--batch", str(args.batch), "--image", str(args.image), "--no-e2e",
+           "--warmup", "3", "--model", model, "--batch", str(args.batch), "--image", str(args.image), "--no-e2e",
            "--no-arms", "--child-json", out_path]
     if args.no_fused:
         cmd.append("--no-fused")
@@ -282,6 +288,10 @@ def main() -> int:
     ap.add_argument("--no-extra", action="store_true", help="skip the all-reduce busbw side measurement")
     ap.add_argument("--no-arms", action="store_true", help="N > 1: skip the NCCL-over-plugin / stock-NCCL DDP arms")
     ap.add_argument("--arm-timeout", type=float, default=150.0, help="seconds one DDP arm (child processes) may take")
+    ap.add_argument("--no-resnet", action="store_true", help="skip the ResNet-50 side arms (BASELINE config #4)")
+    ap.add_argument("--resnet-timeout", type=float, default=100.0, help="seconds one ResNet-50 arm may take")
+    ap.add_argument("--resnet-deadline", type=float, default=170.0,
+                    help="no ResNet-50 arm starts once the run is this many seconds old")
     ap.add_argument("--no-prefetch", action="store_true", help="e2e: per-step API instead of the prefetching loop")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel of the step individually (no CUDA graph)")
     ap.add_argument("--no-fused", action="store_true", help="eager bias/ReLU/pool instead of the fused sm_100a conv blocks")
@@ -643,6 +653,30 @@ def main() -> int:
             if rank == 0:
                 arms[key] = res
 
+    # ---- BASELINE config #4: the same three arms on ResNet-50 (child processes, short, under an overall deadline) ----
+    # The headline stays VGG16 (the model the reference quotes its speed-up on); the reference's README benchmarks
+    # ResNet-50 the same way (reference README.md:52-84), so the run reports it next to the headline while the GPUs are here.
+    if (args.comm == "bnet" and args.model == "vgg16" and not args.no_arms and not args.no_resnet
+            and not os.environ.get("BNET_BENCH_CHILD")):
+        sync_all()
+        second = [("resnet50_bnet", "bnet")] + ([("resnet50_nccl_plugin", "nccl-plugin"), ("resnet50_nccl_stock", "nccl")] if world > 1 else [])
+        for i, (key, comm_name) in enumerate(second):
+            # every rank takes rank 0's decision: an arm starts only while the whole run is younger than the deadline
+            go = torch.tensor([1 if time.time() - _T0 < args.resnet_deadline else 0], device=dev, dtype=torch.int32)
+            if world > 1:
+                dist.broadcast(go, 0)
+            if int(go.item()) == 0:
+                if rank == 0:
+                    arms[key] = {"status": f"skipped: the run was already {time.time() - _T0:.0f} s old (deadline {args.resnet_deadline:.0f} s)"}
+                continue
+            note(f"arm resnet50/{comm_name}: child processes (timeout {args.resnet_timeout:.0f} s)")
+            res = run_child_arm(comm_name, args, rank, world, 175 + 37 * i, args.resnet_timeout, model="resnet50")
+            note(f"arm resnet50/{comm_name}: {res.get('status') if res else None}")
+            if world > 1:
+                dist.barrier()
+            if rank == 0:
+                arms[key] = res
+
     if rank == 0:
         opt_desc = (f"sgd(lr={lr},momentum={mom},wd={wd}) fused into the collective" if args.comm == "bnet"
                     else f"torch.optim.SGD(lr={lr},momentum={mom},wd={wd})")
@@ -669,7 +703,8 @@ def main() -> int:
             # keep the arm compact: its headline, its sweep, its checks
             keep = {k: res.get(k) for k in ("status", "wall_s", "value", "ms_per_step", "log_tail") if res.get(k) is not None}
             cfg = res.get("config") or {}
-            keep.update({k: cfg.get(k) for k in ("comm", "cuda_graph", "fused_conv_blocks", "graph_note") if cfg.get(k) is not None})
+            keep.update({k: cfg.get(k) for k in ("model", "comm", "path", "cuda_graph", "fused_conv_blocks", "fused_note", "graph_note")
+                         if cfg.get(k) is not None})
             ex = res.get("extra") or {}
             keep.update({k: ex[k] for k in ("allreduce_busbw_gbs_bf16", "allreduce_time_us", "allreduce_exact", "allreduce_error")
                          if k in ex})
