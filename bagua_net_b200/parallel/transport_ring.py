@@ -43,6 +43,7 @@ def _lib():
         lib.bnet_tmesh_connect.argtypes = [vp, vp, i]
         lib.bnet_tmesh_register.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t]
         lib.bnet_tmesh_allreduce.argtypes = [vp, vp, vp, C.c_size_t, i, i, C.c_size_t, i, i]
+        lib.bnet_tmesh_allreduce2.argtypes = [vp, vp, vp, C.c_size_t, i, i, i, C.c_size_t, i, i]
         lib.bnet_tmesh_stats.argtypes = [vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
         lib.bnet_tmesh_destroy.argtypes = [vp]
         lib.bnet_tmesh_last_error.argtypes = [vp]
@@ -172,9 +173,12 @@ class TransportRing:
         self.core.close()
 
 
+MESH_ALGOS = {"one-shot": 0, "two-shot": 1}
+
+
 class MeshCore:
-    """The native one-shot all-reduce over a full mesh of plugin connections (csrc/coll/transport_mesh.cc) without torch:
-    callers exchange the 128-byte handles themselves (used by the CPU tests)."""
+    """The native all-reduces over a full mesh of plugin connections (csrc/coll/transport_mesh.cc: one-shot and two-shot)
+    without torch: callers exchange the 128-byte handles themselves (used by the CPU tests)."""
 
     def __init__(self, rank: int, world: int, net_dev: int = 0):
         self.lib = _lib()
@@ -206,10 +210,10 @@ class MeshCore:
             raise RuntimeError(f"mesh register: {self._err()}")
 
     def all_reduce(self, in_ptr: int, out_ptr: int, count: int, in_dtype: int, out_dtype: int, piece_bytes: int = 1 << 20,
-                   inflight: int = 8, timeout_ms: int = 60000):
-        if self.lib.bnet_tmesh_allreduce(self._h, C.c_void_p(in_ptr), C.c_void_p(out_ptr), count, in_dtype, out_dtype, piece_bytes,
-                                         inflight, timeout_ms) != 0:
-            raise RuntimeError(f"mesh all-reduce: {self._err()}")
+                   inflight: int = 8, timeout_ms: int = 60000, algo: str = "one-shot"):
+        if self.lib.bnet_tmesh_allreduce2(self._h, C.c_void_p(in_ptr), C.c_void_p(out_ptr), count, in_dtype, out_dtype,
+                                          MESH_ALGOS[algo], piece_bytes, inflight, timeout_ms) != 0:
+            raise RuntimeError(f"mesh all-reduce ({algo}): {self._err()}")
 
     def stats(self) -> dict:
         m, b = C.c_ulonglong(0), C.c_ulonglong(0)
@@ -223,13 +227,19 @@ class MeshCore:
 
 
 class TransportMesh:
-    """One-shot all-reduce over the bnet transport: every rank sends its input to every peer once and the sending GPU's
-    kernel accumulates it into the peer's output while it moves (``red.global.add`` over NVLink).  One network step — the
-    latency-optimal companion of :class:`TransportRing` for messages up to a few MiB.
+    """All-reduce over a full mesh of bnet connections; the sending GPU's kernel accumulates into the peer's buffer while
+    it moves the data (``red.global.add`` over NVLink).
+
+    ``algo="one-shot"``: every rank sends its input to every peer once — one network step, the latency-optimal companion
+    of :class:`TransportRing` for messages up to a few MiB.  ``algo="two-shot"``: reduce-scatter into the slice owners, then
+    all-gather by copy — two steps whatever the world size, ``2 (n-1)/n`` x size on the wire (what an NVSwitch wants), every
+    rank ends with the same bits, and ``x is out`` (in place) is allowed.  The CollNet table of the plugin runs this one.
 
         mesh = TransportMesh()
         x, y = mesh.buffers(numel, torch.bfloat16, torch.float32)     # registered input / output
         x.copy_(grad); mesh.all_reduce(x, y)                           # y = sum over ranks of x, accumulated in fp32
+        g = mesh.buffer(numel, torch.float32)                          # one registered buffer
+        mesh.all_reduce(g, g, algo="two-shot")                         # in place
     """
 
     def __init__(self, group=None, net_dev: int = 0):
@@ -259,12 +269,24 @@ class TransportMesh:
                            self._out.numel() * self._out.element_size())
         return self._in, self._out
 
-    def all_reduce(self, x: torch.Tensor, out: torch.Tensor, piece_bytes: int = 1 << 20, inflight: int = 8) -> torch.Tensor:
+    def buffer(self, numel: int, dtype=torch.float32, device=None) -> torch.Tensor:
+        """One registered buffer, for in-place two-shot all-reduces."""
+        if dtype not in _DT:
+            raise TypeError("supported: fp32, bf16")
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        self._in = self._out = torch.zeros(numel, dtype=dtype, device=device)
+        nbytes = self._in.numel() * self._in.element_size()
+        self.core.register(self._in.data_ptr(), nbytes, self._in.data_ptr(), nbytes)
+        return self._in
+
+    def all_reduce(self, x: torch.Tensor, out: torch.Tensor, piece_bytes: int = 1 << 20, inflight: int = 8,
+                   algo: str = "one-shot") -> torch.Tensor:
         """out = sum over ranks of x (both inside the registered buffers, same number of elements)."""
         if x.numel() != out.numel() or x.dtype not in _DT or out.dtype not in _DT:
             raise TypeError("mesh all-reduce: fp32 / bf16 tensors of equal length")
         torch.cuda.current_stream(x.device).synchronize()
-        self.core.all_reduce(x.data_ptr(), out.data_ptr(), x.numel(), _DT[x.dtype], _DT[out.dtype], piece_bytes, inflight)
+        self.core.all_reduce(x.data_ptr(), out.data_ptr(), x.numel(), _DT[x.dtype], _DT[out.dtype], piece_bytes, inflight,
+                             algo=algo)
         return out
 
     def close(self):

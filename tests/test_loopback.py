@@ -387,7 +387,7 @@ def test_transport_ring_compressed_allreduce_over_tcp(impl):
     assert len({o["digest"] for o in outs}) == 1
 
 
-def _run_tmesh(world, count, idt, odt, piece, inflight, timeout=180):
+def _run_tmesh(world, count, idt, odt, piece, inflight, timeout=180, algo="one-shot", inplace=False):
     import json
     import subprocess
     import sys
@@ -397,7 +397,8 @@ def _run_tmesh(world, count, idt, odt, piece, inflight, timeout=180):
     env = dict(os.environ, BNET_FAKE_CUDA="1", BNET_NVL="1", PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
     with tempfile.TemporaryDirectory() as d:
         procs = [subprocess.Popen([sys.executable, os.path.join(root, "tests", "tmesh_worker.py"), str(r), str(world), d, str(count),
-                                   idt, odt, str(piece), str(inflight)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+                                   idt, odt, str(piece), str(inflight), "2", algo, "1" if inplace else "0"], env=env,
+                                  stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
                  for r in range(world)]
         outs = []
         for p in procs:
@@ -424,6 +425,23 @@ def test_transport_mesh_oneshot_allreduce(world, count, idt, odt, piece, infligh
     assert all(o["transport"] == "nvl" for o in outs)
     ies = 4 if idt == "f32" else 2
     assert all(o["stats"]["bytes_sent"] == (world - 1) * count * ies for o in outs), outs
+
+
+@pytest.mark.parametrize("world,count,idt,odt,piece,inflight,inplace", [
+    (2, 1 << 16, "f32", "f32", 16384, 4, False), (3, 100003, "bf16", "f32", 8192, 8, False), (4, 1 << 17, "bf16", "bf16", 65536, 8, True),
+    (5, 7, "f32", "f32", 4096, 2, False), (8, 50000, "f32", "f32", 16384, 8, True), (8, 300, "bf16", "bf16", 4096, 2, False)])
+def test_transport_mesh_twoshot_allreduce(world, count, idt, odt, piece, inflight, inplace):
+    """The bandwidth-optimal shape on a switch, two network steps for any world size: every peer's kernel accumulates its
+    part of slice r into rank r's output (fused isend), then the owner copies the finished slice to everybody.  Exact against
+    the closed-form sum, in place or out of place, with slices that are short or empty (count < world * 64)."""
+    outs = _run_tmesh(world, count, idt, odt, piece, inflight, algo="two-shot", inplace=inplace)
+    assert all(o["ok"] for o in outs), outs
+    assert all(o["transport"] == "nvl" for o in outs)
+    ies, oes = (4 if idt == "f32" else 2), (4 if odt == "f32" else 2)
+    seg = -(-(-(-count // world)) // 64) * 64
+    sl = [max(0, min(count, (r + 1) * seg) - min(count, r * seg)) for r in range(world)]
+    # rank r sends its part of every other slice (input type) and its own finished slice to every peer (output type)
+    assert all(o["stats"]["bytes_sent"] == (sum(sl) - sl[r]) * ies + (world - 1) * sl[r] * oes for r, o in enumerate(outs)), outs
 
 
 def test_nccl_tuner_plugin_picks_the_protocol_by_size():

@@ -1,6 +1,7 @@
 """One rank of the one-shot (full-mesh) all-reduce test: every rank sends its input to every peer once, the sender's kernel —
 here its CPU emulation over the NVL transport with emulated device memory — accumulates into the peer's output.
-usage: tmesh_worker.py <rank> <world> <dir> <count> <in f32|bf16> <out f32|bf16> <piece_bytes> <inflight> [rounds]"""
+usage: tmesh_worker.py <rank> <world> <dir> <count> <in f32|bf16> <out f32|bf16> <piece_bytes> <inflight> [rounds] [algo] [inplace]
+algo: one-shot | two-shot (reduce-scatter into the slice owners, all-gather by copy); inplace = 1: input and output are ONE buffer"""
 import ctypes as C
 import json
 import os
@@ -13,6 +14,8 @@ rank, world, d = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
 count, idt, odt = int(sys.argv[4]), sys.argv[5], sys.argv[6]
 piece, inflight = int(sys.argv[7]), int(sys.argv[8])
 rounds = int(sys.argv[9]) if len(sys.argv) > 9 else 2
+algo = sys.argv[10] if len(sys.argv) > 10 else "one-shot"
+inplace = len(sys.argv) > 11 and sys.argv[11] == "1"
 
 from bagua_net_b200.parallel.transport_ring import MeshCore  # noqa: E402
 from bagua_net_b200.utils.native import load  # noqa: E402
@@ -22,8 +25,9 @@ lib.bnet_fake_cuda_alloc.restype = C.c_void_p
 lib.bnet_fake_cuda_alloc.argtypes = [C.c_size_t]
 ies, oes = (4 if idt == "f32" else 2), (4 if odt == "f32" else 2)
 ib, ob = max(count * ies, 64), max(count * oes, 64)
-iptr, optr = lib.bnet_fake_cuda_alloc(ib + 64), lib.bnet_fake_cuda_alloc(ob + 64)
-assert iptr and optr
+iptr = lib.bnet_fake_cuda_alloc(ib + 64)
+optr = iptr if inplace else lib.bnet_fake_cuda_alloc(ob + 64)
+assert iptr and optr and (not inplace or idt == odt)
 iraw, oraw = (C.c_char * ib).from_address(iptr), (C.c_char * ob).from_address(optr)
 
 core = MeshCore(rank, world)
@@ -58,11 +62,12 @@ def get(raw, dt):
 ok = True
 for rnd in range(rounds):
     gen = lambda r: ((np.arange(count) * 5 + r + rnd) % 9 - 4).astype(np.float32)   # noqa: E731  (small integers: exact in bf16, any order)
+    if not inplace:
+        put(oraw, odt, np.full(count, 99.0, dtype=np.float32))        # stale output: every element must be overwritten
     put(iraw, idt, gen(rank))
-    put(oraw, odt, np.full(count, 99.0, dtype=np.float32))            # stale output: the local pass must overwrite it
     want = sum(gen(r) for r in range(world))
-    core.all_reduce(iptr, optr, count, 0 if idt == "f32" else 1, 0 if odt == "f32" else 1, piece, inflight)
-    ok = ok and bool(np.array_equal(get(oraw, odt), want)) and bool(np.array_equal(get(iraw, idt), gen(rank)))
+    core.all_reduce(iptr, optr, count, 0 if idt == "f32" else 1, 0 if odt == "f32" else 1, piece, inflight, algo=algo)
+    ok = ok and bool(np.array_equal(get(oraw, odt), want)) and (inplace or bool(np.array_equal(get(iraw, idt), gen(rank))))
     # nobody may start the next round (and overwrite its input) before every rank has checked this one
     open(os.path.join(d, f"done{rnd}_{rank}"), "w").close()
     for r in range(world):
