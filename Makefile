@@ -31,8 +31,8 @@ CU_SRCS   := $(wildcard csrc/cuda/*.cu)
 
 HOST_OBJS := $(patsubst csrc/%.cc,$(BUILD)/%.o,$(HOST_SRCS))
 CU_OBJS   := $(patsubst csrc/%.cu,$(BUILD)/%.cu.o,$(CU_SRCS))
-PLUGIN_OBJ  := $(BUILD)/plugin/plugin.o
-PLUGINX_OBJ := $(BUILD)/plugin/plugin_x.o
+PLUGIN_OBJ  := $(BUILD)/plugin/plugin.o $(BUILD)/plugin/collnet.o
+PLUGINX_OBJ := $(BUILD)/plugin/plugin_x.o $(BUILD)/plugin/collnet_x.o
 
 PLUGIN_SO  := $(OUT)/libnccl-net.so
 PLUGINX_SO := $(OUT)/libnccl-net-bnetx.so
@@ -48,7 +48,7 @@ $(BUILD)/%.cu.o: csrc/%.cu
 	@mkdir -p $(dir $@)
 	$(NVCC) $(NVCCFLAGS) -MMD -MP -c $< -o $@
 
-$(PLUGINX_OBJ): csrc/plugin/plugin.cc
+$(BUILD)/plugin/%_x.o: csrc/plugin/%.cc
 	@mkdir -p $(dir $@)
 	$(CXX) $(CXXFLAGS) -DBNET_EXPORT_V9_V10 -MMD -MP -c $< -o $@
 

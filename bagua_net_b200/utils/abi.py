@@ -149,6 +149,76 @@ _TABLES = {3: NetV4, 4: NetV4, 5: None, 6: NetV6, 8: NetV8, 10: NetV10}
 _PROPS = {3: PropsV4, 4: PropsV4, 6: PropsV6, 8: PropsV8, 10: PropsV9}
 
 
+class CollNetV6(C.Structure):       # include/bnet/nccl_net_abi.h: ncclCollNet_v6_t (v7 differs in the properties struct only)
+    _fields_ = [
+        ("name", C.c_char_p),
+        ("init", _fn(_logger_t)),
+        ("devices", _fn(_ip)),
+        ("getProperties", _fn(_i, C.POINTER(PropsV6))),
+        ("listen", _fn(_i, _vp, _vpp)),
+        ("connect", _fn(_vpp, _i, _i, _vp, _vpp)),
+        ("reduceSupport", _fn(_i, _i, _ip)),
+        ("regMr", _fn(_vp, _vp, _i, _i, _vpp)),
+        ("regMrDmaBuf", _fn(_vp, _vp, _sz, _i, C.c_uint64, _i, _vpp)),
+        ("deregMr", _fn(_vp, _vp)),
+        ("iallreduce", _fn(_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vpp)),
+        ("iflush", _fn(_vp, _vp, _i, _vp, _vpp)),
+        ("test", _fn(_vp, _ip, _ip)),
+        ("closeColl", _fn(_vp)),
+        ("closeListen", _fn(_vp)),
+    ]
+
+
+class CollNetV8(C.Structure):       # ncclCollNet_v8_t
+    _fields_ = [
+        ("name", C.c_char_p),
+        ("init", _fn(_logger_t)),
+        ("devices", _fn(_ip)),
+        ("getProperties", _fn(_i, C.POINTER(PropsV8))),
+        ("listen", _fn(_i, _vp, _vpp)),
+        ("connect", _fn(_vpp, _i, _i, _vp, _vpp)),
+        ("reduceSupport", _fn(_i, _i, _ip)),
+        ("regMr", _fn(_vp, _vp, _sz, _i, _vpp)),
+        ("regMrDmaBuf", _fn(_vp, _vp, _sz, _i, C.c_uint64, _i, _vpp)),
+        ("deregMr", _fn(_vp, _vp)),
+        ("iallreduce", _fn(_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vpp)),
+        ("iallgather", _fn(_vp, _vp, _i, _vp, _sz, _sz, _sz, _vp, _vpp)),
+        ("ireducescatter", _fn(_vp, _i, _vp, _vp, _sz, _sz, _sz, _i, _i, _vp, _vpp)),
+        ("iflush", _fn(_vp, _vp, _i, _vp, _vpp)),
+        ("test", _fn(_vp, _ip, _ip)),
+        ("closeColl", _fn(_vp)),
+        ("closeListen", _fn(_vp)),
+    ]
+
+
+class CollNetV10(C.Structure):      # ncclCollNet_v9_t / _v10_t (exported by libnccl-net-bnetx.so)
+    _fields_ = [
+        ("name", C.c_char_p),
+        ("init", _fn(_logger_t)),
+        ("devices", _fn(_ip)),
+        ("getProperties", _fn(_i, C.POINTER(PropsV9))),
+        ("listen", _fn(_i, _vp, _vpp)),
+        ("connect", _fn(_vpp, _i, _i, _vp, _vpp)),
+        ("reduceSupport", _fn(_i, _i, _ip)),
+        ("regMr", _fn(_vp, _vp, _sz, _i, _vpp)),
+        ("regMrDmaBuf", _fn(_vp, _vp, _sz, _i, C.c_uint64, _i, _vpp)),
+        ("deregMr", _fn(_vp, _vp)),
+        ("iallreduce", _fn(_vp, _vp, _vp, _sz, _i, _i, _vp, _vp, _vpp)),
+        ("iallgather", _fn(_vp, _vp, _i, _vp, _sz, _sz, _sz, _vp, _vpp)),
+        ("ireducescatter", _fn(_vp, _i, _vp, _vp, _sz, _sz, _sz, _i, _i, _vp, _vpp)),
+        ("iflush", _fn(_vp, _vp, _i, _vp, _vpp)),
+        ("test", _fn(_vp, _ip, _ip)),
+        ("closeColl", _fn(_vp)),
+        ("closeListen", _fn(_vp)),
+        ("makeVDevice", _fn(_ip, _vp)),
+    ]
+
+
+_COLL_TABLES = {6: CollNetV6, 8: CollNetV8, 9: CollNetV10, 10: CollNetV10}
+_COLL_PROPS = {6: PropsV6, 8: PropsV8, 9: PropsV9, 10: PropsV9}
+ncclSum, ncclFloat32, ncclBfloat16 = 0, 7, 9
+
+
 # ncclProfilerCallback_t(void** eHandle, int type, void* pHandle, int64_t pluginId, void* extData)
 PROFILER_CB = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int64, C.c_void_p)
 
@@ -323,3 +393,83 @@ class NetPlugin:
 
     def transport_of(self, comm) -> str:
         return self.lib.bnet_comm_transport(comm).decode()
+
+
+class CollNetPlugin:
+    """Drives one exported ``ncclCollNetPlugin_vN`` table the way NCCL does (csrc/plugin/collnet.cc): listen on every rank,
+    connect with everybody's handles, register the send and receive buffers, ``iallreduce`` + ``test``."""
+
+    def __init__(self, version: int = 8, lib_name: str | None = None):
+        if version not in _COLL_TABLES:
+            raise ValueError(f"CollNet ABI v{version} has no ctypes table here")
+        self.version = version
+        self.lib = load(lib_name) if lib_name else load()
+        self.tab = _COLL_TABLES[version].in_dll(self.lib, f"ncclCollNetPlugin_v{version}")
+        self.name = self.tab.name.decode()
+
+    def _chk(self, what, rc):
+        if rc != ncclSuccess:
+            raise PluginError(what, rc)
+
+    def init(self):
+        self._chk("init", self.tab.init(None))
+
+    def devices(self) -> int:
+        n = C.c_int(0)
+        self._chk("devices", self.tab.devices(C.byref(n)))
+        return n.value
+
+    def get_properties(self, dev: int) -> dict:
+        p = _COLL_PROPS[self.version]()
+        self._chk("getProperties", self.tab.getProperties(dev, C.byref(p)))
+        return {f: (getattr(p, f).decode() if isinstance(getattr(p, f), bytes) else getattr(p, f)) for f, _t in p._fields_
+                if not isinstance(getattr(p, f), VProps)}
+
+    def listen(self, dev: int = 0):
+        handle = C.create_string_buffer(HANDLE_BYTES[self.version])
+        comm = C.c_void_p()
+        self._chk("listen", self.tab.listen(dev, handle, C.byref(comm)))
+        return bytes(handle.raw), comm
+
+    def connect(self, handles: list, rank: int, listen_comm):
+        bufs = [C.create_string_buffer(bytes(h), HANDLE_BYTES[self.version]) for h in handles]
+        arr = (C.c_void_p * len(bufs))(*[C.cast(b, C.c_void_p) for b in bufs])
+        comm = C.c_void_p()
+        self._chk("connect", self.tab.connect(arr, len(bufs), rank, listen_comm, C.byref(comm)))
+        return comm
+
+    def reduce_support(self, dtype: int, op: int = ncclSum) -> bool:
+        ok = C.c_int(0)
+        self._chk("reduceSupport", self.tab.reduceSupport(dtype, op, C.byref(ok)))
+        return bool(ok.value)
+
+    def reg_mr(self, comm, ptr: int, nbytes: int, ptr_type: int = NCCL_PTR_CUDA):
+        mh = C.c_void_p()
+        self._chk("regMr", self.tab.regMr(comm, C.c_void_p(ptr), nbytes, ptr_type, C.byref(mh)))
+        return mh
+
+    def dereg_mr(self, comm, mh):
+        self._chk("deregMr", self.tab.deregMr(comm, mh))
+
+    def iallreduce(self, comm, send_ptr: int, recv_ptr: int, count: int, dtype: int, send_mh, recv_mh, op: int = ncclSum):
+        """Returns the request, or None when the plugin asks to try again later."""
+        req = C.c_void_p()
+        self._chk("iallreduce", self.tab.iallreduce(comm, C.c_void_p(send_ptr), C.c_void_p(recv_ptr), count, dtype, op, send_mh,
+                                                   recv_mh, C.byref(req)))
+        return req if req.value else None
+
+    def iflush(self, comm, ptr: int, nbytes: int, mh):
+        req = C.c_void_p()
+        self._chk("iflush", self.tab.iflush(comm, C.c_void_p(ptr), nbytes, mh, C.byref(req)))
+        return req
+
+    def test(self, req):
+        done, size = C.c_int(0), C.c_int(0)
+        self._chk("test", self.tab.test(req, C.byref(done), C.byref(size)))
+        return bool(done.value), size.value
+
+    def close_coll(self, comm):
+        self._chk("closeColl", self.tab.closeColl(comm))
+
+    def close_listen(self, comm):
+        self._chk("closeListen", self.tab.closeListen(comm))

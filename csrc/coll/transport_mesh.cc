@@ -247,7 +247,9 @@ MeshOp* tmesh_op_start(BnetTMesh* m, int algo, const void* in, MeshMr* in_mr, vo
   char* dst = (char*)out;
   if (!tmesh_mr_covers(in_mr, src, count * ies)) { fail(m, "input outside the registered range"); return nullptr; }
   if (!tmesh_mr_covers(out_mr, dst, count * oes)) { fail(m, "output outside the registered range"); return nullptr; }
-  if ((((uintptr_t)src) & 63) || (((uintptr_t)dst) & 63)) { fail(m, "buffers must be 64-byte aligned"); return nullptr; }
+  // (16-byte alignment of both buffers puts every piece on the vector path of the executor ops; anything element-aligned
+  //  still works, element by element)
+  if (((uintptr_t)src % ies) || ((uintptr_t)dst % oes)) { fail(m, "buffers must be aligned to their element size"); return nullptr; }
   const bool in_place = src == dst;
   if (in_place && (algo != MESH_TWO_SHOT || ies != oes)) { fail(m, "in-place needs the two-shot algorithm and equal types"); return nullptr; }
   if (!in_place && src < dst + count * oes && dst < src + count * ies) { fail(m, "input and output overlap"); return nullptr; }

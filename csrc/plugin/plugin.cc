@@ -19,6 +19,7 @@
 #include "bnet/nccl_net_abi.h"
 #include "core/engine.h"
 #include "core/telemetry.h"
+#include "plugin/plugin_shims.h"
 
 using namespace bnet;
 
@@ -275,6 +276,13 @@ ncclResult_t props_v6like(int dev, P* o) {
   o->maxRecvs = p.max_recvs;
   return ncclSuccess;
 }
+}  // namespace
+
+// (shared with the CollNet tables of csrc/plugin/collnet.cc: csrc/plugin/plugin_shims.h)
+namespace bnet {
+namespace plugin {
+ncclResult_t init(ncclDebugLogger_t logfn) { return do_init(logfn); }
+ncclResult_t v4_props(int dev, ncclNetProperties_v4_t* o) { return ::v4_props(dev, o); }
 ncclResult_t v6_props(int dev, ncclNetProperties_v6_t* o) { return props_v6like(dev, o); }
 ncclResult_t v7_props(int dev, ncclNetProperties_v7_t* o) {
   ncclResult_t r = props_v6like(dev, o);
@@ -301,6 +309,14 @@ ncclResult_t v9_props(int dev, ncclNetProperties_v9_t* o) {
   o->maxCollBytes = (size_t)1 << 40;
   return r;
 }
+}  // namespace plugin
+}  // namespace bnet
+
+namespace {
+using bnet::plugin::v6_props;
+using bnet::plugin::v7_props;
+using bnet::plugin::v8_props;
+using bnet::plugin::v9_props;
 
 ncclResult_t v6_listen(int dev, void* h, void** l) { return do_listen(dev, h, NCCL_NET_HANDLE_MAXSIZE, l); }
 ncclResult_t v6_connect(int dev, void* h, void** s) { return do_connect(dev, h, s); }

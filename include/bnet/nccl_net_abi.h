@@ -156,7 +156,9 @@ typedef struct {
 } ncclNet_v4_t;
 
 /* Collective-offload table of the v4 era.  The reference only carries the
- * declaration (cc/v4/nccl_net_v4.h:64-101); we implement and export it. */
+ * declaration (cc/v4/nccl_net_v4.h:64-101) and exports no ncclCollNetPlugin symbol;
+ * ours is exported too (csrc/plugin/collnet.cc), next to the v6..v10 tables at the
+ * end of this header that the installed NCCLs actually probe. */
 typedef struct {
   const char* name;
   ncclResult_t (*init)(ncclDebugLogger_t logFunction);
@@ -400,6 +402,125 @@ typedef struct {
   ncclResult_t (*irecvConsumed)(void* recvComm, int n, void* request);
   ncclResult_t (*makeVDevice)(int* d, ncclNetVDeviceProps_v10_t* props);
 } ncclNet_v10_t;
+
+/* ====================== collective offload (CollNet), v6 .. v10 =================
+ * What NCCL dlsym()s as ncclCollNetPlugin_vN next to the net table of the same library (NCCL 2.27 / 2.28 probe
+ * v10, v9, v8, v7, v6).  The reference carries only the v4 declaration above and exports nothing; here the tables
+ * are implemented by csrc/plugin/collnet.cc on top of the two-shot all-reduce of csrc/coll/transport_mesh.cc.
+ * Layouts written from NCCL's public ext-net contract (from memory, verify by loading). */
+typedef struct {
+  const char* name;
+  ncclResult_t (*init)(ncclDebugLogger_t logFunction);
+  ncclResult_t (*devices)(int* ndev);
+  ncclResult_t (*getProperties)(int dev, ncclNetProperties_v6_t* props);
+  ncclResult_t (*listen)(int dev, void* handle, void** listenComm);
+  ncclResult_t (*connect)(void* handles[], int nranks, int rank, void* listenComm, void** collComm);
+  ncclResult_t (*reduceSupport)(ncclDataType_t dataType, ncclRedOp_t redOp, int* supported);
+  ncclResult_t (*regMr)(void* collComm, void* data, int size, int type, void** mhandle);
+  ncclResult_t (*regMrDmaBuf)(void* collComm, void* data, size_t size, int type, uint64_t offset, int fd,
+                              void** mhandle);
+  ncclResult_t (*deregMr)(void* collComm, void* mhandle);
+  ncclResult_t (*iallreduce)(void* collComm, void* sendData, void* recvData, int count,
+                             ncclDataType_t dataType, ncclRedOp_t redOp, void* sendMhandle,
+                             void* recvMhandle, void** request);
+  ncclResult_t (*iflush)(void* collComm, void* data, int size, void* mhandle, void** request);
+  ncclResult_t (*test)(void* request, int* done, int* size);
+  ncclResult_t (*closeColl)(void* collComm);
+  ncclResult_t (*closeListen)(void* listenComm);
+} ncclCollNet_v6_t;
+
+typedef struct {
+  const char* name;
+  ncclResult_t (*init)(ncclDebugLogger_t logFunction);
+  ncclResult_t (*devices)(int* ndev);
+  ncclResult_t (*getProperties)(int dev, ncclNetProperties_v7_t* props);
+  ncclResult_t (*listen)(int dev, void* handle, void** listenComm);
+  ncclResult_t (*connect)(void* handles[], int nranks, int rank, void* listenComm, void** collComm);
+  ncclResult_t (*reduceSupport)(ncclDataType_t dataType, ncclRedOp_t redOp, int* supported);
+  ncclResult_t (*regMr)(void* collComm, void* data, int size, int type, void** mhandle);
+  ncclResult_t (*regMrDmaBuf)(void* collComm, void* data, size_t size, int type, uint64_t offset, int fd,
+                              void** mhandle);
+  ncclResult_t (*deregMr)(void* collComm, void* mhandle);
+  ncclResult_t (*iallreduce)(void* collComm, void* sendData, void* recvData, int count,
+                             ncclDataType_t dataType, ncclRedOp_t redOp, void* sendMhandle,
+                             void* recvMhandle, void** request);
+  ncclResult_t (*iflush)(void* collComm, void* data, int size, void* mhandle, void** request);
+  ncclResult_t (*test)(void* request, int* done, int* size);
+  ncclResult_t (*closeColl)(void* collComm);
+  ncclResult_t (*closeListen)(void* listenComm);
+} ncclCollNet_v7_t;
+
+typedef struct {
+  void* mhandle;
+  void* address;
+  uint32_t size;
+} ncclNetSGE_v8_t;
+
+typedef struct {
+  const char* name;
+  ncclResult_t (*init)(ncclDebugLogger_t logFunction);
+  ncclResult_t (*devices)(int* ndev);
+  ncclResult_t (*getProperties)(int dev, ncclNetProperties_v8_t* props);
+  ncclResult_t (*listen)(int dev, void* handle, void** listenComm);
+  ncclResult_t (*connect)(void* handles[], int nranks, int rank, void* listenComm, void** collComm);
+  ncclResult_t (*reduceSupport)(ncclDataType_t dataType, ncclRedOp_t redOp, int* supported);
+  ncclResult_t (*regMr)(void* collComm, void* data, size_t size, int type, void** mhandle);
+  ncclResult_t (*regMrDmaBuf)(void* collComm, void* data, size_t size, int type, uint64_t offset, int fd,
+                              void** mhandle);
+  ncclResult_t (*deregMr)(void* collComm, void* mhandle);
+  ncclResult_t (*iallreduce)(void* collComm, void* sendData, void* recvData, int count,
+                             ncclDataType_t dataType, ncclRedOp_t redOp, void* sendMhandle,
+                             void* recvMhandle, void** request);
+  ncclResult_t (*iallgather)(void* collComm, void* sendData, int nRecvParts, ncclNetSGE_v8_t* recvParts,
+                             size_t bytesPerRank, size_t windowOffset, size_t windowBytes,
+                             void* sendMhandle, void** request);
+  ncclResult_t (*ireducescatter)(void* collComm, int nSendParts, ncclNetSGE_v8_t* sendParts, void* recvData,
+                                 size_t bytesPerRank, size_t windowOffset, size_t windowBytes,
+                                 ncclDataType_t dataType, ncclRedOp_t redOp, void* recvMhandle,
+                                 void** request);
+  ncclResult_t (*iflush)(void* collComm, void* data, int size, void* mhandle, void** request);
+  ncclResult_t (*test)(void* request, int* done, int* size);
+  ncclResult_t (*closeColl)(void* collComm);
+  ncclResult_t (*closeListen)(void* listenComm);
+} ncclCollNet_v8_t;
+
+typedef struct {
+  void* mhandle;
+  void* address;
+  size_t size;
+} ncclNetSGE_v9_t;
+
+typedef struct {
+  const char* name;
+  ncclResult_t (*init)(ncclDebugLogger_t logFunction);
+  ncclResult_t (*devices)(int* ndev);
+  ncclResult_t (*getProperties)(int dev, ncclNetProperties_v9_t* props);
+  ncclResult_t (*listen)(int dev, void* handle, void** listenComm);
+  ncclResult_t (*connect)(void* handles[], int nranks, int rank, void* listenComm, void** collComm);
+  ncclResult_t (*reduceSupport)(ncclDataType_t dataType, ncclRedOp_t redOp, int* supported);
+  ncclResult_t (*regMr)(void* collComm, void* data, size_t size, int type, void** mhandle);
+  ncclResult_t (*regMrDmaBuf)(void* collComm, void* data, size_t size, int type, uint64_t offset, int fd,
+                              void** mhandle);
+  ncclResult_t (*deregMr)(void* collComm, void* mhandle);
+  ncclResult_t (*iallreduce)(void* collComm, void* sendData, void* recvData, size_t count,
+                             ncclDataType_t dataType, ncclRedOp_t redOp, void* sendMhandle,
+                             void* recvMhandle, void** request);
+  ncclResult_t (*iallgather)(void* collComm, void* sendData, int nRecvParts, ncclNetSGE_v9_t* recvParts,
+                             size_t bytesPerRank, size_t windowOffset, size_t windowBytes,
+                             void* sendMhandle, void** request);
+  ncclResult_t (*ireducescatter)(void* collComm, int nSendParts, ncclNetSGE_v9_t* sendParts, void* recvData,
+                                 size_t bytesPerRank, size_t windowOffset, size_t windowBytes,
+                                 ncclDataType_t dataType, ncclRedOp_t redOp, void* recvMhandle,
+                                 void** request);
+  ncclResult_t (*iflush)(void* collComm, void* data, int size, void* mhandle, void** request);
+  ncclResult_t (*test)(void* request, int* done, int* size);
+  ncclResult_t (*closeColl)(void* collComm);
+  ncclResult_t (*closeListen)(void* listenComm);
+  ncclResult_t (*makeVDevice)(int* d, ncclNetVDeviceProps_v9_t* props);
+} ncclCollNet_v9_t;
+
+typedef ncclNetSGE_v9_t ncclNetSGE_v10_t;
+typedef ncclCollNet_v9_t ncclCollNet_v10_t;   /* same entry points; the properties type is shared with v9 already */
 
 #ifdef __cplusplus
 }

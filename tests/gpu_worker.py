@@ -982,6 +982,59 @@ def job_transport_mesh():
     teardown()
 
 
+def job_transport_mesh_twoshot():
+    """Two-shot all-reduce over the mesh (reduce-scatter by fused isend into the slice owner, all-gather by copy), out of
+    place and in place; ranks must end with identical bits even for data whose sums round."""
+    from bagua_net_b200.parallel.transport_ring import TransportMesh
+
+    setup()
+    mesh = TransportMesh()
+    assert mesh.transport == "nvl", mesh.transport
+    res = []
+    for idt, odt, count in ((torch.float32, torch.float32, 1 << 22), (torch.bfloat16, torch.float32, (1 << 20) + 24),
+                            (torch.bfloat16, torch.bfloat16, 4096), (torch.float32, torch.float32, 9)):
+        x, y = mesh.buffers(count, idt, odt)
+        for rnd in range(2):
+            x.copy_(((torch.arange(count, device="cuda") * 5 + RANK + rnd) % 9 - 4).to(idt))
+            y.fill_(99)
+            torch.cuda.synchronize()
+            dist.barrier()
+            mesh.all_reduce(x, y, algo="two-shot")
+            want = sum(((torch.arange(count, device="cuda") * 5 + r + rnd) % 9 - 4).float() for r in range(WORLD))
+            assert torch.equal(y.float(), want), f"rank {RANK}: two-shot all-reduce {idt}->{odt} x{count} is wrong"
+            dist.barrier()
+        if count >= (1 << 20):
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            iters = 10
+            for _ in range(iters):
+                mesh.all_reduce(x, y, algo="two-shot")
+            res.append((count * x.element_size(), (time.perf_counter() - t0) / iters))
+    # in place, random floats: the sums round, yet every rank must hold the owner's bits
+    g = mesh.buffer(1 << 20, torch.float32)
+    torch.manual_seed(100 + RANK)
+    g.copy_(torch.randn(1 << 20, device="cuda"))
+    mine = g.clone()
+    torch.cuda.synchronize()
+    dist.barrier()
+    mesh.all_reduce(g, g, algo="two-shot")
+    ref = mine.clone()
+    dist.all_reduce(ref)
+    assert (g - ref).abs().max().item() < 1e-4 * WORLD, "in-place two-shot all-reduce differs from NCCL's sum"
+    digest = torch.stack([g.double().sum(), g.double().abs().sum()])
+    alld = [torch.zeros_like(digest) for _ in range(WORLD)]
+    dist.all_gather(alld, digest)
+    assert all(torch.equal(alld[0], d_) for d_ in alld), "ranks hold different bits after the two-shot all-reduce"
+    if RANK == 0:
+        for nbytes, dt in res:
+            busbw = nbytes / dt / 1e9 * 2 * (WORLD - 1) / WORLD
+            print(f"transport mesh two-shot all-reduce {nbytes >> 10} KiB: {dt * 1e6:.1f} us per call, {busbw:.1f} GB/s busbw "
+                  f"(host-timed, world {WORLD})", flush=True)
+    mesh.close()
+    teardown()
+
+
 def job_tc_conv():
     from bagua_net_b200.ops import tc_conv, tc_linear
 

@@ -229,3 +229,9 @@ def test_transport_ring_compressed_allreduce_2gpu():
 @pytest.mark.multigpu
 def test_transport_mesh_oneshot_allreduce_2gpu():
     _run_worker("transport_mesh", 2)
+
+
+@pytest.mark.multigpu
+def test_transport_mesh_twoshot_allreduce_2gpu():
+    """Reduce-scatter by fused isend into the slice owner + all-gather by copy; in place; ranks end with identical bits."""
+    _run_worker("transport_mesh_twoshot", 2)

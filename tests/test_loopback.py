@@ -444,6 +444,53 @@ def test_transport_mesh_twoshot_allreduce(world, count, idt, odt, piece, infligh
     assert all(o["stats"]["bytes_sent"] == (sum(sl) - sl[r]) * ies + (world - 1) * sl[r] * oes for r, o in enumerate(outs)), outs
 
 
+@pytest.mark.parametrize("world,ver,count,dt,lib", [(2, 8, 70000, "f32", "-"), (4, 6, 5000, "bf16", "-"), (3, 10, 33, "f32", "libnccl-net-bnetx.so"),
+                                                     (8, 8, 200000, "bf16", "-")])
+def test_collnet_table_allreduces_like_nccl_would_drive_it(world, ver, count, dt, lib):
+    """ncclCollNetPlugin_vN (csrc/plugin/collnet.cc): listen / connect(handles, nranks, rank) / regMr / iallreduce / test /
+    iflush through the exported table, several all-reduces queued per rank and tested out of order; exact sums; only
+    sum of fp32 / bf16 on device memory is offered."""
+    import json
+    import subprocess
+    import sys
+    import tempfile
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, BNET_FAKE_CUDA="1", BNET_NVL="1", BNET_COLLNET="1",
+               PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    with tempfile.TemporaryDirectory() as d:
+        procs = [subprocess.Popen([sys.executable, os.path.join(root, "tests", "collnet_worker.py"), str(r), str(world), d, str(ver),
+                                   str(count), dt, lib], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+                 for r in range(world)]
+        outs = []
+        for p in procs:
+            try:
+                o, e = p.communicate(timeout=180)
+            except subprocess.TimeoutExpired:
+                for q in procs:
+                    q.kill()
+                raise
+            assert p.returncode == 0, e[-3000:]
+            outs.append(json.loads([ln for ln in o.splitlines() if ln.startswith("{")][-1]))
+    for o in outs:
+        assert o["ok"] and o["name"] == "BNet" and o["ndev"] >= 1 and o["ptr_support"] == 2 and o["host_refused"], o
+        assert o["support"] == {"sum_this_type": True, "max": False, "int32": False}, o
+
+
+def test_collnet_table_is_silent_unless_asked_for():
+    """Without BNET_COLLNET=1 the table reports no devices: NCCL drops it at init and the net path is all it sees."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = {k: v for k, v in os.environ.items() if k != "BNET_COLLNET"}
+    env.update(BNET_FAKE_CUDA="1", PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    code = ("from bagua_net_b200.utils.abi import CollNetPlugin\n"
+            "p = CollNetPlugin(8); p.init(); print('ndev', p.devices())")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "ndev 0" in out.stdout, out.stderr[-2000:]
+
+
 def test_nccl_tuner_plugin_picks_the_protocol_by_size():
     """ncclTunerPlugin_v3/_v4 inside the net plugin library (csrc/plugin/tuner.cc): over this transport LL for tiny messages,
     Simple above, LL128 never — and no opinion at all when the device path is off."""

@@ -13,6 +13,8 @@
 #   plugin       nccl-tests clone over the plugin: 8 B .. 128 MiB, then a short INFO run (network / GDRDMA / tuner lines)
 #   stock        the same sweep with stock NCCL (no plugin)
 #   knobs        the 32 MiB / 128 MiB rows under env variants (KNOBS="A=1,B=2;C=3": one variant per ';')
+#   collnet      the CollNet experiment: nccl-tests clone with BNET_COLLNET=1 NCCL_COLLNET_ENABLE=1, one virtual host per rank
+#                (NCCL then sees one GPU per "node" and may pick CollNetDirect / CollNetChain: grep "CollNet" in collnet_info.log)
 #   debug        bounded small sweeps over the plugin with the watchdog at 3 s and the transport's INFO log
 #   coll         symmetric-heap collectives (LL latency, P2P / NVLS bandwidth), transport ring, staggered fused SGD
 #   sweep        bench/allreduce_sweep.py: fused kernels vs stock NCCL, 1 KiB .. 1 GiB
@@ -70,6 +72,12 @@ for recipe in "$@"; do
     grep -i "Using network\|via NET\|tuner" $OUT/plugin_info.log | sed 's/.*NCCL INFO //; s/[0-9]*\[[0-9]*\] -> [0-9]*\[[0-9]*\]/A->B/; s/Channel [0-9]*\/[0-9]*/Channel/; s/BNet\/[0-9]/BNet\/x/' | sort | uniq -c | sort -rn | head -6 | cut -c1-200 ;;
   stock)
     TAILN=16 step stock 150 $ARP $SWEEP ;;
+  collnet)
+    CN="BNET_COLLNET=1 NCCL_COLLNET_ENABLE=1 NCCL_COLLNET_NODE_THRESHOLD=1"
+    TAILN=6 step collnet_info 120 env $PLUG $CN NCCL_DEBUG=INFO NCCL_DEBUG_SUBSYS=INIT,NET,COLL,TUNING BNET_LOG_LEVEL=2 $ARP -H -b 1M -e 16M -f 4 -n 5 -w 2
+    grep -i "collnet\|coll net" $OUT/collnet_info.log | sed 's/.*NCCL INFO //' | sort | uniq -c | sort -rn | head -8 | cut -c1-200
+    TAILN=16 step collnet 150 env $PLUG $CN $ARP -H $SWEEP
+    TAILN=16 step collnet_forced 150 env $PLUG $CN NCCL_ALGO=CollnetDirect,CollnetChain,Ring $ARP -H $SWEEP ;;
   knobs)
     i=0; IFS=';' read -ra VARIANTS <<< "${KNOBS:-BNET_MSG_BATCH_US=20;NCCL_MIN_NCHANNELS=8,NCCL_MAX_NCHANNELS=8;NCCL_BUFFSIZE=8388608;BNET_MSG_CLUSTER=0;BNET_EXEC_MODE=ce}"
     TAILN=4 step knob_base 90 env $PLUG BNET_EXEC_STATS=1 $ARP -b 32M -e 128M -f 4 -n 8 -w 2
@@ -84,6 +92,7 @@ for recipe in "$@"; do
     TAILN=6 step transport_ring 200 $TR --master-port 29642 tests/gpu_worker.py transport_ring
     TAILN=4 step fused_sgd_staggered 150 $TR --master-port 29643 tests/gpu_worker.py fused_sgd_staggered
     TAILN=4 step transport_mesh 150 $TR --master-port 29645 tests/gpu_worker.py transport_mesh
+    TAILN=4 step transport_mesh_twoshot 150 $TR --master-port 29647 tests/gpu_worker.py transport_mesh_twoshot
     TAILN=4 step transport_ring_compressed 150 $TR --master-port 29646 tests/gpu_worker.py transport_ring_compressed ;;
   sweep)
     TAILN=30 step allreduce_sweep 400 $TR --master-port 29644 bench/allreduce_sweep.py ;;
