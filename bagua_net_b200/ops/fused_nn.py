@@ -64,23 +64,27 @@ def _conv(x, w, stride, padding):
 
 
 def _conv_backward(gz, x, w, stride, padding, need_x):
-    """(gx, gw) of the convolution.  3x3 / stride 1 / pad 1 layers whose shape the autotuner gave to the tcgen05 kernel
-    (ops/tc_conv.py) take their input gradient from it — the filter is read as stored, MN-major, taps flipped — and only
-    the filter gradient from cuDNN."""
-    if need_x and _is_3x3_s1p1(w, stride, padding):
+    """(gx, gw) of the convolution.  For 3x3 / stride 1 / pad 1 layers the autotuner (ops/tc_conv.py) decides per shape and
+    per gradient: the input gradient from the tcgen05 kernel (the filter is read as stored, MN-major, taps flipped), the
+    filter gradient from the tcgen05 kernel (64-pixel boxes of gz and x, split over the pixels) — or cuDNN for either."""
+    def lib(want_x, want_w):
+        return torch.ops.aten.convolution_backward(gz, x, w, None, stride, padding, [1, 1], False, [0, 0], 1, [want_x, want_w, False])
+
+    if _is_3x3_s1p1(w, stride, padding) and gz.dtype == torch.bfloat16:
         from . import tc_conv
 
-        def lib():
-            return torch.ops.aten.convolution_backward(gz, x, w, None, stride, padding, [1, 1], False, [0, 0], 1,
-                                                       [True, False, False])[0]
-
-        if tc_conv.choose("dgrad", gz, w, lib, lambda: tc_conv.conv3x3_dgrad(gz, w), tc_conv.close) == "tc":
-            gx = tc_conv.conv3x3_dgrad(gz, w)
-            gw = torch.ops.aten.convolution_backward(gz, x, w, None, stride, padding, [1, 1], False, [0, 0], 1,
-                                                     [False, True, False])[1]
+        tc_x = need_x and tc_conv.choose("dgrad", gz, w, lambda: lib(True, False)[0], lambda: tc_conv.conv3x3_dgrad(gz, w),
+                                         tc_conv.close) == "tc"
+        tc_w = tc_conv.choose_wgrad(gz, x, w, lambda: lib(False, True)[1]) == "tc"
+        if tc_x or tc_w:
+            gx = tc_conv.conv3x3_dgrad(gz, w) if tc_x else None
+            gw = tc_conv.conv3x3_wgrad(gz, x) if tc_w else None
+            if (need_x and gx is None) or gw is None:
+                rx, rw, _ = lib(need_x and gx is None, gw is None)
+                gx = rx if gx is None else gx
+                gw = rw if gw is None else gw
             return gx, gw
-    gx, gw, _ = torch.ops.aten.convolution_backward(gz, x, w, None, stride, padding, [1, 1], False, [0, 0], 1,
-                                                    [need_x, True, False])
+    gx, gw, _ = lib(need_x, True)
     return gx, gw
 
 

@@ -2,11 +2,19 @@
 
     y  = tc_conv.conv3x3(x, w, bias, relu=True)     # NHWC bf16, stride 1, pad 1; bias + ReLU applied from TMEM
     dx = tc_conv.conv3x3_dgrad(gy, w)               # same filter, read MN-major with flipped taps (no rotated copy)
+    dw = tc_conv.conv3x3_wgrad(gy, x)               # filter gradient: the reduction runs over 64-pixel TMA boxes of gy and x
 
 Implicit GEMM: the 128 accumulator rows of a tile are a patch of output pixels (bw x bh pixels of bn images); for every
 (filter tap, 64-channel block) the patch's shifted input arrives as ONE 4-D TMA box of the NHWC activation, the padding
 being the TMA unit's zero fill.  No im2col buffer exists anywhere.  Filters are used exactly as torch stores a
 channels_last ``Conv2d.weight`` ([Cout][3][3][Cin]).
+
+The filter gradient ``dw[co, tap, ci] = sum_p gy[p, co] * x[p + tap, ci]`` is the same kernel with both operands MN-major
+(the layout the linear layer's ``dW = gY^T . X`` uses): 64-pixel boxes of ``gy`` ride the TMEM lanes, 64-pixel boxes of the
+shifted ``x`` the columns, the pixel blocks are split over ``grid.z`` and the slice that arrives last at a tile converts
+the fp32 sums to bf16 — the result is the ``channels_last`` weight gradient itself.  It was written after the last hardware
+session of round 2: ``wgrad_trusted()`` lets it run only after ``self_check_wgrad()`` passed in a CHILD process on this GPU
+(verdict cached per library build and GPU model; ``BNET_TC_WGRAD=0`` disables it, ``=1`` skips the child).
 
 The layers above (``fused_nn.ConvBiasReLU``) ask ``choose()`` which implementation to run for a given shape: on first
 (eager) use each candidate is timed on the actual tensors with CUDA events and the winner is cached for the process —
@@ -37,6 +45,9 @@ def _L():
         vp, i = C.c_void_p, C.c_int
         _lib.bnet_tc_conv3x3.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, vp, vp]
         _lib.bnet_tc_conv3x3_dgrad.argtypes = [vp, vp, vp, i, i, i, i, i, vp, vp]
+        _lib.bnet_tc_conv3x3_wgrad.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, vp, vp]
+        _lib.bnet_tc_conv3x3_wgrad_tiles.argtypes = [i, i]
+        _lib.bnet_tc_conv3x3_wgrad_plan.argtypes = [i, i, i, i, i, i, C.POINTER(tc_linear.Plan)]
         _lib.bnet_tc_last_error.restype = C.c_char_p
     return _lib
 
@@ -100,6 +111,118 @@ def conv3x3_dgrad(gy: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     LAUNCHES += rc
     tc_linear.LAUNCHES += rc
     return dx
+
+
+def wgrad_plan(n: int, h: int, w: int, cin: int, cout: int, splits: int = 0) -> dict:
+    """The tiling the filter-gradient kernel would use (host-only; works without a GPU)."""
+    p = tc_linear.Plan()
+    if _L().bnet_tc_conv3x3_wgrad_plan(n, h, w, cin, cout, splits, C.byref(p)) != 0:
+        raise ValueError(_L().bnet_tc_last_error().decode())
+    return p.as_dict()
+
+
+_wgrad_scratch: dict = {}
+
+
+def _wgrad_ws(device, cin: int, cout: int):
+    """fp32 [Cout, 9 Cin] workspace + tile counters of the split-K fix-up, shared by every call of that shape on that device
+    (calls on one stream are ordered; the kernel hands both back all-zero)."""
+    key = (device.index, cin, cout)
+    if key not in _wgrad_scratch:
+        tiles = _L().bnet_tc_conv3x3_wgrad_tiles(cin, cout)
+        _wgrad_scratch[key] = (torch.zeros((cout, 9 * cin), dtype=torch.float32, device=device),
+                               torch.zeros(tiles + 8, dtype=torch.int32, device=device))
+    return _wgrad_scratch[key]
+
+
+def wgrad_shape_ok(gy: torch.Tensor, x: torch.Tensor) -> bool:
+    if not (gy.is_cuda and gy.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and _nhwc(gy) and _nhwc(x)):
+        return False
+    if gy.shape[0] != x.shape[0] or gy.shape[2:] != x.shape[2:] or gy.data_ptr() % 16 or x.data_ptr() % 16:
+        return False
+    return gy.shape[1] % 64 == 0 and x.shape[1] % 64 == 0
+
+
+def conv3x3_wgrad(gy: torch.Tensor, x: torch.Tensor, splits: int = 0) -> torch.Tensor:
+    """Filter gradient of ``conv2d(x, w, stride=1, padding=1)``: gy [N,Cout,H,W], x [N,Cin,H,W] channels_last bf16 ->
+    dw [Cout,Cin,3,3] channels_last bf16 (memory [Cout][3][3][Cin]).  ``splits``: slices of the pixel reduction (0 = as many
+    as fill the SMs)."""
+    global LAUNCHES
+    n, cout, h, wd = gy.shape
+    cin = x.shape[1]
+    dw = torch.empty((cout, cin, 3, 3), device=gy.device, dtype=torch.bfloat16, memory_format=torch.channels_last)
+    ws, counters = _wgrad_ws(gy.device, cin, cout)
+    L = _L()
+    rc = L.bnet_tc_conv3x3_wgrad(gy.data_ptr(), x.data_ptr(), dw.data_ptr(), ws.data_ptr(), counters.data_ptr(), n, h, wd, cin, cout,
+                                 splits, tc_linear._err_flag(gy.device.index).data_ptr(), tc_linear._stream())
+    if rc < 0:
+        raise RuntimeError(f"bnet_tc_conv3x3_wgrad: {L.bnet_tc_last_error().decode()}")
+    LAUNCHES += rc
+    tc_linear.LAUNCHES += rc
+    return dw
+
+
+_wgrad_trusted = None
+
+
+def wgrad_trusted() -> bool:
+    """May the filter-gradient kernel run in THIS process?  ``BNET_TC_WGRAD``: ``0`` never, ``1`` yes (no check), default:
+    only after ``self_check_wgrad()`` passed in a child process on this GPU — a kernel that has never run on hardware must
+    not be able to poison the training process' CUDA context.  The verdict is cached per library build and GPU model."""
+    global _wgrad_trusted
+    if _wgrad_trusted is None:
+        v = os.environ.get("BNET_TC_WGRAD", "auto").lower()
+        if v in ("0", "off") or not usable():
+            _wgrad_trusted = False
+        elif v in ("1", "on"):
+            _wgrad_trusted = True
+        else:
+            if torch.cuda.is_current_stream_capturing():
+                return False
+            _wgrad_trusted = tc_linear._isolated_self_check(
+                check="from bagua_net_b200.ops import tc_conv; ok = tc_conv.self_check_wgrad()", tag="tc_wgrad_self_check")
+    return _wgrad_trusted
+
+
+def choose_wgrad(gy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, cudnn_fn) -> str:
+    """"tc" or "cudnn" for this layer's filter gradient: like ``choose`` (results compared, both timed, winner cached per
+    shape), behind ``wgrad_trusted()``."""
+    n, cout, h, wd = gy.shape
+    key = ("wgrad", n, h, wd, x.shape[1], cout)
+    got = _choice.get(key)
+    if got is not None:
+        return got
+    m = mode()
+    if m == "off" or not usable() or not wgrad_shape_ok(gy, x) or not w.is_contiguous(memory_format=torch.channels_last):
+        _choice[key] = "cudnn"
+        return "cudnn"
+    if torch.cuda.is_current_stream_capturing():
+        return "cudnn"
+    if not wgrad_trusted():
+        _choice[key] = "cudnn"
+        TIMINGS[key] = {"error": "weight-gradient kernel not trusted on this GPU (self-check in a child process failed or BNET_TC_WGRAD=0)"}
+        return "cudnn"
+    try:
+        def tc_fn():
+            return conv3x3_wgrad(gy, x)
+
+        a, b = tc_fn(), cudnn_fn()
+        torch.cuda.synchronize()
+        if tc_linear.last_error(gy.device.index):
+            raise RuntimeError("pipeline watchdog")
+        if not close(a, b):
+            raise RuntimeError("results differ from cuDNN")
+        del a, b
+        if m == "on":
+            _choice[key] = "tc"
+            return "tc"
+        t_tc, t_cudnn = _time_us(tc_fn), _time_us(cudnn_fn)
+        TIMINGS[key] = {"tc": round(t_tc, 1), "cudnn": round(t_cudnn, 1)}
+        _choice[key] = "tc" if t_tc <= t_cudnn else "cudnn"
+    except Exception as ex:   # noqa: BLE001 — anything unexpected keeps the library path for this shape
+        TIMINGS[key] = {"error": f"{type(ex).__name__}: {str(ex)[:80]}"}
+        _choice[key] = "cudnn"
+    return _choice[key]
 
 
 def _time_us(fn, iters: int = 5) -> float:
@@ -178,4 +301,33 @@ def self_check(device=None, verbose: bool = False) -> bool:
         if verbose:
             print(f"[tc_conv.self_check] N={n} {cin}->{cout} {hw}x{hw}: relative L2 errors {errs} watchdog {bad}")
         ok = ok and bad == 0 and all(e == e and e < 2e-2 for e in errs)
+    return ok
+
+
+def self_check_wgrad(device=None, verbose: bool = False) -> bool:
+    """The filter-gradient kernel against cuDNN in bf16: exact and ragged 64-pixel patches, one and many slices of the pixel
+    reduction, Cout below one lane tile, tiles that straddle taps (Cin = 64), columns past 9 Cin (Cin = 128), a VGG-sized
+    layer; the workspace and the tile counters must come back all zero."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    g = torch.Generator(device=dev).manual_seed(7)
+    ok = True
+    for n, cin, cout, hw, splits in ((2, 64, 64, 32, 0), (3, 64, 128, 14, 1), (2, 128, 256, 28, 0), (5, 256, 64, 7, 3),
+                                     (1, 64, 320, 20, 0), (32, 512, 512, 14, 0), (8, 128, 128, 56, 0)):
+        x = torch.randn(n, cin, hw, hw, device=dev, generator=g).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        gy = (torch.randn(n, cout, hw, hw, device=dev, generator=g) * (1.0 / hw)).to(torch.bfloat16).contiguous(
+            memory_format=torch.channels_last)
+        w = torch.empty(cout, cin, 3, 3, device=dev, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        errs = []
+        for _ in range(2):                    # twice: the second call runs on the scratch the first one handed back
+            dw = conv3x3_wgrad(gy, x, splits)
+            ref = torch.ops.aten.convolution_backward(gy, x, w, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [False, True, False])[1]
+            errs.append(((dw.float() - ref.float()).norm() / ref.float().norm().clamp_min(1e-6)).item())
+        torch.cuda.synchronize()
+        bad = tc_linear.last_error(dev.index)
+        ws, counters = _wgrad_ws(dev, cin, cout)
+        clean = bool((ws == 0).all().item()) and bool((counters == 0).all().item())
+        if verbose:
+            print(f"[tc_conv.self_check_wgrad] N={n} {cin}->{cout} {hw}x{hw} splits={splits}: relative L2 errors {errs} watchdog {bad} "
+                  f"scratch clean {clean}")
+        ok = ok and bad == 0 and clean and all(e == e and e < 2e-2 for e in errs)
     return ok

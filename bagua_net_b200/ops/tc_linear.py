@@ -12,9 +12,9 @@ multicast mapping, ``red.global`` per peer otherwise), so no separate all-reduce
 
 The reference has no compute path — this belongs to the B200 side of the framework.
 
-STATUS (round 1): built and descriptor-checked on the host, never run on hardware yet.  Nothing calls it unless
-``BNET_TC=1``; the GPU tests for it run only with ``BNET_TEST_TC=1``; ``self_check()`` must pass before any caller
-trusts it, and every launch carries a device-side watchdog (``last_error()``)."""
+STATUS: validated on B200 in round 2 (profiles/r2/tc_probe_1gpu.txt, profiles/r2/tc_linear_vs_cublas_1gpu.txt) and on by
+default (``BNET_TC=0`` disables); ``self_check()`` must pass on the GPU at hand before any caller trusts it
+(``trusted()``), and every launch carries a device-side watchdog (``last_error()``)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -248,9 +248,9 @@ def linear_bias_act(x, w, bias=None, relu=False):
 _trusted: bool | None = None
 
 
-def _isolated_self_check(timeout: float = 180.0) -> bool:
-    """``self_check()`` in a child process: a kernel that faults (a poisoned CUDA context) or hangs past its own watchdog
-    must not take the training process with it.  The verdict is cached per (library build, GPU model) under
+def _isolated_self_check(timeout: float = 180.0, check: str | None = None, tag: str = "tc_self_check") -> bool:
+    """``self_check()`` (or `check`: Python source that leaves its verdict in ``ok``) in a child process: a kernel that
+    faults (a poisoned CUDA context) or hangs past its own watchdog must not take the training process with it.  The verdict is cached per (library build, GPU model) under
     ``$BNET_CACHE_DIR`` (default ``~/.cache/bnet``), so only the first process on a machine pays for it."""
     import hashlib
     import json
@@ -265,7 +265,7 @@ def _isolated_self_check(timeout: float = 180.0) -> bool:
     except Exception:  # noqa: BLE001
         return False
     cache_dir = os.environ.get("BNET_CACHE_DIR") or os.path.join(os.path.expanduser("~"), ".cache", "bnet")
-    path = os.path.join(cache_dir, "tc_self_check_" + hashlib.sha1(key.encode()).hexdigest()[:16] + ".json")
+    path = os.path.join(cache_dir, tag + "_" + hashlib.sha1(key.encode()).hexdigest()[:16] + ".json")
     try:
         with open(path) as f:
             return bool(json.load(f)["ok"])
@@ -277,8 +277,8 @@ def _isolated_self_check(timeout: float = 180.0) -> bool:
         env.pop("CUDA_VISIBLE_DEVICES")
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):     # the child is a plain 1-GPU process
         env.pop(k, None)
-    code = ("import sys, torch; torch.cuda.set_device(%d); from bagua_net_b200.ops import tc_linear; "
-            "sys.exit(0 if tc_linear.self_check() else 1)" % torch.cuda.current_device())
+    body = check or "from bagua_net_b200.ops import tc_linear; ok = tc_linear.self_check()"
+    code = "import sys, torch; torch.cuda.set_device(%d); %s; sys.exit(0 if ok else 1)" % (torch.cuda.current_device(), body)
     try:
         ok = subprocess.run([sys.executable, "-c", code], env=env, timeout=timeout, stdout=subprocess.DEVNULL,
                             stderr=subprocess.DEVNULL).returncode == 0

@@ -695,6 +695,16 @@ def main() -> int:
             "clocks": clocks, "gpu_launches": nlaunch, "wall_ms_per_step": round(wall_total / args.steps, 3),
             "param_checksum": checksum,
         }
+        try:
+            # what the per-shape autotuner measured on THIS GPU (tcgen05 kernel vs cuDNN, us) and which one the step runs
+            from bagua_net_b200.ops import tc_conv
+
+            if tc_conv.TIMINGS or tc_conv._choice:
+                out["config"]["tc_conv_autotune"] = {
+                    f"{k[0]} n{k[1]} {k[2]}x{k[3]} {k[4]}->{k[5]}": dict(tc_conv.TIMINGS.get(k, {}), choice=v)
+                    for k, v in sorted(tc_conv._choice.items(), key=lambda kv: str(kv[0]))}
+        except Exception:   # noqa: BLE001 - reporting only
+            pass
         if e2e:
             out["e2e"] = {k: (round(v, 3) if isinstance(v, float) else v) for k, v in e2e.items()}
         for key, res in arms.items():
@@ -705,6 +715,8 @@ def main() -> int:
             cfg = res.get("config") or {}
             keep.update({k: cfg.get(k) for k in ("model", "comm", "path", "cuda_graph", "fused_conv_blocks", "fused_note", "graph_note")
                          if cfg.get(k) is not None})
+            if key == "resnet50_bnet" and cfg.get("tc_conv_autotune"):       # (the other arms run the headline's layer shapes)
+                keep["tc_conv_autotune"] = cfg["tc_conv_autotune"]
             ex = res.get("extra") or {}
             keep.update({k: ex[k] for k in ("allreduce_busbw_gbs_bf16", "allreduce_time_us", "allreduce_exact", "allreduce_error")
                          if k in ex})

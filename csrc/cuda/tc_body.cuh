@@ -359,6 +359,123 @@ inline const char* setup_conv(const void* x, const void* w, const void* bias, vo
   return nullptr;
 }
 
+// ---- convolution weight gradient ---------------------------------------------------------------------------------------
+//     dw[co, tap, ci] = sum over pixels p of  gy[p, co] * x[p shifted by tap, ci]
+// A GEMM whose REDUCTION runs over the pixels: D[i = co, j = tap * Cin + ci], both operands MN-major (reduction outer), the
+// output matrix [Cout][9 * Cin] IS the filter gradient in torch's channels_last layout.  One k-block = a patch of 64 pixels
+// (bw x bh pixels of bn images, bw * bh * bn == 64):
+//   lane operand   gy: one 4-D box {64 co, bw, bh, bn} per 64 output channels of the tile at (co0 + 64 h, w0, h0, n0)
+//   column operand x : one 4-D box {64 ci, bw, bh, bn} per 64 columns; every 64-column atom decodes its OWN (tap, ci0) —
+//                      Cin is a multiple of 64, so an atom never straddles two taps, and a tile may (9 * Cin need not be
+//                      a multiple of the tile width) — at (ci0, w0 + dw[tap], h0 + dh[tap], n0)
+// A box lands in shared memory as [64 pixel rows x 128 bytes], exactly the [64 reduction rows x 64 MN elements] atom the
+// MN-major shared-memory descriptor describes (the layout the linear layer's dW = gY^T . X already uses).  Padding, ragged
+// patches, channels past Cout and columns past 9 * Cin are all the TMA unit's zero fill.  The pixel blocks are split over
+// grid.z (split-K with the fix-up: TcArgs::fix_out), because Cout x 9 Cin alone rarely fills 148 SMs.
+template <int BN, class FA, class FB>
+BNET_TC_HD void wgrad_stage_loads(const TcArgs& args, const TileCoord& c, int kb, FA&& lda, FB&& ldb) {
+  const ConvGeom& g = args.conv;
+  int t = kb;
+  const int w0 = (t % g.tiles_w) * g.bw;
+  t /= g.tiles_w;
+  const int h0 = (t % g.tiles_h) * g.bh;
+  const int n0 = (t / g.tiles_h) * g.bn;
+  for (int h = 0; h < kBM / 64; h++) lda(h * kAtomBytes, c.a_row0 + 64 * h, w0, h0, n0);
+  for (int h = 0; h < BN / 64; h++) {
+    const int col = c.b_row0 + 64 * h;
+    int tap = col / g.col_pitch, ci0 = col - tap * g.col_pitch;
+    if (tap >= 9) { tap = 0; ci0 = g.col_pitch; }          // past the last filter column: a box outside the tensor (zeros)
+    ldb(h * kAtomBytes, ci0, w0 + g.dw[tap], h0 + g.dh[tap], n0);
+  }
+}
+
+// the 64-pixel patch that needs the fewest k-blocks (ties: the widest), all powers of two
+inline void conv_pick_patch64(int N, int H, int W, int* bw, int* bh, int* bn) {
+  long long best = -1;
+  for (int w = 1; w <= 64; w *= 2)
+    for (int h = 1; w * h <= 64; h *= 2) {
+      const int n = 64 / (w * h);
+      const long long tiles = (long long)((W + w - 1) / w) * ((H + h - 1) / h) * ((N + n - 1) / n);
+      if (best < 0 || tiles < best || (tiles == best && w > *bw)) { best = tiles; *bw = w; *bh = h; *bn = n; }
+    }
+}
+
+struct WgradProblem {
+  BnetTcPlan plan;
+  TcArgs args;
+  MapDesc4 gy_map, x_map;      // boxes of {64 channels, bw, bh, bn} with bw * bh * bn == 64
+};
+
+// dw[Cout][3][3][Cin] (bf16) = filter gradient of y = conv3x3(x, w), stride 1, pad 1; gy [N,H,W,Cout], x [N,H,W,Cin] NHWC bf16.
+// `ws`: fp32 [Cout][9 * Cin] workspace, `counters`: one int per output tile (>= wgrad_max_tiles), both all zero on entry and
+// left all zero.  splits <= 0: as many K slices as fill the SMs.  Pure: no CUDA calls.
+inline int wgrad_max_tiles(int Cin, int Cout) { return ((Cout + kBM - 1) / kBM) * ((9 * Cin + 127) / 128); }
+
+inline const char* setup_conv_wgrad(const void* gy, const void* x, float* ws, void* dw, int* counters, int N, int H, int W, int Cin,
+                                    int Cout, int splits, int* err_dev, int sm_count, WgradProblem* wp) {
+  if (N < 1 || H < 1 || W < 1 || Cin < 64 || Cin % 64 || Cout < 64 || Cout % 64)
+    return "conv3x3 wgrad: input and output channels must be multiples of 64";
+  if (!err_dev || !ws || !counters) return "conv3x3 wgrad needs err_dev, a workspace and tile counters";
+  if ((long long)N * H * W > 0x7fffffffLL) return "too many pixels for one launch";
+  TcArgs& a = wp->args;
+  memset(&a, 0, sizeof(a));
+  ConvGeom& g = a.conv;
+  g.N = N; g.H = H; g.W = W;
+  conv_pick_patch64(N, H, W, &g.bw, &g.bh, &g.bn);
+  g.tiles_w = (W + g.bw - 1) / g.bw;
+  g.tiles_h = (H + g.bh - 1) / g.bh;
+  g.tiles_n = (N + g.bn - 1) / g.bn;
+  g.cpb = Cin / 64;
+  g.col_pitch = Cin;
+  for (int t = 0; t < 9; t++) {
+    g.dh[t] = (signed char)(t / 3 - 1);
+    g.dw[t] = (signed char)(t % 3 - 1);
+  }
+  const long long kblocks = (long long)g.tiles_w * g.tiles_h * g.tiles_n;
+  if (kblocks > 0x3fffffffLL) return "too many pixel blocks";
+  const int cols = 9 * Cin;
+  // 256-column tiles (half the MMA issues per byte of gy) unless they waste more than ~1/7 of the columns (Cin = 64: 576 columns)
+  const int t256 = (cols + 255) / 256, t128 = (cols + 127) / 128;
+  const int bn_cols = (long long)t256 * 256 * 7 <= (long long)cols * 8 ? 256 : 128;
+  const int tiles_b = bn_cols == 256 ? t256 : t128;
+  const int tiles_a = (Cout + kBM - 1) / kBM;
+  BnetTcPlan& p = wp->plan;
+  memset(&p, 0, sizeof(p));
+  p.swap = 0;
+  p.bn = bn_cols;
+  p.stages = stages_for(bn_cols);
+  p.grid_x = tiles_b;
+  p.grid_y = tiles_a;
+  p.k_blocks = (int)kblocks;
+  const int n_tiles = tiles_a * tiles_b;
+  int z = splits > 0 ? splits : (sm_count / n_tiles > 0 ? sm_count / n_tiles : 1);
+  if (z > p.k_blocks) z = p.k_blocks;
+  if (z > 65535) z = 65535;
+  p.k_per_split = (p.k_blocks + z - 1) / z;
+  p.grid_z = (p.k_blocks + p.k_per_split - 1) / p.k_per_split;      // no empty slices
+  p.smem_bytes = p.stages * (kABytes + bn_cols * kBK * 2) + 1024 + (2 * p.stages + 4) * 8 + 16;
+  const int per_slice = sm_count / p.grid_z > 0 ? sm_count / p.grid_z : 1;
+  p.ctas = n_tiles < per_slice ? n_tiles : per_slice;
+  a.rows_a = Cout;
+  a.rows_b = cols;
+  a.tiles_a = tiles_a;
+  a.n_tiles = n_tiles;
+  a.k_blocks = p.k_blocks;
+  a.k_per_split = p.k_per_split;
+  a.ldo = cols;
+  a.act = BNET_TC_ACT_NONE;
+  a.bias = nullptr;
+  a.outs[0] = ws;
+  a.n_outs = 1;
+  a.err = err_dev;
+  a.fix_out = dw;
+  a.fix_counters = counters;
+  a.fix_ldo = cols;
+  wp->gy_map = MapDesc4{gy, Cout, W, H, N, g.bw, g.bh, g.bn};
+  wp->x_map = MapDesc4{x, Cin, W, H, N, g.bw, g.bh, g.bn};
+  return nullptr;
+}
+
 // One epilogue step of one thread: 16 consecutive accumulator columns (j0 .. j0+15) of accumulator row i_glob.
 //   kSwap:   false -> lane i = batch row m, column j = feature n; out[m, n] = out[i * ldo + j]
 //            true  -> lane i = feature n,   column j = batch row m; out[m, n] = out[j * ldo + i]

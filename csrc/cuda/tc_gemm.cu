@@ -30,8 +30,10 @@
 // Every mbarrier wait carries a watchdog (kWatchdogNs): a pipeline that stops — a descriptor the hardware rejects, a
 // lost TMA completion — sets *err and lets every role fall through to the teardown instead of hanging the GPU.
 //
-// STATUS: not yet run on hardware (see include/bnet/bnet_tc.h).  Descriptor packing is unit-tested against CuTe
-// (csrc/tests/tc_desc_test.cc).
+// STATUS: validated on B200 in round 2 (profiles/r2/tc_probe_1gpu.txt: every probe of tools/tc_probe.py, linear forward /
+// backward, split-K, GEMM + all-reduce, 3x3 convolution forward + input gradient); the convolution WEIGHT gradient
+// (kConv == 2) was written afterwards and has only run on the CPU emulation — ops/tc_conv.py therefore trusts it only after a
+// self-check in a child process on the GPU at hand.  Descriptor packing is unit-tested against CuTe (csrc/tests/tc_desc_test.cc).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -207,14 +209,17 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // boundaries, and the accumulator is double-buffered in TMEM (2 x BN columns): the epilogue of tile t drains one half
 // while the MMAs of tile t+1 fill the other.  With gridDim.x == n_tiles every CTA simply does one tile.
 // kAMn / kBMn: the lane / column operand is MN-major (reduction dimension outer) instead of K-major
-// kConv: the lane operand is a 3x3 convolution's input patch, loaded as 4-D TMA boxes (tc_body.cuh::ConvGeom)
-template <int BN, int kStages, bool kSwap, bool kReduce, bool kAMn, bool kBMn, bool kConv = false>
+// kConv: 1 = the lane operand is a 3x3 convolution's input patch, loaded as 4-D TMA boxes (tc_body.cuh::ConvGeom);
+//        2 = convolution weight gradient: BOTH operands are 4-D boxes of NHWC activations (gy on the lanes through
+//            maps_batch.m[0], the shifted input on the columns through map_feat), MN-major, the reduction runs over pixels
+template <int BN, int kStages, bool kSwap, bool kReduce, bool kAMn, bool kBMn, int kConv = 0>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_linear_kernel(const __grid_constant__ TcBatchMaps maps_batch, const __grid_constant__ CUtensorMap map_feat, const TcArgs args) {
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M = 128");
   static_assert((BN & (BN - 1)) == 0 && BN >= 32, "TMEM allocations are powers of two >= 32 columns");
   static_assert(!kBMn || BN % 64 == 0, "an MN-major operand is staged in 64-element atoms");
-  static_assert(!kConv || (!kSwap && !kAMn && !kReduce), "convolution: pixels ride the lanes, K-major patches, bf16 store");
+  static_assert(kConv != 1 || (!kSwap && !kAMn && !kReduce), "convolution: pixels ride the lanes, K-major patches, bf16 store");
+  static_assert(kConv != 2 || (!kSwap && kAMn && kBMn && kReduce), "weight gradient: MN-major operands, split over pixel blocks");
   constexpr uint32_t kTmemCols = 2 * BN;          // two accumulator stages
   extern __shared__ uint8_t smem_raw[];
   // swizzle-128B atoms must start on 1024-byte boundaries of the shared window
@@ -262,16 +267,20 @@ tc_linear_kernel(const __grid_constant__ TcBatchMaps maps_batch, const __grid_co
         const CUtensorMap* map_a = kSwap ? &map_feat : &maps_batch.m[tc.a_map];
         const CUtensorMap* map_b = kSwap ? &maps_batch.m[tc.b_map] : &map_feat;
         ConvTile ct{};
-        if constexpr (kConv) ct = conv_tile<BN>(args, t);
+        if constexpr (kConv == 1) ct = conv_tile<BN>(args, t);
         for (int i = 0; i < nkb; i++, g++) {
           const uint32_t s = g % kStages, round = g / kStages;
           if (round > 0 && !mbar_wait_wd(empty0 + 8 * s, (round - 1) & 1, args.err, 1)) { alive = false; break; }
           const uint32_t a_dst = base + s * Smem<BN>::kStageBytes, bar = full0 + 8 * s;
           mbar_expect_tx(bar, Smem<BN>::kStageBytes);
-          if constexpr (kConv) {
+          if constexpr (kConv == 1) {
             conv_stage_loads<BN, kBMn>(args, ct, kb_begin + i,
                 [&](int offset, int c0, int c1, int c2, int c3) { tma_load_4d(a_dst + offset, &maps_batch.m[0], bar, c0, c1, c2, c3); },
                 [&](int offset, int c0, int c1) { tma_load_2d(a_dst + kABytes + offset, &map_feat, bar, c0, c1); });
+          } else if constexpr (kConv == 2) {
+            wgrad_stage_loads<BN>(args, tc, kb_begin + i,
+                [&](int offset, int c0, int c1, int c2, int c3) { tma_load_4d(a_dst + offset, &maps_batch.m[0], bar, c0, c1, c2, c3); },
+                [&](int offset, int c0, int c1, int c2, int c3) { tma_load_4d(a_dst + kABytes + offset, &map_feat, bar, c0, c1, c2, c3); });
           } else {
             stage_loads<BN, kAMn, kBMn>(tc, (kb_begin + i) * kBK, [&](int operand, int offset, int c0, int c1) {
               tma_load_2d(a_dst + (operand ? kABytes : 0) + offset, operand ? map_b : map_a, bar, c0, c1);
@@ -320,7 +329,7 @@ tc_linear_kernel(const __grid_constant__ TcBatchMaps maps_batch, const __grid_co
       const uint32_t as = lt & 1;
       TileCoord tc = tile_coord<BN, kSwap>(args, t);
       int i_glob = tc.a_row0 + q * 32 + lane;         // row of the lane operand this thread owns
-      if constexpr (kConv) {
+      if constexpr (kConv == 1) {
         // the lane is a pixel of the tile's patch: its row in the [N*H*W, Cout] output, or "past the end" outside the image
         const ConvTile ct = conv_tile<BN>(args, t);
         const long long row = conv_out_row(args, ct, q * 32 + lane);
@@ -434,7 +443,7 @@ bool make_map(CUtensorMap* map, const MapDesc& d) {
   return true;
 }
 
-template <int BN, int kStages, bool kSwap, bool kReduce, bool kAMn, bool kBMn, bool kConv = false>
+template <int BN, int kStages, bool kSwap, bool kReduce, bool kAMn, bool kBMn, int kConv = 0>
 int launch(const TcBatchMaps& mbatch, const CUtensorMap& mfeat, const TcArgs& a, const BnetTcPlan& p, cudaStream_t st) {
   auto kern = tc_linear_kernel<BN, kStages, kSwap, kReduce, kAMn, kBMn, kConv>;
   static std::once_flag once;
@@ -535,11 +544,32 @@ int run_conv(const void* x, const void* w, const void* bias, void* out, int N, i
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const BnetTcPlan& p = cp.plan;
 #define BNET_CONV_CASE(BN, BMN) \
-  if (p.bn == BN && cp.dgrad == BMN) return launch<BN, stages_for(BN), false, false, false, BMN, true>(mbatch, mfeat, cp.args, p, st);
+  if (p.bn == BN && cp.dgrad == BMN) return launch<BN, stages_for(BN), false, false, false, BMN, 1>(mbatch, mfeat, cp.args, p, st);
   BNET_CONV_CASE(64, false) BNET_CONV_CASE(128, false) BNET_CONV_CASE(256, false)
   BNET_CONV_CASE(64, true)  BNET_CONV_CASE(128, true)  BNET_CONV_CASE(256, true)
 #undef BNET_CONV_CASE
   g_err = "no convolution kernel for this plan";
+  return -1;
+}
+
+// filter gradient: index logic tc_body.cuh::setup_conv_wgrad; both tensor maps are 4-D NHWC maps with 64-pixel boxes
+int run_conv_wgrad(const void* gy, const void* x, void* dw, float* ws, int* counters, int N, int H, int W, int Cin, int Cout, int splits,
+                   int* err_dev, void* stream) {
+  WgradProblem wp;
+  if (const char* e = setup_conv_wgrad(gy, x, ws, dw, counters, N, H, W, Cin, Cout, splits, err_dev, sm_count(), &wp)) {
+    g_err = e;
+    return -1;
+  }
+  if (reinterpret_cast<uintptr_t>(dw) & 15) { g_err = "the filter gradient must be 16-byte aligned"; return -1; }
+  TcBatchMaps mbatch;
+  CUtensorMap mfeat;
+  if (!make_map_nhwc(&mbatch.m[0], wp.gy_map)) return -1;
+  if (!make_map_nhwc(&mfeat, wp.x_map)) return -1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const BnetTcPlan& p = wp.plan;
+  if (p.bn == 128) return launch<128, stages_for(128), false, true, true, true, 2>(mbatch, mfeat, wp.args, p, st);
+  if (p.bn == 256) return launch<256, stages_for(256), false, true, true, true, 2>(mbatch, mfeat, wp.args, p, st);
+  g_err = "no weight-gradient kernel for this plan";
   return -1;
 }
 
@@ -639,4 +669,29 @@ BNET_API int bnet_tc_conv3x3(const void* x, const void* w, const void* bias, voi
 BNET_API int bnet_tc_conv3x3_dgrad(const void* gy, const void* w, void* dx, int N, int H, int W, int Cin, int Cout, int* err_dev,
                                    void* stream) {
   return run_conv(gy, w, nullptr, dx, N, H, W, Cout, Cin, BNET_TC_ACT_NONE, 1, err_dev, stream);
+}
+
+// dw[Cout][3][3][Cin] = filter gradient of the same convolution: gy [N,H,W,Cout] and x [N,H,W,Cin] are read as 4-D TMA boxes of
+// 64 pixels (the reduction), both MN-major; the pixel blocks are split over grid.z and the slice that arrives last at a tile
+// converts the fp32 sums to bf16 (split-K fix-up).  `ws` (fp32 [Cout][9 Cin]) and `counters` (bnet_tc_conv3x3_wgrad_tiles ints)
+// must be all zero on entry and are all zero again on exit.  splits <= 0: automatic.  Cin and Cout multiples of 64.
+BNET_API int bnet_tc_conv3x3_wgrad(const void* gy, const void* x, void* dw, float* ws, int* counters, int N, int H, int W, int Cin,
+                                   int Cout, int splits, int* err_dev, void* stream) {
+  return run_conv_wgrad(gy, x, dw, ws, counters, N, H, W, Cin, Cout, splits, err_dev, stream);
+}
+BNET_API int bnet_tc_conv3x3_wgrad_tiles(int Cin, int Cout) { return wgrad_max_tiles(Cin, Cout); }
+// the tiling of a filter gradient (pure host function, like bnet_tc_plan): grid_x x grid_y tiles of 128 x bn, grid_z slices of
+// the k_blocks 64-pixel blocks, ctas per slice
+BNET_API int bnet_tc_conv3x3_wgrad_plan(int N, int H, int W, int Cin, int Cout, int splits, BnetTcPlan* plan) {
+  if (!plan) { g_err = "null plan"; return -1; }
+  WgradProblem wp;
+  float ws_dummy = 0.f;
+  int counters_dummy = 0, err_dummy = 0;
+  if (const char* e = setup_conv_wgrad(&ws_dummy, &ws_dummy, &ws_dummy, &ws_dummy, &counters_dummy, N, H, W, Cin, Cout, splits,
+                                       &err_dummy, sm_count(), &wp)) {
+    g_err = e;
+    return -1;
+  }
+  *plan = wp.plan;
+  return 0;
 }

@@ -369,8 +369,130 @@ static void conv(int N, int H, int W, int Cin, int Cout, bool relu, int sms) {
   CHECK(bad == 0, "conv dgrad N=%d %dx%d %d->%d (bn %d): %d wrong", N, H, W, Cin, Cout, cp.plan.bn, bad);
 }
 
+// ---- convolution weight gradient: both operands 4-D boxes of 64 pixels, MN-major; split over pixel blocks with the fix-up --
+template <int BN>
+static void run_wgrad_kernel(const WgradProblem& wp, const HostOut& out) {
+  const TcArgs& args = wp.args;
+  const BnetTcPlan& p = wp.plan;
+  std::vector<uint16_t> stage_a(kABytes / 2), stage_b(BN * kBK);
+  std::vector<float> tmem(size_t(kBM) * BN);
+  CHECK(args.conv.bw * args.conv.bh * args.conv.bn == 64, "wgrad patch %d x %d x %d", args.conv.bw, args.conv.bh, args.conv.bn);
+  CHECK(wp.gy_map.bw * wp.gy_map.bh * wp.gy_map.bn == 64 && wp.x_map.bw * wp.x_map.bh * wp.x_map.bn == 64, "wgrad boxes");
+  int* counters = args.fix_counters;
+  float* ws = static_cast<float*>(args.outs[0]);
+  for (int z = 0; z < p.grid_z; z++) {
+    const int kb_begin = z * args.k_per_split;
+    const int kb_end = kb_begin + args.k_per_split < args.k_blocks ? kb_begin + args.k_per_split : args.k_blocks;
+    CHECK(kb_end > kb_begin, "empty pixel slice %d", z);
+    for (int cta = 0; cta < p.ctas; cta++)
+      for (int t = cta; t < args.n_tiles; t += p.ctas) {
+        const TileCoord tc = tile_coord<BN, false>(args, t);
+        std::fill(tmem.begin(), tmem.end(), 0.f);
+        for (int kb = kb_begin; kb < kb_end; kb++) {
+          std::fill(stage_a.begin(), stage_a.end(), uint16_t(0x7fc0));
+          std::fill(stage_b.begin(), stage_b.end(), uint16_t(0x7fc0));
+          int bytes = 0;
+          wgrad_stage_loads<BN>(args, tc, kb,
+              [&](int offset, int c0, int c1, int c2, int c3) { tma_box4(wp.gy_map, c0, c1, c2, c3, stage_a.data() + offset / 2); bytes += kAtomBytes; },
+              [&](int offset, int c0, int c1, int c2, int c3) { tma_box4(wp.x_map, c0, c1, c2, c3, stage_b.data() + offset / 2); bytes += kAtomBytes; });
+          CHECK(bytes == kABytes + BN * kBK * 2, "wgrad expect_tx bytes %d", bytes);
+          for (int i = 0; i < kBM; i++)
+            for (int j = 0; j < BN; j++) {
+              float s = 0.f;
+              for (int k = 0; k < kBK; k++) s += stage_at(stage_a.data(), true, i, k) * stage_at(stage_b.data(), true, j, k);
+              tmem[size_t(i) * BN + j] += s;
+            }
+        }
+        // the epilogue of the reduce instantiation: fp32 adds into the workspace ...
+        for (int r = 0; r < kBM; r++)
+          for (int c = 0; c < BN / 16; c++) {
+            float acc[16];
+            for (int u = 0; u < 16; u++) acc[u] = tmem[size_t(r) * BN + c * 16 + u];
+            epilogue_chunk<false, true>(args, tc.a_row0 + r, tc.b_row0 + c * 16, acc, false, out);
+          }
+        // ... and the fix-up: the slice that arrives last at the tile reads the sums back, writes bf16, re-zeroes what it read
+        if (++counters[t] == p.grid_z) {
+          TcArgs fa = args;
+          fa.outs[0] = args.fix_out;
+          fa.ldo = args.fix_ldo;
+          for (int r = 0; r < kBM; r++) {
+            const int i_glob = tc.a_row0 + r;
+            if (i_glob >= args.rows_a) continue;
+            for (int c = 0; c < BN / 16; c++) {
+              const int j0 = tc.b_row0 + c * 16;
+              if (j0 >= args.rows_b) break;
+              float acc[16];
+              for (int u = 0; u < 16; u++) {
+                acc[u] = 0.f;
+                if (j0 + u < args.rows_b) {
+                  float* q = ws + size_t(i_glob) * args.ldo + j0 + u;
+                  acc[u] = *q;
+                  *q = 0.f;
+                }
+              }
+              epilogue_chunk<false, false>(fa, i_glob, j0, acc, false, out);
+            }
+          }
+          counters[t] = 0;
+        }
+      }
+  }
+}
+
+static void conv_wgrad(int N, int H, int W, int Cin, int Cout, int sms, int splits) {
+  Mat gy(N * H * W, Cout), x(N * H * W, Cin);
+  const int cols = 9 * Cin;
+  std::vector<float> ws(size_t(Cout) * cols, 0.f);
+  std::vector<int> counters(wgrad_max_tiles(Cin, Cout), 0);
+  std::vector<uint16_t> dv(size_t(Cout) * cols + 16, 0xdead);
+  uint16_t* dw = dv.data();
+  while (reinterpret_cast<uintptr_t>(dw) & 15) dw++;
+  int err = 0;
+  WgradProblem wp;
+  const char* e = setup_conv_wgrad(gy.ptr(), x.ptr(), ws.data(), dw, counters.data(), N, H, W, Cin, Cout, splits, &err, sms, &wp);
+  CHECK(e == nullptr, "wgrad setup: %s", e ? e : "");
+  if (e) return;
+  CHECK(wp.args.n_tiles <= (int)counters.size(), "wgrad_max_tiles %zu < %d tiles", counters.size(), wp.args.n_tiles);
+  CHECK((long long)wp.plan.ctas * wp.plan.grid_z <= (sms > wp.plan.grid_z ? sms : wp.plan.grid_z) || wp.plan.ctas == 1, "wgrad launches %d x %d CTAs on %d SMs",
+        wp.plan.ctas, wp.plan.grid_z, sms);
+  if (wp.plan.bn == 128) run_wgrad_kernel<128>(wp, HostOut{});
+  else run_wgrad_kernel<256>(wp, HostOut{});
+  int bad = 0;
+  for (int co = 0; co < Cout; co++)
+    for (int kh = 0; kh < 3; kh++)
+      for (int kw = 0; kw < 3; kw++)
+        for (int ci = 0; ci < Cin; ci++) {
+          double r = 0;
+          for (int n = 0; n < N; n++)
+            for (int h = 0; h < H; h++)
+              for (int w2 = 0; w2 < W; w2++) {
+                const int hi = h + kh - 1, wi = w2 + kw - 1;          // the input pixel output (h, w) read through tap (kh, kw)
+                if (hi < 0 || hi >= H || wi < 0 || wi >= W) continue;
+                r += double(gy.at((n * H + h) * W + w2, co)) * x.at((n * H + hi) * W + wi, ci);
+              }
+          if (!close(bf16_to_f32(dw[size_t(co) * cols + (kh * 3 + kw) * Cin + ci]), r)) bad++;
+        }
+  if (getenv("TC_EMU_VERBOSE"))
+    printf("  wgrad N=%d %dx%d %d->%d: patch %dx%dx%d, %d pixel blocks in %d slices, %d tiles of 128x%d on %d CTAs per slice, %d wrong\n", N, H, W,
+           Cin, Cout, wp.args.conv.bw, wp.args.conv.bh, wp.args.conv.bn, wp.plan.k_blocks, wp.plan.grid_z, wp.args.n_tiles, wp.plan.bn,
+           wp.plan.ctas, bad);
+  int dirty = 0;
+  for (float v : ws) dirty += v != 0.f;
+  for (int c : counters) dirty += c != 0;
+  CHECK(bad == 0 && dirty == 0, "conv wgrad N=%d %dx%d %d->%d (patch %dx%dx%d bn %d tiles %d slices %d ctas %d): %d wrong, %d scratch words left dirty",
+        N, H, W, Cin, Cout, wp.args.conv.bw, wp.args.conv.bh, wp.args.conv.bn, wp.plan.bn, wp.args.n_tiles, wp.plan.grid_z, wp.plan.ctas, bad, dirty);
+}
+
 int main() {
-  // 3x3 convolutions: exact patches, ragged patches (7x7, 14x14 with odd batch), several images per patch, persistent CTAs
+  // filter gradients: exact and ragged 64-pixel patches, Cout below / above one lane tile, tiles that straddle taps (Cin = 64
+  // with 128 columns), columns past 9 * Cin (Cin = 128 with 256-column tiles), one slice / many slices / persistent CTAs
+  conv_wgrad(2, 8, 8, 64, 64, 148, 0);
+  conv_wgrad(3, 7, 7, 64, 128, 4, 0);
+  conv_wgrad(1, 14, 14, 128, 64, 148, 3);
+  conv_wgrad(5, 4, 4, 64, 192, 2, 1);
+  conv_wgrad(2, 6, 10, 128, 256, 7, 0);
+  conv_wgrad(1, 5, 3, 256, 128, 148, 0);
+  // forward / input gradient: exact patches, ragged patches (7x7, 14x14 with odd batch), several images per patch, persistent CTAs
   conv(2, 8, 16, 64, 64, true, 148);
   conv(3, 7, 7, 64, 128, false, 3);
   conv(1, 14, 14, 128, 64, true, 2);

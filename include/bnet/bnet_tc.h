@@ -11,9 +11,10 @@
  * overlaps the math of tile t+1.  The caller zeroes the output, runs a rank barrier before and after (bnet_barrier).
  *
  * The reference has no counterpart (it moves bytes for NCCL): this is the B200 "compute step followed
- * by a collective" path.  STATUS: compiles for sm_100a and its descriptor packing is checked against the CuTe
- * definitions on the host (tests/test_utils.py), but it has not run on hardware yet — it is off unless BNET_TC=1 and
- * every launch carries a watchdog that turns a stuck pipeline into an error code instead of a hang.
+ * by a collective" path.  STATUS: validated on B200 in round 2 (profiles/r2/tc_probe_1gpu.txt; on by default, BNET_TC=0
+ * disables); descriptor packing is checked against the CuTe definitions on the host (tests/test_utils.py), and every
+ * launch carries a watchdog that turns a stuck pipeline into an error code instead of a hang.  The convolution filter
+ * gradient (bnet_tc_conv3x3_wgrad) came after the last hardware session: CPU-emulated only, see ops/tc_conv.py.
  */
 #ifndef BNET_TC_H_
 #define BNET_TC_H_
@@ -88,6 +89,15 @@ int bnet_tc_conv3x3(const void* x, const void* w, const void* bias, void* out, i
                     int* err_dev, void* stream);
 int bnet_tc_conv3x3_dgrad(const void* gy, const void* w, void* dx, int N, int H, int W, int Cin, int Cout, int* err_dev,
                           void* stream);
+/* Filter gradient dw[Cout][3][3][Cin] (bf16) of the same convolution: D[co, tap * Cin + ci] = sum over pixels of
+ * gy[p, co] * x[p + tap, ci] — both operands MN-major 4-D TMA boxes of 64 pixels, the pixel blocks split over grid.z, the
+ * slice that arrives last at a tile converts the fp32 sums (split-K fix-up).  `ws`: fp32 [Cout][9 Cin], `counters`:
+ * bnet_tc_conv3x3_wgrad_tiles(Cin, Cout) ints; both all zero on entry and all zero again on exit.  splits <= 0: automatic.
+ * Cin % 64 == 0, Cout % 64 == 0. */
+int bnet_tc_conv3x3_wgrad(const void* gy, const void* x, void* dw, float* ws, int* counters, int N, int H, int W, int Cin, int Cout,
+                          int splits, int* err_dev, void* stream);
+int bnet_tc_conv3x3_wgrad_tiles(int Cin, int Cout);
+int bnet_tc_conv3x3_wgrad_plan(int N, int H, int W, int Cin, int Cout, int splits, BnetTcPlan* plan);   /* host only */
 
 /* The 64-bit shared-memory matrix descriptor (K-major, 128-byte swizzle) and the 32-bit instruction descriptor
  * (bf16 x bf16 -> fp32) the kernel issues, exposed so a host test can compare them with the CuTe definitions. */

@@ -1045,6 +1045,24 @@ def job_tc_conv():
     teardown()
 
 
+def job_tc_conv_wgrad():
+    """The tcgen05 filter gradient against cuDNN (several shapes, one and many pixel slices, scratch handed back clean),
+    then inside a fused conv block: the autotuner may pick it per shape, training must look the same either way."""
+    from bagua_net_b200.ops import tc_conv, tc_linear
+
+    setup()
+    assert tc_linear.supported()
+    assert tc_conv.self_check_wgrad(verbose=RANK == 0), "tcgen05 filter gradient differs from cuDNN"
+    os.environ["BNET_TC_WGRAD"] = "1"          # just checked in this very process
+    x = torch.randn(8, 128, 28, 28, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
+    gy = torch.randn(8, 256, 28, 28, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last) / 28
+    w = torch.randn(256, 128, 3, 3, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
+    ref = lambda: torch.ops.aten.convolution_backward(gy, x, w, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [False, True, False])[1]   # noqa: E731
+    pick = tc_conv.choose_wgrad(gy, x, w, ref)
+    print(f"tcgen05 conv3x3 filter gradient matches cuDNN; autotuner for 128->256 @28: {pick} {tc_conv.TIMINGS}", flush=True)
+    teardown()
+
+
 JOBS = {k[4:]: v for k, v in globals().items() if k.startswith("job_")}
 
 if __name__ == "__main__":

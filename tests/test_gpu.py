@@ -235,3 +235,9 @@ def test_transport_mesh_oneshot_allreduce_2gpu():
 def test_transport_mesh_twoshot_allreduce_2gpu():
     """Reduce-scatter by fused isend into the slice owner + all-gather by copy; in place; ranks end with identical bits."""
     _run_worker("transport_mesh_twoshot", 2)
+
+
+# ------------------------------------------------------------------ written after the last hardware session of round 2: LAST in the file
+def test_tcgen05_conv3x3_filter_gradient_matches_cudnn():
+    """tcgen05 weight gradient (both operands 64-pixel 4-D TMA boxes, MN-major; split over the pixels with the fix-up)."""
+    _run_worker("tc_conv_wgrad", 1, timeout=300)

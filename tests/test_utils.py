@@ -334,6 +334,46 @@ def test_tc_self_check_runs_isolated_and_is_cached(monkeypatch, tmp_path):
     assert tc_linear._isolated_self_check(timeout=0.001) is True
 
 
+def test_tc_conv_wgrad_plan_and_gating(monkeypatch, tmp_path):
+    """The tcgen05 filter gradient: every VGG16 layer it accepts (batch 32) is cut into enough pixel slices to put 140+ CTAs
+    on the 148 SMs with one resident CTA each, within shared memory; and the kernel — never run on hardware yet — is only
+    trusted after a self-check in a child process, with the verdict cached under its own name."""
+    import glob
+
+    import torch
+
+    from bagua_net_b200.ops import tc_conv, tc_linear
+
+    for cin, cout, hw in ((64, 64, 224), (64, 128, 112), (128, 128, 112), (128, 256, 56), (256, 256, 56), (256, 512, 28), (512, 512, 28),
+                          (512, 512, 14)):
+        p = tc_conv.wgrad_plan(32, hw, hw, cin, cout)
+        assert 140 <= p["ctas"] * p["grid_z"] <= 148, (cin, cout, hw, p)
+        assert p["k_blocks"] == 32 * hw * hw // 64 and p["k_per_split"] * p["grid_z"] >= p["k_blocks"]          # exact 64-pixel patches
+        assert (p["grid_z"] - 1) * p["k_per_split"] < p["k_blocks"]                                              # no empty slice
+        assert p["grid_x"] * p["bn"] >= 9 * cin and p["grid_y"] * 128 >= cout and p["smem_bytes"] + 1024 <= 227 * 1024
+        assert p["grid_x"] * p["grid_y"] <= tc_conv._L().bnet_tc_conv3x3_wgrad_tiles(cin, cout)
+    assert tc_conv.wgrad_plan(32, 28, 28, 512, 512, splits=1)["grid_z"] == 1
+    assert tc_conv.wgrad_plan(32, 28, 28, 512, 512, splits=1)["ctas"] == 72
+    with pytest.raises(ValueError):
+        tc_conv.wgrad_plan(32, 224, 224, 3, 64)                      # the first layer stays with cuDNN
+    # gating: off by switch, and without a passing child-process check
+    monkeypatch.setenv("BNET_TC_WGRAD", "0")
+    monkeypatch.setattr(tc_conv, "_wgrad_trusted", None)
+    assert tc_conv.wgrad_trusted() is False
+    monkeypatch.delenv("BNET_TC_WGRAD", raising=False)
+    monkeypatch.setattr(tc_conv, "_wgrad_trusted", None)
+    monkeypatch.setattr(tc_conv, "usable", lambda: True)
+    monkeypatch.setenv("BNET_CACHE_DIR", str(tmp_path))
+    monkeypatch.setattr(torch.cuda, "get_device_name", lambda *a: "Fake B200")
+    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+    monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)
+    assert tc_conv.wgrad_trusted() is False                          # the child has no GPU either: a clean "no", cached
+    files = glob.glob(str(tmp_path / "tc_wgrad_self_check_*.json"))
+    assert len(files) == 1 and json.load(open(files[0]))["ok"] is False
+    assert not glob.glob(str(tmp_path / "tc_self_check_*.json"))     # (the linear kernel's verdict is a different file)
+    assert tc_linear._isolated_self_check(timeout=0.001, check="ok = True", tag="tc_wgrad_self_check") is False   # cached verdict wins
+
+
 def test_bench_isolated_self_check_classifies_child_outcomes(monkeypatch):
     """bench.py trusts the fused layer kernels only after their self-check ran in a child process: verdicts (exit 0 / 3,
     or death by signal) are final, anything else falls back to the in-process check."""

@@ -99,7 +99,7 @@ for recipe in "$@"; do
   tc)
     TAILN=30 step tc_probe 300 python tools/tc_probe.py
     TAILN=20 step tc_linear_bench 300 python tools/tc_linear_bench.py
-    TAILN=24 step tc_conv_bench 300 python tools/tc_conv_bench.py
+    TAILN=24 step tc_conv_bench 300 python tools/tc_conv_bench.py --wgrad
     step ncu_tc 400 ncu --set full --clock-control none --import-source on -k "regex:tc_linear_kernel" -c 4 -f -o $OUT/tc_linear \
       python tools/tc_linear_bench.py --iters 1 --warmup 0 --shapes 4096x4096x4096,32x4096x25088 ;;
   kernels)

@@ -1,5 +1,6 @@
 """tcgen05 3x3 convolution (csrc/cuda/tc_gemm.cu, kConv) against cuDNN at the flagship's layer shapes: forward with
-bias + ReLU (ours: one kernel; library: cuDNN convolution + our in-place bias/ReLU pass) and the input gradient.
+bias + ReLU (ours: one kernel; library: cuDNN convolution + our in-place bias/ReLU pass), the input gradient and the
+filter gradient (--wgrad; ours: 64-pixel 4-D TMA boxes of gy and x, split over the pixels).
 CUDA-event timed; TFLOP/s against MEASURED_PEAKS.json's cuBLAS bf16 rate.
 
     python tools/tc_conv_bench.py [--batch 32] [--iters 10] [--model vgg16|resnet]
@@ -41,6 +42,7 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--model", default="vgg16")
     ap.add_argument("--shapes", default="")
+    ap.add_argument("--wgrad", action="store_true", help="also time the filter gradient (ours vs cuDNN), with the splits ours used")
     args = ap.parse_args()
     peak = 1483.0
     try:
@@ -83,8 +85,20 @@ def main():
         else:
             t_dtc = t_dlib = float("nan")
         tf = lambda us: flops / us / 1e6      # noqa: E731
+        extra = ""
+        if args.wgrad and cin % 64 == 0 and cout % 64 == 0:
+            def lib_wgrad():
+                return torch.ops.aten.convolution_backward(gy, x, w, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [False, True, False])[1]
+
+            w_tc, w_lib = tc_conv.conv3x3_wgrad(gy, x), lib_wgrad()
+            werr = ((w_tc.float() - w_lib.float()).norm() / w_lib.float().norm()).item()
+            t_wtc = timed(lambda: tc_conv.conv3x3_wgrad(gy, x), args.iters)
+            t_wlib = timed(lib_wgrad, args.iters)
+            p = tc_conv.wgrad_plan(n, hw, hw, cin, cout)
+            extra = (f" | wgrad ours {t_wtc:7.1f} us {tf(t_wtc):5.0f} TF/s, cuDNN {t_wlib:7.1f} us {tf(t_wlib):5.0f} TF/s, ratio {t_wlib / t_wtc:5.2f}, "
+                     f"err {werr:.4f} ({p['grid_x'] * p['grid_y']} tiles of 128x{p['bn']} x {p['grid_z']} pixel slices)")
         print(f" {cin:5d} {cout:5d} {hw:4d} | {t_tc:9.1f} {tf(t_tc):6.0f} {t_lib:9.1f} {tf(t_lib):6.0f} {t_lib / t_tc:6.2f} | "
-              f"{t_dtc:10.1f} {tf(t_dtc):6.0f} {t_dlib:8.1f} {tf(t_dlib):6.0f} {t_dlib / t_dtc:6.2f} | {err:.4f}")
+              f"{t_dtc:10.1f} {tf(t_dtc):6.0f} {t_dlib:8.1f} {tf(t_dlib):6.0f} {t_dlib / t_dtc:6.2f} | {err:.4f}{extra}")
     print(f"# watchdog flag {tc_linear.last_error()}")
 
 
