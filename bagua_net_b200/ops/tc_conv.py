@@ -184,6 +184,17 @@ def wgrad_trusted() -> bool:
     return _wgrad_trusted
 
 
+def prepare() -> dict:
+    """Settle every once-per-process verdict NOW: the linear / convolution kernels' self-check and the filter gradient's
+    child-process check (tens of seconds the first time on a machine, a file read afterwards).  Training engines call this
+    before their first collective, so that no rank sits in a child process while its peers already wait inside one —
+    the cross-rank barriers of the fused kernels carry a 20 s watchdog."""
+    if not torch.cuda.is_available() or torch.cuda.is_current_stream_capturing():
+        return {"usable": False, "wgrad": False}
+    u = usable()
+    return {"usable": u, "wgrad": wgrad_trusted() if u else False}
+
+
 def choose_wgrad(gy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, cudnn_fn) -> str:
     """"tc" or "cudnn" for this layer's filter gradient: like ``choose`` (results compared, both timed, winner cached per
     shape), behind ``wgrad_trusted()``."""

@@ -94,6 +94,12 @@ class BnetDDP(torch.nn.Module):
             self.buckets.append(b)
 
         dev = params[0].device
+        if dev.type == "cuda" and any(p.dim() == 4 and p.dtype == torch.bfloat16 for p in params):
+            # once-per-process kernel verdicts (a child-process self-check the first time on a machine) are settled here,
+            # before the heap's rendezvous lines the ranks up again and long before the first cross-rank kernel barrier
+            from ..ops import tc_conv
+
+            tc_conv.prepare()
         if comm is None:
             comm = SymmComm(2 * total * es + extra_heap_bytes + (1 << 20), device=dev.index, group=group)
         self.comm = comm

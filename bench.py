@@ -359,6 +359,14 @@ def main() -> int:
             args.fused_failed = True
             if rank == 0:
                 print(f"[bench] WARNING: {fused_note}", file=sys.stderr)
+    if fused:
+        # settle the tcgen05 kernels' once-per-process verdicts (the filter gradient's runs in a child process the first
+        # time on a machine) while no collective is in flight, then line the ranks up again
+        from bagua_net_b200.ops import tc_conv
+
+        note(f"tcgen05 kernels: {tc_conv.prepare()}")
+        if world > 1:
+            dist.barrier()
     model = build_model(args.model, **({"fused": True} if fused else {}))
     model = model.to(dev).to(torch.bfloat16).to(memory_format=torch.channels_last)
     model.train()
