@@ -353,6 +353,29 @@ class NetPlugin:
         self._chk("irecv", rc)
         return req if req.value else None
 
+    def irecv_group(self, comm, addrs: list, sizes: list, mhs: list, tags: list | None = None):
+        """One grouped receive (ncclNet v5+, ``maxRecvs`` > 1): ``len(addrs)`` buffers under ONE request, matched in order to
+        the sender's next isends.  Returns the request, or None when the plugin asks to try again."""
+        if self.version < 5:
+            raise ValueError("grouped receives exist from ncclNet v5 on")
+        n = len(addrs)
+        req = C.c_void_p()
+        data = (C.c_void_p * n)(*addrs)
+        tg = (C.c_int * n)(*(tags or [0] * n))
+        mh = (C.c_void_p * n)(*[(m.value if m is not None and m.value else None) for m in mhs])
+        if self.version >= 10:
+            rc = self.tab.irecv(comm, n, data, (C.c_size_t * n)(*sizes), tg, mh, None, C.byref(req))
+        else:
+            rc = self.tab.irecv(comm, n, data, (C.c_int * n)(*sizes), tg, mh, C.byref(req))
+        self._chk("irecv(group)", rc)
+        return req if req.value else None
+
+    def test_group(self, req, n: int):
+        """(done, [size of every entry]) of a grouped receive."""
+        done, sizes = C.c_int(0), (C.c_int * n)()
+        self._chk("test", self.tab.test(req, C.byref(done), sizes))
+        return bool(done.value), list(sizes)
+
     def iflush(self, comm, addr: int, size: int, mh=None):
         req = C.c_void_p()
         if self.version == 3:

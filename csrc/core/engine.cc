@@ -95,6 +95,12 @@ int Comm::iflush(void*, size_t, MemHandle*, Request** out) {
   return kOk;
 }
 
+int Comm::free_requests() const {
+  int n = 0;
+  for (const Request& r : pool) n += r.in_use.load(std::memory_order_relaxed) == 0;
+  return n;
+}
+
 Request* Comm::alloc_req(ReqKind k, void* buf, size_t size, int tag, MemHandle* mh) {
   uint64_t rid = next_req.fetch_add(1, std::memory_order_relaxed);
   for (int probe = 0; probe < kMaxRequests; probe++) {
@@ -232,6 +238,11 @@ int Engine::init() {
   gpu_of_dev_.clear();
   props_.clear();
   long long speed_override = env_int("SPEED_MBPS", 0);
+  // grouped receives (ncclNet v5+ irecv with n > 1; csrc/plugin/plugin.cc: GroupReq): 1 = what every measured run used;
+  // BNET_MAX_RECVS=8 lets NCCL aggregate the receives of grouped send/recv to one peer (not used by its all-reduce)
+  int max_recvs = (int)env_int("MAX_RECVS", 1);
+  if (max_recvs < 1) max_recvs = 1;
+  if (max_recvs > kMaxGroupRecvs) max_recvs = kMaxGroupRecvs;
   const bool gpu_devs = env_int("GPU_DEVICES", cuda::fake() ? 0 : 1) != 0 && cfg.nvl && cuda_ok_ && !nics.empty();
   if (gpu_devs) {
     for (int g = 0; g < cuda::device_count(); g++) {
@@ -253,7 +264,7 @@ int Engine::init() {
       p.port = 0;
       p.latency_us = 0;
       p.max_comms = 65536;
-      p.max_recvs = 1;
+      p.max_recvs = max_recvs;
       devs_.push_back(nif);
       gpu_of_dev_.push_back(g);
       props_.push_back(p);
@@ -272,7 +283,7 @@ int Engine::init() {
     p.port = 0;
     p.latency_us = 0;
     p.max_comms = 65536;
-    p.max_recvs = 1;
+    p.max_recvs = max_recvs;
     devs_.push_back(nics[i]);
     gpu_of_dev_.push_back(-1);
     props_.push_back(p);

@@ -206,9 +206,77 @@ ncclResult_t do_iflush(void* rcomm, void* data, size_t size, void* mh, void** re
   return ncclSuccess;
 }
 
+// A grouped receive (ncclNet v5+: irecv with n > 1 — NCCL aggregates the receives of grouped send/recv to one peer and
+// gives every entry of a group the SAME tag, the sender's rank) is n ordinary receives matched, in posting order, to the
+// next n isends of the connection: exactly what the transports' FIFO matching delivers.  The parent lives on the heap for
+// the lifetime of the group; `magic` sits where a Request keeps its in_use word (0 / 1), which is how test() tells them apart.
+struct GroupReq {
+  uint32_t magic;
+  int n;
+  Request* sub[kMaxGroupRecvs];
+  int sizes[kMaxGroupRecvs];
+  bool fin[kMaxGroupRecvs];
+  int err;
+};
+constexpr uint32_t kGroupMagic = 0x47525051u;   // "GRPQ"
+static_assert(offsetof(Request, in_use) == 0, "GroupReq::magic must overlay Request::in_use");
+
+ncclResult_t do_irecv_group(void* rcomm, int n, void** data, const size_t* sizes, int* tags, void** mhs, void** request) {
+  CallScope cs_("irecv(group)");
+  if (!rcomm || !request || !data || !sizes || n < 1) return ncclInvalidArgument;
+  if (n > kMaxGroupRecvs) return ncclInvalidUsage;
+  *request = nullptr;
+  Comm* c = static_cast<Comm*>(rcomm);
+  if (c->free_requests() < n) return ncclSuccess;            // all of the group or nothing: NCCL retries
+  GroupReq* g = new GroupReq();
+  g->magic = kGroupMagic;
+  g->n = n;
+  for (int i = 0; i < n; i++) {
+    Request* r = nullptr;
+    int st = c->irecv(data[i], sizes[i], tags ? tags[i] : 0, mhs ? static_cast<MemHandle*>(mhs[i]) : nullptr, &r);
+    if (st || !r) {
+      // part of the group is posted and cannot be taken back: the connection is unusable from here on
+      BNET_WARN("irecv group: entry %d of %d could not be posted (%s)", i, n, st ? status_str(st) : "request pool exhausted");
+      c->broken.store(st ? st : kErrInternal, std::memory_order_release);
+      delete g;
+      return st ? to_nccl(st) : ncclInternalError;
+    }
+    g->sub[i] = r;
+  }
+  *request = g;
+  return ncclSuccess;
+}
+
+ncclResult_t test_group(GroupReq* g, int* done, int* sizes) {
+  *done = 0;
+  bool all = true;
+  for (int i = 0; i < g->n; i++) {
+    if (g->fin[i]) continue;
+    int d = 0;
+    size_t sz = 0;
+    int st = g->sub[i]->comm->test(g->sub[i], &d, &sz);
+    if (st) {
+      BNET_WARN("test: entry %d of a grouped receive failed: %s", i, status_str(st));
+      g->fin[i] = true;                  // (a failed request has been released by the transport)
+      g->err = st;
+      continue;
+    }
+    if (d) { g->fin[i] = true; g->sizes[i] = (int)sz; } else all = false;
+  }
+  if (!all) return ncclSuccess;
+  const int err = g->err;
+  if (!err) {
+    *done = 1;
+    if (sizes) for (int i = 0; i < g->n; i++) sizes[i] = g->sizes[i];
+  }
+  delete g;
+  return err ? to_nccl(err) : ncclSuccess;
+}
+
 ncclResult_t do_test(void* request, int* done, int* size) {
   CallScope cs_("test");
   if (!request || !done) return ncclInvalidArgument;
+  if (*static_cast<uint32_t*>(request) == kGroupMagic) return test_group(static_cast<GroupReq*>(request), done, size);
   Request* r = static_cast<Request*>(request);
   size_t sz = 0;
   int st = r->comm->test(r, done, &sz);
@@ -346,20 +414,32 @@ ncclResult_t v10_isend(void* c, void* d, size_t size, int tag, void* mh, void* p
   return r;
 }
 ncclResult_t v6_irecv(void* c, int n, void** data, int* sizes, int* tags, void** mhs, void** req) {
-  if (n != 1) return ncclInvalidUsage;   // maxRecvs = 1
-  return do_irecv(c, data[0], (size_t)sizes[0], tags ? tags[0] : 0, mhs ? mhs[0] : nullptr, req);
+  if (n == 1) return do_irecv(c, data[0], (size_t)sizes[0], tags ? tags[0] : 0, mhs ? mhs[0] : nullptr, req);
+  if (n < 1 || n > kMaxGroupRecvs || !sizes) return ncclInvalidUsage;
+  size_t sz[kMaxGroupRecvs];
+  for (int i = 0; i < n; i++) sz[i] = (size_t)sizes[i];
+  return do_irecv_group(c, n, data, sz, tags, mhs, req);
 }
 ncclResult_t v9_irecv(void* c, int n, void** data, size_t* sizes, int* tags, void** mhs, void** req) {
-  if (n != 1) return ncclInvalidUsage;
-  return do_irecv(c, data[0], sizes[0], tags ? tags[0] : 0, mhs ? mhs[0] : nullptr, req);
+  if (n == 1) return do_irecv(c, data[0], sizes[0], tags ? tags[0] : 0, mhs ? mhs[0] : nullptr, req);
+  return do_irecv_group(c, n, data, sizes, tags, mhs, req);
 }
 ncclResult_t v10_irecv(void* c, int n, void** data, size_t* sizes, int* tags, void** mhs, void** phs, void** req) {
   ncclResult_t r = v9_irecv(c, n, data, sizes, tags, mhs, req);
-  if (r == ncclSuccess && *req && phs && phs[0]) profiler_start(static_cast<Request*>(*req), phs[0]);
+  if (r == ncclSuccess && *req && phs) {
+    if (n == 1) {
+      if (phs[0]) profiler_start(static_cast<Request*>(*req), phs[0]);
+    } else {
+      GroupReq* g = static_cast<GroupReq*>(*req);
+      for (int i = 0; i < n; i++)
+        if (phs[i]) profiler_start(g->sub[i], phs[i]);
+    }
+  }
   return r;
 }
+// one flush covers a group: the sender's kernel has fenced every entry before its completion word became visible
 ncclResult_t v6_iflush(void* c, int n, void** data, int* sizes, void** mhs, void** req) {
-  if (n != 1) return ncclInvalidUsage;
+  if (n < 1 || n > kMaxGroupRecvs) return ncclInvalidUsage;
   return do_iflush(c, data[0], (size_t)sizes[0], mhs ? mhs[0] : nullptr, req);
 }
 ncclResult_t v7_get_device_mr(void*, void*, void**) { return ncclInternalError; }

@@ -22,6 +22,7 @@
 namespace bnet {
 
 constexpr int kMaxRequests = 64;      // per comm; >= NCCL_NET_MAX_REQUESTS (32)
+constexpr int kMaxGroupRecvs = 8;     // receives one grouped irecv may carry (NCCL_NET_MAX_RECVS / NCCL_PROXY_MAX_SUBS)
 constexpr uint32_t kHandleMagic = 0x424E4554u;  // "BNET"
 constexpr uint16_t kWireVersion = 1;
 
@@ -137,6 +138,7 @@ struct Comm {
 
   Request* alloc_req(ReqKind kind, void* buf, size_t size, int tag, MemHandle* mh);
   void free_req(Request* r);
+  int free_requests() const;          // slots of the pool that are free right now (a lower bound for the caller that owns the comm)
 };
 
 struct DeviceProps {

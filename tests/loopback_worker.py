@@ -106,6 +106,7 @@ def main() -> int:
     ap.add_argument("--die-after", type=int, default=-1, help="sender exits abruptly after N messages")
     ap.add_argument("--expect-error", action="store_true")
     ap.add_argument("--bw", action="store_true", help="print a bandwidth line for the largest size")
+    ap.add_argument("--group", type=int, default=1, help="receiver posts its receives in groups of this many (one request each)")
     a = ap.parse_args()
 
     sizes = [int(s) for s in a.sizes.split(",") if s != ""]
@@ -157,19 +158,42 @@ def main() -> int:
                     bufs.append(b)
                     mhs.append(mh)
                 t0 = time.perf_counter()
-                for j in range(a.inflight):
-                    while True:
-                        r = (p.irecv(comm, bufs[j].addr, size + extra, mhs[j]) if a.role == 0
-                             else p.isend(comm, bufs[j].addr, size, mhs[j]))
-                        if r is not None:
-                            break
-                    reqs.append(r)
-                    nmsg += 1
-                    if a.role == 1 and a.die_after >= 0 and nmsg >= a.die_after:
-                        os._exit(17)        # simulate a crashed peer mid-transfer
-                for j in range(a.inflight):
-                    got = p.wait(reqs[j], timeout=60)
-                    assert got == size, f"size mismatch: {got} != {size}"
+                if a.role == 0 and a.group > 1:
+                    # grouped receives: `group` buffers under one request, the sender's isends fill them in order
+                    groups = []
+                    for j0 in range(0, a.inflight, a.group):
+                        idx = list(range(j0, min(j0 + a.group, a.inflight)))
+                        while True:
+                            r = p.irecv_group(comm, [bufs[j].addr for j in idx], [size + extra] * len(idx), [mhs[j] for j in idx],
+                                              tags=[5] * len(idx))
+                            if r is not None:
+                                break
+                        groups.append((r, len(idx)))
+                        nmsg += len(idx)
+                    for r, n in groups:
+                        t1 = time.time()
+                        while True:
+                            done, got = p.test_group(r, n)
+                            if done:
+                                break
+                            if time.time() - t1 > 60:
+                                raise TimeoutError("grouped receive did not complete")
+                        assert got == [size] * n, f"sizes of a grouped receive: {got} != {size} x {n}"
+                    result["grouped"] = result.get("grouped", 0) + len(groups)
+                else:
+                    for j in range(a.inflight):
+                        while True:
+                            r = (p.irecv(comm, bufs[j].addr, size + extra, mhs[j]) if a.role == 0
+                                 else p.isend(comm, bufs[j].addr, size, mhs[j], tag=5 if a.group > 1 else 0))
+                            if r is not None:
+                                break
+                        reqs.append(r)
+                        nmsg += 1
+                        if a.role == 1 and a.die_after >= 0 and nmsg >= a.die_after:
+                            os._exit(17)        # simulate a crashed peer mid-transfer
+                    for j in range(a.inflight):
+                        got = p.wait(reqs[j], timeout=60)
+                        assert got == size, f"size mismatch: {got} != {size}"
                 dt = time.perf_counter() - t0
                 if a.role == 0:
                     for j in range(a.inflight):

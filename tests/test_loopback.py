@@ -153,6 +153,36 @@ def test_nvl_direct_path_with_emulated_device_memory():
     assert outs[0][1]["messages"] == 96
 
 
+@pytest.mark.parametrize("name,env,extra,transport", [
+    ("tcp-basic", {"BNET_NVL": "0"}, [], "tcp-threads"),
+    ("tcp-async", {"BNET_NVL": "0", "BAGUA_NET_IMPLEMENT": "TOKIO"}, [], "tcp-async"),
+    ("nvl-host", {"BNET_NVL": "1"}, [], "nvl"),
+    ("nvl-device", {"BNET_NVL": "1", "BNET_FAKE_CUDA": "1"}, ["--mem", "fakecuda"], "nvl")])
+@pytest.mark.parametrize("abi", [6, 8])
+def test_grouped_receives(name, env, extra, transport, abi):
+    """ncclNet v5+ `irecv(n > 1)` (`maxRecvs`, BNET_MAX_RECVS): n buffers under one request, filled in order by the sender's
+    next n isends (NCCL gives every entry of a group the same tag), `test` reports n sizes; a last, shorter group included."""
+    outs = _check(run_pair(["--abi", str(abi), "--sizes", "0,1,4096,1048577", "--inflight", "7", "--rounds", "2", "--group", "3"] + extra,
+                           env=dict(env, BNET_MAX_RECVS="8")), transport)
+    assert outs[0][1]["grouped"] == 3 * 4 * 2 and outs[0][1]["messages"] == 7 * 4 * 2, outs[0][1]
+
+
+def test_max_recvs_property_follows_the_knob():
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("from bagua_net_b200.utils.abi import NetPlugin\n"
+            "p = NetPlugin(8); p.init(); print('maxRecvs', p.get_properties(0)['maxRecvs'])")
+    for knob, want in ((None, 1), ("8", 8), ("99", 8)):
+        env = {k: v for k, v in os.environ.items() if k != "BNET_MAX_RECVS"}
+        env["PYTHONPATH"] = root + os.pathsep + env.get("PYTHONPATH", "")
+        if knob:
+            env["BNET_MAX_RECVS"] = knob
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0 and f"maxRecvs {want}" in out.stdout, (knob, out.stdout, out.stderr[-1500:])
+
+
 def test_nvl_pinned_host_source_goes_direct_when_enabled():
     # NCCL keeps its LL send buffers in pinned host memory; with BNET_HOST_SRC_DIRECT=1 the copy kernel reads them
     # through their device alias and stores into the peer's device buffer (emulated here), no ring, no staging
