@@ -152,13 +152,13 @@ SAN_FLAGS_asan := -fsanitize=address -fsanitize=undefined -fno-omit-frame-pointe
 define SAN_RULES
 $(BUILD)/$(1)/%.o: csrc/%.cc
 	@mkdir -p $$(dir $$@)
-	$(SAN_CXX) $(CXXFLAGS) -O1 $$(SAN_FLAGS_$(1)) -MMD -MP -c $$< -o $$@
-$(BUILD)/$(1)/libnccl-net.so: $(patsubst csrc/%.cc,$(BUILD)/$(1)/%.o,$(HOST_SRCS) csrc/plugin/plugin.cc) $(CU_OBJS)
+	$(SAN_CXX) $(CXXFLAGS) -O1 -DBNET_EXPORT_V9_V10 $$(SAN_FLAGS_$(1)) -MMD -MP -c $$< -o $$@
+$(BUILD)/$(1)/libnccl-net.so: $(patsubst csrc/%.cc,$(BUILD)/$(1)/%.o,$(HOST_SRCS) csrc/plugin/plugin.cc csrc/plugin/collnet.cc) $(CU_OBJS)
 	$(NVCC) -ccbin $(SAN_CXX) $(ARCH) $(LDFLAGS) $$(addprefix -Xcompiler ,$$(SAN_FLAGS_$(1))) -o $$@ $$^
 $(BUILD)/$(1)/tests/%: csrc/tests/%.cc $(BUILD)/$(1)/libnccl-net.so
 	@mkdir -p $$(dir $$@)
 	$(SAN_CXX) $(CXXFLAGS) -O1 $$(SAN_FLAGS_$(1)) -fvisibility=default $$< -o $$@ -ldl -pthread
--include $(patsubst csrc/%.cc,$(BUILD)/$(1)/%.d,$(HOST_SRCS) csrc/plugin/plugin.cc)
+-include $(patsubst csrc/%.cc,$(BUILD)/$(1)/%.d,$(HOST_SRCS) csrc/plugin/plugin.cc csrc/plugin/collnet.cc)
 $(1): $(BUILD)/$(1)/tests/unit_tests $(BUILD)/$(1)/tests/loopback_test
 	$(BUILD)/$(1)/tests/unit_tests $(BUILD)/$(1)/libnccl-net.so
 	$(BUILD)/$(1)/tests/loopback_test $(BUILD)/$(1)/libnccl-net.so

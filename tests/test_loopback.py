@@ -44,7 +44,8 @@ def test_abi_v10_table():
     lib = ctypes.CDLL(bagua_net_b200.lib_path())
     for v in (3, 4, 5, 6, 7, 8):
         assert hasattr(lib, f"ncclNetPlugin_v{v}")
-    assert not hasattr(lib, "ncclNetPlugin_v10")      # default build stays on well-known layouts
+    if "BNET_LIB_DIR" not in os.environ:              # (the sanitizer builds put every table into one library)
+        assert not hasattr(lib, "ncclNetPlugin_v10")  # default build stays on well-known layouts
 
 
 def test_v10_profiler_callback_brackets_every_request():
