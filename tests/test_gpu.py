@@ -238,6 +238,11 @@ def test_transport_mesh_twoshot_allreduce_2gpu():
 
 
 # ------------------------------------------------------------------ written after the last hardware session of round 2: LAST in the file
+def test_executor_fp8_decompression_ops():
+    """fp8 -> fp32 overwrite ops (OP_CAST_E4M3_TO_F32 / OP_CAST_E5M2_TO_F32) of the compressed all-reduce's all-gather half."""
+    _run_worker("executor_decompress", 1, timeout=120)
+
+
 def test_tcgen05_conv3x3_filter_gradient_matches_cudnn():
     """tcgen05 weight gradient (both operands 64-pixel 4-D TMA boxes, MN-major; split over the pixels with the fix-up)."""
     _run_worker("tc_conv_wgrad", 1, timeout=300)
