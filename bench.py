@@ -295,6 +295,7 @@ def main() -> int:
     ap.add_argument("--no-prefetch", action="store_true", help="e2e: per-step API instead of the prefetching loop")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel of the step individually (no CUDA graph)")
     ap.add_argument("--no-fused", action="store_true", help="eager bias/ReLU/pool instead of the fused sm_100a conv blocks")
+    ap.add_argument("--force-fused", action="store_true", help="resnet: skip the fused-vs-eager timing and use the fused blocks")
     ap.add_argument("--child-json", default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -367,6 +368,40 @@ def main() -> int:
         note(f"tcgen05 kernels: {tc_conv.prepare()}")
         if world > 1:
             dist.barrier()
+    if fused and args.model.startswith("resnet") and not args.force_fused:
+        # The fused BatchNorm blocks are numerically checked but their speed against cuDNN's own BatchNorm kernels was never
+        # measured in a whole model: time forward + backward of both variants on this GPU (no collective involved) and train
+        # the faster one; every rank takes the same decision (slowest rank's times).
+        def fwd_bwd_ms(flag):
+            m = build_model(args.model, **({"fused": True} if flag else {})).to(dev).to(torch.bfloat16).to(memory_format=torch.channels_last)
+            m.train()
+            xs = torch.randn(args.batch, 3, args.image, args.image, device=dev, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            ys = torch.randint(0, 1000, (args.batch,), device=dev)
+            for _ in range(3):
+                torch.nn.functional.cross_entropy(m(xs).float(), ys).backward()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                torch.nn.functional.cross_entropy(m(xs).float(), ys).backward()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / 5
+
+        try:
+            t = torch.tensor([fwd_bwd_ms(True), fwd_bwd_ms(False)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_fused, t_eager = float(t[0].item()), float(t[1].item())
+            note(f"{args.model} forward+backward: fused blocks {t_fused:.2f} ms, eager layers {t_eager:.2f} ms")
+            if t_eager < t_fused:
+                fused = False
+                fused_note = f"eager layers are faster on this GPU ({t_eager:.2f} ms vs {t_fused:.2f} ms forward+backward): eager layers used"
+            else:
+                fused_note = f"fused blocks {t_fused:.2f} ms vs eager layers {t_eager:.2f} ms forward+backward"
+        except Exception as ex:   # noqa: BLE001 - the comparison is optional
+            note(f"fused-vs-eager timing failed: {ex!r}")
+        torch.cuda.empty_cache()
     model = build_model(args.model, **({"fused": True} if fused else {}))
     model = model.to(dev).to(torch.bfloat16).to(memory_format=torch.channels_last)
     model.train()
