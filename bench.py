@@ -636,21 +636,24 @@ def main() -> int:
     extra = {}
     if args.comm == "bnet" and world > 1 and not args.no_extra:
         try:
-            bw = {}
-            for nbytes in (1 << 20, 16 << 20, 128 << 20):
+            bw, lat = {}, {}
+            for nbytes in (1 << 10, 64 << 10, 1 << 20, 16 << 20, 128 << 20):     # BASELINE config #5 (1 KiB .. 128 MiB here)
                 t = comm.alloc(nbytes // 2, torch.bfloat16)
                 t.fill_(1.0)
                 for _ in range(5):
                     comm.all_reduce(t, "sum")
-                ms, _ = timed(lambda: comm.all_reduce(t, "sum"), 20)
-                algbw = nbytes / (ms / 20 / 1e3) / 1e9
-                bw[str(nbytes)] = round(algbw * 2 * (world - 1) / world, 1)
+                iters = 50 if nbytes <= (1 << 20) else 20
+                ms, _ = timed(lambda: comm.all_reduce(t, "sum"), iters)
+                algbw = nbytes / (ms / iters / 1e3) / 1e9
+                bw[str(nbytes)] = round(algbw * 2 * (world - 1) / world, 2 if nbytes < (1 << 20) else 1)
+                lat[str(nbytes)] = round(ms / iters * 1e3, 1)
             extra["allreduce_busbw_gbs_bf16"] = bw
+            extra["allreduce_time_us"] = lat
             # bytes per direction per GPU: in-switch path S(1+1/n), direct two-shot S(n-1)/n
             per_dir = (1 + 1 / world) if path == "nvls" else (world - 1) / world
             extra["allreduce_algo"] = path
             extra["allreduce_roofline_frac_of_770GBs"] = {k: round(v / (2 * (world - 1) / world) * per_dir / 770.0, 3)
-                                                          for k, v in bw.items()}
+                                                          for k, v in bw.items() if int(k) >= (1 << 20)}
         except Exception as ex:   # the headline number must survive a failing side measurement
             extra["allreduce_error"] = str(ex)[:200]
     if args.comm != "bnet" and world > 1 and not args.no_extra:

@@ -4,6 +4,8 @@ SENDING GPU's kernel while it moves the data over NVLink, so no reduce kernel an
   ring       2(n-1) steps, every hop a fused isend (`isend_op(OP_RED_ADD_*)`): bandwidth-optimal, bit-reproducible
   compressed the same ring with bf16 / fp8 on the wire: the quantisation rides the isend, NVLink carries 2-4x fewer bytes
   one-shot   a full mesh, ONE step: every peer's kernel accumulates into every output — latency-optimal up to a few MiB
+  two-shot   the same mesh, TWO steps for any world size: reduce-scatter into the slice owners (fused isends), all-gather by
+             copy; 2(n-1)/n x size on the wire, in place — the shape an NVSwitch wants, and what the CollNet table gives NCCL
 
     torchrun --standalone --local-addr 127.0.0.1 --nproc-per-node 4 examples/transport_collectives.py
 """
@@ -48,10 +50,16 @@ def main():
     mesh.all_reduce(x, y)
     assert float(y[0]) == world * (world + 1) / 2
     t_mesh = timed(lambda: mesh.all_reduce(x, y), iters=20)
+    h = mesh.buffer(n, torch.float32)                                     # one registered buffer: in place
+    h.fill_(rank + 1)
+    mesh.all_reduce(h, h, algo="two-shot")
+    assert float(h[0]) == world * (world + 1) / 2 and float(h[-1]) == world * (world + 1) / 2
+    t_two = timed(lambda: mesh.all_reduce(h, h, algo="two-shot"))
     if rank == 0:
         bus = 2 * (world - 1) / world
         print(f"world {world} over '{ring.transport}': ring 64 MiB fp32 {n * 4 * bus / t_ring / 1e9:.0f} GB/s busbw | "
-              f"e4m3 on the wire {n * 4 * bus / t_comp / 1e9:.0f} GB/s (of fp32 payload) | one-shot 512 KiB bf16->fp32 {t_mesh * 1e6:.0f} us")
+              f"e4m3 on the wire {n * 4 * bus / t_comp / 1e9:.0f} GB/s (of fp32 payload) | one-shot 512 KiB bf16->fp32 {t_mesh * 1e6:.0f} us | "
+              f"two-shot 64 MiB fp32 in place {n * 4 * bus / t_two / 1e9:.0f} GB/s busbw")
     ring.close()
     mesh.close()
 
