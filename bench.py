@@ -20,7 +20,9 @@ At N > 1 the default run also measures the two DDP arms in child processes (boun
 under extra.nccl_plugin / extra.nccl_stock next to the headline: img/s, the all-reduce bus bandwidth 8 B - 128 MiB
 over that path, and a cross-rank parameter checksum.  --no-arms skips them.  The run then repeats the arms on ResNet-50
 (BASELINE config #4; extra.resnet50_bnet at any N, extra.resnet50_nccl_plugin / _nccl_stock at N > 1) as short child
-jobs that only start while the run is younger than --resnet-deadline; --no-resnet skips them.
+jobs that only start while the run is younger than --resnet-deadline; --no-resnet skips them.  At N > 1 one more bounded
+child (bench/transport_coll.py -> extra.transport_allreduce) verifies and times the all-reduces that ride the plugin's own
+connections (ring, two-shot mesh, one-shot mesh; reduction fused into the isends); --no-transport-coll skips it.
 
 Prints ONE JSON line on rank 0 (contract in the task statement).
 """
@@ -210,7 +212,8 @@ def isolated_self_check(name: str, local: int, timeout: float = 240.0):
 ARM_SIZES = (8, 1 << 10, 64 << 10, 1 << 20, 16 << 20, 128 << 20)   # all-reduce message sizes of the DDP arms (bytes)
 
 
-def run_child_arm(comm_name: str, args, rank: int, world: int, port_offset: int, timeout: float, model: str | None = None):
+def run_child_arm(comm_name: str, args, rank: int, world: int, port_offset: int, timeout: float, model: str | None = None,
+                  script: list | None = None):
     """One DDP arm (`--comm nccl-plugin` / `--comm nccl`) as a child process per rank: own CUDA context, own NCCL
     (with or without the plugin on LD_LIBRARY_PATH), own rendezvous port.  Every rank of the parent job calls this at
     the same time; rank 0 returns the child's JSON (or a status dict), the others None.  A child that outlives
@@ -235,13 +238,16 @@ def run_child_arm(comm_name: str, args, rank: int, world: int, port_offset: int,
     out_path = os.path.join(log_dir, f"bnet_bench_arm_{model}_{comm_name}_{os.getppid()}_{env['MASTER_PORT']}.json")
     if rank == 0 and os.path.exists(out_path):
         os.unlink(out_path)
-    cmd = [sys.executable, os.path.abspath(__file__), "--comm", comm_name, "--gpus", str(world), "--steps", str(min(args.steps, 10)),
-           "--warmup", "3", "--model", model, "--batch", str(args.batch), "--image", str(args.image), "--no-e2e",
-           "--no-arms", "--child-json", out_path]
-    if args.no_fused:
-        cmd.append("--no-fused")
-    if args.no_graph:
-        cmd.append("--no-graph")
+    if script:                                   # another measurement script with the same contract: --json <file>, rank 0 writes it
+        cmd = [sys.executable] + list(script) + ["--json", out_path]
+    else:
+        cmd = [sys.executable, os.path.abspath(__file__), "--comm", comm_name, "--gpus", str(world), "--steps", str(min(args.steps, 10)),
+               "--warmup", "3", "--model", model, "--batch", str(args.batch), "--image", str(args.image), "--no-e2e",
+               "--no-arms", "--child-json", out_path]
+        if args.no_fused:
+            cmd.append("--no-fused")
+        if args.no_graph:
+            cmd.append("--no-graph")
     log_path = out_path.replace(".json", f".rank{rank}.log")
     t0 = time.time()
     status = "ok"
@@ -289,8 +295,9 @@ def main() -> int:
     ap.add_argument("--no-arms", action="store_true", help="N > 1: skip the NCCL-over-plugin / stock-NCCL DDP arms")
     ap.add_argument("--arm-timeout", type=float, default=150.0, help="seconds one DDP arm (child processes) may take")
     ap.add_argument("--no-resnet", action="store_true", help="skip the ResNet-50 side arms (BASELINE config #4)")
-    ap.add_argument("--resnet-timeout", type=float, default=100.0, help="seconds one ResNet-50 arm may take")
-    ap.add_argument("--resnet-deadline", type=float, default=170.0,
+    ap.add_argument("--no-transport-coll", action="store_true", help="N > 1: skip the ring / two-shot all-reduces over the plugin's connections")
+    ap.add_argument("--resnet-timeout", type=float, default=90.0, help="seconds one ResNet-50 arm may take")
+    ap.add_argument("--resnet-deadline", type=float, default=230.0,
                     help="no ResNet-50 arm starts once the run is this many seconds old")
     ap.add_argument("--no-prefetch", action="store_true", help="e2e: per-step API instead of the prefetching loop")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel of the step individually (no CUDA graph)")
@@ -699,13 +706,30 @@ def main() -> int:
             if rank == 0:
                 arms[key] = res
 
+    # ---- the collectives that ride the transport (ring / two-shot / one-shot over the plugin's own connections, reduction
+    #      fused into the isends; bench/transport_coll.py) as a bounded child job: verified exact, host-timed, max over ranks
+    if (args.comm == "bnet" and world > 1 and not args.no_arms and not args.no_transport_coll and not os.environ.get("BNET_BENCH_CHILD")):
+        sync_all()
+        go = torch.tensor([1 if time.time() - _T0 < args.resnet_deadline else 0], device=dev, dtype=torch.int32)
+        dist.broadcast(go, 0)
+        if int(go.item()):
+            note("transport collectives: child processes (timeout 75 s)")
+            res = run_child_arm("transport", args, rank, world, 150, 75.0, model="coll",
+                                script=[os.path.join(ROOT, "bench", "transport_coll.py")])
+            note(f"transport collectives: {res.get('status') if res else None}")
+            dist.barrier()
+            if rank == 0 and res is not None:
+                extra["transport_allreduce"] = {k: v for k, v in res.items() if k not in ("note",)}
+
     # ---- BASELINE config #4: the same three arms on ResNet-50 (child processes, short, under an overall deadline) ----
     # The headline stays VGG16 (the model the reference quotes its speed-up on); the reference's README benchmarks
     # ResNet-50 the same way (reference README.md:52-84), so the run reports it next to the headline while the GPUs are here.
     if (args.comm == "bnet" and args.model == "vgg16" and not args.no_arms and not args.no_resnet
             and not os.environ.get("BNET_BENCH_CHILD")):
         sync_all()
-        second = [("resnet50_bnet", "bnet")] + ([("resnet50_nccl_plugin", "nccl-plugin"), ("resnet50_nccl_stock", "nccl")] if world > 1 else [])
+        # (order = what is kept if the deadline cuts the list short: config #4 itself first, then our engine, then the comparator)
+        second = ([("resnet50_nccl_plugin", "nccl-plugin")] if world > 1 else []) + [("resnet50_bnet", "bnet")] + \
+                 ([("resnet50_nccl_stock", "nccl")] if world > 1 else [])
         for i, (key, comm_name) in enumerate(second):
             # every rank takes rank 0's decision: an arm starts only while the whole run is younger than the deadline
             go = torch.tensor([1 if time.time() - _T0 < args.resnet_deadline else 0], device=dev, dtype=torch.int32)
