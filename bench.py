@@ -264,6 +264,8 @@ def run_child_arm(comm_name: str, args, rank: int, world: int, port_offset: int,
     if rank != 0:
         return None
     res = {"status": status, "wall_s": round(time.time() - t0, 1)}
+    if script:
+        res["log_path"] = log_path
     try:
         with open(out_path) as f:
             res.update(json.load(f))
@@ -719,7 +721,36 @@ def main() -> int:
             note(f"transport collectives: {res.get('status') if res else None}")
             dist.barrier()
             if rank == 0 and res is not None:
-                extra["transport_allreduce"] = {k: v for k, v in res.items() if k not in ("note",)}
+                extra["transport_allreduce"] = {k: v for k, v in res.items() if k not in ("note", "log_path")}
+
+    # ---- does NCCL accept the plugin's CollNet table?  (bench/nccl_collnet_probe.py: plugin + BNET_COLLNET=1 NCCL_COLLNET_ENABLE=1,
+    #      one virtual host per rank; fp32 all-reduce sweep, exactness, the plugin's own count of all-reduces it executed)
+    if (args.comm == "bnet" and world > 1 and not args.no_arms and not args.no_transport_coll and not os.environ.get("BNET_BENCH_CHILD")):
+        sync_all()
+        go = torch.tensor([1 if time.time() - _T0 < args.resnet_deadline else 0], device=dev, dtype=torch.int32)
+        dist.broadcast(go, 0)
+        if int(go.item()):
+            note("NCCL CollNet probe: child processes (timeout 75 s)")
+            res = run_child_arm("collnet", args, rank, world, 163, 75.0, model="probe",
+                                script=[os.path.join(ROOT, "bench", "nccl_collnet_probe.py")])
+            note(f"NCCL CollNet probe: {res.get('status') if res else None}")
+            dist.barrier()
+            if rank == 0 and res is not None:
+                try:      # what NCCL itself said about CollNet (rank 0's INFO log of the child)
+                    logp = [p_ for p_ in (res.get("log_path"),) if p_]
+                    lines = []
+                    for lp in logp:
+                        with open(lp, errors="replace") as f:
+                            for ln in f:
+                                if "ollnet" in ln.lower() or "coll net" in ln.lower():
+                                    ln = ln.strip().split("NCCL INFO ")[-1][:160]
+                                    if ln not in lines:
+                                        lines.append(ln)
+                    res["nccl_log_collnet_lines"] = lines[:8]
+                except Exception:   # noqa: BLE001
+                    pass
+                res.pop("log_path", None)
+                extra["nccl_collnet"] = res
 
     # ---- BASELINE config #4: the same three arms on ResNet-50 (child processes, short, under an overall deadline) ----
     # The headline stays VGG16 (the model the reference quotes its speed-up on); the reference's README benchmarks

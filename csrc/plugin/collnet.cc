@@ -22,6 +22,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <deque>
 #include <vector>
 
@@ -67,6 +68,8 @@ struct CollComm {
   int inflight = 8;
   int timeout_ms = 0;
 };
+
+std::atomic<uint64_t> g_allreduces_done{0};     // all-reduces this process completed through the table (bnet_collnet_allreduces)
 
 bool collnet_enabled() {
   static const bool on = env_int("COLLNET", 0) != 0;
@@ -284,6 +287,7 @@ ncclResult_t coll_test(void* request, int* done, int* size) {
       tmesh_op_free(h->op);
       h->op = nullptr;
       h->state = st > 0 ? 2 : -1;
+      if (st > 0) g_allreduces_done.fetch_add(1, std::memory_order_relaxed);
       c->queue.pop_front();        // (the request object lives until its owner has tested it)
       advance(c);
     }
@@ -325,6 +329,9 @@ ncclResult_t coll_make_vdevice(int*, ncclNetVDeviceProps_v9_t*) { return ncclInv
 }  // namespace
 
 extern "C" {
+// evidence for "did NCCL really run its all-reduces through the table": completed iallreduce calls of this process
+BNET_EXPORT unsigned long long bnet_collnet_allreduces(void) { return g_allreduces_done.load(std::memory_order_relaxed); }
+
 BNET_EXPORT ncclCollNet_v4_t ncclCollNetPlugin_v4 = {
     kCollName, coll_init, coll_devices, coll_props<ncclNetProperties_v4_t, plugin::v4_props>, coll_listen_v4, coll_connect_v4,
     coll_reduce_support, coll_regmr_int, coll_deregmr, coll_iallreduce_int, coll_iflush, coll_test, coll_close, coll_close_listen};

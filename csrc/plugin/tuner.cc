@@ -29,7 +29,9 @@ enum { PROTO_LL = 0, PROTO_LL128 = 1, PROTO_SIMPLE = 2 };
 struct TunerCtx {
   bool active;
   size_t ll_max;
+  bool prefer_collnet;     // BNET_COLLNET=1 (the CollNet table is on): make NCCL take its CollNet algorithms wherever it offers them
 };
+enum { ALGO_COLLNET_DIRECT = 2, ALGO_COLLNET_CHAIN = 3 };   // NCCL_ALGO_* (tree 0, ring 1, collnet direct 2, collnet chain 3, nvls 4, ...)
 
 ncclResult_t tuner_init(size_t nRanks, size_t nNodes, ncclDebugLogger_t logFunction, void** context) {
   (void)nRanks; (void)nNodes;
@@ -45,6 +47,7 @@ ncclResult_t tuner_init(size_t nRanks, size_t nNodes, ncclDebugLogger_t logFunct
   Engine::get().init();
   c->active = env_int("TUNER", 1) != 0 && cfg.nvl && cfg.gdr && ours && Engine::get().cuda_ok();
   c->ll_max = (size_t)env_int("TUNER_LL_MAX", 8192);
+  c->prefer_collnet = env_int("TUNER_PREFER_COLLNET", env_int("COLLNET", 0)) != 0;
   if (c->active) {
     // the protocol choice is ours now: lift the blanket "Simple only" default the net plugin's init supplied (if it was us)
     const char* p = getenv("NCCL_PROTO");
@@ -68,6 +71,13 @@ ncclResult_t tuner_coll_info(void* context, size_t nBytes, float** collCostTable
       if (row[PROTO_SIMPLE] != kIgnore) row[PROTO_LL] = kIgnore;
     }
   }
+  // With the CollNet table switched on the user wants the offload: where NCCL offers a CollNet algorithm for this
+  // collective (entry not "ignore": the table supports the type / op and the topology allows it), it wins.
+  if (c->prefer_collnet && numAlgo > ALGO_COLLNET_CHAIN)
+    for (int a : {ALGO_COLLNET_DIRECT, ALGO_COLLNET_CHAIN}) {
+      float* row = table + (size_t)a * numProto;
+      if (row[PROTO_SIMPLE] != kIgnore) row[PROTO_SIMPLE] = 0.0f;
+    }
   return ncclSuccess;
 }
 

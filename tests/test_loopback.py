@@ -579,3 +579,11 @@ print(json.dumps({"name": T4.in_dll(lib, "ncclTunerPlugin_v4").name.decode(), "o
                 assert (ll, simple) == ((10.0, -1.0) if row != 4 else (-1.0, 10.0))   # LL where offered, else Simple stays
                 assert edge[3 * row:3 * row + 3] == small[3 * row:3 * row + 3]
                 assert above[3 * row:3 * row + 3] == [-1.0, -1.0, 10.0] and big[3 * row:3 * row + 3] == [-1.0, -1.0, 10.0]
+    # BNET_COLLNET=1: wherever NCCL offers a CollNet algorithm (rows 2 and 3, Simple not "ignore") it is made the cheapest
+    env = dict(os.environ, BNET_FAKE_CUDA="1", BNET_NVL="1", BNET_COLLNET="1", PYTHONPATH=root)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-3000:]
+    d = json.loads(r.stdout.splitlines()[-1])
+    for ver in ("4", "3"):
+        big = d["out"][ver]["1048576"]
+        assert big[3 * 2 + 2] == 0.0 and big[3 * 3 + 2] == 0.0 and big[3 * 1 + 2] == 10.0 and big[3 * 0 + 2] == 10.0, big
