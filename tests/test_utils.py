@@ -4,6 +4,7 @@ NIC-filter syntax and chunking invariants SURVEY.md §4 asks for."""
 import json
 import os
 import subprocess
+import time
 import sys
 
 import pytest
@@ -372,6 +373,41 @@ def test_tc_conv_wgrad_plan_and_gating(monkeypatch, tmp_path):
     assert len(files) == 1 and json.load(open(files[0]))["ok"] is False
     assert not glob.glob(str(tmp_path / "tc_self_check_*.json"))     # (the linear kernel's verdict is a different file)
     assert tc_linear._isolated_self_check(timeout=0.001, check="ok = True", tag="tc_wgrad_self_check") is False   # cached verdict wins
+
+
+def test_bench_child_jobs_are_bounded_and_fail_soft(monkeypatch, tmp_path):
+    """The side measurements of bench.py (DDP arms, ResNet arms, transport collectives, the CollNet probe) are child
+    processes: a result file is merged into the status, a child that fails or outlives its timeout costs that entry only."""
+    import argparse
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_under_test3", os.path.join(ROOT, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    monkeypatch.setenv("BNET_BENCH_LOG_DIR", str(tmp_path))
+    monkeypatch.setenv("MASTER_PORT", "29500")
+    monkeypatch.setenv("TORCHELASTIC_RUN_ID", "x")
+    args = argparse.Namespace(model="vgg16", steps=20, batch=32, image=224, no_fused=False, no_graph=False)
+    good = tmp_path / "good.py"
+    good.write_text("import argparse, json, os, sys\n"
+                    "a = argparse.ArgumentParser(); a.add_argument('--json'); a = a.parse_args()\n"
+                    "assert os.environ['BNET_BENCH_CHILD'] == '1' and 'TORCHELASTIC_RUN_ID' not in os.environ\n"
+                    "assert os.environ['MASTER_PORT'] == '29650' and 'BNET_BENCH_FUSED_VERDICT' not in os.environ\n"
+                    "print('child log line')\n"
+                    "open(a.json, 'w').write(json.dumps({'busbw': 123.0, 'exact': True}))\n")
+    res = mod.run_child_arm("transport", args, 0, 2, 150, 30.0, model="coll", script=[str(good)])
+    assert res["status"] == "ok" and res["busbw"] == 123.0 and res["exact"] is True and os.path.exists(res["log_path"])
+    assert "child log line" in open(res["log_path"]).read()
+    assert mod.run_child_arm("transport", args, 1, 2, 150, 30.0, model="coll", script=[str(good)]) is None     # only rank 0 reports
+    bad = tmp_path / "bad.py"
+    bad.write_text("import sys\nprint('boom: something failed')\nsys.exit(7)\n")
+    res = mod.run_child_arm("collnet", args, 0, 2, 163, 30.0, model="probe", script=[str(bad)])
+    assert res["status"] == "exit code 7" and any("boom" in ln for ln in res["log_tail"])
+    slow = tmp_path / "slow.py"
+    slow.write_text("import time\ntime.sleep(60)\n")
+    t0 = time.time()
+    res = mod.run_child_arm("collnet", args, 0, 2, 163, 1.0, model="probe", script=[str(slow)])
+    assert res["status"].startswith("timeout") and time.time() - t0 < 20
 
 
 def test_bench_isolated_self_check_classifies_child_outcomes(monkeypatch):
