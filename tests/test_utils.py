@@ -375,6 +375,105 @@ def test_tc_conv_wgrad_plan_and_gating(monkeypatch, tmp_path):
     assert tc_linear._isolated_self_check(timeout=0.001, check="ok = True", tag="tc_wgrad_self_check") is False   # cached verdict wins
 
 
+def test_conv_backward_composes_tcgen05_and_library_gradients(monkeypatch):
+    """fused_nn._conv_backward asks the autotuner per gradient (input / filter) and per shape; whatever mix it answers, the
+    pair that comes back must be the convolution's gradients, and a gradient nobody asked for is not computed."""
+    import torch
+
+    from bagua_net_b200.ops import fused_nn, tc_conv
+
+    torch.manual_seed(0)
+    x = torch.randn(2, 8, 6, 6).bfloat16().contiguous(memory_format=torch.channels_last)
+    w = torch.randn(16, 8, 3, 3).bfloat16().contiguous(memory_format=torch.channels_last)
+    gz = torch.randn(2, 16, 6, 6).bfloat16().contiguous(memory_format=torch.channels_last)
+    ref_x, ref_w, _ = torch.ops.aten.convolution_backward(gz, x, w, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [True, True, False])
+    calls = []
+
+    def fake_dgrad(g, ww):
+        calls.append("tc_dgrad")
+        return torch.ops.aten.convolution_backward(g, x, ww, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [True, False, False])[0]
+
+    def fake_wgrad(g, xx, splits=0):
+        calls.append("tc_wgrad")
+        return torch.ops.aten.convolution_backward(g, xx, w, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [False, True, False])[1]
+
+    monkeypatch.setattr(tc_conv, "conv3x3_dgrad", fake_dgrad)
+    monkeypatch.setattr(tc_conv, "conv3x3_wgrad", fake_wgrad)
+    for pick_x in ("tc", "cudnn"):
+        for pick_w in ("tc", "cudnn"):
+            for need_x in (True, False):
+                monkeypatch.setattr(tc_conv, "choose", lambda kind, *a, _p=pick_x, **k: _p)
+                monkeypatch.setattr(tc_conv, "choose_wgrad", lambda *a, _p=pick_w, **k: _p)
+                calls.clear()
+                gx, gw = fused_nn._conv_backward(gz, x, w, [1, 1], [1, 1], need_x)
+                assert torch.equal(gw, ref_w), (pick_x, pick_w, need_x)
+                assert (gx is None) if not need_x else torch.equal(gx, ref_x), (pick_x, pick_w, need_x)
+                assert calls.count("tc_dgrad") == (1 if (need_x and pick_x == "tc") else 0), (calls, pick_x, pick_w, need_x)
+                assert calls.count("tc_wgrad") == (1 if pick_w == "tc" else 0), (calls, pick_x, pick_w, need_x)
+    # anything but 3x3 / stride 1 / pad 1 never reaches the autotuner
+    monkeypatch.setattr(tc_conv, "choose", lambda *a, **k: (_ for _ in ()).throw(AssertionError("asked")))
+    monkeypatch.setattr(tc_conv, "choose_wgrad", lambda *a, **k: (_ for _ in ()).throw(AssertionError("asked")))
+    w1 = torch.randn(16, 8, 1, 1).bfloat16().contiguous(memory_format=torch.channels_last)
+    gx, gw = fused_nn._conv_backward(gz, x, w1, [1, 1], [0, 0], True)
+    assert gx.shape == x.shape and gw.shape == w1.shape
+
+
+def test_wgrad_autotuner_decisions(monkeypatch):
+    """choose_wgrad: untrusted kernel, wrong results, a tripped watchdog or an exception keep cuDNN; otherwise the faster
+    implementation wins; every verdict is cached per layer shape."""
+    import torch
+
+    from bagua_net_b200.ops import tc_conv, tc_linear
+
+    w = torch.zeros(64, 64, 3, 3).bfloat16().contiguous(memory_format=torch.channels_last)
+    good = torch.ones(64, 64, 3, 3)
+    state = {"trusted": True, "tc": good, "watchdog": 0, "t": {"tc": 10.0, "lib": 20.0}}
+    monkeypatch.setattr(tc_conv, "usable", lambda: True)
+    monkeypatch.setattr(tc_conv, "wgrad_shape_ok", lambda a, b: True)
+    monkeypatch.setattr(tc_conv, "wgrad_trusted", lambda: state["trusted"])
+    monkeypatch.setattr(tc_conv, "mode", lambda: "auto")
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)
+    monkeypatch.setattr(tc_linear, "last_error", lambda *a: state["watchdog"])
+
+    def fake_wgrad(g, xx, splits=0):
+        if isinstance(state["tc"], Exception):
+            raise state["tc"]
+        return state["tc"]
+
+    monkeypatch.setattr(tc_conv, "conv3x3_wgrad", fake_wgrad)
+    lib = lambda: good                                                     # noqa: E731
+    monkeypatch.setattr(tc_conv, "_time_us", lambda fn, iters=5: state["t"]["lib"] if fn is lib else state["t"]["tc"])
+
+    def decide(n):                                                         # a fresh shape (batch n) every time
+        x = torch.zeros(n, 64, 4, 4).bfloat16().contiguous(memory_format=torch.channels_last)
+        return tc_conv.choose_wgrad(torch.zeros_like(x), x, w, lib), ("wgrad", n, 4, 4, 64, 64)
+
+    monkeypatch.setattr(tc_conv, "_choice", {})
+    monkeypatch.setattr(tc_conv, "TIMINGS", {})
+    pick, key = decide(1)
+    assert pick == "tc" and tc_conv.TIMINGS[key] == {"tc": 10.0, "cudnn": 20.0}
+    state["t"] = {"tc": 30.0, "lib": 20.0}
+    assert decide(1)[0] == "tc"                                            # cached: not timed again
+    assert decide(2)[0] == "cudnn"
+    state["t"] = {"tc": 10.0, "lib": 20.0}
+    state["tc"] = good * 1.5
+    pick, key = decide(3)
+    assert pick == "cudnn" and "differ" in tc_conv.TIMINGS[key]["error"]
+    state["tc"], state["watchdog"] = good, 2
+    pick, key = decide(4)
+    assert pick == "cudnn" and "watchdog" in tc_conv.TIMINGS[key]["error"]
+    state["watchdog"], state["tc"] = 0, RuntimeError("bnet_tc_conv3x3_wgrad: no kernel")
+    pick, key = decide(5)
+    assert pick == "cudnn" and "RuntimeError" in tc_conv.TIMINGS[key]["error"]
+    state["tc"], state["trusted"] = good, False
+    pick, key = decide(6)
+    assert pick == "cudnn" and "not trusted" in tc_conv.TIMINGS[key]["error"]
+    monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: True)
+    state["trusted"] = True
+    assert decide(7)[0] == "cudnn" and ("wgrad", 7, 4, 4, 64, 64) not in tc_conv._choice     # a capture decides nothing
+
+
 def test_bench_child_jobs_are_bounded_and_fail_soft(monkeypatch, tmp_path):
     """The side measurements of bench.py (DDP arms, ResNet arms, transport collectives, the CollNet probe) are child
     processes: a result file is merged into the status, a child that fails or outlives its timeout costs that entry only."""
