@@ -179,8 +179,17 @@ def wgrad_trusted() -> bool:
         else:
             if torch.cuda.is_current_stream_capturing():
                 return False
-            _wgrad_trusted = tc_linear._isolated_self_check(
-                check="from bagua_net_b200.ops import tc_conv; ok = tc_conv.self_check_wgrad()", tag="tc_wgrad_self_check")
+            check = "from bagua_net_b200.ops import tc_conv; ok = tc_conv.self_check_wgrad()"
+            _wgrad_trusted = tc_linear._isolated_self_check(check=check, tag="tc_wgrad_self_check")
+            if not _wgrad_trusted and "BNET_TC_WGRAD_BN" not in os.environ:
+                # Fallback ladder: the 256-column tiles are the one building block of this kernel that no validated kernel
+                # shares (the linear dW ran its MN-major column operand with 128-column tiles on hardware).  If only they
+                # are at fault, every layer can still run on 128-column tiles.  The library reads the variable at its first
+                # filter-gradient launch, which cannot have happened yet in this process.
+                os.environ["BNET_TC_WGRAD_BN"] = "128"
+                _wgrad_trusted = tc_linear._isolated_self_check(check=check, tag="tc_wgrad_bn128_self_check")
+                if not _wgrad_trusted:
+                    del os.environ["BNET_TC_WGRAD_BN"]
     return _wgrad_trusted
 
 

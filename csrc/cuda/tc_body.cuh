@@ -412,7 +412,7 @@ struct WgradProblem {
 inline int wgrad_max_tiles(int Cin, int Cout) { return ((Cout + kBM - 1) / kBM) * ((9 * Cin + 127) / 128); }
 
 inline const char* setup_conv_wgrad(const void* gy, const void* x, float* ws, void* dw, int* counters, int N, int H, int W, int Cin,
-                                    int Cout, int splits, int* err_dev, int sm_count, WgradProblem* wp) {
+                                    int Cout, int splits, int* err_dev, int sm_count, WgradProblem* wp, int force_bn = 0) {
   if (N < 1 || H < 1 || W < 1 || Cin < 64 || Cin % 64 || Cout < 64 || Cout % 64)
     return "conv3x3 wgrad: input and output channels must be multiples of 64";
   if (!err_dev || !ws || !counters) return "conv3x3 wgrad needs err_dev, a workspace and tile counters";
@@ -436,7 +436,8 @@ inline const char* setup_conv_wgrad(const void* gy, const void* x, float* ws, vo
   const int cols = 9 * Cin;
   // 256-column tiles (half the MMA issues per byte of gy) unless they waste more than ~1/7 of the columns (Cin = 64: 576 columns)
   const int t256 = (cols + 255) / 256, t128 = (cols + 127) / 128;
-  const int bn_cols = (long long)t256 * 256 * 7 <= (long long)cols * 8 ? 256 : 128;
+  int bn_cols = (long long)t256 * 256 * 7 <= (long long)cols * 8 ? 256 : 128;
+  if (force_bn == 128 || force_bn == 256) bn_cols = force_bn;       // (BNET_TC_WGRAD_BN: the self-check's fallback ladder)
   const int tiles_b = bn_cols == 256 ? t256 : t128;
   const int tiles_a = (Cout + kBM - 1) / kBM;
   BnetTcPlan& p = wp->plan;

@@ -38,6 +38,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <mutex>
 #include <string>
@@ -556,7 +557,10 @@ int run_conv(const void* x, const void* w, const void* bias, void* out, int N, i
 int run_conv_wgrad(const void* gy, const void* x, void* dw, float* ws, int* counters, int N, int H, int W, int Cin, int Cout, int splits,
                    int* err_dev, void* stream) {
   WgradProblem wp;
-  if (const char* e = setup_conv_wgrad(gy, x, ws, dw, counters, N, H, W, Cin, Cout, splits, err_dev, sm_count(), &wp)) {
+  // BNET_TC_WGRAD_BN=128: every layer on 128-column tiles (ops/tc_conv.py sets it when only that configuration passed the
+  // self-check on the GPU at hand)
+  static const int force_bn = [] { const char* v = getenv("BNET_TC_WGRAD_BN"); return v ? atoi(v) : 0; }();
+  if (const char* e = setup_conv_wgrad(gy, x, ws, dw, counters, N, H, W, Cin, Cout, splits, err_dev, sm_count(), &wp, force_bn)) {
     g_err = e;
     return -1;
   }

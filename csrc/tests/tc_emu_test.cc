@@ -439,7 +439,7 @@ static void run_wgrad_kernel(const WgradProblem& wp, const HostOut& out) {
   }
 }
 
-static void conv_wgrad(int N, int H, int W, int Cin, int Cout, int sms, int splits) {
+static void conv_wgrad(int N, int H, int W, int Cin, int Cout, int sms, int splits, int force_bn = 0) {
   Mat gy(N * H * W, Cout), x(N * H * W, Cin);
   const int cols = 9 * Cin;
   std::vector<float> ws(size_t(Cout) * cols, 0.f);
@@ -449,9 +449,10 @@ static void conv_wgrad(int N, int H, int W, int Cin, int Cout, int sms, int spli
   while (reinterpret_cast<uintptr_t>(dw) & 15) dw++;
   int err = 0;
   WgradProblem wp;
-  const char* e = setup_conv_wgrad(gy.ptr(), x.ptr(), ws.data(), dw, counters.data(), N, H, W, Cin, Cout, splits, &err, sms, &wp);
+  const char* e = setup_conv_wgrad(gy.ptr(), x.ptr(), ws.data(), dw, counters.data(), N, H, W, Cin, Cout, splits, &err, sms, &wp, force_bn);
   CHECK(e == nullptr, "wgrad setup: %s", e ? e : "");
   if (e) return;
+  CHECK(force_bn == 0 || wp.plan.bn == force_bn, "forced tile width %d, plan has %d", force_bn, wp.plan.bn);
   CHECK(wp.args.n_tiles <= (int)counters.size(), "wgrad_max_tiles %zu < %d tiles", counters.size(), wp.args.n_tiles);
   CHECK((long long)wp.plan.ctas * wp.plan.grid_z <= (sms > wp.plan.grid_z ? sms : wp.plan.grid_z) || wp.plan.ctas == 1, "wgrad launches %d x %d CTAs on %d SMs",
         wp.plan.ctas, wp.plan.grid_z, sms);
@@ -492,6 +493,8 @@ int main() {
   conv_wgrad(5, 4, 4, 64, 192, 2, 1);
   conv_wgrad(2, 6, 10, 128, 256, 7, 0);
   conv_wgrad(1, 5, 3, 256, 128, 148, 0);
+  conv_wgrad(2, 6, 10, 128, 256, 7, 0, 128);         // the self-check's fallback: 128-column tiles for every layer
+  conv_wgrad(1, 5, 3, 256, 128, 148, 2, 128);
   // forward / input gradient: exact patches, ragged patches (7x7, 14x14 with odd batch), several images per patch, persistent CTAs
   conv(2, 8, 16, 64, 64, true, 148);
   conv(3, 7, 7, 64, 128, false, 3);

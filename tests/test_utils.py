@@ -368,9 +368,17 @@ def test_tc_conv_wgrad_plan_and_gating(monkeypatch, tmp_path):
     monkeypatch.setattr(torch.cuda, "get_device_name", lambda *a: "Fake B200")
     monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
     monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)
+    monkeypatch.delenv("BNET_TC_WGRAD_BN", raising=False)
     assert tc_conv.wgrad_trusted() is False                          # the child has no GPU either: a clean "no", cached
     files = glob.glob(str(tmp_path / "tc_wgrad_self_check_*.json"))
     assert len(files) == 1 and json.load(open(files[0]))["ok"] is False
+    # ... after the fallback ladder tried 128-column tiles for every layer in a second child (its own verdict file)
+    files128 = glob.glob(str(tmp_path / "tc_wgrad_bn128_self_check_*.json"))
+    assert len(files128) == 1 and json.load(open(files128[0]))["ok"] is False and "BNET_TC_WGRAD_BN" not in os.environ
+    json.dump({"ok": True}, open(files128[0], "w"))                  # "only the 128-column configuration passed on this GPU"
+    monkeypatch.setattr(tc_conv, "_wgrad_trusted", None)
+    assert tc_conv.wgrad_trusted() is True and os.environ.get("BNET_TC_WGRAD_BN") == "128"
+    monkeypatch.delenv("BNET_TC_WGRAD_BN", raising=False)
     assert not glob.glob(str(tmp_path / "tc_self_check_*.json"))     # (the linear kernel's verdict is a different file)
     assert tc_linear._isolated_self_check(timeout=0.001, check="ok = True", tag="tc_wgrad_self_check") is False   # cached verdict wins
 
