@@ -324,15 +324,18 @@ def self_check(device=None, verbose: bool = False) -> bool:
     return ok
 
 
-def self_check_wgrad(device=None, verbose: bool = False) -> bool:
+WGRAD_CHECK_SHAPES = ((2, 64, 64, 32, 0), (3, 64, 128, 14, 1), (2, 128, 256, 28, 0), (5, 256, 64, 7, 3), (1, 64, 320, 20, 0),
+                      (32, 512, 512, 14, 0), (8, 128, 128, 56, 0))       # (batch, Cin, Cout, height = width, pixel slices)
+
+
+def self_check_wgrad(device=None, verbose: bool = False, shapes=WGRAD_CHECK_SHAPES) -> bool:
     """The filter-gradient kernel against cuDNN in bf16: exact and ragged 64-pixel patches, one and many slices of the pixel
     reduction, Cout below one lane tile, tiles that straddle taps (Cin = 64), columns past 9 Cin (Cin = 128), a VGG-sized
     layer; the workspace and the tile counters must come back all zero."""
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
     g = torch.Generator(device=dev).manual_seed(7)
     ok = True
-    for n, cin, cout, hw, splits in ((2, 64, 64, 32, 0), (3, 64, 128, 14, 1), (2, 128, 256, 28, 0), (5, 256, 64, 7, 3),
-                                     (1, 64, 320, 20, 0), (32, 512, 512, 14, 0), (8, 128, 128, 56, 0)):
+    for n, cin, cout, hw, splits in shapes:
         x = torch.randn(n, cin, hw, hw, device=dev, generator=g).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
         gy = (torch.randn(n, cout, hw, hw, device=dev, generator=g) * (1.0 / hw)).to(torch.bfloat16).contiguous(
             memory_format=torch.channels_last)

@@ -426,6 +426,40 @@ def test_conv_backward_composes_tcgen05_and_library_gradients(monkeypatch):
     assert gx.shape == x.shape and gw.shape == w1.shape
 
 
+def test_wgrad_self_check_body_runs(monkeypatch):
+    """The child-process self-check of the filter gradient is what decides whether the kernel is ever used: its own Python
+    must not be what fails.  Run its body on the CPU with the kernel replaced by the library's result (and by a wrong one)."""
+    import torch
+
+    from bagua_net_b200.ops import tc_conv, tc_linear
+
+    state = {"scale": 1.0, "dirty": False}
+
+    def fake_wgrad(gy, x, splits=0):
+        w = torch.empty(gy.shape[1], x.shape[1], 3, 3, dtype=torch.bfloat16)
+        ws, _ = tc_conv._wgrad_ws(gy.device, x.shape[1], gy.shape[1])
+        if state["dirty"]:
+            ws[0, 0] = 1.0
+        ref = torch.ops.aten.convolution_backward(gy, x, w, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [False, True, False])[1]
+        return (ref.float() * state["scale"]).to(torch.bfloat16)
+
+    monkeypatch.setattr(tc_conv, "conv3x3_wgrad", fake_wgrad)
+    monkeypatch.setattr(tc_conv, "_wgrad_scratch", {})
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(tc_linear, "last_error", lambda *a: 0)
+    cpu, small = torch.device("cpu"), ((2, 64, 64, 6, 0), (1, 64, 128, 5, 2))
+    assert tc_conv.self_check_wgrad(device=cpu, shapes=small) is True
+    state["scale"] = 1.3
+    assert tc_conv.self_check_wgrad(device=cpu, shapes=small) is False          # wrong numbers
+    state["scale"], state["dirty"] = 1.0, True
+    assert tc_conv.self_check_wgrad(device=cpu, shapes=small) is False          # scratch not handed back clean
+    state["dirty"] = False
+    monkeypatch.setattr(tc_conv, "_wgrad_scratch", {})
+    monkeypatch.setattr(tc_linear, "last_error", lambda *a: 2)
+    assert tc_conv.self_check_wgrad(device=cpu, shapes=small) is False          # the pipeline watchdog tripped
+    assert len(tc_conv.WGRAD_CHECK_SHAPES) >= 6 and any(s[1] == 64 for s in tc_conv.WGRAD_CHECK_SHAPES)   # 128- and 256-column plans
+
+
 def test_wgrad_autotuner_decisions(monkeypatch):
     """choose_wgrad: untrusted kernel, wrong results, a tripped watchdog or an exception keep cuDNN; otherwise the faster
     implementation wins; every verdict is cached per layer shape."""
