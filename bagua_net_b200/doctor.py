@@ -67,6 +67,18 @@ def run(out=sys.stdout) -> int:
             except (ValueError, OSError):
                 continue
     say("v8" in have, "ncclNet tables exported", " ".join(have))
+    coll = []
+    for v in (4, 6, 7, 8, 9, 10):
+        for name in (bagua_net_b200.LIB_NAME, "libnccl-net-bnetx.so"):
+            try:
+                ctypes.c_void_p.in_dll(bagua_net_b200.load_library(name), f"ncclCollNetPlugin_v{v}")
+                coll.append(f"v{v}" + ("" if name == bagua_net_b200.LIB_NAME else "(bnetx)"))
+                break
+            except (ValueError, OSError):
+                continue
+    say("v8" in coll, "ncclCollNet tables exported", " ".join(coll) + (
+        " — switched on (BNET_COLLNET=1): with NCCL_COLLNET_ENABLE=1 NCCL may offload all-reduces to the two-shot mesh"
+        if os.environ.get("BNET_COLLNET") == "1" else " — silent (no devices reported) unless BNET_COLLNET=1"))
     for line in _nccl_versions() or ["no NCCL found (the plugin is still usable through bagua_net_b200.utils.abi)"]:
         say(None, "NCCL", line + " — NCCL 2.19+ probes v6..v10 tables; 2.6-2.18 load v4")
     del lib
@@ -116,6 +128,15 @@ def run(out=sys.stdout) -> int:
             say(True, "symmetric heap (cuMem VMM, POSIX-fd exportable)")
         except Exception as e:      # noqa: BLE001
             say(False, "symmetric heap", str(e))
+        try:
+            from bagua_net_b200.ops import tc_conv
+
+            v = tc_conv.prepare()
+            say(None, "tcgen05 kernels", f"linear / convolution self-check {'passed' if v['usable'] else 'not passed (cuBLAS / cuDNN are used)'}; "
+                f"filter gradient {'trusted' if v['wgrad'] else 'not trusted'} on this GPU"
+                + (f" with {os.environ['BNET_TC_WGRAD_BN']}-column tiles" if v["wgrad"] and os.environ.get("BNET_TC_WGRAD_BN") else ""))
+        except Exception as e:      # noqa: BLE001
+            say(None, "tcgen05 kernels", f"could not be checked: {e}")
         try:
             cu = ctypes.CDLL("libcuda.so.1")
             dev, val = ctypes.c_int(), ctypes.c_int()
