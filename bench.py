@@ -213,7 +213,7 @@ ARM_SIZES = (8, 1 << 10, 64 << 10, 1 << 20, 16 << 20, 128 << 20)   # all-reduce 
 
 
 def run_child_arm(comm_name: str, args, rank: int, world: int, port_offset: int, timeout: float, model: str | None = None,
-                  script: list | None = None):
+                  script: list | None = None, extra_env: dict | None = None, tag: str = ""):
     """One DDP arm (`--comm nccl-plugin` / `--comm nccl`) as a child process per rank: own CUDA context, own NCCL
     (with or without the plugin on LD_LIBRARY_PATH), own rendezvous port.  Every rank of the parent job calls this at
     the same time; rank 0 returns the child's JSON (or a status dict), the others None.  A child that outlives
@@ -233,9 +233,10 @@ def run_child_arm(comm_name: str, args, rank: int, world: int, port_offset: int,
     else:
         env.pop("BNET_BENCH_FUSED_VERDICT", None)   # another model family: the child checks its own layer kernels
     env.pop("BNET_BENCH_REEXEC", None)
+    env.update(extra_env or {})
     log_dir = os.environ.get("BNET_BENCH_LOG_DIR") or tempfile.gettempdir()
     os.makedirs(log_dir, exist_ok=True)
-    out_path = os.path.join(log_dir, f"bnet_bench_arm_{model}_{comm_name}_{os.getppid()}_{env['MASTER_PORT']}.json")
+    out_path = os.path.join(log_dir, f"bnet_bench_arm_{model}_{comm_name}{tag}_{os.getppid()}_{env['MASTER_PORT']}.json")
     if rank == 0 and os.path.exists(out_path):
         os.unlink(out_path)
     if script:                                   # another measurement script with the same contract: --json <file>, rank 0 writes it
@@ -777,6 +778,20 @@ def main() -> int:
                 dist.barrier()
             if rank == 0:
                 arms[key] = res
+
+    # ---- last and least: the DDP-over-plugin arm once more with the copy engines moving the bytes (BNET_EXEC_MODE=ce: no SM
+    #      is taken from the backward pass; slower in isolation, never measured under overlap) — only if time is left
+    if (args.comm == "bnet" and world > 1 and not args.no_arms and not args.no_resnet and not os.environ.get("BNET_BENCH_CHILD")):
+        sync_all()
+        go = torch.tensor([1 if time.time() - _T0 < args.resnet_deadline else 0], device=dev, dtype=torch.int32)
+        dist.broadcast(go, 0)
+        if int(go.item()):
+            note(f"arm nccl-plugin with copy engines: child processes (timeout {args.resnet_timeout:.0f} s)")
+            res = run_child_arm("nccl-plugin", args, rank, world, 290, args.resnet_timeout, extra_env={"BNET_EXEC_MODE": "ce"}, tag="_ce")
+            note(f"arm nccl-plugin with copy engines: {res.get('status') if res else None}")
+            dist.barrier()
+            if rank == 0:
+                arms["nccl_plugin_copy_engines"] = res
 
     if rank == 0:
         opt_desc = (f"sgd(lr={lr},momentum={mom},wd={wd}) fused into the collective" if args.comm == "bnet"
