@@ -165,6 +165,23 @@ def conv3x3_wgrad(gy: torch.Tensor, x: torch.Tensor, splits: int = 0) -> torch.T
 _wgrad_trusted = None
 
 
+def _extra_check_shapes():
+    """(tuple of (n, cin, cout, hw, 0) from BNET_TC_WGRAD_CHECK_SHAPES, suffix for the verdict's cache file)."""
+    import hashlib
+
+    raw = os.environ.get("BNET_TC_WGRAD_CHECK_SHAPES", "").strip()
+    shapes = []
+    for item in raw.split(";"):
+        try:
+            n, cin, cout, hw = (int(v) for v in item.split(","))
+        except ValueError:
+            continue
+        if n > 0 and hw > 0 and cin % 64 == 0 and cout % 64 == 0 and cin > 0 and cout > 0:
+            shapes.append((n, cin, cout, hw, 0))
+    shapes = tuple(sorted(set(shapes)))
+    return shapes, ("_" + hashlib.sha1(repr(shapes).encode()).hexdigest()[:8]) if shapes else ""
+
+
 def wgrad_trusted() -> bool:
     """May the filter-gradient kernel run in THIS process?  ``BNET_TC_WGRAD``: ``0`` never, ``1`` yes (no check), default:
     only after ``self_check_wgrad()`` passed in a child process on this GPU — a kernel that has never run on hardware must
@@ -179,15 +196,18 @@ def wgrad_trusted() -> bool:
         else:
             if torch.cuda.is_current_stream_capturing():
                 return False
-            check = "from bagua_net_b200.ops import tc_conv; ok = tc_conv.self_check_wgrad()"
-            _wgrad_trusted = tc_linear._isolated_self_check(check=check, tag="tc_wgrad_self_check")
+            # BNET_TC_WGRAD_CHECK_SHAPES="n,cin,cout,hw;...": layer shapes the caller is about to train (bench.py names the
+            # flagship's) are checked in the child as well, so that a shape-dependent fault cannot happen in this process
+            extra, sfx = _extra_check_shapes()
+            check = f"from bagua_net_b200.ops import tc_conv; ok = tc_conv.self_check_wgrad(shapes=tc_conv.WGRAD_CHECK_SHAPES + {extra!r})"
+            _wgrad_trusted = tc_linear._isolated_self_check(check=check, tag="tc_wgrad_self_check" + sfx)
             if not _wgrad_trusted and "BNET_TC_WGRAD_BN" not in os.environ:
                 # Fallback ladder: the 256-column tiles are the one building block of this kernel that no validated kernel
                 # shares (the linear dW ran its MN-major column operand with 128-column tiles on hardware).  If only they
                 # are at fault, every layer can still run on 128-column tiles.  The library reads the variable at its first
                 # filter-gradient launch, which cannot have happened yet in this process.
                 os.environ["BNET_TC_WGRAD_BN"] = "128"
-                _wgrad_trusted = tc_linear._isolated_self_check(check=check, tag="tc_wgrad_bn128_self_check")
+                _wgrad_trusted = tc_linear._isolated_self_check(check=check, tag="tc_wgrad_bn128_self_check" + sfx)
                 if not _wgrad_trusted:
                     del os.environ["BNET_TC_WGRAD_BN"]
     return _wgrad_trusted

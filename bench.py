@@ -232,6 +232,7 @@ def run_child_arm(comm_name: str, args, rank: int, world: int, port_offset: int,
         env["BNET_BENCH_FUSED_VERDICT"] = "0" if args.no_fused or getattr(args, "fused_failed", False) else "1"
     else:
         env.pop("BNET_BENCH_FUSED_VERDICT", None)   # another model family: the child checks its own layer kernels
+        env.pop("BNET_TC_WGRAD_CHECK_SHAPES", None)  # ... and names its own layer shapes to the filter-gradient self-check
     env.pop("BNET_BENCH_REEXEC", None)
     env.update(extra_env or {})
     log_dir = os.environ.get("BNET_BENCH_LOG_DIR") or tempfile.gettempdir()
@@ -375,6 +376,14 @@ def main() -> int:
         # time on a machine) while no collective is in flight, then line the ranks up again
         from bagua_net_b200.ops import tc_conv
 
+        # the 3x3 / stride-1 layers this run will train, at its batch size: the filter-gradient kernel's child-process
+        # self-check covers exactly these shapes too (a shape-dependent fault must not be able to happen in THIS process)
+        if "BNET_TC_WGRAD_CHECK_SHAPES" not in os.environ:
+            s_ = args.image
+            layers = ([(64, 64, s_), (64, 128, s_ // 2), (128, 128, s_ // 2), (128, 256, s_ // 4), (256, 256, s_ // 4), (256, 512, s_ // 8),
+                       (512, 512, s_ // 8), (512, 512, s_ // 16)] if args.model.startswith("vgg") else
+                      [(64, 64, s_ // 4), (128, 128, s_ // 8), (256, 256, s_ // 16), (512, 512, s_ // 32)])
+            os.environ["BNET_TC_WGRAD_CHECK_SHAPES"] = ";".join(f"{args.batch},{ci},{co},{hw}" for ci, co, hw in layers if hw > 0)
         note(f"tcgen05 kernels: {tc_conv.prepare()}")
         if world > 1:
             dist.barrier()

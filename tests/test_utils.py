@@ -426,6 +426,22 @@ def test_conv_backward_composes_tcgen05_and_library_gradients(monkeypatch):
     assert gx.shape == x.shape and gw.shape == w1.shape
 
 
+def test_wgrad_self_check_can_be_given_the_callers_shapes(monkeypatch):
+    from bagua_net_b200.ops import tc_conv
+
+    monkeypatch.delenv("BNET_TC_WGRAD_CHECK_SHAPES", raising=False)
+    assert tc_conv._extra_check_shapes() == ((), "")
+    monkeypatch.setenv("BNET_TC_WGRAD_CHECK_SHAPES", "32,64,64,224;32,512,512,14;32,3,64,224;junk;32,64,128,0;32,512,512,14")
+    shapes, sfx = tc_conv._extra_check_shapes()
+    assert shapes == ((32, 64, 64, 224, 0), (32, 512, 512, 14, 0)) and len(sfx) == 9 and sfx.startswith("_")
+    # what the child evaluates must be valid Python that extends the built-in list
+    ns = {}
+    exec(f"from bagua_net_b200.ops import tc_conv\nall_shapes = tc_conv.WGRAD_CHECK_SHAPES + {shapes!r}", ns)
+    assert ns["all_shapes"][-1] == (32, 512, 512, 14, 0) and len(ns["all_shapes"]) == len(tc_conv.WGRAD_CHECK_SHAPES) + 2
+    monkeypatch.setenv("BNET_TC_WGRAD_CHECK_SHAPES", "8,64,64,32")
+    assert tc_conv._extra_check_shapes()[1] != sfx                     # another shape list, another verdict file
+
+
 def test_wgrad_self_check_body_runs(monkeypatch):
     """The child-process self-check of the filter gradient is what decides whether the kernel is ever used: its own Python
     must not be what fails.  Run its body on the CPU with the kernel replaced by the library's result (and by a wrong one)."""
