@@ -262,6 +262,12 @@ def choose_wgrad(gy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, cudnn_fn) -
     except Exception as ex:   # noqa: BLE001 — anything unexpected keeps the library path for this shape
         TIMINGS[key] = {"error": f"{type(ex).__name__}: {str(ex)[:80]}"}
         _choice[key] = "cudnn"
+        try:        # a run that went wrong may have left the shared scratch of this (Cin, Cout) dirty: other shapes use it too
+            ws, counters = _wgrad_ws(gy.device, x.shape[1], cout)
+            ws.zero_()
+            counters.zero_()
+        except Exception:   # noqa: BLE001
+            pass
     return _choice[key]
 
 
