@@ -237,6 +237,51 @@ def test_transport_mesh_twoshot_allreduce_2gpu():
     _run_worker("transport_mesh_twoshot", 2)
 
 
+def _run_script(script, nproc, timeout=300):
+    """A benchmark script of bench/ as one process per GPU (torchrun-style environment); returns rank 0's JSON line."""
+    import socket
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    procs = []
+    for r in range(nproc):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(nproc), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                   PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "bench", script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.PIPE, text=True))
+    outs = []
+    for p in procs:
+        try:
+            o, e = p.communicate(timeout=timeout)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+        outs.append((p.returncode, o, e))
+    for rc, o, e in outs:
+        assert rc == 0, f"{script} failed rc={rc}\nstdout:\n{o[-2000:]}\nstderr:\n{e[-3000:]}"
+    return json.loads([ln for ln in outs[0][1].splitlines() if ln.startswith("{")][-1]), "".join(o + e for _, o, e in outs)
+
+
+@pytest.mark.multigpu
+def test_transport_collectives_bench_2gpu():
+    """bench/transport_coll.py (what bench.py reports as extra.transport_allreduce): ring, two-shot and one-shot all-reduces
+    over the plugin's own connections, exact on every rank."""
+    d, _ = _run_script("transport_coll.py", 2)
+    assert d["exact"] and d["transport"] == "nvl" and d["two_shot_fp32_in_place"] and d["ring_fp32"], d
+
+
+@pytest.mark.multigpu
+def test_nccl_collnet_probe_2gpu():
+    """bench/nccl_collnet_probe.py: NCCL with the plugin's CollNet table switched on must at least produce exact all-reduces
+    (whether it ran them THROUGH the table is what `collnet_allreduces_min_over_ranks` reports)."""
+    d, log = _run_script("nccl_collnet_probe.py", 2)
+    assert d["exact"], d
+    print("collnet all-reduces executed by the plugin (min over ranks):", d["collnet_allreduces_min_over_ranks"])
+
+
 # ------------------------------------------------------------------ written after the last hardware session of round 2: LAST in the file
 def test_executor_fp8_decompression_ops():
     """fp8 -> fp32 overwrite ops (OP_CAST_E4M3_TO_F32 / OP_CAST_E5M2_TO_F32) of the compressed all-reduce's all-gather half."""
