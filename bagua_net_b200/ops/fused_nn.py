@@ -78,7 +78,16 @@ def _conv_backward(gz, x, w, stride, padding, need_x):
         tc_w = tc_conv.choose_wgrad(gz, x, w, lambda: lib(False, True)[1]) == "tc"
         if tc_x or tc_w:
             gx = tc_conv.conv3x3_dgrad(gz, w) if tc_x else None
-            gw = tc_conv.conv3x3_wgrad(gz, x) if tc_w else None
+            gw = None
+            if tc_w:
+                # the kernel writes the filter gradient straight into the parameter's slice of the engine's flat gradient
+                # buffer when there is one (ops/grad_target.py); autograd adopts the slice instead of accumulating into it
+                from . import grad_target
+
+                dst = grad_target.lookup(w)
+                gw = tc_conv.conv3x3_wgrad(gz, x, out=dst)
+                if dst is not None and gw.data_ptr() == dst.data_ptr():
+                    gw = grad_target.adopt(dst)
             if (need_x and gx is None) or gw is None:
                 rx, rw, _ = lib(need_x and gx is None, gw is None)
                 gx = rx if gx is None else gx

@@ -143,14 +143,19 @@ def wgrad_shape_ok(gy: torch.Tensor, x: torch.Tensor) -> bool:
     return gy.shape[1] % 64 == 0 and x.shape[1] % 64 == 0
 
 
-def conv3x3_wgrad(gy: torch.Tensor, x: torch.Tensor, splits: int = 0) -> torch.Tensor:
+def conv3x3_wgrad(gy: torch.Tensor, x: torch.Tensor, splits: int = 0, out: torch.Tensor | None = None) -> torch.Tensor:
     """Filter gradient of ``conv2d(x, w, stride=1, padding=1)``: gy [N,Cout,H,W], x [N,Cin,H,W] channels_last bf16 ->
     dw [Cout,Cin,3,3] channels_last bf16 (memory [Cout][3][3][Cin]).  ``splits``: slices of the pixel reduction (0 = as many
     as fill the SMs)."""
     global LAUNCHES
     n, cout, h, wd = gy.shape
     cin = x.shape[1]
-    dw = torch.empty((cout, cin, 3, 3), device=gy.device, dtype=torch.bfloat16, memory_format=torch.channels_last)
+    # `out`: a channels_last bf16 [Cout,Cin,3,3] tensor to write into (the parameter's slice of an engine's flat gradient buffer)
+    if out is not None and (tuple(out.shape) != (cout, cin, 3, 3) or out.dtype != torch.bfloat16 or out.data_ptr() % 16
+                            or not out.is_contiguous(memory_format=torch.channels_last)):
+        out = None
+    dw = out if out is not None else torch.empty((cout, cin, 3, 3), device=gy.device, dtype=torch.bfloat16,
+                                                  memory_format=torch.channels_last)
     ws, counters = _wgrad_ws(gy.device, cin, cout)
     L = _L()
     rc = L.bnet_tc_conv3x3_wgrad(gy.data_ptr(), x.data_ptr(), dw.data_ptr(), ws.data_ptr(), counters.data_ptr(), n, h, wd, cin, cout,

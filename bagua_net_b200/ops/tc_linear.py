@@ -186,13 +186,18 @@ def linear_dgrad(gy: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     return dx
 
 
-def linear_wgrad(gy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
-    """``gy.T @ x`` (dW of a linear layer): gy [M,N], x [M,K] as stored — both read MN-major (the batch is the reduction)."""
+def linear_wgrad(gy: torch.Tensor, x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """``gy.T @ x`` (dW of a linear layer): gy [M,N], x [M,K] as stored — both read MN-major (the batch is the reduction).
+    ``out``: a bf16 [N,K] tensor with unit inner stride and a 16-byte row pitch to write into (e.g. the parameter's slice of
+    a training engine's flat gradient buffer)."""
     global LAUNCHES
     M, N = gy.shape
     K = x.shape[1]
     assert gy.dtype == x.dtype == torch.bfloat16 and x.shape[0] == M and gy.stride(1) == 1 and x.stride(1) == 1
-    dw = torch.empty((N, K), dtype=torch.bfloat16, device=gy.device)
+    if out is not None and (tuple(out.shape) != (N, K) or out.dtype != torch.bfloat16 or out.stride(1) != 1 or out.stride(0) % 8
+                            or out.data_ptr() % 16):
+        out = None
+    dw = torch.empty((N, K), dtype=torch.bfloat16, device=gy.device) if out is None else out
     L = _L()
     rc = L.bnet_tc_linear_wgrad(gy.data_ptr(), x.data_ptr(), dw.data_ptr(), M, N, K, gy.stride(0), x.stride(0), dw.stride(0),
                                 _err_flag(gy.device.index).data_ptr(), _stream())
@@ -210,6 +215,24 @@ def _bwd_on_tc(gy, x, w) -> bool:
     N, K = w.shape
     return (gy.is_contiguous() and N > 64 and N % 8 == 0 and K % 8 == 0 and x.stride(1) == 1 and x.stride(0) % 8 == 0
             and w.stride(1) == 1 and w.stride(0) % 8 == 0)
+
+
+def weight_grad(gy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, tc: bool) -> torch.Tensor:
+    """dW = gy.T @ x of a linear layer.  When a training engine registered a gradient slice for `w` (ops/grad_target.py) the
+    GEMM writes straight into it — the tcgen05 kernel through its output pointer, cuBLAS through ``out=`` — and the slice is
+    handed to autograd for adoption: no tensor of its own, no accumulate pass over the (for VGG16's fc1: 205 MB) gradient."""
+    from . import grad_target
+
+    dst = grad_target.lookup(w, shape=(gy.shape[1], x.shape[1]), dtype=gy.dtype)
+    if dst is not None and not dst.is_contiguous():
+        dst = None
+    if tc:
+        gw = linear_wgrad(gy, x, out=dst)
+        return grad_target.adopt(dst) if dst is not None and gw.data_ptr() == dst.data_ptr() else gw
+    if dst is not None:
+        torch.mm(gy.t(), x, out=dst)
+        return grad_target.adopt(dst)
+    return gy.t() @ x
 
 
 class _LinearAct(torch.autograd.Function):
@@ -235,7 +258,7 @@ class _LinearAct(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             gx = linear_dgrad(gy, w) if tc else gy @ w
         if ctx.needs_input_grad[1]:
-            gw = linear_wgrad(gy, x) if tc else gy.t() @ x
+            gw = weight_grad(gy, x, w, tc)
         gb = gy.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
         return gx, gw, gb, None
 

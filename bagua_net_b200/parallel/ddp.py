@@ -4,9 +4,9 @@ The reference accelerates PyTorch/Bagua DDP by moving NCCL's all-reduce traffic 
 (reference README.md:52-84).  Here the data-parallel step itself is re-designed for an
 NVSwitch box:
 
-* parameters and gradients live in flat buffers inside the symmetric heap; ``p.data`` and
-  ``p.grad`` are views, so autograd accumulates straight into communication memory (no
-  bucket copy-in/copy-out);
+* parameters and gradients live in flat buffers inside the symmetric heap; ``p.data`` is a view, and every
+  gradient has a slice of the flat gradient buffer that its producer writes directly (``ops/grad_target.py``) or
+  that a hook copies it into — autograd never accumulates (no add pass, no bucket copy-in/copy-out);
 * when the last gradient of a bucket has been produced, ONE kernel on a side stream
   reduces the bucket in the switch (NVLS), applies SGD+momentum+weight-decay on the owning
   rank's fp32 master shard, writes the new bf16 parameters to every rank and re-zeroes the
@@ -119,12 +119,31 @@ class BnetDDP(torch.nn.Module):
                 return seg.view(n, h, w, c).permute(0, 3, 1, 2)
             return seg.view(p.shape)
 
+        # Gradients: every parameter owns a slice of the flat gradient buffer the fused kernels read.  p.grad stays None
+        # between steps, so autograd ADOPTS what a backward function hands it instead of adding it into an existing
+        # tensor (an add is three passes over the parameter's bytes; with 138 M parameters that was 32 kernels and 5 % of
+        # a VGG16 step).  Producers that can write anywhere look the slice up (ops/grad_target.py) and write straight
+        # into it; whatever arrives in a tensor of its own is copied there by the hook below.
+        # BNET_DIRECT_GRADS=0 brings the accumulate-into-a-view behaviour back (p.grad = the slice, autograd adds into it).
+        import os
+
+        from ..ops import grad_target
+
+        self._direct_grads = os.environ.get("BNET_DIRECT_GRADS", "1") != "0"
+        self._release = grad_target.release
+        self._grad_view: dict[int, torch.Tensor] = {}
         with torch.no_grad():
             for p, b, off in layout:
                 view = shaped(self.flat_param, off, p)
                 view.copy_(p.data)
                 p.data = view
-                p.grad = shaped(self.flat_grad, off, p)
+                gview = shaped(self.flat_grad, off, p)
+                self._grad_view[id(p)] = gview
+                if self._direct_grads:
+                    grad_target.register(p, gview, owner=self)
+                    p.grad = None
+                else:
+                    p.grad = gview
         self._param_bucket = {id(p): b for p, b, _ in layout}
         # identical start on every rank (like DDP's initial broadcast): rank 0 wins, through our own all-reduce
         if comm.world > 1:
@@ -142,6 +161,7 @@ class BnetDDP(torch.nn.Module):
             b.master = b.param[comm.rank * shard:(comm.rank + 1) * shard].float().contiguous()
             b.mom = torch.zeros_like(b.master)
         self.comm_stream = torch.cuda.Stream(device=dev, priority=-1)
+        self.grad_copies = 0             # gradients that had to be copied into their slice (not written there by their producer)
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in params]
         self._inflight = False
         torch.cuda.synchronize()
@@ -150,6 +170,14 @@ class BnetDDP(torch.nn.Module):
 
     # ------------------------------------------------------------------ autograd integration
     def _on_grad(self, p: torch.Tensor):
+        g = p.grad
+        if g is not None and self._direct_grads:
+            view = self._grad_view[id(p)]
+            if g.data_ptr() != view.data_ptr() or g.stride() != view.stride():
+                view.copy_(g)                     # produced in a tensor of its own: put it where the fused kernel reads
+                self.grad_copies += 1
+            p.grad = None                         # (the slice is zeroed by the fused kernel; the next backward adopts again)
+            self._release(p)                      # its slice may be handed to a producer again (ops/grad_target.py)
         b = self._param_bucket[id(p)]
         b.ready += 1
         if b.ready == len(b.params):

@@ -401,9 +401,13 @@ def test_conv_backward_composes_tcgen05_and_library_gradients(monkeypatch):
         calls.append("tc_dgrad")
         return torch.ops.aten.convolution_backward(g, x, ww, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [True, False, False])[0]
 
-    def fake_wgrad(g, xx, splits=0):
+    def fake_wgrad(g, xx, splits=0, out=None):
         calls.append("tc_wgrad")
-        return torch.ops.aten.convolution_backward(g, xx, w, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [False, True, False])[1]
+        r = torch.ops.aten.convolution_backward(g, xx, w, None, [1, 1], [1, 1], [1, 1], False, [0, 0], 1, [False, True, False])[1]
+        if out is not None:
+            out.copy_(r)
+            return out
+        return r
 
     monkeypatch.setattr(tc_conv, "conv3x3_dgrad", fake_dgrad)
     monkeypatch.setattr(tc_conv, "conv3x3_wgrad", fake_wgrad)
@@ -418,6 +422,19 @@ def test_conv_backward_composes_tcgen05_and_library_gradients(monkeypatch):
                 assert (gx is None) if not need_x else torch.equal(gx, ref_x), (pick_x, pick_w, need_x)
                 assert calls.count("tc_dgrad") == (1 if (need_x and pick_x == "tc") else 0), (calls, pick_x, pick_w, need_x)
                 assert calls.count("tc_wgrad") == (1 if pick_w == "tc" else 0), (calls, pick_x, pick_w, need_x)
+    # an engine registered a gradient slice for this filter: the kernel writes there, autograd gets a tensor over that memory
+    from bagua_net_b200.ops import grad_target
+
+    slot = torch.zeros(w.numel() + 8, dtype=torch.bfloat16)
+    off = (-slot.data_ptr() // 2) % 8                                   # 16-byte aligned start inside the buffer
+    dst = slot[off:off + w.numel()].view(16, 3, 3, 8).permute(0, 3, 1, 2)   # channels_last like the filter
+    grad_target.register(w, dst)
+    monkeypatch.setattr(tc_conv, "choose", lambda *a, **k: "cudnn")
+    monkeypatch.setattr(tc_conv, "choose_wgrad", lambda *a, **k: "tc")
+    gx, gw = fused_nn._conv_backward(gz, x, w, [1, 1], [1, 1], True)
+    assert gw.data_ptr() == dst.data_ptr() and gw is not dst and torch.equal(gw, ref_w) and torch.equal(dst, ref_w)
+    grad_target.unregister(w)
+    assert grad_target.lookup(w) is None
     # anything but 3x3 / stride 1 / pad 1 never reaches the autotuner
     monkeypatch.setattr(tc_conv, "choose", lambda *a, **k: (_ for _ in ()).throw(AssertionError("asked")))
     monkeypatch.setattr(tc_conv, "choose_wgrad", lambda *a, **k: (_ for _ in ()).throw(AssertionError("asked")))
