@@ -780,6 +780,18 @@ def main() -> int:
                 res.pop("log_path", None)
                 extra["nccl_collnet"] = res
 
+    # ---- N = 1: where does the step go?  (tools/step_profile.py in a child: torch.profiler over eager steps of the same model;
+    #      kernel names, launches and time per step — explains the number above, is not a bench value)
+    if (args.comm == "bnet" and world == 1 and args.model == "vgg16" and not args.no_arms and not args.no_resnet
+            and not os.environ.get("BNET_BENCH_CHILD")):
+        note("step profile: child process (timeout 90 s)")
+        res = run_child_arm("profile", args, rank, world, 140, 90.0, tag="_step",      # (same model: the kernels' verdicts are cached)
+                            script=[os.path.join(ROOT, "tools", "step_profile.py"), "--fused", "--batch", str(args.batch), "--steps", "4"])
+        note(f"step profile: {res.get('status') if res else None}")
+        if res is not None:
+            res.pop("log_path", None)
+            extra["step_profile"] = res
+
     # ---- BASELINE config #4: the same three arms on ResNet-50 (child processes, short, under an overall deadline) ----
     # The headline stays VGG16 (the model the reference quotes its speed-up on); the reference's README benchmarks
     # ResNet-50 the same way (reference README.md:52-84), so the run reports it next to the headline while the GPUs are here.

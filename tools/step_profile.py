@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--out", default="")
     ap.add_argument("--fused", action="store_true", help="fused conv blocks (bnet arm default in bench.py)")
+    ap.add_argument("--json", default="", help="also write the top kernels as one JSON object (bench.py: extra.step_profile)")
     a = ap.parse_args()
     torch.cuda.set_device(0)
     torch.backends.cudnn.benchmark = True
@@ -70,6 +71,18 @@ def main():
     if a.out:
         os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
         open(a.out, "w").write(txt + "\n")
+    if a.json:
+        import json
+
+        top = [{"kernel": name[:64], "ms_per_step": round(t / 1e3 / a.steps, 3), "launches_per_step": round(n / a.steps, 1),
+                "share": round(t / busy, 3)} for name, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:16]]
+        ours = sum(t for name, (n, t) in agg.items() if "bnet" in name or "tc_linear_kernel" in name) / busy if busy else 0.0
+        obj = {"note": "torch.profiler (CUPTI) over eager steps, no CUDA graph: explains the step, is not a bench value",
+               "model": a.model, "batch": a.batch, "fused": bool(a.fused), "step_ms_under_profiler": round(wall_ms, 3),
+               "kernel_ms_per_step": round(busy_ms, 3), "share_of_kernel_time_in_our_kernels": round(ours, 3), "top_kernels": top}
+        with open(a.json + ".tmp", "w") as f:
+            f.write(json.dumps(obj))
+        os.replace(a.json + ".tmp", a.json)
 
 
 if __name__ == "__main__":
