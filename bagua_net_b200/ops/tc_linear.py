@@ -301,12 +301,18 @@ def _isolated_self_check(timeout: float = 180.0, check: str | None = None, tag: 
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):     # the child is a plain 1-GPU process
         env.pop(k, None)
     body = check or "from bagua_net_b200.ops import tc_linear; ok = tc_linear.self_check()"
-    code = "import sys, torch; torch.cuda.set_device(%d); %s; sys.exit(0 if ok else 1)" % (torch.cuda.current_device(), body)
+    code = "import sys, torch; torch.cuda.set_device(%d); %s; sys.exit(0 if ok else 3)" % (torch.cuda.current_device(), body)
     try:
-        ok = subprocess.run([sys.executable, "-c", code], env=env, timeout=timeout, stdout=subprocess.DEVNULL,
-                            stderr=subprocess.DEVNULL).returncode == 0
-    except Exception:  # noqa: BLE001 — timeout, spawn failure: not trusted
-        ok = False
+        rc = subprocess.run([sys.executable, "-c", code], env=env, timeout=timeout, stdout=subprocess.DEVNULL,
+                            stderr=subprocess.DEVNULL).returncode
+    except Exception:  # noqa: BLE001 — timeout, spawn failure
+        rc = None
+    # exit 0 / 3: the check ran and passed / failed; death by a signal: a faulting kernel — all definitive, cached.  Anything
+    # else (timeout under a profiler, no GPU for the child, an import problem) is no verdict: not trusted now, asked again
+    # next time
+    if rc is None or (rc > 0 and rc != 3):
+        return False
+    ok = rc == 0
     try:
         os.makedirs(cache_dir, exist_ok=True)
         tmp = f"{path}.{os.getpid()}"

@@ -328,11 +328,30 @@ def test_tc_self_check_runs_isolated_and_is_cached(monkeypatch, tmp_path):
     monkeypatch.setenv("BNET_CACHE_DIR", str(tmp_path))
     monkeypatch.setattr(torch.cuda, "get_device_name", lambda *a: "Fake B200")
     monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
-    assert tc_linear._isolated_self_check(timeout=120) is False        # no GPU in the child either: a clean "no"
-    files = glob.glob(str(tmp_path / "tc_self_check_*.json"))
-    assert len(files) == 1 and json.load(open(files[0]))["ok"] is False
-    json.dump({"ok": True}, open(files[0], "w"))                        # a cached verdict is honoured without a child
-    assert tc_linear._isolated_self_check(timeout=0.001) is True
+    assert tc_linear._isolated_self_check(timeout=120) is False        # no GPU in the child either: no verdict, nothing cached
+    assert not glob.glob(str(tmp_path / "tc_self_check_*.json"))
+    assert tc_linear._isolated_self_check(timeout=0.001) is False      # (a timeout — e.g. under a profiler — is no verdict either)
+    # definitive outcomes are cached: the check ran and failed (exit 3), passed (exit 0), or the child died by a signal
+    failing = "import sys; sys.exit(3)"
+    import subprocess as sp
+    import types
+
+    calls = []
+
+    def fake_run(cmd, **kw):
+        calls.append(cmd[-1])
+        return types.SimpleNamespace(returncode=fake_run.rc)
+
+    monkeypatch.setattr(sp, "run", fake_run)
+    for rc, want, cached in ((3, False, True), (-11, False, True), (1, False, False), (0, True, True)):
+        fake_run.rc = rc
+        tag = f"t_rc{abs(rc)}"
+        assert tc_linear._isolated_self_check(timeout=5, check=failing, tag=tag) is want
+        files = glob.glob(str(tmp_path / f"{tag}_*.json"))
+        assert (len(files) == 1 and json.load(open(files[0]))["ok"] is want) if cached else not files, (rc, files)
+    assert failing in calls[-1] and calls[-1].endswith("sys.exit(0 if ok else 3)")
+    n = len(calls)
+    assert tc_linear._isolated_self_check(timeout=5, check=failing, tag="t_rc0") is True and len(calls) == n   # cached: no child
 
 
 def test_tc_conv_wgrad_plan_and_gating(monkeypatch, tmp_path):
@@ -369,18 +388,25 @@ def test_tc_conv_wgrad_plan_and_gating(monkeypatch, tmp_path):
     monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
     monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)
     monkeypatch.delenv("BNET_TC_WGRAD_BN", raising=False)
-    assert tc_conv.wgrad_trusted() is False                          # the child has no GPU either: a clean "no", cached
-    files = glob.glob(str(tmp_path / "tc_wgrad_self_check_*.json"))
-    assert len(files) == 1 and json.load(open(files[0]))["ok"] is False
-    # ... after the fallback ladder tried 128-column tiles for every layer in a second child (its own verdict file)
-    files128 = glob.glob(str(tmp_path / "tc_wgrad_bn128_self_check_*.json"))
-    assert len(files128) == 1 and json.load(open(files128[0]))["ok"] is False and "BNET_TC_WGRAD_BN" not in os.environ
-    json.dump({"ok": True}, open(files128[0], "w"))                  # "only the 128-column configuration passed on this GPU"
+    assert tc_conv.wgrad_trusted() is False                          # the child has no GPU either: not trusted, nothing cached
+    assert not glob.glob(str(tmp_path / "tc_wgrad_*self_check_*.json")) and "BNET_TC_WGRAD_BN" not in os.environ
+    # verdict files as a GPU box would leave them: the default plan failed its check, the 128-column ladder step passed
+    import hashlib
+
+    import bagua_net_b200
+
+    lib = os.path.join(bagua_net_b200.LIB_DIR, bagua_net_b200.LIB_NAME)
+    key = f"{os.path.getmtime(lib):.0f}-{os.path.getsize(lib)}-Fake B200-{torch.version.cuda}"
+    h = hashlib.sha1(key.encode()).hexdigest()[:16]
+    json.dump({"ok": False}, open(tmp_path / f"tc_wgrad_self_check_{h}.json", "w"))
+    json.dump({"ok": True}, open(tmp_path / f"tc_wgrad_bn128_self_check_{h}.json", "w"))
     monkeypatch.setattr(tc_conv, "_wgrad_trusted", None)
     assert tc_conv.wgrad_trusted() is True and os.environ.get("BNET_TC_WGRAD_BN") == "128"
     monkeypatch.delenv("BNET_TC_WGRAD_BN", raising=False)
+    json.dump({"ok": False}, open(tmp_path / f"tc_wgrad_bn128_self_check_{h}.json", "w"))
+    monkeypatch.setattr(tc_conv, "_wgrad_trusted", None)
+    assert tc_conv.wgrad_trusted() is False and "BNET_TC_WGRAD_BN" not in os.environ
     assert not glob.glob(str(tmp_path / "tc_self_check_*.json"))     # (the linear kernel's verdict is a different file)
-    assert tc_linear._isolated_self_check(timeout=0.001, check="ok = True", tag="tc_wgrad_self_check") is False   # cached verdict wins
 
 
 def test_conv_backward_composes_tcgen05_and_library_gradients(monkeypatch):
