@@ -58,9 +58,10 @@ for recipe in "$@"; do
     TAILN=15 step pytest_gpu 1500 python -m pytest tests -m gpu -x -q
     step smoke 300 python -c "import __graft_entry__ as g; g.smoke()" ;;
   bench)
+    # (N > 1: the run also spawns the DDP arms, the transport-collective child, the CollNet probe and the ResNet arms: ~4 min at 8 GPUs)
     export BNET_BENCH_STACKS=${BNET_BENCH_STACKS:-140} BNET_BENCH_LOG_DIR=$PWD/$OUT/arms
     if [ "$NG" = 1 ]; then TAILN=3 CUT=4000 step bench 400 python bench.py --steps 20 --warmup 5
-    else TAILN=14 CUT=4000 step bench 500 $TR --master-port 29634 bench.py --gpus $NG --steps 20 --warmup 5 --arm-timeout ${ARM_TMO:-150}; fi
+    else TAILN=14 CUT=6000 step bench 700 $TR --master-port 29634 bench.py --gpus $NG --steps 20 --warmup 5 --arm-timeout ${ARM_TMO:-150}; fi
     unset BNET_BENCH_STACKS ;;
   resnet)
     if [ "$NG" = 1 ]; then TAILN=3 CUT=4000 step bench_resnet50 400 python bench.py --steps 20 --warmup 5 --model resnet50
@@ -101,7 +102,10 @@ for recipe in "$@"; do
     TAILN=20 step tc_linear_bench 300 python tools/tc_linear_bench.py
     TAILN=24 step tc_conv_bench 300 python tools/tc_conv_bench.py --wgrad
     step ncu_tc 400 ncu --set full --clock-control none --import-source on -k "regex:tc_linear_kernel" -c 4 -f -o $OUT/tc_linear \
-      python tools/tc_linear_bench.py --iters 1 --warmup 0 --shapes 4096x4096x4096,32x4096x25088 ;;
+      python tools/tc_linear_bench.py --iters 1 --warmup 0 --shapes 4096x4096x4096,32x4096x25088
+    # the convolution kernels at the conv4 shape: launch 0 = forward, 1 = input gradient, 2.. = filter gradient (BNET_TC_WGRAD=1: no child check)
+    step ncu_tc_conv 300 env BNET_TC_WGRAD=1 ncu --set full --clock-control none --import-source on -k regex:tc_linear_kernel -c 4 -f -o $OUT/tc_conv \
+      python tools/tc_conv_bench.py --wgrad --iters 1 --shapes 512x512x28 ;;
   kernels)
     TAILN=12 step nn_kernel_bench 200 python tools/nn_kernel_bench.py
     step ncu_nn 400 ncu --set full --clock-control none --import-source on -k "regex:relu_bwd_bias_grad|pool_relu_bwd" -c 6 -f -o $OUT/nn_bwd \
