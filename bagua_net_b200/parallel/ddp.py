@@ -256,11 +256,13 @@ class BnetDDP(torch.nn.Module):
         torch.cuda.synchronize()
         if self.comm.world > 1:
             dist.barrier()
-        l0, f0 = self.comm.launches, fused_nn.LAUNCHES
+        from ..ops import tc_linear
+
+        l0, f0, t0 = self.comm.launches, fused_nn.LAUNCHES, tc_linear.LAUNCHES
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self._gloss = self._eager_step(self._gx, self._gy, loss_fn)
-        self._graph_launches = (self.comm.launches - l0, fused_nn.LAUNCHES - f0)
+        self._graph_launches = (self.comm.launches - l0, fused_nn.LAUNCHES - f0, tc_linear.LAUNCHES - t0)
         self._graph, self._graph_key = g, key
         torch.cuda.synchronize()
         if self.comm.world > 1:
@@ -285,6 +287,10 @@ class BnetDDP(torch.nn.Module):
         self._graph.replay()
         self.comm.launches += self._graph_launches[0]      # the replay re-issues every captured kernel of ours
         fused_nn.LAUNCHES += self._graph_launches[1]
+        if self._graph_launches[2]:
+            from ..ops import tc_linear
+
+            tc_linear.LAUNCHES += self._graph_launches[2]  # (tcgen05 linear / convolution kernels captured in the step)
         return self._gloss
 
     def train_step_from_host(self, inputs_pinned: torch.Tensor, targets_pinned: torch.Tensor, loss_fn=None) -> float:
