@@ -850,6 +850,15 @@ def main() -> int:
             "clocks": clocks, "gpu_launches": nlaunch, "wall_ms_per_step": round(wall_total / args.steps, 3),
             "param_checksum": checksum,
         }
+        if args.comm == "bnet":
+            # how the gradients reached the flat buffer the fused kernels read: adopted in place (written there by their
+            # producer) or copied in by the hook; counted over the eager / captured passes (graph replays repeat the captured one)
+            try:
+                npar = sum(1 for p_ in model.parameters() if p_.requires_grad)
+                out["config"]["gradient_path"] = {"mode": "adopt" if getattr(engine, "_direct_grads", False) else "accumulate",
+                                                  "parameters": npar, "copies_in_eager_and_captured_passes": int(engine.grad_copies)}
+            except Exception:   # noqa: BLE001 - reporting only
+                pass
         try:
             # what the per-shape autotuner measured on THIS GPU (tcgen05 kernel vs cuDNN, us) and which one the step runs
             from bagua_net_b200.ops import tc_conv
