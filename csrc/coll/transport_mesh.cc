@@ -33,6 +33,7 @@
 
 #include <vector>
 
+#include "core/telemetry.h"
 #include "cuda/cuda_iface.h"
 #include "cuda/exec_ops.h"
 #include "cuda/nvl_exec.h"
@@ -53,6 +54,7 @@ struct BnetTMesh {
   volatile uint64_t* jflags = nullptr;   // completion words of the local pass
   uint64_t* jflags_dev = nullptr;
   uint64_t jseq = 0;
+  uint64_t op_seq = 0;              // all-reduces started on this mesh (span ids)
   MeshOp* active = nullptr;         // one operation at a time (FIFO matching per connection)
   char err[256] = {0};
   uint64_t last_msgs = 0, last_bytes_sent = 0;
@@ -108,6 +110,8 @@ struct MeshOp {
   int inflight = 8;
   int timeout_ms = 0;
   uint64_t t0 = 0;
+  uint64_t span = 0;          // "coll-<rank>" span around the whole operation (its isend / irecv spans fall inside it)
+  uint64_t out_bytes = 0;
 };
 
 BnetTMesh* tmesh_new(ListenComm* listen, int rank, int world, int net_dev) {
@@ -314,6 +318,8 @@ MeshOp* tmesh_op_start(BnetTMesh* m, int algo, const void* in, MeshMr* in_mr, vo
   }
   m->last_msgs = 0;
   m->last_bytes_sent = 0;
+  op->out_bytes = (uint64_t)count * oes;
+  op->span = Telemetry::get().span_begin(SPAN_COLL, (uint64_t)m->rank, ++m->op_seq, op->out_bytes);
   // ---- the local pass: out <- in over [i0, i1), finished before any receive is posted (nobody adds into garbage)
   op->stage = 1;
   if (!in_place && i1 > i0) {
@@ -321,7 +327,7 @@ MeshOp* tmesh_op_start(BnetTMesh* m, int algo, const void* in, MeshMr* in_mr, vo
     if (cuda::exec_transfer(cuda_dev, init_op, 1.0f, src + i0 * ies, dst + i0 * oes, (i1 - i0) * ies, m->jflags, m->jflags_dev,
                             op->init_value, &op->init_chunks) != 0) {
       fail(m, "the local initialisation pass failed");
-      delete op;
+      tmesh_op_free(op);
       return nullptr;
     }
     op->stage = 0;
@@ -393,6 +399,8 @@ int tmesh_op_step(MeshOp* op) {
   }
   if (op->remaining == 0) {
     op->stage = 2;
+    if (op->span) Telemetry::get().span_end(op->span, op->out_bytes);
+    op->span = 0;
     return 1;
   }
   if (!moved && expired) {
@@ -404,6 +412,7 @@ int tmesh_op_step(MeshOp* op) {
 
 void tmesh_op_free(MeshOp* op) {
   if (!op) return;
+  if (op->span) Telemetry::get().span_end(op->span, 0);       // (failed or abandoned: closed with 0 bytes)
   if (op->m && op->m->active == op) op->m->active = nullptr;
   delete op;
 }

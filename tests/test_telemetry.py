@@ -219,3 +219,33 @@ def test_otlp_http_json_export():
     kids = [sp for sp in spans if sp["name"].startswith(("isend-", "irecv-"))]
     assert len(kids) == 16 and all(len(sp["parentSpanId"]) == 16 for sp in kids)     # 8 sends + 8 receives
     assert len({(sp["traceId"], sp["spanId"]) for sp in kids}) == 16                   # every span exactly once
+
+
+def test_collectives_over_the_mesh_are_spans_around_their_messages(tmp_path):
+    """An all-reduce over the mesh of plugin connections opens a "coll-<rank>" span (its bytes as an attribute); the isend /
+    irecv spans of its messages fall inside it in the exported trace."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    world, count = 3, 40000
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, BNET_FAKE_CUDA="1", BNET_NVL="1", RANK=str(r), BNET_TRACE_FILE=str(tmp_path / f"trace{r}.json"),
+                   PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(root, "tests", "tmesh_worker.py"), str(r), str(world), str(tmp_path),
+                                       str(count), "f32", "f32", "16384", "4", "2", "two-shot", "0"], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.PIPE, text=True))
+    for p in procs:
+        o, e = p.communicate(timeout=180)
+        assert p.returncode == 0, e[-2000:]
+        assert json.loads([ln for ln in o.splitlines() if ln.startswith("{")][-1])["ok"]
+    for r in range(world):
+        tr = json.loads((tmp_path / f"trace{r}.json").read_text())
+        colls = [e for e in tr["traceEvents"] if e["name"] == f"coll-{r}"]
+        assert len(colls) == 2 and all(e["args"]["nbytes"] == count * 4 for e in colls), colls        # two rounds
+        msgs = [e for e in tr["traceEvents"] if e["name"].startswith(("isend-", "irecv-")) and e["args"]["nbytes"] > 4]
+        assert msgs
+        lo, hi = min(c["ts"] for c in colls), max(c["ts"] + c["dur"] for c in colls)
+        assert all(lo <= e["ts"] and e["ts"] + e["dur"] <= hi + 1 for e in msgs), "a message span lies outside the collectives"
