@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "core/engine.h"
+#include "core/telemetry.h"
 #include "cuda/cuda_iface.h"
 #include "cuda/exec_ops.h"
 #include "cuda/nvl_exec.h"
@@ -52,6 +53,7 @@ struct BnetTRing {
   volatile uint64_t* jflags = nullptr;
   uint64_t* jflags_dev = nullptr;
   uint64_t jseq = 0;
+  uint64_t op_seq = 0;             // all-reduces started on this ring (span ids)
 };
 
 namespace {
@@ -64,6 +66,15 @@ int fail(BnetTRing* r, const char* fmt, ...) {
   BNET_WARN("transport ring: %s", r->err);
   return -1;
 }
+
+// "coll-<rank>" span around one all-reduce (the isend / irecv spans of its messages fall inside it); closed with the byte
+// count on success, with 0 when the call leaves early
+struct CollSpan {
+  uint64_t id, bytes;
+  bool ok = false;
+  CollSpan(int rank, uint64_t seq, uint64_t nbytes) : id(Telemetry::get().span_begin(SPAN_COLL, (uint64_t)rank, seq, nbytes)), bytes(nbytes) {}
+  ~CollSpan() { if (id) Telemetry::get().span_end(id, ok ? bytes : 0); }
+};
 }  // namespace
 
 BNET_API const char* bnet_tring_last_error(BnetTRing* r) { return r ? r->err : "null ring"; }
@@ -160,6 +171,7 @@ BNET_API int bnet_tring_allreduce(BnetTRing* r, void* buf, size_t count, int dty
   r->last_msgs = 0;
   r->last_bytes_sent = 0;
   const uint64_t t0 = now_ns();
+  CollSpan span(r->rank, ++r->op_seq, total);
   while (done_r < M || done_s < M) {
     bool moved = false;
     // receives: posted in message order (the transport matches strictly FIFO per connection)
@@ -213,6 +225,7 @@ BNET_API int bnet_tring_allreduce(BnetTRing* r, void* buf, size_t count, int dty
     if (!moved && timeout_ms > 0 && now_ns() - t0 > (uint64_t)timeout_ms * 1000000ull)
       return fail(r, "all-reduce timed out: %zu/%zu receives, %zu/%zu sends done", done_r, M, done_s, M);
   }
+  span.ok = true;
   return 0;
 }
 
@@ -341,6 +354,7 @@ BNET_API int bnet_tring_allreduce_compressed(BnetTRing* r, void* buf, size_t cou
   r->last_msgs = 0;
   r->last_bytes_sent = 0;
   const uint64_t t0 = now_ns();
+  CollSpan span(r->rank, ++r->op_seq, (uint64_t)count * 4);
   auto submit = [&](uint32_t op, float sc, const void* src, void* dst, size_t src_bytes, LocalJob* j) -> int {
     if (src_bytes == 0) { j->slot = -1; return 0; }
     if (free_slots.empty()) return 1;                                   // try again later
@@ -473,6 +487,7 @@ BNET_API int bnet_tring_allreduce_compressed(BnetTRing* r, void* buf, size_t cou
     if (!moved && timeout_ms > 0 && now_ns() - t0 > (uint64_t)timeout_ms * 1000000ull)
       return fail(r, "compressed all-reduce timed out: %zu/%zu receives ready, %zu/%zu sends done", ready_r, M, done_s, M);
   }
+  span.ok = true;
   return 0;
 }
 
