@@ -409,6 +409,12 @@ def test_tc_conv_wgrad_plan_and_gating(monkeypatch, tmp_path):
     assert not glob.glob(str(tmp_path / "tc_self_check_*.json"))     # (the linear kernel's verdict is a different file)
 
 
+# pure-PyTorch tests (no native code of ours involved): skipped under ThreadSanitizer, whose runtime reports races inside
+# libtorch's own OpenMP convolution kernels (uninstrumented libgomp) — ci/run_sanitizers.sh is about OUR host engine
+no_tsan = pytest.mark.skipif("tsan" in os.environ.get("LD_PRELOAD", ""), reason="libtorch CPU kernels under ThreadSanitizer")
+
+
+@no_tsan
 def test_conv_backward_composes_tcgen05_and_library_gradients(monkeypatch):
     """fused_nn._conv_backward asks the autotuner per gradient (input / filter) and per shape; whatever mix it answers, the
     pair that comes back must be the convolution's gradients, and a gradient nobody asked for is not computed."""
@@ -485,6 +491,7 @@ def test_wgrad_self_check_can_be_given_the_callers_shapes(monkeypatch):
     assert tc_conv._extra_check_shapes()[1] != sfx                     # another shape list, another verdict file
 
 
+@no_tsan
 def test_wgrad_self_check_body_runs(monkeypatch):
     """The child-process self-check of the filter gradient is what decides whether the kernel is ever used: its own Python
     must not be what fails.  Run its body on the CPU with the kernel replaced by the library's result (and by a wrong one)."""
