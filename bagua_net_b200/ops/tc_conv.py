@@ -162,6 +162,10 @@ def conv3x3_wgrad(gy: torch.Tensor, x: torch.Tensor, splits: int = 0, out: torch
                                  splits, tc_linear._err_flag(gy.device.index).data_ptr(), tc_linear._stream())
     if rc < 0:
         raise RuntimeError(f"bnet_tc_conv3x3_wgrad: {L.bnet_tc_last_error().decode()}")
+    if os.environ.get("BNET_TC_WGRAD_FIXUP", "1") == "0":
+        # fall-back mode (the self-check's ladder): the kernel only added its slices' sums into the fp32 workspace
+        dw.copy_(ws.view(cout, 3, 3, cin).permute(0, 3, 1, 2))
+        ws.zero_()
     LAUNCHES += rc
     tc_linear.LAUNCHES += rc
     return dw
@@ -205,16 +209,23 @@ def wgrad_trusted() -> bool:
             # flagship's) are checked in the child as well, so that a shape-dependent fault cannot happen in this process
             extra, sfx = _extra_check_shapes()
             check = f"from bagua_net_b200.ops import tc_conv; ok = tc_conv.self_check_wgrad(shapes=tc_conv.WGRAD_CHECK_SHAPES + {extra!r})"
-            _wgrad_trusted = tc_linear._isolated_self_check(check=check, tag="tc_wgrad_self_check" + sfx)
-            if not _wgrad_trusted and "BNET_TC_WGRAD_BN" not in os.environ:
-                # Fallback ladder: the 256-column tiles are the one building block of this kernel that no validated kernel
-                # shares (the linear dW ran its MN-major column operand with 128-column tiles on hardware).  If only they
-                # are at fault, every layer can still run on 128-column tiles.  The library reads the variable at its first
-                # filter-gradient launch, which cannot have happened yet in this process.
-                os.environ["BNET_TC_WGRAD_BN"] = "128"
-                _wgrad_trusted = tc_linear._isolated_self_check(check=check, tag="tc_wgrad_bn128_self_check" + sfx)
-                if not _wgrad_trusted:
-                    del os.environ["BNET_TC_WGRAD_BN"]
+            # Fallback ladder.  Two building blocks of this kernel are shared with no hardware-validated kernel: the 256-column
+            # MN-major column operand (the linear dW ran 128-column tiles) and the in-kernel finish of the split reduction in
+            # this orientation (the linear layer's ran with swapped operands).  If the default configuration fails its check,
+            # the configurations without one or both of them are tried; the library reads the variables at its first
+            # filter-gradient launch, which cannot have happened yet in this process.
+            ladder = ({}, {"BNET_TC_WGRAD_BN": "128"}, {"BNET_TC_WGRAD_FIXUP": "0"}, {"BNET_TC_WGRAD_BN": "128", "BNET_TC_WGRAD_FIXUP": "0"})
+            preset = any(k in os.environ for k in ("BNET_TC_WGRAD_BN", "BNET_TC_WGRAD_FIXUP"))
+            _wgrad_trusted = False
+            for cfg in (ladder[:1] if preset else ladder):
+                os.environ.update(cfg)
+                tag = ("tc_wgrad" + ("_bn128" if os.environ.get("BNET_TC_WGRAD_BN") == "128" else "")
+                       + ("_nofix" if os.environ.get("BNET_TC_WGRAD_FIXUP") == "0" else ""))
+                if tc_linear._isolated_self_check(check=check, tag=tag + "_self_check" + sfx):
+                    _wgrad_trusted = True
+                    break
+                for k in cfg:
+                    os.environ.pop(k, None)
     return _wgrad_trusted
 
 

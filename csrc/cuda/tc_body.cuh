@@ -411,8 +411,11 @@ struct WgradProblem {
 // left all zero.  splits <= 0: as many K slices as fill the SMs.  Pure: no CUDA calls.
 inline int wgrad_max_tiles(int Cin, int Cout) { return ((Cout + kBM - 1) / kBM) * ((9 * Cin + 127) / 128); }
 
+// fixup == 0: plain reduce mode — the slices only ADD into `ws` (fp32 [Cout][9 Cin], zero on entry) and the caller converts
+// it to bf16 and clears it afterwards (two small passes); the fall-back when the in-kernel finish cannot be trusted.
 inline const char* setup_conv_wgrad(const void* gy, const void* x, float* ws, void* dw, int* counters, int N, int H, int W, int Cin,
-                                    int Cout, int splits, int* err_dev, int sm_count, WgradProblem* wp, int force_bn = 0) {
+                                    int Cout, int splits, int* err_dev, int sm_count, WgradProblem* wp, int force_bn = 0,
+                                    int fixup = 1) {
   if (N < 1 || H < 1 || W < 1 || Cin < 64 || Cin % 64 || Cout < 64 || Cout % 64)
     return "conv3x3 wgrad: input and output channels must be multiples of 64";
   if (!err_dev || !ws || !counters) return "conv3x3 wgrad needs err_dev, a workspace and tile counters";
@@ -469,8 +472,8 @@ inline const char* setup_conv_wgrad(const void* gy, const void* x, float* ws, vo
   a.outs[0] = ws;
   a.n_outs = 1;
   a.err = err_dev;
-  a.fix_out = dw;
-  a.fix_counters = counters;
+  a.fix_out = fixup ? dw : nullptr;
+  a.fix_counters = fixup ? counters : nullptr;
   a.fix_ldo = cols;
   wp->gy_map = MapDesc4{gy, Cout, W, H, N, g.bw, g.bh, g.bn};
   wp->x_map = MapDesc4{x, Cin, W, H, N, g.bw, g.bh, g.bn};

@@ -559,8 +559,10 @@ int run_conv_wgrad(const void* gy, const void* x, void* dw, float* ws, int* coun
   WgradProblem wp;
   // BNET_TC_WGRAD_BN=128: every layer on 128-column tiles (ops/tc_conv.py sets it when only that configuration passed the
   // self-check on the GPU at hand)
+  // BNET_TC_WGRAD_FIXUP=0: the slices only add into the fp32 workspace, the caller converts and clears it (ops/tc_conv.py)
   static const int force_bn = [] { const char* v = getenv("BNET_TC_WGRAD_BN"); return v ? atoi(v) : 0; }();
-  if (const char* e = setup_conv_wgrad(gy, x, ws, dw, counters, N, H, W, Cin, Cout, splits, err_dev, sm_count(), &wp, force_bn)) {
+  static const int fixup = [] { const char* v = getenv("BNET_TC_WGRAD_FIXUP"); return v ? atoi(v) : 1; }();
+  if (const char* e = setup_conv_wgrad(gy, x, ws, dw, counters, N, H, W, Cin, Cout, splits, err_dev, sm_count(), &wp, force_bn, fixup)) {
     g_err = e;
     return -1;
   }

@@ -411,7 +411,7 @@ static void run_wgrad_kernel(const WgradProblem& wp, const HostOut& out) {
             epilogue_chunk<false, true>(args, tc.a_row0 + r, tc.b_row0 + c * 16, acc, false, out);
           }
         // ... and the fix-up: the slice that arrives last at the tile reads the sums back, writes bf16, re-zeroes what it read
-        if (++counters[t] == p.grid_z) {
+        if (args.fix_out != nullptr && ++counters[t] == p.grid_z) {
           TcArgs fa = args;
           fa.outs[0] = args.fix_out;
           fa.ldo = args.fix_ldo;
@@ -439,7 +439,7 @@ static void run_wgrad_kernel(const WgradProblem& wp, const HostOut& out) {
   }
 }
 
-static void conv_wgrad(int N, int H, int W, int Cin, int Cout, int sms, int splits, int force_bn = 0) {
+static void conv_wgrad(int N, int H, int W, int Cin, int Cout, int sms, int splits, int force_bn = 0, int fixup = 1) {
   Mat gy(N * H * W, Cout), x(N * H * W, Cin);
   const int cols = 9 * Cin;
   std::vector<float> ws(size_t(Cout) * cols, 0.f);
@@ -449,7 +449,7 @@ static void conv_wgrad(int N, int H, int W, int Cin, int Cout, int sms, int spli
   while (reinterpret_cast<uintptr_t>(dw) & 15) dw++;
   int err = 0;
   WgradProblem wp;
-  const char* e = setup_conv_wgrad(gy.ptr(), x.ptr(), ws.data(), dw, counters.data(), N, H, W, Cin, Cout, splits, &err, sms, &wp, force_bn);
+  const char* e = setup_conv_wgrad(gy.ptr(), x.ptr(), ws.data(), dw, counters.data(), N, H, W, Cin, Cout, splits, &err, sms, &wp, force_bn, fixup);
   CHECK(e == nullptr, "wgrad setup: %s", e ? e : "");
   if (e) return;
   CHECK(force_bn == 0 || wp.plan.bn == force_bn, "forced tile width %d, plan has %d", force_bn, wp.plan.bn);
@@ -458,6 +458,8 @@ static void conv_wgrad(int N, int H, int W, int Cin, int Cout, int sms, int spli
         wp.plan.ctas, wp.plan.grid_z, sms);
   if (wp.plan.bn == 128) run_wgrad_kernel<128>(wp, HostOut{});
   else run_wgrad_kernel<256>(wp, HostOut{});
+  if (!fixup)            // what the caller does in that mode: convert the sums, clear the workspace
+    for (size_t i = 0; i < ws.size(); i++) { dw[i] = f32_to_bf16(ws[i]); ws[i] = 0.f; }
   int bad = 0;
   for (int co = 0; co < Cout; co++)
     for (int kh = 0; kh < 3; kh++)
@@ -495,6 +497,8 @@ int main() {
   conv_wgrad(1, 5, 3, 256, 128, 148, 0);
   conv_wgrad(2, 6, 10, 128, 256, 7, 0, 128);         // the self-check's fallback: 128-column tiles for every layer
   conv_wgrad(1, 5, 3, 256, 128, 148, 2, 128);
+  conv_wgrad(3, 7, 7, 64, 128, 4, 0, 0, 0);          // ... and without the in-kernel finish (the caller converts the workspace)
+  conv_wgrad(2, 6, 10, 128, 256, 7, 2, 128, 0);
   // forward / input gradient: exact patches, ragged patches (7x7, 14x14 with odd batch), several images per patch, persistent CTAs
   conv(2, 8, 16, 64, 64, true, 148);
   conv(3, 7, 7, 64, 128, false, 3);

@@ -388,6 +388,7 @@ def test_tc_conv_wgrad_plan_and_gating(monkeypatch, tmp_path):
     monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
     monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)
     monkeypatch.delenv("BNET_TC_WGRAD_BN", raising=False)
+    monkeypatch.delenv("BNET_TC_WGRAD_FIXUP", raising=False)
     assert tc_conv.wgrad_trusted() is False                          # the child has no GPU either: not trusted, nothing cached
     assert not glob.glob(str(tmp_path / "tc_wgrad_*self_check_*.json")) and "BNET_TC_WGRAD_BN" not in os.environ
     # verdict files as a GPU box would leave them: the default plan failed its check, the 128-column ladder step passed
@@ -403,9 +404,16 @@ def test_tc_conv_wgrad_plan_and_gating(monkeypatch, tmp_path):
     monkeypatch.setattr(tc_conv, "_wgrad_trusted", None)
     assert tc_conv.wgrad_trusted() is True and os.environ.get("BNET_TC_WGRAD_BN") == "128"
     monkeypatch.delenv("BNET_TC_WGRAD_BN", raising=False)
+    # further down the ladder: neither tile width passes with the in-kernel finish, the plain-reduce mode does
     json.dump({"ok": False}, open(tmp_path / f"tc_wgrad_bn128_self_check_{h}.json", "w"))
+    json.dump({"ok": True}, open(tmp_path / f"tc_wgrad_nofix_self_check_{h}.json", "w"))
     monkeypatch.setattr(tc_conv, "_wgrad_trusted", None)
-    assert tc_conv.wgrad_trusted() is False and "BNET_TC_WGRAD_BN" not in os.environ
+    assert tc_conv.wgrad_trusted() is True and os.environ.get("BNET_TC_WGRAD_FIXUP") == "0" and "BNET_TC_WGRAD_BN" not in os.environ
+    monkeypatch.delenv("BNET_TC_WGRAD_FIXUP", raising=False)
+    json.dump({"ok": False}, open(tmp_path / f"tc_wgrad_nofix_self_check_{h}.json", "w"))
+    json.dump({"ok": False}, open(tmp_path / f"tc_wgrad_bn128_nofix_self_check_{h}.json", "w"))
+    monkeypatch.setattr(tc_conv, "_wgrad_trusted", None)
+    assert tc_conv.wgrad_trusted() is False and "BNET_TC_WGRAD_BN" not in os.environ and "BNET_TC_WGRAD_FIXUP" not in os.environ
     assert not glob.glob(str(tmp_path / "tc_self_check_*.json"))     # (the linear kernel's verdict is a different file)
 
 
