@@ -475,6 +475,23 @@ def test_transport_mesh_twoshot_allreduce(world, count, idt, odt, piece, infligh
     assert all(o["stats"]["bytes_sent"] == (sum(sl) - sl[r]) * ies + (world - 1) * sl[r] * oes for r, o in enumerate(outs)), outs
 
 
+@pytest.mark.parametrize("seed", [11, 23, 37, 41, 59, 67])
+def test_transport_mesh_randomized(seed):
+    """Random world size, element count (including counts below one slice per rank), piece size, window, type pair,
+    algorithm and placement: the sums must be exact every time."""
+    import random
+
+    rng = random.Random(seed)
+    world = rng.choice([2, 3, 4, 5, 6, 7])
+    count = rng.choice([1, 63, 64, 65, 1000, 4097, 65536 + rng.randrange(0, 5000), rng.randrange(100000, 400000)])
+    algo = rng.choice(["one-shot", "two-shot"])
+    idt, odt = rng.choice([("f32", "f32"), ("bf16", "bf16"), ("bf16", "f32")])
+    inplace = algo == "two-shot" and idt == odt and rng.random() < 0.5
+    piece, inflight = rng.choice([4096, 8192, 65536, 1 << 20]), rng.choice([1, 2, 8, 32])
+    outs = _run_tmesh(world, count, idt, odt, piece, inflight, algo=algo, inplace=inplace)
+    assert all(o["ok"] for o in outs), (world, count, algo, idt, odt, inplace, piece, inflight, outs)
+
+
 @pytest.mark.parametrize("world,ver,count,dt,lib", [(2, 8, 70000, "f32", "-"), (4, 6, 5000, "bf16", "-"), (3, 10, 33, "f32", "libnccl-net-bnetx.so"),
                                                      (8, 8, 200000, "bf16", "-")])
 def test_collnet_table_allreduces_like_nccl_would_drive_it(world, ver, count, dt, lib):
