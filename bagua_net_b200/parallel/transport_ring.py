@@ -42,6 +42,7 @@ def _lib():
         lib.bnet_tmesh_create.argtypes = [i, i, i, vp, C.POINTER(vp)]
         lib.bnet_tmesh_connect.argtypes = [vp, vp, i]
         lib.bnet_tmesh_register.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t]
+        lib.bnet_tmesh_register2.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, i]
         lib.bnet_tmesh_allreduce.argtypes = [vp, vp, vp, C.c_size_t, i, i, C.c_size_t, i, i]
         lib.bnet_tmesh_allreduce2.argtypes = [vp, vp, vp, C.c_size_t, i, i, i, C.c_size_t, i, i]
         lib.bnet_tmesh_stats.argtypes = [vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
@@ -205,8 +206,11 @@ class MeshCore:
     def transport(self) -> str:
         return self.lib.bnet_tmesh_transport(self._h).decode()
 
-    def register(self, in_ptr: int, in_bytes: int, out_ptr: int, out_bytes: int):
-        if self.lib.bnet_tmesh_register(self._h, C.c_void_p(in_ptr), in_bytes, C.c_void_p(out_ptr), out_bytes) != 0:
+    def register(self, in_ptr: int, in_bytes: int, out_ptr: int, out_bytes: int, host_memory: bool = False):
+        """host_memory: the buffers are ordinary host memory — reduced with the two-shot schedule over any transport (TCP
+        between hosts included), the reduce-scatter pieces added on the host."""
+        if self.lib.bnet_tmesh_register2(self._h, C.c_void_p(in_ptr), in_bytes, C.c_void_p(out_ptr), out_bytes,
+                                         1 if host_memory else 2) != 0:
             raise RuntimeError(f"mesh register: {self._err()}")
 
     def all_reduce(self, in_ptr: int, out_ptr: int, count: int, in_dtype: int, out_dtype: int, piece_bytes: int = 1 << 20,

@@ -18,6 +18,12 @@
 //             owner's bits, so ranks agree exactly even for floats (the order INSIDE a slice's sum is still not fixed).
 //             In-place (in == out) is allowed.  This is the algorithm behind the CollNet table (csrc/plugin/collnet.cc).
 //
+//   HOST MODE  buffers registered as host memory (NCCL_PTR_HOST) are reduced with the two-shot schedule over ANY transport —
+//             multi-stream TCP between hosts, the same-host shared-memory ring: phase A pieces are plain isends into a
+//             per-connection staging area of the owner, which adds them into its slice on the host when they have arrived
+//             (no fused isend exists off NVLink); phase B is the same copy.  This is what the CollNet table runs when NCCL
+//             hands it host buffers (no GPUDirect), i.e. the all-reduce offload for the reference's own deployment.
+//
 // Messages are cut into pieces, `inflight` requests per connection and direction; strictly FIFO per connection (the
 // transport's matching rule), phase A before phase B.  The incoming connections carry no identity of their own, so the
 // first message on every connection is the sender's rank (4 bytes of host memory).
@@ -87,7 +93,35 @@ struct MeshMsg {
   uint32_t op;        // sends: ExecOp (0 = plain isend)
   MemHandle* mh;
   uint8_t phase;      // 0 = A, 1 = B (B sends wait for every A receive)
+  char* acc = nullptr;   // host mode, phase A receives: the piece landed in a staging area and is added into this place
 };
+
+// out[i] += in[i] on the host (the reduce-scatter of the host mode); dtype pairs as everywhere in this file
+void host_accumulate(char* out, const char* in, size_t in_bytes, int in_dtype, int out_dtype) {
+  if (in_dtype == 0) {
+    float* o = reinterpret_cast<float*>(out);
+    const float* a = reinterpret_cast<const float*>(in);
+    for (size_t i = 0, n = in_bytes / 4; i < n; i++) o[i] += a[i];
+    return;
+  }
+  const uint16_t* a = reinterpret_cast<const uint16_t*>(in);
+  auto widen = [](uint16_t v) { uint32_t u = (uint32_t)v << 16; float f; memcpy(&f, &u, 4); return f; };
+  const size_t n = in_bytes / 2;
+  if (out_dtype == 0) {
+    float* o = reinterpret_cast<float*>(out);
+    for (size_t i = 0; i < n; i++) o[i] += widen(a[i]);
+    return;
+  }
+  uint16_t* o = reinterpret_cast<uint16_t*>(out);
+  for (size_t i = 0; i < n; i++) {                     // bf16 += bf16: add in fp32, round to nearest even (like the device op)
+    float f = widen(o[i]) + widen(a[i]);
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) { o[i] = (uint16_t)((u >> 16) | 0x40); continue; }
+    u += 0x7fffu + ((u >> 16) & 1);
+    o[i] = (uint16_t)(u >> 16);
+  }
+}
 
 struct MeshSide {
   std::vector<MeshMsg> msgs;
@@ -112,6 +146,11 @@ struct MeshOp {
   uint64_t t0 = 0;
   uint64_t span = 0;          // "coll-<rank>" span around the whole operation (its isend / irecv spans fall inside it)
   uint64_t out_bytes = 0;
+  // host mode (buffers in host memory, any transport): no fused isend exists, so phase A pieces land in per-connection
+  // staging areas and are added into the own slice here, on the host; phase B is unchanged
+  bool host = false;
+  int in_dtype = 0, out_dtype = 0;
+  std::vector<std::vector<char>> staging;
 };
 
 BnetTMesh* tmesh_new(ListenComm* listen, int rank, int world, int net_dev) {
@@ -258,7 +297,13 @@ MeshOp* tmesh_op_start(BnetTMesh* m, int algo, const void* in, MeshMr* in_mr, vo
   if (in_place && (algo != MESH_TWO_SHOT || ies != oes)) { fail(m, "in-place needs the two-shot algorithm and equal types"); return nullptr; }
   if (!in_place && src < dst + count * oes && dst < src + count * ies) { fail(m, "input and output overlap"); return nullptr; }
   int cuda_dev = 0;
-  if (!cuda::fake() && (!cuda::available() || !cuda::pointer_is_device(out, &cuda_dev))) { fail(m, "buffers must be device memory"); return nullptr; }
+  const bool host = in_mr->type == NCCL_PTR_HOST && out_mr->type == NCCL_PTR_HOST;
+  if (in_mr->type != out_mr->type) { fail(m, "input and output must both be host memory or both be device memory"); return nullptr; }
+  if (host && algo != MESH_TWO_SHOT) { fail(m, "host memory is reduced with the two-shot algorithm only"); return nullptr; }
+  if (!host && !cuda::fake() && (!cuda::available() || !cuda::pointer_is_device(out, &cuda_dev))) {
+    fail(m, "buffers registered as device memory must be device memory");
+    return nullptr;
+  }
   const int n = m->world, nc = n - 1;
   size_t piece = piece_bytes / ies / 64 * 64;             // elements per message; keeps both sides vector aligned
   if (piece < 1024) piece = 1024;
@@ -273,6 +318,9 @@ MeshOp* tmesh_op_start(BnetTMesh* m, int algo, const void* in, MeshMr* in_mr, vo
   op->t0 = now_ns();
   op->rs.resize(nc);
   op->ss.resize(nc);
+  op->host = host;
+  op->in_dtype = in_dtype;
+  op->out_dtype = out_dtype;
   // pieces of the element range [e0, e1) appended to a side's message list
   auto cut = [&](MeshSide& side, char* base, size_t es, size_t e0, size_t e1, uint32_t xop, MemHandle* mh, uint8_t phase) {
     for (size_t a = e0; a < e1; a += piece) {
@@ -297,13 +345,25 @@ MeshOp* tmesh_op_start(BnetTMesh* m, int algo, const void* in, MeshMr* in_mr, vo
     slice(m->rank, &m0, &m1);
     i0 = m0;
     i1 = m1;
+    if (host) op->staging.assign(nc, std::vector<char>((m1 - m0) * ies + 64));
     for (int c = 0; c < nc; c++) {
       size_t q0, q1;
-      cut(op->rs[c], dst, oes, m0, m1, 0, out_mr->rmh[c], 0);               // A: contributions to my slice
+      if (!host) {
+        cut(op->rs[c], dst, oes, m0, m1, 0, out_mr->rmh[c], 0);             // A: contributions to my slice (added by the sender)
+      } else {
+        // A, host mode: the peer's share of my slice lands in this connection's staging area (plain bytes of the input
+        // type), piece by piece, and is added into out[slice] when it has arrived
+        for (size_t a = m0; a < m1; a += piece) {
+          const size_t b = a + piece < m1 ? a + piece : m1;
+          MeshMsg g{op->staging[c].data() + (a - m0) * ies, (b - a) * ies, 0, nullptr, 0};
+          g.acc = dst + a * oes;
+          op->rs[c].msgs.push_back(g);
+        }
+      }
       slice(m->recv_peer[c], &q0, &q1);
       cut(op->rs[c], dst, oes, q0, q1, 0, out_mr->rmh[c], 1);               // B: that peer's finished slice
       slice((m->rank + 1 + c) % n, &q0, &q1);
-      cut(op->ss[c], src, ies, q0, q1, add_op, in_mr->smh[c], 0);           // A: my contribution to the peer's slice
+      cut(op->ss[c], src, ies, q0, q1, host ? 0 : add_op, in_mr->smh[c], 0);   // A: my contribution to the peer's slice
       cut(op->ss[c], dst, oes, m0, m1, 0, out_mr->smh[c], 1);               // B: my finished slice
     }
   }
@@ -322,7 +382,14 @@ MeshOp* tmesh_op_start(BnetTMesh* m, int algo, const void* in, MeshMr* in_mr, vo
   op->span = Telemetry::get().span_begin(SPAN_COLL, (uint64_t)m->rank, ++m->op_seq, op->out_bytes);
   // ---- the local pass: out <- in over [i0, i1), finished before any receive is posted (nobody adds into garbage)
   op->stage = 1;
-  if (!in_place && i1 > i0) {
+  if (host && !in_place && i1 > i0) {
+    if (ies == oes) {
+      memcpy(dst + i0 * oes, src + i0 * ies, (i1 - i0) * ies);
+    } else {
+      memset(dst + i0 * oes, 0, (i1 - i0) * oes);
+      host_accumulate(dst + i0 * oes, src + i0 * ies, (i1 - i0) * ies, in_dtype, out_dtype);
+    }
+  } else if (!in_place && i1 > i0) {
     op->init_value = ++m->jseq;
     if (cuda::exec_transfer(cuda_dev, init_op, 1.0f, src + i0 * ies, dst + i0 * oes, (i1 - i0) * ies, m->jflags, m->jflags_dev,
                             op->init_value, &op->init_chunks) != 0) {
@@ -390,7 +457,10 @@ int tmesh_op_step(MeshOp* op) {
         if (done) {
           X.fin[i] = 1;
           op->remaining--;
-          if (!side && X.msgs[i].phase == 0) op->a_recv_left--;
+          if (!side && X.msgs[i].phase == 0) {
+            if (X.msgs[i].acc) host_accumulate(X.msgs[i].acc, X.msgs[i].ptr, X.msgs[i].len, op->in_dtype, op->out_dtype);
+            op->a_recv_left--;
+          }
           moved = true;
         }
       }
@@ -455,19 +525,24 @@ BNET_API const char* bnet_tmesh_transport(BnetTMesh* m) { return m && !m->send.e
 
 // Step 3: the input (read by this rank's kernels) and the output (accumulated into by every peer's kernels, and read by
 // this rank's kernels in the all-gather phase).  in == out registers one buffer for in-place two-shot all-reduces.
-BNET_API int bnet_tmesh_register(BnetTMesh* m, void* in, size_t in_bytes, void* out, size_t out_bytes) {
-  if (!m || !m->identified || m->active) return -1;
+// ptr_type: NCCL_PTR_CUDA (2: device memory, NVLink transport, reduction fused into the isends) or NCCL_PTR_HOST (1: host
+// memory over ANY transport — TCP between hosts included; two-shot only, the reduce-scatter pieces are added on the host).
+BNET_API int bnet_tmesh_register2(BnetTMesh* m, void* in, size_t in_bytes, void* out, size_t out_bytes, int ptr_type) {
+  if (!m || !m->identified || m->active || (ptr_type != NCCL_PTR_CUDA && ptr_type != NCCL_PTR_HOST)) return -1;
   tmesh_dereg(m, m->in_mr);
   if (m->out_mr != m->in_mr) tmesh_dereg(m, m->out_mr);
   m->in_mr = m->out_mr = nullptr;
-  m->in_mr = tmesh_reg(m, in, in_bytes, NCCL_PTR_CUDA);
+  m->in_mr = tmesh_reg(m, in, in_bytes, ptr_type);
   if (!m->in_mr) return -1;
   if (in == out && in_bytes == out_bytes) {
     m->out_mr = m->in_mr;
     return 0;
   }
-  m->out_mr = tmesh_reg(m, out, out_bytes, NCCL_PTR_CUDA);
+  m->out_mr = tmesh_reg(m, out, out_bytes, ptr_type);
   return m->out_mr ? 0 : -1;
+}
+BNET_API int bnet_tmesh_register(BnetTMesh* m, void* in, size_t in_bytes, void* out, size_t out_bytes) {
+  return bnet_tmesh_register2(m, in, in_bytes, out, out_bytes, NCCL_PTR_CUDA);
 }
 
 // out = sum over ranks of in.  in_dtype / out_dtype: 0 = fp32, 1 = bf16; (fp32, fp32), (bf16, bf16) and (bf16 in, fp32 out:

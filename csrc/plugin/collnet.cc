@@ -14,7 +14,9 @@
 //
 // Semantics:
 //   * sum of fp32 or bf16 (reduceSupport says so); everything else is left to NCCL's own algorithms
-//   * device memory on both sides (ptrSupport = NCCL_PTR_CUDA): the fused isend has no host path
+//   * device memory (NVLink transport: the reduction is fused into the isends) or host memory (any transport — multi-stream
+//     TCP between hosts, what NCCL hands a plugin without GPUDirect: the reduce-scatter pieces are added on the host);
+//     the send and the receive buffer of one call must be of the same kind
 //   * one all-reduce at a time per collComm, in call order (the mesh matches messages strictly FIFO per connection);
 //     up to 8 further calls queue behind it, beyond that iallreduce returns request = NULL ("try again", like isend)
 //   * iflush: the sender's kernel fences at system scope before the completion word is visible, nothing is left to flush
@@ -80,14 +82,15 @@ ncclResult_t coll_init(ncclDebugLogger_t logfn) { return plugin::init(logfn); }
 
 ncclResult_t coll_devices(int* ndev) {
   if (!ndev) return ncclInvalidArgument;
-  *ndev = collnet_enabled() && Engine::get().cuda_ok() ? Engine::get().ndev() : 0;
+  *ndev = collnet_enabled() ? Engine::get().ndev() : 0;
   return ncclSuccess;
 }
 
 template <typename P, ncclResult_t (*F)(int, P*)>
 ncclResult_t coll_props(int dev, P* o) {
   ncclResult_t r = F(dev, o);
-  if (r == ncclSuccess) o->ptrSupport = NCCL_PTR_CUDA;
+  // device memory rides the fused isends of the NVLink transport; host memory is reduced over any transport (TCP between hosts)
+  if (r == ncclSuccess) o->ptrSupport = NCCL_PTR_HOST | (Engine::get().cuda_ok() ? NCCL_PTR_CUDA : 0);
   return r;
 }
 
@@ -164,8 +167,8 @@ ncclResult_t coll_reduce_support(ncclDataType_t dt, ncclRedOp_t op, int* support
 ncclResult_t coll_regmr(void* ccomm, void* data, size_t size, int type, void** mhandle) {
   if (!ccomm || !mhandle) return ncclInvalidArgument;
   CollComm* c = static_cast<CollComm*>(ccomm);
-  if (type != NCCL_PTR_CUDA) {
-    BNET_WARN("collnet regMr: only device memory can be all-reduced by the fused isend (type %d)", type);
+  if (type != NCCL_PTR_CUDA && type != NCCL_PTR_HOST) {
+    BNET_WARN("collnet regMr: unsupported pointer type %d", type);
     return ncclInvalidUsage;
   }
   MeshMr* mr = tmesh_reg(c->mesh, data, size, type);

@@ -1,7 +1,8 @@
 """One rank of the CollNet test: drives ncclCollNetPlugin_vN the way NCCL does — listen, connect with everybody's handles,
 regMr of a send and a receive buffer, several iallreduce calls in flight (they queue), test until done.  Device memory is
 the CPU emulation (BNET_FAKE_CUDA=1); the all-reduce underneath is the two-shot mesh with fused isends.
-usage: collnet_worker.py <rank> <world> <dir> <abi version> <count> <f32|bf16> <lib name or ->"""
+usage: collnet_worker.py <rank> <world> <dir> <abi version> <count> <f32|bf16> <lib name or -> [host]
+host: ordinary host memory (NCCL_PTR_HOST) instead of emulated device memory — works over TCP as well"""
 import ctypes as C
 import json
 import os
@@ -12,6 +13,7 @@ import numpy as np
 
 rank, world, d, ver, count, dt = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3], int(sys.argv[4]), int(sys.argv[5]), sys.argv[6]
 lib_name = None if sys.argv[7] == "-" else sys.argv[7]
+host_mem = len(sys.argv) > 8 and sys.argv[8] == "host"
 
 from bagua_net_b200.utils.abi import NCCL_PTR_HOST, CollNetPlugin, PluginError, ncclBfloat16, ncclFloat32  # noqa: E402
 
@@ -26,8 +28,13 @@ lib.bnet_fake_cuda_alloc.argtypes = [C.c_size_t]
 es = 4 if dt == "f32" else 2
 nb = max(count * es, 64)
 NCALLS = 3
-sptr = [lib.bnet_fake_cuda_alloc(nb + 64) for _ in range(NCALLS)]
-rptr = lib.bnet_fake_cuda_alloc(NCALLS * nb + 64)
+if host_mem:
+    _keep = [np.zeros(nb + 64, dtype=np.uint8) for _ in range(NCALLS)] + [np.zeros(NCALLS * nb + 64, dtype=np.uint8)]
+    sptr, rptr = [a.ctypes.data for a in _keep[:NCALLS]], _keep[NCALLS].ctypes.data
+else:
+    sptr = [lib.bnet_fake_cuda_alloc(nb + 64) for _ in range(NCALLS)]
+    rptr = lib.bnet_fake_cuda_alloc(NCALLS * nb + 64)
+PTR = NCCL_PTR_HOST if host_mem else 2
 sraw = [(C.c_char * nb).from_address(x) for x in sptr]
 rraw = (C.c_char * (NCALLS * nb)).from_address(rptr)
 
@@ -45,13 +52,13 @@ for r in range(world):
 comm = p.connect(handles, rank, lcomm)
 nccl_dt = ncclFloat32 if dt == "f32" else ncclBfloat16
 support = {"sum_this_type": p.reduce_support(nccl_dt), "max": p.reduce_support(nccl_dt, 2), "int32": p.reduce_support(2)}
-host_refused = False
+bad_type_refused = False
 try:
-    p.reg_mr(comm, sptr[0], nb, NCCL_PTR_HOST)
+    p.reg_mr(comm, sptr[0], nb, 4)                 # NCCL_PTR_DMABUF is not offered
 except PluginError:
-    host_refused = True
-smh = [p.reg_mr(comm, x, nb) for x in sptr]
-rmh = p.reg_mr(comm, rptr, NCALLS * nb)
+    bad_type_refused = True
+smh = [p.reg_mr(comm, x, nb, PTR) for x in sptr]
+rmh = p.reg_mr(comm, rptr, NCALLS * nb, PTR)
 
 
 def put(raw, vals):
@@ -104,4 +111,4 @@ for h in smh + [rmh]:
 p.close_coll(comm)
 p.close_listen(lcomm)
 print(json.dumps({"ok": ok, "name": p.name, "ndev": ndev, "ptr_support": props["ptrSupport"], "support": support,
-                  "host_refused": host_refused}))
+                  "bad_type_refused": bad_type_refused}))

@@ -418,7 +418,7 @@ def test_transport_ring_compressed_allreduce_over_tcp(impl):
     assert len({o["digest"] for o in outs}) == 1
 
 
-def _run_tmesh(world, count, idt, odt, piece, inflight, timeout=180, algo="one-shot", inplace=False):
+def _run_tmesh(world, count, idt, odt, piece, inflight, timeout=180, algo="one-shot", inplace=False, env_extra=None, mem="device"):
     import json
     import subprocess
     import sys
@@ -426,9 +426,10 @@ def _run_tmesh(world, count, idt, odt, piece, inflight, timeout=180, algo="one-s
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, BNET_FAKE_CUDA="1", BNET_NVL="1", PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    env.update(env_extra or {})
     with tempfile.TemporaryDirectory() as d:
         procs = [subprocess.Popen([sys.executable, os.path.join(root, "tests", "tmesh_worker.py"), str(r), str(world), d, str(count),
-                                   idt, odt, str(piece), str(inflight), "2", algo, "1" if inplace else "0"], env=env,
+                                   idt, odt, str(piece), str(inflight), "2", algo, "1" if inplace else "0", mem], env=env,
                                   stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
                  for r in range(world)]
         outs = []
@@ -475,6 +476,20 @@ def test_transport_mesh_twoshot_allreduce(world, count, idt, odt, piece, infligh
     assert all(o["stats"]["bytes_sent"] == (sum(sl) - sl[r]) * ies + (world - 1) * sl[r] * oes for r, o in enumerate(outs)), outs
 
 
+@pytest.mark.parametrize("name,env,transport", [
+    ("tcp-basic", {"BNET_NVL": "0", "BNET_FAKE_CUDA": "0"}, "tcp-threads"),
+    ("tcp-async", {"BNET_NVL": "0", "BNET_FAKE_CUDA": "0", "BAGUA_NET_IMPLEMENT": "TOKIO"}, "tcp-async"),
+    ("shm", {"BNET_NVL": "1", "BNET_FAKE_CUDA": "0"}, "nvl")])
+@pytest.mark.parametrize("world,count,idt,odt,inplace", [(3, 100003, "f32", "f32", True), (4, 70000, "bf16", "f32", False),
+                                                          (5, 300, "bf16", "bf16", True), (2, 1 << 18, "f32", "f32", False)])
+def test_transport_mesh_twoshot_on_host_memory_over_any_transport(name, env, transport, world, count, idt, odt, inplace):
+    """Host memory is all-reduced with the same two-shot schedule over multi-stream TCP (both backends) and the same-host
+    shared-memory ring: no fused isend there, the reduce-scatter pieces land in a staging area and are added on the host."""
+    outs = _run_tmesh(world, count, idt, odt, 16384, 8, algo="two-shot", inplace=inplace, env_extra=env, mem="host")
+    assert all(o["ok"] for o in outs), outs
+    assert all(o["transport"] == transport for o in outs), [o["transport"] for o in outs]
+
+
 @pytest.mark.parametrize("seed", [11, 23, 37, 41, 59, 67])
 def test_transport_mesh_randomized(seed):
     """Random world size, element count (including counts below one slice per rank), piece size, window, type pair,
@@ -492,23 +507,30 @@ def test_transport_mesh_randomized(seed):
     assert all(o["ok"] for o in outs), (world, count, algo, idt, odt, inplace, piece, inflight, outs)
 
 
-@pytest.mark.parametrize("world,ver,count,dt,lib", [(2, 8, 70000, "f32", "-"), (4, 6, 5000, "bf16", "-"), (3, 10, 33, "f32", "libnccl-net-bnetx.so"),
-                                                     (8, 8, 200000, "bf16", "-")])
-def test_collnet_table_allreduces_like_nccl_would_drive_it(world, ver, count, dt, lib):
+@pytest.mark.parametrize("world,ver,count,dt,lib,mem,env", [
+    (2, 8, 70000, "f32", "-", "dev", {}), (4, 6, 5000, "bf16", "-", "dev", {}), (3, 10, 33, "f32", "libnccl-net-bnetx.so", "dev", {}),
+    (8, 8, 200000, "bf16", "-", "dev", {}),
+    # host buffers (what NCCL hands a plugin without GPUDirect), over multi-stream TCP and the shared-memory ring
+    (3, 8, 50000, "f32", "-", "host", {"BNET_NVL": "0", "BNET_FAKE_CUDA": "0"}),
+    (4, 8, 30000, "bf16", "-", "host", {"BNET_NVL": "0", "BNET_FAKE_CUDA": "0", "BAGUA_NET_IMPLEMENT": "TOKIO"}),
+    (2, 6, 100000, "f32", "-", "host", {"BNET_NVL": "1", "BNET_FAKE_CUDA": "0"})])
+def test_collnet_table_allreduces_like_nccl_would_drive_it(world, ver, count, dt, lib, mem, env):
     """ncclCollNetPlugin_vN (csrc/plugin/collnet.cc): listen / connect(handles, nranks, rank) / regMr / iallreduce / test /
-    iflush through the exported table, several all-reduces queued per rank and tested out of order; exact sums; only
-    sum of fp32 / bf16 on device memory is offered."""
+    iflush through the exported table, several all-reduces queued per rank and tested out of order; exact sums; sum of
+    fp32 / bf16 on device memory (fused isends over the emulated NVLink transport) or host memory (TCP, shared memory)."""
     import json
     import subprocess
     import sys
     import tempfile
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    extra_env = env
     env = dict(os.environ, BNET_FAKE_CUDA="1", BNET_NVL="1", BNET_COLLNET="1",
                PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    env.update(extra_env)
     with tempfile.TemporaryDirectory() as d:
         procs = [subprocess.Popen([sys.executable, os.path.join(root, "tests", "collnet_worker.py"), str(r), str(world), d, str(ver),
-                                   str(count), dt, lib], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+                                   str(count), dt, lib, mem], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
                  for r in range(world)]
         outs = []
         for p in procs:
@@ -521,7 +543,8 @@ def test_collnet_table_allreduces_like_nccl_would_drive_it(world, ver, count, dt
             assert p.returncode == 0, e[-3000:]
             outs.append(json.loads([ln for ln in o.splitlines() if ln.startswith("{")][-1]))
     for o in outs:
-        assert o["ok"] and o["name"] == "BNet" and o["ndev"] >= 1 and o["ptr_support"] == 2 and o["host_refused"], o
+        assert o["ok"] and o["name"] == "BNet" and o["ndev"] >= 1 and o["bad_type_refused"], o
+        assert o["ptr_support"] == (3 if env.get("BNET_FAKE_CUDA") == "1" else 1), o      # host always, device memory when CUDA is usable
         assert o["support"] == {"sum_this_type": True, "max": False, "int32": False}, o
 
 

@@ -16,6 +16,7 @@ piece, inflight = int(sys.argv[7]), int(sys.argv[8])
 rounds = int(sys.argv[9]) if len(sys.argv) > 9 else 2
 algo = sys.argv[10] if len(sys.argv) > 10 else "one-shot"
 inplace = len(sys.argv) > 11 and sys.argv[11] == "1"
+host_mem = len(sys.argv) > 12 and sys.argv[12] == "host"      # ordinary host memory (any transport) instead of emulated device memory
 
 from bagua_net_b200.parallel.transport_ring import MeshCore  # noqa: E402
 from bagua_net_b200.utils.native import load  # noqa: E402
@@ -25,8 +26,13 @@ lib.bnet_fake_cuda_alloc.restype = C.c_void_p
 lib.bnet_fake_cuda_alloc.argtypes = [C.c_size_t]
 ies, oes = (4 if idt == "f32" else 2), (4 if odt == "f32" else 2)
 ib, ob = max(count * ies, 64), max(count * oes, 64)
-iptr = lib.bnet_fake_cuda_alloc(ib + 64)
-optr = iptr if inplace else lib.bnet_fake_cuda_alloc(ob + 64)
+if host_mem:
+    _keep = [np.zeros(ib + 64, dtype=np.uint8), None]
+    _keep[1] = _keep[0] if inplace else np.zeros(ob + 64, dtype=np.uint8)
+    iptr, optr = _keep[0].ctypes.data, _keep[1].ctypes.data
+else:
+    iptr = lib.bnet_fake_cuda_alloc(ib + 64)
+    optr = iptr if inplace else lib.bnet_fake_cuda_alloc(ob + 64)
 assert iptr and optr and (not inplace or idt == odt)
 iraw, oraw = (C.c_char * ib).from_address(iptr), (C.c_char * ob).from_address(optr)
 
@@ -43,7 +49,7 @@ for r in range(world):
         time.sleep(0.01)
     handles.append(open(p, "rb").read())
 core.connect(handles)
-core.register(iptr, ib, optr, ob)
+core.register(iptr, ib, optr, ob, host_memory=host_mem)
 
 
 def put(raw, dt, vals):
