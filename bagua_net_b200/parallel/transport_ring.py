@@ -266,21 +266,22 @@ class TransportMesh:
         out_dtype = in_dtype if out_dtype is None else out_dtype
         if (in_dtype, out_dtype) not in ((torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16), (torch.bfloat16, torch.float32)):
             raise TypeError("supported: fp32 -> fp32, bf16 -> bf16, bf16 -> fp32")
-        device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self._in = torch.zeros(numel, dtype=in_dtype, device=device)
         self._out = torch.zeros(numel, dtype=out_dtype, device=device)
         self.core.register(self._in.data_ptr(), self._in.numel() * self._in.element_size(), self._out.data_ptr(),
-                           self._out.numel() * self._out.element_size())
+                           self._out.numel() * self._out.element_size(), host_memory=device.type == "cpu")
         return self._in, self._out
 
     def buffer(self, numel: int, dtype=torch.float32, device=None) -> torch.Tensor:
-        """One registered buffer, for in-place two-shot all-reduces."""
+        """One registered buffer, for in-place two-shot all-reduces.  ``device="cpu"``: host memory — reduced over any
+        transport (TCP between hosts, shared memory), the reduce-scatter pieces added on the host."""
         if dtype not in _DT:
             raise TypeError("supported: fp32, bf16")
-        device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self._in = self._out = torch.zeros(numel, dtype=dtype, device=device)
         nbytes = self._in.numel() * self._in.element_size()
-        self.core.register(self._in.data_ptr(), nbytes, self._in.data_ptr(), nbytes)
+        self.core.register(self._in.data_ptr(), nbytes, self._in.data_ptr(), nbytes, host_memory=device.type == "cpu")
         return self._in
 
     def all_reduce(self, x: torch.Tensor, out: torch.Tensor, piece_bytes: int = 1 << 20, inflight: int = 8,
@@ -288,7 +289,10 @@ class TransportMesh:
         """out = sum over ranks of x (both inside the registered buffers, same number of elements)."""
         if x.numel() != out.numel() or x.dtype not in _DT or out.dtype not in _DT:
             raise TypeError("mesh all-reduce: fp32 / bf16 tensors of equal length")
-        torch.cuda.current_stream(x.device).synchronize()
+        if x.is_cuda:
+            torch.cuda.current_stream(x.device).synchronize()
+        elif algo != "two-shot":
+            raise ValueError("host memory is reduced with algo='two-shot'")
         self.core.all_reduce(x.data_ptr(), out.data_ptr(), x.numel(), _DT[x.dtype], _DT[out.dtype], piece_bytes, inflight,
                              algo=algo)
         return out

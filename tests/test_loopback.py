@@ -490,6 +490,40 @@ def test_transport_mesh_twoshot_on_host_memory_over_any_transport(name, env, tra
     assert all(o["transport"] == transport for o in outs), [o["transport"] for o in outs]
 
 
+@pytest.mark.parametrize("env,transport", [({"BNET_NVL": "0"}, "tcp-threads"), ({"BNET_NVL": "1"}, "nvl")])
+def test_transport_mesh_torch_api_on_host_tensors(env, transport):
+    """TransportMesh (the torch-facing wrapper) on CPU tensors: torch.distributed / gloo only exchanges the handles, the
+    all-reduce rides the plugin's connections."""
+    import json
+    import socket
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    s_ = socket.socket()
+    s_.bind(("127.0.0.1", 0))
+    port = s_.getsockname()[1]
+    s_.close()
+    world = 3
+    procs = []
+    for r in range(world):
+        e = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), BNET_FAKE_CUDA="0",
+                 PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+        e.update(env)
+        procs.append(subprocess.Popen([sys.executable, os.path.join(root, "tests", "tmesh_torch_worker.py")], env=e, stdout=subprocess.PIPE,
+                                      stderr=subprocess.PIPE, text=True))
+    for p in procs:
+        try:
+            o, err = p.communicate(timeout=180)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+        assert p.returncode == 0, err[-3000:]
+        d = json.loads([ln for ln in o.splitlines() if ln.startswith("{")][-1])
+        assert d["ok"] and d["transport"] == transport, d
+
+
 @pytest.mark.parametrize("seed", [11, 23, 37, 41, 59, 67])
 def test_transport_mesh_randomized(seed):
     """Random world size, element count (including counts below one slice per rank), piece size, window, type pair,
