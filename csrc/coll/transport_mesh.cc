@@ -32,6 +32,7 @@
 // only, reference cc/v4/nccl_net_v4.h:64-101); this and the ring are what section 7.2 step 4 of the survey asks for.
 #include "coll/transport_mesh.h"
 
+#include <sched.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -62,6 +63,8 @@ struct BnetTMesh {
   uint64_t jseq = 0;
   uint64_t op_seq = 0;              // all-reduces started on this mesh (span ids)
   MeshOp* active = nullptr;         // one operation at a time (FIFO matching per connection)
+  std::vector<std::vector<char>> staging;   // host mode: per incoming connection, where phase-A pieces land (kept between calls:
+                                            // a fresh 8 MiB vector per connection and call costs a memset and its page faults)
   char err[256] = {0};
   uint64_t last_msgs = 0, last_bytes_sent = 0;
 };
@@ -150,7 +153,7 @@ struct MeshOp {
   // staging areas and are added into the own slice here, on the host; phase B is unchanged
   bool host = false;
   int in_dtype = 0, out_dtype = 0;
-  std::vector<std::vector<char>> staging;
+  unsigned idle = 0;          // consecutive steps in which nothing moved (the blocking wrapper backs off on it)
 };
 
 BnetTMesh* tmesh_new(ListenComm* listen, int rank, int world, int net_dev) {
@@ -345,7 +348,11 @@ MeshOp* tmesh_op_start(BnetTMesh* m, int algo, const void* in, MeshMr* in_mr, vo
     slice(m->rank, &m0, &m1);
     i0 = m0;
     i1 = m1;
-    if (host) op->staging.assign(nc, std::vector<char>((m1 - m0) * ies + 64));
+    if (host) {
+      m->staging.resize(nc);
+      for (auto& v : m->staging)
+        if (v.size() < (m1 - m0) * ies + 64) v.resize((m1 - m0) * ies + 64);
+    }
     for (int c = 0; c < nc; c++) {
       size_t q0, q1;
       if (!host) {
@@ -355,7 +362,7 @@ MeshOp* tmesh_op_start(BnetTMesh* m, int algo, const void* in, MeshMr* in_mr, vo
         // type), piece by piece, and is added into out[slice] when it has arrived
         for (size_t a = m0; a < m1; a += piece) {
           const size_t b = a + piece < m1 ? a + piece : m1;
-          MeshMsg g{op->staging[c].data() + (a - m0) * ies, (b - a) * ies, 0, nullptr, 0};
+          MeshMsg g{m->staging[c].data() + (a - m0) * ies, (b - a) * ies, 0, nullptr, 0};
           g.acc = dst + a * oes;
           op->rs[c].msgs.push_back(g);
         }
@@ -467,6 +474,7 @@ int tmesh_op_step(MeshOp* op) {
       while (X.done < X.posted && X.fin[X.done]) X.done++;
     }
   }
+  op->idle = moved ? 0 : op->idle + 1;
   if (op->remaining == 0) {
     op->stage = 2;
     if (op->span) Telemetry::get().span_end(op->span, op->out_bytes);
@@ -554,7 +562,12 @@ BNET_API int bnet_tmesh_allreduce2(BnetTMesh* m, const void* in, void* out, size
   MeshOp* op = tmesh_op_start(m, algo, in, m->in_mr, out, m->out_mr, count, in_dtype, out_dtype, piece_bytes, inflight, timeout_ms);
   if (!op) return -1;
   int st;
-  while ((st = tmesh_op_step(op)) == 0) {}
+  while ((st = tmesh_op_step(op)) == 0) {
+    // Poll hot while things move (a GPU kernel's completion word arrives within microseconds); when nothing has moved for
+    // a while the peers' threads — TCP stream workers, other ranks of an oversubscribed host — need the core more than we do
+    if (op->idle > 1024) usleep(30);
+    else if (op->idle > 32) sched_yield();
+  }
   tmesh_op_free(op);
   return st == 1 ? 0 : -1;
 }

@@ -15,6 +15,7 @@
 //   ring with up to `inflight` requests per direction in flight, striped over the executor's clusters by the transport.
 //
 // Host-driven (one polling thread per rank, like NCCL's proxy); every request goes through Comm::isend_op / irecv / test.
+#include <sched.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -172,6 +173,7 @@ BNET_API int bnet_tring_allreduce(BnetTRing* r, void* buf, size_t count, int dty
   r->last_bytes_sent = 0;
   const uint64_t t0 = now_ns();
   CollSpan span(r->rank, ++r->op_seq, total);
+  unsigned idle = 0;
   while (done_r < M || done_s < M) {
     bool moved = false;
     // receives: posted in message order (the transport matches strictly FIFO per connection)
@@ -224,6 +226,11 @@ BNET_API int bnet_tring_allreduce(BnetTRing* r, void* buf, size_t count, int dty
     while (head_s < posted_s && sdone[head_s]) head_s++;
     if (!moved && timeout_ms > 0 && now_ns() - t0 > (uint64_t)timeout_ms * 1000000ull)
       return fail(r, "all-reduce timed out: %zu/%zu receives, %zu/%zu sends done", done_r, M, done_s, M);
+    // poll hot while things move; when nothing has for a while, the transport's worker threads (or other ranks of an
+    // oversubscribed host) need the core more than this loop does
+    idle = moved ? 0 : idle + 1;
+    if (idle > 1024) usleep(30);
+    else if (idle > 32) sched_yield();
   }
   span.ok = true;
   return 0;
@@ -355,6 +362,7 @@ BNET_API int bnet_tring_allreduce_compressed(BnetTRing* r, void* buf, size_t cou
   r->last_bytes_sent = 0;
   const uint64_t t0 = now_ns();
   CollSpan span(r->rank, ++r->op_seq, (uint64_t)count * 4);
+  unsigned idle = 0;
   auto submit = [&](uint32_t op, float sc, const void* src, void* dst, size_t src_bytes, LocalJob* j) -> int {
     if (src_bytes == 0) { j->slot = -1; return 0; }
     if (free_slots.empty()) return 1;                                   // try again later
@@ -486,6 +494,9 @@ BNET_API int bnet_tring_allreduce_compressed(BnetTRing* r, void* buf, size_t cou
     if (!cuda::fake()) cuda::exec_kick(cuda_dev);                       // launch what the executor has collected
     if (!moved && timeout_ms > 0 && now_ns() - t0 > (uint64_t)timeout_ms * 1000000ull)
       return fail(r, "compressed all-reduce timed out: %zu/%zu receives ready, %zu/%zu sends done", ready_r, M, done_s, M);
+    idle = moved ? 0 : idle + 1;
+    if (idle > 1024) usleep(30);
+    else if (idle > 32) sched_yield();
   }
   span.ok = true;
   return 0;
