@@ -226,6 +226,8 @@ def wgrad_trusted() -> bool:
                     break
                 for k in cfg:
                     os.environ.pop(k, None)
+                if not tc_linear.LAST_CHECK_DEFINITIVE:
+                    break       # the child could not run or timed out: the next rung would wait just as long for nothing
     return _wgrad_trusted
 
 

@@ -271,6 +271,9 @@ def linear_bias_act(x, w, bias=None, relu=False):
 _trusted: bool | None = None
 
 
+LAST_CHECK_DEFINITIVE = True      # did the last child-process check end with a verdict (False: timeout / could not run)?
+
+
 def _isolated_self_check(timeout: float = 180.0, check: str | None = None, tag: str = "tc_self_check") -> bool:
     """``self_check()`` (or `check`: Python source that leaves its verdict in ``ok``) in a child process: a kernel that
     faults (a poisoned CUDA context) or hangs past its own watchdog must not take the training process with it.  The verdict is cached per (library build, GPU model) under
@@ -289,9 +292,12 @@ def _isolated_self_check(timeout: float = 180.0, check: str | None = None, tag: 
         return False
     cache_dir = os.environ.get("BNET_CACHE_DIR") or os.path.join(os.path.expanduser("~"), ".cache", "bnet")
     path = os.path.join(cache_dir, tag + "_" + hashlib.sha1(key.encode()).hexdigest()[:16] + ".json")
+    global LAST_CHECK_DEFINITIVE
     try:
         with open(path) as f:
-            return bool(json.load(f)["ok"])
+            ok = bool(json.load(f)["ok"])
+        LAST_CHECK_DEFINITIVE = True
+        return ok
     except Exception:  # noqa: BLE001 — no verdict yet
         pass
     env = dict(os.environ, PYTHONPATH=REPO_ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""),
@@ -310,7 +316,8 @@ def _isolated_self_check(timeout: float = 180.0, check: str | None = None, tag: 
     # exit 0 / 3: the check ran and passed / failed; death by a signal: a faulting kernel — all definitive, cached.  Anything
     # else (timeout under a profiler, no GPU for the child, an import problem) is no verdict: not trusted now, asked again
     # next time
-    if rc is None or (rc > 0 and rc != 3):
+    LAST_CHECK_DEFINITIVE = not (rc is None or (rc > 0 and rc != 3))
+    if not LAST_CHECK_DEFINITIVE:
         return False
     ok = rc == 0
     try:

@@ -389,7 +389,13 @@ def test_tc_conv_wgrad_plan_and_gating(monkeypatch, tmp_path):
     monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)
     monkeypatch.delenv("BNET_TC_WGRAD_BN", raising=False)
     monkeypatch.delenv("BNET_TC_WGRAD_FIXUP", raising=False)
+    import subprocess
+
+    spawned, real_run = [], subprocess.run
+    monkeypatch.setattr(subprocess, "run", lambda *a, **k: (spawned.append(1), real_run(*a, **k))[1])
     assert tc_conv.wgrad_trusted() is False                          # the child has no GPU either: not trusted, nothing cached
+    monkeypatch.setattr(subprocess, "run", real_run)
+    assert len(spawned) == 1                                         # ... and no verdict stops the ladder: one child, not four
     assert not glob.glob(str(tmp_path / "tc_wgrad_*self_check_*.json")) and "BNET_TC_WGRAD_BN" not in os.environ
     # verdict files as a GPU box would leave them: the default plan failed its check, the 128-column ladder step passed
     import hashlib
