@@ -301,7 +301,7 @@ def main() -> int:
     ap.add_argument("--no-resnet", action="store_true", help="skip the ResNet-50 side arms (BASELINE config #4)")
     ap.add_argument("--no-transport-coll", action="store_true", help="N > 1: skip the ring / two-shot all-reduces over the plugin's connections")
     ap.add_argument("--resnet-timeout", type=float, default=90.0, help="seconds one ResNet-50 arm may take")
-    ap.add_argument("--resnet-deadline", type=float, default=230.0,
+    ap.add_argument("--resnet-deadline", type=float, default=300.0,
                     help="no ResNet-50 arm starts once the run is this many seconds old")
     ap.add_argument("--no-prefetch", action="store_true", help="e2e: per-step API instead of the prefetching loop")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel of the step individually (no CUDA graph)")
@@ -751,35 +751,6 @@ def main() -> int:
             if rank == 0 and res is not None:
                 extra["transport_allreduce"] = {k: v for k, v in res.items() if k not in ("note", "log_path")}
 
-    # ---- does NCCL accept the plugin's CollNet table?  (bench/nccl_collnet_probe.py: plugin + BNET_COLLNET=1 NCCL_COLLNET_ENABLE=1,
-    #      one virtual host per rank; fp32 all-reduce sweep, exactness, the plugin's own count of all-reduces it executed)
-    if (args.comm == "bnet" and world > 1 and not args.no_arms and not args.no_transport_coll and not os.environ.get("BNET_BENCH_CHILD")):
-        sync_all()
-        go = torch.tensor([1 if time.time() - _T0 < args.resnet_deadline else 0], device=dev, dtype=torch.int32)
-        dist.broadcast(go, 0)
-        if int(go.item()):
-            note("NCCL CollNet probe: child processes (timeout 75 s)")
-            res = run_child_arm("collnet", args, rank, world, 163, 75.0, model="probe",
-                                script=[os.path.join(ROOT, "bench", "nccl_collnet_probe.py")])
-            note(f"NCCL CollNet probe: {res.get('status') if res else None}")
-            dist.barrier()
-            if rank == 0 and res is not None:
-                try:      # what NCCL itself said about CollNet (rank 0's INFO log of the child)
-                    logp = [p_ for p_ in (res.get("log_path"),) if p_]
-                    lines = []
-                    for lp in logp:
-                        with open(lp, errors="replace") as f:
-                            for ln in f:
-                                if "ollnet" in ln.lower() or "coll net" in ln.lower():
-                                    ln = ln.strip().split("NCCL INFO ")[-1][:160]
-                                    if ln not in lines:
-                                        lines.append(ln)
-                    res["nccl_log_collnet_lines"] = lines[:8]
-                except Exception:   # noqa: BLE001
-                    pass
-                res.pop("log_path", None)
-                extra["nccl_collnet"] = res
-
     # ---- N = 1: where does the step go?  (tools/step_profile.py in a child: torch.profiler over eager steps of the same model;
     #      kernel names, launches and time per step — explains the number above, is not a bench value)
     if (args.comm == "bnet" and world == 1 and args.model == "vgg16" and not args.no_arms and not args.no_resnet
@@ -817,6 +788,35 @@ def main() -> int:
                 dist.barrier()
             if rank == 0:
                 arms[key] = res
+
+    # ---- does NCCL accept the plugin's CollNet table?  (bench/nccl_collnet_probe.py: plugin + BNET_COLLNET=1 NCCL_COLLNET_ENABLE=1,
+    #      one virtual host per rank; fp32 all-reduce sweep, exactness, the plugin's own count of all-reduces it executed)
+    if (args.comm == "bnet" and world > 1 and not args.no_arms and not args.no_transport_coll and not os.environ.get("BNET_BENCH_CHILD")):
+        sync_all()
+        go = torch.tensor([1 if time.time() - _T0 < args.resnet_deadline else 0], device=dev, dtype=torch.int32)
+        dist.broadcast(go, 0)
+        if int(go.item()):
+            note("NCCL CollNet probe: child processes (timeout 75 s)")
+            res = run_child_arm("collnet", args, rank, world, 163, 75.0, model="probe",
+                                script=[os.path.join(ROOT, "bench", "nccl_collnet_probe.py")])
+            note(f"NCCL CollNet probe: {res.get('status') if res else None}")
+            dist.barrier()
+            if rank == 0 and res is not None:
+                try:      # what NCCL itself said about CollNet (rank 0's INFO log of the child)
+                    logp = [p_ for p_ in (res.get("log_path"),) if p_]
+                    lines = []
+                    for lp in logp:
+                        with open(lp, errors="replace") as f:
+                            for ln in f:
+                                if "ollnet" in ln.lower() or "coll net" in ln.lower():
+                                    ln = ln.strip().split("NCCL INFO ")[-1][:160]
+                                    if ln not in lines:
+                                        lines.append(ln)
+                    res["nccl_log_collnet_lines"] = lines[:8]
+                except Exception:   # noqa: BLE001
+                    pass
+                res.pop("log_path", None)
+                extra["nccl_collnet"] = res
 
     # ---- last and least: the DDP-over-plugin arm once more with the copy engines moving the bytes (BNET_EXEC_MODE=ce: no SM
     #      is taken from the backward pass; slower in isolation, never measured under overlap) — only if time is left
