@@ -131,6 +131,78 @@ def test_wire_compat_mode():
                     env={"BNET_WIRE_COMPAT": "1", "BNET_NVL": "0"}), "tcp-threads")
 
 
+@pytest.mark.parametrize("impl", ["BASIC", "TOKIO"])
+@pytest.mark.parametrize("ours", ["receiver", "sender"])
+@pytest.mark.parametrize("streams", [(2, None), (5, 4096)])
+def test_interoperates_with_a_peer_that_speaks_the_reference_format(impl, ours, streams):
+    """The other end is tests/ref_wire_peer.py: the reference's wire format re-implemented from its specification with plain
+    Python sockets (handle = bare sockaddr, 8-byte stream ids, u64 / u32 length framing, the reference's chunking and
+    stream cursor).  The plugin is driven through the reference's ABI (ncclNet v4) with BNET_WIRE_COMPAT=1."""
+    import json
+    import subprocess
+    import sys
+    import tempfile
+    import threading
+    import time
+
+    from conftest import ROOT
+    from loopback_worker import pattern
+    from ref_wire_peer import RefReceiver, RefSender
+
+    sizes, inflight, rounds = [0, 8, 65536, 1048577, 3145729], 4, 2
+    worker = os.path.join(ROOT, "tests", "loopback_worker.py")
+    env = dict(os.environ, PYTHONPATH=ROOT, BNET_NVL="0", BNET_WIRE_COMPAT="1", BAGUA_NET_IMPLEMENT=impl)
+    env.pop("BAGUA_NET_NSTREAMS", None)
+    env.pop("BAGUA_NET_MIN_CHUNKSIZE", None)
+    nstreams, min_chunk = streams          # (the reference's defaults / five streams and chunks from 4 KiB: both ends set alike)
+    if min_chunk is not None:
+        env.update(BAGUA_NET_NSTREAMS=str(nstreams), BAGUA_NET_MIN_CHUNKSIZE=str(min_chunk))
+    messages = [bytes(pattern(size, 1000 * rnd + 7 * j + size % 97)[:size])
+                for rnd in range(rounds) for size in sizes for j in range(inflight)]
+    args = ["--abi", "4", "--sizes", ",".join(map(str, sizes)), "--inflight", str(inflight), "--rounds", str(rounds)]
+    with tempfile.TemporaryDirectory() as d:
+        hfile = os.path.join(d, "handle.bin")
+        if ours == "receiver":
+            proc = subprocess.Popen([sys.executable, worker, "0", d] + args, env=env, stdout=subprocess.PIPE, text=True)
+            t0 = time.time()
+            while not os.path.exists(hfile):
+                assert time.time() - t0 < 60 and proc.poll() is None, "the plugin's listener did not come up"
+                time.sleep(0.01)
+            handle = open(hfile, "rb").read()
+            assert handle[28:32] == b"\0\0\0\0"            # (no magic: a bare sockaddr, as the reference's handle)
+            peer = RefSender(handle, impl, nstreams, min_chunk)
+            err = []
+
+            def feed():
+                try:
+                    for m in messages:
+                        peer.send(m)
+                except Exception as ex:   # noqa: BLE001
+                    err.append(ex)
+
+            th = threading.Thread(target=feed, daemon=True)
+            th.start()
+            out = proc.communicate(timeout=120)[0]
+            th.join(timeout=30)
+            peer.close()
+            assert not err, err
+        else:
+            peer = RefReceiver(impl, nstreams, min_chunk)
+            with open(hfile + ".tmp", "wb") as f:
+                f.write(peer.handle)
+            os.rename(hfile + ".tmp", hfile)
+            proc = subprocess.Popen([sys.executable, worker, "1", d] + args, env=env, stdout=subprocess.PIPE, text=True)
+            peer.accept()
+            for i, m in enumerate(messages):
+                got = peer.recv()
+                assert got == m, f"message {i}: {len(got)} bytes, expected {len(m)}"
+            out = proc.communicate(timeout=120)[0]
+            peer.close()
+    res = json.loads(out.splitlines()[-1])
+    assert res["ok"] and res["messages"] == len(messages), res
+    assert res["transport"] == ("tcp-threads" if impl == "BASIC" else "tcp-async")
+
+
 def test_nvl_shared_memory_host_buffers():
     _check(run_pair(["--sizes", SIZES + ",9437184", "--inflight", "8", "--rounds", "2"],
                     env={"BNET_NVL": "1", "BNET_SHM_RING_BYTES": "1048576"}), "nvl")
