@@ -789,6 +789,27 @@ def main() -> int:
             if rank == 0:
                 arms[key] = res
 
+    # ---- the reference-equivalent data path on THIS box: torch DDP over NCCL over the plugin restricted to what bagua-net does
+    #      (host pointers only: NCCL stages through host memory; multi-stream TCP, here over the loopback interface; no NVLink or
+    #      shared-memory transport).  The reference itself cannot be built here (--impl reference says why); this is its product
+    #      re-implemented, same model, same step, so the ratio to the headline is the same-box speed-up over "what the
+    #      reference gives on an 8 x B200 node".
+    if (args.comm == "bnet" and world > 1 and not args.no_arms and not args.no_resnet and not os.environ.get("BNET_BENCH_CHILD")):
+        sync_all()
+        go = torch.tensor([1 if time.time() - _T0 < args.resnet_deadline else 0], device=dev, dtype=torch.int32)
+        dist.broadcast(go, 0)
+        if int(go.item()):
+            note(f"arm nccl-plugin, host pointers over TCP (reference-equivalent): child processes (timeout {args.resnet_timeout:.0f} s)")
+            res = run_child_arm("nccl-plugin", args, rank, world, 327, args.resnet_timeout,
+                                extra_env={"BNET_NVL": "0", "BNET_GDR": "0"}, tag="_tcp")
+            note(f"arm nccl-plugin, host pointers over TCP: {res.get('status') if res else None}")
+            dist.barrier()
+            if rank == 0:
+                if res is not None:
+                    res["note"] = ("reference-equivalent path: NCCL over the plugin with host pointers only and multi-stream TCP "
+                                   "over loopback (BNET_NVL=0 BNET_GDR=0), what bagua-net does on one node")
+                arms["nccl_plugin_tcp_host_pointers"] = res
+
     # ---- does NCCL accept the plugin's CollNet table?  (bench/nccl_collnet_probe.py: plugin + BNET_COLLNET=1 NCCL_COLLNET_ENABLE=1,
     #      one virtual host per rank; fp32 all-reduce sweep, exactness, the plugin's own count of all-reduces it executed)
     if (args.comm == "bnet" and world > 1 and not args.no_arms and not args.no_transport_coll and not os.environ.get("BNET_BENCH_CHILD")):
@@ -875,7 +896,7 @@ def main() -> int:
             if res is None:
                 continue
             # keep the arm compact: its headline, its sweep, its checks
-            keep = {k: res.get(k) for k in ("status", "wall_s", "value", "ms_per_step", "log_tail") if res.get(k) is not None}
+            keep = {k: res.get(k) for k in ("status", "wall_s", "value", "ms_per_step", "log_tail", "note") if res.get(k) is not None}
             cfg = res.get("config") or {}
             keep.update({k: cfg.get(k) for k in ("model", "comm", "path", "cuda_graph", "fused_conv_blocks", "fused_note", "graph_note")
                          if cfg.get(k) is not None})
