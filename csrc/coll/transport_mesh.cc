@@ -30,9 +30,9 @@
 //
 // The reference has no collectives (reference README.md:88; its ncclCollNet_v4_t is a declaration
 // only, reference cc/v4/nccl_net_v4.h:64-101); this and the ring are what section 7.2 step 4 of the survey asks for.
+#include "coll/backoff.h"
 #include "coll/transport_mesh.h"
 
-#include <sched.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -154,6 +154,11 @@ struct MeshOp {
   bool host = false;
   int in_dtype = 0, out_dtype = 0;
   unsigned idle = 0;          // consecutive steps in which nothing moved (the blocking wrapper backs off on it)
+  // In place, over transports whose sends are served by other threads (TCP): the reduce-scatter sends to connection c's peer
+  // that have not completed locally.  That peer's finished slice arrives in the memory those sends read — only after it got
+  // them, by causality through the network; the receive is nevertheless posted only when the count is zero (an explicit
+  // happens-before).  Empty = not tracked: out of place, or the NVLink path (kernels on both ends), which posts ahead.
+  std::vector<uint32_t> a_send_left;
 };
 
 BnetTMesh* tmesh_new(ListenComm* listen, int rank, int world, int net_dev) {
@@ -383,6 +388,15 @@ MeshOp* tmesh_op_start(BnetTMesh* m, int algo, const void* in, MeshMr* in_mr, vo
     for (const MeshMsg& g : op->rs[c].msgs)
       if (g.phase == 0) op->a_recv_left++;
   }
+  bool threads_serve_sends = false;
+  for (int c = 0; c < nc; c++)
+    threads_serve_sends = threads_serve_sends || strcmp(m->send[c]->transport(), "nvl") != 0 || strcmp(m->recv[c]->transport(), "nvl") != 0;
+  if (in_place && threads_serve_sends) {
+    op->a_send_left.assign(nc, 0);
+    for (int c = 0; c < nc; c++)
+      for (const MeshMsg& g : op->ss[c].msgs)
+        if (g.phase == 0) op->a_send_left[c]++;
+  }
   m->last_msgs = 0;
   m->last_bytes_sent = 0;
   op->out_bytes = (uint64_t)count * oes;
@@ -432,6 +446,8 @@ int tmesh_op_step(MeshOp* op) {
     MeshSide& R = op->rs[c];
     while (R.posted < R.msgs.size() && R.posted - R.done < (size_t)op->inflight) {
       const MeshMsg& g = R.msgs[R.posted];
+      // in place, this peer's finished slice lands where my contribution to it was read: see MeshOp::a_send_left
+      if (g.phase == 1 && !op->a_send_left.empty() && op->a_send_left[(m->recv_peer[c] - m->rank - 1 + m->world) % m->world]) break;
       Request* q = nullptr;
       int st = m->recv[c]->irecv(g.ptr, g.len, 0, g.mh, &q);
       if (st) { op->stage = -1; return fail(m, "irecv failed: %s", status_str(st)); }
@@ -464,6 +480,7 @@ int tmesh_op_step(MeshOp* op) {
         if (done) {
           X.fin[i] = 1;
           op->remaining--;
+          if (side && X.msgs[i].phase == 0 && !op->a_send_left.empty()) op->a_send_left[c]--;
           if (!side && X.msgs[i].phase == 0) {
             if (X.msgs[i].acc) host_accumulate(X.msgs[i].acc, X.msgs[i].ptr, X.msgs[i].len, op->in_dtype, op->out_dtype);
             op->a_recv_left--;
@@ -562,11 +579,12 @@ BNET_API int bnet_tmesh_allreduce2(BnetTMesh* m, const void* in, void* out, size
   MeshOp* op = tmesh_op_start(m, algo, in, m->in_mr, out, m->out_mr, count, in_dtype, out_dtype, piece_bytes, inflight, timeout_ms);
   if (!op) return -1;
   int st;
+  IdleBackoff backoff;
   while ((st = tmesh_op_step(op)) == 0) {
     // Poll hot while things move (a GPU kernel's completion word arrives within microseconds); when nothing has moved for
     // a while the peers' threads — TCP stream workers, other ranks of an oversubscribed host — need the core more than we do
-    if (op->idle > 1024) usleep(30);
-    else if (op->idle > 32) sched_yield();
+    // (coll/backoff.h)
+    backoff.step(op->idle == 0);
   }
   tmesh_op_free(op);
   return st == 1 ? 0 : -1;

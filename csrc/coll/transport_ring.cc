@@ -15,7 +15,6 @@
 //   ring with up to `inflight` requests per direction in flight, striped over the executor's clusters by the transport.
 //
 // Host-driven (one polling thread per rank, like NCCL's proxy); every request goes through Comm::isend_op / irecv / test.
-#include <sched.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -23,6 +22,7 @@
 
 #include <vector>
 
+#include "coll/backoff.h"
 #include "core/engine.h"
 #include "core/telemetry.h"
 #include "cuda/cuda_iface.h"
@@ -58,6 +58,16 @@ struct BnetTRing {
 };
 
 namespace {
+// In place, the receive of an all-gather piece writes the memory a reduce-scatter send read n-1 steps earlier.  The bytes can
+// only arrive after that send's data went all the way round the ring, so posting the receive early is harmless — by causality
+// through the network, which no tool (and no transport with its own idea of "send complete") can see.  Over transports whose
+// sends are served by other threads (TCP) the receive is therefore posted only once that send has completed locally: an
+// explicit happens-before, a poll iteration late at worst.  The NVLink path (kernels on both ends, validated on hardware as
+// it is) keeps posting ahead.
+bool orders_receives_after_own_sends(const BnetTRing* r) {
+  return strcmp(r->send_next->transport(), "nvl") != 0 || strcmp(r->recv_prev->transport(), "nvl") != 0;
+}
+
 int fail(BnetTRing* r, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
 int fail(BnetTRing* r, const char* fmt, ...) {
   va_list ap;
@@ -173,12 +183,15 @@ BNET_API int bnet_tring_allreduce(BnetTRing* r, void* buf, size_t count, int dty
   r->last_bytes_sent = 0;
   const uint64_t t0 = now_ns();
   CollSpan span(r->rank, ++r->op_seq, total);
-  unsigned idle = 0;
+  IdleBackoff backoff;
+  const bool send_after_own_send = orders_receives_after_own_sends(r);
   while (done_r < M || done_s < M) {
     bool moved = false;
     // receives: posted in message order (the transport matches strictly FIFO per connection)
     while (posted_r < M && posted_r - done_r < (size_t)inflight) {
       const int g = (int)(posted_r / np);
+      // an all-gather receive lands where the reduce-scatter send of n-1 steps earlier read (see send_after_own_send)
+      if (send_after_own_send && g >= n - 1 && !sdone[posted_r - (size_t)(n - 1) * np]) break;
       size_t off, len;
       piece(recv_seg(g), posted_r % np, &off, &len);
       Request* q = nullptr;
@@ -227,10 +240,8 @@ BNET_API int bnet_tring_allreduce(BnetTRing* r, void* buf, size_t count, int dty
     if (!moved && timeout_ms > 0 && now_ns() - t0 > (uint64_t)timeout_ms * 1000000ull)
       return fail(r, "all-reduce timed out: %zu/%zu receives, %zu/%zu sends done", done_r, M, done_s, M);
     // poll hot while things move; when nothing has for a while, the transport's worker threads (or other ranks of an
-    // oversubscribed host) need the core more than this loop does
-    idle = moved ? 0 : idle + 1;
-    if (idle > 1024) usleep(30);
-    else if (idle > 32) sched_yield();
+    // oversubscribed host) need the core more than this loop does (coll/backoff.h)
+    backoff.step(moved);
   }
   span.ok = true;
   return 0;
@@ -362,7 +373,7 @@ BNET_API int bnet_tring_allreduce_compressed(BnetTRing* r, void* buf, size_t cou
   r->last_bytes_sent = 0;
   const uint64_t t0 = now_ns();
   CollSpan span(r->rank, ++r->op_seq, (uint64_t)count * 4);
-  unsigned idle = 0;
+  IdleBackoff backoff;
   auto submit = [&](uint32_t op, float sc, const void* src, void* dst, size_t src_bytes, LocalJob* j) -> int {
     if (src_bytes == 0) { j->slot = -1; return 0; }
     if (free_slots.empty()) return 1;                                   // try again later
@@ -375,11 +386,13 @@ BNET_API int bnet_tring_allreduce_compressed(BnetTRing* r, void* buf, size_t cou
     if (j.slot >= 0) free_slots.push_back(j.slot);
     j.slot = -1;
   };
+  const bool send_after_own_send = orders_receives_after_own_sends(r);
   while (done_s < M || ready_r < M || owner_done < np) {
     bool moved = false;
     // ---- receives: posted in message order into the wire mirror
     while (posted_r < M && posted_r - done_r < (size_t)inflight) {
       const int g = (int)(posted_r / np);
+      if (send_after_own_send && g >= n - 1 && sst[posted_r - (size_t)(n - 1) * np] != 4) break;   // (as in the plain ring)
       size_t e0, len;
       piece(recv_seg(g), posted_r % np, &e0, &len);
       Request* q = nullptr;
@@ -494,9 +507,7 @@ BNET_API int bnet_tring_allreduce_compressed(BnetTRing* r, void* buf, size_t cou
     if (!cuda::fake()) cuda::exec_kick(cuda_dev);                       // launch what the executor has collected
     if (!moved && timeout_ms > 0 && now_ns() - t0 > (uint64_t)timeout_ms * 1000000ull)
       return fail(r, "compressed all-reduce timed out: %zu/%zu receives ready, %zu/%zu sends done", ready_r, M, done_s, M);
-    idle = moved ? 0 : idle + 1;
-    if (idle > 1024) usleep(30);
-    else if (idle > 32) sched_yield();
+    backoff.step(moved);
   }
   span.ok = true;
   return 0;

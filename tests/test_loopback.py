@@ -562,6 +562,9 @@ def test_transport_mesh_twoshot_on_host_memory_over_any_transport(name, env, tra
     assert all(o["transport"] == transport for o in outs), [o["transport"] for o in outs]
 
 
+# (torch's gloo process group and its OpenMP tensor kernels are not instrumented: ThreadSanitizer reports races inside
+#  libtorch_cpu.so for this one; the same all-reduce without torch is test_transport_mesh_twoshot_on_host_memory_over_any_transport)
+@pytest.mark.skipif("tsan" in os.environ.get("LD_PRELOAD", ""), reason="libtorch (gloo, OpenMP) under ThreadSanitizer")
 @pytest.mark.parametrize("env,transport", [({"BNET_NVL": "0"}, "tcp-threads"), ({"BNET_NVL": "1"}, "nvl")])
 def test_transport_mesh_torch_api_on_host_tensors(env, transport):
     """TransportMesh (the torch-facing wrapper) on CPU tensors: torch.distributed / gloo only exchanges the handles, the
