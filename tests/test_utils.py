@@ -702,3 +702,85 @@ def test_plugin_environment_helper(monkeypatch):
     assert nccl_plugin_env(gdr=False)["BNET_GDR"] == "0"
     assert nccl_plugin_env(tuned=True)["NCCL_BUFFSIZE"] == str(32 << 20)
     assert "NCCL_TUNER_PLUGIN" not in nccl_plugin_env(plugin="bnetx")
+
+
+def test_bench_headline_survives_hung_or_failing_optional_parts(tmp_path):
+    """Once bench.py's timed region is over its number is printed whatever the optional measurements do: a watchdog (every rank
+    runs the same timer) kills a child arm that is still running, prints the contract's JSON line from what is there — e2e and
+    checksum included when they were finished — and ends the process with exit code 0; an exception that escapes main() after
+    the headline takes the same exit."""
+    script = tmp_path / "drive.py"
+    script.write_text(
+        "import argparse, importlib.util, os, subprocess, sys, time\n"
+        f"spec = importlib.util.spec_from_file_location('bench_wd', {os.path.join(ROOT, 'bench.py')!r})\n"
+        "mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)\n"
+        "args = argparse.Namespace(model='vgg16', steps=20, warmup=5, batch=32, image=224, comm='bnet', child_json=None,\n"
+        "                          resnet_deadline=300.0, resnet_timeout=90.0, arm_timeout=150.0, no_arms=False)\n"
+        "extra = {}\n"
+        "mod._HEADLINE.update({'extra': extra, 'args': args, 'world': 1, 'rank': 0, 'img_s': 7000.0, 'ms_step': 4.571,\n"
+        "                      'clocks': {'sm_mhz': 1965, 'sm_max_mhz': 1965, 'reasons': []}, 'nlaunch': 1234, 'wall_ms': 4.6,\n"
+        "                      'path': 'single', 'fused': True, 'graph_used': True, 'n_params': 138357544})\n"
+        "mod._HEADLINE['e2e'] = {'value': 6990.0, 'unit': 'img/s', 'h2d_bytes_per_step': 9633792 + 256, 'd2h_bytes_per_step': 4}\n"
+        "extra['allreduce_algo'] = 'single'\n"
+        "if sys.argv[1] == 'hang':\n"
+        "    os.environ['BNET_BENCH_HARD_DEADLINE'] = str(time.time() - mod._T0 + 1.5)\n"
+        "    mod.arm_watchdog()\n"
+        "    child = subprocess.Popen([sys.executable, '-c', 'import time; time.sleep(120)'])\n"
+        "    mod._CHILDREN.append(child)\n"
+        "    print(child.pid, file=sys.stderr, flush=True)\n"
+        "    child.wait()\n"
+        "    time.sleep(60)\n"
+        "    sys.exit(9)\n"
+        "else:\n"
+        "    def boom():\n"
+        "        raise RuntimeError('CUDA error: an illegal memory access was encountered')\n"
+        "    mod._main = boom\n"
+        "    sys.exit(mod.main())\n")
+    for how in ("hang", "raise"):
+        t0 = time.time()
+        r = subprocess.run([sys.executable, str(script), how], capture_output=True, text=True, timeout=60)
+        assert r.returncode == 0 and time.time() - t0 < 30, (how, r.returncode, r.stderr[-400:])
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        assert len(lines) == 1, r.stdout
+        out = json.loads(lines[0])
+        assert out["metric"] == "vgg16_train_img_per_sec" and out["value"] == 7000.0 and out["n_gpus"] == 1
+        assert out["steps"] == 20 and out["warmup"] == 5 and out["higher_is_better"] is True and out["scaling"] == "weak"
+        assert out["gpu_launches"] == 1234 and out["e2e"]["value"] == 6990.0 and out["clocks"]["sm_mhz"] == 1965
+        assert out["config"]["global_batch"] == 32 and out["extra"]["allreduce_algo"] == "single"
+        assert ("watchdog" if how == "hang" else "illegal memory access") in out["extra"]["cut_short"]
+        if how == "hang":           # the child arm that was still running is gone (its exact pid was killed)
+            pid = int(r.stderr.split()[0])
+            with pytest.raises(ProcessLookupError):
+                for _ in range(50):
+                    os.kill(pid, 0)
+                    time.sleep(0.1)
+
+
+def test_bench_failed_run_is_repeated_in_a_fresh_process_with_the_unproven_paths_off(tmp_path):
+    """A 1-GPU run that fails before its timed region is over is repeated by a fresh process (a faulting kernel poisons the CUDA
+    context) with the paths that have the least hardware mileage switched off — level by level, each level a superset of the one
+    before; a multi-rank job and the reference arm are never repeated."""
+    script = tmp_path / "drive.py"
+    script.write_text(
+        "import importlib.util, os, sys\n"
+        f"spec = importlib.util.spec_from_file_location('bench_retry', {os.path.join(ROOT, 'bench.py')!r})\n"
+        "mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)\n"
+        "def fake():\n"
+        "    lvl = os.environ.get('BNET_BENCH_SAFE_LEVEL', '0')\n"
+        "    print('attempt', lvl, os.environ.get('BNET_DIRECT_GRADS'), os.environ.get('BNET_TC_WGRAD'), os.environ.get('BNET_TC'), flush=True)\n"
+        "    if int(lvl) < int(sys.argv[1]):\n"
+        "        raise RuntimeError('boom at level ' + lvl)\n"
+        "    print('reason', os.environ.get('BNET_BENCH_SAFE_REASON'), flush=True)\n"
+        "    return 0\n"
+        "mod._main = fake\n"
+        "sys.exit(mod.main())\n")
+    env = {k: v for k, v in os.environ.items() if not k.startswith("BNET_") and k != "WORLD_SIZE"}
+    r = subprocess.run([sys.executable, str(script), "2"], capture_output=True, text=True, timeout=120, env=env)
+    assert r.returncode == 0, r.stderr[-400:]
+    assert [ln for ln in r.stdout.splitlines() if ln.startswith("attempt")] == [
+        "attempt 0 None None None", "attempt 1 0 0 None", "attempt 2 0 0 0"]
+    assert "reason RuntimeError: boom at level 1" in r.stdout
+    r = subprocess.run([sys.executable, str(script), "3"], capture_output=True, text=True, timeout=120, env=env)
+    assert r.returncode != 0 and r.stdout.count("attempt") == 3 and "boom at level 2" in r.stderr      # the ladder is finite
+    r = subprocess.run([sys.executable, str(script), "1"], capture_output=True, text=True, timeout=120, env=dict(env, WORLD_SIZE="2"))
+    assert r.returncode != 0 and r.stdout.count("attempt") == 1                                         # multi-rank: no repeat
