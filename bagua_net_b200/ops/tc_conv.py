@@ -217,11 +217,20 @@ def wgrad_trusted() -> bool:
             ladder = ({}, {"BNET_TC_WGRAD_BN": "128"}, {"BNET_TC_WGRAD_FIXUP": "0"}, {"BNET_TC_WGRAD_BN": "128", "BNET_TC_WGRAD_FIXUP": "0"})
             preset = any(k in os.environ for k in ("BNET_TC_WGRAD_BN", "BNET_TC_WGRAD_FIXUP"))
             _wgrad_trusted = False
+            # the whole ladder is bounded in time (BNET_TC_WGRAD_BUDGET_S, default 240 s: every rung is a fresh process that
+            # imports torch on a possibly cold machine); a rung that cannot start within what is left is not tried
+            import time
+
+            budget = float(os.environ.get("BNET_TC_WGRAD_BUDGET_S", "240") or 240)
+            t_start = time.monotonic()
             for cfg in (ladder[:1] if preset else ladder):
+                left = budget - (time.monotonic() - t_start)
+                if left < 20.0:
+                    break
                 os.environ.update(cfg)
                 tag = ("tc_wgrad" + ("_bn128" if os.environ.get("BNET_TC_WGRAD_BN") == "128" else "")
                        + ("_nofix" if os.environ.get("BNET_TC_WGRAD_FIXUP") == "0" else ""))
-                if tc_linear._isolated_self_check(check=check, tag=tag + "_self_check" + sfx):
+                if tc_linear._isolated_self_check(timeout=min(180.0, left), check=check, tag=tag + "_self_check" + sfx):
                     _wgrad_trusted = True
                     break
                 for k in cfg:

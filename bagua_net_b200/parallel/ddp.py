@@ -48,6 +48,76 @@ def plan_buckets(numels, element_size: int, world: int, bucket_mb: float):
     return plan, offset
 
 
+def direct_grads_self_check(device=None, group=None, steps: int = 3, make_model=None, make_comm=None, make_batch=None,
+                            use_graph: bool = True, fused: bool = True, verbose: bool = False):
+    """Do adopted gradients (``BNET_DIRECT_GRADS=1``: producers write into the flat buffer, ``p.grad`` stays ``None``) train like
+    accumulated ones (``BNET_DIRECT_GRADS=0``: autograd adds into views of the flat buffer) on THIS machine?
+
+    Two engines are built from the same seed on a small full-width VGG16 (64-multiple channels, so the tcgen05 producers that
+    write in place take part; 32 x 32 images), both run `steps` steps — captured in a CUDA graph like the benchmark's — and the
+    fp32 master-weight UPDATES are compared (relative L2 error; an update is what a misplaced or missing gradient changes).
+    `group`: a single-rank process group when the job has more ranks (nothing here may wait for a peer).
+    Returns (verdict, detail).  Any exception is a failed check, not an error: the caller falls back to accumulation."""
+    import gc
+    import os
+
+    saved = os.environ.get("BNET_DIRECT_GRADS")
+    detail = {}
+    try:
+        updates, losses = {}, {}
+        for mode in ("0", "1"):
+            os.environ["BNET_DIRECT_GRADS"] = mode
+            torch.manual_seed(4321)
+            if make_model is not None:
+                model = make_model()
+            else:
+                from ..models import build_model
+
+                model = build_model("vgg16", fc_dim=256, image_size=32, num_classes=16, dropout=0.0, **({"fused": True} if fused else {}))
+                model = model.to(device).to(torch.bfloat16).to(memory_format=torch.channels_last)
+            model.train()
+            if make_batch is not None:
+                x, y = make_batch()
+            else:
+                x = torch.randn(4, 3, 32, 32, device=device, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+                y = torch.randint(0, 16, (4,), device=device)
+            eng = BnetDDP(model, lr=0.05, momentum=0.9, weight_decay=1e-4, bucket_mb=8.0, group=group,
+                          comm=make_comm() if make_comm is not None else None, extra_heap_bytes=8 << 20)
+            assert eng._direct_grads == (mode == "1")
+            before = torch.cat([b.master.reshape(-1).clone() for b in eng.buckets])
+            if use_graph:
+                eng.enable_cuda_graph(True)
+            loss = None
+            for _ in range(steps):
+                loss = eng.train_step(x, y)
+            if x.is_cuda:
+                torch.cuda.synchronize()
+            after = torch.cat([b.master.reshape(-1) for b in eng.buckets])
+            updates[mode] = (after - before).double()
+            losses[mode] = float(loss)
+            detail[f"grad_copies_{'adopt' if mode == '1' else 'accumulate'}"] = int(eng.grad_copies)
+            for h in eng._hooks:
+                h.remove()
+            del eng, model, before, after
+            gc.collect()
+        ref, got = updates["0"], updates["1"]
+        finite = bool(torch.isfinite(got).all()) and bool(torch.isfinite(ref).all())
+        err = float((got - ref).norm() / ref.norm().clamp_min(1e-30)) if finite else float("inf")
+        detail.update({"rel_l2_error_of_updates": err, "loss_accumulate": losses["0"], "loss_adopt": losses["1"]})
+        ok = finite and float(ref.norm()) > 0 and err < 0.05 and abs(losses["0"] - losses["1"]) <= 0.05 * max(1.0, abs(losses["0"]))
+    except Exception as ex:   # noqa: BLE001 - a failed check, whatever the reason
+        ok = False
+        detail["error"] = f"{type(ex).__name__}: {str(ex)[:200]}"
+    finally:
+        if saved is None:
+            os.environ.pop("BNET_DIRECT_GRADS", None)
+        else:
+            os.environ["BNET_DIRECT_GRADS"] = saved
+    if verbose:
+        print(f"direct_grads_self_check: {ok} {detail}")
+    return ok, detail
+
+
 class _Bucket:
     __slots__ = ("params", "start", "numel", "ready", "grad", "param", "master", "mom")
 

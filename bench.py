@@ -536,6 +536,25 @@ def _main() -> int:
         except Exception as ex:   # noqa: BLE001 - the comparison is optional
             note(f"fused-vs-eager timing failed: {ex!r}")
         torch.cuda.empty_cache()
+    grads_check = None
+    if (args.comm == "bnet" and os.environ.get("BNET_DIRECT_GRADS", "1") != "0" and os.environ.get("BNET_BENCH_GRADS_CHECK", "1") != "0"):
+        # Gradients written straight into the engine's flat buffer ("adopted", ops/grad_target.py) must train like accumulated
+        # ones on THIS machine before the benchmark relies on them: two small engines, same seed, fp32 updates compared — on a
+        # single-rank group (nothing in the check waits for a peer); every rank takes the same decision.  A failed check is not
+        # an error: the run then accumulates (BNET_DIRECT_GRADS=0, inherited by the child arms) and says so in the JSON line.
+        from bagua_net_b200.parallel.ddp import direct_grads_self_check
+
+        solo = [dist.new_group([r]) for r in range(world)][rank] if world > 1 else None
+        ok_, grads_check = direct_grads_self_check(dev, group=solo, fused=fused)
+        flag = torch.tensor([1 if ok_ else 0], device=dev, dtype=torch.int32)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        grads_check = dict(grads_check, passed=bool(ok_), used=bool(int(flag.item())))
+        note(f"adopted-gradient self-check: {grads_check}")
+        if int(flag.item()) == 0:
+            os.environ["BNET_DIRECT_GRADS"] = "0"
+        torch.cuda.empty_cache()
+        torch.manual_seed(1234)
     model = build_model(args.model, **({"fused": True} if fused else {}))
     model = model.to(dev).to(torch.bfloat16).to(memory_format=torch.channels_last)
     model.train()
@@ -1009,6 +1028,8 @@ def _main() -> int:
                 npar = sum(1 for p_ in model.parameters() if p_.requires_grad)
                 out["config"]["gradient_path"] = {"mode": "adopt" if getattr(engine, "_direct_grads", False) else "accumulate",
                                                   "parameters": npar, "copies_in_eager_and_captured_passes": int(engine.grad_copies)}
+                if grads_check is not None:
+                    out["config"]["gradient_path"]["self_check"] = {k: (round(v, 6) if isinstance(v, float) else v) for k, v in grads_check.items()}
             except Exception:   # noqa: BLE001 - reporting only
                 pass
         try:

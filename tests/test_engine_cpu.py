@@ -294,3 +294,41 @@ def test_engine_rejects_mixed_dtypes_and_empty_models(cpu_engine):
     with pytest.raises(ValueError):
         BnetDDP(m, comm=FakeComm())
     assert ddp_mod.BnetDDP is BnetDDP
+
+
+def test_direct_grads_self_check_accepts_the_working_path_and_rejects_a_broken_one(cpu_engine):
+    """bench.py asks `direct_grads_self_check` before it trusts adopted gradients with the benchmark: the same model trained
+    with accumulated and with adopted gradients must receive the same fp32 updates.  Here on the CPU test bed: the real engine
+    passes; an engine whose hook loses the gradients that arrive in tensors of their own fails; so does one that raises."""
+    from bagua_net_b200.parallel.ddp import direct_grads_self_check
+
+    def batch():
+        torch.manual_seed(11)
+        return torch.randn(4, 3, 8, 8).contiguous(memory_format=torch.channels_last), torch.randint(0, 10, (4,))
+
+    kw = dict(make_model=_model, make_comm=FakeComm, make_batch=batch, use_graph=False)
+    ok, detail = direct_grads_self_check(**kw)
+    assert ok and detail["rel_l2_error_of_updates"] < 1e-6 and detail["grad_copies_accumulate"] == 0 and detail["grad_copies_adopt"] > 0
+    import os
+
+    assert "BNET_DIRECT_GRADS" not in os.environ
+
+    real = BnetDDP._on_grad
+
+    def lossy(self, p):
+        if self._direct_grads and p.dim() == 4:
+            p.grad = None                                  # the filter gradients never reach the flat buffer
+        return real(self, p)
+
+    cpu_engine.setattr(BnetDDP, "_on_grad", lossy)
+    ok, detail = direct_grads_self_check(**kw)
+    assert not ok and detail["rel_l2_error_of_updates"] > 0.05
+
+    def broken(self, p):
+        if self._direct_grads:
+            raise RuntimeError("hook failed")
+        return real(self, p)
+
+    cpu_engine.setattr(BnetDDP, "_on_grad", broken)
+    ok, detail = direct_grads_self_check(**kw)
+    assert not ok and "hook failed" in detail["error"]
