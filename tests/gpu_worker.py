@@ -1075,6 +1075,33 @@ def job_tc_conv_wgrad():
     teardown()
 
 
+def job_grads_check():
+    """bench.py's question before it relies on adopted gradients (BnetDDP writes them straight into the flat buffer): do they
+    train like accumulated ones on this GPU?  Eager and captured; then the verdict of a deliberately broken hook."""
+    from bagua_net_b200.parallel import ddp
+
+    setup()
+    os.environ.setdefault("BNET_TC_WGRAD", "0")      # (the filter-gradient kernel has a test of its own; no child process here)
+    for graph in (False, True):
+        ok, detail = ddp.direct_grads_self_check(torch.device("cuda", LOCAL), use_graph=graph)
+        print(f"adopted vs accumulated gradients (cuda graph: {graph}): {ok} {detail}", flush=True)
+        assert ok, detail
+        assert detail["grad_copies_accumulate"] == 0
+    real = ddp.BnetDDP._on_grad
+
+    def lossy(self, p):
+        if self._direct_grads and p.dim() == 4:
+            p.grad = None
+        return real(self, p)
+
+    ddp.BnetDDP._on_grad = lossy
+    ok, detail = ddp.direct_grads_self_check(torch.device("cuda", LOCAL), use_graph=False)
+    ddp.BnetDDP._on_grad = real
+    assert not ok, detail
+    print(f"... and an engine that loses its filter gradients is rejected: {detail}", flush=True)
+    teardown()
+
+
 JOBS = {k[4:]: v for k, v in globals().items() if k.startswith("job_")}
 
 if __name__ == "__main__":

@@ -291,3 +291,8 @@ def test_executor_fp8_decompression_ops():
 def test_tcgen05_conv3x3_filter_gradient_matches_cudnn():
     """tcgen05 weight gradient (both operands 64-pixel 4-D TMA boxes, MN-major; split over the pixels with the fix-up)."""
     _run_worker("tc_conv_wgrad", 1, timeout=300)
+
+
+def test_adopted_gradients_self_check():
+    """parallel/ddp.py::direct_grads_self_check — what bench.py asks before the flagship run relies on adopted gradients."""
+    _run_worker("grads_check", 1, timeout=300)
