@@ -79,8 +79,8 @@ def direct_grads_self_check(device=None, group=None, steps: int = 3, make_model=
             if make_batch is not None:
                 x, y = make_batch()
             else:
-                x = torch.randn(4, 3, 32, 32, device=device, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
-                y = torch.randint(0, 16, (4,), device=device)
+                x = torch.randn(8, 3, 32, 32, device=device, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+                y = torch.randint(0, 16, (8,), device=device)
             eng = BnetDDP(model, lr=0.05, momentum=0.9, weight_decay=1e-4, bucket_mb=8.0, group=group,
                           comm=make_comm() if make_comm is not None else None, extra_heap_bytes=8 << 20)
             assert eng._direct_grads == (mode == "1")
