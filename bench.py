@@ -57,7 +57,7 @@ def note(msg: str) -> None:
 # not finished — and ends the process with exit code 0; every rank runs the same timer, so the job ends together.
 _HEADLINE: dict = {}
 _CHILDREN: list = []          # Popen objects of child arms that are still running (killed by the watchdog, exact pids)
-_PRINT_LOCK = threading.Lock()
+_PRINT_LOCK = threading.RLock()
 
 
 def headline_line(reason: str | None = None) -> str:
@@ -86,6 +86,13 @@ def headline_line(reason: str | None = None) -> str:
 
 
 def _watchdog_fire(reason: str) -> None:
+    try:
+        _watchdog_fire_inner(reason)
+    finally:
+        os._exit(0)
+
+
+def _watchdog_fire_inner(reason: str) -> None:
     for proc in list(_CHILDREN):
         try:
             proc.kill()
@@ -94,7 +101,11 @@ def _watchdog_fire(reason: str) -> None:
     with _PRINT_LOCK:
         if _HEADLINE.get("rank") == 0 and not _HEADLINE.get("printed"):
             _HEADLINE["printed"] = True
-            line = headline_line(reason)
+            try:
+                line = headline_line(reason)
+            except Exception:   # noqa: BLE001 - e.g. the main thread was adding to `extra` at this very moment
+                _HEADLINE["extra"] = {}
+                line = headline_line(reason)
             a = _HEADLINE["args"]
             if a.child_json:
                 try:
@@ -112,7 +123,8 @@ def _watchdog_fire(reason: str) -> None:
 
 def arm_watchdog() -> None:
     """Every optional part of the run is bounded (child timeouts, nothing optional starts after --resnet-deadline), so a
-    complete run is over well before this fires.  BNET_BENCH_HARD_DEADLINE (seconds since start, 0 = off)."""
+    complete run is over well before this fires.  BNET_BENCH_HARD_DEADLINE: seconds since start (unset / 0: derived from the
+    arm timeouts, never less than four minutes after the headline)."""
     limit = float(os.environ.get("BNET_BENCH_HARD_DEADLINE", "0") or 0)
     if limit <= 0:
         a = _HEADLINE["args"]
