@@ -121,6 +121,11 @@ class Pool {
 // Chunks at least this large are handed to another loop of the pool for the duration of the chunk (parallel
 // copies; costs two epoll_ctl calls and two cross-thread wake-ups, ~25 us); smaller ones stay on the home loop.
 constexpr size_t kParallelChunk = 512 * 1024;
+// from how many large chunks of one message on are they lent to other loops of the pool (BNET_ASYNC_LEND_MIN)
+inline int lend_min_chunks() {
+  static const int v = [] { long long n = env_int("ASYNC_LEND_MIN", 3); return n < 1 ? 1 : (int)n; }();
+  return v;
+}
 
 class AsyncComm : public Comm {
  public:
@@ -351,7 +356,7 @@ class AsyncComm : public Comm {
         // alternates between the sockets is as fast and needs no cross-thread wake-ups)
         int big = 0;
         for (size_t j = 0; j < ns; j++) big += ch_[j].total >= kParallelChunk;
-        const bool lend = big >= 3;
+        const bool lend = big >= lend_min_chunks();
         for (size_t j = 0; j < ns; j++) {
           Ch& c = ch_[j];
           if (!c.total) continue;
