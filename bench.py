@@ -320,6 +320,9 @@ def run_child_arm(comm_name: str, args, rank: int, world: int, port_offset: int,
         env.pop("BNET_BENCH_FUSED_VERDICT", None)   # another model family: the child checks its own layer kernels
         env.pop("BNET_TC_WGRAD_CHECK_SHAPES", None)  # ... and names its own layer shapes to the filter-gradient self-check
     env.pop("BNET_BENCH_REEXEC", None)
+    # a child that has its headline but not yet its side measurements when the parent's patience ends prints what it has
+    # (its own watchdog, a few seconds before this process would kill it)
+    env["BNET_BENCH_HARD_DEADLINE"] = str(max(timeout - 8.0, 5.0))
     env.update(extra_env or {})
     log_dir = os.environ.get("BNET_BENCH_LOG_DIR") or tempfile.gettempdir()
     os.makedirs(log_dir, exist_ok=True)

@@ -58,6 +58,14 @@ def main() -> int:
     def pattern(n, r, salt):
         return ((torch.arange(n, device=dev) * 5 + r + salt) % 9 - 4).float()
 
+    def checkpoint(stage):
+        # what has been measured so far survives a later stage that hangs or faults (the parent reads the file whatever the
+        # child's end was); `exact` is rank 0's own view until the final all-reduce over the ranks
+        if rank == 0 and args.json:
+            with open(args.json + ".tmp", "w") as f:
+                f.write(json.dumps(dict(out, partial=f"stopped after: {stage}")))
+            os.replace(args.json + ".tmp", args.json)
+
     bus = 2 * (world - 1) / world
     out = {"world": world, "ring_fp32": {}, "two_shot_fp32_in_place": {}, "exact": True}
     t_start = time.time()
@@ -77,6 +85,7 @@ def main() -> int:
         out["ring_fp32"][str(nbytes)] = {"us": round(t * 1e6, 1), "busbw_gbs": round(nbytes * bus / t / 1e9, 1)}
     ring.close()
     del g
+    checkpoint("ring")
     mesh = TransportMesh()
     h = mesh.buffer(nmax, torch.float32)
     for nbytes in sizes:
@@ -90,6 +99,7 @@ def main() -> int:
         dist.barrier()
         t = timed(lambda: mesh.all_reduce(h[:n], h[:n], algo="two-shot"), args.iters)
         out["two_shot_fp32_in_place"][str(nbytes)] = {"us": round(t * 1e6, 1), "busbw_gbs": round(nbytes * bus / t / 1e9, 1)}
+    checkpoint("ring, two-shot mesh")
     # latency shape: one network step, 256 Ki bf16 gradients accumulated in fp32
     x, y = mesh.buffers(1 << 18, torch.bfloat16, torch.float32)
     x.copy_(pattern(1 << 18, rank, 3).to(torch.bfloat16))
