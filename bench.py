@@ -1070,8 +1070,8 @@ def _main() -> int:
             if key == "resnet50_bnet" and cfg.get("tc_conv_autotune"):       # (the other arms run the headline's layer shapes)
                 keep["tc_conv_autotune"] = cfg["tc_conv_autotune"]
             ex = res.get("extra") or {}
-            keep.update({k: ex[k] for k in ("allreduce_busbw_gbs_bf16", "allreduce_time_us", "allreduce_exact", "allreduce_error")
-                         if k in ex})
+            keep.update({k: ex[k] for k in ("allreduce_busbw_gbs_bf16", "allreduce_time_us", "allreduce_exact", "allreduce_error",
+                                            "cut_short", "post_headline_error") if k in ex})
             if res.get("param_checksum"):
                 keep["param_checksum"] = res["param_checksum"]
             extra[key] = keep
