@@ -1054,7 +1054,7 @@ def _main() -> int:
             if tc_conv.TIMINGS or tc_conv._choice:
                 out["config"]["tc_conv_autotune"] = {
                     f"{k[0]} n{k[1]} {k[2]}x{k[3]} {k[4]}->{k[5]}": dict(tc_conv.TIMINGS.get(k, {}), choice=v)
-                    for k, v in sorted(tc_conv._choice.items(), key=lambda kv: str(kv[0]))}
+                    for k, v in sorted(tc_conv._choice.items(), key=lambda kv: str(kv[0])) if k[1] == args.batch}   # (not the self-check's shapes)
         except Exception:   # noqa: BLE001 - reporting only
             pass
         if e2e:
